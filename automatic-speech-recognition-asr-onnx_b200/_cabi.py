@@ -1,0 +1,72 @@
+"""ctypes binding of include/b200asr.h.  There is no fallback: if the shared
+library is missing the import of the engine fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("B200ASR_LIB", PKG / "libb200asr.so"))
+
+OK, E_INVALID, E_CUDA, E_MISSING, E_NOGPU = 0, -1, -2, -3, -4
+PRECISION_F32, PRECISION_BF16 = 0, 1
+PCM_I16, PCM_F32 = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_mels", "d_model", "n_heads", "ffn", "enc_layers", "dec_layers", "vocab", "max_source", "max_target",
+        "n_fft", "hop", "max_batch", "max_samples", "precision", "device", "use_tensor_cores")]
+
+
+# every symbol include/b200asr.h declares: (restype, argtypes)
+_P = C.c_void_p
+_I32P = C.POINTER(C.c_int32)
+_F32P = C.POINTER(C.c_float)
+SYMBOLS = {
+    "b200asr_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
+    "b200asr_destroy": (None, [_P]),
+    "b200asr_last_error": (C.c_char_p, [_P]),
+    "b200asr_set_tensor": (C.c_int, [_P, C.c_char_p, _F32P, C.c_int64]),
+    "b200asr_finalize_weights": (C.c_int, [_P]),
+    "b200asr_encode": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32]),
+    "b200asr_upload_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32]),
+    "b200asr_encode_resident": (C.c_int, [_P]),
+    "b200asr_set_decode_options": (C.c_int, [_P, _I32P, C.c_int32, C.c_int32, C.c_float, C.c_int32]),
+    "b200asr_prefill": (C.c_int, [_P, _I32P, C.c_int32, _F32P, _I32P]),
+    "b200asr_decode_step": (C.c_int, [_P, _I32P, _F32P, _I32P]),
+    "b200asr_decode": (C.c_int, [_P, C.c_int32, _I32P, C.c_int32, _I32P]),
+    "b200asr_no_speech_prob": (C.c_int, [_P, C.c_int32, _F32P]),
+    "b200asr_transcribe": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _I32P, C.c_int32, C.c_int32, _I32P,
+                                     C.c_int32, _I32P]),
+    "b200asr_transcribe_resident": (C.c_int, [_P, _I32P, C.c_int32, C.c_int32, _I32P, C.c_int32, _I32P]),
+    "b200asr_get_stage": (C.c_int, [_P, C.c_char_p, _F32P, C.c_int64, C.POINTER(C.c_int64)]),
+    "b200asr_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "b200asr_stream": (_P, [_P]),
+    "b200asr_synchronize": (C.c_int, [_P]),
+    "b200asr_kernel_launches": (C.c_int64, [_P]),
+    "b200asr_num_sms": (C.c_int, [_P]),
+    "b200asr_test_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F32P, _F32P, _F32P, _F32P,
+                                    C.c_int32, _F32P, C.c_char_p, C.c_int32]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libb200asr.so and type every entry point.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+            "(nvcc, sm_100a).  b200asr has no CPU or PyTorch fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)           # AttributeError = header/library drift
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,137 @@
+// Shared declarations for the b200asr CUDA engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <string>
+
+namespace b200asr {
+
+enum DType : int { kF32 = 0, kBF16 = 1 };
+enum Act : int { kActNone = 0, kActGelu = 1 };
+
+typedef __nv_bfloat16 bf16;
+
+__host__ __device__ inline size_t dtype_size(int dt) { return dt == kF32 ? 4 : 2; }
+
+// C[z][m][n] = act(sum_k A[z][m][k] * B[z][n][k] + bias[n]) + residual[z][m][n]
+// Batch index z is split as z = zo * batch_inner + zi so one launch can walk
+// (utterance, head) with two independent strides per operand.
+struct GemmArgs {
+  const void* A = nullptr; int64_t lda = 0, sAo = 0, sAi = 0; int a_dtype = kF32;
+  const void* B = nullptr; int64_t ldb = 0, sBo = 0, sBi = 0; int b_dtype = kF32;
+  int transB = 0;                     // 0: B is [N][K] (K contiguous); 1: B is [K][N]
+  void* C = nullptr; int64_t ldc = 0, sCo = 0, sCi = 0; int c_dtype = kF32;
+  const float* bias = nullptr;
+  const float* residual = nullptr; int64_t ldr = 0, sRo = 0, sRi = 0;
+  int act = kActNone;
+  int M = 0, N = 0, K = 0;
+  int batch = 1, batch_inner = 1;
+};
+
+// ---- device helpers ---------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// exact (erf) GELU: torch.nn.functional.gelu default, Whisper/Export_Whisper.py:428,437,662
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// order-preserving float <-> int key (for atomicMax on floats of either sign)
+__device__ __forceinline__ int float_to_key(float f) {
+  int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_to_float(int k) {
+  return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+
+// ---- launch wrappers (one per .cu) -------------------------------------------
+// frontend.cu
+cudaError_t launch_logmel(const void* pcm, int pcm_is_f32, int batch, int n_samples, int64_t pcm_stride,
+                          const float* basis_t /*[n_fft][2F]*/, const float* fbank /*[n_mels][F]*/,
+                          const int* fb_start, const int* fb_len, int n_fft, int hop, int n_mels,
+                          float* mel_raw /*[B][T][n_mels]*/, int* max_key /*[B]*/, cudaStream_t st);
+cudaError_t launch_mel_finalize(const float* mel_raw, const int* max_key, int batch, int T, int n_mels,
+                                void* mel_pad /*[B][T+2][n_mels]*/, int out_dtype, cudaStream_t st);
+cudaError_t launch_fill_i32(int* p, int v, int n, cudaStream_t st);
+
+// gemm_simt.cu
+cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
+
+// gemm_tc.cu  (tcgen05 + TMA; bf16 operands, fp32 accumulate)
+bool gemm_tc_supported(const GemmArgs& g);
+cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t st, std::string* err);
+
+// layers.cu
+cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, void* out,
+                             int out_dtype, int64_t ldo, int rows, int d, float eps, cudaStream_t st);
+cudaError_t launch_softmax_rows(const float* s, void* p, int p_dtype, int64_t rows, int cols, cudaStream_t st);
+
+// decoder.cu
+struct DecState {           // lives in device memory, one per engine
+  int kv_len;               // tokens already in the self-KV cache
+  int step;                 // decode launches since prefill (0 = prefill head)
+  int all_done;             // 1 when every utterance has latched a stop token / hit the limit
+  int pad;
+};
+struct DecLinearArgs {
+  const float* x; int64_t ldx;          // fp32 rows [rows][K]
+  int ln_mode;                          // 0 none, 1 affine-less LN, 2 affine LN (gamma/beta)
+  const float* gamma; const float* beta; float eps;
+  const void* W; int w_dtype;           // [N][K]
+  const float* bias;                    // [N] or null
+  int act;
+  const float* residual; int64_t ldr;   // fp32 [rows][N] or null (may alias out)
+  float* out; int64_t ldo;              // fp32 [rows][N]        (mode 0)
+  // mode 1: fused-QKV scatter: cols [0,d) -> out (q, ld=ldo); [d,2d) -> K cache; [2d,3d) -> V cache
+  int mode; void* kcache; void* vcache; int kv_dtype;
+  int n_new, n_heads, head_dim, max_target, batch; const DecState* state;
+  int rows, N, K;
+};
+cudaError_t launch_dec_linear(const DecLinearArgs& a, cudaStream_t st);
+cudaError_t launch_dec_embed(const int* tokens /*[B][n_new]*/, const void* embed, int w_dtype, const void* pos,
+                             int batch, int n_new, int d, const DecState* state, float* x, cudaStream_t st);
+cudaError_t launch_dec_self_attn(const float* q /*[rows][d]*/, const void* kcache, const void* vcache, int kv_dtype,
+                                 int batch, int n_new, int n_heads, int head_dim, int max_target,
+                                 const DecState* state, float* ctx /*[rows][d]*/, cudaStream_t st);
+cudaError_t launch_dec_cross_attn(const float* q, const void* cross_kv /*[B][T][2*L*d]*/, int kv_dtype, int layer,
+                                  int n_layers, int batch, int n_new, int n_heads, int head_dim, int T,
+                                  float* ctx, cudaStream_t st);
+struct SelectArgs {
+  float* logits; int vocab; int batch;
+  const float* begin_bias;   // [vocab] added on the fly for the prefill head only (nullable)
+  int* cur_token;            // [B] token fed to the next step
+  int* tokens; int tokens_ld;// [B][tokens_ld] accepted (non-stop) tokens
+  int* n_gen;                // [B]
+  int* finished;             // [B]
+  int* save_id; int save_ld; // [B][save_ld] every selected id (GREEDY_SEARCH history)
+  int* n_save;               // [B]
+  int* selected_hist; int sel_ld;   // [B][sel_ld] selected id per launch (prefill = 0)
+  const int* stop_ids; int n_stop;
+  int limit;
+  float penalty_value; int penalty_range;   // penalty_value == 1 -> plain argmax
+  DecState* state; int n_new;               // state->kv_len += n_new, step += 1
+};
+cudaError_t launch_select_token(const SelectArgs& a, cudaStream_t st);
+cudaError_t launch_softmax_pick(const float* logits, const float* add_bias, int vocab, int batch, int index,
+                                float* out, cudaStream_t st);
+
+}  // namespace b200asr

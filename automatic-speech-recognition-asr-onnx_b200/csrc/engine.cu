@@ -1,0 +1,839 @@
+// Engine object + C ABI (include/b200asr.h).  Host-side orchestration only: every
+// arithmetic step is one of the kernels in frontend.cu / gemm_tc.cu / gemm_simt.cu /
+// layers.cu / decoder.cu, enqueued on the engine's single stream.
+#include "common.cuh"
+#include "../../include/b200asr.h"
+
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace b200asr;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevTensor {
+  void* ptr = nullptr;
+  int64_t numel = 0;
+  int dtype = kF32;
+};
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace
+
+struct b200asr_engine {
+  b200asr_config cfg{};
+  cudaStream_t st = nullptr;
+  std::string err;
+  int num_sms = 148;
+  int64_t launches = 0;
+  bool finalized = false;
+  bool keep_stages = false;
+  int act_dtype = kF32;      // activations fed to GEMMs, weights, KV caches
+  size_t es = 4;
+
+  std::map<std::string, DevTensor> w;
+  float* stage_buf = nullptr; int64_t stage_cap = 0;     // fp32 staging for uploads / stage dumps
+  float* basis_t = nullptr; int* fb_start = nullptr; int* fb_len = nullptr;
+
+  // encoder state
+  int B = 0, n_samples = 0, T_mel = 0, T_enc = 0, pcm_dtype = B200ASR_PCM_I16;
+  void* pcm = nullptr; void* pcm_pinned = nullptr;
+  float* mel_raw = nullptr; int* max_key = nullptr;
+  void* mel_pad = nullptr; void* h1_pad = nullptr;
+  float* hidden = nullptr; float* stem = nullptr;
+  void* xhat = nullptr; void* qkv = nullptr; void* ctx = nullptr; void* ffn = nullptr;
+  float* S = nullptr; void* P = nullptr;
+  void* cross_kv = nullptr;
+  // decoder state
+  void* kcache = nullptr; void* vcache = nullptr;
+  float *dx = nullptr, *dq = nullptr, *dctx = nullptr, *dffn = nullptr, *logits = nullptr, *prob = nullptr;
+  int *d_prompt = nullptr, *cur_token = nullptr, *tokens = nullptr, *n_gen = nullptr, *finished = nullptr;
+  int *save_id = nullptr, *n_save = nullptr, *selected_hist = nullptr, *d_stop = nullptr;
+  DecState* dstate = nullptr;
+  int* h_pinned = nullptr;          // pinned scratch for small D2H results
+  size_t h_pinned_bytes = 0;
+  std::vector<int> stop_ids; int limit = 0; int limit_cfg = 0; float repeat_penalty = 1.0f; int penalty_range = 20;
+  int n_prompt = 0; bool prefilled = false; bool encoded = false;
+  cudaGraphExec_t step_graph = nullptr; int64_t step_graph_nodes = 0;
+  std::string graph_key;
+
+  int fail(int code, const std::string& m) { err = m; return code; }
+  int cuda_fail(cudaError_t e, const char* what) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return B200ASR_E_CUDA;
+  }
+};
+
+#define CK(expr)                                                           \
+  do {                                                                     \
+    cudaError_t _e = (expr);                                               \
+    if (_e != cudaSuccess) return e->cuda_fail(_e, #expr);                 \
+  } while (0)
+#define KL(expr)                                                           \
+  do {                                                                     \
+    cudaError_t _e = (expr);                                               \
+    e->launches++;                                                         \
+    if (_e != cudaSuccess) return e->cuda_fail(_e, #expr);                 \
+  } while (0)
+#define RET(expr)                                                          \
+  do {                                                                     \
+    int _r = (expr);                                                       \
+    if (_r != B200ASR_OK) return _r;                                       \
+  } while (0)
+
+namespace {
+
+bool is_weight_matrix(const std::string& n) {
+  return (n.size() > 2 && n.compare(n.size() - 2, 2, ".w") == 0) || n == "dec.embed";
+}
+
+int ensure_stage(b200asr_engine* e, int64_t numel) {
+  if (numel <= e->stage_cap) return B200ASR_OK;
+  if (e->stage_buf) cudaFree(e->stage_buf);
+  e->stage_buf = nullptr; e->stage_cap = 0;
+  CK(cudaMalloc(&e->stage_buf, (size_t)numel * sizeof(float)));
+  e->stage_cap = numel;
+  return B200ASR_OK;
+}
+
+template <typename T>
+int dmalloc(b200asr_engine* e, T** p, size_t bytes) {
+  CK(cudaMalloc(reinterpret_cast<void**>(p), bytes ? bytes : 16));
+  CK(cudaMemsetAsync(*p, 0, bytes ? bytes : 16, e->st));
+  return B200ASR_OK;
+}
+
+const DevTensor* find(b200asr_engine* e, const std::string& n) {
+  auto it = e->w.find(n);
+  return it == e->w.end() ? nullptr : &it->second;
+}
+
+int need(b200asr_engine* e, const std::string& n, int64_t numel) {
+  const DevTensor* t = find(e, n);
+  if (!t) return e->fail(B200ASR_E_MISSING, "missing weight tensor '" + n + "'");
+  if (t->numel != numel)
+    return e->fail(B200ASR_E_INVALID, "tensor '" + n + "' has " + std::to_string(t->numel) + " elements, expected " +
+                                          std::to_string(numel));
+  return B200ASR_OK;
+}
+
+const void* W(b200asr_engine* e, const std::string& n) { return e->w[n].ptr; }
+const float* WF(b200asr_engine* e, const std::string& n) { return reinterpret_cast<const float*>(e->w[n].ptr); }
+
+// one Linear on the encoder side: tcgen05 when possible, CUDA cores otherwise
+int gemm(b200asr_engine* e, const GemmArgs& g) {
+  if (e->act_dtype == kBF16 && e->cfg.use_tensor_cores && gemm_tc_supported(g)) {
+    std::string msg;
+    cudaError_t r = launch_gemm_tc(g, e->num_sms, e->st, &msg);
+    e->launches++;
+    if (r != cudaSuccess) return e->fail(B200ASR_E_CUDA, "gemm_tc: " + (msg.empty() ? std::string(cudaGetErrorString(r)) : msg));
+    return B200ASR_OK;
+  }
+  KL(launch_gemm_simt(g, e->st));
+  return B200ASR_OK;
+}
+
+GemmArgs linear_args(b200asr_engine* e, const void* A, int64_t lda, const std::string& wname, const std::string& bname,
+                     void* C, int64_t ldc, int c_dtype, int M, int N, int K) {
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.a_dtype = e->act_dtype;
+  g.B = W(e, wname); g.ldb = K; g.b_dtype = e->act_dtype;
+  g.C = C; g.ldc = ldc; g.c_dtype = c_dtype;
+  g.bias = bname.empty() ? nullptr : WF(e, bname);
+  g.M = M; g.N = N; g.K = K;
+  return g;
+}
+
+int run_encoder(b200asr_engine* e) {
+  const b200asr_config& c = e->cfg;
+  const int B = e->B, d = c.d_model, H = c.n_heads, Tm = e->T_mel, T = e->T_enc, L = c.dec_layers;
+  const int M = B * T;
+  const int ad = e->act_dtype;
+  const size_t es = e->es;
+  // ---- front end ----
+  KL(launch_fill_i32(e->max_key, INT_MIN, B, e->st));
+  KL(launch_logmel(e->pcm, e->pcm_dtype == B200ASR_PCM_F32, B, e->n_samples, e->n_samples, e->basis_t,
+                   WF(e, "mel_fbank"), e->fb_start, e->fb_len, c.n_fft, c.hop, c.n_mels, e->mel_raw, e->max_key, e->st));
+  // zero the conv padding rows (row 0 and row Tm+1 of every utterance)
+  CK(cudaMemset2DAsync(e->mel_pad, (size_t)(Tm + 2) * c.n_mels * es, 0, (size_t)c.n_mels * es, B, e->st));
+  CK(cudaMemset2DAsync((char*)e->mel_pad + (size_t)(Tm + 1) * c.n_mels * es, (size_t)(Tm + 2) * c.n_mels * es, 0,
+                       (size_t)c.n_mels * es, B, e->st));
+  CK(cudaMemset2DAsync(e->h1_pad, (size_t)(Tm + 2) * d * es, 0, (size_t)d * es, B, e->st));
+  CK(cudaMemset2DAsync((char*)e->h1_pad + (size_t)(Tm + 1) * d * es, (size_t)(Tm + 2) * d * es, 0, (size_t)d * es, B, e->st));
+  KL(launch_mel_finalize(e->mel_raw, e->max_key, B, Tm, c.n_mels, e->mel_pad, ad, e->st));
+  // ---- conv stem as strided-view GEMMs (Export_Whisper.py:428-429) ----
+  {
+    GemmArgs g = linear_args(e, e->mel_pad, c.n_mels, "enc.conv1.w", "enc.conv1.b", (char*)e->h1_pad + (size_t)d * es, d,
+                             ad, Tm, d, 3 * c.n_mels);
+    g.sAo = (int64_t)(Tm + 2) * c.n_mels; g.sCo = (int64_t)(Tm + 2) * d; g.batch = B; g.act = kActGelu;
+    RET(gemm(e, g));
+    GemmArgs g2 = linear_args(e, e->h1_pad, 2 * d, "enc.conv2.w", "enc.conv2.b", e->hidden, d, kF32, T, d, 3 * d);
+    g2.sAo = (int64_t)(Tm + 2) * d; g2.sCo = (int64_t)T * d; g2.batch = B; g2.act = kActGelu;
+    g2.residual = WF(e, "enc.pos"); g2.ldr = d; g2.sRo = 0;
+    RET(gemm(e, g2));
+  }
+  if (e->keep_stages) CK(cudaMemcpyAsync(e->stem, e->hidden, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, e->st));
+  // ---- encoder layers (Export_Whisper.py:430-437) ----
+  for (int l = 0; l < c.enc_layers; ++l) {
+    const std::string p = "enc.L" + std::to_string(l) + ".";
+    KL(launch_layernorm(e->hidden, d, nullptr, nullptr, e->xhat, ad, d, M, d, 1e-5f, e->st));
+    RET(gemm(e, linear_args(e, e->xhat, d, p + "qkv.w", p + "qkv.b", e->qkv, 3 * d, ad, M, 3 * d, d)));
+    {  // per-(utterance, head) softmax(Q K^T) V ; scale pre-folded into q and k
+      GemmArgs s;
+      s.A = e->qkv; s.lda = 3 * d; s.sAo = (int64_t)T * 3 * d; s.sAi = 64; s.a_dtype = ad;
+      s.B = (char*)e->qkv + (size_t)d * es; s.ldb = 3 * d; s.sBo = (int64_t)T * 3 * d; s.sBi = 64; s.b_dtype = ad;
+      s.C = e->S; s.ldc = T; s.sCo = (int64_t)H * T * T; s.sCi = (int64_t)T * T; s.c_dtype = kF32;
+      s.M = T; s.N = T; s.K = 64; s.batch = B * H; s.batch_inner = H;
+      KL(launch_gemm_simt(s, e->st));
+      KL(launch_softmax_rows(e->S, e->P, ad, (int64_t)B * H * T, T, e->st));
+      GemmArgs o;
+      o.A = e->P; o.lda = T; o.sAo = (int64_t)H * T * T; o.sAi = (int64_t)T * T; o.a_dtype = ad;
+      o.B = (char*)e->qkv + (size_t)2 * d * es; o.ldb = 3 * d; o.sBo = (int64_t)T * 3 * d; o.sBi = 64; o.b_dtype = ad;
+      o.transB = 1;
+      o.C = e->ctx; o.ldc = d; o.sCo = (int64_t)T * d; o.sCi = 64; o.c_dtype = ad;
+      o.M = T; o.N = 64; o.K = T; o.batch = B * H; o.batch_inner = H;
+      KL(launch_gemm_simt(o, e->st));
+    }
+    {
+      GemmArgs g = linear_args(e, e->ctx, d, p + "out.w", p + "out.b", e->hidden, d, kF32, M, d, d);
+      g.residual = e->hidden; g.ldr = d;
+      RET(gemm(e, g));
+    }
+    KL(launch_layernorm(e->hidden, d, nullptr, nullptr, e->xhat, ad, d, M, d, 1e-5f, e->st));
+    {
+      GemmArgs g = linear_args(e, e->xhat, d, p + "fc1.w", p + "fc1.b", e->ffn, c.ffn, ad, M, c.ffn, d);
+      g.act = kActGelu;
+      RET(gemm(e, g));
+      GemmArgs g2 = linear_args(e, e->ffn, c.ffn, p + "fc2.w", p + "fc2.b", e->hidden, d, kF32, M, d, c.ffn);
+      g2.residual = e->hidden; g2.ldr = d;
+      RET(gemm(e, g2));
+    }
+  }
+  // ---- final LN (affine) + fused cross-KV projection (Export_Whisper.py:438-447) ----
+  KL(launch_layernorm(e->hidden, d, WF(e, "enc.ln_post.g"), WF(e, "enc.ln_post.b"), e->xhat, ad, d, M, d, 1e-5f, e->st));
+  RET(gemm(e, linear_args(e, e->xhat, d, "enc.cross_kv.w", "enc.cross_kv.b", e->cross_kv, 2 * L * d, ad, M, 2 * L * d, d)));
+  e->encoded = true;
+  e->prefilled = false;
+  return B200ASR_OK;
+}
+
+// enqueue one decoder launch over n_new tokens per utterance (tokens on device, [B][n_new])
+int enqueue_decoder(b200asr_engine* e, const int* tokens_dev, int n_new, bool first) {
+  const b200asr_config& c = e->cfg;
+  const int B = e->B, d = c.d_model, H = c.n_heads, L = c.dec_layers, T = e->T_enc;
+  const int rows = B * n_new;
+  const int wd = e->act_dtype;
+  KL(launch_dec_embed(tokens_dev, W(e, "dec.embed"), wd, W(e, "dec.pos"), B, n_new, d, e->dstate, e->dx, e->st));
+  const size_t layer_kv = (size_t)B * H * c.max_target * 64 * e->es;
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "dec.L" + std::to_string(l) + ".";
+    DecLinearArgs a{};
+    a.eps = 1e-5f; a.w_dtype = wd; a.n_new = n_new; a.n_heads = H; a.head_dim = 64; a.max_target = c.max_target;
+    a.batch = B; a.state = e->dstate; a.rows = rows; a.kv_dtype = wd;
+    // LN + fused QKV, K/V appended straight into the resident cache
+    DecLinearArgs q = a;
+    q.x = e->dx; q.ldx = d; q.ln_mode = 1; q.W = W(e, p + "qkv.w"); q.bias = WF(e, p + "qkv.b");
+    q.out = e->dq; q.ldo = d; q.mode = 1; q.kcache = (char*)e->kcache + l * layer_kv; q.vcache = (char*)e->vcache + l * layer_kv;
+    q.N = 3 * d; q.K = d;
+    KL(launch_dec_linear(q, e->st));
+    KL(launch_dec_self_attn(e->dq, q.kcache, q.vcache, wd, B, n_new, H, 64, c.max_target, e->dstate, e->dctx, e->st));
+    DecLinearArgs o = a;
+    o.x = e->dctx; o.ldx = d; o.W = W(e, p + "out.w"); o.bias = WF(e, p + "out.b"); o.residual = e->dx; o.ldr = d;
+    o.out = e->dx; o.ldo = d; o.N = d; o.K = d;
+    KL(launch_dec_linear(o, e->st));
+    DecLinearArgs cq = a;
+    cq.x = e->dx; cq.ldx = d; cq.ln_mode = 1; cq.W = W(e, p + "cq.w"); cq.bias = WF(e, p + "cq.b");
+    cq.out = e->dq; cq.ldo = d; cq.N = d; cq.K = d;
+    KL(launch_dec_linear(cq, e->st));
+    KL(launch_dec_cross_attn(e->dq, e->cross_kv, wd, l, L, B, n_new, H, 64, T, e->dctx, e->st));
+    DecLinearArgs co = a;
+    co.x = e->dctx; co.ldx = d; co.W = W(e, p + "cout.w"); co.bias = WF(e, p + "cout.b"); co.residual = e->dx; co.ldr = d;
+    co.out = e->dx; co.ldo = d; co.N = d; co.K = d;
+    KL(launch_dec_linear(co, e->st));
+    DecLinearArgs f1 = a;
+    f1.x = e->dx; f1.ldx = d; f1.ln_mode = 1; f1.W = W(e, p + "fc1.w"); f1.bias = WF(e, p + "fc1.b"); f1.act = kActGelu;
+    f1.out = e->dffn; f1.ldo = c.ffn; f1.N = c.ffn; f1.K = d;
+    KL(launch_dec_linear(f1, e->st));
+    DecLinearArgs f2 = a;
+    f2.x = e->dffn; f2.ldx = c.ffn; f2.W = W(e, p + "fc2.w"); f2.bias = WF(e, p + "fc2.b"); f2.residual = e->dx; f2.ldr = d;
+    f2.out = e->dx; f2.ldo = d; f2.N = d; f2.K = c.ffn;
+    KL(launch_dec_linear(f2, e->st));
+  }
+  {  // last-token LN (affine) + tied lm head + permanent suppress bias (Export_Whisper.py:663-666)
+    DecLinearArgs h{};
+    h.eps = 1e-5f; h.w_dtype = wd; h.rows = B; h.state = e->dstate;
+    h.x = e->dx + (size_t)(n_new - 1) * d; h.ldx = (int64_t)n_new * d; h.ln_mode = 2;
+    h.gamma = WF(e, "dec.ln.g"); h.beta = WF(e, "dec.ln.b");
+    h.W = W(e, "dec.embed"); h.bias = WF(e, "dec.suppress_bias"); h.out = e->logits; h.ldo = c.vocab;
+    h.N = c.vocab; h.K = d;
+    KL(launch_dec_linear(h, e->st));
+  }
+  SelectArgs s{};
+  s.logits = e->logits; s.vocab = c.vocab; s.batch = B;
+  s.begin_bias = first ? WF(e, "dec.begin_suppress_bias") : nullptr;
+  s.cur_token = e->cur_token; s.tokens = e->tokens; s.tokens_ld = c.max_target; s.n_gen = e->n_gen;
+  s.finished = e->finished; s.save_id = e->save_id; s.save_ld = c.max_target; s.n_save = e->n_save;
+  s.selected_hist = e->selected_hist; s.sel_ld = c.max_target;
+  s.stop_ids = e->d_stop; s.n_stop = (int)e->stop_ids.size(); s.limit = e->limit;
+  s.penalty_value = e->repeat_penalty; s.penalty_range = e->penalty_range;
+  s.state = e->dstate; s.n_new = n_new;
+  KL(launch_select_token(s, e->st));
+  e->launches++;   // select = 2 kernels
+  return B200ASR_OK;
+}
+
+int ensure_step_graph(b200asr_engine* e) {
+  char key[256];
+  snprintf(key, sizeof key, "%d/%d/%d/%g/%d/%zu", e->B, e->T_enc, e->limit, e->repeat_penalty, e->penalty_range,
+           e->stop_ids.size());
+  if (e->step_graph && e->graph_key == key) return B200ASR_OK;
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+  cudaGraph_t graph = nullptr;
+  const int64_t before = e->launches;
+  CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
+  int r = enqueue_decoder(e, e->cur_token, 1, false);
+  cudaError_t ce = cudaStreamEndCapture(e->st, &graph);
+  e->step_graph_nodes = e->launches - before;
+  e->launches = before;
+  if (r != B200ASR_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "cudaStreamEndCapture");
+  ce = cudaGraphInstantiate(&e->step_graph, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "cudaGraphInstantiate");
+  e->graph_key = key;
+  return B200ASR_OK;
+}
+
+int launch_step(b200asr_engine* e) {
+  RET(ensure_step_graph(e));
+  CK(cudaGraphLaunch(e->step_graph, e->st));
+  e->launches += e->step_graph_nodes;
+  return B200ASR_OK;
+}
+
+int do_upload(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples) {
+  const b200asr_config& c = e->cfg;
+  if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
+  if (!pcm_host || batch <= 0 || batch > c.max_batch) return e->fail(B200ASR_E_INVALID, "batch out of range");
+  if (n_samples < c.n_fft || n_samples > c.max_samples) return e->fail(B200ASR_E_INVALID, "n_samples out of range");
+  if (pcm_dtype != B200ASR_PCM_I16 && pcm_dtype != B200ASR_PCM_F32) return e->fail(B200ASR_E_INVALID, "bad pcm dtype");
+  const int Tm = n_samples / c.hop;
+  const int T = (Tm + 1) / 2;
+  if (T > c.max_source) return e->fail(B200ASR_E_INVALID, "audio longer than max_source positions");
+  e->B = batch; e->n_samples = n_samples; e->T_mel = Tm; e->T_enc = T; e->pcm_dtype = pcm_dtype;
+  const size_t bytes = (size_t)batch * n_samples * (pcm_dtype == B200ASR_PCM_F32 ? 4 : 2);
+  CK(cudaMemcpyAsync(e->pcm, pcm_host, bytes, cudaMemcpyHostToDevice, e->st));
+  e->encoded = false; e->prefilled = false;
+  return B200ASR_OK;
+}
+
+int do_prefill(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt) {
+  const b200asr_config& c = e->cfg;
+  if (!e->encoded) return e->fail(B200ASR_E_INVALID, "prefill before encode");
+  if (!prompt_ids || n_prompt <= 0 || n_prompt >= c.max_target) return e->fail(B200ASR_E_INVALID, "bad prompt");
+  const int B = e->B;
+  CK(cudaMemcpyAsync(e->d_prompt, prompt_ids, (size_t)B * n_prompt * 4, cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemsetAsync(e->dstate, 0, sizeof(DecState), e->st));
+  CK(cudaMemsetAsync(e->n_gen, 0, (size_t)B * 4, e->st));
+  CK(cudaMemsetAsync(e->finished, 0, (size_t)B * 4, e->st));
+  CK(cudaMemsetAsync(e->n_save, 0, (size_t)B * 4, e->st));
+  e->n_prompt = n_prompt;
+  // generate_limit = MAX_SEQ_LEN - prompt length (Inference_Whisper_ONNX.py:821), optionally tightened
+  e->limit = c.max_target - n_prompt;
+  if (e->limit_cfg > 0 && e->limit_cfg < e->limit) e->limit = e->limit_cfg;
+  RET(enqueue_decoder(e, e->d_prompt, n_prompt, true));
+  e->prefilled = true;
+  return B200ASR_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char* b200asr_last_error(const b200asr_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int b200asr_create(const b200asr_config* cfg, b200asr_engine** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return B200ASR_E_INVALID; }
+  *out = nullptr;
+  if (cfg->d_model <= 0 || cfg->n_heads <= 0 || cfg->d_model != cfg->n_heads * 64) {
+    g_create_error = "d_model must equal n_heads * 64 (Whisper head_dim)"; return B200ASR_E_INVALID;
+  }
+  if (cfg->d_model % 8 || cfg->ffn % 8 || cfg->n_mels % 8 || cfg->n_fft % 2 || cfg->hop <= 0 || cfg->max_batch <= 0 ||
+      cfg->max_samples < cfg->n_fft || cfg->vocab <= 0 || cfg->max_target <= 1 || cfg->enc_layers <= 0 ||
+      cfg->dec_layers <= 0) {
+    g_create_error = "invalid model dimensions"; return B200ASR_E_INVALID;
+  }
+  if (cfg->precision != B200ASR_PRECISION_F32 && cfg->precision != B200ASR_PRECISION_BF16) {
+    g_create_error = "invalid precision"; return B200ASR_E_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = "no CUDA device: the b200asr engine has no CPU fallback"; return B200ASR_E_NOGPU;
+  }
+  cudaDeviceProp prop;
+  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) {
+    g_create_error = "cudaSetDevice failed"; return B200ASR_E_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "device is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this build targets sm_100a only";
+    return B200ASR_E_NOGPU;
+  }
+  b200asr_engine* e = new b200asr_engine();
+  e->cfg = *cfg;
+  e->num_sms = prop.multiProcessorCount;
+  e->act_dtype = cfg->precision == B200ASR_PRECISION_BF16 ? kBF16 : kF32;
+  e->es = dtype_size(e->act_dtype);
+  if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_error = "cudaStreamCreate failed"; delete e; return B200ASR_E_CUDA;
+  }
+  *out = e;
+  return B200ASR_OK;
+}
+
+void b200asr_destroy(b200asr_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->st);
+  if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
+  for (auto& kv : e->w) cudaFree(kv.second.ptr);
+  void* bufs[] = {e->stage_buf, e->basis_t, e->fb_start, e->fb_len, e->pcm, e->mel_raw, e->max_key, e->mel_pad, e->h1_pad,
+                  e->hidden, e->stem, e->xhat, e->qkv, e->ctx, e->ffn, e->S, e->P, e->cross_kv, e->kcache, e->vcache,
+                  e->dx, e->dq, e->dctx, e->dffn, e->logits, e->prob, e->d_prompt, e->cur_token, e->tokens, e->n_gen,
+                  e->finished, e->save_id, e->n_save, e->selected_hist, e->d_stop, e->dstate};
+  for (void* p : bufs) if (p) cudaFree(p);
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  cudaStreamDestroy(e->st);
+  delete e;
+}
+
+int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
+  if (!e || !key) return B200ASR_E_INVALID;
+  if (!strcmp(key, "keep_stages")) { e->keep_stages = value != 0; return B200ASR_OK; }
+  return e->fail(B200ASR_E_INVALID, std::string("unknown option ") + key);
+}
+
+int b200asr_set_tensor(b200asr_engine* e, const char* name_c, const float* host, int64_t numel) {
+  if (!e || !name_c || !host || numel <= 0) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  const std::string name(name_c);
+  const b200asr_config& c = e->cfg;
+  const int F = c.n_fft / 2 + 1;
+  if (name == "stft_kernel") {
+    // [2F][n_fft] (Conv1d weight of STFT_Process.py:136-150) -> basis_t [n_fft][2F] for coalesced reads
+    if (numel != (int64_t)2 * F * c.n_fft) return e->fail(B200ASR_E_INVALID, "stft_kernel size mismatch");
+    std::vector<float> t((size_t)numel);
+    for (int r = 0; r < 2 * F; ++r)
+      for (int k = 0; k < c.n_fft; ++k) t[(size_t)k * 2 * F + r] = host[(size_t)r * c.n_fft + k];
+    if (!e->basis_t) CK(cudaMalloc(&e->basis_t, (size_t)numel * 4));
+    CK(cudaMemcpy(e->basis_t, t.data(), (size_t)numel * 4, cudaMemcpyHostToDevice));
+  }
+  if (name == "mel_fbank") {
+    if (numel != (int64_t)c.n_mels * F) return e->fail(B200ASR_E_INVALID, "mel_fbank size mismatch");
+    std::vector<int> s0(c.n_mels), ln(c.n_mels);
+    for (int m = 0; m < c.n_mels; ++m) {
+      int lo = F, hi = -1;
+      for (int f = 0; f < F; ++f) if (host[(size_t)m * F + f] != 0.f) { if (f < lo) lo = f; hi = f; }
+      s0[m] = hi < 0 ? 0 : lo; ln[m] = hi < 0 ? 0 : hi - lo + 1;
+    }
+    if (!e->fb_start) { CK(cudaMalloc(&e->fb_start, c.n_mels * 4)); CK(cudaMalloc(&e->fb_len, c.n_mels * 4)); }
+    CK(cudaMemcpy(e->fb_start, s0.data(), c.n_mels * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->fb_len, ln.data(), c.n_mels * 4, cudaMemcpyHostToDevice));
+  }
+  DevTensor t;
+  t.numel = numel;
+  t.dtype = is_weight_matrix(name) ? e->act_dtype : kF32;
+  auto it = e->w.find(name);
+  if (it != e->w.end()) { cudaFree(it->second.ptr); e->w.erase(it); }
+  CK(cudaMalloc(&t.ptr, (size_t)numel * dtype_size(t.dtype)));
+  if (t.dtype == kF32) {
+    CK(cudaMemcpy(t.ptr, host, (size_t)numel * 4, cudaMemcpyHostToDevice));
+  } else {
+    RET(ensure_stage(e, numel));
+    CK(cudaMemcpy(e->stage_buf, host, (size_t)numel * 4, cudaMemcpyHostToDevice));
+    f32_to_bf16_kernel<<<1024, 256, 0, e->st>>>(e->stage_buf, (bf16*)t.ptr, numel);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->st));
+  }
+  e->w[name] = t;
+  e->finalized = false;
+  return B200ASR_OK;
+}
+
+int b200asr_finalize_weights(b200asr_engine* e) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  const b200asr_config& c = e->cfg;
+  const int64_t d = c.d_model, f = c.ffn, L = c.dec_layers, F = c.n_fft / 2 + 1;
+  RET(need(e, "stft_kernel", 2 * F * c.n_fft));
+  RET(need(e, "mel_fbank", c.n_mels * F));
+  RET(need(e, "enc.conv1.w", d * 3 * c.n_mels)); RET(need(e, "enc.conv1.b", d));
+  RET(need(e, "enc.conv2.w", d * 3 * d)); RET(need(e, "enc.conv2.b", d));
+  RET(need(e, "enc.pos", (int64_t)c.max_source * d));
+  for (int l = 0; l < c.enc_layers; ++l) {
+    const std::string p = "enc.L" + std::to_string(l) + ".";
+    RET(need(e, p + "qkv.w", 3 * d * d)); RET(need(e, p + "qkv.b", 3 * d));
+    RET(need(e, p + "out.w", d * d)); RET(need(e, p + "out.b", d));
+    RET(need(e, p + "fc1.w", f * d)); RET(need(e, p + "fc1.b", f));
+    RET(need(e, p + "fc2.w", d * f)); RET(need(e, p + "fc2.b", d));
+  }
+  RET(need(e, "enc.ln_post.g", d)); RET(need(e, "enc.ln_post.b", d));
+  RET(need(e, "enc.cross_kv.w", 2 * L * d * d)); RET(need(e, "enc.cross_kv.b", 2 * L * d));
+  RET(need(e, "dec.embed", (int64_t)c.vocab * d)); RET(need(e, "dec.pos", (int64_t)c.max_target * d));
+  for (int l = 0; l < c.dec_layers; ++l) {
+    const std::string p = "dec.L" + std::to_string(l) + ".";
+    RET(need(e, p + "qkv.w", 3 * d * d)); RET(need(e, p + "qkv.b", 3 * d));
+    RET(need(e, p + "out.w", d * d)); RET(need(e, p + "out.b", d));
+    RET(need(e, p + "cq.w", d * d)); RET(need(e, p + "cq.b", d));
+    RET(need(e, p + "cout.w", d * d)); RET(need(e, p + "cout.b", d));
+    RET(need(e, p + "fc1.w", f * d)); RET(need(e, p + "fc1.b", f));
+    RET(need(e, p + "fc2.w", d * f)); RET(need(e, p + "fc2.b", d));
+  }
+  RET(need(e, "dec.ln.g", d)); RET(need(e, "dec.ln.b", d));
+  RET(need(e, "dec.suppress_bias", c.vocab)); RET(need(e, "dec.begin_suppress_bias", c.vocab));
+  if (e->finalized) return B200ASR_OK;
+  if (e->stage_buf) { cudaFree(e->stage_buf); e->stage_buf = nullptr; e->stage_cap = 0; }
+  if (!e->pcm) {
+    const size_t es = e->es;
+    const int64_t B = c.max_batch, Tm = c.max_samples / c.hop, T = (Tm + 1) / 2, M = B * T, H = c.n_heads;
+    const int64_t rows = B * 8;    // decoder rows: up to 8 prompt tokens per utterance
+    RET(dmalloc(e, &e->pcm, (size_t)B * c.max_samples * 4));
+    RET(dmalloc(e, &e->mel_raw, (size_t)B * Tm * c.n_mels * 4));
+    RET(dmalloc(e, &e->max_key, (size_t)B * 4));
+    RET(dmalloc(e, &e->mel_pad, (size_t)B * (Tm + 2) * c.n_mels * es));
+    RET(dmalloc(e, &e->h1_pad, (size_t)B * (Tm + 2) * d * es));
+    RET(dmalloc(e, &e->hidden, (size_t)M * d * 4));
+    RET(dmalloc(e, &e->stem, (size_t)M * d * 4));
+    RET(dmalloc(e, &e->xhat, (size_t)M * d * es));
+    RET(dmalloc(e, &e->qkv, (size_t)M * 3 * d * es));
+    RET(dmalloc(e, &e->ctx, (size_t)M * d * es));
+    RET(dmalloc(e, &e->ffn, (size_t)M * f * es));
+    RET(dmalloc(e, &e->S, (size_t)B * H * T * T * 4));
+    RET(dmalloc(e, &e->P, (size_t)B * H * T * T * es));
+    RET(dmalloc(e, &e->cross_kv, (size_t)M * 2 * L * d * es));
+    RET(dmalloc(e, &e->kcache, (size_t)L * B * H * c.max_target * 64 * es));
+    RET(dmalloc(e, &e->vcache, (size_t)L * B * H * c.max_target * 64 * es));
+    RET(dmalloc(e, &e->dx, (size_t)rows * d * 4));
+    RET(dmalloc(e, &e->dq, (size_t)rows * d * 4));
+    RET(dmalloc(e, &e->dctx, (size_t)rows * d * 4));
+    RET(dmalloc(e, &e->dffn, (size_t)rows * f * 4));
+    RET(dmalloc(e, &e->logits, (size_t)B * c.vocab * 4));
+    RET(dmalloc(e, &e->prob, (size_t)B * 4));
+    RET(dmalloc(e, &e->d_prompt, (size_t)rows * 4));
+    RET(dmalloc(e, &e->cur_token, (size_t)B * 4));
+    RET(dmalloc(e, &e->tokens, (size_t)B * c.max_target * 4));
+    RET(dmalloc(e, &e->n_gen, (size_t)B * 4));
+    RET(dmalloc(e, &e->finished, (size_t)B * 4));
+    RET(dmalloc(e, &e->save_id, (size_t)B * c.max_target * 4));
+    RET(dmalloc(e, &e->n_save, (size_t)B * 4));
+    RET(dmalloc(e, &e->selected_hist, (size_t)B * c.max_target * 4));
+    RET(dmalloc(e, &e->d_stop, 64 * 4));
+    RET(dmalloc(e, &e->dstate, sizeof(DecState)));
+    e->h_pinned_bytes = (size_t)B * (c.max_target + 4) * 4 + 256;
+    CK(cudaMallocHost(&e->h_pinned, e->h_pinned_bytes));
+  }
+  CK(cudaStreamSynchronize(e->st));
+  e->finalized = true;
+  return B200ASR_OK;
+}
+
+int b200asr_upload_pcm(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  RET(do_upload(e, pcm_host, pcm_dtype, batch, n_samples));
+  CK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+
+int b200asr_encode_resident(b200asr_engine* e) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (e->B <= 0) return e->fail(B200ASR_E_INVALID, "no PCM uploaded");
+  RET(run_encoder(e));
+  CK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+
+int b200asr_encode(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  RET(do_upload(e, pcm_host, pcm_dtype, batch, n_samples));
+  RET(run_encoder(e));
+  CK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+
+int b200asr_set_decode_options(b200asr_engine* e, const int32_t* stop_ids, int32_t n_stop, int32_t generate_limit,
+                               float repeat_penalty, int32_t penalty_range) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (n_stop < 0 || n_stop > 64 || (n_stop > 0 && !stop_ids)) return e->fail(B200ASR_E_INVALID, "bad stop id list");
+  if (!(repeat_penalty > 0.f) || penalty_range < 0) return e->fail(B200ASR_E_INVALID, "bad penalty options");
+  if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
+  e->stop_ids.assign(stop_ids, stop_ids + n_stop);
+  if (n_stop) CK(cudaMemcpy(e->d_stop, stop_ids, (size_t)n_stop * 4, cudaMemcpyHostToDevice));
+  e->limit_cfg = generate_limit > 0 ? generate_limit : 0;
+  e->repeat_penalty = repeat_penalty;
+  e->penalty_range = penalty_range;
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+  return B200ASR_OK;
+}
+
+int b200asr_prefill(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt, float* logits_out,
+                    int32_t* first_token_out) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (n_prompt > 8) return e->fail(B200ASR_E_INVALID, "prompt longer than 8 tokens");
+  RET(do_prefill(e, prompt_ids, n_prompt));
+  if (logits_out) CK(cudaMemcpyAsync(logits_out, e->logits, (size_t)e->B * e->cfg.vocab * 4, cudaMemcpyDeviceToHost, e->st));
+  if (first_token_out) CK(cudaMemcpyAsync(first_token_out, e->cur_token, (size_t)e->B * 4, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+
+int b200asr_decode_step(b200asr_engine* e, const int32_t* token_in, float* logits_out, int32_t* token_out) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (!e->prefilled) return e->fail(B200ASR_E_INVALID, "decode before prefill");
+  DecState hs;
+  CK(cudaMemcpyAsync(&hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  if (hs.kv_len + 1 > e->cfg.max_target) return e->fail(B200ASR_E_INVALID, "KV cache full");
+  if (token_in) CK(cudaMemcpyAsync(e->cur_token, token_in, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->st));
+  RET(launch_step(e));
+  if (logits_out) CK(cudaMemcpyAsync(logits_out, e->logits, (size_t)e->B * e->cfg.vocab * 4, cudaMemcpyDeviceToHost, e->st));
+  if (token_out) CK(cudaMemcpyAsync(token_out, e->cur_token, (size_t)e->B * 4, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+
+static int decode_loop(b200asr_engine* e, int max_steps, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  const b200asr_config& c = e->cfg;
+  if (!e->prefilled) return e->fail(B200ASR_E_INVALID, "decode before prefill");
+  if (!tokens_out || !lens_out || tokens_ld <= 0) return e->fail(B200ASR_E_INVALID, "null output");
+  // the loop needs at most limit-1 launches after the prefill head produced token #1
+  int steps = e->limit - 1;
+  if (max_steps >= 0 && max_steps < steps) steps = max_steps;
+  const int room = c.max_target - e->n_prompt;    // cache positions left after the prompt
+  if (steps > room) steps = room;
+  int* h_done = e->h_pinned;
+  for (int s = 0; s < steps; ++s) {
+    RET(launch_step(e));
+    if (!e->stop_ids.empty() && (s % 8) == 7 && s + 1 < steps) {
+      CK(cudaMemcpyAsync(h_done, &e->dstate->all_done, 4, cudaMemcpyDeviceToHost, e->st));
+      CK(cudaStreamSynchronize(e->st));
+      if (*h_done) break;
+    }
+  }
+  const int B = e->B;
+  int* h_len = e->h_pinned + 64;
+  int* h_tok = h_len + B;
+  CK(cudaMemcpyAsync(h_len, e->n_gen, (size_t)B * 4, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaMemcpyAsync(h_tok, e->tokens, (size_t)B * c.max_target * 4, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  for (int b = 0; b < B; ++b) {
+    const int n = h_len[b] < tokens_ld ? h_len[b] : tokens_ld;
+    lens_out[b] = n;
+    memcpy(tokens_out + (size_t)b * tokens_ld, h_tok + (size_t)b * c.max_target, (size_t)n * 4);
+  }
+  return B200ASR_OK;
+}
+
+int b200asr_decode(b200asr_engine* e, int32_t max_steps, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  return decode_loop(e, max_steps, tokens_out, tokens_ld, lens_out);
+}
+
+int b200asr_no_speech_prob(b200asr_engine* e, int32_t no_speech_token, float* prob_out) {
+  if (!e || !prob_out) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (!e->prefilled) return e->fail(B200ASR_E_INVALID, "no_speech_prob before prefill");
+  if (no_speech_token < 0 || no_speech_token >= e->cfg.vocab) return e->fail(B200ASR_E_INVALID, "bad token id");
+  // unsuppress bias = -suppress_bias (+128 on suppressed ids): computed once
+  if (!find(e, "dec.unsuppress_bias")) {
+    std::vector<float> h((size_t)e->cfg.vocab);
+    CK(cudaMemcpy(h.data(), W(e, "dec.suppress_bias"), h.size() * 4, cudaMemcpyDeviceToHost));
+    for (auto& v : h) v = (v != 0.f) ? 128.0f : 0.f;
+    DevTensor t; t.numel = e->cfg.vocab; t.dtype = kF32;
+    CK(cudaMalloc(&t.ptr, h.size() * 4));
+    CK(cudaMemcpy(t.ptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    e->w["dec.unsuppress_bias"] = t;
+  }
+  KL(launch_softmax_pick(e->logits, WF(e, "dec.unsuppress_bias"), e->cfg.vocab, e->B, no_speech_token, e->prob, e->st));
+  CK(cudaMemcpyAsync(prob_out, e->prob, (size_t)e->B * 4, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+
+int b200asr_transcribe_resident(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt, int32_t max_new,
+                                int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (e->B <= 0) return e->fail(B200ASR_E_INVALID, "no PCM uploaded");
+  if (n_prompt > 8) return e->fail(B200ASR_E_INVALID, "prompt longer than 8 tokens");
+  RET(run_encoder(e));
+  const int saved = e->limit_cfg;
+  if (max_new > 0 && (saved == 0 || max_new < saved)) e->limit_cfg = max_new;
+  int r = do_prefill(e, prompt_ids, n_prompt);
+  e->limit_cfg = saved;
+  RET(r);
+  return decode_loop(e, -1, tokens_out, tokens_ld, lens_out);
+}
+
+int b200asr_transcribe(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                       const int32_t* prompt_ids, int32_t n_prompt, int32_t max_new, int32_t* tokens_out,
+                       int32_t tokens_ld, int32_t* lens_out) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  RET(do_upload(e, pcm_host, pcm_dtype, batch, n_samples));
+  return b200asr_transcribe_resident(e, prompt_ids, n_prompt, max_new, tokens_out, tokens_ld, lens_out);
+}
+
+int b200asr_get_stage(b200asr_engine* e, const char* name_c, float* out, int64_t capacity, int64_t* numel_out) {
+  if (!e || !name_c || !out) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  const b200asr_config& c = e->cfg;
+  const std::string name(name_c);
+  const int64_t B = e->B, d = c.d_model, H = c.n_heads, L = c.dec_layers, T = e->T_enc, Tm = e->T_mel;
+  if (!e->encoded) return e->fail(B200ASR_E_INVALID, "get_stage before encode");
+  CK(cudaStreamSynchronize(e->st));
+  auto fetch = [&](const void* src, int64_t n, int dtype, std::vector<float>& h) -> int {
+    h.resize((size_t)n);
+    if (dtype == kF32) { CK(cudaMemcpy(h.data(), src, (size_t)n * 4, cudaMemcpyDeviceToHost)); return B200ASR_OK; }
+    RET(ensure_stage(e, n));
+    bf16_to_f32_kernel<<<1024, 256, 0, e->st>>>((const bf16*)src, e->stage_buf, n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->st));
+    CK(cudaMemcpy(h.data(), e->stage_buf, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return B200ASR_OK;
+  };
+  std::vector<float> h;
+  int64_t n = 0;
+  if (name == "mel") {                       // -> [B][n_mels][Tm]
+    RET(fetch(e->mel_pad, B * (Tm + 2) * c.n_mels, e->act_dtype, h));
+    n = B * c.n_mels * Tm;
+    if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
+    for (int64_t b = 0; b < B; ++b)
+      for (int64_t t = 0; t < Tm; ++t)
+        for (int64_t m = 0; m < c.n_mels; ++m)
+          out[(b * c.n_mels + m) * Tm + t] = h[(size_t)((b * (Tm + 2) + 1 + t) * c.n_mels + m)];
+  } else if (name == "stem" || name == "hidden") {
+    if (name == "stem" && !e->keep_stages) return e->fail(B200ASR_E_INVALID, "set option keep_stages=1 before encode");
+    RET(fetch(name == "stem" ? e->stem : e->hidden, B * T * d, kF32, h));
+    n = B * T * d;
+    if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
+    memcpy(out, h.data(), (size_t)n * 4);
+  } else if (name == "enc_out") {
+    RET(fetch(e->xhat, B * T * d, e->act_dtype, h));
+    n = B * T * d;
+    if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
+    memcpy(out, h.data(), (size_t)n * 4);
+  } else if (name == "cross_k" || name == "cross_v") {      // -> [B][L][H][T][64]
+    RET(fetch(e->cross_kv, B * T * 2 * L * d, e->act_dtype, h));
+    n = B * L * H * T * 64;
+    if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
+    const int64_t off = name == "cross_v" ? L * d : 0;
+    for (int64_t b = 0; b < B; ++b)
+      for (int64_t l = 0; l < L; ++l)
+        for (int64_t hh = 0; hh < H; ++hh)
+          for (int64_t t = 0; t < T; ++t)
+            memcpy(out + ((((b * L + l) * H + hh) * T + t) * 64),
+                   h.data() + (size_t)((b * T + t) * 2 * L * d + off + l * d + hh * 64), 64 * 4);
+  } else if (name == "self_k" || name == "self_v") {        // -> [L][B][H][kv][64]
+    DecState hs;
+    CK(cudaMemcpy(&hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost));
+    const int64_t kv = hs.kv_len, Bm = B, mt = c.max_target;
+    n = L * Bm * H * kv * 64;
+    if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
+    for (int64_t l = 0; l < L; ++l) {
+      const char* base = (const char*)(name == "self_k" ? e->kcache : e->vcache) + (size_t)l * Bm * H * mt * 64 * e->es;
+      RET(fetch(base, Bm * H * mt * 64, e->act_dtype, h));
+      for (int64_t bh = 0; bh < Bm * H; ++bh)
+        memcpy(out + (size_t)((l * Bm * H + bh) * kv * 64), h.data() + (size_t)(bh * mt * 64), (size_t)kv * 64 * 4);
+    }
+  } else if (name == "selected") {                          // [B][step] as float
+    DecState hs;
+    CK(cudaMemcpy(&hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost));
+    std::vector<int> hi((size_t)B * c.max_target);
+    CK(cudaMemcpy(hi.data(), e->selected_hist, hi.size() * 4, cudaMemcpyDeviceToHost));
+    n = B * hs.step;
+    if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
+    for (int64_t b = 0; b < B; ++b)
+      for (int64_t s = 0; s < hs.step; ++s) out[b * hs.step + s] = (float)hi[(size_t)(b * c.max_target + s)];
+  } else {
+    return e->fail(B200ASR_E_INVALID, "unknown stage '" + name + "'");
+  }
+  if (numel_out) *numel_out = n;
+  return B200ASR_OK;
+}
+
+void* b200asr_stream(b200asr_engine* e) { return e ? (void*)e->st : nullptr; }
+int b200asr_synchronize(b200asr_engine* e) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+int64_t b200asr_kernel_launches(const b200asr_engine* e) { return e ? e->launches : 0; }
+int b200asr_num_sms(const b200asr_engine* e) { return e ? e->num_sms : 0; }
+
+int b200asr_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
+                      const float* bias, const float* residual, int32_t act, float* C, char* err, int32_t err_len) {
+  auto fail = [&](const std::string& m, int code) {
+    if (err && err_len > 0) { strncpy(err, m.c_str(), err_len - 1); err[err_len - 1] = 0; }
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed", B200ASR_E_NOGPU);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  float *dA32 = nullptr, *dB32 = nullptr, *dC = nullptr, *dbias = nullptr, *dres = nullptr;
+  bf16 *dA = nullptr, *dB = nullptr;
+  const int64_t Kp = (K + 7) / 8 * 8;       // row pitch padded to 16 bytes for TMA
+  cudaError_t ce = cudaSuccess;
+  auto ok = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; return x == cudaSuccess; };
+  ok(cudaMalloc(&dA32, (size_t)M * Kp * 4)); ok(cudaMalloc(&dB32, (size_t)N * Kp * 4));
+  ok(cudaMalloc(&dA, (size_t)M * Kp * 2)); ok(cudaMalloc(&dB, (size_t)N * Kp * 2));
+  ok(cudaMalloc(&dC, (size_t)M * N * 4));
+  if (ce == cudaSuccess) {
+    ok(cudaMemset(dA32, 0, (size_t)M * Kp * 4)); ok(cudaMemset(dB32, 0, (size_t)N * Kp * 4));
+    ok(cudaMemcpy2D(dA32, Kp * 4, A, (size_t)K * 4, (size_t)K * 4, M, cudaMemcpyHostToDevice));
+    ok(cudaMemcpy2D(dB32, Kp * 4, B, (size_t)K * 4, (size_t)K * 4, N, cudaMemcpyHostToDevice));
+    f32_to_bf16_kernel<<<256, 256>>>(dA32, dA, (int64_t)M * Kp);
+    f32_to_bf16_kernel<<<256, 256>>>(dB32, dB, (int64_t)N * Kp);
+    if (bias) { ok(cudaMalloc(&dbias, (size_t)N * 4)); ok(cudaMemcpy(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice)); }
+    if (residual) { ok(cudaMalloc(&dres, (size_t)M * N * 4)); ok(cudaMemcpy(dres, residual, (size_t)M * N * 4, cudaMemcpyHostToDevice)); }
+  }
+  std::string msg;
+  if (ce == cudaSuccess) {
+    GemmArgs g;
+    g.A = dA; g.lda = Kp; g.a_dtype = kBF16; g.B = dB; g.ldb = Kp; g.b_dtype = kBF16;
+    g.C = dC; g.ldc = N; g.c_dtype = kF32; g.bias = dbias; g.residual = dres; g.ldr = N; g.act = act;
+    g.M = M; g.N = N; g.K = K;
+    if (impl == 1) ok(launch_gemm_tc(g, prop.multiProcessorCount, 0, &msg));
+    else ok(launch_gemm_simt(g, 0));
+    ok(cudaDeviceSynchronize());
+    if (ce == cudaSuccess) ok(cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(dA32); cudaFree(dB32); cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dbias); cudaFree(dres);
+  if (ce != cudaSuccess) return fail(msg.empty() ? std::string(cudaGetErrorString(ce)) : msg, B200ASR_E_CUDA);
+  return B200ASR_OK;
+}
+
+}  // extern "C"

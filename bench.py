@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Headline benchmark: Whisper-large-v3 greedy transcription of synthetic 8 s / 16 kHz clips.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one batch of clips per GPU:
+int16 PCM -> log-mel -> 32-layer encoder -> fused cross-KV -> 4-token prefill ->
+32 greedy decode launches (33 tokens), i.e. the work of one PROBE/PREFILL + 32 DECODE
+`InferenceSession.run_with_iobinding` calls of the reference driver
+(Whisper/Inference_Whisper_ONNX.py:766-827, DETECT_LANGUAGE=False,
+NO_SPEECH_DETECTION=False, REPEAT_PENALTY=1.0).
+
+Prints ONE JSON line (see DESIGN.md "Measurement" for every key).
+  value = audio seconds transcribed per wall second (xRT), all ranks, PCM resident in HBM
+  e2e   = same through b200asr_transcribe with pinned host PCM (H2D + D2H inside the timed region)
+--impl reference times the CPU oracle port of the reference graph on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np
+import torch
+
+PROMPT = [50258, 50259, 50360, 50364]       # <|startoftranscript|><|en|><|transcribe|><|notimestamps|> (large-v3 ids)
+EOS = 50257
+N_SAMPLES = 128000                          # 8 s @ 16 kHz
+DECODE_LAUNCHES = 32
+MAX_NEW = DECODE_LAUNCHES + 1               # prefill head yields token 1
+SEED = 20260
+
+
+def _dims(preset):
+    from b200asr.config import PRESETS
+    return PRESETS[preset]
+
+
+def _prompt(dims):
+    return PROMPT if dims.vocab > max(PROMPT) else [3, 10, 11, 12]
+
+
+def _suppress(dims):
+    # stand-in for generation_config.suppress_tokens / begin_suppress_tokens (no tokenizer files offline)
+    if dims.vocab > 50364:
+        return [1, 2, 7, 8, 9, 10, 14, 25, 50358, 50359, 50360, 50361, 50362, 50363], [220, EOS]
+    return [1, 5, 7, 13], [220, 2]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes_per_decode_step(dims, batch, T_enc, kv_mid):
+    """HBM bytes one decode launch must move in bf16 (DESIGN.md 'Roofline'): every decoder weight once,
+    the tied lm-head once, cross-KV of every utterance, the self-KV read so far."""
+    d, f, L = dims.d_model, dims.ffn, dims.dec_layers
+    per_layer = (3 * d * d) + (d * d) * 3 + 2 * d * f           # qkv, out, cq, cout, fc1, fc2
+    weights = (L * per_layer + dims.vocab * d) * 2
+    cross = batch * L * 2 * T_enc * d * 2
+    self_kv = batch * L * 2 * kv_mid * d * 2
+    return weights + cross + self_kv
+
+
+def encoder_flops(dims, T_mel, T_enc):
+    d, f, L = dims.d_model, dims.ffn, dims.enc_layers
+    lin = 2 * T_enc * (3 * d * d + d * d + 2 * d * f)
+    att = 4 * T_enc * T_enc * d
+    stem = 2 * T_mel * d * 3 * dims.n_mels + 2 * T_enc * d * 3 * d
+    cross = 2 * T_enc * d * 2 * dims.dec_layers * d
+    return L * (lin + att) + stem + cross
+
+
+def run_reference(args, dims):
+    """CPU arm: the oracle port of the reference graph (torch fp32, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import whisper_oracle as wo
+    from b200asr.synth import synth_pcm
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    odims = wo.WhisperDims(**dims.to_dict())
+    sup, beg = _suppress(dims)
+    t0 = time.time()
+    raw = wo.make_raw_weights(odims, SEED)
+    fw = wo.fold_weights(raw, odims, sup, beg)
+    del raw
+    setup_s = time.time() - t0
+    prompt = _prompt(dims)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            pcm = synth_pcm(i, N_SAMPLES)
+            t = time.time()
+            r = wo.greedy_transcribe(pcm, fw, odims, prompt, stop_tokens=[], max_new=MAX_NEW, return_logits=False)
+            dt = time.time() - t
+            if i >= args.warmup:
+                times.append(dt)
+    audio_s = N_SAMPLES / dims.sample_rate
+    wall = sum(times)
+    value = audio_s * len(times) / wall
+    line = {
+        "impl": "reference", "metric": "xRT (audio_s/wall_s)", "value": value, "unit": "x real time",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "rtf": wall / (audio_s * len(times)), "utterances_per_s": len(times) / wall,
+        "config": {"workload": f"{args.preset} greedy, batch=1, 8 s chunk: encoder + 4-token prefill + "
+                               f"{DECODE_LAUNCHES} decode launches, host CPU", "decode_launches": DECODE_LAUNCHES},
+        "cpu_baseline": {"value": value, "unit": "x real time", "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} utterance(s) of the same workload; oracle/whisper_oracle.py "
+                                   f"(torch fp32 restatement of the reference graph; onnxruntime is not installed)"},
+        "e2e": {"value": value, "unit": "x real time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "setup_s": setup_s,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--preset", default="whisper-large-v3")
+    ap.add_argument("--batch-per-gpu", type=int, default=1)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    dims = _dims(args.preset)
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 2
+        args.warmup = args.warmup if args.warmup is not None else 1
+        return run_reference(args, dims)
+    args.steps = args.steps if args.steps is not None else 20
+    args.warmup = max(3, args.warmup if args.warmup is not None else 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the b200asr engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from b200asr.engine import WhisperEngine
+    from b200asr.synth import synth_batch, synth_whisper_checkpoint
+    from b200asr.weights import fold_whisper
+
+    B = args.batch_per_gpu
+    sup, beg = _suppress(dims)
+    t0 = time.time()
+    raw = synth_whisper_checkpoint(dims, SEED)
+    tensors = fold_whisper(raw, dims, sup, beg)
+    del raw
+    eng = WhisperEngine(dims, tensors, precision=args.precision, max_batch=B, max_samples=N_SAMPLES, device=local_rank)
+    del tensors
+    setup_s = time.time() - t0
+    prompt = _prompt(dims)
+    eng.set_decode_options(stop_ids=[], generate_limit=MAX_NEW)
+    pcm = torch.from_numpy(synth_batch(B, N_SAMPLES, first_index=rank * B)).pin_memory()
+    pcm_np = pcm.numpy()
+    toks = torch.zeros((B, dims.max_target), dtype=torch.int32).pin_memory()
+    lens = torch.zeros((B,), dtype=torch.int32).pin_memory()
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident arm ----
+    eng.upload_pcm(pcm_np)
+    result = {}
+
+    def step_resident():
+        result["tokens"] = eng.transcribe_resident(prompt, max_new=MAX_NEW)
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.kernel_launches
+    ms_total = timed(step_resident, args.steps)
+    launches = eng.kernel_launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end arm: pinned host PCM in, tokens out, every step ----
+    def step_e2e():
+        eng.transcribe(pcm_np, prompt, max_new=MAX_NEW, out_tokens=toks.numpy(), out_lens=lens.numpy())
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- dominant kernel: the weight-streaming decode launch ----
+    eng.encode_resident()
+    eng.prefill(prompt, want_logits=False)
+    eng.decode(max_steps=4)
+    eng.prefill(prompt, want_logits=False)
+    ms_dec = timed(lambda: eng.decode(max_steps=DECODE_LAUNCHES), 1) / DECODE_LAUNCHES
+    ms_enc = timed(eng.encode_resident, 3) / 3
+
+    audio_s = N_SAMPLES / dims.sample_rate
+    total_audio = audio_s * B * world * args.steps
+    value = total_audio / (ms_total / 1e3)
+    e2e = total_audio / (ms_e2e / 1e3)
+    T_mel = N_SAMPLES // dims.hop
+    T_enc = (T_mel + 1) // 2
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+    bytes_step = algorithmic_bytes_per_decode_step(dims, B, T_enc, len(prompt) + DECODE_LAUNCHES // 2)
+    achieved = bytes_step / (ms_dec / 1e3) / 1e9
+    enc_tf = encoder_flops(dims, T_mel, T_enc) * B / (ms_enc / 1e3) / 1e12
+
+    if rank == 0:
+        line = {
+            "metric": "xRT (audio_s/wall_s)", "value": value, "unit": "x real time", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+            "data": "synthetic", "impl": "b200",
+            "rtf": (ms_total / 1e3) / total_audio, "utterances_per_s": B * world * args.steps / (ms_total / 1e3),
+            "config": {
+                "workload": f"{args.preset} {args.precision} greedy, batch={B}/GPU, 8 s chunk, {world}xB200: encoder + "
+                            f"4-token prefill + {DECODE_LAUNCHES} decode launches",
+                "batch_per_gpu": B, "n_samples": N_SAMPLES, "decode_launches": DECODE_LAUNCHES,
+                "weights": "seeded random init (no checkpoints offline)",
+                "l2": "no flush: the 3.1 GB bf16 weight set streamed every decode launch is 24x the 126 MB L2",
+            },
+            "e2e": {"value": e2e, "unit": "x real time", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(pcm_np.nbytes + B * len(prompt) * 4),
+                    "d2h_bytes_per_step": int(B * (dims.max_target + 1) * 4)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "decode launch (dec_linear_kernel weight streaming + attention), CUDA graph of one step",
+                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "ms_per_launch": ms_dec, "algorithmic_bytes_per_launch": bytes_step,
+            },
+            "encoder": {"ms": ms_enc, "tflops": enc_tf, "frac_of_bf16_peak": enc_tf / tf_peak},
+            "setup_s": setup_s, "tokens_head": result["tokens"][0][:8],
+        }
+        if not args.no_cpu_baseline and world == 1 and args.preset == "whisper-large-v3":
+            line["cpu_baseline"] = cpu_baseline(dims, prompt, result["tokens"][0])
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(dims, prompt, gpu_tokens):
+    """The oracle port timed on this box's host cores on ONE utterance of the same workload."""
+    from oracle import whisper_oracle as wo
+    from b200asr.synth import synth_pcm
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    odims = wo.WhisperDims(**dims.to_dict())
+    sup, beg = _suppress(dims)
+    raw = wo.make_raw_weights(odims, SEED)
+    fw = wo.fold_weights(raw, odims, sup, beg)
+    del raw
+    pcm = synth_pcm(0, N_SAMPLES)
+    with torch.no_grad():
+        t = time.time()
+        r = wo.greedy_transcribe(pcm, fw, odims, prompt, stop_tokens=[], max_new=MAX_NEW, return_logits=False)
+        dt = time.time() - t
+    match = 0
+    for a, b in zip(r["tokens"], gpu_tokens):
+        if a != b:
+            break
+        match += 1
+    audio_s = N_SAMPLES / dims.sample_rate
+    return {"value": audio_s / dt, "unit": "x real time", "cores": cores, "kind": "port", "seconds": dt,
+            "sample": "1 utterance (8 s) of the same workload, oracle/whisper_oracle.py torch-fp32 port of the "
+                      "reference graph, all host threads",
+            "greedy_prefix_match_vs_gpu": match, "tokens_compared": len(gpu_tokens)}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,126 @@
+/* b200asr -- C ABI of the B200-native ASR engine (libb200asr.so).
+ *
+ * This is the drop-in boundary for the ONE hot path this repository replaces:
+ * onnxruntime.InferenceSession.run()/run_with_iobinding() as called by the
+ * reference's Whisper driver script.  Plain pointers and sizes only; no torch,
+ * numpy or ORT types.  Every function returns 0 on success, a negative
+ * B200ASR_E_* code otherwise; b200asr_last_error() gives the message.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   b200asr_encode / _transcribe   PROBE_SESSION.run_with_iobinding -- encoder half
+ *                                  Whisper/Inference_Whisper_ONNX.py:493-550 (call :549),
+ *                                  math Whisper/Export_Whisper.py:422-447, Whisper/STFT_Process.py:224-246
+ *   b200asr_prefill                PREFILL_SESSION.run_with_iobinding  :437-490 (call :489),
+ *                                  graph = merge_prefill_greedy Whisper/Shared_Merged.py:864-874
+ *   b200asr_decode_step / _decode  DECODE_SESSION.run_with_iobinding   :584-663 (call :640),
+ *                                  graph = merge_decode_greedy Whisper/Shared_Merged.py:877-888
+ *   b200asr_no_speech_prob         NO_SPEECH_SESSION.run_with_iobinding :691-699,
+ *                                  math Whisper/Export_Whisper.py:334-348
+ *   b200asr_set_tensor             SessionOptions.add_initializer via attach_shared_initializers
+ *                                  Whisper/Shared_Merged.py:1713-1743 (one shared weight blob)
+ *
+ * Threading: one engine per GPU, one CUDA stream per engine, calls on one
+ * engine are not re-entrant (the reference is single-threaded, ORT_SEQUENTIAL).
+ * Ownership: the caller owns every host buffer and must keep it alive until the
+ * call returns; the engine owns all device memory.
+ */
+#ifndef B200ASR_H_
+#define B200ASR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ASR_OK 0
+#define B200ASR_E_INVALID (-1)   /* bad argument / shape / state */
+#define B200ASR_E_CUDA (-2)      /* CUDA runtime or kernel failure */
+#define B200ASR_E_MISSING (-3)   /* a required weight tensor was never set */
+#define B200ASR_E_NOGPU (-4)     /* no usable sm_100 device */
+
+#define B200ASR_PRECISION_F32 0  /* fp32 CUDA-core path: the parity mode (logits within 1e-3) */
+#define B200ASR_PRECISION_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate/residual */
+
+#define B200ASR_PCM_I16 0        /* raw int16 PCM; the 1/32768 scale is applied on device */
+#define B200ASR_PCM_F32 1        /* float PCM already divided by audio_pcm_scale */
+
+typedef struct b200asr_engine b200asr_engine;
+
+typedef struct b200asr_config {
+  int32_t n_mels, d_model, n_heads, ffn, enc_layers, dec_layers, vocab;
+  int32_t max_source;      /* encoder positions (1500) */
+  int32_t max_target;      /* decoder positions = MAX_SEQ_LEN metadata (448) */
+  int32_t n_fft, hop;      /* 400 / 160 */
+  int32_t max_batch;       /* utterances resident at once */
+  int32_t max_samples;     /* per-utterance PCM capacity (<= 480000) */
+  int32_t precision;       /* B200ASR_PRECISION_* */
+  int32_t device;          /* CUDA ordinal */
+  int32_t use_tensor_cores;/* bf16 only: 1 = tcgen05 GEMMs (default), 0 = CUDA-core GEMMs (debug cross-check) */
+} b200asr_config;
+
+/* lifecycle ------------------------------------------------------------------*/
+int b200asr_create(const b200asr_config* cfg, b200asr_engine** out);
+void b200asr_destroy(b200asr_engine* e);
+const char* b200asr_last_error(const b200asr_engine* e);   /* e may be NULL: last create() error */
+
+/* weights: folded fp32 tensors by name (see DESIGN.md "Weight tensors"); the
+ * engine converts to its storage dtype on device.  finalize() checks that the
+ * set is complete. */
+int b200asr_set_tensor(b200asr_engine* e, const char* name, const float* host_data, int64_t numel);
+int b200asr_finalize_weights(b200asr_engine* e);
+
+/* encoder: PCM [batch][n_samples] (row stride = n_samples) -> cross-KV resident in HBM */
+int b200asr_encode(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples);
+/* same, split so a benchmark can time with inputs already resident */
+int b200asr_upload_pcm(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples);
+int b200asr_encode_resident(b200asr_engine* e);
+
+/* decoder: prefill resets the self-KV cache and the token bookkeeping.
+ * prompt_ids [batch][n_prompt]; logits_out (optional) [batch][vocab] raw logits
+ * (suppress bias applied, begin-suppress NOT applied = the graph's "logits"
+ * output); first_token_out (optional) [batch] = argmax after begin-suppress. */
+int b200asr_set_decode_options(b200asr_engine* e, const int32_t* stop_ids, int32_t n_stop, int32_t generate_limit,
+                               float repeat_penalty, int32_t penalty_range);
+int b200asr_prefill(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt, float* logits_out,
+                    int32_t* first_token_out);
+/* one decode launch.  token_in (optional) [batch] overrides the fed-back token
+ * (teacher forcing); logits_out (optional) [batch][vocab]; token_out (optional) [batch]. */
+int b200asr_decode_step(b200asr_engine* e, const int32_t* token_in, float* logits_out, int32_t* token_out);
+/* device-resident greedy loop: up to max_steps decode launches without host
+ * round trips; stops early when every utterance has latched a stop token or
+ * hit generate_limit.  tokens_out [batch][tokens_ld], lens_out [batch]. */
+int b200asr_decode(b200asr_engine* e, int32_t max_steps, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
+/* P(<|nospeech|>) from the last prefill's logits with the -128 suppress bias undone */
+int b200asr_no_speech_prob(b200asr_engine* e, int32_t no_speech_token, float* prob_out);
+
+/* whole path, one host call, one sync: encode + prefill + decode */
+int b200asr_transcribe(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                       const int32_t* prompt_ids, int32_t n_prompt, int32_t max_new, int32_t* tokens_out,
+                       int32_t tokens_ld, int32_t* lens_out);
+/* same with PCM already uploaded (b200asr_upload_pcm): device-resident timing */
+int b200asr_transcribe_resident(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt, int32_t max_new,
+                                int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
+
+/* introspection (parity tests, profiling) ------------------------------------*/
+/* copy an intermediate to host as fp32: "mel" [B][n_mels][T], "stem"/"enc_out" [B][T_enc][d],
+ * "cross_k"/"cross_v" [B][L][H][T_enc][64], "self_k"/"self_v" [L][B][H][kv][64].
+ * Returns the number of floats written through *numel_out. */
+int b200asr_get_stage(b200asr_engine* e, const char* name, float* out, int64_t capacity, int64_t* numel_out);
+/* options: "keep_stages" (0/1) keeps a copy of the conv-stem output for get_stage("stem") */
+int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value);
+void* b200asr_stream(b200asr_engine* e);                 /* cudaStream_t of the engine */
+int b200asr_synchronize(b200asr_engine* e);
+int64_t b200asr_kernel_launches(const b200asr_engine* e);   /* kernels launched by this engine so far */
+int b200asr_num_sms(const b200asr_engine* e);
+
+/* standalone operator tests (the GEMM the encoder is built on) ----------------
+ * C[M][N] = act(A[M][K] . B[N][K]^T + bias) + residual, host fp32 in/out, computed
+ * on device in bf16 by the tcgen05 kernel (impl 1) or the CUDA-core kernel (impl 0). */
+int b200asr_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
+                      const float* bias, const float* residual, int32_t act, float* C, char* err, int32_t err_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ASR_H_ */

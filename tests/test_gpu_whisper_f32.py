@@ -1,0 +1,98 @@
+"""fp32 precision mode of the CUDA engine vs goldens minted from the reference modules.
+Tolerance = north_star's "logits within 1e-3 fp32"; tokens must match exactly."""
+import numpy as np
+import pytest
+
+from gpu_common import GOLD, NO_SPEECH, load_case, make_engine, maxdiff
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=GOLD, ids=[p.stem for p in GOLD])
+def ctx(request):
+    g, raw, tensors = load_case(request.param)
+    eng = make_engine(tensors, "f32")
+    eng.set_option("keep_stages", 1)
+    yield g, eng
+    eng.close()
+
+
+def test_encoder_stages(ctx):
+    g, eng = ctx
+    eng.encode(g["pcm"])
+    T = (len(g["pcm"]) // 160 + 1) // 2
+    mel = eng.get_stage("mel", 128 * 4000).reshape(128, -1)
+    np.testing.assert_allclose(mel, g["mel"], atol=2e-4)
+    stem = eng.get_stage("stem", T * 256).reshape(T, 256)
+    np.testing.assert_allclose(stem, g["stem"], atol=5e-4)
+    enc_out = eng.get_stage("enc_out", T * 256).reshape(T, 256)
+    np.testing.assert_allclose(enc_out, g["enc_out"], atol=1e-3)
+    ck = eng.get_stage("cross_k", 2 * 4 * T * 64).reshape(2, 4, T, 64)
+    cv = eng.get_stage("cross_v", 2 * 4 * T * 64).reshape(2, 4, T, 64)
+    np.testing.assert_allclose(ck[0].transpose(0, 2, 1), g["cross_k_layer0"], atol=1e-3)   # golden K is (H, dh, T)
+    np.testing.assert_allclose(cv[1], g["cross_v_last"], atol=1e-3)
+
+
+def test_free_running_greedy(ctx):
+    g, eng = ctx
+    eng.encode(g["pcm"])
+    eng.set_decode_options(stop_ids=[], generate_limit=0)
+    logits, tok = eng.prefill(g["prompt"])
+    all_logits, toks = [logits[0]], [int(tok[0])]
+    for _ in range(6):
+        logits, tok = eng.decode_step()
+        all_logits.append(logits[0]); toks.append(int(tok[0]))
+    assert maxdiff(np.stack(all_logits), g["free_logits"]) <= 1e-3
+    assert toks == g["free_tokens"].tolist()
+    kv = eng.get_stage("self_k", 2 * 4 * 448 * 64).reshape(2, 4, -1, 64)
+    np.testing.assert_allclose(kv[1].transpose(0, 2, 1), g["self_k_last_layer"], atol=1e-3)
+    vv = eng.get_stage("self_v", 2 * 4 * 448 * 64).reshape(2, 4, -1, 64)
+    np.testing.assert_allclose(vv[0], g["self_v_layer0"], atol=1e-3)
+
+
+def test_teacher_forced(ctx):
+    g, eng = ctx
+    eng.encode(g["pcm"])
+    eng.set_decode_options(stop_ids=[])
+    logits, _ = eng.prefill(g["prompt"])
+    all_logits = [logits[0]]
+    for t in g["forced_tokens"].tolist():
+        logits, _ = eng.decode_step(token_in=[t])
+        all_logits.append(logits[0])
+    assert maxdiff(np.stack(all_logits), g["forced_logits"]) <= 1e-3
+
+
+def test_device_loop_and_transcribe(ctx):
+    g, eng = ctx
+    eng.set_decode_options(stop_ids=[], generate_limit=7)
+    eng.encode(g["pcm"])
+    eng.prefill(g["prompt"], want_logits=False)
+    toks = eng.decode()[0]
+    assert toks == g["free_tokens"].tolist()
+    toks2 = eng.transcribe(g["pcm"], g["prompt"], max_new=7)[0]
+    assert toks2 == g["free_tokens"].tolist()
+    # stop latch: stopping on the 3rd selected token keeps exactly the first two
+    stop = int(g["free_tokens"][2])
+    eng.set_decode_options(stop_ids=[stop], generate_limit=7)
+    toks3 = eng.transcribe(g["pcm"], g["prompt"], max_new=7)[0]
+    first = g["free_tokens"].tolist().index(stop)
+    assert toks3 == g["free_tokens"].tolist()[:first]
+
+
+def test_penalty_greedy(ctx):
+    g, eng = ctx
+    eng.set_decode_options(stop_ids=[], generate_limit=7, repeat_penalty=0.8, penalty_range=3)
+    toks = eng.transcribe(g["pcm"], g["prompt"], max_new=7)[0]
+    assert toks == g["penalty_tokens"].tolist()
+
+
+def test_probe_heads(ctx):
+    g, eng = ctx
+    eng.encode(g["pcm"])
+    eng.set_decode_options(stop_ids=[])
+    logits, _ = eng.prefill([3])
+    assert maxdiff(logits[0], g["probe_logits"]) <= 1e-3
+    p = eng.no_speech_prob(NO_SPEECH)
+    np.testing.assert_allclose(p, g["no_speech_prob"], rtol=2e-3, atol=1e-7)
+    lang = g["lang_ids"]
+    assert int(lang[np.argmax(logits[0][lang])]) == int(g["detected_language"])

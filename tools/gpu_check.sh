@@ -1,0 +1,10 @@
+#!/bin/bash
+# Runs the GPU parity suites in separate processes (a trapped kernel kills its CUDA context,
+# so one bad suite must not take the others down) with hard timeouts.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv | tee gpurun_out/gpu.txt
+for t in test_gpu_gemm test_gpu_whisper_f32 test_gpu_whisper_bf16; do
+  echo "=== $t"
+  timeout 900 python -m pytest tests/$t.py -m gpu -q -s -x --timeout 600 2>&1 | tail -40 | tee gpurun_out/$t.log
+done
