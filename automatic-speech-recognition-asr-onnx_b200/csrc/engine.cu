@@ -42,6 +42,7 @@ struct b200asr_engine {
   int64_t launches = 0;
   bool finalized = false;
   bool keep_stages = false;
+  bool warned_tmap = false; int64_t tmap_fallbacks = 0;
   int act_dtype = kF32;      // activations fed to GEMMs, weights, KV caches
   size_t es = 4;
 
@@ -77,6 +78,16 @@ struct b200asr_engine {
     return B200ASR_E_CUDA;
   }
 };
+
+
+// Stream-ordered copy + sync on the engine's (non-blocking) stream.  A plain cudaMemcpy from
+// pageable memory may return before the DMA lands and is only ordered against the legacy
+// stream, so kernels on e->st could read a half-written buffer.
+static cudaError_t b200_copy_sync(b200asr_engine* e, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+  cudaError_t r = cudaMemcpyAsync(dst, src, bytes, kind, e->st);
+  if (r != cudaSuccess) return r;
+  return cudaStreamSynchronize(e->st);
+}
 
 #define CK(expr)                                                           \
   do {                                                                     \
@@ -139,9 +150,16 @@ int gemm(b200asr_engine* e, const GemmArgs& g) {
   if (e->act_dtype == kBF16 && e->cfg.use_tensor_cores && gemm_tc_supported(g)) {
     std::string msg;
     cudaError_t r = launch_gemm_tc(g, e->num_sms, e->st, &msg);
-    e->launches++;
-    if (r != cudaSuccess) return e->fail(B200ASR_E_CUDA, "gemm_tc: " + (msg.empty() ? std::string(cudaGetErrorString(r)) : msg));
-    return B200ASR_OK;
+    if (r == cudaErrorNotSupported) {
+      // the driver refused the tensor map (e.g. an overlapping strided view): CUDA-core GEMM for this call
+      cudaGetLastError();
+      if (!e->warned_tmap) { fprintf(stderr, "b200asr: %s; using the CUDA-core GEMM for this operand view\n", msg.c_str()); e->warned_tmap = true; }
+      e->tmap_fallbacks++;
+    } else {
+      e->launches++;
+      if (r != cudaSuccess) return e->fail(B200ASR_E_CUDA, "gemm_tc: " + (msg.empty() ? std::string(cudaGetErrorString(r)) : msg));
+      return B200ASR_OK;
+    }
   }
   KL(launch_gemm_simt(g, e->st));
   return B200ASR_OK;
@@ -442,7 +460,7 @@ int b200asr_set_tensor(b200asr_engine* e, const char* name_c, const float* host,
     for (int r = 0; r < 2 * F; ++r)
       for (int k = 0; k < c.n_fft; ++k) t[(size_t)k * 2 * F + r] = host[(size_t)r * c.n_fft + k];
     if (!e->basis_t) CK(cudaMalloc(&e->basis_t, (size_t)numel * 4));
-    CK(cudaMemcpy(e->basis_t, t.data(), (size_t)numel * 4, cudaMemcpyHostToDevice));
+    CK(b200_copy_sync(e, e->basis_t, t.data(), (size_t)numel * 4, cudaMemcpyHostToDevice));
   }
   if (name == "mel_fbank") {
     if (numel != (int64_t)c.n_mels * F) return e->fail(B200ASR_E_INVALID, "mel_fbank size mismatch");
@@ -453,8 +471,8 @@ int b200asr_set_tensor(b200asr_engine* e, const char* name_c, const float* host,
       s0[m] = hi < 0 ? 0 : lo; ln[m] = hi < 0 ? 0 : hi - lo + 1;
     }
     if (!e->fb_start) { CK(cudaMalloc(&e->fb_start, c.n_mels * 4)); CK(cudaMalloc(&e->fb_len, c.n_mels * 4)); }
-    CK(cudaMemcpy(e->fb_start, s0.data(), c.n_mels * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->fb_len, ln.data(), c.n_mels * 4, cudaMemcpyHostToDevice));
+    CK(b200_copy_sync(e, e->fb_start, s0.data(), c.n_mels * 4, cudaMemcpyHostToDevice));
+    CK(b200_copy_sync(e, e->fb_len, ln.data(), c.n_mels * 4, cudaMemcpyHostToDevice));
   }
   DevTensor t;
   t.numel = numel;
@@ -463,10 +481,10 @@ int b200asr_set_tensor(b200asr_engine* e, const char* name_c, const float* host,
   if (it != e->w.end()) { cudaFree(it->second.ptr); e->w.erase(it); }
   CK(cudaMalloc(&t.ptr, (size_t)numel * dtype_size(t.dtype)));
   if (t.dtype == kF32) {
-    CK(cudaMemcpy(t.ptr, host, (size_t)numel * 4, cudaMemcpyHostToDevice));
+    CK(b200_copy_sync(e, t.ptr, host, (size_t)numel * 4, cudaMemcpyHostToDevice));
   } else {
     RET(ensure_stage(e, numel));
-    CK(cudaMemcpy(e->stage_buf, host, (size_t)numel * 4, cudaMemcpyHostToDevice));
+    CK(b200_copy_sync(e, e->stage_buf, host, (size_t)numel * 4, cudaMemcpyHostToDevice));
     f32_to_bf16_kernel<<<1024, 256, 0, e->st>>>(e->stage_buf, (bf16*)t.ptr, numel);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->st));
@@ -587,7 +605,7 @@ int b200asr_set_decode_options(b200asr_engine* e, const int32_t* stop_ids, int32
   if (!(repeat_penalty > 0.f) || penalty_range < 0) return e->fail(B200ASR_E_INVALID, "bad penalty options");
   if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
   e->stop_ids.assign(stop_ids, stop_ids + n_stop);
-  if (n_stop) CK(cudaMemcpy(e->d_stop, stop_ids, (size_t)n_stop * 4, cudaMemcpyHostToDevice));
+  if (n_stop) CK(b200_copy_sync(e, e->d_stop, stop_ids, (size_t)n_stop * 4, cudaMemcpyHostToDevice));
   e->limit_cfg = generate_limit > 0 ? generate_limit : 0;
   e->repeat_penalty = repeat_penalty;
   e->penalty_range = penalty_range;
@@ -669,11 +687,11 @@ int b200asr_no_speech_prob(b200asr_engine* e, int32_t no_speech_token, float* pr
   // unsuppress bias = -suppress_bias (+128 on suppressed ids): computed once
   if (!find(e, "dec.unsuppress_bias")) {
     std::vector<float> h((size_t)e->cfg.vocab);
-    CK(cudaMemcpy(h.data(), W(e, "dec.suppress_bias"), h.size() * 4, cudaMemcpyDeviceToHost));
+    CK(b200_copy_sync(e, h.data(), W(e, "dec.suppress_bias"), h.size() * 4, cudaMemcpyDeviceToHost));
     for (auto& v : h) v = (v != 0.f) ? 128.0f : 0.f;
     DevTensor t; t.numel = e->cfg.vocab; t.dtype = kF32;
     CK(cudaMalloc(&t.ptr, h.size() * 4));
-    CK(cudaMemcpy(t.ptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    CK(b200_copy_sync(e, t.ptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
     e->w["dec.unsuppress_bias"] = t;
   }
   KL(launch_softmax_pick(e->logits, WF(e, "dec.unsuppress_bias"), e->cfg.vocab, e->B, no_speech_token, e->prob, e->st));
@@ -716,12 +734,12 @@ int b200asr_get_stage(b200asr_engine* e, const char* name_c, float* out, int64_t
   CK(cudaStreamSynchronize(e->st));
   auto fetch = [&](const void* src, int64_t n, int dtype, std::vector<float>& h) -> int {
     h.resize((size_t)n);
-    if (dtype == kF32) { CK(cudaMemcpy(h.data(), src, (size_t)n * 4, cudaMemcpyDeviceToHost)); return B200ASR_OK; }
+    if (dtype == kF32) { CK(b200_copy_sync(e, h.data(), src, (size_t)n * 4, cudaMemcpyDeviceToHost)); return B200ASR_OK; }
     RET(ensure_stage(e, n));
     bf16_to_f32_kernel<<<1024, 256, 0, e->st>>>((const bf16*)src, e->stage_buf, n);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->st));
-    CK(cudaMemcpy(h.data(), e->stage_buf, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CK(b200_copy_sync(e, h.data(), e->stage_buf, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return B200ASR_OK;
   };
   std::vector<float> h;
@@ -758,7 +776,7 @@ int b200asr_get_stage(b200asr_engine* e, const char* name_c, float* out, int64_t
                    h.data() + (size_t)((b * T + t) * 2 * L * d + off + l * d + hh * 64), 64 * 4);
   } else if (name == "self_k" || name == "self_v") {        // -> [L][B][H][kv][64]
     DecState hs;
-    CK(cudaMemcpy(&hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost));
+    CK(b200_copy_sync(e, &hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost));
     const int64_t kv = hs.kv_len, Bm = B, mt = c.max_target;
     n = L * Bm * H * kv * 64;
     if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
@@ -770,9 +788,9 @@ int b200asr_get_stage(b200asr_engine* e, const char* name_c, float* out, int64_t
     }
   } else if (name == "selected") {                          // [B][step] as float
     DecState hs;
-    CK(cudaMemcpy(&hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost));
+    CK(b200_copy_sync(e, &hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost));
     std::vector<int> hi((size_t)B * c.max_target);
-    CK(cudaMemcpy(hi.data(), e->selected_hist, hi.size() * 4, cudaMemcpyDeviceToHost));
+    CK(b200_copy_sync(e, hi.data(), e->selected_hist, hi.size() * 4, cudaMemcpyDeviceToHost));
     n = B * hs.step;
     if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
     for (int64_t b = 0; b < B; ++b)

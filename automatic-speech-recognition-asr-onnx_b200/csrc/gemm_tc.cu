@@ -313,9 +313,9 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t st, st
     attr_done = true;
   }
   CUtensorMap tmA, tmB;
-  if (!make_tmap(&tmA, g.A, g.K, g.M, g.batch, g.lda, g.sAo, BM, err)) return cudaErrorInvalidValue;
+  if (!make_tmap(&tmA, g.A, g.K, g.M, g.batch, g.lda, g.sAo, BM, err)) return cudaErrorNotSupported;
   const bool b_batched = g.sBo != 0 && g.batch > 1;
-  if (!make_tmap(&tmB, g.B, g.K, g.N, b_batched ? g.batch : 1, g.ldb, g.sBo, BN, err)) return cudaErrorInvalidValue;
+  if (!make_tmap(&tmB, g.B, g.K, g.N, b_batched ? g.batch : 1, g.ldb, g.sBo, BN, err)) return cudaErrorNotSupported;
   EpiArgs e;
   e.C = g.C; e.ldc = g.ldc; e.sC = g.sCo; e.c_dtype = g.c_dtype;
   e.bias = g.bias; e.residual = g.residual; e.ldr = g.ldr; e.sR = g.sRo; e.act = g.act;
