@@ -23,7 +23,7 @@ struct GemmArgs {
   const void* B = nullptr; int64_t ldb = 0, sBo = 0, sBi = 0; int b_dtype = kF32;
   int transB = 0;                     // 0: B is [N][K] (K contiguous); 1: B is [K][N]
   void* C = nullptr; int64_t ldc = 0, sCo = 0, sCi = 0; int c_dtype = kF32;
-  const float* bias = nullptr;
+  const float* bias = nullptr; int64_t sBias = 0;   // bias advances by sBias per batch index z
   const float* residual = nullptr; int64_t ldr = 0, sRo = 0, sRi = 0;
   int act = kActNone;
   int M = 0, N = 0, K = 0;
@@ -112,7 +112,7 @@ cudaError_t launch_dec_embed(const int* tokens /*[B][n_new]*/, const void* embed
 cudaError_t launch_dec_self_attn(const float* q /*[rows][d]*/, const void* kcache, const void* vcache, int kv_dtype,
                                  int batch, int n_new, int n_heads, int head_dim, int max_target,
                                  const DecState* state, float* ctx /*[rows][d]*/, cudaStream_t st);
-cudaError_t launch_dec_cross_attn(const float* q, const void* cross_kv /*[B][T][2*L*d]*/, int kv_dtype, int layer,
+cudaError_t launch_dec_cross_attn(const float* q, const void* cross_kv /*[2L][B][T][d]: K layers then V layers*/, int kv_dtype, int layer,
                                   int n_layers, int batch, int n_new, int n_heads, int head_dim, int T,
                                   float* ctx, cudaStream_t st);
 struct SelectArgs {
@@ -133,5 +133,38 @@ struct SelectArgs {
 cudaError_t launch_select_token(const SelectArgs& a, cudaStream_t st);
 cudaError_t launch_softmax_pick(const float* logits, const float* add_bias, int vocab, int batch, int index,
                                 float* out, cudaStream_t st);
+
+// decoder_mega.cu: persistent prefill + greedy-loop kernel (one cooperative launch)
+struct MegaLayer {
+  const void *qkv_w, *out_w, *cq_w, *cout_w, *fc1_w, *fc2_w;
+  const float *qkv_b, *out_b, *cq_b, *cout_b, *fc1_b, *fc2_b;
+};
+// one contiguous region of the per-step read stream; `start` is its offset in the padded stream
+// (every block is padded to a multiple of the super-chunk so a super-chunk never straddles blocks)
+struct PfBlock { const char* ptr; long long bytes; long long padded; long long start; };
+
+struct MegaArgs {
+  const MegaLayer* layers; int n_layers;
+  const void* embed; const float* pos; const float* ln_g; const float* ln_b;
+  const float* suppress_bias; const float* begin_bias;
+  void* kcache; void* vcache; const void* cross_kv; int T;
+  int batch, d, ffn, n_heads, vocab, max_target;
+  float* x; float* q; float* ctx; float* f; float* logits;     // logits may be null
+  const int* first_tokens; int first_n_new;                      // iteration 0: [B][first_n_new]
+  int* cur_token; int* tokens; int tokens_ld; int* n_gen; int* finished;
+  int* save_id; int save_ld; int* n_save; int* selected_hist; int sel_ld;
+  const int* stop_ids; int n_stop; int limit; float penalty_value; int penalty_range;
+  DecState* state;
+  unsigned int* bar;
+  float* cand_val; int* cand_idx;        // [gridDim.x][batch]
+  int n_iters; int first_is_prefill;     // begin-suppress bias applies to iteration 0 only when set
+  const PfBlock* pf_blocks; int n_pf_blocks; long long pf_total; long long pf_ahead;
+  float eps;
+};
+
+size_t mega_smem_bytes(int d, int ffn, int T, int max_target);
+bool mega_supported(int batch, int first_n_new, int d, int ffn);
+int mega_pf_piece();
+cudaError_t launch_decoder_mega(const MegaArgs& a, int w_dtype, int num_sms, cudaStream_t st);
 
 }  // namespace b200asr

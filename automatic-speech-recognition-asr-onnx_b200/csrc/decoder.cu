@@ -270,8 +270,8 @@ cudaError_t launch_dec_self_attn(const float* q, const void* kcache, const void*
 
 // ---------------------------------------------------------------------------
 // cross-attention: one CTA per (row, head) over T encoder positions.
-// cross_kv row t = [K(all layers, d each) | V(all layers, d each)], i.e. the
-// row-major output of the fused cross-KV projection (Export_Whisper.py:393-447).
+// cross_kv = [2L][B][T][d]: the fused cross-KV projection (Export_Whisper.py:393-447) written
+// per (kind, layer) so one layer's K (z = l) and V (z = L + l) are contiguous in HBM.
 // ---------------------------------------------------------------------------
 constexpr int kCrossThreads = 128;
 
@@ -287,9 +287,10 @@ dec_cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, i
   const int row = blockIdx.x, h = blockIdx.y;
   const int b = row / n_new;
   const int d = n_heads * 64;
-  const int64_t ld = 2 * (int64_t)n_layers * d;
-  const KT* kb = ckv + (int64_t)b * T * ld + (int64_t)layer * d + h * 64;
-  const KT* vb = kb + (int64_t)n_layers * d;
+  const int64_t ld = d;
+  const int B = gridDim.x / n_new;
+  const KT* kb = ckv + (((int64_t)layer * B + b) * T) * d + h * 64;
+  const KT* vb = ckv + (((int64_t)(n_layers + layer) * B + b) * T) * d + h * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < 64) qs[threadIdx.x] = q[(int64_t)row * d + h * 64 + threadIdx.x];
   __syncthreads();

@@ -70,6 +70,11 @@ struct b200asr_engine {
   std::vector<int> stop_ids; int limit = 0; int limit_cfg = 0; float repeat_penalty = 1.0f; int penalty_range = 20;
   int n_prompt = 0; bool prefilled = false; bool encoded = false;
   cudaGraphExec_t step_graph = nullptr; int64_t step_graph_nodes = 0;
+  // persistent decoder kernel state
+  bool use_mega = true; long long pf_ahead = 32ll << 20;
+  MegaLayer* mega_layers = nullptr; PfBlock* pf_blocks = nullptr; int n_pf_blocks = 0; long long pf_total = 0;
+  int pf_B = -1, pf_T = -1;
+  unsigned int* mega_bar = nullptr; float* cand_val = nullptr; int* cand_idx = nullptr;
   std::string graph_key;
 
   int fail(int code, const std::string& m) { err = m; return code; }
@@ -243,7 +248,12 @@ int run_encoder(b200asr_engine* e) {
   }
   // ---- final LN (affine) + fused cross-KV projection (Export_Whisper.py:438-447) ----
   KL(launch_layernorm(e->hidden, d, WF(e, "enc.ln_post.g"), WF(e, "enc.ln_post.b"), e->xhat, ad, d, M, d, 1e-5f, e->st));
-  RET(gemm(e, linear_args(e, e->xhat, d, "enc.cross_kv.w", "enc.cross_kv.b", e->cross_kv, 2 * L * d, ad, M, 2 * L * d, d)));
+  {  // 2L projections of the same rows: batched over z = (kind, layer) so each layer's K / V lands contiguous:
+     // cross_kv[z][b*T + t][d], z = l for K (pre-scaled), z = L + l for V
+    GemmArgs g = linear_args(e, e->xhat, d, "enc.cross_kv.w", "enc.cross_kv.b", e->cross_kv, d, ad, M, d, d);
+    g.batch = 2 * L; g.sAo = 0; g.sBo = (int64_t)d * d; g.sCo = (int64_t)M * d; g.sBias = d;
+    RET(gemm(e, g));
+  }
   e->encoded = true;
   e->prefilled = false;
   return B200ASR_OK;
@@ -343,6 +353,85 @@ int launch_step(b200asr_engine* e) {
   return B200ASR_OK;
 }
 
+
+// ---- persistent decoder kernel plumbing ------------------------------------------------------
+bool mega_ok(b200asr_engine* e, int first_n_new) {
+  return e->use_mega && mega_supported(e->B, first_n_new, e->cfg.d_model, e->cfg.ffn) && e->penalty_range <= 32 &&
+         e->B * (first_n_new > 1 ? first_n_new : 1) <= 64 &&
+         mega_smem_bytes(e->cfg.d_model, e->cfg.ffn, e->T_enc, e->cfg.max_target) <= 220 * 1024;
+}
+
+int build_mega_tables(b200asr_engine* e) {
+  const b200asr_config& c = e->cfg;
+  const int L = c.dec_layers;
+  const long long d = c.d_model, f = c.ffn;
+  const long long es = (long long)e->es;
+  if (!e->mega_layers) {
+    std::vector<MegaLayer> hl(L);
+    for (int l = 0; l < L; ++l) {
+      const std::string p = "dec.L" + std::to_string(l) + ".";
+      hl[l].qkv_w = W(e, p + "qkv.w"); hl[l].out_w = W(e, p + "out.w"); hl[l].cq_w = W(e, p + "cq.w");
+      hl[l].cout_w = W(e, p + "cout.w"); hl[l].fc1_w = W(e, p + "fc1.w"); hl[l].fc2_w = W(e, p + "fc2.w");
+      hl[l].qkv_b = WF(e, p + "qkv.b"); hl[l].out_b = WF(e, p + "out.b"); hl[l].cq_b = WF(e, p + "cq.b");
+      hl[l].cout_b = WF(e, p + "cout.b"); hl[l].fc1_b = WF(e, p + "fc1.b"); hl[l].fc2_b = WF(e, p + "fc2.b");
+    }
+    CK(cudaMalloc(&e->mega_layers, sizeof(MegaLayer) * L));
+    CK(b200_copy_sync(e, e->mega_layers, hl.data(), sizeof(MegaLayer) * L, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&e->pf_blocks, sizeof(PfBlock) * (8 * L + 1)));
+    CK(cudaMalloc(&e->mega_bar, 64));
+    CK(cudaMalloc(&e->cand_val, sizeof(float) * e->num_sms * c.max_batch));
+    CK(cudaMalloc(&e->cand_idx, sizeof(int) * e->num_sms * c.max_batch));
+  }
+  if (e->pf_B == e->B && e->pf_T == e->T_enc) return B200ASR_OK;
+  // per-step read stream in phase order: qkv, out, cq, crossK, crossV, cout, fc1, fc2 per layer, then the lm head
+  std::vector<PfBlock> hb;
+  const long long super = (long long)e->num_sms * mega_pf_piece();
+  long long pos = 0;
+  auto add = [&](const void* ptr, long long bytes) {
+    PfBlock b; b.ptr = (const char*)ptr; b.bytes = bytes; b.padded = (bytes + super - 1) / super * super; b.start = pos;
+    pos += b.padded; hb.push_back(b);
+  };
+  const long long kvb = (long long)e->B * e->T_enc * d * es;
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "dec.L" + std::to_string(l) + ".";
+    add(W(e, p + "qkv.w"), 3 * d * d * es); add(W(e, p + "out.w"), d * d * es); add(W(e, p + "cq.w"), d * d * es);
+    add((const char*)e->cross_kv + (long long)l * kvb, kvb); add((const char*)e->cross_kv + (long long)(L + l) * kvb, kvb);
+    add(W(e, p + "cout.w"), d * d * es); add(W(e, p + "fc1.w"), f * d * es); add(W(e, p + "fc2.w"), d * f * es);
+  }
+  add(W(e, "dec.embed"), (long long)c.vocab * d * es);
+  e->n_pf_blocks = (int)hb.size(); e->pf_total = pos;
+  CK(b200_copy_sync(e, e->pf_blocks, hb.data(), sizeof(PfBlock) * hb.size(), cudaMemcpyHostToDevice));
+  e->pf_B = e->B; e->pf_T = e->T_enc;
+  return B200ASR_OK;
+}
+
+// one cooperative launch: iteration 0 consumes first_tokens [B][first_n_new], later iterations feed back the argmax
+int run_mega(b200asr_engine* e, int n_iters, const int* first_tokens, int first_n_new, bool first_is_prefill,
+             bool want_logits) {
+  const b200asr_config& c = e->cfg;
+  RET(build_mega_tables(e));
+  MegaArgs a{};
+  a.layers = e->mega_layers; a.n_layers = c.dec_layers;
+  a.embed = W(e, "dec.embed"); a.pos = WF(e, "dec.pos"); a.ln_g = WF(e, "dec.ln.g"); a.ln_b = WF(e, "dec.ln.b");
+  a.suppress_bias = WF(e, "dec.suppress_bias"); a.begin_bias = WF(e, "dec.begin_suppress_bias");
+  a.kcache = e->kcache; a.vcache = e->vcache; a.cross_kv = e->cross_kv; a.T = e->T_enc;
+  a.batch = e->B; a.d = c.d_model; a.ffn = c.ffn; a.n_heads = c.n_heads; a.vocab = c.vocab; a.max_target = c.max_target;
+  a.x = e->dx; a.q = e->dq; a.ctx = e->dctx; a.f = e->dffn; a.logits = want_logits ? e->logits : nullptr;
+  a.first_tokens = first_tokens; a.first_n_new = first_n_new;
+  a.cur_token = e->cur_token; a.tokens = e->tokens; a.tokens_ld = c.max_target; a.n_gen = e->n_gen; a.finished = e->finished;
+  a.save_id = e->save_id; a.save_ld = c.max_target; a.n_save = e->n_save; a.selected_hist = e->selected_hist; a.sel_ld = c.max_target;
+  a.stop_ids = e->d_stop; a.n_stop = (int)e->stop_ids.size(); a.limit = e->limit;
+  a.penalty_value = e->repeat_penalty; a.penalty_range = e->penalty_range;
+  a.state = e->dstate; a.bar = e->mega_bar; a.cand_val = e->cand_val; a.cand_idx = e->cand_idx;
+  a.n_iters = n_iters; a.first_is_prefill = first_is_prefill ? 1 : 0;
+  a.pf_blocks = e->pf_blocks; a.n_pf_blocks = e->n_pf_blocks;
+  a.pf_total = e->pf_ahead > 0 ? e->pf_total : 0; a.pf_ahead = e->pf_ahead;
+  a.eps = 1e-5f;
+  CK(cudaMemsetAsync(e->mega_bar, 0, 64, e->st));
+  KL(launch_decoder_mega(a, e->act_dtype, e->num_sms, e->st));
+  return B200ASR_OK;
+}
+
 int do_upload(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples) {
   const b200asr_config& c = e->cfg;
   if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
@@ -359,7 +448,7 @@ int do_upload(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_
   return B200ASR_OK;
 }
 
-int do_prefill(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt) {
+int do_prefill(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt, int extra_iters = 0) {
   const b200asr_config& c = e->cfg;
   if (!e->encoded) return e->fail(B200ASR_E_INVALID, "prefill before encode");
   if (!prompt_ids || n_prompt <= 0 || n_prompt >= c.max_target) return e->fail(B200ASR_E_INVALID, "bad prompt");
@@ -373,7 +462,12 @@ int do_prefill(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt) {
   // generate_limit = MAX_SEQ_LEN - prompt length (Inference_Whisper_ONNX.py:821), optionally tightened
   e->limit = c.max_target - n_prompt;
   if (e->limit_cfg > 0 && e->limit_cfg < e->limit) e->limit = e->limit_cfg;
-  RET(enqueue_decoder(e, e->d_prompt, n_prompt, true));
+  if (extra_iters < 0) {          // caller only wanted the reset (it launches the fused prefill+decode itself)
+    e->prefilled = true;
+    return B200ASR_OK;
+  }
+  if (mega_ok(e, n_prompt)) RET(run_mega(e, 1 + extra_iters, e->d_prompt, n_prompt, true, true));
+  else RET(enqueue_decoder(e, e->d_prompt, n_prompt, true));
   e->prefilled = true;
   return B200ASR_OK;
 }
@@ -434,7 +528,8 @@ void b200asr_destroy(b200asr_engine* e) {
   void* bufs[] = {e->stage_buf, e->basis_t, e->fb_start, e->fb_len, e->pcm, e->mel_raw, e->max_key, e->mel_pad, e->h1_pad,
                   e->hidden, e->stem, e->xhat, e->qkv, e->ctx, e->ffn, e->S, e->P, e->cross_kv, e->kcache, e->vcache,
                   e->dx, e->dq, e->dctx, e->dffn, e->logits, e->prob, e->d_prompt, e->cur_token, e->tokens, e->n_gen,
-                  e->finished, e->save_id, e->n_save, e->selected_hist, e->d_stop, e->dstate};
+                  e->finished, e->save_id, e->n_save, e->selected_hist, e->d_stop, e->dstate, e->mega_layers, e->pf_blocks,
+                  e->mega_bar, e->cand_val, e->cand_idx};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -444,6 +539,8 @@ void b200asr_destroy(b200asr_engine* e) {
 int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!e || !key) return B200ASR_E_INVALID;
   if (!strcmp(key, "keep_stages")) { e->keep_stages = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "mega")) { e->use_mega = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "pf_ahead_mb")) { e->pf_ahead = (long long)value << 20; return B200ASR_OK; }
   return e->fail(B200ASR_E_INVALID, std::string("unknown option ") + key);
 }
 
@@ -634,13 +731,15 @@ int b200asr_decode_step(b200asr_engine* e, const int32_t* token_in, float* logit
   CK(cudaStreamSynchronize(e->st));
   if (hs.kv_len + 1 > e->cfg.max_target) return e->fail(B200ASR_E_INVALID, "KV cache full");
   if (token_in) CK(cudaMemcpyAsync(e->cur_token, token_in, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->st));
-  RET(launch_step(e));
+  if (mega_ok(e, 1)) RET(run_mega(e, 1, e->cur_token, 1, false, true));
+  else RET(launch_step(e));
   if (logits_out) CK(cudaMemcpyAsync(logits_out, e->logits, (size_t)e->B * e->cfg.vocab * 4, cudaMemcpyDeviceToHost, e->st));
   if (token_out) CK(cudaMemcpyAsync(token_out, e->cur_token, (size_t)e->B * 4, cudaMemcpyDeviceToHost, e->st));
   CK(cudaStreamSynchronize(e->st));
   return B200ASR_OK;
 }
 
+static int fetch_tokens(b200asr_engine* e, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
 static int decode_loop(b200asr_engine* e, int max_steps, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
   const b200asr_config& c = e->cfg;
   if (!e->prefilled) return e->fail(B200ASR_E_INVALID, "decode before prefill");
@@ -651,14 +750,23 @@ static int decode_loop(b200asr_engine* e, int max_steps, int32_t* tokens_out, in
   const int room = c.max_target - e->n_prompt;    // cache positions left after the prompt
   if (steps > room) steps = room;
   int* h_done = e->h_pinned;
-  for (int s = 0; s < steps; ++s) {
-    RET(launch_step(e));
-    if (!e->stop_ids.empty() && (s % 8) == 7 && s + 1 < steps) {
-      CK(cudaMemcpyAsync(h_done, &e->dstate->all_done, 4, cudaMemcpyDeviceToHost, e->st));
-      CK(cudaStreamSynchronize(e->st));
-      if (*h_done) break;
+  if (steps > 0 && mega_ok(e, 1)) {
+    RET(run_mega(e, steps, e->cur_token, 1, false, false));     // the kernel leaves the loop itself when all latched
+  } else {
+    for (int s = 0; s < steps; ++s) {
+      RET(launch_step(e));
+      if (!e->stop_ids.empty() && (s % 8) == 7 && s + 1 < steps) {
+        CK(cudaMemcpyAsync(h_done, &e->dstate->all_done, 4, cudaMemcpyDeviceToHost, e->st));
+        CK(cudaStreamSynchronize(e->st));
+        if (*h_done) break;
+      }
     }
   }
+  return fetch_tokens(e, tokens_out, tokens_ld, lens_out);
+}
+
+static int fetch_tokens(b200asr_engine* e, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  const b200asr_config& c = e->cfg;
   const int B = e->B;
   int* h_len = e->h_pinned + 64;
   int* h_tok = h_len + B;
@@ -707,9 +815,18 @@ int b200asr_transcribe_resident(b200asr_engine* e, const int32_t* prompt_ids, in
   if (e->B <= 0) return e->fail(B200ASR_E_INVALID, "no PCM uploaded");
   if (n_prompt > 8) return e->fail(B200ASR_E_INVALID, "prompt longer than 8 tokens");
   RET(run_encoder(e));
+  if (!tokens_out || !lens_out || tokens_ld <= 0) return e->fail(B200ASR_E_INVALID, "null output");
   const int saved = e->limit_cfg;
   if (max_new > 0 && (saved == 0 || max_new < saved)) e->limit_cfg = max_new;
-  int r = do_prefill(e, prompt_ids, n_prompt);
+  int r;
+  if (mega_ok(e, n_prompt)) {
+    r = do_prefill(e, prompt_ids, n_prompt, -1);                 // reset + upload the prompt only
+    if (r == B200ASR_OK) r = run_mega(e, e->limit, e->d_prompt, n_prompt, true, false);   // prefill + (limit-1) decode launches
+    e->limit_cfg = saved;
+    RET(r);
+    return fetch_tokens(e, tokens_out, tokens_ld, lens_out);
+  }
+  r = do_prefill(e, prompt_ids, n_prompt);
   e->limit_cfg = saved;
   RET(r);
   return decode_loop(e, -1, tokens_out, tokens_ld, lens_out);
@@ -767,13 +884,13 @@ int b200asr_get_stage(b200asr_engine* e, const char* name_c, float* out, int64_t
     RET(fetch(e->cross_kv, B * T * 2 * L * d, e->act_dtype, h));
     n = B * L * H * T * 64;
     if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
-    const int64_t off = name == "cross_v" ? L * d : 0;
+    const int64_t zoff = name == "cross_v" ? L : 0;
     for (int64_t b = 0; b < B; ++b)
       for (int64_t l = 0; l < L; ++l)
         for (int64_t hh = 0; hh < H; ++hh)
           for (int64_t t = 0; t < T; ++t)
             memcpy(out + ((((b * L + l) * H + hh) * T + t) * 64),
-                   h.data() + (size_t)((b * T + t) * 2 * L * d + off + l * d + hh * 64), 64 * 4);
+                   h.data() + (size_t)((((zoff + l) * B + b) * T + t) * d + hh * 64), 64 * 4);
   } else if (name == "self_k" || name == "self_v") {        // -> [L][B][H][kv][64]
     DecState hs;
     CK(b200_copy_sync(e, &hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost));

@@ -80,7 +80,7 @@ gemm_simt_kernel(GemmArgs g) {
       const int gn = n0 + tx * 4 + j;
       if (gn >= g.N) continue;
       float v = acc[i][j];
-      if (g.bias) v += g.bias[gn];
+      if (g.bias) v += g.bias[(int64_t)z * g.sBias + gn];
       if (g.act == kActGelu) v = gelu_erf(v);
       if (R) v += R[(int64_t)gm * g.ldr + gn];
       C[(int64_t)gm * g.ldc + gn] = from_f<TC>(v);

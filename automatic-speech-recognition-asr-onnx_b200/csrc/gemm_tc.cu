@@ -33,7 +33,8 @@ struct EpiArgs {
   int act;
   int M, N, K, batch;
   int tiles_m, tiles_n;
-  int b_batched;
+  int a_batched, b_batched;
+  int64_t sBias;
 };
 
 // ---------------------------------------------------------------------------
@@ -169,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kStageBytesA;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_3d(sa, &tmA, kb * BK, m0, z, &full_bar[stage]);
+          tma_load_3d(sa, &tmA, kb * BK, m0, e.a_batched ? z : 0, &full_bar[stage]);
           tma_load_3d(sb, &tmB, kb * BK, n0, e.b_batched ? z : 0, &full_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -227,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         const int col = n0 + c0 + lane;
         if (col < e.N) {
-          const float bv = e.bias ? e.bias[col] : 0.f;
+          const float bv = e.bias ? e.bias[(int64_t)z * e.sBias + col] : 0.f;
           for (int rr = 0; rr < rows_here; ++rr) {
             const int64_t row = m0 + rr;
             float v = my[rr * 33 + lane] + bv;
@@ -313,14 +314,15 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t st, st
     attr_done = true;
   }
   CUtensorMap tmA, tmB;
-  if (!make_tmap(&tmA, g.A, g.K, g.M, g.batch, g.lda, g.sAo, BM, err)) return cudaErrorNotSupported;
+  const bool a_batched = g.sAo != 0 && g.batch > 1;
+  if (!make_tmap(&tmA, g.A, g.K, g.M, a_batched ? g.batch : 1, g.lda, g.sAo, BM, err)) return cudaErrorNotSupported;
   const bool b_batched = g.sBo != 0 && g.batch > 1;
   if (!make_tmap(&tmB, g.B, g.K, g.N, b_batched ? g.batch : 1, g.ldb, g.sBo, BN, err)) return cudaErrorNotSupported;
   EpiArgs e;
   e.C = g.C; e.ldc = g.ldc; e.sC = g.sCo; e.c_dtype = g.c_dtype;
   e.bias = g.bias; e.residual = g.residual; e.ldr = g.ldr; e.sR = g.sRo; e.act = g.act;
   e.M = g.M; e.N = g.N; e.K = g.K; e.batch = g.batch;
-  e.tiles_m = (g.M + BM - 1) / BM; e.tiles_n = (g.N + BN - 1) / BN; e.b_batched = b_batched ? 1 : 0;
+  e.tiles_m = (g.M + BM - 1) / BM; e.tiles_n = (g.N + BN - 1) / BN; e.a_batched = a_batched ? 1 : 0; e.b_batched = b_batched ? 1 : 0; e.sBias = g.sBias;
   const int tiles = e.tiles_m * e.tiles_n * g.batch;
   const int grid = tiles < num_sms ? tiles : num_sms;
   gemm_tc_kernel<BN><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, e);
