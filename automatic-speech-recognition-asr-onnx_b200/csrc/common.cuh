@@ -160,6 +160,7 @@ struct MegaArgs {
   int n_iters; int first_is_prefill;     // begin-suppress bias applies to iteration 0 only when set
   const PfBlock* pf_blocks; int n_pf_blocks; long long pf_total; long long pf_ahead;
   float eps;
+  unsigned long long* timing; int timing_cap;   // optional: globaltimer after every grid barrier (block 0)
 };
 
 size_t mega_smem_bytes(int d, int ffn, int T, int max_target);

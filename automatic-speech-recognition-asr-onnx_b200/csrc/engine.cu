@@ -71,10 +71,11 @@ struct b200asr_engine {
   int n_prompt = 0; bool prefilled = false; bool encoded = false;
   cudaGraphExec_t step_graph = nullptr; int64_t step_graph_nodes = 0;
   // persistent decoder kernel state
-  bool use_mega = true; long long pf_ahead = 32ll << 20;
+  bool use_mega = true; long long pf_ahead = 0;
   MegaLayer* mega_layers = nullptr; PfBlock* pf_blocks = nullptr; int n_pf_blocks = 0; long long pf_total = 0;
   int pf_B = -1, pf_T = -1;
   unsigned int* mega_bar = nullptr; float* cand_val = nullptr; int* cand_idx = nullptr;
+  bool mega_timing = false; unsigned long long* timing = nullptr; static constexpr int kTimingCap = 16384;
   std::string graph_key;
 
   int fail(int code, const std::string& m) { err = m; return code; }
@@ -427,6 +428,12 @@ int run_mega(b200asr_engine* e, int n_iters, const int* first_tokens, int first_
   a.pf_blocks = e->pf_blocks; a.n_pf_blocks = e->n_pf_blocks;
   a.pf_total = e->pf_ahead > 0 ? e->pf_total : 0; a.pf_ahead = e->pf_ahead;
   a.eps = 1e-5f;
+  a.timing = nullptr; a.timing_cap = 0;
+  if (e->mega_timing) {
+    if (!e->timing) CK(cudaMalloc(&e->timing, sizeof(unsigned long long) * b200asr_engine::kTimingCap));
+    CK(cudaMemsetAsync(e->timing, 0, sizeof(unsigned long long) * b200asr_engine::kTimingCap, e->st));
+    a.timing = e->timing; a.timing_cap = b200asr_engine::kTimingCap;
+  }
   CK(cudaMemsetAsync(e->mega_bar, 0, 64, e->st));
   KL(launch_decoder_mega(a, e->act_dtype, e->num_sms, e->st));
   return B200ASR_OK;
@@ -529,7 +536,7 @@ void b200asr_destroy(b200asr_engine* e) {
                   e->hidden, e->stem, e->xhat, e->qkv, e->ctx, e->ffn, e->S, e->P, e->cross_kv, e->kcache, e->vcache,
                   e->dx, e->dq, e->dctx, e->dffn, e->logits, e->prob, e->d_prompt, e->cur_token, e->tokens, e->n_gen,
                   e->finished, e->save_id, e->n_save, e->selected_hist, e->d_stop, e->dstate, e->mega_layers, e->pf_blocks,
-                  e->mega_bar, e->cand_val, e->cand_idx};
+                  e->mega_bar, e->cand_val, e->cand_idx, e->timing};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -539,6 +546,7 @@ void b200asr_destroy(b200asr_engine* e) {
 int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!e || !key) return B200ASR_E_INVALID;
   if (!strcmp(key, "keep_stages")) { e->keep_stages = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "mega_timing")) { e->mega_timing = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "mega")) { e->use_mega = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "pf_ahead_mb")) { e->pf_ahead = (long long)value << 20; return B200ASR_OK; }
   return e->fail(B200ASR_E_INVALID, std::string("unknown option ") + key);
@@ -903,6 +911,12 @@ int b200asr_get_stage(b200asr_engine* e, const char* name_c, float* out, int64_t
       for (int64_t bh = 0; bh < Bm * H; ++bh)
         memcpy(out + (size_t)((l * Bm * H + bh) * kv * 64), h.data() + (size_t)(bh * mt * 64), (size_t)kv * 64 * 4);
     }
+  } else if (name == "mega_timing") {                       // us between consecutive grid barriers of the last launch
+    if (!e->timing) return e->fail(B200ASR_E_INVALID, "set option mega_timing=1 first");
+    std::vector<unsigned long long> ht(b200asr_engine::kTimingCap);
+    CK(b200_copy_sync(e, ht.data(), e->timing, ht.size() * 8, cudaMemcpyDeviceToHost));
+    n = 0;
+    for (size_t i = 1; i < ht.size() && ht[i] != 0 && n < capacity; ++i) out[n++] = (float)((double)(ht[i] - ht[i - 1]) * 1e-3);
   } else if (name == "selected") {                          // [B][step] as float
     DecState hs;
     CK(b200_copy_sync(e, &hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost));
