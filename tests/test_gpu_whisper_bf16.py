@@ -39,6 +39,23 @@ def test_bf16_tc_logits(path):
     eng.close()
 
 
+def test_bf16_mega_vs_stepgraph_decoder():
+    """Same bf16 weights through the persistent kernel and through the per-op kernels."""
+    g, raw, tensors = load_case(GOLD[1])
+    outs = []
+    for mega in (1, 0):
+        eng = make_engine(tensors, "bf16")
+        eng.set_option("mega", mega)
+        outs.append(_run(eng, g["pcm"], g["prompt"], g["forced_tokens"].tolist()))
+        eng.set_decode_options(stop_ids=[], generate_limit=7)
+        outs.append(eng.transcribe(g["pcm"], g["prompt"], max_new=7))
+        eng.close()
+    d = maxdiff(outs[0], outs[2])
+    print("mega vs stepgraph max |dlogit| =", d)
+    assert d <= 5e-3
+    assert outs[1] == outs[3]
+
+
 def test_bf16_tc_vs_simt_engine():
     g, raw, tensors = load_case(GOLD[0])
     a = make_engine(tensors, "bf16", tc=True)

@@ -8,11 +8,17 @@ from gpu_common import GOLD, NO_SPEECH, load_case, make_engine, maxdiff
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=GOLD, ids=[p.stem for p in GOLD])
+CASES = [(p, mega) for p in GOLD for mega in (1, 0)]
+
+
+@pytest.fixture(scope="module", params=CASES, ids=[f"{p.stem}-{'mega' if m else 'stepgraph'}" for p, m in CASES])
 def ctx(request):
-    g, raw, tensors = load_case(request.param)
+    """mega=1: persistent decoder kernel (decoder_mega.cu); mega=0: per-op kernels in a CUDA graph (decoder.cu)."""
+    path, mega = request.param
+    g, raw, tensors = load_case(path)
     eng = make_engine(tensors, "f32")
     eng.set_option("keep_stages", 1)
+    eng.set_option("mega", mega)
     yield g, eng
     eng.close()
 
