@@ -229,14 +229,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col = n0 + c0 + lane;
         if (col < e.N) {
           const float bv = e.bias ? e.bias[(int64_t)z * e.sBias + col] : 0.f;
-          for (int rr = 0; rr < rows_here; ++rr) {
-            const int64_t row = m0 + rr;
-            float v = my[rr * 33 + lane] + bv;
-            if (e.act == kActGelu) v = gelu_erf(v);
-            if (e.residual) v += e.residual[(int64_t)z * e.sR + row * e.ldr + col];
-            const int64_t o = (int64_t)z * e.sC + row * e.ldc + col;
-            if (e.c_dtype == kF32) reinterpret_cast<float*>(e.C)[o] = v;
-            else reinterpret_cast<bf16*>(e.C)[o] = __float2bfloat16_rn(v);
+          // residual may alias C (in-place residual add), so the compiler cannot hoist these loads past the
+          // stores below: fetch the whole column strip first (32 independent loads in flight, not 32 round trips)
+          float res[32];
+          if (e.residual) {
+            const float* rp = e.residual + (int64_t)z * e.sR + (int64_t)m0 * e.ldr + col;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) res[rr] = rr < rows_here ? rp[(int64_t)rr * e.ldr] : 0.f;
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) res[rr] = 0.f;
+          }
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr < rows_here) {
+              const int64_t row = m0 + rr;
+              float v = my[rr * 33 + lane] + bv;
+              if (e.act == kActGelu) v = gelu_erf(v);
+              v += res[rr];
+              const int64_t o = (int64_t)z * e.sC + row * e.ldc + col;
+              if (e.c_dtype == kF32) reinterpret_cast<float*>(e.C)[o] = v;
+              else reinterpret_cast<bf16*>(e.C)[o] = __float2bfloat16_rn(v);
+            }
           }
         }
         __syncwarp();
