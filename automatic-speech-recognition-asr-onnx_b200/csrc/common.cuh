@@ -168,4 +168,25 @@ bool mega_supported(int batch, int first_n_new, int d, int ffn);
 int mega_pf_piece();
 cudaError_t launch_decoder_mega(const MegaArgs& a, int w_dtype, int num_sms, cudaStream_t st);
 
+// decoder_ring.cu: streaming greedy-decode kernel (TMA weight ring + flag-in-data exchanges); bf16, batch <= 4
+struct RingArgs {
+  MegaArgs m;
+  unsigned long long* ll; long long ll_stride;   // 4 exchange buffers of ll_stride 8-byte words each (zeroed per launch)
+  int ld_vec;                                    // words per utterance row in an exchange buffer
+  int n_stages, stage_bytes;                     // shared-memory ring
+  int task_inv;                                  // inverse (mod grid) of the attention-task -> CTA stride
+  int part_cap, sc_cap;
+  int debug;                                     // timing experiments: skip parts of a phase (see decoder_ring.cu)
+  int fine_timing;                               // stamp inside linear phases too (after gather / LN / ring / publish)
+};
+constexpr int kRingTaskMul = 7;                  // task t of layer l -> CTA (t * 7 + offset(l)) % grid
+bool ring_supported(int batch, int d, int ffn, int n_heads, int vocab, int num_sms);
+bool ring_plan(const MegaArgs& a, int num_sms, RingArgs* ra, size_t* smem_bytes);
+size_t ring_exchange_words(int batch, int d, int ffn, int num_sms);
+cudaError_t launch_decoder_ring(const RingArgs& ra, const CUtensorMap& cross_map, int num_sms, size_t smem_bytes,
+                                cudaStream_t st);
+// gemm_tc.cu: plain (unswizzled) 2-D bf16 tensor map over [rows][ld] with a [box_rows][box_cols] box
+bool make_tmap_2d_plain(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_cols,
+                        int box_rows, std::string* err);
+
 }  // namespace b200asr

@@ -1,0 +1,878 @@
+// Streaming greedy-decode kernel ("ring"): the whole decode loop of
+// /root/reference/Whisper/Inference_Whisper_ONNX.py:584-663 (one DECODE_SESSION launch
+// per token, 64 KV rebinds, `.numpy()` sync) as ONE cooperative launch, like
+// decoder_mega.cu, but organised so that the HBM stream never waits on the token's
+// dependency chain:
+//
+//   * one producer lane per CTA walks the CTA's static share of the per-token read
+//     stream (its rows of every weight matrix of WHISPER_DECODER.forward,
+//     /root/reference/Whisper/Export_Whisper.py:614-667, plus the cross-attention K/V
+//     tiles of the (utterance, head) tasks it owns) and copies it into a shared-memory
+//     ring with cp.async.bulk / cp.async.bulk.tensor (TMA) + mbarrier complete_tx,
+//     running ahead of the consumers by the ring's capacity, across phase and token
+//     boundaries;
+//   * 16 consumer warps take stages off the ring (half a d-wide weight segment per
+//     warp), so a phase's critical path is: poll the input vector -> LayerNorm in
+//     shared memory -> dot products against weights that are already on chip ->
+//     publish;
+//   * phases exchange their (tiny) activation vectors through L2 with flag-in-data
+//     words (value, sequence number) written by one 64-bit store and polled by one
+//     64-bit load -- no grid barrier, no fence on the critical path (decoder_mega.cu
+//     pays ~2 us barrier + ~0.7 us reload per phase, 257 phases per token).
+//
+// bf16 weights / KV, fp32 activations and accumulation; batch <= 4 utterances, one new
+// token per utterance per iteration (the multi-token prefill stays in decoder_mega.cu).
+#include "common.cuh"
+#include <algorithm>
+#include <cstdio>
+
+namespace b200asr {
+
+constexpr int kRingConsumerWarps = 16;
+constexpr int kRingConsumers = kRingConsumerWarps * 32;     // 512
+constexpr int kRingThreads = kRingConsumers + 32;           // + producer warp
+constexpr int kRingMaxStages = 16;
+constexpr int kSegPerStage = 8;                             // d-wide weight segments per ring stage
+constexpr long long kSpinLimit = 6000000000LL;              // ~3 s at 2 GHz: a protocol bug traps instead of hanging
+
+// ---------------------------------------------------------------------------
+// PTX wrappers (local to this file)
+// ---------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint32_t rs_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void rbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void rbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rs_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rs_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool rbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(rs_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void rbar_wait(uint64_t* bar, uint32_t parity) {
+  if (rbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!rbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kSpinLimit) {
+      printf("b200asr decoder_ring: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+// contiguous global -> shared bulk copy, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(rs_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(rs_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_g2s_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(rs_u32(smem_dst)), "l"(tm), "r"(rs_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// named barrier over the 512 consumer threads (the producer warp never joins it)
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(kRingConsumers) : "memory"); }
+
+// flag-in-data exchange word: low 32 bits = fp32 (or int) payload, high 32 bits = sequence number
+__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned payload, unsigned seq) {
+  const unsigned long long v = ((unsigned long long)seq << 32) | payload;
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __noinline__ unsigned ll_spin(const unsigned long long* p, unsigned seq) {
+  const long long t0 = clock64();
+  for (;;) {
+    const unsigned long long v = ll_load(p);
+    if ((unsigned)(v >> 32) == seq) return (unsigned)v;
+    if (clock64() - t0 > kSpinLimit) {
+      printf("b200asr decoder_ring: exchange wait timed out (block %d thread %d seq %u saw %u)\n", blockIdx.x,
+             threadIdx.x, seq, (unsigned)(v >> 32));
+      __trap();
+    }
+  }
+}
+// gather n exchange words of sequence `seq` into fp32 shared memory; `tid` in [0, nthr)
+__device__ __forceinline__ void ll_gather(const unsigned long long* src, int n, unsigned seq, float* dst, int tid, int nthr,
+                                          bool nospin = false) {
+  constexpr int U = 4;
+  for (int i0 = tid; i0 < n; i0 += nthr * U) {
+    unsigned long long v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int i = i0 + u * nthr; if (i < n) v[u] = ll_load(src + i); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * nthr;
+      if (i < n) {
+        unsigned pay = (unsigned)v[u];
+        if ((unsigned)(v[u] >> 32) != seq && !nospin) pay = ll_spin(src + i, seq);
+        dst[i] = __uint_as_float(pay);
+      }
+    }
+  }
+}
+
+struct Pipe { int stage; uint32_t phase; };
+__device__ __forceinline__ void pipe_advance(Pipe& p, int n_stages) {
+  if (++p.stage == n_stages) { p.stage = 0; p.phase ^= 1; }
+}
+
+// balanced split of N output columns over the grid: every CTA owns floor(N/G) or ceil(N/G) of them
+__device__ __forceinline__ void col_split(int N, int& n0, int& cnt) {
+  const int G = gridDim.x, c = blockIdx.x;
+  const int q = N / G, r = N - q * G;
+  cnt = q + (c < r ? 1 : 0);
+  n0 = c * q + min(c, r);
+}
+
+enum RIn { kRInLocal = 0, kRInX = 1, kRInVec = 2 };
+enum ROut { kROutVec = 0, kROutResid = 1, kROutHead = 2 };
+
+struct RLin {
+  const bf16* W; const float* bias; int N, K;
+  int in_mode, ln_mode; const float* gamma; const float* beta;
+  int act, out_mode;
+};
+
+__device__ __forceinline__ RLin ring_lin(const MegaArgs& a, int l, int ph) {
+  const int d = a.d;
+  if (ph == 8)
+    return RLin{reinterpret_cast<const bf16*>(a.embed), a.suppress_bias, a.vocab, d, kRInX, 2, a.ln_g, a.ln_b, kActNone, kROutHead};
+  const MegaLayer& w = a.layers[l];
+  switch (ph) {
+    case 0: return RLin{(const bf16*)w.qkv_w, w.qkv_b, 3 * d, d, l == 0 ? kRInLocal : kRInX, 1, nullptr, nullptr, kActNone, kROutVec};
+    case 2: return RLin{(const bf16*)w.out_w, w.out_b, d, d, kRInVec, 0, nullptr, nullptr, kActNone, kROutResid};
+    case 3: return RLin{(const bf16*)w.cq_w, w.cq_b, d, d, kRInX, 1, nullptr, nullptr, kActNone, kROutVec};
+    case 5: return RLin{(const bf16*)w.cout_w, w.cout_b, d, d, kRInVec, 0, nullptr, nullptr, kActNone, kROutResid};
+    case 6: return RLin{(const bf16*)w.fc1_w, w.fc1_b, a.ffn, d, kRInX, 1, nullptr, nullptr, kActGelu, kROutVec};
+    default: return RLin{(const bf16*)w.fc2_w, w.fc2_b, d, a.ffn, kRInVec, 0, nullptr, nullptr, kActNone, kROutResid};
+  }
+}
+
+// (utterance, head) attention task owned by this CTA in layer l (kind 0 self, 1 cross), or -1
+__device__ __forceinline__ int my_task(const RingArgs& ra, int l, int kind, int ntask) {
+  const int G = gridDim.x;
+  const int off = (l * 37 + (kind ? G / 2 : 0)) % G;
+  const int rel = ((int)blockIdx.x - off + G) % G;
+  const int t = (int)(((long long)rel * ra.task_inv) % G);
+  return t < ntask ? t : -1;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+template <int NR, bool DBG>
+__global__ void __launch_bounds__(kRingThreads, 1)
+decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_constant__ RingArgs ra) {
+  const MegaArgs& a = ra.m;
+  extern __shared__ __align__(128) uint8_t smem_raw[];     // no integer round trip: keeps the shared address space visible
+  uint8_t* ring = smem_raw;
+  const int d = a.d, ffn = a.ffn, B = a.batch, H = a.n_heads, T = a.T;
+  const int SB = ra.stage_bytes, NS = ra.n_stages;
+  const int kmax = d > ffn ? d : ffn;
+  float* xs = reinterpret_cast<float*>(ring + (size_t)NS * SB);      // [NR][kmax]   staged (normalised) input rows
+  float* xloc = xs + (size_t)NR * kmax;                              // [NR][d]      this CTA's copy of the residual stream
+  float* part = xloc + (size_t)NR * d;                               // [part_cap][NR] per-(segment, half) partial dots
+  float* sc = part + (size_t)ra.part_cap * NR;                       // [sc_cap]     attention scores
+  float* qs = sc + ra.sc_cap;                                        // [64]
+  float* opart = qs + 64;                                            // [16][64]
+  float* cand = opart + kRingConsumerWarps * 64;                     // [G][NR][2]
+
+  __shared__ uint64_t full_bar[kRingMaxStages], empty_bar[kRingMaxStages];
+  __shared__ float wbest_v[kRingConsumerWarps * 4];
+  __shared__ int wbest_i[kRingConsumerWarps * 4];
+  __shared__ int s_tok[4], s_ngen[4], s_fin[4], s_nsave[4];
+  __shared__ int s_pen[4 * 32];
+  __shared__ int s_hist[4 * 32];                   // last 32 selected ids per utterance (circular, index = n_save % 32)
+  __shared__ int s_pen_n, s_all_done;
+  __shared__ volatile int s_stop;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x;
+  const int L = a.n_layers;
+  const int R = SB / 128;                          // cross-attention rows per ring stage
+  const int nbox = (T + R - 1) / R;
+  const int ntask = B * H;
+  const int dbg = DBG ? ra.debug : 0;              // timing experiments only (results are garbage when set)
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { rbar_init(&full_bar[s], 1); rbar_init(&empty_bar[s], kRingConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&cross_map) : "memory");
+    s_stop = 0;
+  }
+  if (tid < B) {
+    s_ngen[tid] = a.n_gen[tid]; s_fin[tid] = a.finished[tid]; s_nsave[tid] = a.n_save[tid]; s_tok[tid] = a.first_tokens[tid];
+    // selection history written by earlier launches; ids selected inside this launch are tracked in shared memory
+    // by every CTA (other CTAs' plain global stores are not visible through this SM's L1)
+    const int ns = a.n_save[tid];
+    for (int j = max(0, ns - 32); j < ns; ++j) s_hist[tid * 32 + (j & 31)] = a.save_id[(long long)tid * a.save_ld + j];
+  }
+  __syncthreads();
+
+  // =========================================================================
+  // producer: one lane streams this CTA's share of every token's read stream
+  // =========================================================================
+  if (warp == kRingConsumerWarps) {
+    if (lane == 0) {
+      Pipe p{0, 0};
+      long long issued = 0;
+      bool stop = false;
+      auto acquire = [&]() -> bool {           // wait until the consumers released ring slot p.stage
+        if (rbar_try_wait(&empty_bar[p.stage], p.phase ^ 1)) return true;
+        const long long t0 = clock64();
+        while (!rbar_try_wait(&empty_bar[p.stage], p.phase ^ 1)) {
+          if (s_stop) return false;
+          if (clock64() - t0 > kSpinLimit) { printf("b200asr decoder_ring: producer stalled (block %d)\n", blockIdx.x); __trap(); }
+        }
+        return true;
+      };
+      auto stream_rows = [&](const bf16* W, int N, int K) {
+        int n0, cnt; col_split(N, n0, cnt);
+        const char* src = reinterpret_cast<const char*>(W + (long long)n0 * K);
+        const long long bytes = (long long)cnt * K * 2;
+        for (long long off = 0; off < bytes && !stop; off += SB) {
+          if (s_stop || !acquire()) { stop = true; break; }
+          const uint32_t n = (uint32_t)min((long long)SB, bytes - off);
+          rbar_expect_tx(&full_bar[p.stage], n);
+          bulk_g2s(ring + (size_t)p.stage * SB, src + off, n, &full_bar[p.stage]);
+          ++issued; pipe_advance(p, NS);
+        }
+      };
+      // one call site per helper: the phases run one after the other, so every inlined copy of a phase body
+      // would be a separate, cold stretch of the instruction stream
+      const int n_phases = 8 * L + 1;
+      for (int iter = 0; iter < a.n_iters && !stop; ++iter) {
+        for (int idx = 0; idx < n_phases && !stop; ++idx) {
+          const int l = idx >> 3;
+          const int ph = (idx == n_phases - 1) ? 8 : (idx & 7);
+          if (ph == 1) continue;                    // self-attention reads the resident cache directly
+          if (ph == 4) {
+            const int t = (dbg & 16) ? -1 : my_task(ra, l, 1, ntask);
+            if (t < 0) continue;
+            const int b = t / H, h = t - b * H;
+            for (int i = 0; i < 2 * nbox; ++i) {
+              const int kind = i >= nbox ? 1 : 0;
+              const int row0 = ((kind * L + l) * B + b) * T + (i - kind * nbox) * R;
+              if (s_stop || !acquire()) { stop = true; break; }
+              rbar_expect_tx(&full_bar[p.stage], (uint32_t)SB);
+              tma_g2s_2d(ring + (size_t)p.stage * SB, &cross_map, h * 64, row0, &full_bar[p.stage]);
+              ++issued; pipe_advance(p, NS);
+            }
+            continue;
+          }
+          if (dbg & 8) continue;
+          const RLin Lp = ring_lin(a, l, ph);
+          stream_rows(Lp.W, Lp.N, Lp.K);
+        }
+      }
+      // drain: every copy that was issued must have landed before the CTA may exit
+      for (int s = 0; s < NS; ++s) {
+        if (issued > s) {
+          const uint32_t par = (s < p.stage) ? p.phase : (p.phase ^ 1);
+          rbar_wait(&full_bar[s], par);
+        }
+      }
+    }
+    __syncthreads();
+    return;
+  }
+
+  // =========================================================================
+  // consumers
+  // =========================================================================
+  Pipe pipe{0, 0};
+  unsigned seq = 1;                                // sequence number of the NEXT exchange to be published
+  int kv_len = a.state->kv_len;
+  int step = a.state->step;
+  int t_idx = 0;
+  auto stamp = [&]() {
+    if (DBG && a.timing && blockIdx.x == 0 && tid == 0 && t_idx < a.timing_cap) {
+      unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.timing[t_idx++] = t;
+    }
+  };
+  auto fstamp = [&]() { if (DBG && ra.fine_timing) stamp(); };
+  auto exbuf = [&](unsigned e) -> unsigned long long* { return ra.ll + (size_t)(e & 3u) * ra.ll_stride; };
+  stamp();
+
+  // token embedding + learned position of the fed-back token -> xloc (every CTA, redundantly)
+  auto embed_rows = [&]() {
+    for (int r = 0; r < B; ++r) {
+      const bf16* er = reinterpret_cast<const bf16*>(a.embed) + (long long)s_tok[r] * d;
+      const float* pr = a.pos + (long long)kv_len * d;
+      for (int k = tid * 2; k < d; k += kRingConsumers * 2) {
+        const float2 e2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(er + k));
+        const float2 p2 = *reinterpret_cast<const float2*>(pr + k);
+        xloc[r * d + k] = p2.x + e2.x;
+        xloc[r * d + k + 1] = p2.y + e2.y;
+      }
+    }
+  };
+
+  // ---- one skinny linear phase ------------------------------------------------------------
+  auto linear_phase = [&](const RLin& Lp, bool pen_on) {
+    const int K = Lp.K;
+    int n0, cnt; col_split(Lp.N, n0, cnt);
+    const int kq = K / d;                          // d-wide segments per weight row
+    const unsigned long long* in = exbuf(seq - 1);
+    // epilogue operands fetched before the wait so their latency hides behind it
+    float bias_v = 0.f;
+    if (Lp.out_mode != kROutHead && tid < cnt * NR && Lp.bias) bias_v = Lp.bias[n0 + tid / NR];
+    // ---- input ----
+    constexpr int GV = 4;                          // values of one d-wide row a thread stages (d <= 2048)
+    if (Lp.in_mode == kRInVec) {
+      for (int r = 0; r < B; ++r) ll_gather(in + (size_t)r * ra.ld_vec, K, seq - 1, xs + (size_t)r * K, tid, kRingConsumers, dbg & 1);
+      for (int r = B; r < NR; ++r) for (int k = tid; k < K; k += kRingConsumers) xs[(size_t)r * K + k] = 0.f;
+      csync();
+      fstamp();
+    } else {
+      // residual-stream rows: gather (or reuse the local copy) into registers, two-pass LayerNorm with one
+      // cross-warp exchange per pass, normalised rows into xs.  K == d for every phase that takes this path.
+      float xv[NR][GV];
+      if (Lp.in_mode == kRInX) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          if (r < B) {
+            const unsigned long long* src = in + (size_t)r * ra.ld_vec;
+            unsigned long long w[GV];
+#pragma unroll
+            for (int u = 0; u < GV; ++u) { const int k = tid + u * kRingConsumers; if (k < d) w[u] = ll_load(src + k); }
+#pragma unroll
+            for (int u = 0; u < GV; ++u) {
+              const int k = tid + u * kRingConsumers;
+              xv[r][u] = 0.f;
+              if (k < d) {
+                unsigned pay = (unsigned)w[u];
+                if ((unsigned)(w[u] >> 32) != seq - 1 && !(dbg & 1)) pay = ll_spin(src + k, seq - 1);
+                xv[r][u] = __uint_as_float(pay);
+                xloc[r * d + k] = xv[r][u];
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+          for (int u = 0; u < GV; ++u) { const int k = tid + u * kRingConsumers; xv[r][u] = (r < B && k < d) ? xloc[r * d + k] : 0.f; }
+      }
+      float mean[NR], rstd[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) { mean[r] = 0.f; rstd[r] = 1.f; }
+      if (Lp.ln_mode != 0 && !(dbg & 2)) {
+        float* red = opart;                        // [2][NR][16] cross-warp partials (opart is idle outside attention)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          float sv = (xv[r][0] + xv[r][1]) + (xv[r][2] + xv[r][3]);
+          sv = warp_sum(sv);
+          if (lane == 0) red[r * kRingConsumerWarps + warp] = sv;
+        }
+        csync();
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          float m = 0.f;
+#pragma unroll
+          for (int w = 0; w < kRingConsumerWarps; ++w) m += red[r * kRingConsumerWarps + w];
+          mean[r] = m / (float)d;
+          float qv = 0.f;
+#pragma unroll
+          for (int u = 0; u < GV; ++u) { const int k = tid + u * kRingConsumers; if (k < d) { const float t0 = xv[r][u] - mean[r]; qv = fmaf(t0, t0, qv); } }
+          qv = warp_sum(qv);
+          if (lane == 0) red[(NR + r) * kRingConsumerWarps + warp] = qv;
+        }
+        csync();
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < kRingConsumerWarps; ++w) v += red[(NR + r) * kRingConsumerWarps + w];
+          rstd[r] = rsqrtf(v / (float)d + a.eps);
+        }
+      }
+      fstamp();
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+#pragma unroll
+        for (int u = 0; u < GV; ++u) {
+          const int k = tid + u * kRingConsumers;
+          if (k < d) {
+            float v = (xv[r][u] - mean[r]) * rstd[r];
+            if (Lp.ln_mode == 2) v = v * Lp.gamma[k] + Lp.beta[k];
+            xs[(size_t)r * K + k] = (r < B) ? v : 0.f;
+          }
+        }
+      }
+      csync();
+    }
+    fstamp();
+    // ---- weights off the ring: warp w takes half (w & 1) of segment (w >> 1) of every stage.  8 % kq == 0, so a
+    //      warp always meets the same d/2-wide slice of the input row: it lives in registers for the whole phase ----
+    const int nseg = cnt * kq;
+    const long long bytes = (long long)cnt * K * 2;
+    const int nchunk = (int)((bytes + SB - 1) / SB);
+    const int hseg = warp >> 1, hhalf = warp & 1;
+    const int half_elems = d >> 1;
+    constexpr int XJ = 5;                          // float4 fragments per lane: d/2 <= 5 * 128
+    constexpr bool kRegX = NR <= 2;                // 4 rows would need 80 registers: those re-read shared memory per chunk
+    float4 xf[kRegX ? NR : 1][XJ];
+    const float* xb = xs + (hseg % kq) * d + hhalf * half_elems + lane * 4;
+    if (kRegX) {
+#pragma unroll
+      for (int r = 0; r < (kRegX ? NR : 1); ++r)
+#pragma unroll
+        for (int j = 0; j < XJ; ++j)
+          xf[r][j] = (j * 128 + lane * 4 < half_elems) ? *reinterpret_cast<const float4*>(xb + (size_t)r * K + j * 128)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    constexpr int PB = 4;                          // chunks whose warp reductions are batched (independent shuffle chains)
+    float pend[PB][NR];
+    for (int ch0 = 0; ch0 < nchunk; ch0 += PB) {
+#pragma unroll
+      for (int c = 0; c < PB; ++c) {
+        const int ch = ch0 + c;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) pend[c][r] = 0.f;
+        if (ch < nchunk) {
+          if (!(dbg & 8)) rbar_wait(&full_bar[pipe.stage], pipe.phase);
+          const int g = ch * kSegPerStage + hseg;
+          if (g < nseg && !(dbg & 4)) {
+            const bf16* wseg = reinterpret_cast<const bf16*>(ring + (size_t)pipe.stage * SB) + hseg * d + hhalf * half_elems + lane * 4;
+            uint2 wu[XJ];
+#pragma unroll
+            for (int j = 0; j < XJ; ++j)
+              wu[j] = (j * 128 + lane * 4 < half_elems) ? *reinterpret_cast<const uint2*>(wseg + j * 128) : make_uint2(0u, 0u);
+            float a0[NR], a1[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) { a0[r] = 0.f; a1[r] = 0.f; }
+#pragma unroll
+            for (int j = 0; j < XJ; ++j) {
+              const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wu[j].x));
+              const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wu[j].y));
+#pragma unroll
+              for (int r = 0; r < NR; ++r) {
+                float4 x;
+                if (kRegX) x = xf[kRegX ? r : 0][j];
+                else x = (j * 128 + lane * 4 < half_elems) ? *reinterpret_cast<const float4*>(xb + (size_t)r * K + j * 128)
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                a0[r] = fmaf(w01.x, x.x, a0[r]); a1[r] = fmaf(w01.y, x.y, a1[r]);
+                a0[r] = fmaf(w23.x, x.z, a0[r]); a1[r] = fmaf(w23.y, x.w, a1[r]);
+              }
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) pend[c][r] = a0[r] + a1[r];
+          }
+          __syncwarp();
+          if (lane == 0 && !(dbg & 8)) rbar_arrive(&empty_bar[pipe.stage]);
+          if (!(dbg & 8)) pipe_advance(pipe, NS);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < PB; ++c)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) pend[c][r] += __shfl_xor_sync(0xffffffffu, pend[c][r], o);
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < PB; ++c) {
+          const int g = (ch0 + c) * kSegPerStage + hseg;
+          if (ch0 + c < nchunk && g < nseg) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) part[(size_t)(g * 2 + hhalf) * NR + r] = pend[c][r];
+          }
+        }
+      }
+    }
+    csync();
+    fstamp();
+    // ---- epilogue + publish ----
+    unsigned long long* out = exbuf(seq);
+    if (Lp.out_mode != kROutHead) {
+      if (tid < cnt * NR) {
+        const int j = tid / NR, r = tid - j * NR;
+        if (r < B) {
+          float v = 0.f;
+          for (int s = 0; s < 2 * kq; ++s) v += part[(size_t)(j * 2 * kq + s) * NR + r];
+          v += bias_v;
+          if (Lp.act == kActGelu) v = gelu_erf(v);
+          if (Lp.out_mode == kROutResid) v += xloc[r * d + n0 + j];
+          ll_store(out + (size_t)r * ra.ld_vec + n0 + j, __float_as_uint(v), seq);
+        }
+      }
+    } else {
+      // tied lm head: suppress bias, sliding-window penalty, per-CTA argmax candidate per utterance
+      const int r = tid % NR;                       // kRingConsumers % NR == 0: a thread keeps one row
+      float bv = -INFINITY; int bi = 0x7fffffff;
+      if (r < B) {
+        for (int t = tid; t < cnt * NR; t += kRingConsumers) {
+          const int j = t / NR, n = n0 + j;
+          float v = part[(size_t)(j * 2) * NR + r] + part[(size_t)(j * 2 + 1) * NR + r] + Lp.bias[n];
+          if (pen_on) {
+            bool hit = false;
+            for (int q = 0; q < s_pen_n; ++q) hit |= (s_pen[r * 32 + q] == n);
+            if (hit) v *= a.penalty_value;
+          }
+          if (a.logits) a.logits[(long long)r * a.vocab + n] = v;
+          if (v > bv || (v == bv && n < bi)) { bv = v; bi = n; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o >= NR; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane < NR) { wbest_v[warp * 4 + lane] = bv; wbest_i[warp * 4 + lane] = bi; }
+      csync();
+      if (tid < NR) {                              // rows >= B publish (-inf, none) so the gather below completes
+        bv = -INFINITY; bi = 0x7fffffff;
+        for (int w = 0; w < kRingConsumerWarps; ++w) {
+          const float v = wbest_v[w * 4 + tid]; const int i = wbest_i[w * 4 + tid];
+          if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+        ll_store(out + (size_t)(blockIdx.x * NR + tid) * 2, __float_as_uint(bv), seq);
+        ll_store(out + (size_t)(blockIdx.x * NR + tid) * 2 + 1, (unsigned)bi, seq);
+      }
+    }
+    ++seq;
+    stamp();
+  };
+
+  // ---- self-attention of one (utterance, head): q/k/v of the new position arrive through the exchange,
+  //      older positions come from the resident cache (appended by this same CTA in earlier iterations) ----
+  auto self_attn_phase = [&](int l) {
+    const int t = (dbg & 16) ? -1 : my_task(ra, l, 0, ntask);
+    if (t >= 0) {
+      const int b = t / H, h = t - b * H;
+      const unsigned long long* in = exbuf(seq - 1) + (size_t)b * ra.ld_vec;
+      bf16* kc = reinterpret_cast<bf16*>(a.kcache) + ((((long long)l * B + b) * H + h) * a.max_target) * 64;
+      bf16* vc = reinterpret_cast<bf16*>(a.vcache) + ((((long long)l * B + b) * H + h) * a.max_target) * 64;
+      if (tid < 192) {
+        const int which = tid >> 6, dd = tid & 63;
+        const unsigned long long* p = in + which * d + h * 64 + dd;
+        unsigned long long v = ll_load(p);
+        unsigned pay = (unsigned)v;
+        if ((unsigned)(v >> 32) != seq - 1 && !(dbg & 1)) pay = ll_spin(p, seq - 1);
+        const float f = __uint_as_float(pay);
+        if (which == 0) qs[dd] = f;
+        else (which == 1 ? kc : vc)[(long long)kv_len * 64 + dd] = __float2bfloat16_rn(f);
+      }
+      csync();                                     // CTA-scope ordering makes the appended row visible to the loads below
+      const int npos = kv_len + 1;
+      float m = -INFINITY;
+      for (int p = tid; p < npos; p += kRingConsumers) {
+        const bf16* kr = kc + (long long)p * 64;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 u = __ldcg(reinterpret_cast<const uint4*>(kr + j * 8));
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(hh[i]);
+            s = fmaf(f.x, qs[j * 8 + 2 * i], s);
+            s = fmaf(f.y, qs[j * 8 + 2 * i + 1], s);
+          }
+        }
+        sc[p] = s;
+        m = fmaxf(m, s);
+      }
+      m = warp_max(m);
+      if (lane == 0) opart[warp] = m;
+      csync();
+      m = opart[0];
+#pragma unroll
+      for (int w = 1; w < kRingConsumerWarps; ++w) m = fmaxf(m, opart[w]);
+      csync();
+      float sum = 0.f;
+      for (int p = tid; p < npos; p += kRingConsumers) { const float e = expf(sc[p] - m); sc[p] = e; sum += e; }
+      sum = warp_sum(sum);
+      if (lane == 0) opart[kRingConsumerWarps * 64 - 32 + warp] = sum;     // tail of opart: not touched by the PV partials of warp < 15.5
+      csync();
+      float o0 = 0.f, o1 = 0.f;
+      for (int p = warp; p < npos; p += kRingConsumerWarps) {
+        const float w = sc[p];
+        const unsigned u = __ldcg(reinterpret_cast<const unsigned*>(vc + (long long)p * 64 + 2 * lane));
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+        o0 = fmaf(w, v.x, o0); o1 = fmaf(w, v.y, o1);
+      }
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRingConsumerWarps; ++w) tot += opart[kRingConsumerWarps * 64 - 32 + w];
+      csync();                                     // everyone has read the sums before the partials overwrite the area
+      opart[warp * 64 + 2 * lane] = o0;
+      opart[warp * 64 + 2 * lane + 1] = o1;
+      csync();
+      if (tid < 64) {
+        float o = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRingConsumerWarps; ++w) o += opart[w * 64 + tid];
+        ll_store(exbuf(seq) + (size_t)b * ra.ld_vec + h * 64 + tid, __float_as_uint(o / tot), seq);
+      }
+      csync();
+    }
+    ++seq;
+    stamp();
+  };
+
+  // ---- cross-attention of one (utterance, head): K and V tiles come off the ring ----
+  auto cross_attn_phase = [&](int l) {
+    const int t = (dbg & 16) ? -1 : my_task(ra, l, 1, ntask);
+    if (t >= 0) {
+      const int b = t / H, h = t - b * H;
+      if (tid < 64) {
+        const unsigned long long* p = exbuf(seq - 1) + (size_t)b * ra.ld_vec + h * 64 + tid;
+        unsigned long long v = ll_load(p);
+        unsigned pay = (unsigned)v;
+        if ((unsigned)(v >> 32) != seq - 1 && !(dbg & 1)) pay = ll_spin(p, seq - 1);
+        qs[tid] = __uint_as_float(pay);
+      }
+      csync();
+      // scores: two threads per position (32 dims each), 16-byte chunks rotated by position -> conflict-free
+      for (int i = 0; i < nbox; ++i) {
+        rbar_wait(&full_bar[pipe.stage], pipe.phase);
+        const bf16* kb = reinterpret_cast<const bf16*>(ring + (size_t)pipe.stage * SB);
+        for (int idx = tid; idx < R * 2; idx += kRingConsumers) {
+          const int p = idx >> 1, hf = idx & 1;
+          const bf16* kr = kb + p * 64 + hf * 32;
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int jj = (j + p) & 3;
+            const uint4 u = *reinterpret_cast<const uint4*>(kr + jj * 8);
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const float4 qa = *reinterpret_cast<const float4*>(qs + hf * 32 + jj * 8);
+            const float4 qb = *reinterpret_cast<const float4*>(qs + hf * 32 + jj * 8 + 4);
+            float2 f = __bfloat1622float2(hh[0]); s = fmaf(f.x, qa.x, s); s = fmaf(f.y, qa.y, s);
+            f = __bfloat1622float2(hh[1]); s = fmaf(f.x, qa.z, s); s = fmaf(f.y, qa.w, s);
+            f = __bfloat1622float2(hh[2]); s = fmaf(f.x, qb.x, s); s = fmaf(f.y, qb.y, s);
+            f = __bfloat1622float2(hh[3]); s = fmaf(f.x, qb.z, s); s = fmaf(f.y, qb.w, s);
+          }
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          const int pos = i * R + p;
+          if (hf == 0 && pos < T) sc[pos] = s;
+        }
+        __syncwarp();
+        if (lane == 0) rbar_arrive(&empty_bar[pipe.stage]);
+        pipe_advance(pipe, NS);
+      }
+      csync();
+      float m = -INFINITY;
+      for (int p = lane; p < T; p += 32) m = fmaxf(m, sc[p]);
+      m = warp_max(m);                             // every warp computes the same maximum
+      csync();
+      for (int p = tid; p < T; p += kRingConsumers) sc[p] = expf(sc[p] - m);
+      csync();
+      float tot = 0.f;
+      for (int p = lane; p < T; p += 32) tot += sc[p];
+      tot = warp_sum(tot);
+      float o0 = 0.f, o1 = 0.f;
+      for (int i = 0; i < nbox; ++i) {
+        rbar_wait(&full_bar[pipe.stage], pipe.phase);
+        const bf16* vb = reinterpret_cast<const bf16*>(ring + (size_t)pipe.stage * SB);
+        const int pmax = min(R, T - i * R);
+        for (int p = warp; p < pmax; p += kRingConsumerWarps) {
+          const float w = sc[i * R + p];
+          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + p * 64 + 2 * lane));
+          o0 = fmaf(w, v.x, o0); o1 = fmaf(w, v.y, o1);
+        }
+        __syncwarp();
+        if (lane == 0) rbar_arrive(&empty_bar[pipe.stage]);
+        pipe_advance(pipe, NS);
+      }
+      opart[warp * 64 + 2 * lane] = o0;
+      opart[warp * 64 + 2 * lane + 1] = o1;
+      csync();
+      if (tid < 64) {
+        float o = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRingConsumerWarps; ++w) o += opart[w * 64 + tid];
+        ll_store(exbuf(seq) + (size_t)b * ra.ld_vec + h * 64 + tid, __float_as_uint(o / tot), seq);
+      }
+      csync();
+    }
+    ++seq;
+    stamp();
+  };
+
+  // =========================================================================
+  for (int iter = 0; iter < a.n_iters; ++iter) {
+    if (tid == 0) {
+      int done = 1;
+      for (int b = 0; b < B; ++b) done &= (s_fin[b] != 0);
+      s_all_done = done;
+    }
+    csync();
+    if (s_all_done) break;                         // identical in every CTA
+    embed_rows();
+    csync();
+    const int n_phases = 8 * L + 1;
+    for (int idx = 0; idx < n_phases; ++idx) {      // one call site per phase body (instruction-cache footprint)
+      const int l = idx >> 3;
+      const int ph = (idx == n_phases - 1) ? 8 : (idx & 7);
+      if (ph == 1) { self_attn_phase(l); continue; }
+      if (ph == 4) { cross_attn_phase(l); continue; }
+      bool pen_on = false;
+      if (ph == 8) {
+        // sliding-window penalty ids (APPLY_PENALTY, Export_Whisper.py:318-331): active once generated >= penalty_range
+        if (tid == 0) {
+          int nmax = 0;
+          if (a.penalty_value != 1.0f) {
+            for (int b = 0; b < B; ++b) {
+              const bool act = s_ngen[b] >= a.penalty_range;
+              const int ns = s_nsave[b];
+              const int first = max(0, ns - a.penalty_range);
+              int cntp = 0;
+              if (act) for (int j = first; j < ns && cntp < 32; ++j) s_pen[b * 32 + cntp++] = s_hist[b * 32 + (j & 31)];
+              for (int j = cntp; j < 32; ++j) s_pen[b * 32 + j] = -1;
+              nmax = max(nmax, cntp);
+            }
+          }
+          s_pen_n = nmax;
+        }
+        csync();
+        pen_on = s_pen_n > 0;
+      }
+      linear_phase(ring_lin(a, l, ph), pen_on);
+    }
+    // ---- every CTA reduces the per-CTA candidates identically ----
+    ll_gather(exbuf(seq - 1), G * NR * 2, seq - 1, cand, tid, kRingConsumers, dbg & 1);
+    csync();
+    if (warp < B) {
+      float bv = -INFINITY; int bi = 0x7fffffff;
+      for (int c = lane; c < G; c += 32) {
+        const float v = cand[(c * NR + warp) * 2];
+        const int i = __float_as_int(cand[(c * NR + warp) * 2 + 1]);
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        if (bi == 0x7fffffff) bi = 0;
+        if (dbg) bi = (int)((unsigned)bi % (unsigned)a.vocab);   // timing experiments feed back garbage: keep the gather in range
+        const int b = warp;
+        s_tok[b] = bi;
+        const int gen = s_ngen[b];
+        const int ns = s_nsave[b];
+        const bool g0 = blockIdx.x == 0;
+        if (g0) {
+          a.cur_token[b] = bi;
+          if (step < a.sel_ld) a.selected_hist[(long long)b * a.sel_ld + step] = bi;
+          if (ns < a.save_ld) a.save_id[(long long)b * a.save_ld + ns] = bi;
+        }
+        if (ns < a.save_ld) { s_hist[b * 32 + (ns & 31)] = bi; s_nsave[b] = ns + 1; }
+        if (!s_fin[b]) {
+          bool stop = false;
+          for (int s = 0; s < a.n_stop; ++s) stop |= (a.stop_ids[s] == bi);
+          if (stop || a.limit <= 0) {
+            s_fin[b] = 1;
+          } else {
+            if (g0) a.tokens[(long long)b * a.tokens_ld + gen] = bi;
+            s_ngen[b] = gen + 1;
+            if (gen + 1 >= a.limit) s_fin[b] = 1;
+          }
+        }
+      }
+    }
+    csync();
+    kv_len += 1;
+    step += 1;
+  }
+  csync();
+  if (tid == 0) s_stop = 1;
+  if (blockIdx.x == 0 && tid < B) {
+    a.n_gen[tid] = s_ngen[tid];
+    a.finished[tid] = s_fin[tid];
+    a.n_save[tid] = s_nsave[tid];
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    int done = 1;
+    for (int b = 0; b < B; ++b) done &= (s_fin[b] != 0);
+    a.state->kv_len = kv_len; a.state->step = step; a.state->all_done = done;
+  }
+  __syncthreads();                                 // joins the producer warp after its drain
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int ring_nr(int batch) { return batch <= 1 ? 1 : (batch <= 2 ? 2 : 4); }
+
+bool ring_supported(int batch, int d, int ffn, int n_heads, int vocab, int num_sms) {
+  return batch >= 1 && batch <= 4 && d % 256 == 0 && d <= 1280 && ffn % d == 0 && (kSegPerStage % (ffn / d)) == 0 &&
+         d >= num_sms && vocab >= num_sms && batch * n_heads <= num_sms && d == n_heads * 64;
+}
+
+// shared-memory plan for one launch; returns false when it does not fit
+bool ring_plan(const MegaArgs& a, int num_sms, RingArgs* ra, size_t* smem_bytes) {
+  const int NR = ring_nr(a.batch);
+  const int d = a.d, ffn = a.ffn;
+  const int kmax = d > ffn ? d : ffn;
+  ra->stage_bytes = kSegPerStage * d * 2;
+  auto per_cta = [&](int N) { return (N + num_sms - 1) / num_sms; };
+  int cap = per_cta(3 * d) * 2;
+  cap = std::max(cap, per_cta(ffn) * 2);
+  cap = std::max(cap, per_cta(d) * 2 * (ffn / d));
+  cap = std::max(cap, per_cta(a.vocab) * 2);
+  ra->part_cap = (cap + kSegPerStage * 2 + 3) & ~3;     // keeps the arrays carved after it 16-byte aligned
+  ra->sc_cap = ((a.T > a.max_target ? a.T : a.max_target) + 8 + 3) & ~3;
+  const size_t fixed = 128 /*alignment slack*/ +
+                       sizeof(float) * ((size_t)NR * kmax + (size_t)NR * d + (size_t)ra->part_cap * NR + ra->sc_cap + 64 +
+                                        kRingConsumerWarps * 64 + (size_t)num_sms * NR * 2);
+  const size_t budget = 227 * 1024 - 2048;        // static __shared__ + slack
+  if (fixed + 2 * (size_t)ra->stage_bytes > budget) return false;
+  int ns = (int)((budget - fixed) / ra->stage_bytes);
+  if (ns > kRingMaxStages) ns = kRingMaxStages;
+  ra->n_stages = ns;
+  *smem_bytes = fixed + (size_t)ns * ra->stage_bytes;
+  return true;
+}
+
+size_t ring_exchange_words(int batch, int d, int ffn, int num_sms) {
+  const int NR = ring_nr(batch);
+  const size_t vec = (size_t)NR * (size_t)std::max(3 * d, ffn);
+  const size_t cand = (size_t)num_sms * NR * 2;
+  return std::max(vec, cand);
+}
+
+cudaError_t launch_decoder_ring(const RingArgs& ra_in, const CUtensorMap& cross_map, int num_sms, size_t smem_bytes,
+                                cudaStream_t st) {
+  const int NR = ring_nr(ra_in.m.batch);
+  // the instrumented build (phase stamps, ablation switches) is a separate instantiation so the product path
+  // carries none of its branches
+  const bool dbg = ra_in.debug != 0 || ra_in.fine_timing != 0 || ra_in.m.timing != nullptr;
+  void* fns[6] = {(void*)decoder_ring_kernel<1, false>, (void*)decoder_ring_kernel<2, false>, (void*)decoder_ring_kernel<4, false>,
+                  (void*)decoder_ring_kernel<1, true>,  (void*)decoder_ring_kernel<2, true>,  (void*)decoder_ring_kernel<4, true>};
+  static bool done[6] = {false, false, false, false, false, false};
+  const int slot = (NR == 1 ? 0 : (NR == 2 ? 1 : 2)) + (dbg ? 3 : 0);
+  void* fn = fns[slot];
+  if (!done[slot]) {
+    cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    if (r != cudaSuccess) return r;
+    done[slot] = true;
+  }
+  RingArgs ra = ra_in;
+  CUtensorMap tm = cross_map;
+  void* params[] = {&tm, &ra};
+  return cudaLaunchCooperativeKernel(fn, dim3(num_sms), dim3(kRingThreads), params, smem_bytes, st);
+}
+
+}  // namespace b200asr

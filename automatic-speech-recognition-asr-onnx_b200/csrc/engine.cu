@@ -76,6 +76,9 @@ struct b200asr_engine {
   int pf_B = -1, pf_T = -1;
   unsigned int* mega_bar = nullptr; float* cand_val = nullptr; int* cand_idx = nullptr;
   bool mega_timing = false; unsigned long long* timing = nullptr; static constexpr int kTimingCap = 16384;
+  // streaming decode kernel (decoder_ring.cu)
+  bool use_ring = true; bool ring_fine = false; int ring_debug = 0; unsigned long long* ring_ll = nullptr; size_t ring_ll_words = 0;
+  CUtensorMap cross_map{}; int cmap_B = -1, cmap_T = -1; int ring_task_inv = 0;
   std::string graph_key;
 
   int fail(int code, const std::string& m) { err = m; return code; }
@@ -406,12 +409,9 @@ int build_mega_tables(b200asr_engine* e) {
   return B200ASR_OK;
 }
 
-// one cooperative launch: iteration 0 consumes first_tokens [B][first_n_new], later iterations feed back the argmax
-int run_mega(b200asr_engine* e, int n_iters, const int* first_tokens, int first_n_new, bool first_is_prefill,
-             bool want_logits) {
+void fill_mega_args(b200asr_engine* e, MegaArgs& a, int n_iters, const int* first_tokens, int first_n_new,
+                    bool first_is_prefill, bool want_logits) {
   const b200asr_config& c = e->cfg;
-  RET(build_mega_tables(e));
-  MegaArgs a{};
   a.layers = e->mega_layers; a.n_layers = c.dec_layers;
   a.embed = W(e, "dec.embed"); a.pos = WF(e, "dec.pos"); a.ln_g = WF(e, "dec.ln.g"); a.ln_b = WF(e, "dec.ln.b");
   a.suppress_bias = WF(e, "dec.suppress_bias"); a.begin_bias = WF(e, "dec.begin_suppress_bias");
@@ -429,13 +429,71 @@ int run_mega(b200asr_engine* e, int n_iters, const int* first_tokens, int first_
   a.pf_total = e->pf_ahead > 0 ? e->pf_total : 0; a.pf_ahead = e->pf_ahead;
   a.eps = 1e-5f;
   a.timing = nullptr; a.timing_cap = 0;
-  if (e->mega_timing) {
-    if (!e->timing) CK(cudaMalloc(&e->timing, sizeof(unsigned long long) * b200asr_engine::kTimingCap));
-    CK(cudaMemsetAsync(e->timing, 0, sizeof(unsigned long long) * b200asr_engine::kTimingCap, e->st));
-    a.timing = e->timing; a.timing_cap = b200asr_engine::kTimingCap;
-  }
+}
+
+int arm_timing(b200asr_engine* e, MegaArgs& a) {
+  if (!e->mega_timing) return B200ASR_OK;
+  if (!e->timing) CK(cudaMalloc(&e->timing, sizeof(unsigned long long) * b200asr_engine::kTimingCap));
+  CK(cudaMemsetAsync(e->timing, 0, sizeof(unsigned long long) * b200asr_engine::kTimingCap, e->st));
+  a.timing = e->timing; a.timing_cap = b200asr_engine::kTimingCap;
+  return B200ASR_OK;
+}
+
+// one cooperative launch: iteration 0 consumes first_tokens [B][first_n_new], later iterations feed back the argmax
+int run_mega(b200asr_engine* e, int n_iters, const int* first_tokens, int first_n_new, bool first_is_prefill,
+             bool want_logits) {
+  RET(build_mega_tables(e));
+  MegaArgs a{};
+  fill_mega_args(e, a, n_iters, first_tokens, first_n_new, first_is_prefill, want_logits);
+  RET(arm_timing(e, a));
   CK(cudaMemsetAsync(e->mega_bar, 0, 64, e->st));
   KL(launch_decoder_mega(a, e->act_dtype, e->num_sms, e->st));
+  return B200ASR_OK;
+}
+
+// ---- streaming decode kernel plumbing (decoder_ring.cu) ----------------------------------------
+bool ring_ok(b200asr_engine* e) {
+  const b200asr_config& c = e->cfg;
+  if (!e->use_ring || !e->use_mega || e->act_dtype != kBF16 || e->penalty_range > 32) return false;
+  if (e->num_sms % kRingTaskMul == 0) return false;
+  if (!ring_supported(e->B, c.d_model, c.ffn, c.n_heads, c.vocab, e->num_sms)) return false;
+  if (c.d_model / 8 > 256) return false;         // TMA box rows
+  MegaArgs a{}; a.batch = e->B; a.d = c.d_model; a.ffn = c.ffn; a.vocab = c.vocab; a.T = e->T_enc; a.max_target = c.max_target;
+  RingArgs ra{}; size_t smem = 0;
+  return ring_plan(a, e->num_sms, &ra, &smem);
+}
+
+// n_iters single-token iterations starting from cur_token (the prefill has run)
+int run_ring(b200asr_engine* e, int n_iters, bool want_logits) {
+  const b200asr_config& c = e->cfg;
+  RET(build_mega_tables(e));
+  RingArgs ra{};
+  fill_mega_args(e, ra.m, n_iters, e->cur_token, 1, false, want_logits);
+  RET(arm_timing(e, ra.m));
+  size_t smem = 0;
+  if (!ring_plan(ra.m, e->num_sms, &ra, &smem)) return e->fail(B200ASR_E_INVALID, "decoder_ring: shared-memory plan does not fit");
+  const size_t words = ring_exchange_words(c.max_batch < 4 ? c.max_batch : 4, c.d_model, c.ffn, e->num_sms);
+  if (!e->ring_ll) {
+    CK(cudaMalloc(&e->ring_ll, words * 4 * sizeof(unsigned long long)));
+    e->ring_ll_words = words;
+    int inv = 0;
+    for (int i = 1; i < e->num_sms; ++i) if ((i * kRingTaskMul) % e->num_sms == 1) inv = i;
+    e->ring_task_inv = inv;
+  }
+  if (e->cmap_B != e->B || e->cmap_T != e->T_enc) {
+    std::string msg;
+    const int64_t rows = (int64_t)2 * c.dec_layers * e->B * e->T_enc;
+    if (!make_tmap_2d_plain(&e->cross_map, e->cross_kv, c.d_model, rows, c.d_model, 64, ra.stage_bytes / 128, &msg))
+      return e->fail(B200ASR_E_CUDA, "decoder_ring: " + msg);
+    e->cmap_B = e->B; e->cmap_T = e->T_enc;
+  }
+  ra.ll = e->ring_ll; ra.ll_stride = (long long)e->ring_ll_words;
+  ra.ld_vec = c.d_model * 3 > c.ffn ? c.d_model * 3 : c.ffn;
+  ra.task_inv = e->ring_task_inv;
+  ra.fine_timing = e->ring_fine ? 1 : 0;
+  ra.debug = e->ring_debug;
+  CK(cudaMemsetAsync(e->ring_ll, 0, e->ring_ll_words * 4 * sizeof(unsigned long long), e->st));
+  KL(launch_decoder_ring(ra, e->cross_map, e->num_sms, smem, e->st));
   return B200ASR_OK;
 }
 
@@ -536,7 +594,7 @@ void b200asr_destroy(b200asr_engine* e) {
                   e->hidden, e->stem, e->xhat, e->qkv, e->ctx, e->ffn, e->S, e->P, e->cross_kv, e->kcache, e->vcache,
                   e->dx, e->dq, e->dctx, e->dffn, e->logits, e->prob, e->d_prompt, e->cur_token, e->tokens, e->n_gen,
                   e->finished, e->save_id, e->n_save, e->selected_hist, e->d_stop, e->dstate, e->mega_layers, e->pf_blocks,
-                  e->mega_bar, e->cand_val, e->cand_idx, e->timing};
+                  e->mega_bar, e->cand_val, e->cand_idx, e->timing, e->ring_ll};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -548,6 +606,9 @@ int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "keep_stages")) { e->keep_stages = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "mega_timing")) { e->mega_timing = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "mega")) { e->use_mega = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "ring")) { e->use_ring = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "ring_debug")) { e->ring_debug = (int)value; return B200ASR_OK; }
+  if (!strcmp(key, "ring_fine_timing")) { e->ring_fine = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "pf_ahead_mb")) { e->pf_ahead = (long long)value << 20; return B200ASR_OK; }
   return e->fail(B200ASR_E_INVALID, std::string("unknown option ") + key);
 }
@@ -739,7 +800,8 @@ int b200asr_decode_step(b200asr_engine* e, const int32_t* token_in, float* logit
   CK(cudaStreamSynchronize(e->st));
   if (hs.kv_len + 1 > e->cfg.max_target) return e->fail(B200ASR_E_INVALID, "KV cache full");
   if (token_in) CK(cudaMemcpyAsync(e->cur_token, token_in, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->st));
-  if (mega_ok(e, 1)) RET(run_mega(e, 1, e->cur_token, 1, false, true));
+  if (ring_ok(e)) RET(run_ring(e, 1, true));
+  else if (mega_ok(e, 1)) RET(run_mega(e, 1, e->cur_token, 1, false, true));
   else RET(launch_step(e));
   if (logits_out) CK(cudaMemcpyAsync(logits_out, e->logits, (size_t)e->B * e->cfg.vocab * 4, cudaMemcpyDeviceToHost, e->st));
   if (token_out) CK(cudaMemcpyAsync(token_out, e->cur_token, (size_t)e->B * 4, cudaMemcpyDeviceToHost, e->st));
@@ -758,8 +820,10 @@ static int decode_loop(b200asr_engine* e, int max_steps, int32_t* tokens_out, in
   const int room = c.max_target - e->n_prompt;    // cache positions left after the prompt
   if (steps > room) steps = room;
   int* h_done = e->h_pinned;
-  if (steps > 0 && mega_ok(e, 1)) {
-    RET(run_mega(e, steps, e->cur_token, 1, false, false));     // the kernel leaves the loop itself when all latched
+  if (steps > 0 && ring_ok(e)) {
+    RET(run_ring(e, steps, false));                             // the kernel leaves the loop itself when all latched
+  } else if (steps > 0 && mega_ok(e, 1)) {
+    RET(run_mega(e, steps, e->cur_token, 1, false, false));
   } else {
     for (int s = 0; s < steps; ++s) {
       RET(launch_step(e));
@@ -829,7 +893,16 @@ int b200asr_transcribe_resident(b200asr_engine* e, const int32_t* prompt_ids, in
   int r;
   if (mega_ok(e, n_prompt)) {
     r = do_prefill(e, prompt_ids, n_prompt, -1);                 // reset + upload the prompt only
-    if (r == B200ASR_OK) r = run_mega(e, e->limit, e->d_prompt, n_prompt, true, false);   // prefill + (limit-1) decode launches
+    if (r == B200ASR_OK && ring_ok(e)) {
+      // prefill launch (multi-token rows) in the barrier kernel, then the streaming kernel for the greedy loop
+      r = run_mega(e, 1, e->d_prompt, n_prompt, true, false);
+      int steps = e->limit - 1;
+      const int room = e->cfg.max_target - n_prompt;
+      if (steps > room) steps = room;
+      if (r == B200ASR_OK && steps > 0) r = run_ring(e, steps, false);
+    } else if (r == B200ASR_OK) {
+      r = run_mega(e, e->limit, e->d_prompt, n_prompt, true, false);   // prefill + (limit-1) decode launches
+    }
     e->limit_cfg = saved;
     RET(r);
     return fetch_tokens(e, tokens_out, tokens_ld, lens_out);

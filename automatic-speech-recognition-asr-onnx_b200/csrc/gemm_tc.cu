@@ -309,6 +309,24 @@ static bool make_tmap(CUtensorMap* tm, const void* base, int64_t K, int64_t rows
   return true;
 }
 
+bool make_tmap_2d_plain(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_cols,
+                        int box_rows, std::string* err) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { if (err) *err = "cuTensorMapEncodeTiled entry point not found"; return false; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled (2d plain) failed with CUresult " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
+
 bool gemm_tc_supported(const GemmArgs& g) {
   if (g.a_dtype != kBF16 || g.b_dtype != kBF16 || g.transB) return false;
   if (g.batch_inner != 1) return false;

@@ -323,7 +323,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "kernel": "decoder_mega_kernel<bf16> (persistent decoder; one greedy step = all decoder weights streamed once)",
+                "kernel": "decoder_ring_kernel<NR> (streaming greedy-decode kernel: TMA weight ring + flag-in-data "
+                          "exchanges; one greedy step = all decoder weights streamed once)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "ms_per_launch": ms_dec, "algorithmic_bytes_per_launch": bytes_step,
