@@ -1,0 +1,303 @@
+// Fused encoder self-attention for sm_100a: softmax(Q K^T) V of one (utterance, head, 128-query tile) per CTA,
+// both contractions on tcgen05 tensor cores with the accumulators in TMEM.
+//
+// Replaces, for the encoder layer loop of /root/reference/Whisper/Export_Whisper.py:430-437 (per-head
+// softmax(q k^T) v, no mask, the d^-0.25 scale pre-folded into q and k by the exporter, :380-388), the three
+// launches of the first engine version (CUDA-core Q K^T, row softmax, CUDA-core P V through a T x T score matrix
+// in HBM).  Nothing T x T ever leaves the SM here:
+//
+//   TMA   : Q tile [128][64], K [T][64], V [T][64] straight out of the fused-QKV activation buffer [M][3d]
+//           (one tensor map, SWIZZLE_128B), landing in shared memory in UMMA's canonical layouts
+//   MMA 1 : S[128][T] = Q K^T   (A = Q K-major, B = K K-major), fp32 in TMEM columns [0, T)
+//   warps : one thread per query row (= one TMEM lane): row max, exp, row sum in registers -- no shuffles --
+//           P written as bf16 into shared memory in the K-major SWIZZLE_128B layout, 64 keys at a time,
+//           double-buffered against
+//   MMA 2 : O[128][64] += P V   (A = P K-major, B = V MN-major: V stays [key][dh] exactly as the QKV GEMM
+//           wrote it, no transpose), fp32 in TMEM columns [448, 512)
+//   store : O / rowsum -> bf16 context rows [M][d] at column h*64
+//
+// Single pass (the whole score row lives in TMEM), so T <= 448 keys (8.96 s of audio); longer clips keep the
+// unfused path.
+#include "common.cuh"
+#include <cstdio>
+
+namespace b200asr {
+
+constexpr int kAttThreads = 160;          // warps 0-3: softmax / epilogue (TMEM lane quarters), warp 4: TMA + MMA
+constexpr int kAttBM = 128;
+constexpr int kAttMaxT = 448;
+constexpr int kAttOCol = 448;             // TMEM column of the O accumulator
+constexpr int kAttTile = 128 * 64 * 2;    // one [128][64] bf16 tile = 16 KB
+
+namespace {
+
+__device__ __forceinline__ uint32_t as_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ab_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(as_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ab_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(as_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ab_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(as_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool ab_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(as_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void ab_wait(uint64_t* bar, uint32_t parity) {
+  if (ab_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!ab_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("b200asr attention_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void a_tma_3d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(as_u32(dst)), "l"(tm), "r"(as_u32(bar)), "r"(c0), "r"(c1), "r"(0) : "memory");
+}
+__device__ __forceinline__ void a_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void a_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void a_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(as_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void a_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void a_tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void a_tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptors (sm_100 "version 1"), SWIZZLE_128B, 8-row groups 1024 B apart.
+// K-major (Q, K, P tiles: rows = M/N index, 64 contiguous K elements per 128-byte row): LBO unused.
+// MN-major (V tile: rows = K index (keys), 64 contiguous N elements (dh) per 128-byte row): SBO = pitch of the
+// 8-key groups, LBO = pitch of 64-wide N blocks (a single block here).
+__device__ __forceinline__ uint64_t a_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// D = f32, A = B = bf16, M = 128, N = n; b_mn = 1 selects the MN-major B operand
+__device__ __forceinline__ uint32_t a_idesc(int n, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kAttBM >> 4) << 24);
+}
+
+}  // namespace
+
+struct AttArgs {
+  bf16* ctx; int64_t ld_ctx;      // [M][d] context rows
+  int T, d, n_heads;
+};
+
+__global__ void __launch_bounds__(kAttThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
+  extern __shared__ __align__(1024) uint8_t att_smem[];
+  const int T = a.T;
+  const int nkb = (T + 127) / 128;                    // 128-key boxes of K and of V
+  const uint32_t base_addr = as_u32(att_smem);
+  uint8_t* sQ = att_smem + ((1024u - (base_addr & 1023u)) & 1023u);      // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* sK = sQ + kAttTile;
+  uint8_t* sV = sK + (size_t)nkb * kAttTile;
+  uint8_t* sP = sV + (size_t)nkb * kAttTile;          // 2 x [128][64] bf16
+  __shared__ uint64_t bar_qk, bar_v, bar_s, bar_o, bar_pfull[2], bar_pempty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int row0 = b * T;                             // first row of this utterance in [M][3d]
+  const int m0 = mt * kAttBM;
+  const int Tp = (T + 15) & ~15;                      // keys rounded up to the MMA K / N granule
+  const int nblk = (Tp + 63) / 64;                    // 64-key P blocks
+
+  if (threadIdx.x == 0) {
+    ab_init(&bar_qk, 1); ab_init(&bar_v, 1); ab_init(&bar_s, 1); ab_init(&bar_o, 1);
+    for (int i = 0; i < 2; ++i) { ab_init(&bar_pfull[i], 128); ab_init(&bar_pempty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(as_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  a_fence_before();
+  __syncthreads();
+  a_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- TMA: Q + K on one barrier (needed first), V on its own ----
+      ab_expect_tx(&bar_qk, (uint32_t)((1 + nkb) * kAttTile));
+      a_tma_3d(sQ, &tmQKV, h * 64, row0 + m0, &bar_qk);
+      for (int j = 0; j < nkb; ++j) a_tma_3d(sK + (size_t)j * kAttTile, &tmQKV, a.d + h * 64, row0 + j * 128, &bar_qk);
+      ab_expect_tx(&bar_v, (uint32_t)(nkb * kAttTile));
+      for (int j = 0; j < nkb; ++j) a_tma_3d(sV + (size_t)j * kAttTile, &tmQKV, 2 * a.d + h * 64, row0 + j * 128, &bar_v);
+      // ---- S = Q K^T, 128 keys per instruction group ----
+      ab_wait(&bar_qk, 0);
+      a_fence_after();
+      const uint64_t qdesc = a_desc_sw128(as_u32(sQ));
+      for (int n0 = 0; n0 < Tp; n0 += 128) {
+        const int n = min(128, Tp - n0);
+        const uint32_t idesc = a_idesc(n, 0);
+        const uint64_t kdesc = a_desc_sw128(as_u32(sK) + (uint32_t)n0 * 128u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a_mma(tmem + (uint32_t)n0, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc, k != 0);
+      }
+      a_commit(&bar_s);
+      // ---- O += P V, one 64-key block at a time ----
+      ab_wait(&bar_v, 0);
+      const uint32_t idesc_pv = a_idesc(64, 1);
+      for (int j = 0; j < nblk; ++j) {
+        const int buf = j & 1;
+        ab_wait(&bar_pfull[buf], (uint32_t)((j >> 1) & 1));
+        a_fence_after();
+        const int ksteps = min(4, (Tp - j * 64) / 16);
+        const uint64_t pdesc = a_desc_sw128(as_u32(sP) + (uint32_t)buf * kAttTile);
+#pragma unroll 1
+        for (int k = 0; k < ksteps; ++k) {
+          // V rows (keys) j*64 + k*16 ..+15: two 8-key groups, 2048 bytes per step
+          const uint64_t vdesc = a_desc_sw128(as_u32(sV) + (uint32_t)(j * 64 + k * 16) * 128u);
+          a_mma(tmem + kAttOCol, pdesc + (uint64_t)(2 * k), vdesc, idesc_pv, (j | k) != 0);
+        }
+        a_commit(&bar_pempty[buf]);                   // P buffer reusable once these MMAs have read it
+      }
+      a_commit(&bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ---- softmax: thread = query row = TMEM lane ----
+    const int r = threadIdx.x;                        // 0..127
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    ab_wait(&bar_s, 0);
+    a_fence_after();
+    float m = -INFINITY;
+    for (int c0 = 0; c0 < T; c0 += 32) {
+      uint32_t v[32];
+      a_tmem_ld32(lane_base + (uint32_t)c0, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (c0 + i < T) m = fmaxf(m, __uint_as_float(v[i]));
+    }
+    const float ml2 = m * 1.4426950408889634f;
+    float sum = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int buf = j & 1;
+      if (j >= 2) ab_wait(&bar_pempty[buf], (uint32_t)(((j >> 1) - 1) & 1));
+      uint8_t* prow = sP + (size_t)buf * kAttTile + (size_t)r * 128;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c0 = j * 64 + half * 32;
+        uint32_t packed[16];
+        if (c0 < Tp) {
+          uint32_t v[32];
+          a_tmem_ld32(lane_base + (uint32_t)c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float e0 = 0.f, e1 = 0.f;
+            if (c0 + i < T) e0 = exp2f(fmaf(__uint_as_float(v[i]), 1.4426950408889634f, -ml2));
+            if (c0 + i + 1 < T) e1 = exp2f(fmaf(__uint_as_float(v[i + 1]), 1.4426950408889634f, -ml2));
+            sum += e0 + e1;
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(e0, e1);
+            packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&p2);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[i] = 0u;
+        }
+        // 32 keys = four 16-byte chunks; chunk index XOR (row & 7) = SWIZZLE_128B
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int chunk = (half * 4 + c) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+        }
+      }
+      a_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA (async proxy)
+      ab_arrive(&bar_pfull[buf]);
+    }
+    // ---- O / rowsum -> context ----
+    ab_wait(&bar_o, 0);
+    a_fence_after();
+    const float inv = 1.0f / sum;
+    const int t = m0 + r;
+    uint32_t o[64];
+    a_tmem_ld32(lane_base + kAttOCol, o);
+    a_tmem_ld32(lane_base + kAttOCol + 32, o + 32);
+    if (t < T) {
+      bf16* dst = a.ctx + (int64_t)(row0 + t) * a.ld_ctx + h * 64;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(o[c * 8 + 2 * i]) * inv, __uint_as_float(o[c * 8 + 2 * i + 1]) * inv);
+          w[i] = *reinterpret_cast<const uint32_t*>(&p2);
+        }
+        *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  a_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    a_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+bool attention_tc_supported(int T, int d, int n_heads) {
+  return T >= 1 && T <= kAttMaxT && d == n_heads * 64 && (d % 8) == 0;
+}
+
+// qkv: bf16 [M = batch*T][3d] (q | k | v per row), ctx: bf16 [M][d]
+cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, int d, int n_heads, cudaStream_t st,
+                                std::string* err) {
+  if (!attention_tc_supported(T, d, n_heads)) { if (err) *err = "attention_tc: unsupported shape"; return cudaErrorInvalidValue; }
+  const int nkb = (T + 127) / 128;
+  const size_t smem = (size_t)(1 + 2 * nkb + 2) * kAttTile + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t r = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * kAttTile + 1024);
+    if (r != cudaSuccess) return r;
+    attr_done = true;
+  }
+  CUtensorMap tm;
+  if (!make_tmap_rows_sw128(&tm, qkv, 3 * (int64_t)d, (int64_t)batch * T, 3 * (int64_t)d, 128, err)) return cudaErrorNotSupported;
+  AttArgs a;
+  a.ctx = reinterpret_cast<bf16*>(ctx); a.ld_ctx = d; a.T = T; a.d = d; a.n_heads = n_heads;
+  dim3 grid((T + kAttBM - 1) / kAttBM, n_heads, batch);
+  attention_tc_kernel<<<grid, kAttThreads, smem, st>>>(tm, a);
+  return cudaGetLastError();
+}
+
+}  // namespace b200asr

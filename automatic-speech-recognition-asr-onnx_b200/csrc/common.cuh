@@ -185,6 +185,13 @@ bool ring_plan(const MegaArgs& a, int num_sms, RingArgs* ra, size_t* smem_bytes)
 size_t ring_exchange_words(int batch, int d, int ffn, int num_sms);
 cudaError_t launch_decoder_ring(const RingArgs& ra, const CUtensorMap& cross_map, int num_sms, size_t smem_bytes,
                                 cudaStream_t st);
+// gemm_tc.cu: SWIZZLE_128B bf16 tensor map over [rows][ld] with a [box_rows][64] box (3-D form, batch 1)
+bool make_tmap_rows_sw128(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_rows,
+                          std::string* err);
+// attention_tc.cu: fused softmax(Q K^T) V per (utterance, head) on tcgen05; qkv bf16 [batch*T][3d], ctx bf16 [batch*T][d]
+bool attention_tc_supported(int T, int d, int n_heads);
+cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, int d, int n_heads, cudaStream_t st,
+                                std::string* err);
 // gemm_tc.cu: plain (unswizzled) 2-D bf16 tensor map over [rows][ld] with a [box_rows][box_cols] box
 bool make_tmap_2d_plain(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_cols,
                         int box_rows, std::string* err);

@@ -77,6 +77,7 @@ struct b200asr_engine {
   unsigned int* mega_bar = nullptr; float* cand_val = nullptr; int* cand_idx = nullptr;
   bool mega_timing = false; unsigned long long* timing = nullptr; static constexpr int kTimingCap = 16384;
   // streaming decode kernel (decoder_ring.cu)
+  bool use_attn_tc = true;
   bool use_ring = true; bool ring_fine = false; int ring_debug = 0; unsigned long long* ring_ll = nullptr; size_t ring_ll_words = 0;
   CUtensorMap cross_map{}; int cmap_B = -1, cmap_T = -1; int ring_task_inv = 0;
   std::string graph_key;
@@ -219,7 +220,13 @@ int run_encoder(b200asr_engine* e) {
     const std::string p = "enc.L" + std::to_string(l) + ".";
     KL(launch_layernorm(e->hidden, d, nullptr, nullptr, e->xhat, ad, d, M, d, 1e-5f, e->st));
     RET(gemm(e, linear_args(e, e->xhat, d, p + "qkv.w", p + "qkv.b", e->qkv, 3 * d, ad, M, 3 * d, d)));
-    {  // per-(utterance, head) softmax(Q K^T) V ; scale pre-folded into q and k
+    if (ad == kBF16 && c.use_tensor_cores && e->use_attn_tc && attention_tc_supported(T, d, H)) {
+      // fused softmax(Q K^T) V on tcgen05: scores and probabilities never leave the SM
+      std::string msg;
+      cudaError_t r = launch_attention_tc(e->qkv, e->ctx, B, T, d, H, e->st, &msg);
+      e->launches++;
+      if (r != cudaSuccess) return e->fail(B200ASR_E_CUDA, "attention_tc: " + (msg.empty() ? std::string(cudaGetErrorString(r)) : msg));
+    } else {  // per-(utterance, head) softmax(Q K^T) V ; scale pre-folded into q and k
       GemmArgs s;
       s.A = e->qkv; s.lda = 3 * d; s.sAo = (int64_t)T * 3 * d; s.sAi = 64; s.a_dtype = ad;
       s.B = (char*)e->qkv + (size_t)d * es; s.ldb = 3 * d; s.sBo = (int64_t)T * 3 * d; s.sBi = 64; s.b_dtype = ad;
@@ -606,6 +613,7 @@ int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "keep_stages")) { e->keep_stages = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "mega_timing")) { e->mega_timing = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "mega")) { e->use_mega = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring")) { e->use_ring = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_debug")) { e->ring_debug = (int)value; return B200ASR_OK; }
   if (!strcmp(key, "ring_fine_timing")) { e->ring_fine = value != 0; return B200ASR_OK; }

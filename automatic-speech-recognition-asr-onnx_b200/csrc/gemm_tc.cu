@@ -309,6 +309,11 @@ static bool make_tmap(CUtensorMap* tm, const void* base, int64_t K, int64_t rows
   return true;
 }
 
+bool make_tmap_rows_sw128(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_rows,
+                          std::string* err) {
+  return make_tmap(tm, base, cols, rows, 1, ld, 0, box_rows, err);
+}
+
 bool make_tmap_2d_plain(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_cols,
                         int box_rows, std::string* err) {
   EncodeTiledFn fn = get_encode_fn();

@@ -1,0 +1,47 @@
+"""Fused tcgen05 encoder attention (attention_tc.cu) against the unfused CUDA-core path of the same engine
+(Q K^T -> row softmax -> P V through HBM) and against the fp32 goldens.  Both paths round Q/K/V/P to bf16 and
+accumulate in fp32; they differ in where P is normalised (before vs after the P V contraction), so encoder
+outputs agree to a few bf16 ulps of an O(1) LayerNorm output: tolerance 3e-2 on enc_out, written here."""
+import numpy as np
+import pytest
+
+from gpu_common import GOLD, load_case, make_engine, maxdiff
+from b200asr.synth import synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n_samples", [32000, 24160, 48160, 128000, 143200])
+def test_attention_tc_vs_unfused(n_samples):
+    g, raw, tensors = load_case(GOLD[0])
+    T = (n_samples // 160 + 1) // 2
+    clips = np.stack([synth_pcm(40 + i, n_samples) for i in range(2)])
+    outs = []
+    for fused in (1, 0):
+        eng = make_engine(tensors, "bf16", max_batch=2, max_samples=n_samples)
+        eng.set_option("attn_tc", fused)
+        eng.encode(clips)
+        enc = eng.get_stage("enc_out", 2 * T * 256).reshape(2, T, 256)
+        ck = eng.get_stage("cross_k", 2 * 2 * 4 * T * 64)
+        launches = eng.kernel_launches
+        outs.append((enc.copy(), ck.copy(), launches))
+        eng.close()
+    d = maxdiff(outs[0][0], outs[1][0])
+    print(f"T={T}: fused vs unfused enc_out max|d| = {d:.4f}, launches {outs[0][2]} vs {outs[1][2]}")
+    assert np.isfinite(outs[0][0]).all()
+    assert d <= 3e-2
+    assert maxdiff(outs[0][1], outs[1][1]) <= 3e-2
+    assert outs[0][2] < outs[1][2]          # the fused path really ran (one launch instead of three per layer)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])
+def test_attention_tc_vs_golden(path):
+    g, raw, tensors = load_case(path)
+    eng = make_engine(tensors, "bf16")
+    eng.encode(g["pcm"])
+    T = (len(g["pcm"]) // 160 + 1) // 2
+    enc = eng.get_stage("enc_out", T * 256).reshape(T, 256)
+    d = maxdiff(enc, g["enc_out"])
+    print("bf16 fused-attention enc_out vs fp32 golden max|d| =", d)
+    assert d <= 6e-2
+    eng.close()
