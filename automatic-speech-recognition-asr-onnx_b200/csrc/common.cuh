@@ -129,6 +129,9 @@ struct SelectArgs {
   int limit;
   float penalty_value; int penalty_range;   // penalty_value == 1 -> plain argmax
   DecState* state; int n_new;               // state->kv_len += n_new, step += 1
+  // TOPK_TOPP_SAMPLING (Export_Whisper.py:263-307); temperature <= 0 selects the argmax heads above
+  float temperature; int top_k; float top_p; float rep_penalty; unsigned long long seed;
+  const float* noise; int noise_ld; int noise_rows;   // optional uniform noise [launch][B][top_k] (reproducible runs)
 };
 cudaError_t launch_select_token(const SelectArgs& a, cudaStream_t st);
 cudaError_t launch_softmax_pick(const float* logits, const float* add_bias, int vocab, int batch, int index,

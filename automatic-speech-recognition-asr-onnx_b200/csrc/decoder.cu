@@ -355,7 +355,7 @@ select_token_kernel(SelectArgs a) {
   const int b = blockIdx.x;
   float* lg = a.logits + (int64_t)b * a.vocab;
   const int gen = a.n_gen[b];
-  if (a.penalty_value != 1.0f && begin_bias == nullptr) {
+  if (a.penalty_value != 1.0f && begin_bias == nullptr && a.temperature <= 0.f) {
     // merged decode graph: penalty_value input is 1.0 until generated_count >= PENALTY_RANGE (:629-633)
     if (threadIdx.x == 0 && gen >= a.penalty_range) {
       const int ns = a.n_save[b];
@@ -372,6 +372,91 @@ select_token_kernel(SelectArgs a) {
   }
   float best = -INFINITY;
   int besti = 0x7fffffff;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (a.temperature > 0.f) {
+    // ---- TOPK_TOPP_SAMPLING: repetition penalty on every selected id -> / temperature -> sorted top-k ->
+    //      softmax -> keep while (cumsum - p) <= top_p -> Gumbel-max (Export_Whisper.py:281-307) ----
+    __shared__ float tk_v[64];
+    __shared__ int tk_i[64];
+    __shared__ float s_prev_v; __shared__ int s_prev_i;
+    const int ns0 = a.n_save[b];
+    const float rp = a.rep_penalty, irp = 1.0f / a.rep_penalty;
+    // membership of "previously selected" as a bitmap (vocab <= 65536; larger vocabularies search the list)
+    __shared__ unsigned hitmap[2048];
+    const bool use_map = a.vocab <= 65536;
+    if (rp != 1.0f && use_map) {
+      for (int i = threadIdx.x; i < 2048; i += blockDim.x) hitmap[i] = 0u;
+      __syncthreads();
+      for (int j = threadIdx.x; j < ns0; j += blockDim.x) {
+        const int id = a.save_id[(int64_t)b * a.save_ld + j];
+        atomicOr(&hitmap[id >> 5], 1u << (id & 31));
+      }
+      __syncthreads();
+    }
+    auto score = [&](int i) -> float {
+      float v = lg[i];
+      if (begin_bias) v += begin_bias[i];
+      if (rp != 1.0f) {
+        bool hit = false;
+        if (use_map) hit = (hitmap[i >> 5] >> (i & 31)) & 1u;
+        else for (int j = 0; j < ns0; ++j) hit |= (a.save_id[(int64_t)b * a.save_ld + j] == i);
+        if (hit) v = v < 0.f ? v * rp : v * irp;
+      }
+      return v;
+    };
+    const int K = min(a.top_k, 64);
+    if (threadIdx.x == 0) { s_prev_v = INFINITY; s_prev_i = -1; }
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {
+      const float pv = s_prev_v; const int pi = s_prev_i;
+      best = -INFINITY; besti = 0x7fffffff;
+      for (int i = threadIdx.x; i < a.vocab; i += blockDim.x) {
+        const float v = score(i);
+        const bool after = (v < pv) || (v == pv && i > pi);      // strictly after the previous pick in (value desc, index asc)
+        if (after && (v > best || (v == best && i < besti))) { best = v; besti = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+      }
+      if (lane == 0) { sv[warp] = best; si[warp] = besti; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+          if (sv[w] > best || (sv[w] == best && si[w] < besti)) { best = sv[w]; besti = si[w]; }
+        tk_v[k] = best; tk_i[k] = besti == 0x7fffffff ? 0 : besti;
+        s_prev_v = best; s_prev_i = besti;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const float it = 1.0f / a.temperature;
+      float mx = tk_v[0] * it, den = 0.f;
+      float pr[64];
+      for (int k = 0; k < K; ++k) { pr[k] = expf(tk_v[k] * it - mx); den += pr[k]; }
+      const int launch = a.state->step;
+      float cum = 0.f, gbest = -INFINITY; int win = 0;
+      for (int k = 0; k < K; ++k) {
+        const float p = pr[k] / den;
+        cum += p;
+        const bool keep = (cum - p) <= a.top_p;
+        float u;
+        if (a.noise && launch < a.noise_rows) {
+          u = a.noise[((int64_t)launch * a.batch + b) * a.noise_ld + k];
+        } else {                                       // counter-based hash (splitmix64) keyed by (seed, launch, b, k)
+          unsigned long long z = a.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(((int64_t)launch * a.batch + b) * 64 + k + 1);
+          z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+          u = (float)((z >> 40) + 0.5) * (1.0f / 16777216.0f);
+        }
+        u = fminf(fmaxf(u, 1.0e-7f), 1.0f - 1.0e-7f);
+        const float g = keep ? tk_v[k] * it - logf(-logf(u)) : -INFINITY;
+        if (g > gbest) { gbest = g; win = k; }
+      }
+      best = tk_v[win]; besti = tk_i[win];
+    }
+  } else {
   for (int i = threadIdx.x; i < a.vocab; i += blockDim.x) {
     float v = lg[i];
     if (begin_bias) v += begin_bias[i];
@@ -383,10 +468,11 @@ select_token_kernel(SelectArgs a) {
     const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
     if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { sv[warp] = best; si[warp] = besti; }
   __syncthreads();
+  }
   if (threadIdx.x == 0) {
+    if (a.temperature <= 0.f)
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
       if (sv[w] > best || (sv[w] == best && si[w] < besti)) { best = sv[w]; besti = si[w]; }
     if (besti == 0x7fffffff) besti = 0;       // all -inf / NaN row: torch.argmax returns 0

@@ -78,6 +78,9 @@ struct b200asr_engine {
   bool mega_timing = false; unsigned long long* timing = nullptr; static constexpr int kTimingCap = 16384;
   // streaming decode kernel (decoder_ring.cu)
   bool use_attn_tc = true;
+  // sampling head (TOPK_TOPP_SAMPLING); temperature <= 0 = argmax heads
+  float samp_temperature = 0.f; int samp_top_k = 10; float samp_top_p = 0.95f; float samp_rep = 1.0f;
+  unsigned long long samp_seed = 0; float* samp_noise = nullptr; int samp_noise_rows = 0, samp_noise_ld = 0;
   bool use_ring = true; bool ring_fine = false; int ring_debug = 0; unsigned long long* ring_ll = nullptr; size_t ring_ll_words = 0;
   CUtensorMap cross_map{}; int cmap_B = -1, cmap_T = -1; int ring_task_inv = 0;
   std::string graph_key;
@@ -330,15 +333,17 @@ int enqueue_decoder(b200asr_engine* e, const int* tokens_dev, int n_new, bool fi
   s.stop_ids = e->d_stop; s.n_stop = (int)e->stop_ids.size(); s.limit = e->limit;
   s.penalty_value = e->repeat_penalty; s.penalty_range = e->penalty_range;
   s.state = e->dstate; s.n_new = n_new;
+  s.temperature = e->samp_temperature; s.top_k = e->samp_top_k; s.top_p = e->samp_top_p; s.rep_penalty = e->samp_rep;
+  s.seed = e->samp_seed; s.noise = e->samp_noise; s.noise_ld = e->samp_noise_ld; s.noise_rows = e->samp_noise_rows;
   KL(launch_select_token(s, e->st));
   e->launches++;   // select = 2 kernels
   return B200ASR_OK;
 }
 
 int ensure_step_graph(b200asr_engine* e) {
-  char key[256];
-  snprintf(key, sizeof key, "%d/%d/%d/%g/%d/%zu", e->B, e->T_enc, e->limit, e->repeat_penalty, e->penalty_range,
-           e->stop_ids.size());
+  char key[384];
+  snprintf(key, sizeof key, "%d/%d/%d/%g/%d/%zu/%g/%d/%g/%g/%llu/%p", e->B, e->T_enc, e->limit, e->repeat_penalty, e->penalty_range,
+           e->stop_ids.size(), e->samp_temperature, e->samp_top_k, e->samp_top_p, e->samp_rep, e->samp_seed, (void*)e->samp_noise);
   if (e->step_graph && e->graph_key == key) return B200ASR_OK;
   if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
   cudaGraph_t graph = nullptr;
@@ -367,7 +372,7 @@ int launch_step(b200asr_engine* e) {
 
 // ---- persistent decoder kernel plumbing ------------------------------------------------------
 bool mega_ok(b200asr_engine* e, int first_n_new) {
-  return e->use_mega && mega_supported(e->B, first_n_new, e->cfg.d_model, e->cfg.ffn) && e->penalty_range <= 32 &&
+  return e->use_mega && e->samp_temperature <= 0.f && mega_supported(e->B, first_n_new, e->cfg.d_model, e->cfg.ffn) && e->penalty_range <= 32 &&
          e->B * (first_n_new > 1 ? first_n_new : 1) <= 64 &&
          mega_smem_bytes(e->cfg.d_model, e->cfg.ffn, e->T_enc, e->cfg.max_target) <= 220 * 1024;
 }
@@ -461,7 +466,7 @@ int run_mega(b200asr_engine* e, int n_iters, const int* first_tokens, int first_
 // ---- streaming decode kernel plumbing (decoder_ring.cu) ----------------------------------------
 bool ring_ok(b200asr_engine* e) {
   const b200asr_config& c = e->cfg;
-  if (!e->use_ring || !e->use_mega || e->act_dtype != kBF16 || e->penalty_range > 32) return false;
+  if (!e->use_ring || !e->use_mega || e->samp_temperature > 0.f || e->act_dtype != kBF16 || e->penalty_range > 32) return false;
   if (e->num_sms % kRingTaskMul == 0) return false;
   if (!ring_supported(e->B, c.d_model, c.ffn, c.n_heads, c.vocab, e->num_sms)) return false;
   if (c.d_model / 8 > 256) return false;         // TMA box rows
@@ -601,7 +606,7 @@ void b200asr_destroy(b200asr_engine* e) {
                   e->hidden, e->stem, e->xhat, e->qkv, e->ctx, e->ffn, e->S, e->P, e->cross_kv, e->kcache, e->vcache,
                   e->dx, e->dq, e->dctx, e->dffn, e->logits, e->prob, e->d_prompt, e->cur_token, e->tokens, e->n_gen,
                   e->finished, e->save_id, e->n_save, e->selected_hist, e->d_stop, e->dstate, e->mega_layers, e->pf_blocks,
-                  e->mega_bar, e->cand_val, e->cand_idx, e->timing, e->ring_ll};
+                  e->mega_bar, e->cand_val, e->cand_idx, e->timing, e->ring_ll, e->samp_noise};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -783,6 +788,26 @@ int b200asr_set_decode_options(b200asr_engine* e, const int32_t* stop_ids, int32
   e->limit_cfg = generate_limit > 0 ? generate_limit : 0;
   e->repeat_penalty = repeat_penalty;
   e->penalty_range = penalty_range;
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+  return B200ASR_OK;
+}
+
+int b200asr_set_sampling(b200asr_engine* e, float temperature, int32_t top_k, float top_p, float repetition_penalty,
+                         uint64_t seed, const float* noise_host, int32_t noise_rows) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (temperature > 0.f && (top_k < 1 || top_k > 64 || top_k > e->cfg.vocab || !(top_p > 0.f) || !(repetition_penalty > 0.f)))
+    return e->fail(B200ASR_E_INVALID, "bad sampling options (1 <= top_k <= 64, top_p > 0, repetition_penalty > 0)");
+  e->samp_temperature = temperature; e->samp_top_k = top_k; e->samp_top_p = top_p; e->samp_rep = repetition_penalty;
+  e->samp_seed = seed;
+  if (e->samp_noise) { cudaFree(e->samp_noise); e->samp_noise = nullptr; }
+  e->samp_noise_rows = 0; e->samp_noise_ld = top_k;
+  if (temperature > 0.f && noise_host && noise_rows > 0) {
+    const size_t n = (size_t)noise_rows * e->cfg.max_batch * top_k;
+    CK(cudaMalloc(&e->samp_noise, n * 4));
+    CK(b200_copy_sync(e, e->samp_noise, noise_host, n * 4, cudaMemcpyHostToDevice));
+    e->samp_noise_rows = noise_rows;
+  }
   if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
   return B200ASR_OK;
 }

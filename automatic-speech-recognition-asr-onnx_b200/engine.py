@@ -49,6 +49,7 @@ class WhisperEngine:
         self.h = h
         self.max_batch = max_batch
         self.batch = 0
+        self.T_enc = 0                         # encoder positions of the clips currently resident
         for name, arr in tensors.items():
             a = np.ascontiguousarray(arr, dtype=np.float32)
             self._ck(self.lib.b200asr_set_tensor(self.h, name.encode(), _f32p(a), a.size))
@@ -103,11 +104,13 @@ class WhisperEngine:
     def encode(self, pcm: np.ndarray):
         pcm, code = self._pcm(pcm)
         self.batch = pcm.shape[0]
+        self.T_enc = (pcm.shape[1] // self.dims.hop + 1) // 2
         self._ck(self.lib.b200asr_encode(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1]))
 
     def upload_pcm(self, pcm: np.ndarray):
         pcm, code = self._pcm(pcm)
         self.batch = pcm.shape[0]
+        self.T_enc = (pcm.shape[1] // self.dims.hop + 1) // 2
         self._ck(self.lib.b200asr_upload_pcm(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1]))
 
     def encode_resident(self):
@@ -119,6 +122,18 @@ class WhisperEngine:
         s = np.asarray(list(stop_ids), dtype=np.int32)
         self._ck(self.lib.b200asr_set_decode_options(self.h, _i32p(s) if s.size else None, s.size, generate_limit,
                                                      float(repeat_penalty), penalty_range))
+
+    def set_sampling(self, temperature: float = 0.0, top_k: int = 10, top_p: float = 0.95, repetition_penalty: float = 1.0,
+                     seed: int = 0, noise: Optional[np.ndarray] = None):
+        """TOPK_TOPP_SAMPLING head (Whisper/Export_Whisper.py:263-307); temperature <= 0 = argmax heads.
+        noise: optional uniform numbers [launches][max_batch][top_k] for reproducible runs."""
+        n = None
+        rows = 0
+        if noise is not None:
+            n = np.ascontiguousarray(noise, dtype=np.float32).reshape(-1, self.max_batch, top_k)
+            rows = n.shape[0]
+        self._ck(self.lib.b200asr_set_sampling(self.h, float(temperature), int(top_k), float(top_p),
+                                               float(repetition_penalty), int(seed), _f32p(n), rows))
 
     def _prompt(self, prompt) -> np.ndarray:
         p = np.asarray(prompt, dtype=np.int32)
@@ -159,6 +174,7 @@ class WhisperEngine:
                    out_lens: Optional[np.ndarray] = None):
         pcm, code = self._pcm(pcm)
         self.batch = pcm.shape[0]
+        self.T_enc = (pcm.shape[1] // self.dims.hop + 1) // 2
         p = self._prompt(prompt)
         ld = self.dims.max_target
         toks = out_tokens if out_tokens is not None else np.zeros((self.batch, ld), np.int32)

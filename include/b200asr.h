@@ -82,6 +82,14 @@ int b200asr_encode_resident(b200asr_engine* e);
  * output); first_token_out (optional) [batch] = argmax after begin-suppress. */
 int b200asr_set_decode_options(b200asr_engine* e, const int32_t* stop_ids, int32_t n_stop, int32_t generate_limit,
                                float repeat_penalty, int32_t penalty_range);
+/* sampling head = TOPK_TOPP_SAMPLING of Whisper/Export_Whisper.py:263-307 (strategy "sampling" of
+ * Whisper/Inference_Whisper_ONNX.py:294-304, controls bound at :571-582): HF-style repetition penalty over every
+ * id selected so far, / temperature, sorted top-k (<= 64), top-p on the sorted softmax, Gumbel-max.
+ * temperature <= 0 switches back to the argmax heads.  noise_host (optional) = uniform numbers
+ * [noise_rows][max_batch][top_k] consumed launch by launch (prefill = row 0) so a run is reproducible against
+ * the oracle; beyond noise_rows, or with noise_host NULL, a counter-based generator keyed by `seed` is used. */
+int b200asr_set_sampling(b200asr_engine* e, float temperature, int32_t top_k, float top_p, float repetition_penalty,
+                         uint64_t seed, const float* noise_host, int32_t noise_rows);
 int b200asr_prefill(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt, float* logits_out,
                     int32_t* first_token_out);
 /* one decode launch.  token_in (optional) [batch] overrides the fed-back token

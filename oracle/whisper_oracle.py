@@ -427,6 +427,65 @@ def apply_penalty(logits, save_id, penalty_value: float, penalty_range: int):
     return logits.scatter(1, idx, pen)
 
 
+def topk_topp_sample(logits, temperature: float, top_k: int, top_p: float, repetition_penalty: float,
+                     previous_ids, noise):
+    """TOPK_TOPP_SAMPLING.forward (Whisper/Export_Whisper.py:281-307) with the uniform noise supplied by the
+    caller instead of drawn by torch.rand_like (:298-300), so a run is reproducible: HF-style repetition penalty on
+    every previously selected id (negative logits * p, positive / p, gather-then-scatter), / temperature, sorted
+    top-k, softmax, keep while (cumsum - prob) <= top_p, Gumbel-max over the kept scores.
+    logits [B, vocab], previous_ids int [B, n], noise [B, top_k] in (0, 1).  Returns (sampled_id [B,1] int32, save_id)."""
+    rp = torch.tensor(float(repetition_penalty), dtype=torch.float32)
+    prev = previous_ids.long()
+    prev_logits = torch.gather(logits, 1, prev)
+    prev_scores = torch.where(prev_logits < 0.0, prev_logits * rp, prev_logits * torch.reciprocal(rp))
+    scores = torch.scatter(logits, 1, prev, prev_scores)
+    scores = scores * torch.reciprocal(torch.tensor(float(temperature), dtype=torch.float32))
+    sorted_scores, sorted_indices = torch.topk(scores, k=int(top_k), dim=-1, largest=True, sorted=True)
+    probs = torch.softmax(sorted_scores, dim=-1)
+    cums = torch.cumsum(probs, dim=-1)
+    keep = (cums - probs) <= top_p
+    sorted_scores = torch.where(keep, sorted_scores, torch.tensor(float("-inf")))
+    u = torch.clamp(torch.as_tensor(noise, dtype=torch.float32), 1.0e-7, 1.0 - 1.0e-7)
+    gumbel = -torch.log(-torch.log(u))
+    winner = torch.argmax(sorted_scores + gumbel, dim=-1, keepdim=True)
+    sampled = torch.gather(sorted_indices, 1, winner).int()
+    return sampled, torch.cat([previous_ids.int(), sampled], dim=-1)
+
+
+def sampling_transcribe(pcm_int16: np.ndarray, fw, dims: "WhisperDims", prompt: Sequence[int], stop_tokens: Sequence[int],
+                        max_new: int, temperature: float, top_k: int, top_p: float, repetition_penalty: float,
+                        noise: np.ndarray):
+    """The `sampling` strategy of the driver (Inference_Whisper_ONNX.py:294-304, graphs Shared_Merged.py:925-975):
+    begin-suppress + sampling head on the prefill logits with an empty history, then one sampling head per decode
+    launch fed with every id selected so far.  noise [launch][top_k]."""
+    stop = set(int(s) for s in stop_tokens)
+    audio = prepare_audio(pcm_int16)
+    ck, cv, _ = encoder(audio, fw, dims)
+    sk, sv = empty_self_kv(dims)
+    ids = torch.tensor([list(prompt)], dtype=torch.int32)
+    limit = min(max(0, dims.max_target - ids.shape[-1]), int(max_new))
+    sk, sv, logits = decoder(ids, 0, sk, sv, ck, cv, fw, dims)
+    kv_len = ids.shape[-1]
+    save_id = torch.zeros(1, 0, dtype=torch.int32)
+    sampled, save_id = topk_topp_sample(begin_suppress(logits, fw), temperature, top_k, top_p, repetition_penalty, save_id,
+                                        noise[0:1])
+    selected = int(sampled[0, 0])
+    tokens, generated, step = [], 0, 0
+    if selected not in stop and limit > 0:
+        generated = 1
+        tokens.append(selected)
+    while generated < limit and selected not in stop:
+        sk, sv, logits = decoder(torch.tensor([[selected]], dtype=torch.int32), kv_len, sk, sv, ck, cv, fw, dims)
+        kv_len += 1
+        step += 1
+        sampled, save_id = topk_topp_sample(logits, temperature, top_k, top_p, repetition_penalty, save_id, noise[step:step + 1])
+        selected = int(sampled[0, 0])
+        if selected not in stop:
+            generated += 1
+            tokens.append(selected)
+    return dict(tokens=tokens, selected=save_id[0].tolist())
+
+
 def no_speech_prob(logits, suppress_tokens, no_speech_token: int) -> torch.Tensor:
     """Export_Whisper.py:334-348."""
     unsup = torch.zeros(1, logits.shape[-1])
