@@ -20,6 +20,13 @@ class Config(C.Structure):
         "n_fft", "hop", "max_batch", "max_samples", "precision", "device", "use_tensor_cores")]
 
 
+class NarConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "kind", "n_mels", "nfft", "win", "hop", "lfr_m", "lfr_n", "d_model", "n_heads", "ffn", "n_blocks0", "n_blocks",
+        "n_tp_blocks", "vocab", "blank_id", "n_prompt", "n_lang", "fsmn_kernel", "max_batch", "max_samples", "precision",
+        "device", "use_tensor_cores")] + [("ln_eps", C.c_float)]
+
+
 # every symbol include/b200asr.h declares: (restype, argtypes)
 _P = C.c_void_p
 _I32P = C.POINTER(C.c_int32)
@@ -48,6 +55,16 @@ SYMBOLS = {
     "b200asr_synchronize": (C.c_int, [_P]),
     "b200asr_kernel_launches": (C.c_int64, [_P]),
     "b200asr_num_sms": (C.c_int, [_P]),
+    "b200asr_nar_create": (C.c_int, [C.POINTER(NarConfig), C.POINTER(C.c_void_p)]),
+    "b200asr_nar_destroy": (None, [C.c_void_p]),
+    "b200asr_nar_last_error": (C.c_char_p, [C.c_void_p]),
+    "b200asr_nar_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.c_int64]),
+    "b200asr_nar_finalize_weights": (C.c_int, [C.c_void_p]),
+    "b200asr_nar_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+    "b200asr_nar_get_stage": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64)]),
+    "b200asr_nar_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "b200asr_nar_stream": (C.c_void_p, [C.c_void_p]),
     "b200asr_test_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F32P, _F32P, _F32P, _F32P,
                                     C.c_int32, _F32P, C.c_char_p, C.c_int32]),
 }

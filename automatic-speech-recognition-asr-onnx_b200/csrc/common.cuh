@@ -9,7 +9,7 @@
 namespace b200asr {
 
 enum DType : int { kF32 = 0, kBF16 = 1 };
-enum Act : int { kActNone = 0, kActGelu = 1 };
+enum Act : int { kActNone = 0, kActGelu = 1, kActRelu = 2 };
 
 typedef __nv_bfloat16 bf16;
 

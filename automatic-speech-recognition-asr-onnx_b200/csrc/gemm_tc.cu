@@ -246,6 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int64_t row = m0 + rr;
               float v = my[rr * 33 + lane] + bv;
               if (e.act == kActGelu) v = gelu_erf(v);
+              else if (e.act == kActRelu) v = fmaxf(v, 0.f);
               v += res[rr];
               const int64_t o = (int64_t)z * e.sC + row * e.ldc + col;
               if (e.c_dtype == kF32) reinterpret_cast<float*>(e.C)[o] = v;

@@ -1,0 +1,535 @@
+// Non-autoregressive SANM path (SenseVoiceSmall): Kaldi fbank front end -> LFR + CMVN + prompts -> SANM encoder
+// blocks (self-attention || FSMN memory, position-wise FFN) -> CTC head with greedy collapse, one call per batch
+// of equal-length clips.  Replaces `ort_session_A.run_with_iobinding` of
+// /root/reference/SenseVoice/Inference_SenseVoice_ONNX.py:303; the math follows SENSE_VOICE.forward,
+// /root/reference/SenseVoice/Export_SenseVoice.py:271-296 (block :227-258, folds :208-220, front end :139-169).
+//
+// Linear layers run on the engine's GEMMs (tcgen05 in bf16 mode, CUDA cores in the fp32 parity mode); attention uses
+// the fused tcgen05 kernel when the head dimension is 64 and the unfused batched products otherwise (SenseVoiceSmall
+// has head_dim 128); the kernels in this file are the HBM-bound pieces around them.
+#include "common.cuh"
+#include "../../include/b200asr.h"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace b200asr;
+
+namespace {
+
+constexpr int kFbFrames = 8;          // frames per CTA of the fbank kernel
+constexpr int kFbThreads = 288;       // >= nfft/2 + 1 = 257 frequency bins
+
+// ---- Kaldi fbank: conv1d with the folded [2F][win] basis (stride hop, snip-edges) -> power -> mel -> log ----
+__global__ void __launch_bounds__(kFbThreads)
+kaldi_fbank_kernel(const void* __restrict__ pcm, int pcm_is_f32, int n_samples, const float* __restrict__ basis_t /*[win][2F]*/,
+                   const float* __restrict__ melw /*[F][n_mels]*/, int win, int hop, int F, int n_mels, int frames,
+                   float log_floor, float* __restrict__ mel /*[B][frames][n_mels]*/) {
+  extern __shared__ float fsm[];
+  const int span = (kFbFrames - 1) * hop + win;
+  float* xs = fsm;                       // [span]
+  float* pw = fsm + span;                // [kFbFrames][F]
+  const int b = blockIdx.y, f0 = blockIdx.x * kFbFrames;
+  const int64_t base = (int64_t)b * n_samples + (int64_t)f0 * hop;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    const int64_t s = (int64_t)f0 * hop + i;
+    float v = 0.f;
+    if (s < n_samples) v = pcm_is_f32 ? reinterpret_cast<const float*>(pcm)[base + i]
+                                      : (float)reinterpret_cast<const short*>(pcm)[base + i];
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int f = threadIdx.x;
+  if (f < F) {
+    float re[kFbFrames], im[kFbFrames];
+#pragma unroll
+    for (int j = 0; j < kFbFrames; ++j) { re[j] = 0.f; im[j] = 0.f; }
+    for (int k = 0; k < win; ++k) {
+      const float c = basis_t[(int64_t)k * 2 * F + f];
+      const float s = basis_t[(int64_t)k * 2 * F + F + f];
+#pragma unroll
+      for (int j = 0; j < kFbFrames; ++j) {
+        const float x = xs[j * hop + k];
+        re[j] = fmaf(c, x, re[j]);
+        im[j] = fmaf(s, x, im[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kFbFrames; ++j) pw[j * F + f] = re[j] * re[j] + im[j] * im[j];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < kFbFrames * n_mels; o += blockDim.x) {
+    const int j = o / n_mels, m = o - j * n_mels;
+    if (f0 + j >= frames) continue;
+    float acc = 0.f;
+    for (int q = 0; q < F; ++q) acc = fmaf(pw[j * F + q], melw[(int64_t)q * n_mels + m], acc);
+    mel[((int64_t)b * frames + f0 + j) * n_mels + m] = logf(fmaxf(acc, log_floor));
+  }
+}
+
+// ---- LFR stack (m frames every n, clamped gather) + CMVN + sinusoid position; prompt rows in front ----
+__global__ void lfr_cmvn_kernel(const float* __restrict__ mel, int frames, int n_mels, int lfr_m, int lfr_n, int T_lfr, int n_prompt,
+                                const float* __restrict__ means, const float* __restrict__ vars, const float* __restrict__ pos,
+                                const float* __restrict__ lang_embed, const float* __restrict__ sys_embed,
+                                const int* __restrict__ lang_idx, float* __restrict__ x /*[B][n_prompt + T_lfr][feat]*/) {
+  const int feat = n_mels * lfr_m;
+  const int t = blockIdx.x, b = blockIdx.y;
+  float* xr = x + ((int64_t)b * (n_prompt + T_lfr) + t) * feat;
+  if (t < n_prompt) {
+    const float* src = t == 0 ? lang_embed + (int64_t)lang_idx[b] * feat : sys_embed + (int64_t)(t - 1) * feat;
+    for (int c = threadIdx.x; c < feat; c += blockDim.x) xr[c] = src[c];
+    return;
+  }
+  const int tl = t - n_prompt;
+  const int half = (lfr_m - 1) / 2;
+  for (int c = threadIdx.x; c < feat; c += blockDim.x) {
+    const int j = c / n_mels, m = c - j * n_mels;
+    int fr = tl * lfr_n + j - half;
+    fr = max(0, min(fr, frames - 1));
+    const float v = mel[((int64_t)b * frames + fr) * n_mels + m];
+    xr[c] = (v + means[c]) * vars[c] + pos[(int64_t)tl * feat + c];
+  }
+}
+
+// ---- FSMN memory: depth-wise conv over time on the value rows (+ bias = linear_out's bias, + residual) ----
+template <typename T>
+__global__ void fsmn_kernel(const T* __restrict__ qkv, int64_t ld_qkv, int v_off, const float* __restrict__ w /*[D][k]*/,
+                            const float* __restrict__ bias, const float* __restrict__ resid /*[M][D] or null*/, int Tn, int D, int ksz,
+                            float* __restrict__ out /*[M][D]*/) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  const int half = (ksz - 1) / 2;
+  const int64_t row0 = (int64_t)b * Tn;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = bias[c];
+    for (int j = 0; j < ksz; ++j) {
+      const int tt = t + j - half;
+      if (tt >= 0 && tt < Tn) acc = fmaf(w[c * ksz + j], to_f<T>(qkv[(row0 + tt) * ld_qkv + v_off + c]), acc);
+    }
+    if (resid) acc += resid[(row0 + t) * D + c];
+    out[(row0 + t) * D + c] = acc;
+  }
+}
+
+// ---- CTC head: per-frame argmax (warp per row), then greedy collapse per utterance ----
+__global__ void __launch_bounds__(256)
+row_argmax_kernel(const float* __restrict__ logits, int rows, int vocab, int* __restrict__ ids) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* lr = logits + (int64_t)row * vocab;
+  float best = -INFINITY; int bi = 0x7fffffff;
+  for (int i = lane; i < vocab; i += 32) { const float v = lr[i]; if (v > best) { best = v; bi = i; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) ids[row] = bi == 0x7fffffff ? 0 : bi;
+}
+// keep frame t when id[t] != id[(t+1) % T] and id[t] != blank (Export_SenseVoice.py:289-294)
+__global__ void ctc_collapse_kernel(const int* __restrict__ ids, int Tn, int blank, int* __restrict__ tokens, int tokens_ld,
+                                    int* __restrict__ lens) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const int* r = ids + (int64_t)b * Tn;
+  int n = 0;
+  for (int t = 0; t < Tn; ++t) {
+    const int id = r[t], nx = r[t + 1 == Tn ? 0 : t + 1];
+    if (id != nx && id != blank && n < tokens_ld) tokens[(int64_t)b * tokens_ld + n++] = id;
+  }
+  lens[b] = n;
+}
+
+__global__ void nar_f32_to_bf16(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void nar_bf16_to_f32(const bf16* __restrict__ in, float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+struct NarTensor { void* ptr = nullptr; int64_t numel = 0; int dtype = kF32; };
+std::string g_nar_create_error;
+
+}  // namespace
+
+struct b200asr_nar {
+  b200asr_nar_config cfg{};
+  cudaStream_t st = nullptr;
+  std::string err;
+  int num_sms = 148;
+  int64_t launches = 0;
+  bool finalized = false;
+  int act = kF32; size_t es = 4;
+  std::map<std::string, NarTensor> w;
+  float* basis_t = nullptr;
+  float* stage_buf = nullptr; int64_t stage_cap = 0;
+  // per-call state
+  int B = 0, n_samples = 0, frames = 0, T_lfr = 0, T = 0, pcm_dtype = B200ASR_PCM_I16;
+  void* pcm = nullptr; float* mel = nullptr; float* feats = nullptr; float* hidden = nullptr; float* resid = nullptr;
+  void *xhat = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *P = nullptr;
+  float* S = nullptr; float* logits = nullptr; float* enc_out = nullptr;
+  int *frame_ids = nullptr, *tokens = nullptr, *lens = nullptr, *lang = nullptr;
+  int* h_pinned = nullptr;
+  int max_frames = 0, max_T = 0;
+
+  int fail(int code, const std::string& m) { err = m; return code; }
+  int cuda_fail(cudaError_t e, const char* what) { err = std::string(what) + ": " + cudaGetErrorString(e); return B200ASR_E_CUDA; }
+};
+
+#define NCK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return e->cuda_fail(_e, #expr); } while (0)
+#define NKL(expr) do { cudaError_t _e = (expr); e->launches++; if (_e != cudaSuccess) return e->cuda_fail(_e, #expr); } while (0)
+#define NRET(expr) do { int _r = (expr); if (_r != B200ASR_OK) return _r; } while (0)
+
+namespace {
+
+bool nar_is_matrix(const std::string& n) {
+  return n.size() > 2 && n.compare(n.size() - 2, 2, ".w") == 0 && n.find("fsmn") == std::string::npos;
+}
+const void* NW(b200asr_nar* e, const std::string& n) { return e->w[n].ptr; }
+const float* NWF(b200asr_nar* e, const std::string& n) { return reinterpret_cast<const float*>(e->w[n].ptr); }
+
+int nar_need(b200asr_nar* e, const std::string& n, int64_t numel) {
+  auto it = e->w.find(n);
+  if (it == e->w.end()) return e->fail(B200ASR_E_MISSING, "missing weight tensor '" + n + "'");
+  if (it->second.numel != numel)
+    return e->fail(B200ASR_E_INVALID, "tensor '" + n + "' has " + std::to_string(it->second.numel) + " elements, expected " + std::to_string(numel));
+  return B200ASR_OK;
+}
+
+int nar_gemm(b200asr_nar* e, const GemmArgs& g) {
+  if (e->act == kBF16 && e->cfg.use_tensor_cores && gemm_tc_supported(g)) {
+    std::string msg;
+    cudaError_t r = launch_gemm_tc(g, e->num_sms, e->st, &msg);
+    if (r != cudaErrorNotSupported) {
+      e->launches++;
+      if (r != cudaSuccess) return e->fail(B200ASR_E_CUDA, "gemm_tc: " + (msg.empty() ? std::string(cudaGetErrorString(r)) : msg));
+      return B200ASR_OK;
+    }
+    cudaGetLastError();
+  }
+  NKL(launch_gemm_simt(g, e->st));
+  return B200ASR_OK;
+}
+
+GemmArgs nar_linear(b200asr_nar* e, const void* A, int64_t lda, const std::string& wn, const std::string& bn, void* C, int64_t ldc,
+                    int c_dtype, int M, int N, int K) {
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.a_dtype = e->act;
+  g.B = NW(e, wn); g.ldb = K; g.b_dtype = e->act;
+  g.C = C; g.ldc = ldc; g.c_dtype = c_dtype;
+  g.bias = bn.empty() ? nullptr : NWF(e, bn);
+  g.M = M; g.N = N; g.K = K;
+  return g;
+}
+
+template <typename T>
+int nar_alloc(b200asr_nar* e, T** p, size_t bytes) {
+  NCK(cudaMalloc(reinterpret_cast<void**>(p), bytes ? bytes : 16));
+  NCK(cudaMemsetAsync(*p, 0, bytes ? bytes : 16, e->st));
+  return B200ASR_OK;
+}
+
+int nar_block(b200asr_nar* e, int i, const float* x_in, int din) {
+  const b200asr_nar_config& c = e->cfg;
+  const int D = c.d_model, H = c.n_heads, dh = D / H, T = e->T, B = e->B, M = B * T, ad = e->act;
+  const size_t es = e->es;
+  const std::string p = "blk" + std::to_string(i) + ".";
+  NKL(launch_layernorm(x_in, din, NWF(e, p + "norm1.g"), NWF(e, p + "norm1.b"), e->xhat, ad, din, M, din, c.ln_eps, e->st));
+  NRET(nar_gemm(e, nar_linear(e, e->xhat, din, p + "qkv.w", p + "qkv.b", e->qkv, 3 * D, ad, M, 3 * D, din)));
+  // FSMN memory (+ x when the block keeps its width) -> the fp32 residual the out-projection adds
+  const float* res_in = (din == D) ? x_in : nullptr;
+  if (ad == kBF16)
+    fsmn_kernel<bf16><<<dim3(T, B), 256, 0, e->st>>>((const bf16*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, p + "fsmn.b"), res_in, T, D, c.fsmn_kernel, e->resid);
+  else
+    fsmn_kernel<float><<<dim3(T, B), 256, 0, e->st>>>((const float*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, p + "fsmn.b"), res_in, T, D, c.fsmn_kernel, e->resid);
+  NKL(cudaGetLastError());
+  if (ad == kBF16 && c.use_tensor_cores && dh == 64 && attention_tc_supported(T, D, H)) {
+    std::string msg;
+    cudaError_t r = launch_attention_tc(e->qkv, e->ctx, B, T, D, H, e->st, &msg);
+    e->launches++;
+    if (r != cudaSuccess) return e->fail(B200ASR_E_CUDA, "attention_tc: " + (msg.empty() ? std::string(cudaGetErrorString(r)) : msg));
+  } else {
+    GemmArgs s;
+    s.A = e->qkv; s.lda = 3 * D; s.sAo = (int64_t)T * 3 * D; s.sAi = dh; s.a_dtype = ad;
+    s.B = (char*)e->qkv + (size_t)D * es; s.ldb = 3 * D; s.sBo = (int64_t)T * 3 * D; s.sBi = dh; s.b_dtype = ad;
+    s.C = e->S; s.ldc = T; s.sCo = (int64_t)H * T * T; s.sCi = (int64_t)T * T; s.c_dtype = kF32;
+    s.M = T; s.N = T; s.K = dh; s.batch = B * H; s.batch_inner = H;
+    NKL(launch_gemm_simt(s, e->st));
+    NKL(launch_softmax_rows(e->S, e->P, ad, (int64_t)B * H * T, T, e->st));
+    GemmArgs o;
+    o.A = e->P; o.lda = T; o.sAo = (int64_t)H * T * T; o.sAi = (int64_t)T * T; o.a_dtype = ad;
+    o.B = (char*)e->qkv + (size_t)2 * D * es; o.ldb = 3 * D; o.sBo = (int64_t)T * 3 * D; o.sBi = dh; o.b_dtype = ad;
+    o.transB = 1;
+    o.C = e->ctx; o.ldc = D; o.sCo = (int64_t)T * D; o.sCi = dh; o.c_dtype = ad;
+    o.M = T; o.N = dh; o.K = T; o.batch = B * H; o.batch_inner = H;
+    NKL(launch_gemm_simt(o, e->st));
+  }
+  {
+    GemmArgs g = nar_linear(e, e->ctx, D, p + "out.w", "", e->hidden, D, kF32, M, D, D);
+    g.residual = e->resid; g.ldr = D;
+    NRET(nar_gemm(e, g));
+  }
+  NKL(launch_layernorm(e->hidden, D, NWF(e, p + "norm2.g"), NWF(e, p + "norm2.b"), e->xhat, ad, D, M, D, c.ln_eps, e->st));
+  {
+    GemmArgs g = nar_linear(e, e->xhat, D, p + "w1.w", p + "w1.b", e->ffn, c.ffn, ad, M, c.ffn, D);
+    g.act = kActRelu;
+    NRET(nar_gemm(e, g));
+    GemmArgs g2 = nar_linear(e, e->ffn, c.ffn, p + "w2.w", p + "w2.b", e->hidden, D, kF32, M, D, c.ffn);
+    g2.residual = e->hidden; g2.ldr = D;
+    NRET(nar_gemm(e, g2));
+  }
+  return B200ASR_OK;
+}
+
+int nar_forward(b200asr_nar* e) {
+  const b200asr_nar_config& c = e->cfg;
+  const int F = c.nfft / 2 + 1, feat = c.n_mels * c.lfr_m, D = c.d_model, B = e->B, T = e->T, M = B * T;
+  {
+    const int span = (kFbFrames - 1) * c.hop + c.win;
+    const size_t smem = (size_t)(span + kFbFrames * F) * sizeof(float);
+    dim3 grid((e->frames + kFbFrames - 1) / kFbFrames, B);
+    kaldi_fbank_kernel<<<grid, kFbThreads, smem, e->st>>>(e->pcm, e->pcm_dtype == B200ASR_PCM_F32, e->n_samples, e->basis_t,
+                                                          NWF(e, "mel_filters"), c.win, c.hop, F, c.n_mels, e->frames,
+                                                          1.1920928955078125e-07f, e->mel);
+    NKL(cudaGetLastError());
+  }
+  lfr_cmvn_kernel<<<dim3(T, B), 256, 0, e->st>>>(e->mel, e->frames, c.n_mels, c.lfr_m, c.lfr_n, e->T_lfr, c.n_prompt,
+                                                 NWF(e, "cmvn_means"), NWF(e, "cmvn_vars"), NWF(e, "speech_position"),
+                                                 NWF(e, "language_embed"), NWF(e, "system_embed"), e->lang, e->feats);
+  NKL(cudaGetLastError());
+  const int n_main = c.n_blocks0 + c.n_blocks, n_all = n_main + c.n_tp_blocks;
+  for (int i = 0; i < n_all; ++i) {
+    NRET(nar_block(e, i, i == 0 ? e->feats : e->hidden, i == 0 ? feat : D));
+    if (i == n_main - 1)      // after_norm between the encoder blocks and the transformer-postnet blocks (:266)
+      NKL(launch_layernorm(e->hidden, D, NWF(e, "after_norm.g"), NWF(e, "after_norm.b"), e->hidden, kF32, D, M, D, c.ln_eps, e->st));
+  }
+  NKL(launch_layernorm(e->hidden, D, NWF(e, "tp_norm.g"), NWF(e, "tp_norm.b"), e->enc_out, kF32, D, M, D, c.ln_eps, e->st));
+  NKL(launch_layernorm(e->hidden, D, NWF(e, "tp_norm.g"), NWF(e, "tp_norm.b"), e->xhat, e->act, D, M, D, c.ln_eps, e->st));
+  NRET(nar_gemm(e, nar_linear(e, e->xhat, D, "ctc.w", "ctc.b", e->logits, c.vocab, kF32, M, c.vocab, D)));
+  row_argmax_kernel<<<(M + 7) / 8, 256, 0, e->st>>>(e->logits, M, c.vocab, e->frame_ids);
+  NKL(cudaGetLastError());
+  ctc_collapse_kernel<<<B, 32, 0, e->st>>>(e->frame_ids, T, c.blank_id, e->tokens, e->max_T, e->lens);
+  NKL(cudaGetLastError());
+  return B200ASR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200asr_nar_last_error(const b200asr_nar* e) { return e ? e->err.c_str() : g_nar_create_error.c_str(); }
+
+int b200asr_nar_create(const b200asr_nar_config* cfg, b200asr_nar** out) {
+  if (!cfg || !out) { g_nar_create_error = "null argument"; return B200ASR_E_INVALID; }
+  *out = nullptr;
+  if (cfg->kind != B200ASR_NAR_SENSEVOICE) { g_nar_create_error = "unknown model kind"; return B200ASR_E_INVALID; }
+  if (cfg->d_model <= 0 || cfg->n_heads <= 0 || cfg->d_model % cfg->n_heads || cfg->d_model % 8 || cfg->ffn % 8 ||
+      (cfg->n_mels * cfg->lfr_m) % 8 || cfg->nfft / 2 + 1 > kFbThreads || cfg->win <= 0 || cfg->hop <= 0 || cfg->vocab <= 0 ||
+      cfg->max_batch <= 0 || cfg->max_samples < cfg->win || cfg->n_prompt < 1 || cfg->fsmn_kernel < 1 || (cfg->fsmn_kernel & 1) == 0) {
+    g_nar_create_error = "invalid model dimensions"; return B200ASR_E_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    g_nar_create_error = "no CUDA device: the b200asr engine has no CPU fallback"; return B200ASR_E_NOGPU;
+  }
+  cudaDeviceProp prop;
+  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) {
+    g_nar_create_error = "cudaSetDevice failed"; return B200ASR_E_CUDA;
+  }
+  if (prop.major != 10) { g_nar_create_error = "this build targets sm_100a only"; return B200ASR_E_NOGPU; }
+  b200asr_nar* e = new b200asr_nar();
+  e->cfg = *cfg;
+  e->num_sms = prop.multiProcessorCount;
+  e->act = cfg->precision == B200ASR_PRECISION_BF16 ? kBF16 : kF32;
+  e->es = dtype_size(e->act);
+  if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess) { g_nar_create_error = "cudaStreamCreate failed"; delete e; return B200ASR_E_CUDA; }
+  *out = e;
+  return B200ASR_OK;
+}
+
+void b200asr_nar_destroy(b200asr_nar* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->st);
+  for (auto& kv : e->w) cudaFree(kv.second.ptr);
+  void* bufs[] = {e->basis_t, e->stage_buf, e->pcm, e->mel, e->feats, e->hidden, e->resid, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->S,
+                  e->logits, e->enc_out, e->frame_ids, e->tokens, e->lens, e->lang};
+  for (void* p : bufs) if (p) cudaFree(p);
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  cudaStreamDestroy(e->st);
+  delete e;
+}
+
+int b200asr_nar_set_tensor(b200asr_nar* e, const char* name_c, const float* host, int64_t numel) {
+  if (!e || !name_c || !host || numel <= 0) return B200ASR_E_INVALID;
+  NCK(cudaSetDevice(e->cfg.device));
+  const std::string name(name_c);
+  const b200asr_nar_config& c = e->cfg;
+  const int F = c.nfft / 2 + 1;
+  if (name == "fbank_kernel") {        // [2F][win] Conv1d weight -> [win][2F] so a thread's frequency bin is the fast axis
+    if (numel != (int64_t)2 * F * c.win) return e->fail(B200ASR_E_INVALID, "fbank_kernel size mismatch");
+    std::vector<float> t((size_t)numel);
+    for (int r = 0; r < 2 * F; ++r)
+      for (int k = 0; k < c.win; ++k) t[(size_t)k * 2 * F + r] = host[(size_t)r * c.win + k];
+    if (!e->basis_t) NCK(cudaMalloc(&e->basis_t, (size_t)numel * 4));
+    NCK(cudaMemcpyAsync(e->basis_t, t.data(), (size_t)numel * 4, cudaMemcpyHostToDevice, e->st));
+    NCK(cudaStreamSynchronize(e->st));
+  }
+  NarTensor t;
+  t.numel = numel;
+  t.dtype = nar_is_matrix(name) ? e->act : kF32;
+  auto it = e->w.find(name);
+  if (it != e->w.end()) { cudaFree(it->second.ptr); e->w.erase(it); }
+  NCK(cudaMalloc(&t.ptr, (size_t)numel * dtype_size(t.dtype)));
+  if (t.dtype == kF32) {
+    NCK(cudaMemcpyAsync(t.ptr, host, (size_t)numel * 4, cudaMemcpyHostToDevice, e->st));
+    NCK(cudaStreamSynchronize(e->st));
+  } else {
+    if (numel > e->stage_cap) {
+      if (e->stage_buf) cudaFree(e->stage_buf);
+      e->stage_buf = nullptr; e->stage_cap = 0;
+      NCK(cudaMalloc(&e->stage_buf, (size_t)numel * 4));
+      e->stage_cap = numel;
+    }
+    NCK(cudaMemcpyAsync(e->stage_buf, host, (size_t)numel * 4, cudaMemcpyHostToDevice, e->st));
+    nar_f32_to_bf16<<<1024, 256, 0, e->st>>>(e->stage_buf, (bf16*)t.ptr, numel);
+    NCK(cudaGetLastError());
+    NCK(cudaStreamSynchronize(e->st));
+  }
+  e->w[name] = t;
+  e->finalized = false;
+  return B200ASR_OK;
+}
+
+int b200asr_nar_finalize_weights(b200asr_nar* e) {
+  if (!e) return B200ASR_E_INVALID;
+  NCK(cudaSetDevice(e->cfg.device));
+  const b200asr_nar_config& c = e->cfg;
+  const int64_t F = c.nfft / 2 + 1, feat = c.n_mels * c.lfr_m, D = c.d_model, f = c.ffn;
+  e->max_frames = (c.max_samples - c.win) / c.hop + 1;
+  const int max_lfr = (e->max_frames + c.lfr_n - 1) / c.lfr_n;
+  e->max_T = max_lfr + c.n_prompt;
+  NRET(nar_need(e, "fbank_kernel", 2 * F * c.win)); NRET(nar_need(e, "mel_filters", F * c.n_mels));
+  NRET(nar_need(e, "cmvn_means", feat)); NRET(nar_need(e, "cmvn_vars", feat));
+  NRET(nar_need(e, "language_embed", (int64_t)c.n_lang * feat)); NRET(nar_need(e, "system_embed", (int64_t)(c.n_prompt - 1) * feat));
+  {
+    auto it = e->w.find("speech_position");
+    if (it == e->w.end()) return e->fail(B200ASR_E_MISSING, "missing weight tensor 'speech_position'");
+    if (it->second.numel < (int64_t)max_lfr * feat) return e->fail(B200ASR_E_INVALID, "speech_position shorter than max_samples needs");
+  }
+  const int n_all = c.n_blocks0 + c.n_blocks + c.n_tp_blocks;
+  for (int i = 0; i < n_all; ++i) {
+    const std::string p = "blk" + std::to_string(i) + ".";
+    const int64_t din = i == 0 ? feat : D;
+    NRET(nar_need(e, p + "norm1.g", din)); NRET(nar_need(e, p + "norm1.b", din));
+    NRET(nar_need(e, p + "qkv.w", 3 * D * din)); NRET(nar_need(e, p + "qkv.b", 3 * D));
+    NRET(nar_need(e, p + "fsmn.w", D * c.fsmn_kernel)); NRET(nar_need(e, p + "fsmn.b", D));
+    NRET(nar_need(e, p + "out.w", D * D));
+    NRET(nar_need(e, p + "norm2.g", D)); NRET(nar_need(e, p + "norm2.b", D));
+    NRET(nar_need(e, p + "w1.w", f * D)); NRET(nar_need(e, p + "w1.b", f));
+    NRET(nar_need(e, p + "w2.w", D * f)); NRET(nar_need(e, p + "w2.b", D));
+  }
+  NRET(nar_need(e, "after_norm.g", D)); NRET(nar_need(e, "after_norm.b", D));
+  NRET(nar_need(e, "tp_norm.g", D)); NRET(nar_need(e, "tp_norm.b", D));
+  NRET(nar_need(e, "ctc.w", (int64_t)c.vocab * D)); NRET(nar_need(e, "ctc.b", c.vocab));
+  if (e->finalized) return B200ASR_OK;
+  if (e->stage_buf) { cudaFree(e->stage_buf); e->stage_buf = nullptr; e->stage_cap = 0; }
+  if (!e->pcm) {
+    const size_t es = e->es;
+    const int64_t B = c.max_batch, M = B * e->max_T, H = c.n_heads, Tm = e->max_T;
+    const int64_t wide = feat > D ? feat : D;
+    NRET(nar_alloc(e, &e->pcm, (size_t)B * c.max_samples * 4));
+    NRET(nar_alloc(e, &e->mel, (size_t)B * e->max_frames * c.n_mels * 4));
+    NRET(nar_alloc(e, &e->feats, (size_t)M * feat * 4));
+    NRET(nar_alloc(e, &e->hidden, (size_t)M * D * 4));
+    NRET(nar_alloc(e, &e->resid, (size_t)M * D * 4));
+    NRET(nar_alloc(e, &e->enc_out, (size_t)M * D * 4));
+    NRET(nar_alloc(e, &e->xhat, (size_t)M * wide * es));
+    NRET(nar_alloc(e, &e->qkv, (size_t)M * 3 * D * es));
+    NRET(nar_alloc(e, &e->ctx, (size_t)M * D * es));
+    NRET(nar_alloc(e, &e->ffn, (size_t)M * f * es));
+    NRET(nar_alloc(e, &e->S, (size_t)B * H * Tm * Tm * 4));
+    NRET(nar_alloc(e, &e->P, (size_t)B * H * Tm * Tm * es));
+    NRET(nar_alloc(e, &e->logits, (size_t)M * c.vocab * 4));
+    NRET(nar_alloc(e, &e->frame_ids, (size_t)M * 4));
+    NRET(nar_alloc(e, &e->tokens, (size_t)B * Tm * 4));
+    NRET(nar_alloc(e, &e->lens, (size_t)B * 4));
+    NRET(nar_alloc(e, &e->lang, (size_t)B * 4));
+    NCK(cudaMallocHost(&e->h_pinned, (size_t)B * (Tm + 2) * 4 + 64));
+    const int span = (kFbFrames - 1) * c.hop + c.win;
+    NCK(cudaFuncSetAttribute(kaldi_fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((span + kFbFrames * F) * sizeof(float))));
+  }
+  NCK(cudaStreamSynchronize(e->st));
+  e->finalized = true;
+  return B200ASR_OK;
+}
+
+int b200asr_nar_run(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                    const int32_t* language_idx, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  if (!e) return B200ASR_E_INVALID;
+  NCK(cudaSetDevice(e->cfg.device));
+  const b200asr_nar_config& c = e->cfg;
+  if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
+  if (!pcm_host || !language_idx || !tokens_out || !lens_out || tokens_ld <= 0) return e->fail(B200ASR_E_INVALID, "null argument");
+  if (batch <= 0 || batch > c.max_batch) return e->fail(B200ASR_E_INVALID, "batch out of range");
+  if (n_samples < c.win || n_samples > c.max_samples) return e->fail(B200ASR_E_INVALID, "n_samples out of range");
+  if (pcm_dtype != B200ASR_PCM_I16 && pcm_dtype != B200ASR_PCM_F32) return e->fail(B200ASR_E_INVALID, "bad pcm dtype");
+  for (int b = 0; b < batch; ++b)
+    if (language_idx[b] < 0 || language_idx[b] >= c.n_lang) return e->fail(B200ASR_E_INVALID, "language_idx out of range");
+  e->B = batch; e->n_samples = n_samples; e->pcm_dtype = pcm_dtype;
+  e->frames = (n_samples - c.win) / c.hop + 1;
+  e->T_lfr = (e->frames + c.lfr_n - 1) / c.lfr_n;
+  e->T = e->T_lfr + c.n_prompt;
+  NCK(cudaMemcpyAsync(e->pcm, pcm_host, (size_t)batch * n_samples * (pcm_dtype == B200ASR_PCM_F32 ? 4 : 2), cudaMemcpyHostToDevice, e->st));
+  NCK(cudaMemcpyAsync(e->lang, language_idx, (size_t)batch * 4, cudaMemcpyHostToDevice, e->st));
+  NRET(nar_forward(e));
+  int* h_len = e->h_pinned;
+  int* h_tok = e->h_pinned + batch;
+  NCK(cudaMemcpyAsync(h_len, e->lens, (size_t)batch * 4, cudaMemcpyDeviceToHost, e->st));
+  NCK(cudaMemcpyAsync(h_tok, e->tokens, (size_t)batch * e->max_T * 4, cudaMemcpyDeviceToHost, e->st));
+  NCK(cudaStreamSynchronize(e->st));
+  for (int b = 0; b < batch; ++b) {
+    const int n = h_len[b] < tokens_ld ? h_len[b] : tokens_ld;
+    lens_out[b] = n;
+    memcpy(tokens_out + (size_t)b * tokens_ld, h_tok + (size_t)b * e->max_T, (size_t)n * 4);
+  }
+  return B200ASR_OK;
+}
+
+int b200asr_nar_get_stage(b200asr_nar* e, const char* name_c, float* out, int64_t capacity, int64_t* numel_out) {
+  if (!e || !name_c || !out) return B200ASR_E_INVALID;
+  NCK(cudaSetDevice(e->cfg.device));
+  const b200asr_nar_config& c = e->cfg;
+  const std::string name(name_c);
+  if (e->B <= 0) return e->fail(B200ASR_E_INVALID, "get_stage before run");
+  const int64_t B = e->B, T = e->T, feat = c.n_mels * c.lfr_m;
+  const void* src = nullptr; int64_t n = 0; bool is_int = false;
+  if (name == "mel") { src = e->mel; n = B * e->frames * c.n_mels; }
+  else if (name == "feats") { src = e->feats; n = B * T * feat; }
+  else if (name == "enc_out") { src = e->enc_out; n = B * T * c.d_model; }
+  else if (name == "logits") { src = e->logits; n = B * T * c.vocab; }
+  else if (name == "frame_ids") { src = e->frame_ids; n = B * T; is_int = true; }
+  else return e->fail(B200ASR_E_INVALID, "unknown stage '" + name + "'");
+  if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
+  NCK(cudaStreamSynchronize(e->st));
+  if (!is_int) {
+    NCK(cudaMemcpy(out, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<int> h((size_t)n);
+    NCK(cudaMemcpy(h.data(), src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) out[i] = (float)h[(size_t)i];
+  }
+  if (numel_out) *numel_out = n;
+  return B200ASR_OK;
+}
+
+int64_t b200asr_nar_kernel_launches(const b200asr_nar* e) { return e ? e->launches : 0; }
+void* b200asr_nar_stream(b200asr_nar* e) { return e ? (void*)e->st : nullptr; }
+
+}  // extern "C"

@@ -128,6 +128,50 @@ int b200asr_num_sms(const b200asr_engine* e);
 int b200asr_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
                       const float* bias, const float* residual, int32_t act, float* C, char* err, int32_t err_len);
 
+/* ---------------------------------------------------------------------------------------------
+ * Non-autoregressive models (SenseVoiceSmall): one call = front end + encoder + CTC head.
+ * Replaces ort_session_A.run_with_iobinding of SenseVoice/Inference_SenseVoice_ONNX.py:303
+ * (graph inputs `audio` [1,1,N] + `language_idx` [1], outputs `token_ids` [num_token] + `num_id` [1];
+ * math SenseVoice/Export_SenseVoice.py:271-296).  The reference graph is batch 1; a batch here is that
+ * many independent clips of equal length.
+ * ------------------------------------------------------------------------------------------- */
+#define B200ASR_NAR_SENSEVOICE 0
+
+typedef struct b200asr_nar b200asr_nar;
+
+typedef struct b200asr_nar_config {
+  int32_t kind;                    /* B200ASR_NAR_* */
+  int32_t n_mels, nfft, win, hop;  /* 80 / 512 / 400 / 160 : Kaldi fbank (snip-edges framing) */
+  int32_t lfr_m, lfr_n;            /* 7 / 6 : low-frame-rate stacking */
+  int32_t d_model, n_heads, ffn;   /* 512 / 4 / 2048 */
+  int32_t n_blocks0, n_blocks, n_tp_blocks;   /* 1 / 49 / 20 SANM blocks; after_norm sits before the tp blocks */
+  int32_t vocab, blank_id;
+  int32_t n_prompt;                /* prompt rows in front of the speech rows: 1 language + 3 system = 4 */
+  int32_t n_lang;                  /* rows of the language prompt table (7) */
+  int32_t fsmn_kernel;             /* 11 */
+  int32_t max_batch, max_samples;
+  int32_t precision, device, use_tensor_cores;
+  float ln_eps;                    /* LayerNorm epsilon of the checkpoint's norm modules */
+} b200asr_nar_config;
+
+int b200asr_nar_create(const b200asr_nar_config* cfg, b200asr_nar** out);
+void b200asr_nar_destroy(b200asr_nar* e);
+const char* b200asr_nar_last_error(const b200asr_nar* e);
+/* tensors (fp32, as the exported graph holds them): fbank_kernel [2F][win], mel_filters [F][n_mels], cmvn_means,
+ * cmvn_vars [feat], speech_position [>= max T_lfr][feat], language_embed [n_lang][feat], system_embed [n_prompt-1][feat],
+ * blk{i}.{norm1.g,norm1.b,qkv.w,qkv.b,fsmn.w,fsmn.b,out.w,norm2.g,norm2.b,w1.w,w1.b,w2.w,w2.b}, after_norm.{g,b},
+ * tp_norm.{g,b}, ctc.{w,b} */
+int b200asr_nar_set_tensor(b200asr_nar* e, const char* name, const float* host_data, int64_t numel);
+int b200asr_nar_finalize_weights(b200asr_nar* e);
+/* pcm [batch][n_samples]: int16, or float32 carrying int16-range values (audio_pcm_scale = 1); language_idx [batch]
+ * selects the language prompt row; tokens_out [batch][tokens_ld], lens_out [batch] */
+int b200asr_nar_run(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                    const int32_t* language_idx, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
+/* "mel" [B][frames][n_mels], "feats" [B][T][feat], "enc_out" [B][T][d], "logits" [B][T][vocab], "frame_ids" [B][T] */
+int b200asr_nar_get_stage(b200asr_nar* e, const char* name, float* out, int64_t capacity, int64_t* numel_out);
+int64_t b200asr_nar_kernel_launches(const b200asr_nar* e);
+void* b200asr_nar_stream(b200asr_nar* e);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,86 @@
+"""SenseVoice on the CUDA engine (csrc/sanm.cu) against goldens minted from the reference SENSE_VOICE module.
+fp32 mode: stage tensors to 2e-3 (log-mel of int16-range audio is O(10), logits O(5)), frame ids and tokens exact.
+bf16 mode (tcgen05 GEMMs + fused attention): encoder output to 0.12 on O(1) LayerNorm outputs, frame ids equal
+wherever the golden top-2 logit margin exceeds 0.5, written here."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sensevoice_oracle as so
+from b200asr import sensevoice as sv
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted((Path(__file__).parent / "golden").glob("sensevoice_tiny_case*.npz"))
+D = sv.SENSEVOICE_TINY_TEST
+MAX_SAMPLES = 160000
+
+
+def _engine(seed, precision, max_batch=1):
+    raw = sv.synth_sensevoice_checkpoint(D, seed)
+    return sv.SenseVoiceEngine(D, sv.fold_sensevoice(raw, D, MAX_SAMPLES), precision=precision, max_batch=max_batch,
+                               max_samples=MAX_SAMPLES)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])
+def test_sensevoice_f32_vs_reference_golden(path):
+    g = dict(np.load(path))
+    eng = _engine(int(g["seed"]), "f32")
+    toks = eng.run(g["pcm"], int(g["language_idx"]))[0]
+    T = g["feats"].shape[0]
+    mel = eng.get_stage("mel", g["mel"].size).reshape(g["mel"].shape)
+    np.testing.assert_allclose(mel, g["mel"], atol=2e-3)
+    feats = eng.get_stage("feats", g["feats"].size).reshape(g["feats"].shape)
+    np.testing.assert_allclose(feats, g["feats"], atol=2e-3)
+    enc = eng.get_stage("enc_out", T * D.d_model).reshape(T, D.d_model)
+    np.testing.assert_allclose(enc, g["enc_out"], atol=2e-3)
+    logits = eng.get_stage("logits", T * D.vocab).reshape(T, D.vocab)
+    np.testing.assert_allclose(logits[:, :64], g["logits_sub"], atol=2e-3)
+    ids = eng.get_stage("frame_ids", T).astype(np.int32)
+    assert ids.tolist() == g["frame_ids"].tolist()
+    assert toks == g["tokens"].tolist()
+    # float32 input carrying int16-range values (the reference's F32 audio mode, audio_pcm_scale = 1)
+    assert eng.run(g["pcm"].astype(np.float32), int(g["language_idx"]))[0] == g["tokens"].tolist()
+    eng.close()
+
+
+@pytest.mark.parametrize("path", GOLD[:2], ids=[p.stem for p in GOLD[:2]])
+def test_sensevoice_bf16_vs_reference_golden(path):
+    g = dict(np.load(path))
+    eng = _engine(int(g["seed"]), "bf16")
+    eng.run(g["pcm"], int(g["language_idx"]))
+    T = g["feats"].shape[0]
+    enc = eng.get_stage("enc_out", T * D.d_model).reshape(T, D.d_model)
+    d = float(np.abs(enc - g["enc_out"]).max())
+    print("bf16 enc_out max|d| =", d)
+    assert d <= 0.12
+    raw = so.make_raw_weights(so.TINY_TEST, int(g["seed"]))
+    fw = so.fold_weights(raw, so.TINY_TEST, int(g["max_lfr"]))
+    with torch.no_grad():
+        _, st = so.transcribe(g["pcm"], fw, so.TINY_TEST, int(g["language_idx"]), return_stages=True)
+    ref = st["logits"].numpy()
+    top2 = np.sort(ref, axis=-1)[:, -2:]
+    safe = (top2[:, 1] - top2[:, 0]) > 0.5
+    ids = eng.get_stage("frame_ids", T).astype(np.int32)
+    assert safe.sum() > 0 and np.array_equal(ids[safe], ref.argmax(-1)[safe])
+    eng.close()
+
+
+def test_sensevoice_batch_and_language_selector():
+    g = dict(np.load(GOLD[0]))
+    eng = _engine(int(g["seed"]), "f32", max_batch=3)
+    raw = so.make_raw_weights(so.TINY_TEST, int(g["seed"]))
+    fw = so.fold_weights(raw, so.TINY_TEST, D.lfr_frames(MAX_SAMPLES))
+    rng = np.random.default_rng(1)
+    clips = (rng.standard_normal((3, 40000)) * 2500).clip(-32768, 32767).astype(np.int16)
+    langs = [0, 2, 6]
+    got = eng.run(clips, langs)
+    with torch.no_grad():
+        want = [so.transcribe(clips[i], fw, so.TINY_TEST, langs[i]) for i in range(3)]
+    assert got == want
+    r = sv.transcribe_clip(eng, clips[1], "English")
+    assert r["language"] == "en" and r["tokens"] == want[1] and r["rtf"] > 0
+    with pytest.raises(Exception, match="language_idx"):
+        eng.run(clips[:1], 9)
+    eng.close()
