@@ -470,13 +470,11 @@ int b200asr_nar_finalize_weights(b200asr_nar* e) {
   return B200ASR_OK;
 }
 
-int b200asr_nar_run(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
-                    const int32_t* language_idx, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
-  if (!e) return B200ASR_E_INVALID;
-  NCK(cudaSetDevice(e->cfg.device));
+static int nar_upload(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                      const int32_t* language_idx) {
   const b200asr_nar_config& c = e->cfg;
   if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
-  if (!pcm_host || !language_idx || !tokens_out || !lens_out || tokens_ld <= 0) return e->fail(B200ASR_E_INVALID, "null argument");
+  if (!pcm_host || !language_idx) return e->fail(B200ASR_E_INVALID, "null argument");
   if (batch <= 0 || batch > c.max_batch) return e->fail(B200ASR_E_INVALID, "batch out of range");
   if (n_samples < c.win || n_samples > c.max_samples) return e->fail(B200ASR_E_INVALID, "n_samples out of range");
   if (pcm_dtype != B200ASR_PCM_I16 && pcm_dtype != B200ASR_PCM_F32) return e->fail(B200ASR_E_INVALID, "bad pcm dtype");
@@ -488,7 +486,12 @@ int b200asr_nar_run(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int
   e->T = e->T_lfr + c.n_prompt;
   NCK(cudaMemcpyAsync(e->pcm, pcm_host, (size_t)batch * n_samples * (pcm_dtype == B200ASR_PCM_F32 ? 4 : 2), cudaMemcpyHostToDevice, e->st));
   NCK(cudaMemcpyAsync(e->lang, language_idx, (size_t)batch * 4, cudaMemcpyHostToDevice, e->st));
-  NRET(nar_forward(e));
+  return B200ASR_OK;
+}
+
+static int nar_fetch(b200asr_nar* e, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  if (!tokens_out || !lens_out || tokens_ld <= 0) return e->fail(B200ASR_E_INVALID, "null output");
+  const int batch = e->B;
   int* h_len = e->h_pinned;
   int* h_tok = e->h_pinned + batch;
   NCK(cudaMemcpyAsync(h_len, e->lens, (size_t)batch * 4, cudaMemcpyDeviceToHost, e->st));
@@ -500,6 +503,32 @@ int b200asr_nar_run(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int
     memcpy(tokens_out + (size_t)b * tokens_ld, h_tok + (size_t)b * e->max_T, (size_t)n * 4);
   }
   return B200ASR_OK;
+}
+
+int b200asr_nar_run(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                    const int32_t* language_idx, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  if (!e) return B200ASR_E_INVALID;
+  NCK(cudaSetDevice(e->cfg.device));
+  NRET(nar_upload(e, pcm_host, pcm_dtype, batch, n_samples, language_idx));
+  NRET(nar_forward(e));
+  return nar_fetch(e, tokens_out, tokens_ld, lens_out);
+}
+
+int b200asr_nar_upload(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                       const int32_t* language_idx) {
+  if (!e) return B200ASR_E_INVALID;
+  NCK(cudaSetDevice(e->cfg.device));
+  NRET(nar_upload(e, pcm_host, pcm_dtype, batch, n_samples, language_idx));
+  NCK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+
+int b200asr_nar_run_resident(b200asr_nar* e, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  if (!e) return B200ASR_E_INVALID;
+  NCK(cudaSetDevice(e->cfg.device));
+  if (e->B <= 0) return e->fail(B200ASR_E_INVALID, "no PCM uploaded");
+  NRET(nar_forward(e));
+  return nar_fetch(e, tokens_out, tokens_ld, lens_out);
 }
 
 int b200asr_nar_get_stage(b200asr_nar* e, const char* name_c, float* out, int64_t capacity, int64_t* numel_out) {

@@ -250,6 +250,23 @@ class SenseVoiceEngine:
         self.batch, self.n_samples = B, N
         return [toks[b, :lens[b]].tolist() for b in range(B)]
 
+    def upload(self, pcm: np.ndarray, language_idx=0):
+        pcm = np.ascontiguousarray(pcm)
+        if pcm.ndim == 1:
+            pcm = pcm[None]
+        code = _cabi.PCM_I16 if pcm.dtype == np.int16 else _cabi.PCM_F32
+        B, N = pcm.shape
+        lang = np.ascontiguousarray(np.broadcast_to(np.asarray(language_idx, dtype=np.int32).reshape(-1), (B,)))
+        self._ck(self.lib.b200asr_nar_upload(self.h, pcm.ctypes.data_as(C.c_void_p), code, B, N, lang.ctypes.data_as(_cabi._I32P)))
+        self.batch, self.n_samples = B, N
+
+    def run_resident(self) -> List[List[int]]:
+        ld = self.dims.lfr_frames(self.max_samples) + 1 + len(SYSTEM_PROMPT_IDS)
+        toks = np.zeros((self.batch, ld), np.int32)
+        lens = np.zeros(self.batch, np.int32)
+        self._ck(self.lib.b200asr_nar_run_resident(self.h, toks.ctypes.data_as(_cabi._I32P), ld, lens.ctypes.data_as(_cabi._I32P)))
+        return [toks[b, :lens[b]].tolist() for b in range(self.batch)]
+
     def get_stage(self, name: str, capacity: int) -> np.ndarray:
         out = np.empty(capacity, np.float32)
         n = C.c_int64(0)

@@ -167,6 +167,10 @@ int b200asr_nar_finalize_weights(b200asr_nar* e);
  * selects the language prompt row; tokens_out [batch][tokens_ld], lens_out [batch] */
 int b200asr_nar_run(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
                     const int32_t* language_idx, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
+/* same, split so a benchmark can time with the PCM already resident in HBM */
+int b200asr_nar_upload(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                       const int32_t* language_idx);
+int b200asr_nar_run_resident(b200asr_nar* e, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
 /* "mel" [B][frames][n_mels], "feats" [B][T][feat], "enc_out" [B][T][d], "logits" [B][T][vocab], "frame_ids" [B][T] */
 int b200asr_nar_get_stage(b200asr_nar* e, const char* name, float* out, int64_t capacity, int64_t* numel_out);
 int64_t b200asr_nar_kernel_launches(const b200asr_nar* e);
