@@ -24,7 +24,8 @@ class NarConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "kind", "n_mels", "nfft", "win", "hop", "lfr_m", "lfr_n", "d_model", "n_heads", "ffn", "n_blocks0", "n_blocks",
         "n_tp_blocks", "vocab", "blank_id", "n_prompt", "n_lang", "fsmn_kernel", "max_batch", "max_samples", "precision",
-        "device", "use_tensor_cores")] + [("ln_eps", C.c_float)]
+        "device", "use_tensor_cores")] + [("ln_eps", C.c_float)] + [(n, C.c_int32) for n in (
+        "dec_att_blocks", "dec_ffn_blocks", "dec_ffn", "cif_kernel")] + [("tail_threshold", C.c_float), ("dec_ln_eps", C.c_float)]
 
 
 # every symbol include/b200asr.h declares: (restype, argtypes)

@@ -90,7 +90,7 @@ __global__ void lfr_cmvn_kernel(const float* __restrict__ mel, int frames, int n
     int fr = tl * lfr_n + j - half;
     fr = max(0, min(fr, frames - 1));
     const float v = mel[((int64_t)b * frames + fr) * n_mels + m];
-    xr[c] = (v + means[c]) * vars[c] + pos[(int64_t)tl * feat + c];
+    xr[c] = (means ? (v + means[c]) * vars[c] : v * vars[c]) + pos[(int64_t)tl * feat + c];
   }
 }
 
@@ -144,6 +144,80 @@ __global__ void ctc_collapse_kernel(const int* __restrict__ ids, int Tn, int bla
   lens[b] = n;
 }
 
+// ---- Paraformer CIF predictor (Export_Paraformer.py:499-521) ----
+// alpha[t] = sigmoid(w . relu_conv[t] + b); one warp per encoder frame
+template <typename T>
+__global__ void __launch_bounds__(256)
+cif_alpha_kernel(const T* __restrict__ conv, const float* __restrict__ w, const float* __restrict__ b, int rows, int D,
+                 float* __restrict__ alphas /*[B][Tn + 1]*/, int Tn) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int c = lane; c < D; c += 32) acc = fmaf(to_f<T>(conv[(int64_t)row * D + c]), w[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const int bb = row / Tn, t = row - bb * Tn;
+    alphas[(int64_t)bb * (Tn + 1) + t] = 1.0f / (1.0f + expf(-(acc + b[0])));
+  }
+}
+// integrate-and-fire: float64 prefix sum of alpha (+ tail), fire where its floor advances, acoustic embedding n =
+// difference of the weighted hidden prefix sums completed at consecutive fires.  One CTA per utterance.
+__global__ void __launch_bounds__(256)
+cif_scan_kernel(float* __restrict__ alphas /*[B][Tn+1]: tail written here*/, float tail, const float* __restrict__ enc /*[B][Tn][D]*/,
+                int Tn, int D, float* __restrict__ acoustic /*[B][Tn+1][D]*/, int* __restrict__ n_tok) {
+  extern __shared__ float cs[];            // prefix[Tn+1] | fire flags as float [Tn+1]
+  float* prefix = cs;
+  float* fire = cs + Tn + 1;
+  const int b = blockIdx.x;
+  float* a = alphas + (int64_t)b * (Tn + 1);
+  if (threadIdx.x == 0) {
+    a[Tn] = tail;
+    double acc = 0.0;
+    float prev_floor = 0.f;
+    for (int t = 0; t <= Tn; ++t) {
+      acc += (double)a[t];
+      const float p = (float)acc;
+      const float fl = floorf(p);
+      prefix[t] = p;
+      fire[t] = fl > prev_floor ? 1.f : 0.f;
+      prev_floor = fl;
+    }
+    n_tok[b] = (int)floorf(prefix[Tn]);
+  }
+  __syncthreads();
+  const float* h = enc + (int64_t)b * Tn * D;
+  float* out = acoustic + (int64_t)b * (Tn + 1) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    double acc = 0.0;                       // torch's CPU cumsum accumulates float32 inputs in double
+    float prev = 0.f;
+    int n = 0;
+    for (int t = 0; t <= Tn; ++t) {
+      const float hv = t < Tn ? h[(int64_t)t * D + c] : 0.f;
+      acc += (double)(a[t] * hv);
+      if (fire[t] != 0.f) {
+        const float remains = prefix[t] - floorf(prefix[t]);
+        const float completed = (float)acc - remains * hv;
+        out[(int64_t)n * D + c] = completed - prev;
+        prev = completed;
+        ++n;
+      }
+    }
+  }
+}
+// rows [0, n) <- src rows, rows beyond zero-filled up to `rows` (the zero-fire guard's dummy frame)
+__global__ void copy_rows_kernel(const float* __restrict__ src, int n, int rows, int D, float* __restrict__ dst) {
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) dst[(int64_t)r * D + c] = r < n ? src[(int64_t)r * D + c] : 0.f;
+}
+template <typename T>
+__global__ void pad_rows_kernel(const float* __restrict__ src /*[B][Tn][D]*/, int Tn, int D, int pad, T* __restrict__ dst /*[B][Tn+2*pad][D]*/) {
+  const int t = blockIdx.x, b = blockIdx.y;      // t in [0, Tn + 2*pad)
+  const int ts = t - pad;
+  for (int c = threadIdx.x; c < D; c += blockDim.x)
+    dst[((int64_t)b * (Tn + 2 * pad) + t) * D + c] = from_f<T>((ts >= 0 && ts < Tn) ? src[((int64_t)b * Tn + ts) * D + c] : 0.f);
+}
+
 __global__ void nar_f32_to_bf16(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
@@ -175,6 +249,10 @@ struct b200asr_nar {
   void *xhat = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *P = nullptr;
   float* S = nullptr; float* logits = nullptr; float* enc_out = nullptr;
   int *frame_ids = nullptr, *tokens = nullptr, *lens = nullptr, *lang = nullptr;
+  // Paraformer
+  void *enc_pad = nullptr, *conv_out = nullptr, *kvbuf = nullptr, *dq = nullptr;
+  float *alphas = nullptr, *acoustic = nullptr, *dec = nullptr, *dx = nullptr, *f32buf = nullptr, *sa_in = nullptr, *dec_logits = nullptr;
+  int* n_tok = nullptr; int last_rows = 0;
   int* h_pinned = nullptr;
   int max_frames = 0, max_T = 0;
 
@@ -189,7 +267,7 @@ struct b200asr_nar {
 namespace {
 
 bool nar_is_matrix(const std::string& n) {
-  return n.size() > 2 && n.compare(n.size() - 2, 2, ".w") == 0 && n.find("fsmn") == std::string::npos;
+  return n.size() > 2 && n.compare(n.size() - 2, 2, ".w") == 0 && n.find("fsmn") == std::string::npos && n != "cif.out.w";
 }
 const void* NW(b200asr_nar* e, const std::string& n) { return e->w[n].ptr; }
 const float* NWF(b200asr_nar* e, const std::string& n) { return reinterpret_cast<const float*>(e->w[n].ptr); }
@@ -235,19 +313,25 @@ int nar_alloc(b200asr_nar* e, T** p, size_t bytes) {
   return B200ASR_OK;
 }
 
-int nar_block(b200asr_nar* e, int i, const float* x_in, int din) {
+const float* NWF_opt(b200asr_nar* e, const std::string& n) {
+  auto it = e->w.find(n);
+  return it == e->w.end() ? nullptr : reinterpret_cast<const float*>(it->second.ptr);
+}
+
+// one SANM block; `p` = tensor-name prefix.  LayerNorm affines are optional (Paraformer folds them into the Linears);
+// the FSMN bias operand is `fsmn_bias` (SenseVoice: the conv's own bias = linear_out's; Paraformer: linear_out's bias)
+int nar_block(b200asr_nar* e, const std::string& p, const std::string& fsmn_bias, const float* x_in, int din) {
   const b200asr_nar_config& c = e->cfg;
   const int D = c.d_model, H = c.n_heads, dh = D / H, T = e->T, B = e->B, M = B * T, ad = e->act;
   const size_t es = e->es;
-  const std::string p = "blk" + std::to_string(i) + ".";
-  NKL(launch_layernorm(x_in, din, NWF(e, p + "norm1.g"), NWF(e, p + "norm1.b"), e->xhat, ad, din, M, din, c.ln_eps, e->st));
+  NKL(launch_layernorm(x_in, din, NWF_opt(e, p + "norm1.g"), NWF_opt(e, p + "norm1.b"), e->xhat, ad, din, M, din, c.ln_eps, e->st));
   NRET(nar_gemm(e, nar_linear(e, e->xhat, din, p + "qkv.w", p + "qkv.b", e->qkv, 3 * D, ad, M, 3 * D, din)));
   // FSMN memory (+ x when the block keeps its width) -> the fp32 residual the out-projection adds
   const float* res_in = (din == D) ? x_in : nullptr;
   if (ad == kBF16)
-    fsmn_kernel<bf16><<<dim3(T, B), 256, 0, e->st>>>((const bf16*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, p + "fsmn.b"), res_in, T, D, c.fsmn_kernel, e->resid);
+    fsmn_kernel<bf16><<<dim3(T, B), 256, 0, e->st>>>((const bf16*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, fsmn_bias), res_in, T, D, c.fsmn_kernel, e->resid);
   else
-    fsmn_kernel<float><<<dim3(T, B), 256, 0, e->st>>>((const float*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, p + "fsmn.b"), res_in, T, D, c.fsmn_kernel, e->resid);
+    fsmn_kernel<float><<<dim3(T, B), 256, 0, e->st>>>((const float*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, fsmn_bias), res_in, T, D, c.fsmn_kernel, e->resid);
   NKL(cudaGetLastError());
   if (ad == kBF16 && c.use_tensor_cores && dh == 64 && attention_tc_supported(T, D, H)) {
     std::string msg;
@@ -275,7 +359,7 @@ int nar_block(b200asr_nar* e, int i, const float* x_in, int din) {
     g.residual = e->resid; g.ldr = D;
     NRET(nar_gemm(e, g));
   }
-  NKL(launch_layernorm(e->hidden, D, NWF(e, p + "norm2.g"), NWF(e, p + "norm2.b"), e->xhat, ad, D, M, D, c.ln_eps, e->st));
+  NKL(launch_layernorm(e->hidden, D, NWF_opt(e, p + "norm2.g"), NWF_opt(e, p + "norm2.b"), e->xhat, ad, D, M, D, c.ln_eps, e->st));
   {
     GemmArgs g = nar_linear(e, e->xhat, D, p + "w1.w", p + "w1.b", e->ffn, c.ffn, ad, M, c.ffn, D);
     g.act = kActRelu;
@@ -287,25 +371,31 @@ int nar_block(b200asr_nar* e, int i, const float* x_in, int din) {
   return B200ASR_OK;
 }
 
-int nar_forward(b200asr_nar* e) {
+int nar_fbank(b200asr_nar* e) {
   const b200asr_nar_config& c = e->cfg;
-  const int F = c.nfft / 2 + 1, feat = c.n_mels * c.lfr_m, D = c.d_model, B = e->B, T = e->T, M = B * T;
-  {
-    const int span = (kFbFrames - 1) * c.hop + c.win;
-    const size_t smem = (size_t)(span + kFbFrames * F) * sizeof(float);
-    dim3 grid((e->frames + kFbFrames - 1) / kFbFrames, B);
-    kaldi_fbank_kernel<<<grid, kFbThreads, smem, e->st>>>(e->pcm, e->pcm_dtype == B200ASR_PCM_F32, e->n_samples, e->basis_t,
-                                                          NWF(e, "mel_filters"), c.win, c.hop, F, c.n_mels, e->frames,
-                                                          1.1920928955078125e-07f, e->mel);
-    NKL(cudaGetLastError());
-  }
+  const int F = c.nfft / 2 + 1, B = e->B;
+  const int span = (kFbFrames - 1) * c.hop + c.win;
+  const size_t smem = (size_t)(span + kFbFrames * F) * sizeof(float);
+  dim3 grid((e->frames + kFbFrames - 1) / kFbFrames, B);
+  kaldi_fbank_kernel<<<grid, kFbThreads, smem, e->st>>>(e->pcm, e->pcm_dtype == B200ASR_PCM_F32, e->n_samples, e->basis_t,
+                                                        NWF(e, "mel_filters"), c.win, c.hop, F, c.n_mels, e->frames,
+                                                        1.1920928955078125e-07f, e->mel);
+  NKL(cudaGetLastError());
+  return B200ASR_OK;
+}
+
+int sensevoice_forward(b200asr_nar* e) {
+  const b200asr_nar_config& c = e->cfg;
+  const int feat = c.n_mels * c.lfr_m, D = c.d_model, B = e->B, T = e->T, M = B * T;
+  NRET(nar_fbank(e));
   lfr_cmvn_kernel<<<dim3(T, B), 256, 0, e->st>>>(e->mel, e->frames, c.n_mels, c.lfr_m, c.lfr_n, e->T_lfr, c.n_prompt,
                                                  NWF(e, "cmvn_means"), NWF(e, "cmvn_vars"), NWF(e, "speech_position"),
                                                  NWF(e, "language_embed"), NWF(e, "system_embed"), e->lang, e->feats);
   NKL(cudaGetLastError());
   const int n_main = c.n_blocks0 + c.n_blocks, n_all = n_main + c.n_tp_blocks;
   for (int i = 0; i < n_all; ++i) {
-    NRET(nar_block(e, i, i == 0 ? e->feats : e->hidden, i == 0 ? feat : D));
+    const std::string p = "blk" + std::to_string(i) + ".";
+    NRET(nar_block(e, p, p + "fsmn.b", i == 0 ? e->feats : e->hidden, i == 0 ? feat : D));
     if (i == n_main - 1)      // after_norm between the encoder blocks and the transformer-postnet blocks (:266)
       NKL(launch_layernorm(e->hidden, D, NWF(e, "after_norm.g"), NWF(e, "after_norm.b"), e->hidden, kF32, D, M, D, c.ln_eps, e->st));
   }
@@ -319,6 +409,112 @@ int nar_forward(b200asr_nar* e) {
   return B200ASR_OK;
 }
 
+// ---- Paraformer (Export_Paraformer.py:474-563) ----
+int paraformer_decode_one(b200asr_nar* e, int b, int n_tok) {
+  const b200asr_nar_config& c = e->cfg;
+  const int D = c.d_model, H = c.n_heads, dh = D / H, T = e->T, ad = e->act, Fd = c.dec_ffn;
+  const size_t es = e->es;
+  const int rows = n_tok > 0 ? n_tok : 1;                      // zero-fire guard: one zero frame, dropped again below (:523-528)
+  copy_rows_kernel<<<rows, 128, 0, e->st>>>(e->acoustic + (int64_t)b * (T + 1) * D, n_tok, rows, D, e->dec);
+  NKL(cudaGetLastError());
+  const char* memory = (const char*)e->xhat + (size_t)b * T * D * es;           // encoder_out of utterance b in the activation dtype
+  auto ffn = [&](const std::string& p, float* out, const float* resid) -> int {
+    NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+    {
+      GemmArgs g = nar_linear(e, e->dq, D, p + "w1.w", p + "w1.b", e->f32buf, Fd, kF32, rows, Fd, D);
+      g.act = kActRelu;
+      NRET(nar_gemm(e, g));
+    }
+    NKL(launch_layernorm(e->f32buf, Fd, nullptr, nullptr, e->ffn, ad, Fd, rows, Fd, c.dec_ln_eps, e->st));
+    GemmArgs g2 = nar_linear(e, e->ffn, Fd, p + "w2.w", p + "w2.b", out, D, kF32, rows, D, Fd);
+    if (resid) { g2.residual = resid; g2.ldr = D; }
+    return nar_gemm(e, g2);
+  };
+  for (int i = 0; i < c.dec_att_blocks; ++i) {
+    const std::string p = "dec" + std::to_string(i) + ".";
+    NRET(ffn(p, e->dx, nullptr));                                                               // x = FFN(dec)
+    NKL(launch_layernorm(e->dx, D, NWF(e, p + "norm2.g"), NWF(e, p + "norm2.b"), e->sa_in, kF32, D, rows, D, c.dec_ln_eps, e->st));
+    fsmn_kernel<float><<<dim3(rows, 1), 256, 0, e->st>>>(e->sa_in, D, 0, NWF(e, p + "fsmn.w"), NWF(e, "zero_bias"), e->dec, rows, D,
+                                                       c.fsmn_kernel, e->dx);                  // x = dec + fsmn(norm2(x))
+    NKL(cudaGetLastError());
+    NKL(launch_layernorm(e->dx, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+    NRET(nar_gemm(e, nar_linear(e, e->dq, D, p + "q.w", p + "q.b", e->qkv, D, ad, rows, D, D)));
+    NRET(nar_gemm(e, nar_linear(e, memory, D, p + "kv.w", p + "kv.b", e->kvbuf, 2 * D, ad, T, 2 * D, D)));
+    GemmArgs sgm;
+    sgm.A = e->qkv; sgm.lda = D; sgm.sAi = dh; sgm.a_dtype = ad;
+    sgm.B = e->kvbuf; sgm.ldb = 2 * D; sgm.sBi = dh; sgm.b_dtype = ad;
+    sgm.C = e->S; sgm.ldc = T; sgm.sCi = (int64_t)rows * T; sgm.c_dtype = kF32;
+    sgm.M = rows; sgm.N = T; sgm.K = dh; sgm.batch = H; sgm.batch_inner = H;
+    NKL(launch_gemm_simt(sgm, e->st));
+    NKL(launch_softmax_rows(e->S, e->P, ad, (int64_t)H * rows, T, e->st));
+    GemmArgs o;
+    o.A = e->P; o.lda = T; o.sAi = (int64_t)rows * T; o.a_dtype = ad;
+    o.B = (char*)e->kvbuf + (size_t)D * es; o.ldb = 2 * D; o.sBi = dh; o.b_dtype = ad; o.transB = 1;
+    o.C = e->ctx; o.ldc = D; o.sCi = dh; o.c_dtype = ad;
+    o.M = rows; o.N = dh; o.K = T; o.batch = H; o.batch_inner = H;
+    NKL(launch_gemm_simt(o, e->st));
+    GemmArgs g = nar_linear(e, e->ctx, D, p + "cout.w", p + "cout.b", e->dec, D, kF32, rows, D, D);
+    g.residual = e->dx; g.ldr = D;
+    NRET(nar_gemm(e, g));                                                                       // dec = x + cross_out
+  }
+  for (int i = c.dec_att_blocks; i < c.dec_att_blocks + c.dec_ffn_blocks; ++i) {
+    NRET(ffn("dec" + std::to_string(i) + ".", e->dx, nullptr));
+    NCK(cudaMemcpyAsync(e->dec, e->dx, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, e->st));
+  }
+  NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+  NRET(nar_gemm(e, nar_linear(e, e->dq, D, "out.w", "out.b", e->dec_logits, c.vocab, kF32, rows, c.vocab, D)));
+  row_argmax_kernel<<<(rows + 7) / 8, 256, 0, e->st>>>(e->dec_logits, rows, c.vocab, e->tokens + (int64_t)b * e->max_T);
+  NKL(cudaGetLastError());
+  e->last_rows = rows;
+  return B200ASR_OK;
+}
+
+int paraformer_forward(b200asr_nar* e) {
+  const b200asr_nar_config& c = e->cfg;
+  const int feat = c.n_mels * c.lfr_m, D = c.d_model, B = e->B, T = e->T, M = B * T, ad = e->act;
+  NRET(nar_fbank(e));
+  lfr_cmvn_kernel<<<dim3(T, B), 256, 0, e->st>>>(e->mel, e->frames, c.n_mels, c.lfr_m, c.lfr_n, e->T_lfr, 0, nullptr,
+                                                 NWF(e, "cmvn_vars"), NWF(e, "encoder_input_bias"), nullptr, nullptr, e->lang, e->feats);
+  NKL(cudaGetLastError());
+  const int n_enc = c.n_blocks0 + c.n_blocks;
+  for (int i = 0; i < n_enc; ++i) {
+    const std::string p = "enc" + std::to_string(i) + ".";
+    NRET(nar_block(e, p, p + "out.b", i == 0 ? e->feats : e->hidden, i == 0 ? feat : D));
+  }
+  NKL(launch_layernorm(e->hidden, D, NWF(e, "enc_after_norm.g"), NWF(e, "enc_after_norm.b"), e->enc_out, kF32, D, M, D, c.ln_eps, e->st));
+  NKL(launch_layernorm(e->hidden, D, NWF(e, "enc_after_norm.g"), NWF(e, "enc_after_norm.b"), e->xhat, ad, D, M, D, c.ln_eps, e->st));
+  // CIF: conv k over time as a GEMM on the zero-padded, overlapping-row view (row t = k*D contiguous values from padded row t)
+  const int pad = (c.cif_kernel - 1) / 2;
+  if (ad == kBF16) pad_rows_kernel<bf16><<<dim3(T + 2 * pad, B), 128, 0, e->st>>>(e->enc_out, T, D, pad, (bf16*)e->enc_pad);
+  else pad_rows_kernel<float><<<dim3(T + 2 * pad, B), 128, 0, e->st>>>(e->enc_out, T, D, pad, (float*)e->enc_pad);
+  NKL(cudaGetLastError());
+  {
+    GemmArgs g = nar_linear(e, e->enc_pad, D, "cif.conv.w", "cif.conv.b", e->conv_out, D, ad, T, D, c.cif_kernel * D);
+    g.sAo = (int64_t)(T + 2 * pad) * D; g.sCo = (int64_t)T * D; g.batch = B; g.act = kActRelu;
+    NRET(nar_gemm(e, g));
+  }
+  if (ad == kBF16) cif_alpha_kernel<bf16><<<(M + 7) / 8, 256, 0, e->st>>>((const bf16*)e->conv_out, NWF(e, "cif.out.w"), NWF(e, "cif.out.b"), M, D, e->alphas, T);
+  else cif_alpha_kernel<float><<<(M + 7) / 8, 256, 0, e->st>>>((const float*)e->conv_out, NWF(e, "cif.out.w"), NWF(e, "cif.out.b"), M, D, e->alphas, T);
+  NKL(cudaGetLastError());
+  cif_scan_kernel<<<B, 256, (size_t)2 * (T + 1) * sizeof(float), e->st>>>(e->alphas, c.tail_threshold, e->enc_out, T, D, e->acoustic, e->n_tok);
+  NKL(cudaGetLastError());
+  // the token count sizes the decoder: one small device->host read (the reference graph has the same data-dependent shape)
+  int* h_n = e->h_pinned;
+  NCK(cudaMemcpyAsync(h_n, e->n_tok, (size_t)B * 4, cudaMemcpyDeviceToHost, e->st));
+  NCK(cudaStreamSynchronize(e->st));
+  std::vector<int> counts(h_n, h_n + B);
+  for (int b = 0; b < B; ++b) {
+    if (counts[b] > T + 1) return e->fail(B200ASR_E_CUDA, "CIF fired more tokens than frames");
+    NRET(paraformer_decode_one(e, b, counts[b]));
+  }
+  NCK(cudaMemcpyAsync(e->lens, e->n_tok, (size_t)B * 4, cudaMemcpyDeviceToDevice, e->st));
+  return B200ASR_OK;
+}
+
+int nar_forward(b200asr_nar* e) {
+  return e->cfg.kind == B200ASR_NAR_PARAFORMER ? paraformer_forward(e) : sensevoice_forward(e);
+}
+
 }  // namespace
 
 extern "C" {
@@ -328,10 +524,12 @@ const char* b200asr_nar_last_error(const b200asr_nar* e) { return e ? e->err.c_s
 int b200asr_nar_create(const b200asr_nar_config* cfg, b200asr_nar** out) {
   if (!cfg || !out) { g_nar_create_error = "null argument"; return B200ASR_E_INVALID; }
   *out = nullptr;
-  if (cfg->kind != B200ASR_NAR_SENSEVOICE) { g_nar_create_error = "unknown model kind"; return B200ASR_E_INVALID; }
+  if (cfg->kind != B200ASR_NAR_SENSEVOICE && cfg->kind != B200ASR_NAR_PARAFORMER) { g_nar_create_error = "unknown model kind"; return B200ASR_E_INVALID; }
+  if (cfg->kind == B200ASR_NAR_PARAFORMER && (cfg->dec_att_blocks < 0 || cfg->dec_ffn_blocks < 0 || cfg->dec_ffn <= 0 || cfg->dec_ffn % 8 || cfg->dec_ffn > 2048 ||
+                                              cfg->cif_kernel < 1 || (cfg->cif_kernel & 1) == 0)) { g_nar_create_error = "invalid Paraformer decoder dimensions"; return B200ASR_E_INVALID; }
   if (cfg->d_model <= 0 || cfg->n_heads <= 0 || cfg->d_model % cfg->n_heads || cfg->d_model % 8 || cfg->ffn % 8 ||
       (cfg->n_mels * cfg->lfr_m) % 8 || cfg->nfft / 2 + 1 > kFbThreads || cfg->win <= 0 || cfg->hop <= 0 || cfg->vocab <= 0 ||
-      cfg->max_batch <= 0 || cfg->max_samples < cfg->win || cfg->n_prompt < 1 || cfg->fsmn_kernel < 1 || (cfg->fsmn_kernel & 1) == 0) {
+      cfg->max_batch <= 0 || cfg->max_samples < cfg->win || cfg->n_prompt < 0 || cfg->fsmn_kernel < 1 || (cfg->fsmn_kernel & 1) == 0) {
     g_nar_create_error = "invalid model dimensions"; return B200ASR_E_INVALID;
   }
   int ndev = 0;
@@ -359,7 +557,8 @@ void b200asr_nar_destroy(b200asr_nar* e) {
   cudaStreamSynchronize(e->st);
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
   void* bufs[] = {e->basis_t, e->stage_buf, e->pcm, e->mel, e->feats, e->hidden, e->resid, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->S,
-                  e->logits, e->enc_out, e->frame_ids, e->tokens, e->lens, e->lang};
+                  e->logits, e->enc_out, e->frame_ids, e->tokens, e->lens, e->lang, e->enc_pad, e->conv_out, e->kvbuf, e->dq, e->alphas,
+                  e->acoustic, e->dec, e->dx, e->f32buf, e->sa_in, e->dec_logits, e->n_tok};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -380,6 +579,16 @@ int b200asr_nar_set_tensor(b200asr_nar* e, const char* name_c, const float* host
     if (!e->basis_t) NCK(cudaMalloc(&e->basis_t, (size_t)numel * 4));
     NCK(cudaMemcpyAsync(e->basis_t, t.data(), (size_t)numel * 4, cudaMemcpyHostToDevice, e->st));
     NCK(cudaStreamSynchronize(e->st));
+  }
+  std::vector<float> relaid;
+  if (name == "cif.conv.w") {         // Conv1d weight [co][ci][k] -> [co][k*D + ci]: the GEMM's K axis walks k then ci
+    const int D = c.d_model, K = c.cif_kernel;
+    if (numel != (int64_t)D * D * K) return e->fail(B200ASR_E_INVALID, "cif.conv.w size mismatch");
+    relaid.resize((size_t)numel);
+    for (int co = 0; co < D; ++co)
+      for (int ci = 0; ci < D; ++ci)
+        for (int k = 0; k < K; ++k) relaid[((size_t)co * K + k) * D + ci] = host[((size_t)co * D + ci) * K + k];
+    host = relaid.data();
   }
   NarTensor t;
   t.numel = numel;
@@ -414,30 +623,70 @@ int b200asr_nar_finalize_weights(b200asr_nar* e) {
   const int64_t F = c.nfft / 2 + 1, feat = c.n_mels * c.lfr_m, D = c.d_model, f = c.ffn;
   e->max_frames = (c.max_samples - c.win) / c.hop + 1;
   const int max_lfr = (e->max_frames + c.lfr_n - 1) / c.lfr_n;
-  e->max_T = max_lfr + c.n_prompt;
+  const bool para = c.kind == B200ASR_NAR_PARAFORMER;
+  e->max_T = max_lfr + c.n_prompt + (para ? 1 : 0);            // Paraformer: up to T + 1 decoder rows (tail fire)
   NRET(nar_need(e, "fbank_kernel", 2 * F * c.win)); NRET(nar_need(e, "mel_filters", F * c.n_mels));
-  NRET(nar_need(e, "cmvn_means", feat)); NRET(nar_need(e, "cmvn_vars", feat));
-  NRET(nar_need(e, "language_embed", (int64_t)c.n_lang * feat)); NRET(nar_need(e, "system_embed", (int64_t)(c.n_prompt - 1) * feat));
-  {
+  NRET(nar_need(e, "cmvn_vars", feat));
+  if (!para) {
+    NRET(nar_need(e, "cmvn_means", feat));
+    NRET(nar_need(e, "language_embed", (int64_t)c.n_lang * feat)); NRET(nar_need(e, "system_embed", (int64_t)(c.n_prompt - 1) * feat));
     auto it = e->w.find("speech_position");
     if (it == e->w.end()) return e->fail(B200ASR_E_MISSING, "missing weight tensor 'speech_position'");
     if (it->second.numel < (int64_t)max_lfr * feat) return e->fail(B200ASR_E_INVALID, "speech_position shorter than max_samples needs");
+    const int n_all = c.n_blocks0 + c.n_blocks + c.n_tp_blocks;
+    for (int i = 0; i < n_all; ++i) {
+      const std::string p = "blk" + std::to_string(i) + ".";
+      const int64_t din = i == 0 ? feat : D;
+      NRET(nar_need(e, p + "norm1.g", din)); NRET(nar_need(e, p + "norm1.b", din));
+      NRET(nar_need(e, p + "qkv.w", 3 * D * din)); NRET(nar_need(e, p + "qkv.b", 3 * D));
+      NRET(nar_need(e, p + "fsmn.w", D * c.fsmn_kernel)); NRET(nar_need(e, p + "fsmn.b", D));
+      NRET(nar_need(e, p + "out.w", D * D));
+      NRET(nar_need(e, p + "norm2.g", D)); NRET(nar_need(e, p + "norm2.b", D));
+      NRET(nar_need(e, p + "w1.w", f * D)); NRET(nar_need(e, p + "w1.b", f));
+      NRET(nar_need(e, p + "w2.w", D * f)); NRET(nar_need(e, p + "w2.b", D));
+    }
+    NRET(nar_need(e, "after_norm.g", D)); NRET(nar_need(e, "after_norm.b", D));
+    NRET(nar_need(e, "tp_norm.g", D)); NRET(nar_need(e, "tp_norm.b", D));
+    NRET(nar_need(e, "ctc.w", (int64_t)c.vocab * D)); NRET(nar_need(e, "ctc.b", c.vocab));
+  } else {
+    const int64_t Fd = c.dec_ffn;
+    {
+      auto it = e->w.find("encoder_input_bias");
+      if (it == e->w.end()) return e->fail(B200ASR_E_MISSING, "missing weight tensor 'encoder_input_bias'");
+      if (it->second.numel < (int64_t)max_lfr * feat) return e->fail(B200ASR_E_INVALID, "encoder_input_bias shorter than max_samples needs");
+    }
+    for (int i = 0; i < c.n_blocks0 + c.n_blocks; ++i) {
+      const std::string p = "enc" + std::to_string(i) + ".";
+      const int64_t din = i == 0 ? feat : D;
+      NRET(nar_need(e, p + "qkv.w", 3 * D * din)); NRET(nar_need(e, p + "qkv.b", 3 * D));
+      NRET(nar_need(e, p + "fsmn.w", D * c.fsmn_kernel));
+      NRET(nar_need(e, p + "out.w", D * D)); NRET(nar_need(e, p + "out.b", D));
+      NRET(nar_need(e, p + "w1.w", f * D)); NRET(nar_need(e, p + "w1.b", f));
+      NRET(nar_need(e, p + "w2.w", D * f)); NRET(nar_need(e, p + "w2.b", D));
+    }
+    NRET(nar_need(e, "enc_after_norm.g", D)); NRET(nar_need(e, "enc_after_norm.b", D));
+    NRET(nar_need(e, "cif.conv.w", D * D * c.cif_kernel)); NRET(nar_need(e, "cif.conv.b", D));
+    NRET(nar_need(e, "cif.out.w", D)); NRET(nar_need(e, "cif.out.b", 1));
+    for (int i = 0; i < c.dec_att_blocks + c.dec_ffn_blocks; ++i) {
+      const std::string p = "dec" + std::to_string(i) + ".";
+      NRET(nar_need(e, p + "w1.w", Fd * D)); NRET(nar_need(e, p + "w1.b", Fd));
+      NRET(nar_need(e, p + "w2.w", D * Fd)); NRET(nar_need(e, p + "w2.b", D));
+      if (i < c.dec_att_blocks) {
+        NRET(nar_need(e, p + "norm2.g", D)); NRET(nar_need(e, p + "norm2.b", D));
+        NRET(nar_need(e, p + "fsmn.w", D * c.fsmn_kernel));
+        NRET(nar_need(e, p + "q.w", D * D)); NRET(nar_need(e, p + "q.b", D));
+        NRET(nar_need(e, p + "kv.w", 2 * D * D)); NRET(nar_need(e, p + "kv.b", 2 * D));
+        NRET(nar_need(e, p + "cout.w", D * D)); NRET(nar_need(e, p + "cout.b", D));
+      }
+    }
+    NRET(nar_need(e, "out.w", (int64_t)c.vocab * D)); NRET(nar_need(e, "out.b", c.vocab));
+    if (e->w.find("zero_bias") == e->w.end()) {
+      NarTensor z; z.numel = D; z.dtype = kF32;
+      NCK(cudaMalloc(&z.ptr, (size_t)D * 4));
+      NCK(cudaMemsetAsync(z.ptr, 0, (size_t)D * 4, e->st));
+      e->w["zero_bias"] = z;
+    }
   }
-  const int n_all = c.n_blocks0 + c.n_blocks + c.n_tp_blocks;
-  for (int i = 0; i < n_all; ++i) {
-    const std::string p = "blk" + std::to_string(i) + ".";
-    const int64_t din = i == 0 ? feat : D;
-    NRET(nar_need(e, p + "norm1.g", din)); NRET(nar_need(e, p + "norm1.b", din));
-    NRET(nar_need(e, p + "qkv.w", 3 * D * din)); NRET(nar_need(e, p + "qkv.b", 3 * D));
-    NRET(nar_need(e, p + "fsmn.w", D * c.fsmn_kernel)); NRET(nar_need(e, p + "fsmn.b", D));
-    NRET(nar_need(e, p + "out.w", D * D));
-    NRET(nar_need(e, p + "norm2.g", D)); NRET(nar_need(e, p + "norm2.b", D));
-    NRET(nar_need(e, p + "w1.w", f * D)); NRET(nar_need(e, p + "w1.b", f));
-    NRET(nar_need(e, p + "w2.w", D * f)); NRET(nar_need(e, p + "w2.b", D));
-  }
-  NRET(nar_need(e, "after_norm.g", D)); NRET(nar_need(e, "after_norm.b", D));
-  NRET(nar_need(e, "tp_norm.g", D)); NRET(nar_need(e, "tp_norm.b", D));
-  NRET(nar_need(e, "ctc.w", (int64_t)c.vocab * D)); NRET(nar_need(e, "ctc.b", c.vocab));
   if (e->finalized) return B200ASR_OK;
   if (e->stage_buf) { cudaFree(e->stage_buf); e->stage_buf = nullptr; e->stage_cap = 0; }
   if (!e->pcm) {
@@ -453,7 +702,7 @@ int b200asr_nar_finalize_weights(b200asr_nar* e) {
     NRET(nar_alloc(e, &e->xhat, (size_t)M * wide * es));
     NRET(nar_alloc(e, &e->qkv, (size_t)M * 3 * D * es));
     NRET(nar_alloc(e, &e->ctx, (size_t)M * D * es));
-    NRET(nar_alloc(e, &e->ffn, (size_t)M * f * es));
+    NRET(nar_alloc(e, &e->ffn, (size_t)M * (f > c.dec_ffn ? f : c.dec_ffn) * es));
     NRET(nar_alloc(e, &e->S, (size_t)B * H * Tm * Tm * 4));
     NRET(nar_alloc(e, &e->P, (size_t)B * H * Tm * Tm * es));
     NRET(nar_alloc(e, &e->logits, (size_t)M * c.vocab * 4));
@@ -461,6 +710,21 @@ int b200asr_nar_finalize_weights(b200asr_nar* e) {
     NRET(nar_alloc(e, &e->tokens, (size_t)B * Tm * 4));
     NRET(nar_alloc(e, &e->lens, (size_t)B * 4));
     NRET(nar_alloc(e, &e->lang, (size_t)B * 4));
+    if (c.kind == B200ASR_NAR_PARAFORMER) {
+      const int64_t pad = (c.cif_kernel - 1) / 2;
+      NRET(nar_alloc(e, &e->enc_pad, (size_t)B * (Tm + 2 * pad) * D * es));
+      NRET(nar_alloc(e, &e->conv_out, (size_t)M * D * es));
+      NRET(nar_alloc(e, &e->kvbuf, (size_t)Tm * 2 * D * es));
+      NRET(nar_alloc(e, &e->dq, (size_t)Tm * D * es));
+      NRET(nar_alloc(e, &e->alphas, (size_t)B * (Tm + 1) * 4));
+      NRET(nar_alloc(e, &e->acoustic, (size_t)B * (Tm + 1) * D * 4));
+      NRET(nar_alloc(e, &e->dec, (size_t)Tm * D * 4));
+      NRET(nar_alloc(e, &e->dx, (size_t)Tm * D * 4));
+      NRET(nar_alloc(e, &e->sa_in, (size_t)Tm * D * 4));
+      NRET(nar_alloc(e, &e->f32buf, (size_t)Tm * c.dec_ffn * 4));
+      NRET(nar_alloc(e, &e->dec_logits, (size_t)Tm * c.vocab * 4));
+      NRET(nar_alloc(e, &e->n_tok, (size_t)B * 4));
+    }
     NCK(cudaMallocHost(&e->h_pinned, (size_t)B * (Tm + 2) * 4 + 64));
     const int span = (kFbFrames - 1) * c.hop + c.win;
     NCK(cudaFuncSetAttribute(kaldi_fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((span + kFbFrames * F) * sizeof(float))));
@@ -474,18 +738,20 @@ static int nar_upload(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, i
                       const int32_t* language_idx) {
   const b200asr_nar_config& c = e->cfg;
   if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
-  if (!pcm_host || !language_idx) return e->fail(B200ASR_E_INVALID, "null argument");
+  const bool para = c.kind == B200ASR_NAR_PARAFORMER;
+  if (!pcm_host || (!language_idx && !para)) return e->fail(B200ASR_E_INVALID, "null argument");
   if (batch <= 0 || batch > c.max_batch) return e->fail(B200ASR_E_INVALID, "batch out of range");
   if (n_samples < c.win || n_samples > c.max_samples) return e->fail(B200ASR_E_INVALID, "n_samples out of range");
   if (pcm_dtype != B200ASR_PCM_I16 && pcm_dtype != B200ASR_PCM_F32) return e->fail(B200ASR_E_INVALID, "bad pcm dtype");
-  for (int b = 0; b < batch; ++b)
-    if (language_idx[b] < 0 || language_idx[b] >= c.n_lang) return e->fail(B200ASR_E_INVALID, "language_idx out of range");
+  if (!para)
+    for (int b = 0; b < batch; ++b)
+      if (language_idx[b] < 0 || language_idx[b] >= c.n_lang) return e->fail(B200ASR_E_INVALID, "language_idx out of range");
   e->B = batch; e->n_samples = n_samples; e->pcm_dtype = pcm_dtype;
   e->frames = (n_samples - c.win) / c.hop + 1;
   e->T_lfr = (e->frames + c.lfr_n - 1) / c.lfr_n;
   e->T = e->T_lfr + c.n_prompt;
   NCK(cudaMemcpyAsync(e->pcm, pcm_host, (size_t)batch * n_samples * (pcm_dtype == B200ASR_PCM_F32 ? 4 : 2), cudaMemcpyHostToDevice, e->st));
-  NCK(cudaMemcpyAsync(e->lang, language_idx, (size_t)batch * 4, cudaMemcpyHostToDevice, e->st));
+  if (!para) NCK(cudaMemcpyAsync(e->lang, language_idx, (size_t)batch * 4, cudaMemcpyHostToDevice, e->st));
   return B200ASR_OK;
 }
 
@@ -544,6 +810,10 @@ int b200asr_nar_get_stage(b200asr_nar* e, const char* name_c, float* out, int64_
   else if (name == "enc_out") { src = e->enc_out; n = B * T * c.d_model; }
   else if (name == "logits") { src = e->logits; n = B * T * c.vocab; }
   else if (name == "frame_ids") { src = e->frame_ids; n = B * T; is_int = true; }
+  else if (name == "alphas" && e->alphas) { src = e->alphas; n = B * (T + 1); }
+  else if (name == "acoustic" && e->acoustic) { src = e->acoustic; n = B * (T + 1) * c.d_model; }
+  else if (name == "dec_logits" && e->dec_logits) { src = e->dec_logits; n = (int64_t)e->last_rows * c.vocab; }
+  else if (name == "n_tok" && e->n_tok) { src = e->n_tok; n = B; is_int = true; }
   else return e->fail(B200ASR_E_INVALID, "unknown stage '" + name + "'");
   if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
   NCK(cudaStreamSynchronize(e->st));

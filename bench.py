@@ -176,23 +176,29 @@ def run_sensevoice(args):
     """Parity-case leg (BASELINE config 0): SenseVoiceSmall, 8 s clips, one run = front end + 70 SANM blocks + CTC.
     Not the headline: `python bench.py --preset sensevoice-small [--precision f32|bf16] [--batch-per-gpu B]`."""
     from b200asr import sensevoice as sv
+    from b200asr import paraformer as pfm
     from b200asr.synth import synth_batch
-    dims = sv.PRESETS[args.preset]
+    para = args.preset.startswith("paraformer")
+    dims = (pfm.PRESETS if para else sv.PRESETS)[args.preset]
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         if rank != 0:
             return
-        from oracle import sensevoice_oracle as so
+        if para:
+            from oracle import paraformer_oracle as so
+            od = so.ParaformerDims(**dims.to_dict())
+        else:
+            from oracle import sensevoice_oracle as so
+            od = so.SenseVoiceDims(**dims.to_dict())
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        od = so.SenseVoiceDims(**dims.to_dict())
         fw = so.fold_weights(so.make_raw_weights(od, SEED), od, dims.lfr_frames(N_SAMPLES))
         steps, warm = (args.steps or 3), (args.warmup or 1)
         times = []
         with torch.no_grad():
             for i in range(warm + steps):
                 pcm = synth_batch(1, N_SAMPLES, first_index=i)[0]
-                t = time.time(); so.transcribe(pcm, fw, od, 0); dt = time.time() - t
+                t = time.time(); (so.transcribe(pcm, fw, od) if para else so.transcribe(pcm, fw, od, 0)); dt = time.time() - t
                 if i >= warm:
                     times.append(dt)
         audio_s = N_SAMPLES / dims.sample_rate
@@ -202,7 +208,7 @@ def run_sensevoice(args):
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"{args.preset} f32, batch=1, 8 s clip, host CPU"},
                           "cpu_baseline": {"value": v, "unit": "x real time", "cores": cores, "kind": "port",
-                                           "sample": f"{len(times)} clip(s); oracle/sensevoice_oracle.py (torch fp32 restatement of SENSE_VOICE.forward)"},
+                                           "sample": f"{len(times)} clip(s); oracle/{'paraformer' if para else 'sensevoice'}_oracle.py (torch fp32 restatement of the reference graph)"},
                           "e2e": {"value": v, "unit": "x real time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
     steps = args.steps if args.steps is not None else 20
@@ -210,8 +216,12 @@ def run_sensevoice(args):
     B = args.batch_per_gpu
     torch.cuda.set_device(0)
     t0 = time.time()
-    tensors = sv.fold_sensevoice(sv.synth_sensevoice_checkpoint(dims, SEED), dims, N_SAMPLES)
-    eng = sv.SenseVoiceEngine(dims, tensors, precision=args.precision, max_batch=B, max_samples=N_SAMPLES)
+    if para:
+        tensors = pfm.fold_paraformer(pfm.synth_paraformer_checkpoint(dims, SEED), dims, N_SAMPLES)
+        eng = pfm.ParaformerEngine(dims, tensors, precision=args.precision, max_batch=B, max_samples=N_SAMPLES)
+    else:
+        tensors = sv.fold_sensevoice(sv.synth_sensevoice_checkpoint(dims, SEED), dims, N_SAMPLES)
+        eng = sv.SenseVoiceEngine(dims, tensors, precision=args.precision, max_batch=B, max_samples=N_SAMPLES)
     del tensors
     setup_s = time.time() - t0
     pcm = torch.from_numpy(synth_batch(B, N_SAMPLES)).pin_memory().numpy()
@@ -235,20 +245,23 @@ def run_sensevoice(args):
     clocks = sampler.stop()
     ms_e2e = timed(lambda: eng.run(pcm, 0), steps)
     audio = N_SAMPLES / dims.sample_rate * B * steps
-    T = dims.lfr_frames(N_SAMPLES) + 4
+    T = dims.lfr_frames(N_SAMPLES) + (0 if para else 4)
     d, f = dims.d_model, dims.ffn
-    flops = B * (2 * T * (3 * d * dims.feat + d * d + 2 * d * f) + (dims.total_blocks - 1) * 2 * T * (3 * d * d + d * d + 2 * d * f)
-                 + dims.total_blocks * 4 * T * T * d + 2 * T * d * dims.vocab + 2 * dims.frames(N_SAMPLES) * dims.win * (dims.nfft + 2))
-    wbytes = (2 if args.precision == "bf16" else 4) * (dims.total_blocks * (4 * d * d + 2 * d * f) + d * dims.vocab)
+    nblk = dims.enc_blocks if para else dims.total_blocks
+    flops = B * (2 * T * (3 * d * dims.feat + d * d + 2 * d * f) + (nblk - 1) * 2 * T * (3 * d * d + d * d + 2 * d * f)
+                 + nblk * 4 * T * T * d + 2 * dims.frames(N_SAMPLES) * dims.win * (dims.nfft + 2) + (0 if para else 2 * T * d * dims.vocab))
+    wbytes = (2 if args.precision == "bf16" else 4) * (nblk * (4 * d * d + 2 * d * f) + d * dims.vocab
+                                                       + (dims.dec_att_blocks * (4 * d * d + 2 * d * dims.dec_ffn) + 3 * d * d if para else 0))
     line = {"metric": "xRT (audio_s/wall_s)", "value": audio / (ms / 1e3), "unit": "x real time", "n_gpus": 1, "steps": steps,
             "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic", "impl": "b200",
-            "config": {"workload": f"{args.preset} {args.precision}, batch={B}, 8 s clips, 1xB200: fbank + LFR + {dims.total_blocks} SANM blocks + CTC",
-                       "weights": "seeded random init", "l2": "weights (0.47 GB bf16 / 0.94 GB f32) exceed the 126 MB L2"},
+            "config": {"workload": f"{args.preset} {args.precision}, batch={B}, 8 s clips, 1xB200: fbank + LFR + {nblk} SANM blocks + "
+                                   + ("CIF + FSMN/cross-attention decoder" if para else "CTC"),
+                       "weights": "seeded random init", "l2": "weights (~0.45 GB bf16 / ~0.9 GB f32) exceed the 126 MB L2"},
             "e2e": {"value": audio / (ms_e2e / 1e3), "unit": "x real time", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": int(pcm.nbytes + 4 * B), "d2h_bytes_per_step": int(B * (T + 1) * 4)},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"kernel": "whole run (launch-bound at batch 1: ~9 launches per SANM block)", "bound": "hbm",
+            "roofline": {"kernel": "whole run (launch-bound at batch 1: ~9 launches per block)", "bound": "hbm",
                          "achieved": wbytes / (ms / steps / 1e3) / 1e9, "peak": 6650.0, "unit": "GB/s",
                          "frac": wbytes / (ms / steps / 1e3) / 1e9 / 6650.0, "traffic": None, "algorithmic_bytes_per_launch": wbytes,
                          "tflops": flops / (ms / steps / 1e3) / 1e12},
@@ -268,7 +281,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.preset.startswith("sensevoice"):
+    if args.preset.startswith("sensevoice") or args.preset.startswith("paraformer"):
         return run_sensevoice(args)
     dims = _dims(args.preset)
     if args.impl == "reference":

@@ -136,6 +136,7 @@ int b200asr_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_
  * many independent clips of equal length.
  * ------------------------------------------------------------------------------------------- */
 #define B200ASR_NAR_SENSEVOICE 0
+#define B200ASR_NAR_PARAFORMER 1   /* Paraformer/Non-Streaming/Inference_Paraformer_ONNX.py:293; math Export_Paraformer.py:474-563 */
 
 typedef struct b200asr_nar b200asr_nar;
 
@@ -152,6 +153,11 @@ typedef struct b200asr_nar_config {
   int32_t max_batch, max_samples;
   int32_t precision, device, use_tensor_cores;
   float ln_eps;                    /* LayerNorm epsilon of the checkpoint's norm modules */
+  /* Paraformer only (ignored for SenseVoice): n_tp_blocks = 0, n_prompt = 0, n_lang = 0 */
+  int32_t dec_att_blocks, dec_ffn_blocks, dec_ffn;   /* 16 / 1 / 2048 */
+  int32_t cif_kernel;              /* 3 */
+  float tail_threshold;            /* 0.45 appended to the alpha sequence */
+  float dec_ln_eps;
 } b200asr_nar_config;
 
 int b200asr_nar_create(const b200asr_nar_config* cfg, b200asr_nar** out);
@@ -160,11 +166,14 @@ const char* b200asr_nar_last_error(const b200asr_nar* e);
 /* tensors (fp32, as the exported graph holds them): fbank_kernel [2F][win], mel_filters [F][n_mels], cmvn_means,
  * cmvn_vars [feat], speech_position [>= max T_lfr][feat], language_embed [n_lang][feat], system_embed [n_prompt-1][feat],
  * blk{i}.{norm1.g,norm1.b,qkv.w,qkv.b,fsmn.w,fsmn.b,out.w,norm2.g,norm2.b,w1.w,w1.b,w2.w,w2.b}, after_norm.{g,b},
- * tp_norm.{g,b}, ctc.{w,b} */
+ * tp_norm.{g,b}, ctc.{w,b}
+ * Paraformer: fbank_kernel, mel_filters, cmvn_vars, encoder_input_bias [>= max T_lfr][feat], enc{i}.{qkv.w,qkv.b,fsmn.w,out.w,
+ * out.b,w1.w,w1.b,w2.w,w2.b} (LayerNorm affines already folded), enc_after_norm.{g,b}, cif.conv.{w [D][D][k],b},
+ * cif.out.{w,b}, dec{i}.{w1.w,w1.b,w2.w,w2.b[,norm2.g,norm2.b,fsmn.w,q.w,q.b,kv.w,kv.b,cout.w,cout.b]}, out.{w,b} */
 int b200asr_nar_set_tensor(b200asr_nar* e, const char* name, const float* host_data, int64_t numel);
 int b200asr_nar_finalize_weights(b200asr_nar* e);
 /* pcm [batch][n_samples]: int16, or float32 carrying int16-range values (audio_pcm_scale = 1); language_idx [batch]
- * selects the language prompt row; tokens_out [batch][tokens_ld], lens_out [batch] */
+ * selects the language prompt row (ignored, may be NULL, for Paraformer); tokens_out [batch][tokens_ld], lens_out [batch] */
 int b200asr_nar_run(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
                     const int32_t* language_idx, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
 /* same, split so a benchmark can time with the PCM already resident in HBM */

@@ -1,0 +1,66 @@
+"""Paraformer on the CUDA engine (csrc/sanm.cu, kind = PARAFORMER) against goldens minted from the reference PARAFORMER
+module.  fp32: encoder output / alphas / acoustic embeddings / logits within 2e-3, CIF token count and token ids exact.
+bf16: token count may only differ when the float64 prefix sum lands within 0.02 of an integer (not the case for the
+goldens); ids equal wherever the oracle's top-2 logit margin exceeds 0.5."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import paraformer_oracle as po
+from b200asr import paraformer as pf
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted((Path(__file__).parent / "golden").glob("paraformer_tiny_case*.npz"))
+D = pf.PARAFORMER_TINY_TEST
+MAX_SAMPLES = 160000
+
+
+def _engine(seed, precision, max_batch=1):
+    raw = pf.synth_paraformer_checkpoint(D, seed)
+    return pf.ParaformerEngine(D, pf.fold_paraformer(raw, D, MAX_SAMPLES), precision=precision, max_batch=max_batch,
+                               max_samples=MAX_SAMPLES)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])
+def test_paraformer_f32_vs_reference_golden(path):
+    g = dict(np.load(path))
+    eng = _engine(int(g["seed"]), "f32")
+    toks = eng.run(g["pcm"])[0]
+    T = g["enc_out"].shape[0]
+    n = int(g["num"][0])
+    np.testing.assert_allclose(eng.get_stage("mel", g["mel"].size).reshape(g["mel"].shape), g["mel"], atol=2e-3)
+    np.testing.assert_allclose(eng.get_stage("enc_out", T * D.d_model).reshape(T, D.d_model), g["enc_out"], atol=2e-3)
+    np.testing.assert_allclose(eng.get_stage("alphas", T + 1)[:T], g["alphas"], atol=1e-4)
+    assert int(eng.get_stage("n_tok", 1)[0]) == n
+    ac = eng.get_stage("acoustic", (T + 1) * D.d_model).reshape(T + 1, D.d_model)[:n]
+    np.testing.assert_allclose(ac, g["acoustic"], atol=2e-3)
+    lg = eng.get_stage("dec_logits", max(n, 1) * D.vocab).reshape(max(n, 1), D.vocab)
+    np.testing.assert_allclose(lg[:, :64], g["logits_sub"], atol=3e-3)
+    assert toks == g["tokens"].tolist()
+    assert eng.run(g["pcm"].astype(np.float32))[0] == g["tokens"].tolist()
+    eng.close()
+
+
+def test_paraformer_bf16_and_batch():
+    g = dict(np.load(GOLD[0]))
+    raw = po.make_raw_weights(po.TINY_TEST, int(g["seed"]))
+    fw = po.fold_weights(raw, po.TINY_TEST, D.lfr_frames(MAX_SAMPLES))
+    rng = np.random.default_rng(2)
+    clips = (rng.standard_normal((3, 36000)) * 2500).clip(-32768, 32767).astype(np.int16)
+    with torch.no_grad():
+        want = [po.transcribe(clips[i], fw, po.TINY_TEST, return_stages=True) for i in range(3)]
+    eng = _engine(int(g["seed"]), "f32", max_batch=3)
+    assert eng.run(clips) == [w[0] for w in want]                 # ragged token counts across the batch
+    eng.close()
+    eng = _engine(int(g["seed"]), "bf16", max_batch=3)
+    got = eng.run(clips)
+    for i in range(3):
+        toks, st = want[i]
+        assert len(got[i]) == len(toks)
+        lg = st["logits"].numpy()[:len(toks)]
+        top2 = np.sort(lg, axis=-1)[:, -2:]
+        safe = (top2[:, 1] - top2[:, 0]) > 0.5
+        assert np.array_equal(np.asarray(got[i])[safe], np.asarray(toks)[safe])
+    eng.close()

@@ -50,3 +50,49 @@ def test_product_folds_equal_oracle_folds():
     cat = sv.build_supported_languages()
     assert [cat[c]["selector_index"] for c in ("auto", "zh", "en", "yue", "ja", "ko", "nospeech")] == list(range(7))
     assert cat["en"]["prompt_token_ids"] == [4]
+
+
+# ---- Paraformer (a14) -------------------------------------------------------------------------------------------
+from oracle import paraformer_oracle as po       # noqa: E402
+from b200asr import paraformer as pf             # noqa: E402
+
+PGOLD = sorted((Path(__file__).parent / "golden").glob("paraformer_tiny_case*.npz"))
+
+
+@pytest.mark.parametrize("path", PGOLD, ids=[p.stem for p in PGOLD])
+def test_paraformer_oracle_matches_reference_golden(path):
+    g = dict(np.load(path))
+    raw = po.make_raw_weights(po.TINY_TEST, int(g["seed"]))
+    fw = po.fold_weights(raw, po.TINY_TEST, int(g["max_lfr"]))
+    with torch.no_grad():
+        toks, st = po.transcribe(g["pcm"], fw, po.TINY_TEST, return_stages=True)
+    assert toks == g["tokens"].tolist() and st["n_tok"] == int(g["num"][0])
+    np.testing.assert_allclose(st["mel"].numpy(), g["mel"], atol=1e-4)
+
+
+def test_cif_fires_where_the_float64_prefix_floor_advances():
+    d = po.TINY_TEST
+    enc = torch.arange(6 * d.d_model, dtype=torch.float32).reshape(6, d.d_model) / 100.0
+    fw = {"cif.conv.w": torch.zeros(d.d_model, d.d_model, 3), "cif.conv.b": torch.zeros(d.d_model),
+          "cif.out.w": torch.zeros(1, d.d_model), "cif.out.b": torch.tensor([0.0])}      # alpha = 0.5 everywhere
+    ac, n, alphas = po.cif(enc, fw, d)
+    assert torch.allclose(alphas, torch.full((6,), 0.5))
+    assert n == 3 and ac.shape == (3, d.d_model)                 # 6 x 0.5 + tail 0.45 = 3.45
+    np.testing.assert_allclose(ac[0].numpy(), (0.5 * enc[0] + 0.5 * enc[1]).numpy(), rtol=1e-6)   # remains = 0 at the fire
+    fw["cif.out.b"] = torch.tensor([-20.0])                      # alpha ~ 0: only the tail, nothing fires
+    ac, n, _ = po.cif(enc, fw, d)
+    assert n == 0 and ac.shape[0] == 0
+
+
+def test_paraformer_product_folds_equal_oracle_folds():
+    d, o = pf.PARAFORMER_TINY_TEST, po.TINY_TEST
+    assert d.to_dict() == o.to_dict()
+    raw_p, raw_o = pf.synth_paraformer_checkpoint(d, 2), po.make_raw_weights(o, 2)
+    assert raw_p.keys() == raw_o.keys() and all(torch.equal(raw_p[k], raw_o[k]) for k in raw_p)
+    fp = pf.fold_paraformer(raw_p, d, 64000)
+    fo = po.fold_weights(raw_o, o, d.lfr_frames(64000))
+    assert fp.keys() == fo.keys()
+    for k in fp:
+        assert np.array_equal(fp[k], fo[k].numpy()), k
+    assert pf.tokens_to_text([0, 1, 2], ["hel@@", "lo", "world"], "en") == "hello world"
+    assert pf.tokens_to_text([0, 1], ["你", "好"], "zh") == "你好"
