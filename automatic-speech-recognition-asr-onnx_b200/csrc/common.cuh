@@ -177,6 +177,8 @@ struct RingArgs {
   unsigned long long* ll; long long ll_stride;   // 4 exchange buffers of ll_stride 8-byte words each (zeroed per launch)
   int ld_vec;                                    // words per utterance row in an exchange buffer
   int n_stages, stage_bytes;                     // shared-memory ring
+  int box_rows;                                  // cross-attention K/V rows per ring stage (TMA box)
+  int tc;                                        // 1: mma.sync dot products (weight rows skewed by 16 B in the ring)
   int task_inv;                                  // inverse (mod grid) of the attention-task -> CTA stride
   int part_cap, sc_cap;
   int debug;                                     // timing experiments: skip parts of a phase (see decoder_ring.cu)
@@ -184,7 +186,7 @@ struct RingArgs {
 };
 constexpr int kRingTaskMul = 7;                  // task t of layer l -> CTA (t * 7 + offset(l)) % grid
 bool ring_supported(int batch, int d, int ffn, int n_heads, int vocab, int num_sms);
-bool ring_plan(const MegaArgs& a, int num_sms, RingArgs* ra, size_t* smem_bytes);
+bool ring_plan(const MegaArgs& a, int num_sms, bool tc, RingArgs* ra, size_t* smem_bytes);
 size_t ring_exchange_words(int batch, int d, int ffn, int num_sms);
 cudaError_t launch_decoder_ring(const RingArgs& ra, const CUtensorMap& cross_map, int num_sms, size_t smem_bytes,
                                 cudaStream_t st);

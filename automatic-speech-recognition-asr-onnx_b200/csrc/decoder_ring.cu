@@ -33,6 +33,7 @@ constexpr int kRingConsumers = kRingConsumerWarps * 32;     // 512
 constexpr int kRingThreads = kRingConsumers + 32;           // + producer warp
 constexpr int kRingMaxStages = 16;
 constexpr int kSegPerStage = 8;                             // d-wide weight segments per ring stage
+constexpr int kTcRound = 8;                                 // TC path: chunks whose per-warp partials are reduced together
 constexpr long long kSpinLimit = 6000000000LL;              // ~3 s at 2 GHz: a protocol bug traps instead of hanging
 
 // ---------------------------------------------------------------------------
@@ -125,6 +126,15 @@ __device__ __forceinline__ void ll_gather(const unsigned long long* src, int n, 
   }
 }
 
+// warp-level tensor-core pieces of the TC dot-product path (weights = A, activations = B)
+__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(saddr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 struct Pipe { int stage; uint32_t phase; };
 __device__ __forceinline__ void pipe_advance(Pipe& p, int n_stages) {
   if (++p.stage == n_stages) { p.stage = 0; p.phase ^= 1; }
@@ -174,7 +184,7 @@ __device__ __forceinline__ int my_task(const RingArgs& ra, int l, int kind, int 
 }  // namespace
 
 // ---------------------------------------------------------------------------
-template <int NR, bool DBG>
+template <int NR, bool DBG, bool TC>
 __global__ void __launch_bounds__(kRingThreads, 1)
 decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_constant__ RingArgs ra) {
   const MegaArgs& a = ra.m;
@@ -190,6 +200,8 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
   float* qs = sc + ra.sc_cap;                                        // [64]
   float* opart = qs + 64;                                            // [16][64]
   float* cand = opart + kRingConsumerWarps * 64;                     // [G][NR][2]
+  float* sbias2 = cand + (size_t)gridDim.x * NR * 2;                 // [2][part_cap] bias slice of the current / next phase (TC path)
+  float* tcpart = sbias2 + 2 * ra.part_cap;                             // [kTcRound][16 warps][8 rows][NR] (TC path)
 
   __shared__ uint64_t full_bar[kRingMaxStages], empty_bar[kRingMaxStages];
   __shared__ float wbest_v[kRingConsumerWarps * 4];
@@ -203,7 +215,8 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x;
   const int L = a.n_layers;
-  const int R = SB / 128;                          // cross-attention rows per ring stage
+  const int R = ra.box_rows;                       // cross-attention rows per ring stage
+  const int P = TC ? 2 * d + 16 : 2 * d;           // TC path: weight rows land 16 bytes askew so ldmatrix is conflict-free
   const int nbox = (T + R - 1) / R;
   const int ntask = B * H;
   const int dbg = DBG ? ra.debug : 0;              // timing experiments only (results are garbage when set)
@@ -227,28 +240,55 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
   // producer: one lane streams this CTA's share of every token's read stream
   // =========================================================================
   if (warp == kRingConsumerWarps) {
-    if (lane == 0) {
+    {                                             // the whole warp walks the schedule; lane 0 owns the barriers
       Pipe p{0, 0};
       long long issued = 0;
       bool stop = false;
-      auto acquire = [&]() -> bool {           // wait until the consumers released ring slot p.stage
-        if (rbar_try_wait(&empty_bar[p.stage], p.phase ^ 1)) return true;
-        const long long t0 = clock64();
-        while (!rbar_try_wait(&empty_bar[p.stage], p.phase ^ 1)) {
-          if (s_stop) return false;
-          if (clock64() - t0 > kSpinLimit) { printf("b200asr decoder_ring: producer stalled (block %d)\n", blockIdx.x); __trap(); }
+      auto acquire = [&]() -> bool {           // wait until the consumers released ring slot p.stage (warp-uniform result)
+        int ok = 1;
+        if (lane == 0) {
+          if (s_stop) ok = 0;
+          else if (!rbar_try_wait(&empty_bar[p.stage], p.phase ^ 1)) {
+            const long long t0 = clock64();
+            while (!rbar_try_wait(&empty_bar[p.stage], p.phase ^ 1)) {
+              if (s_stop) { ok = 0; break; }
+              if (clock64() - t0 > kSpinLimit) { printf("b200asr decoder_ring: producer stalled (block %d)\n", blockIdx.x); __trap(); }
+            }
+          }
         }
-        return true;
+        return __shfl_sync(0xffffffffu, ok, 0) != 0;
       };
       auto stream_rows = [&](const bf16* W, int N, int K) {
         int n0, cnt; col_split(N, n0, cnt);
+        if (TC) {
+          // chunk = up to 8 weight rows x one d-wide K part, one bulk copy per row (rows land P bytes apart);
+          // K parts outermost so a consumer warp re-reads its activation fragment only when the part changes
+          const int kparts = K / d, ngroups = (cnt + 7) >> 3;
+          for (int part = 0; part < kparts && !stop; ++part)
+            for (int grp = 0; grp < ngroups && !stop; ++grp) {
+              if (!acquire()) { stop = true; break; }
+              const int nrows = min(8, cnt - grp * 8);
+              if (lane == 0) rbar_expect_tx(&full_bar[p.stage], (uint32_t)(nrows * 2 * d));
+              if (ra.debug & 32) {                  // timing experiment: one copy per chunk (rows land unskewed: garbage results)
+                if (lane == 0) bulk_g2s(ring + (size_t)p.stage * SB, W + ((long long)(n0 + grp * 8) * K + (long long)part * d),
+                                        (uint32_t)(nrows * 2 * d), &full_bar[p.stage]);
+              } else
+              if (lane < nrows)                     // one copy per lane: the eight row copies of a chunk issue in parallel
+                bulk_g2s(ring + (size_t)p.stage * SB + (size_t)lane * P, W + ((long long)(n0 + grp * 8 + lane) * K + (long long)part * d),
+                         (uint32_t)(2 * d), &full_bar[p.stage]);
+              ++issued; pipe_advance(p, NS);
+            }
+          return;
+        }
         const char* src = reinterpret_cast<const char*>(W + (long long)n0 * K);
         const long long bytes = (long long)cnt * K * 2;
         for (long long off = 0; off < bytes && !stop; off += SB) {
-          if (s_stop || !acquire()) { stop = true; break; }
+          if (!acquire()) { stop = true; break; }
           const uint32_t n = (uint32_t)min((long long)SB, bytes - off);
-          rbar_expect_tx(&full_bar[p.stage], n);
-          bulk_g2s(ring + (size_t)p.stage * SB, src + off, n, &full_bar[p.stage]);
+          if (lane == 0) {
+            rbar_expect_tx(&full_bar[p.stage], n);
+            bulk_g2s(ring + (size_t)p.stage * SB, src + off, n, &full_bar[p.stage]);
+          }
           ++issued; pipe_advance(p, NS);
         }
       };
@@ -267,9 +307,11 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
             for (int i = 0; i < 2 * nbox; ++i) {
               const int kind = i >= nbox ? 1 : 0;
               const int row0 = ((kind * L + l) * B + b) * T + (i - kind * nbox) * R;
-              if (s_stop || !acquire()) { stop = true; break; }
-              rbar_expect_tx(&full_bar[p.stage], (uint32_t)SB);
-              tma_g2s_2d(ring + (size_t)p.stage * SB, &cross_map, h * 64, row0, &full_bar[p.stage]);
+              if (!acquire()) { stop = true; break; }
+              if (lane == 0) {
+                rbar_expect_tx(&full_bar[p.stage], (uint32_t)(R * 128));
+                tma_g2s_2d(ring + (size_t)p.stage * SB, &cross_map, h * 64, row0, &full_bar[p.stage]);
+              }
               ++issued; pipe_advance(p, NS);
             }
             continue;
@@ -280,7 +322,8 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
         }
       }
       // drain: every copy that was issued must have landed before the CTA may exit
-      for (int s = 0; s < NS; ++s) {
+      __syncwarp();
+      for (int s = 0; s < NS && lane == 0; ++s) {
         if (issued > s) {
           const uint32_t par = (s < p.stage) ? p.phase : (p.phase ^ 1);
           rbar_wait(&full_bar[s], par);
@@ -331,7 +374,9 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
     const unsigned long long* in = exbuf(seq - 1);
     // epilogue operands fetched before the wait so their latency hides behind it
     float bias_v = 0.f;
-    if (Lp.out_mode != kROutHead && tid < cnt * NR && Lp.bias) bias_v = Lp.bias[n0 + tid / NR];
+    if (!TC && Lp.out_mode != kROutHead && tid < cnt * NR && Lp.bias) bias_v = Lp.bias[n0 + tid / NR];
+    float* sbias = sbias2 + (seq & 1u) * ra.part_cap;       // alternates per phase: the previous phase's epilogue may still read its copy
+    if (TC && tid < cnt) sbias[tid] = Lp.bias ? Lp.bias[n0 + tid] : 0.f;
     // ---- input ----
     constexpr int GV = 4;                          // values of one d-wide row a thread stages (d <= 2048)
     if (Lp.in_mode == kRInVec) {
@@ -419,6 +464,97 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
       csync();
     }
     fstamp();
+    unsigned long long* out = exbuf(seq);
+    if constexpr (TC) {
+      // ---- weights off the ring on the tensor cores: a chunk is an [8 rows][d] bf16 tile; warp w multiplies its
+      //      d/16-wide K slice (mma.sync m16n8k16, rows 8-15 of the A tile zero) by the activation fragment it keeps in
+      //      registers (B operand: up to 8 utterances), and leaves an [8][NR] partial for the cross-warp reduction ----
+      const int kparts = K / d, ngroups = (cnt + 7) >> 3, nchunk = kparts * ngroups;
+      const int ksl = d >> 4;                      // K elements per warp
+      const int nsteps = ksl >> 4;                 // k16 steps per warp (d = 1280: 5)
+      constexpr int XS = 5;
+      uint32_t bfr[XS][2];
+      int cur_part = -1;
+      const int g8 = lane >> 2, q4 = lane & 3;
+      for (int c0 = 0; c0 < nchunk; c0 += kTcRound) {
+        const int cend = min(nchunk, c0 + kTcRound);
+        for (int ch = c0; ch < cend; ++ch) {
+          const int part_i = kparts > 1 ? ch / ngroups : 0;
+          if (part_i != cur_part) {
+            cur_part = part_i;
+            const float* xb = xs + part_i * d + warp * ksl + q4 * 2;        // B[k][n] = x_hat[n][k], n = lane / 4
+#pragma unroll
+            for (int sidx = 0; sidx < XS; ++sidx) {
+              float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+              if (sidx < nsteps && g8 < NR) {
+                lo = *reinterpret_cast<const float2*>(xb + (size_t)g8 * K + sidx * 16);
+                hi = *reinterpret_cast<const float2*>(xb + (size_t)g8 * K + sidx * 16 + 8);
+              }
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(lo.x, lo.y), h2 = __floats2bfloat162_rn(hi.x, hi.y);
+              bfr[sidx][0] = *reinterpret_cast<const uint32_t*>(&l2);
+              bfr[sidx][1] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+          }
+          rbar_wait(&full_bar[pipe.stage], pipe.phase);
+          // independent accumulators: the k16 steps of a warp are not chained through one C fragment (the phase is
+          // latency-bound, a dependent mma.sync chain would cost ~35 cycles per step)
+          float cacc[XS][4];
+          const uint32_t abase = rs_u32(ring + (size_t)pipe.stage * SB) + (uint32_t)((lane & 7) * P) +
+                                 (uint32_t)((warp * ksl + ((lane >> 3) & 1) * 8) * 2);
+          uint32_t afr[XS][2];
+#pragma unroll
+          for (int sidx = 0; sidx < XS; ++sidx) {
+            afr[sidx][0] = afr[sidx][1] = 0u;
+            if (sidx < nsteps) ldsm_x2(afr[sidx][0], afr[sidx][1], abase + (uint32_t)(sidx * 32));
+          }
+#pragma unroll
+          for (int sidx = 0; sidx < XS; ++sidx) {
+            cacc[sidx][0] = cacc[sidx][1] = cacc[sidx][2] = cacc[sidx][3] = 0.f;
+            if (sidx < nsteps) mma_bf16_16816(cacc[sidx], afr[sidx][0], 0u, afr[sidx][1], 0u, bfr[sidx][0], bfr[sidx][1]);
+          }
+          const float s0 = ((cacc[0][0] + cacc[1][0]) + (cacc[2][0] + cacc[3][0])) + cacc[4][0];
+          const float s1 = ((cacc[0][1] + cacc[1][1]) + (cacc[2][1] + cacc[3][1])) + cacc[4][1];
+          float* tp = tcpart + ((size_t)((ch - c0) * kRingConsumerWarps + warp) * 8 + g8) * NR;
+          if (q4 * 2 < NR) tp[q4 * 2] = s0;
+          if (q4 * 2 + 1 < NR) tp[q4 * 2 + 1] = s1;
+          __syncwarp();
+          if (lane == 0) rbar_arrive(&empty_bar[pipe.stage]);
+          pipe_advance(pipe, NS);
+        }
+        csync();
+        // ---- reduce the 16 (x kparts) per-warp partials of every output of this round: 16 lanes per output ----
+        const int j_lo = kparts > 1 ? 0 : c0 * 8;
+        const int j_hi = kparts > 1 ? cnt : min(cnt, cend * 8);
+        const int n_out = (j_hi - j_lo) * NR;
+        for (int base = 0; base < n_out * 16; base += kRingConsumers) {
+          const int t = base + tid;
+          const int o = t >> 4, wsub = t & 15;
+          float v = 0.f;
+          int j = 0, r = 0;
+          if (o < n_out) {
+            j = j_lo + o / NR; r = o - (o / NR) * NR;
+            const int grp = j >> 3, g = j & 7;
+            for (int pi = 0; pi < kparts; ++pi) {
+              const int cc = (kparts > 1 ? pi * ngroups + grp : grp) - c0;
+              v += tcpart[((size_t)(cc * kRingConsumerWarps + wsub) * 8 + g) * NR + r];
+            }
+          }
+#pragma unroll
+          for (int sh = 8; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+          if (o < n_out && wsub == 0) {
+            if (Lp.out_mode == kROutHead) {
+              part[(size_t)j * NR + r] = v;          // summed logits; the head epilogue below adds bias / penalty
+            } else if (r < B) {
+              v += sbias[j];
+              if (Lp.act == kActGelu) v = gelu_erf(v);
+              if (Lp.out_mode == kROutResid) v += xloc[r * d + n0 + j];
+              ll_store(out + (size_t)r * ra.ld_vec + n0 + j, __float_as_uint(v), seq);
+            }
+          }
+        }
+        if (cend < nchunk || Lp.out_mode == kROutHead) csync();       // partials are reused by the next round
+      }
+    } else {
     // ---- weights off the ring: warp w takes half (w & 1) of segment (w >> 1) of every stage.  8 % kq == 0, so a
     //      warp always meets the same d/2-wide slice of the input row: it lives in registers for the whole phase ----
     const int nseg = cnt * kq;
@@ -499,10 +635,10 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
     }
     csync();
     fstamp();
+    }
     // ---- epilogue + publish ----
-    unsigned long long* out = exbuf(seq);
     if (Lp.out_mode != kROutHead) {
-      if (tid < cnt * NR) {
+      if (!TC && tid < cnt * NR) {
         const int j = tid / NR, r = tid - j * NR;
         if (r < B) {
           float v = 0.f;
@@ -520,7 +656,8 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
       if (r < B) {
         for (int t = tid; t < cnt * NR; t += kRingConsumers) {
           const int j = t / NR, n = n0 + j;
-          float v = part[(size_t)(j * 2) * NR + r] + part[(size_t)(j * 2 + 1) * NR + r] + Lp.bias[n];
+          float v = TC ? part[(size_t)j * NR + r] + sbias[j]
+                       : part[(size_t)(j * 2) * NR + r] + part[(size_t)(j * 2 + 1) * NR + r] + Lp.bias[n];
           if (pen_on) {
             bool hit = false;
             for (int q = 0; q < s_pen_n; ++q) hit |= (s_pen[r * 32 + q] == n);
@@ -822,21 +959,29 @@ bool ring_supported(int batch, int d, int ffn, int n_heads, int vocab, int num_s
 }
 
 // shared-memory plan for one launch; returns false when it does not fit
-bool ring_plan(const MegaArgs& a, int num_sms, RingArgs* ra, size_t* smem_bytes) {
+bool ring_plan(const MegaArgs& a, int num_sms, bool tc, RingArgs* ra, size_t* smem_bytes) {
   const int NR = ring_nr(a.batch);
   const int d = a.d, ffn = a.ffn;
   const int kmax = d > ffn ? d : ffn;
-  ra->stage_bytes = kSegPerStage * d * 2;
+  ra->tc = tc ? 1 : 0;
+  ra->stage_bytes = tc ? kSegPerStage * (2 * d + 16) : kSegPerStage * d * 2;
+  ra->box_rows = tc ? ((ra->stage_bytes / 128) & ~31) : ra->stage_bytes / 128;
   auto per_cta = [&](int N) { return (N + num_sms - 1) / num_sms; };
+  int max_cnt = std::max(std::max(per_cta(3 * d), per_cta(ffn)), std::max(per_cta(d), per_cta(a.vocab)));
   int cap = per_cta(3 * d) * 2;
   cap = std::max(cap, per_cta(ffn) * 2);
   cap = std::max(cap, per_cta(d) * 2 * (ffn / d));
   cap = std::max(cap, per_cta(a.vocab) * 2);
-  ra->part_cap = (cap + kSegPerStage * 2 + 3) & ~3;     // keeps the arrays carved after it 16-byte aligned
+  ra->part_cap = tc ? ((max_cnt + 3) & ~3) : ((cap + kSegPerStage * 2 + 3) & ~3);     // keeps the arrays carved after it 16-byte aligned
   ra->sc_cap = ((a.T > a.max_target ? a.T : a.max_target) + 8 + 3) & ~3;
+  if (tc) {      // a K = ffn phase must reduce all its K parts in one round
+    const int ngroups = (per_cta(d) + 7) / 8;
+    if (ngroups * (ffn / d) > kTcRound || ra->box_rows < 32) return false;
+  }
   const size_t fixed = 128 /*alignment slack*/ +
                        sizeof(float) * ((size_t)NR * kmax + (size_t)NR * d + (size_t)ra->part_cap * NR + ra->sc_cap + 64 +
-                                        kRingConsumerWarps * 64 + (size_t)num_sms * NR * 2);
+                                        kRingConsumerWarps * 64 + (size_t)num_sms * NR * 2 + 2 * (size_t)ra->part_cap +
+                                        (tc ? (size_t)kTcRound * kRingConsumerWarps * 8 * NR : 0));
   const size_t budget = 227 * 1024 - 2048;        // static __shared__ + slack
   if (fixed + 2 * (size_t)ra->stage_bytes > budget) return false;
   int ns = (int)((budget - fixed) / ra->stage_bytes);
@@ -859,10 +1004,14 @@ cudaError_t launch_decoder_ring(const RingArgs& ra_in, const CUtensorMap& cross_
   // the instrumented build (phase stamps, ablation switches) is a separate instantiation so the product path
   // carries none of its branches
   const bool dbg = ra_in.debug != 0 || ra_in.fine_timing != 0 || ra_in.m.timing != nullptr;
-  void* fns[6] = {(void*)decoder_ring_kernel<1, false>, (void*)decoder_ring_kernel<2, false>, (void*)decoder_ring_kernel<4, false>,
-                  (void*)decoder_ring_kernel<1, true>,  (void*)decoder_ring_kernel<2, true>,  (void*)decoder_ring_kernel<4, true>};
-  static bool done[6] = {false, false, false, false, false, false};
-  const int slot = (NR == 1 ? 0 : (NR == 2 ? 1 : 2)) + (dbg ? 3 : 0);
+  // three builds per row count: tensor-core dot products (product path), CUDA-core dot products (cross-check),
+  // CUDA-core + instrumentation
+  void* fns[9] = {(void*)decoder_ring_kernel<1, false, true>,  (void*)decoder_ring_kernel<2, false, true>,  (void*)decoder_ring_kernel<4, false, true>,
+                  (void*)decoder_ring_kernel<1, false, false>, (void*)decoder_ring_kernel<2, false, false>, (void*)decoder_ring_kernel<4, false, false>,
+                  (void*)decoder_ring_kernel<1, true, false>,  (void*)decoder_ring_kernel<2, true, false>,  (void*)decoder_ring_kernel<4, true, false>};
+  static bool done[9] = {false, false, false, false, false, false, false, false, false};
+  if (dbg && ra_in.tc && ra_in.debug != 32) return cudaErrorInvalidValue;   // the instrumented build exists for the CUDA-core path only
+  const int slot = (NR == 1 ? 0 : (NR == 2 ? 1 : 2)) + (ra_in.tc ? 0 : (dbg ? 6 : 3));
   void* fn = fns[slot];
   if (!done[slot]) {
     cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);

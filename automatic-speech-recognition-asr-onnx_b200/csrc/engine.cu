@@ -81,8 +81,9 @@ struct b200asr_engine {
   // sampling head (TOPK_TOPP_SAMPLING); temperature <= 0 = argmax heads
   float samp_temperature = 0.f; int samp_top_k = 10; float samp_top_p = 0.95f; float samp_rep = 1.0f;
   unsigned long long samp_seed = 0; float* samp_noise = nullptr; int samp_noise_rows = 0, samp_noise_ld = 0;
-  bool use_ring = true; bool ring_fine = false; int ring_debug = 0; unsigned long long* ring_ll = nullptr; size_t ring_ll_words = 0;
-  CUtensorMap cross_map{}; int cmap_B = -1, cmap_T = -1; int ring_task_inv = 0;
+  bool use_ring = true; bool ring_tc = false;   // mma.sync dot products: correct but measured slower than the CUDA-core path
+   bool ring_fine = false; int ring_debug = 0; unsigned long long* ring_ll = nullptr; size_t ring_ll_words = 0;
+  CUtensorMap cross_map{}; int cmap_B = -1, cmap_T = -1, cmap_rows = -1; int ring_task_inv = 0;
   std::string graph_key;
 
   int fail(int code, const std::string& m) { err = m; return code; }
@@ -472,7 +473,8 @@ bool ring_ok(b200asr_engine* e) {
   if (c.d_model / 8 > 256) return false;         // TMA box rows
   MegaArgs a{}; a.batch = e->B; a.d = c.d_model; a.ffn = c.ffn; a.vocab = c.vocab; a.T = e->T_enc; a.max_target = c.max_target;
   RingArgs ra{}; size_t smem = 0;
-  return ring_plan(a, e->num_sms, &ra, &smem);
+  const bool tc = e->ring_tc && !e->ring_fine && (!e->ring_debug || e->ring_debug == 32) && !e->mega_timing;
+  return ring_plan(a, e->num_sms, tc, &ra, &smem);
 }
 
 // n_iters single-token iterations starting from cur_token (the prefill has run)
@@ -483,7 +485,8 @@ int run_ring(b200asr_engine* e, int n_iters, bool want_logits) {
   fill_mega_args(e, ra.m, n_iters, e->cur_token, 1, false, want_logits);
   RET(arm_timing(e, ra.m));
   size_t smem = 0;
-  if (!ring_plan(ra.m, e->num_sms, &ra, &smem)) return e->fail(B200ASR_E_INVALID, "decoder_ring: shared-memory plan does not fit");
+  const bool tc = e->ring_tc && !e->ring_fine && (!e->ring_debug || e->ring_debug == 32) && !e->mega_timing;
+  if (!ring_plan(ra.m, e->num_sms, tc, &ra, &smem)) return e->fail(B200ASR_E_INVALID, "decoder_ring: shared-memory plan does not fit");
   const size_t words = ring_exchange_words(c.max_batch < 4 ? c.max_batch : 4, c.d_model, c.ffn, e->num_sms);
   if (!e->ring_ll) {
     CK(cudaMalloc(&e->ring_ll, words * 4 * sizeof(unsigned long long)));
@@ -492,12 +495,12 @@ int run_ring(b200asr_engine* e, int n_iters, bool want_logits) {
     for (int i = 1; i < e->num_sms; ++i) if ((i * kRingTaskMul) % e->num_sms == 1) inv = i;
     e->ring_task_inv = inv;
   }
-  if (e->cmap_B != e->B || e->cmap_T != e->T_enc) {
+  if (e->cmap_B != e->B || e->cmap_T != e->T_enc || e->cmap_rows != ra.box_rows) {
     std::string msg;
     const int64_t rows = (int64_t)2 * c.dec_layers * e->B * e->T_enc;
-    if (!make_tmap_2d_plain(&e->cross_map, e->cross_kv, c.d_model, rows, c.d_model, 64, ra.stage_bytes / 128, &msg))
+    if (!make_tmap_2d_plain(&e->cross_map, e->cross_kv, c.d_model, rows, c.d_model, 64, ra.box_rows, &msg))
       return e->fail(B200ASR_E_CUDA, "decoder_ring: " + msg);
-    e->cmap_B = e->B; e->cmap_T = e->T_enc;
+    e->cmap_B = e->B; e->cmap_T = e->T_enc; e->cmap_rows = ra.box_rows;
   }
   ra.ll = e->ring_ll; ra.ll_stride = (long long)e->ring_ll_words;
   ra.ld_vec = c.d_model * 3 > c.ffn ? c.d_model * 3 : c.ffn;
@@ -620,6 +623,7 @@ int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "mega")) { e->use_mega = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring")) { e->use_ring = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "ring_tc")) { e->ring_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_debug")) { e->ring_debug = (int)value; return B200ASR_OK; }
   if (!strcmp(key, "ring_fine_timing")) { e->ring_fine = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "pf_ahead_mb")) { e->pf_ahead = (long long)value << 20; return B200ASR_OK; }

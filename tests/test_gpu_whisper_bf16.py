@@ -46,6 +46,7 @@ def test_bf16_mega_vs_stepgraph_decoder():
     for mega in (1, 0):
         eng = make_engine(tensors, "bf16")
         eng.set_option("mega", mega)
+        eng.set_option("ring_tc", 0)          # fp32-activation dot products on both sides (the mma.sync path is held in test_gpu_ring.py)
         outs.append(_run(eng, g["pcm"], g["prompt"], g["forced_tokens"].tolist()))
         eng.set_decode_options(stop_ids=[], generate_limit=7)
         outs.append(eng.transcribe(g["pcm"], g["prompt"], max_new=7))
