@@ -419,33 +419,27 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
 #pragma unroll
       for (int r = 0; r < NR; ++r) { mean[r] = 0.f; rstd[r] = 1.f; }
       if (Lp.ln_mode != 0 && !(dbg & 2)) {
+        // one cross-warp exchange: per-warp fp32 sums of x and x^2 (<= 96 values each), combined in double so the
+        // E[x^2] - mean^2 form loses nothing that matters next to the two-pass form of the other decoder kernels
         float* red = opart;                        // [2][NR][16] cross-warp partials (opart is idle outside attention)
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
           float sv = (xv[r][0] + xv[r][1]) + (xv[r][2] + xv[r][3]);
+          float qv = fmaf(xv[r][0], xv[r][0], xv[r][1] * xv[r][1]) + fmaf(xv[r][2], xv[r][2], xv[r][3] * xv[r][3]);
           sv = warp_sum(sv);
-          if (lane == 0) red[r * kRingConsumerWarps + warp] = sv;
-        }
-        csync();
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          float m = 0.f;
-#pragma unroll
-          for (int w = 0; w < kRingConsumerWarps; ++w) m += red[r * kRingConsumerWarps + w];
-          mean[r] = m / (float)d;
-          float qv = 0.f;
-#pragma unroll
-          for (int u = 0; u < GV; ++u) { const int k = tid + u * kRingConsumers; if (k < d) { const float t0 = xv[r][u] - mean[r]; qv = fmaf(t0, t0, qv); } }
           qv = warp_sum(qv);
-          if (lane == 0) red[(NR + r) * kRingConsumerWarps + warp] = qv;
+          if (lane == 0) { red[r * kRingConsumerWarps + warp] = sv; red[(NR + r) * kRingConsumerWarps + warp] = qv; }
         }
         csync();
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          float v = 0.f;
+          double sm = 0.0, sq = 0.0;
 #pragma unroll
-          for (int w = 0; w < kRingConsumerWarps; ++w) v += red[(NR + r) * kRingConsumerWarps + w];
-          rstd[r] = rsqrtf(v / (float)d + a.eps);
+          for (int w = 0; w < kRingConsumerWarps; ++w) { sm += (double)red[r * kRingConsumerWarps + w]; sq += (double)red[(NR + r) * kRingConsumerWarps + w]; }
+          const double mu = sm / (double)d;
+          const double var = fmax(sq / (double)d - mu * mu, 0.0);
+          mean[r] = (float)mu;
+          rstd[r] = rsqrtf((float)var + a.eps);
         }
       }
       fstamp();
@@ -698,6 +692,21 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
       const unsigned long long* in = exbuf(seq - 1) + (size_t)b * ra.ld_vec;
       bf16* kc = reinterpret_cast<bf16*>(a.kcache) + ((((long long)l * B + b) * H + h) * a.max_target) * 64;
       bf16* vc = reinterpret_cast<bf16*>(a.vcache) + ((((long long)l * B + b) * H + h) * a.max_target) * 64;
+      // rows already in the cache do not depend on this phase's input: start copying them into the (idle) input-row
+      // buffer before polling for q / k / v, so the score and PV loops below run out of shared memory
+      const int cap_pos = (int)(((size_t)NR * kmax * sizeof(float)) / 256);
+      const int npre = min(kv_len, cap_pos);
+      bf16* sk = reinterpret_cast<bf16*>(xs);
+      bf16* sv = sk + (size_t)npre * 64;
+      for (int idx = tid; idx < npre * 16; idx += kRingConsumers) {
+        const int which = idx >= npre * 8 ? 1 : 0;
+        const int j = idx - which * npre * 8;
+        const bf16* src = (which ? vc : kc) + (long long)(j >> 3) * 64 + (j & 7) * 8;
+        bf16* dst = (which ? sv : sk) + (size_t)(j >> 3) * 64 + (j & 7) * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rs_u32(dst)), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      float* knv = cand;                           // [2][64] the new position's k and v, rounded through bf16 like the cache
       if (tid < 192) {
         const int which = tid >> 6, dd = tid & 63;
         const unsigned long long* p = in + which * d + h * 64 + dd;
@@ -705,24 +714,49 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
         unsigned pay = (unsigned)v;
         if ((unsigned)(v >> 32) != seq - 1 && !(dbg & 1)) pay = ll_spin(p, seq - 1);
         const float f = __uint_as_float(pay);
-        if (which == 0) qs[dd] = f;
-        else (which == 1 ? kc : vc)[(long long)kv_len * 64 + dd] = __float2bfloat16_rn(f);
+        if (which == 0) {
+          qs[dd] = f;
+        } else {
+          const bf16 hb = __float2bfloat16_rn(f);
+          (which == 1 ? kc : vc)[(long long)kv_len * 64 + dd] = hb;      // append for the later tokens
+          knv[(which - 1) * 64 + dd] = __bfloat162float(hb);
+        }
       }
-      csync();                                     // CTA-scope ordering makes the appended row visible to the loads below
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      csync();
       const int npos = kv_len + 1;
       float m = -INFINITY;
       for (int p = tid; p < npos; p += kRingConsumers) {
-        const bf16* kr = kc + (long long)p * 64;
         float s = 0.f;
+        if (p == kv_len) {
+#pragma unroll 8
+          for (int i = 0; i < 64; ++i) s = fmaf(knv[i], qs[i], s);
+        } else if (p < npre) {
+          const bf16* kr = sk + (size_t)p * 64;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint4 u = __ldcg(reinterpret_cast<const uint4*>(kr + j * 8));
-          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+          for (int j = 0; j < 8; ++j) {
+            const int jj = (j + p) & 7;              // 16-byte chunks rotated by position: conflict-free
+            const uint4 u = *reinterpret_cast<const uint4*>(kr + jj * 8);
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const float4 qa = *reinterpret_cast<const float4*>(qs + jj * 8);
+            const float4 qb = *reinterpret_cast<const float4*>(qs + jj * 8 + 4);
+            float2 f = __bfloat1622float2(hh[0]); s = fmaf(f.x, qa.x, s); s = fmaf(f.y, qa.y, s);
+            f = __bfloat1622float2(hh[1]); s = fmaf(f.x, qa.z, s); s = fmaf(f.y, qa.w, s);
+            f = __bfloat1622float2(hh[2]); s = fmaf(f.x, qb.x, s); s = fmaf(f.y, qb.y, s);
+            f = __bfloat1622float2(hh[3]); s = fmaf(f.x, qb.z, s); s = fmaf(f.y, qb.w, s);
+          }
+        } else {
+          const bf16* kr = kc + (long long)p * 64;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(hh[i]);
-            s = fmaf(f.x, qs[j * 8 + 2 * i], s);
-            s = fmaf(f.y, qs[j * 8 + 2 * i + 1], s);
+          for (int j = 0; j < 8; ++j) {
+            const uint4 u = __ldcg(reinterpret_cast<const uint4*>(kr + j * 8));
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(hh[i]);
+              s = fmaf(f.x, qs[j * 8 + 2 * i], s);
+              s = fmaf(f.y, qs[j * 8 + 2 * i + 1], s);
+            }
           }
         }
         sc[p] = s;
@@ -743,8 +777,15 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
       float o0 = 0.f, o1 = 0.f;
       for (int p = warp; p < npos; p += kRingConsumerWarps) {
         const float w = sc[p];
-        const unsigned u = __ldcg(reinterpret_cast<const unsigned*>(vc + (long long)p * 64 + 2 * lane));
-        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+        float2 v;
+        if (p == kv_len) {
+          v = make_float2(knv[64 + 2 * lane], knv[64 + 2 * lane + 1]);
+        } else if (p < npre) {
+          v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sv + (size_t)p * 64 + 2 * lane));
+        } else {
+          const unsigned u = __ldcg(reinterpret_cast<const unsigned*>(vc + (long long)p * 64 + 2 * lane));
+          v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+        }
         o0 = fmaf(w, v.x, o0); o1 = fmaf(w, v.y, o1);
       }
       float tot = 0.f;
