@@ -253,6 +253,8 @@ struct b200asr_nar {
   void *enc_pad = nullptr, *conv_out = nullptr, *kvbuf = nullptr, *dq = nullptr;
   float *alphas = nullptr, *acoustic = nullptr, *dec = nullptr, *dx = nullptr, *f32buf = nullptr, *sa_in = nullptr, *dec_logits = nullptr;
   int* n_tok = nullptr; int last_rows = 0;
+  // SenseVoice: the whole forward is one CUDA graph per (batch, n_samples) -- ~700 small launches are host-bound otherwise
+  bool use_graph = true; cudaGraphExec_t graph = nullptr; int graph_B = -1, graph_N = -1, graph_dtype = -1; int64_t graph_nodes = 0;
   int* h_pinned = nullptr;
   int max_frames = 0, max_T = 0;
 
@@ -512,7 +514,27 @@ int paraformer_forward(b200asr_nar* e) {
 }
 
 int nar_forward(b200asr_nar* e) {
-  return e->cfg.kind == B200ASR_NAR_PARAFORMER ? paraformer_forward(e) : sensevoice_forward(e);
+  if (e->cfg.kind == B200ASR_NAR_PARAFORMER) return paraformer_forward(e);      // data-dependent decoder size: host read inside
+  if (!e->use_graph) return sensevoice_forward(e);
+  if (!e->graph || e->graph_B != e->B || e->graph_N != e->n_samples || e->graph_dtype != e->pcm_dtype) {
+    if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+    cudaGraph_t g = nullptr;
+    const int64_t before = e->launches;
+    NCK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
+    const int r = sensevoice_forward(e);
+    const cudaError_t ce = cudaStreamEndCapture(e->st, &g);
+    e->graph_nodes = e->launches - before;
+    e->launches = before;
+    if (r != B200ASR_OK) { if (g) cudaGraphDestroy(g); return r; }
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "cudaStreamEndCapture");
+    const cudaError_t ci = cudaGraphInstantiate(&e->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ci != cudaSuccess) return e->cuda_fail(ci, "cudaGraphInstantiate");
+    e->graph_B = e->B; e->graph_N = e->n_samples; e->graph_dtype = e->pcm_dtype;
+  }
+  NCK(cudaGraphLaunch(e->graph, e->st));
+  e->launches += e->graph_nodes;
+  return B200ASR_OK;
 }
 
 }  // namespace
@@ -555,6 +577,7 @@ void b200asr_nar_destroy(b200asr_nar* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->st);
+  if (e->graph) cudaGraphExecDestroy(e->graph);
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
   void* bufs[] = {e->basis_t, e->stage_buf, e->pcm, e->mel, e->feats, e->hidden, e->resid, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->S,
                   e->logits, e->enc_out, e->frame_ids, e->tokens, e->lens, e->lang, e->enc_pad, e->conv_out, e->kvbuf, e->dq, e->alphas,
@@ -829,6 +852,11 @@ int b200asr_nar_get_stage(b200asr_nar* e, const char* name_c, float* out, int64_
 }
 
 int64_t b200asr_nar_kernel_launches(const b200asr_nar* e) { return e ? e->launches : 0; }
+int b200asr_nar_set_option(b200asr_nar* e, const char* key, int64_t value) {
+  if (!e || !key) return B200ASR_E_INVALID;
+  if (!strcmp(key, "graph")) { e->use_graph = value != 0; return B200ASR_OK; }
+  return e->fail(B200ASR_E_INVALID, std::string("unknown option ") + key);
+}
 void* b200asr_nar_stream(b200asr_nar* e) { return e ? (void*)e->st : nullptr; }
 
 }  // extern "C"

@@ -221,6 +221,9 @@ class SenseVoiceEngine:
     def kernel_launches(self) -> int:
         return int(self.lib.b200asr_nar_kernel_launches(self.h))
 
+    def set_option(self, key: str, value: int):
+        self._ck(self.lib.b200asr_nar_set_option(self.h, key.encode(), int(value)))
+
     @property
     def stream_ptr(self) -> int:
         return int(self.lib.b200asr_nar_stream(self.h) or 0)

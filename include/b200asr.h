@@ -183,6 +183,8 @@ int b200asr_nar_run_resident(b200asr_nar* e, int32_t* tokens_out, int32_t tokens
 /* "mel" [B][frames][n_mels], "feats" [B][T][feat], "enc_out" [B][T][d], "logits" [B][T][vocab], "frame_ids" [B][T] */
 int b200asr_nar_get_stage(b200asr_nar* e, const char* name, float* out, int64_t capacity, int64_t* numel_out);
 int64_t b200asr_nar_kernel_launches(const b200asr_nar* e);
+/* options: "graph" (0/1, default 1): replay the SenseVoice forward as one CUDA graph per (batch, n_samples) */
+int b200asr_nar_set_option(b200asr_nar* e, const char* key, int64_t value);
 void* b200asr_nar_stream(b200asr_nar* e);
 
 #ifdef __cplusplus
