@@ -426,7 +426,10 @@ def main():
                 "kernel": "decoder_ring_kernel<NR> (streaming greedy-decode kernel: TMA weight ring + flag-in-data "
                           "exchanges; one greedy step = all decoder weights streamed once)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (8 greedy steps in
+                # one launch, profiles/ncu_r01_summary.md) divided by its 8 steps: bytes per greedy step, like `achieved`
+                "traffic": (13.371254e9 + 11.967e6) / 8 if (B == 1 and args.preset == "whisper-large-v3" and args.precision == "bf16") else None,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
                 "ms_per_launch": ms_dec, "algorithmic_bytes_per_launch": bytes_step,
             },
             "encoder": {"ms": ms_enc, "tflops": enc_tf, "frac_of_bf16_peak": enc_tf / tf_peak},
