@@ -1,0 +1,95 @@
+"""Command line of the drop-in: the reference invocation
+
+    python Whisper/Inference_Whisper_ONNX.py --onnx-folder DIR [--tokenizer-path P]
+
+(/root/reference/Whisper/Inference_Whisper_ONNX.py:37-53) becomes
+
+    python -m b200asr.cli whisper --model-folder DIR [--tokenizer-path P] --audio clip.wav [more.wav ...]
+
+where DIR is the HF checkpoint folder the exporter starts from (`config.json`, `model.safetensors`,
+`generation_config.json`; Export_Whisper.py:14).  Behaviour constants keep the script's names (`--set REPEAT_PENALTY=1.0
+DETECT_LANGUAGE=0 ...`, defaults of :71-100).  Output = the script's block: `ASR Result:` / `RTF:` (:836-841).
+Without tokenizer files the token ids are printed instead of text.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from dataclasses import fields
+from pathlib import Path
+
+import numpy as np
+
+from . import ingest
+from .engine import WhisperEngine
+from .weights import fold_whisper
+from .whisper_infer import InferenceOptions, WhisperPipeline
+
+
+def whisper_metadata(dims, gen: dict, sample_rate: int = 16000) -> dict:
+    """The custom_metadata_map the exporter writes into ASR_Metadata.onnx (Export_Whisper.py:684-716, 1062-1074), from the
+    checkpoint's generation config."""
+    lang = gen.get("lang_to_id") or {}
+    langs = {tok[2:-2]: {"name": tok[2:-2], "aliases": [], "token_id": int(i), "prompt_token_ids": []} for tok, i in lang.items()}
+    no_ts = int(gen.get("no_timestamps_token_id", 0))
+    special = {"decoder_start": int(gen.get("decoder_start_token_id", 0)), "eos": int(gen.get("eos_token_id", 0)),
+               "stop": [int(gen.get("eos_token_id", 0))], "no_speech": int(gen.get("no_speech_token_id", no_ts - 1)),
+               "no_timestamps": no_ts, "tasks": {str(k): int(v) for k, v in (gen.get("task_to_id") or {}).items()}}
+    return {"audio_pcm_scale": "32768", "max_seq_len": str(dims.max_target), "sample_rate": str(sample_rate),
+            "special_token_ids": json.dumps(special), "supported_languages": json.dumps(langs)}
+
+
+def _options(pairs) -> InferenceOptions:
+    opt = InferenceOptions()
+    types = {f.name: f.type for f in fields(InferenceOptions)}
+    for p in pairs or []:
+        k, _, v = p.partition("=")
+        if k not in types:
+            raise SystemExit(f"unknown option {k}; choose from {sorted(types)}")
+        cur = getattr(opt, k)
+        setattr(opt, k, (v.lower() in ("1", "true", "yes")) if isinstance(cur, bool) else type(cur)(v))
+    return opt
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="b200asr")
+    sub = ap.add_subparsers(dest="model", required=True)
+    w = sub.add_parser("whisper")
+    w.add_argument("--model-folder", "--onnx-folder", dest="folder", required=True)
+    w.add_argument("--tokenizer-path", default=None)
+    w.add_argument("--audio", nargs="+", required=True)
+    w.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
+    w.add_argument("--device", type=int, default=0)
+    w.add_argument("--set", nargs="*", default=[], metavar="NAME=VALUE", help="script constants, e.g. REPEAT_PENALTY=1.0")
+    args = ap.parse_args(argv)
+
+    dims, state, gen = ingest.load_hf_whisper(args.folder)
+    tensors = fold_whisper(state, dims, gen.get("suppress_tokens") or [], gen.get("begin_suppress_tokens") or [])
+    del state
+    md = whisper_metadata(dims, gen)
+    tokenizer = None
+    tok_dir = Path(args.tokenizer_path) if args.tokenizer_path else Path(args.folder)
+    try:
+        from transformers import AutoTokenizer
+        tokenizer = AutoTokenizer.from_pretrained(str(tok_dir))
+    except Exception as exc:                                   # no tokenizer files: ids are still a complete result
+        print(f"(tokenizer not loaded from {tok_dir}: {exc.__class__.__name__}; printing token ids)", file=sys.stderr)
+    clips = [ingest.read_wav(p) for p in args.audio]
+    sr = int(md["sample_rate"])
+    pcm = [ingest.to_model_rate(x, r, sr) for x, r in clips]
+    eng = WhisperEngine(dims, tensors, precision=args.precision, max_batch=1, max_samples=max(480000, max(len(x) for x in pcm)),
+                        device=args.device)
+    pipe = WhisperPipeline(eng, md, _options(args.set))
+    for path, x in zip(args.audio, pcm):
+        print("-" * 106)
+        print(f"\nTest Input Audio: {path}")
+        res = pipe.transcribe_pcm(x, verbose=True)
+        text = tokenizer.decode(res.tokens, skip_special_tokens=True) if tokenizer is not None else " ".join(map(str, res.tokens))
+        print(pipe.report(res, text))
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

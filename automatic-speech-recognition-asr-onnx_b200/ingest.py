@@ -1,0 +1,146 @@
+"""Checkpoint and audio ingest for the drop-in scripts (the parts that need no ONNX Runtime).
+
+* `read_safetensors` / `write_safetensors`: the safetensors container (8-byte little-endian header length, JSON header
+  {name: {dtype, shape, data_offsets}}, raw little-endian tensor bytes) read with numpy only, so an HF Whisper folder
+  (`config.json` + `model.safetensors`) loads without transformers: `load_hf_whisper(folder)` -> (dims, state dict),
+  which `weights.fold_whisper` turns into engine tensors -- the same folds the exporter bakes into the ONNX initialisers
+  (/root/reference/Whisper/Export_Whisper.py:376-420, 527-550), applied to the checkpoint the exporter starts from
+  (:14, `whisper-large-v3-turbo` by default).
+* `read_wav` + `to_model_rate`: what the driver gets from pydub at
+  /root/reference/Whisper/Inference_Whisper_ONNX.py:731-732 (`AudioSegment.from_file(...).set_channels(1)
+  .set_frame_rate(SAMPLE_RATE).set_sample_width(2)`) for PCM WAV input: mono mix-down, polyphase resampling to the model
+  rate, int16.  Compressed formats need a decoder the image does not have and are out of scope.
+"""
+from __future__ import annotations
+
+import json
+import struct
+import wave
+from math import gcd
+from pathlib import Path
+from typing import Dict, Tuple
+
+import numpy as np
+
+from .config import WhisperDims
+
+_ST_DTYPES = {"F32": np.float32, "F16": np.float16, "F64": np.float64, "I64": np.int64, "I32": np.int32, "I16": np.int16,
+              "I8": np.int8, "U8": np.uint8, "BOOL": np.bool_}
+
+
+def _bf16_to_f32(raw: np.ndarray) -> np.ndarray:
+    return (raw.astype(np.uint32) << 16).view(np.float32)
+
+
+def read_safetensors(path) -> Dict[str, np.ndarray]:
+    """name -> array (bf16 tensors come back as float32)."""
+    data = Path(path).read_bytes()
+    if len(data) < 8:
+        raise ValueError(f"{path}: not a safetensors file")
+    (n,) = struct.unpack("<Q", data[:8])
+    if n <= 0 or 8 + n > len(data):
+        raise ValueError(f"{path}: bad safetensors header length {n}")
+    header = json.loads(data[8:8 + n].decode("utf-8"))
+    base = 8 + n
+    out: Dict[str, np.ndarray] = {}
+    for name, info in header.items():
+        if name == "__metadata__":
+            continue
+        lo, hi = info["data_offsets"]
+        shape = tuple(info["shape"])
+        buf = memoryview(data)[base + lo:base + hi]
+        if info["dtype"] == "BF16":
+            arr = _bf16_to_f32(np.frombuffer(buf, dtype="<u2"))
+        elif info["dtype"] in _ST_DTYPES:
+            arr = np.frombuffer(buf, dtype=np.dtype(_ST_DTYPES[info["dtype"]]).newbyteorder("<"))
+        else:
+            raise ValueError(f"{path}: tensor {name!r} has unsupported dtype {info['dtype']}")
+        if arr.size != int(np.prod(shape, dtype=np.int64)):
+            raise ValueError(f"{path}: tensor {name!r} has {arr.size} elements, header says {shape}")
+        out[name] = arr.reshape(shape)
+    return out
+
+
+def write_safetensors(path, tensors: Dict[str, np.ndarray], metadata: Dict[str, str] | None = None) -> None:
+    """Writer for the same container (fixtures, converted checkpoints)."""
+    rev = {np.dtype(v): k for k, v in _ST_DTYPES.items()}
+    header, blobs, off = {}, [], 0
+    for name, arr in tensors.items():
+        a = np.ascontiguousarray(arr)
+        b = a.astype(a.dtype.newbyteorder("<"), copy=False).tobytes()
+        header[name] = {"dtype": rev[np.dtype(a.dtype)], "shape": list(a.shape), "data_offsets": [off, off + len(b)]}
+        blobs.append(b)
+        off += len(b)
+    if metadata:
+        header["__metadata__"] = dict(metadata)
+    h = json.dumps(header, separators=(",", ":")).encode("utf-8")
+    h += b" " * ((8 - len(h) % 8) % 8)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", len(h)))
+        f.write(h)
+        for b in blobs:
+            f.write(b)
+
+
+def dims_from_hf_config(cfg: dict) -> WhisperDims:
+    """HF `config.json` of a Whisper checkpoint -> engine dimensions."""
+    if cfg.get("encoder_attention_heads") != cfg.get("decoder_attention_heads") or cfg.get("encoder_ffn_dim") != cfg.get("decoder_ffn_dim"):
+        raise ValueError("encoder and decoder must share heads and ffn width")
+    return WhisperDims(n_mels=int(cfg["num_mel_bins"]), d_model=int(cfg["d_model"]), n_heads=int(cfg["encoder_attention_heads"]),
+                       ffn=int(cfg["encoder_ffn_dim"]), enc_layers=int(cfg["encoder_layers"]), dec_layers=int(cfg["decoder_layers"]),
+                       vocab=int(cfg["vocab_size"]), max_source=int(cfg["max_source_positions"]),
+                       max_target=int(cfg["max_target_positions"]))
+
+
+def load_hf_whisper(folder) -> Tuple[WhisperDims, Dict[str, np.ndarray], dict]:
+    """(dims, HF-named state dict, generation config) from a `WhisperForConditionalGeneration` checkpoint folder; sharded
+    checkpoints (`model.safetensors.index.json`) are followed."""
+    folder = Path(folder)
+    cfg = json.loads((folder / "config.json").read_text())
+    dims = dims_from_hf_config(cfg)
+    index = folder / "model.safetensors.index.json"
+    files = sorted(set(json.loads(index.read_text())["weight_map"].values())) if index.exists() else ["model.safetensors"]
+    state: Dict[str, np.ndarray] = {}
+    for fn in files:
+        state.update(read_safetensors(folder / fn))
+    if "proj_out.weight" not in state and "model.decoder.embed_tokens.weight" in state:
+        state["proj_out.weight"] = state["model.decoder.embed_tokens.weight"]          # tied head stored once
+    gen = {}
+    if (folder / "generation_config.json").exists():
+        gen = json.loads((folder / "generation_config.json").read_text())
+    return dims, state, gen
+
+
+# ---------------------------------------------------------------------------------------------
+def read_wav(path) -> Tuple[np.ndarray, int]:
+    """PCM WAV (8/16/24/32-bit integer) -> (mono int16 samples, sample rate).  Channels are averaged like pydub's
+    `set_channels(1)`, wider samples are shifted down to 16 bits like `set_sample_width(2)`."""
+    with wave.open(str(path), "rb") as w:
+        nch, width, rate, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+        if w.getcomptype() != "NONE":
+            raise ValueError(f"{path}: compressed WAV ({w.getcomptype()}) is not supported")
+        raw = w.readframes(n)
+    if width == 1:
+        x = (np.frombuffer(raw, dtype=np.uint8).astype(np.int32) - 128) << 8
+    elif width == 2:
+        x = np.frombuffer(raw, dtype="<i2").astype(np.int32)
+    elif width == 3:
+        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        x = ((b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)) << 8 >> 8) >> 8
+    elif width == 4:
+        x = np.frombuffer(raw, dtype="<i4").astype(np.int64) >> 16
+    else:
+        raise ValueError(f"{path}: unsupported sample width {width}")
+    x = x.reshape(-1, nch)
+    mono = x[:, 0] if nch == 1 else x.sum(axis=1) // nch
+    return np.clip(mono, -32768, 32767).astype(np.int16), int(rate)
+
+
+def to_model_rate(pcm: np.ndarray, rate: int, target: int = 16000) -> np.ndarray:
+    """Polyphase resampling to the model's sample rate (metadata `sample_rate`), int16 in / int16 out."""
+    if rate == target:
+        return np.ascontiguousarray(pcm, dtype=np.int16)
+    from scipy.signal import resample_poly
+    g = gcd(int(rate), int(target))
+    y = resample_poly(pcm.astype(np.float64), target // g, rate // g)
+    return np.clip(np.rint(y), -32768, 32767).astype(np.int16)
