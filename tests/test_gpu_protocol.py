@@ -174,3 +174,40 @@ def test_session_shim_runs_reference_shaped_loop():
     with pytest.raises(ValueError, match="unbound inputs"):
         DECODE.run_with_iobinding(DECODE.io_binding())
     eng.close()
+
+
+def test_cli_end_to_end_from_hf_folder_and_wav(tmp_path, capsys):
+    """`python -m b200asr.cli whisper --model-folder F --audio clip.wav` on a synthetic HF checkpoint folder + WAV file:
+    checkpoint ingest -> folds -> engine -> default protocol -> the script's report block."""
+    import wave
+    from b200asr import cli, ingest
+    from b200asr.config import WHISPER_TINY_TEST as dims
+    from b200asr.synth import synth_whisper_checkpoint
+    g, raw_o, tensors = load_case(GOLD[0])
+    raw = synth_whisper_checkpoint(dims, int(g["seed"]))
+    cfg = {"num_mel_bins": dims.n_mels, "d_model": dims.d_model, "encoder_attention_heads": dims.n_heads,
+           "decoder_attention_heads": dims.n_heads, "encoder_ffn_dim": dims.ffn, "decoder_ffn_dim": dims.ffn,
+           "encoder_layers": dims.enc_layers, "decoder_layers": dims.dec_layers, "vocab_size": dims.vocab,
+           "max_source_positions": dims.max_source, "max_target_positions": dims.max_target}
+    p = g["prompt"].tolist()
+    gen = {"suppress_tokens": g["suppress"].tolist(), "begin_suppress_tokens": g["begin_suppress"].tolist(),
+           "lang_to_id": {f"<|l{int(t)}|>": int(t) for t in g["lang_ids"]} | {"<|en|>": p[1]},
+           "task_to_id": {"transcribe": p[2]}, "no_timestamps_token_id": p[3], "decoder_start_token_id": p[0], "eos_token_id": 2,
+           "no_speech_token_id": NO_SPEECH}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    (tmp_path / "generation_config.json").write_text(json.dumps(gen))
+    ingest.write_safetensors(tmp_path / "model.safetensors", {k: v.numpy() for k, v in raw.items()})
+    with wave.open(str(tmp_path / "clip.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(g["pcm"].astype("<i2").tobytes())
+    rc = cli.main(["whisper", "--model-folder", str(tmp_path), "--audio", str(tmp_path / "clip.wav"), "--precision", "f32",
+                   "--set", "REPEAT_PENALTY=1.0", "NO_SPEECH_THRESHOLD=2.0"])
+    out = capsys.readouterr().out
+    assert rc == 0 and "ASR Result:" in out and "RTF:" in out and "Detected Language:" in out
+    ids = [int(t) for t in out.split("ASR Result:\n")[1].split("\n")[0].split()]
+    # greedy, language detected from the probe: the oracle with the same prompt gives the same ids (EOS = 2 stops both)
+    det = int(g["detected_language"])
+    with torch.no_grad():
+        ref = wo.greedy_transcribe(g["pcm"], _oracle_weights(g), wo.TINY_TEST, [p[0], det, p[2], p[3]], stop_tokens=[2], max_new=40,
+                                   return_logits=False)
+    assert ids[:40] == ref["tokens"][:40]
