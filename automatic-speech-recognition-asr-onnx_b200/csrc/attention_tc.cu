@@ -9,7 +9,8 @@
 //   TMA   : Q tile [128][64], K [T][64], V [T][64] straight out of the fused-QKV activation buffer [M][3d]
 //           (one tensor map, SWIZZLE_128B), landing in shared memory in UMMA's canonical layouts
 //   MMA 1 : S[128][T] = Q K^T   (A = Q K-major, B = K K-major), fp32 in TMEM columns [0, T)
-//   warps : one thread per query row (= one TMEM lane): row max, exp, row sum in registers -- no shuffles --
+//   warps : two threads per query row (= one TMEM lane, 32-key chunks of alternating parity): row max, exp2, row sum in
+//           registers, combined through shared memory once each --
 //           P written as bf16 into shared memory in the K-major SWIZZLE_128B layout, 64 keys at a time,
 //           double-buffered against
 //   MMA 2 : O[128][64] += P V   (A = P K-major, B = V MN-major: V stays [key][dh] exactly as the QKV GEMM
@@ -23,7 +24,8 @@
 
 namespace b200asr {
 
-constexpr int kAttThreads = 160;          // warps 0-3: softmax / epilogue (TMEM lane quarters), warp 4: TMA + MMA
+constexpr int kAttSoftmaxWarps = 8;       // two warps per TMEM lane quarter: each takes every other 32-key chunk of its rows
+constexpr int kAttThreads = (kAttSoftmaxWarps + 1) * 32;   // + warp 8: TMA + MMA
 constexpr int kAttBM = 128;
 constexpr int kAttMaxT = 448;
 constexpr int kAttOCol = 448;             // TMEM column of the O accumulator
@@ -141,11 +143,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
 
   if (threadIdx.x == 0) {
     ab_init(&bar_qk, 1); ab_init(&bar_v, 1); ab_init(&bar_s, 1); ab_init(&bar_o, 1);
-    for (int i = 0; i < 2; ++i) { ab_init(&bar_pfull[i], 128); ab_init(&bar_pempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ab_init(&bar_pfull[i], kAttSoftmaxWarps * 32); ab_init(&bar_pempty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
   }
-  if (warp == 4) {
+  if (warp == kAttSoftmaxWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(as_u32(&tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -154,7 +156,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
   a_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kAttSoftmaxWarps) {
     if (lane == 0) {
       // ---- TMA: Q + K on one barrier (needed first), V on its own ----
       ab_expect_tx(&bar_qk, (uint32_t)((1 + nkb) * kAttTile));
@@ -195,26 +197,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
     }
     __syncwarp();
   } else {
-    // ---- softmax: thread = query row = TMEM lane ----
-    const int r = threadIdx.x;                        // 0..127
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // ---- softmax: a query row = a TMEM lane, shared by two threads (warps w and w + 4 may both read lane quarter
+    //      w % 4): thread `half` takes the 32-key chunks with that parity, i.e. its half of every 64-key P block ----
+    __shared__ float s_mx[2][kAttBM], s_sum[2][kAttBM];
+    const int q4 = warp & 3, half = warp >> 2;
+    const int r = q4 * 32 + lane;                     // 0..127
+    const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
     ab_wait(&bar_s, 0);
     a_fence_after();
     float m = -INFINITY;
-    for (int c0 = 0; c0 < T; c0 += 32) {
+    for (int c0 = half * 32; c0 < T; c0 += 64) {
       uint32_t v[32];
       a_tmem_ld32(lane_base + (uint32_t)c0, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i) if (c0 + i < T) m = fmaxf(m, __uint_as_float(v[i]));
     }
+    s_mx[half][r] = m;
+    asm volatile("bar.sync 1, %0;" ::"n"(kAttSoftmaxWarps * 32) : "memory");
+    m = fmaxf(s_mx[0][r], s_mx[1][r]);
     const float ml2 = m * 1.4426950408889634f;
     float sum = 0.f;
     for (int j = 0; j < nblk; ++j) {
       const int buf = j & 1;
       if (j >= 2) ab_wait(&bar_pempty[buf], (uint32_t)(((j >> 1) - 1) & 1));
       uint8_t* prow = sP + (size_t)buf * kAttTile + (size_t)r * 128;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      {
         const int c0 = j * 64 + half * 32;
         uint32_t packed[16];
         if (c0 < Tp) {
@@ -244,18 +251,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA (async proxy)
       ab_arrive(&bar_pfull[buf]);
     }
-    // ---- O / rowsum -> context ----
+    s_sum[half][r] = sum;
+    asm volatile("bar.sync 1, %0;" ::"n"(kAttSoftmaxWarps * 32) : "memory");
+    // ---- O / rowsum -> context: each of the row's two threads stores 32 of the 64 output dims ----
     ab_wait(&bar_o, 0);
     a_fence_after();
-    const float inv = 1.0f / sum;
+    const float inv = 1.0f / (s_sum[0][r] + s_sum[1][r]);
     const int t = m0 + r;
-    uint32_t o[64];
-    a_tmem_ld32(lane_base + kAttOCol, o);
-    a_tmem_ld32(lane_base + kAttOCol + 32, o + 32);
+    uint32_t o[32];
+    a_tmem_ld32(lane_base + kAttOCol + half * 32, o);
     if (t < T) {
-      bf16* dst = a.ctx + (int64_t)(row0 + t) * a.ld_ctx + h * 64;
+      bf16* dst = a.ctx + (int64_t)(row0 + t) * a.ld_ctx + h * 64 + half * 32;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -268,7 +276,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
   }
   a_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kAttSoftmaxWarps) {
     a_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
