@@ -20,6 +20,7 @@
 // Single pass (the whole score row lives in TMEM), so T <= 448 keys (8.96 s of audio); longer clips keep the
 // unfused path.
 #include "common.cuh"
+#include "ptx.cuh"
 #include <cstdio>
 
 namespace b200asr {
@@ -31,90 +32,7 @@ constexpr int kAttMaxT = 448;
 constexpr int kAttOCol = 448;             // TMEM column of the O accumulator
 constexpr int kAttTile = 128 * 64 * 2;    // one [128][64] bf16 tile = 16 KB
 
-namespace {
-
-__device__ __forceinline__ uint32_t as_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ab_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(as_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void ab_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(as_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ab_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(as_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool ab_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(as_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void ab_wait(uint64_t* bar, uint32_t parity) {
-  if (ab_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!ab_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("b200asr attention_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void a_tma_3d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(as_u32(dst)), "l"(tm), "r"(as_u32(bar)), "r"(c0), "r"(c1), "r"(0) : "memory");
-}
-__device__ __forceinline__ void a_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void a_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void a_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(as_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void a_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void a_tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void a_tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// shared-memory matrix descriptors (sm_100 "version 1"), SWIZZLE_128B, 8-row groups 1024 B apart.
-// K-major (Q, K, P tiles: rows = M/N index, 64 contiguous K elements per 128-byte row): LBO unused.
-// MN-major (V tile: rows = K index (keys), 64 contiguous N elements (dh) per 128-byte row): SBO = pitch of the
-// 8-key groups, LBO = pitch of 64-wide N blocks (a single block here).
-__device__ __forceinline__ uint64_t a_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// D = f32, A = B = bf16, M = 128, N = n; b_mn = 1 selects the MN-major B operand
-__device__ __forceinline__ uint32_t a_idesc(int n, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kAttBM >> 4) << 24);
-}
-
-}  // namespace
+using namespace ptx;
 
 struct AttArgs {
   bf16* ctx; int64_t ld_ctx;      // [M][d] context rows
@@ -126,7 +44,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
   extern __shared__ __align__(1024) uint8_t att_smem[];
   const int T = a.T;
   const int nkb = (T + 127) / 128;                    // 128-key boxes of K and of V
-  const uint32_t base_addr = as_u32(att_smem);
+  const uint32_t base_addr = smem_u32(att_smem);
   uint8_t* sQ = att_smem + ((1024u - (base_addr & 1023u)) & 1023u);      // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* sK = sQ + kAttTile;
   uint8_t* sV = sK + (size_t)nkb * kAttTile;
@@ -142,58 +60,57 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
   const int nblk = (Tp + 63) / 64;                    // 64-key P blocks
 
   if (threadIdx.x == 0) {
-    ab_init(&bar_qk, 1); ab_init(&bar_v, 1); ab_init(&bar_s, 1); ab_init(&bar_o, 1);
-    for (int i = 0; i < 2; ++i) { ab_init(&bar_pfull[i], kAttSoftmaxWarps * 32); ab_init(&bar_pempty[i], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+    mbar_init(&bar_qk, 1); mbar_init(&bar_v, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_pfull[i], kAttSoftmaxWarps * 32); mbar_init(&bar_pempty[i], 1); }
+    mbar_fence_init();
+    prefetch_tensormap(&tmQKV);
   }
   if (warp == kAttSoftmaxWarps) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(as_u32(&tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(&tmem_slot, 512u);
   }
-  a_fence_before();
+  tc_fence_before();
   __syncthreads();
-  a_fence_after();
+  tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
   if (warp == kAttSoftmaxWarps) {
     if (lane == 0) {
       // ---- TMA: Q + K on one barrier (needed first), V on its own ----
-      ab_expect_tx(&bar_qk, (uint32_t)((1 + nkb) * kAttTile));
-      a_tma_3d(sQ, &tmQKV, h * 64, row0 + m0, &bar_qk);
-      for (int j = 0; j < nkb; ++j) a_tma_3d(sK + (size_t)j * kAttTile, &tmQKV, a.d + h * 64, row0 + j * 128, &bar_qk);
-      ab_expect_tx(&bar_v, (uint32_t)(nkb * kAttTile));
-      for (int j = 0; j < nkb; ++j) a_tma_3d(sV + (size_t)j * kAttTile, &tmQKV, 2 * a.d + h * 64, row0 + j * 128, &bar_v);
+      mbar_expect_tx(&bar_qk, (uint32_t)((1 + nkb) * kAttTile));
+      tma_load_3d(sQ, &tmQKV, h * 64, row0 + m0, 0, &bar_qk);
+      for (int j = 0; j < nkb; ++j) tma_load_3d(sK + (size_t)j * kAttTile, &tmQKV, a.d + h * 64, row0 + j * 128, 0, &bar_qk);
+      mbar_expect_tx(&bar_v, (uint32_t)(nkb * kAttTile));
+      for (int j = 0; j < nkb; ++j) tma_load_3d(sV + (size_t)j * kAttTile, &tmQKV, 2 * a.d + h * 64, row0 + j * 128, 0, &bar_v);
       // ---- S = Q K^T, 128 keys per instruction group ----
-      ab_wait(&bar_qk, 0);
-      a_fence_after();
-      const uint64_t qdesc = a_desc_sw128(as_u32(sQ));
+      mbar_wait(&bar_qk, 0, "attention_tc");
+      tc_fence_after();
+      const uint64_t qdesc = smem_desc_sw128(smem_u32(sQ));
       for (int n0 = 0; n0 < Tp; n0 += 128) {
         const int n = min(128, Tp - n0);
-        const uint32_t idesc = a_idesc(n, 0);
-        const uint64_t kdesc = a_desc_sw128(as_u32(sK) + (uint32_t)n0 * 128u);
+        const uint32_t idesc = idesc_bf16(kAttBM, n, 0);
+        const uint64_t kdesc = smem_desc_sw128(smem_u32(sK) + (uint32_t)n0 * 128u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a_mma(tmem + (uint32_t)n0, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc, k != 0);
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem + (uint32_t)n0, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc, k != 0);
       }
-      a_commit(&bar_s);
+      tc_commit(&bar_s);
       // ---- O += P V, one 64-key block at a time ----
-      ab_wait(&bar_v, 0);
-      const uint32_t idesc_pv = a_idesc(64, 1);
+      mbar_wait(&bar_v, 0, "attention_tc");
+      const uint32_t idesc_pv = idesc_bf16(kAttBM, 64, 1);
       for (int j = 0; j < nblk; ++j) {
         const int buf = j & 1;
-        ab_wait(&bar_pfull[buf], (uint32_t)((j >> 1) & 1));
-        a_fence_after();
+        mbar_wait(&bar_pfull[buf], (uint32_t)((j >> 1) & 1), "attention_tc");
+        tc_fence_after();
         const int ksteps = min(4, (Tp - j * 64) / 16);
-        const uint64_t pdesc = a_desc_sw128(as_u32(sP) + (uint32_t)buf * kAttTile);
+        const uint64_t pdesc = smem_desc_sw128(smem_u32(sP) + (uint32_t)buf * kAttTile);
 #pragma unroll 1
         for (int k = 0; k < ksteps; ++k) {
           // V rows (keys) j*64 + k*16 ..+15: two 8-key groups, 2048 bytes per step
-          const uint64_t vdesc = a_desc_sw128(as_u32(sV) + (uint32_t)(j * 64 + k * 16) * 128u);
-          a_mma(tmem + kAttOCol, pdesc + (uint64_t)(2 * k), vdesc, idesc_pv, (j | k) != 0);
+          const uint64_t vdesc = smem_desc_sw128(smem_u32(sV) + (uint32_t)(j * 64 + k * 16) * 128u);
+          tc_mma_bf16(tmem + kAttOCol, pdesc + (uint64_t)(2 * k), vdesc, idesc_pv, (j | k) != 0);
         }
-        a_commit(&bar_pempty[buf]);                   // P buffer reusable once these MMAs have read it
+        tc_commit(&bar_pempty[buf]);                   // P buffer reusable once these MMAs have read it
       }
-      a_commit(&bar_o);
+      tc_commit(&bar_o);
     }
     __syncwarp();
   } else {
@@ -203,12 +120,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
     const int q4 = warp & 3, half = warp >> 2;
     const int r = q4 * 32 + lane;                     // 0..127
     const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
-    ab_wait(&bar_s, 0);
-    a_fence_after();
+    mbar_wait(&bar_s, 0, "attention_tc");
+    tc_fence_after();
     float m = -INFINITY;
     for (int c0 = half * 32; c0 < T; c0 += 64) {
       uint32_t v[32];
-      a_tmem_ld32(lane_base + (uint32_t)c0, v);
+      tmem_ld32(lane_base + (uint32_t)c0, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i) if (c0 + i < T) m = fmaxf(m, __uint_as_float(v[i]));
     }
@@ -219,14 +136,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
     float sum = 0.f;
     for (int j = 0; j < nblk; ++j) {
       const int buf = j & 1;
-      if (j >= 2) ab_wait(&bar_pempty[buf], (uint32_t)(((j >> 1) - 1) & 1));
+      if (j >= 2) mbar_wait(&bar_pempty[buf], (uint32_t)(((j >> 1) - 1) & 1), "attention_tc");
       uint8_t* prow = sP + (size_t)buf * kAttTile + (size_t)r * 128;
       {
         const int c0 = j * 64 + half * 32;
         uint32_t packed[16];
         if (c0 < Tp) {
           uint32_t v[32];
-          a_tmem_ld32(lane_base + (uint32_t)c0, v);
+          tmem_ld32(lane_base + (uint32_t)c0, v);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float e0 = 0.f, e1 = 0.f;
@@ -247,19 +164,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
           *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
         }
       }
-      a_fence_before();
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA (async proxy)
-      ab_arrive(&bar_pfull[buf]);
+      tc_fence_before();
+      fence_proxy_async_smem();                     // generic-proxy writes -> visible to the MMA (async proxy)
+      mbar_arrive(&bar_pfull[buf]);
     }
     s_sum[half][r] = sum;
     asm volatile("bar.sync 1, %0;" ::"n"(kAttSoftmaxWarps * 32) : "memory");
     // ---- O / rowsum -> context: each of the row's two threads stores 32 of the 64 output dims ----
-    ab_wait(&bar_o, 0);
-    a_fence_after();
+    mbar_wait(&bar_o, 0, "attention_tc");
+    tc_fence_after();
     const float inv = 1.0f / (s_sum[0][r] + s_sum[1][r]);
     const int t = m0 + r;
     uint32_t o[32];
-    a_tmem_ld32(lane_base + kAttOCol + half * 32, o);
+    tmem_ld32(lane_base + kAttOCol + half * 32, o);
     if (t < T) {
       bf16* dst = a.ctx + (int64_t)(row0 + t) * a.ld_ctx + h * 64 + half * 32;
 #pragma unroll
@@ -274,11 +191,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
       }
     }
   }
-  a_fence_before();
+  tc_fence_before();
   __syncthreads();
   if (warp == kAttSoftmaxWarps) {
-    a_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    tc_fence_after();
+    tmem_dealloc(tmem, 512u);
   }
 }
 

@@ -23,6 +23,7 @@
 // bf16 weights / KV, fp32 activations and accumulation; batch <= 4 utterances, one new
 // token per utterance per iteration (the multi-token prefill stays in decoder_mega.cu).
 #include "common.cuh"
+#include "ptx.cuh"
 #include <algorithm>
 #include <cstdio>
 
@@ -41,46 +42,8 @@ constexpr long long kSpinLimit = 6000000000LL;              // ~3 s at 2 GHz: a 
 // ---------------------------------------------------------------------------
 namespace {
 
-__device__ __forceinline__ uint32_t rs_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace ptx;
 
-__device__ __forceinline__ void rbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void rbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rs_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void rbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rs_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool rbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(rs_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void rbar_wait(uint64_t* bar, uint32_t parity) {
-  if (rbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!rbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > kSpinLimit) {
-      printf("b200asr decoder_ring: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-// contiguous global -> shared bulk copy, completion counted on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(rs_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(rs_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_g2s_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(rs_u32(smem_dst)), "l"(tm), "r"(rs_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
 // named barrier over the 512 consumer threads (the producer warp never joins it)
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(kRingConsumers) : "memory"); }
 
@@ -222,9 +185,9 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
   const int dbg = DBG ? ra.debug : 0;              // timing experiments only (results are garbage when set)
 
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { rbar_init(&full_bar[s], 1); rbar_init(&empty_bar[s], kRingConsumerWarps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&cross_map) : "memory");
+    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kRingConsumerWarps); }
+    mbar_fence_init();
+    prefetch_tensormap(&cross_map);
     s_stop = 0;
   }
   if (tid < B) {
@@ -248,9 +211,9 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
         int ok = 1;
         if (lane == 0) {
           if (s_stop) ok = 0;
-          else if (!rbar_try_wait(&empty_bar[p.stage], p.phase ^ 1)) {
+          else if (!mbar_try_wait(&empty_bar[p.stage], p.phase ^ 1)) {
             const long long t0 = clock64();
-            while (!rbar_try_wait(&empty_bar[p.stage], p.phase ^ 1)) {
+            while (!mbar_try_wait(&empty_bar[p.stage], p.phase ^ 1)) {
               if (s_stop) { ok = 0; break; }
               if (clock64() - t0 > kSpinLimit) { printf("b200asr decoder_ring: producer stalled (block %d)\n", blockIdx.x); __trap(); }
             }
@@ -268,7 +231,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
             for (int grp = 0; grp < ngroups && !stop; ++grp) {
               if (!acquire()) { stop = true; break; }
               const int nrows = min(8, cnt - grp * 8);
-              if (lane == 0) rbar_expect_tx(&full_bar[p.stage], (uint32_t)(nrows * 2 * d));
+              if (lane == 0) mbar_expect_tx(&full_bar[p.stage], (uint32_t)(nrows * 2 * d));
               if (ra.debug & 32) {                  // timing experiment: one copy per chunk (rows land unskewed: garbage results)
                 if (lane == 0) bulk_g2s(ring + (size_t)p.stage * SB, W + ((long long)(n0 + grp * 8) * K + (long long)part * d),
                                         (uint32_t)(nrows * 2 * d), &full_bar[p.stage]);
@@ -286,7 +249,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
           if (!acquire()) { stop = true; break; }
           const uint32_t n = (uint32_t)min((long long)SB, bytes - off);
           if (lane == 0) {
-            rbar_expect_tx(&full_bar[p.stage], n);
+            mbar_expect_tx(&full_bar[p.stage], n);
             bulk_g2s(ring + (size_t)p.stage * SB, src + off, n, &full_bar[p.stage]);
           }
           ++issued; pipe_advance(p, NS);
@@ -309,8 +272,8 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
               const int row0 = ((kind * L + l) * B + b) * T + (i - kind * nbox) * R;
               if (!acquire()) { stop = true; break; }
               if (lane == 0) {
-                rbar_expect_tx(&full_bar[p.stage], (uint32_t)(R * 128));
-                tma_g2s_2d(ring + (size_t)p.stage * SB, &cross_map, h * 64, row0, &full_bar[p.stage]);
+                mbar_expect_tx(&full_bar[p.stage], (uint32_t)(R * 128));
+                tma_load_2d(ring + (size_t)p.stage * SB, &cross_map, h * 64, row0, &full_bar[p.stage]);
               }
               ++issued; pipe_advance(p, NS);
             }
@@ -326,7 +289,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
       for (int s = 0; s < NS && lane == 0; ++s) {
         if (issued > s) {
           const uint32_t par = (s < p.stage) ? p.phase : (p.phase ^ 1);
-          rbar_wait(&full_bar[s], par);
+          mbar_wait(&full_bar[s], par, "decoder_ring", kSpinLimit);
         }
       }
     }
@@ -489,11 +452,11 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
               bfr[sidx][1] = *reinterpret_cast<const uint32_t*>(&h2);
             }
           }
-          rbar_wait(&full_bar[pipe.stage], pipe.phase);
+          mbar_wait(&full_bar[pipe.stage], pipe.phase, "decoder_ring", kSpinLimit);
           // independent accumulators: the k16 steps of a warp are not chained through one C fragment (the phase is
           // latency-bound, a dependent mma.sync chain would cost ~35 cycles per step)
           float cacc[XS][4];
-          const uint32_t abase = rs_u32(ring + (size_t)pipe.stage * SB) + (uint32_t)((lane & 7) * P) +
+          const uint32_t abase = smem_u32(ring + (size_t)pipe.stage * SB) + (uint32_t)((lane & 7) * P) +
                                  (uint32_t)((warp * ksl + ((lane >> 3) & 1) * 8) * 2);
           uint32_t afr[XS][2];
 #pragma unroll
@@ -512,7 +475,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
           if (q4 * 2 < NR) tp[q4 * 2] = s0;
           if (q4 * 2 + 1 < NR) tp[q4 * 2 + 1] = s1;
           __syncwarp();
-          if (lane == 0) rbar_arrive(&empty_bar[pipe.stage]);
+          if (lane == 0) mbar_arrive(&empty_bar[pipe.stage]);
           pipe_advance(pipe, NS);
         }
         csync();
@@ -577,7 +540,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
 #pragma unroll
         for (int r = 0; r < NR; ++r) pend[c][r] = 0.f;
         if (ch < nchunk) {
-          if (!(dbg & 8)) rbar_wait(&full_bar[pipe.stage], pipe.phase);
+          if (!(dbg & 8)) mbar_wait(&full_bar[pipe.stage], pipe.phase, "decoder_ring", kSpinLimit);
           const int g = ch * kSegPerStage + hseg;
           if (g < nseg && !(dbg & 4)) {
             const bf16* wseg = reinterpret_cast<const bf16*>(ring + (size_t)pipe.stage * SB) + hseg * d + hhalf * half_elems + lane * 4;
@@ -606,7 +569,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
             for (int r = 0; r < NR; ++r) pend[c][r] = a0[r] + a1[r];
           }
           __syncwarp();
-          if (lane == 0 && !(dbg & 8)) rbar_arrive(&empty_bar[pipe.stage]);
+          if (lane == 0 && !(dbg & 8)) mbar_arrive(&empty_bar[pipe.stage]);
           if (!(dbg & 8)) pipe_advance(pipe, NS);
         }
       }
@@ -703,7 +666,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
         const int j = idx - which * npre * 8;
         const bf16* src = (which ? vc : kc) + (long long)(j >> 3) * 64 + (j & 7) * 8;
         bf16* dst = (which ? sv : sk) + (size_t)(j >> 3) * 64 + (j & 7) * 8;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rs_u32(dst)), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       float* knv = cand;                           // [2][64] the new position's k and v, rounded through bf16 like the cache
@@ -822,7 +785,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
       csync();
       // scores: two threads per position (32 dims each), 16-byte chunks rotated by position -> conflict-free
       for (int i = 0; i < nbox; ++i) {
-        rbar_wait(&full_bar[pipe.stage], pipe.phase);
+        mbar_wait(&full_bar[pipe.stage], pipe.phase, "decoder_ring", kSpinLimit);
         const bf16* kb = reinterpret_cast<const bf16*>(ring + (size_t)pipe.stage * SB);
         for (int idx = tid; idx < R * 2; idx += kRingConsumers) {
           const int p = idx >> 1, hf = idx & 1;
@@ -845,7 +808,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
           if (hf == 0 && pos < T) sc[pos] = s;
         }
         __syncwarp();
-        if (lane == 0) rbar_arrive(&empty_bar[pipe.stage]);
+        if (lane == 0) mbar_arrive(&empty_bar[pipe.stage]);
         pipe_advance(pipe, NS);
       }
       csync();
@@ -860,7 +823,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
       tot = warp_sum(tot);
       float o0 = 0.f, o1 = 0.f;
       for (int i = 0; i < nbox; ++i) {
-        rbar_wait(&full_bar[pipe.stage], pipe.phase);
+        mbar_wait(&full_bar[pipe.stage], pipe.phase, "decoder_ring", kSpinLimit);
         const bf16* vb = reinterpret_cast<const bf16*>(ring + (size_t)pipe.stage * SB);
         const int pmax = min(R, T - i * R);
         for (int p = warp; p < pmax; p += kRingConsumerWarps) {
@@ -869,7 +832,7 @@ decoder_ring_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_
           o0 = fmaf(w, v.x, o0); o1 = fmaf(w, v.y, o1);
         }
         __syncwarp();
-        if (lane == 0) rbar_arrive(&empty_bar[pipe.stage]);
+        if (lane == 0) mbar_arrive(&empty_bar[pipe.stage]);
         pipe_advance(pipe, NS);
       }
       opart[warp * 64 + 2 * lane] = o0;
