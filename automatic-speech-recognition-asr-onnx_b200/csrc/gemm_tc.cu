@@ -147,10 +147,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull_bar[acc], acc_phase, "gemm_tc");
       tc_fence_after();
       const int rows_here = min(32, e.M - m0);   // may be <= 0 for a ragged last M tile
+      // vector path: every row pointer is 16-byte aligned, so a thread (= one accumulator row) streams its 32 columns
+      // with 128-bit loads / stores; otherwise (odd leading dimensions, ragged last N chunk) the transposing path below
+      const bool vec_ok = ((e.ldc * (e.c_dtype == kF32 ? 4 : 2)) & 15) == 0 && ((e.sC * (e.c_dtype == kF32 ? 4 : 2)) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(e.C) & 15) == 0 &&
+                          (!e.residual || (((e.ldr * 4) & 15) == 0 && ((e.sR * 4) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.residual) & 15) == 0)) &&
+                          (!e.bias || ((reinterpret_cast<uintptr_t>(e.bias) & 15) == 0 && ((e.sBias * 4) & 15) == 0));
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (n0 + c0 >= e.N || rows_here <= 0) break;
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        if (vec_ok && n0 + c0 + 32 <= e.N) {
+          if (lane < rows_here) {
+            const int64_t row = m0 + lane;
+            const int colb = n0 + c0;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (e.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(e.bias + (int64_t)z * e.sBias + colb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(bp + j); v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w; }
+            }
+            if (e.act == kActGelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (e.act == kActRelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (e.residual) {      // may alias C (in-place residual add): all loads of the strip are issued before its stores
+              const float4* rp = reinterpret_cast<const float4*>(e.residual + (int64_t)z * e.sR + row * e.ldr + colb);
+              float4 r4[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) r4[j] = rp[j];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[4 * j] += r4[j].x; v[4 * j + 1] += r4[j].y; v[4 * j + 2] += r4[j].z; v[4 * j + 3] += r4[j].w; }
+            }
+            const int64_t o = (int64_t)z * e.sC + row * e.ldc + colb;
+            if (e.c_dtype == kF32) {
+              float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + o);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* cp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.C) + o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                  w[i] = *reinterpret_cast<const uint32_t*>(&p2);
+                }
+                cp[j] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) my[lane * 33 + j] = __uint_as_float(r[j]);
         __syncwarp();
