@@ -28,8 +28,6 @@ namespace b200asr {
 constexpr int kAttSoftmaxWarps = 8;       // two warps per TMEM lane quarter: each takes every other 32-key chunk of its rows
 constexpr int kAttThreads = (kAttSoftmaxWarps + 1) * 32;   // + warp 8: TMA + MMA
 constexpr int kAttBM = 128;
-constexpr int kAttMaxT = 448;
-constexpr int kAttOCol = 448;             // TMEM column of the O accumulator
 constexpr int kAttTile = 128 * 64 * 2;    // one [128][64] bf16 tile = 16 KB
 
 using namespace ptx;
@@ -39,16 +37,22 @@ struct AttArgs {
   int T, d, n_heads;
 };
 
+// DH = head dimension (64: Whisper; 128: SenseVoice / Paraformer).  A 128-wide head is two 64-column SWIZZLE_128B tiles per
+// operand: the Q K^T contraction walks both (8 k16 steps), V is an MN-major B operand with two 64-wide N blocks LBO apart,
+// O takes 128 TMEM columns (scores then fit T <= 384; shared memory holds K and V for T <= 256).
+template <int DH>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
+  constexpr int NH = DH / 64;                         // 64-column tiles per operand row
+  constexpr uint32_t kOCol = 512 - DH;                // TMEM column of the O accumulator
   extern __shared__ __align__(1024) uint8_t att_smem[];
   const int T = a.T;
   const int nkb = (T + 127) / 128;                    // 128-key boxes of K and of V
   const uint32_t base_addr = smem_u32(att_smem);
   uint8_t* sQ = att_smem + ((1024u - (base_addr & 1023u)) & 1023u);      // SWIZZLE_128B atoms need 1024-byte alignment
-  uint8_t* sK = sQ + kAttTile;
-  uint8_t* sV = sK + (size_t)nkb * kAttTile;
-  uint8_t* sP = sV + (size_t)nkb * kAttTile;          // 2 x [128][64] bf16
+  uint8_t* sK = sQ + NH * kAttTile;                   // [NH][nkb] tiles of [128 keys][64 dims]
+  uint8_t* sV = sK + (size_t)NH * nkb * kAttTile;     // [NH][nkb] tiles of [128 keys][64 dims]
+  uint8_t* sP = sV + (size_t)NH * nkb * kAttTile;     // 2 x [128][64] bf16
   __shared__ uint64_t bar_qk, bar_v, bar_s, bar_o, bar_pfull[2], bar_pempty[2];
   __shared__ uint32_t tmem_slot;
 
@@ -76,26 +80,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
   if (warp == kAttSoftmaxWarps) {
     if (lane == 0) {
       // ---- TMA: Q + K on one barrier (needed first), V on its own ----
-      mbar_expect_tx(&bar_qk, (uint32_t)((1 + nkb) * kAttTile));
-      tma_load_3d(sQ, &tmQKV, h * 64, row0 + m0, 0, &bar_qk);
-      for (int j = 0; j < nkb; ++j) tma_load_3d(sK + (size_t)j * kAttTile, &tmQKV, a.d + h * 64, row0 + j * 128, 0, &bar_qk);
-      mbar_expect_tx(&bar_v, (uint32_t)(nkb * kAttTile));
-      for (int j = 0; j < nkb; ++j) tma_load_3d(sV + (size_t)j * kAttTile, &tmQKV, 2 * a.d + h * 64, row0 + j * 128, 0, &bar_v);
+      mbar_expect_tx(&bar_qk, (uint32_t)(NH * (1 + nkb) * kAttTile));
+#pragma unroll
+      for (int hf = 0; hf < NH; ++hf) {
+        tma_load_3d(sQ + (size_t)hf * kAttTile, &tmQKV, h * DH + hf * 64, row0 + m0, 0, &bar_qk);
+        for (int j = 0; j < nkb; ++j)
+          tma_load_3d(sK + (size_t)(hf * nkb + j) * kAttTile, &tmQKV, a.d + h * DH + hf * 64, row0 + j * 128, 0, &bar_qk);
+      }
+      mbar_expect_tx(&bar_v, (uint32_t)(NH * nkb * kAttTile));
+#pragma unroll
+      for (int hf = 0; hf < NH; ++hf)
+        for (int j = 0; j < nkb; ++j)
+          tma_load_3d(sV + (size_t)(hf * nkb + j) * kAttTile, &tmQKV, 2 * a.d + h * DH + hf * 64, row0 + j * 128, 0, &bar_v);
       // ---- S = Q K^T, 128 keys per instruction group ----
       mbar_wait(&bar_qk, 0, "attention_tc");
       tc_fence_after();
-      const uint64_t qdesc = smem_desc_sw128(smem_u32(sQ));
       for (int n0 = 0; n0 < Tp; n0 += 128) {
         const int n = min(128, Tp - n0);
         const uint32_t idesc = idesc_bf16(kAttBM, n, 0);
-        const uint64_t kdesc = smem_desc_sw128(smem_u32(sK) + (uint32_t)n0 * 128u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem + (uint32_t)n0, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc, k != 0);
+        for (int k = 0; k < DH / 16; ++k) {
+          const int hf = k >> 2;
+          const uint64_t qdesc = smem_desc_sw128(smem_u32(sQ) + (uint32_t)hf * kAttTile);
+          const uint64_t kdesc = smem_desc_sw128(smem_u32(sK) + (uint32_t)(hf * nkb) * kAttTile + (uint32_t)n0 * 128u);
+          tc_mma_bf16(tmem + (uint32_t)n0, qdesc + (uint64_t)(2 * (k & 3)), kdesc + (uint64_t)(2 * (k & 3)), idesc, k != 0);
+        }
       }
       tc_commit(&bar_s);
       // ---- O += P V, one 64-key block at a time ----
       mbar_wait(&bar_v, 0, "attention_tc");
-      const uint32_t idesc_pv = idesc_bf16(kAttBM, 64, 1);
+      const uint32_t idesc_pv = idesc_bf16(kAttBM, DH, 1);
+      const uint64_t v_lbo = (uint64_t)(((uint32_t)nkb * kAttTile) >> 4) << 16;      // pitch of the 64-wide N blocks of V
       for (int j = 0; j < nblk; ++j) {
         const int buf = j & 1;
         mbar_wait(&bar_pfull[buf], (uint32_t)((j >> 1) & 1), "attention_tc");
@@ -105,8 +120,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
 #pragma unroll 1
         for (int k = 0; k < ksteps; ++k) {
           // V rows (keys) j*64 + k*16 ..+15: two 8-key groups, 2048 bytes per step
-          const uint64_t vdesc = smem_desc_sw128(smem_u32(sV) + (uint32_t)(j * 64 + k * 16) * 128u);
-          tc_mma_bf16(tmem + kAttOCol, pdesc + (uint64_t)(2 * k), vdesc, idesc_pv, (j | k) != 0);
+          uint64_t vdesc = smem_desc_sw128(smem_u32(sV) + (uint32_t)(j * 64 + k * 16) * 128u);
+          if (NH > 1) vdesc = (vdesc & ~(0x3FFFull << 16)) | v_lbo;
+          tc_mma_bf16(tmem + kOCol, pdesc + (uint64_t)(2 * k), vdesc, idesc_pv, (j | k) != 0);
         }
         tc_commit(&bar_pempty[buf]);                   // P buffer reusable once these MMAs have read it
       }
@@ -175,19 +191,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
     tc_fence_after();
     const float inv = 1.0f / (s_sum[0][r] + s_sum[1][r]);
     const int t = m0 + r;
-    uint32_t o[32];
-    tmem_ld32(lane_base + kAttOCol + half * 32, o);
-    if (t < T) {
-      bf16* dst = a.ctx + (int64_t)(row0 + t) * a.ld_ctx + h * 64 + half * 32;
+    bf16* dst = a.ctx + (int64_t)(row0 + t) * a.ld_ctx + h * DH + half * (DH / 2);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t w[4];
+    for (int part = 0; part < DH / 64; ++part) {
+      uint32_t o[32];
+      tmem_ld32(lane_base + kOCol + half * (DH / 2) + part * 32, o);
+      if (t < T) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(o[c * 8 + 2 * i]) * inv, __uint_as_float(o[c * 8 + 2 * i + 1]) * inv);
-          w[i] = *reinterpret_cast<const uint32_t*>(&p2);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(o[c * 8 + 2 * i]) * inv, __uint_as_float(o[c * 8 + 2 * i + 1]) * inv);
+            w[i] = *reinterpret_cast<const uint32_t*>(&p2);
+          }
+          *reinterpret_cast<uint4*>(dst + part * 32 + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -201,18 +220,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
 
 // ---------------------------------------------------------------------------
 bool attention_tc_supported(int T, int d, int n_heads) {
-  return T >= 1 && T <= kAttMaxT && d == n_heads * 64 && (d % 8) == 0;
+  if (T < 1 || n_heads <= 0 || d % n_heads || (d % 8)) return false;
+  const int dh = d / n_heads;
+  if (dh == 64) return T <= 448;            // 448 score columns + 64 output columns of TMEM
+  if (dh == 128) return T <= 256;           // K and V (2 x 2 tiles per 128 keys) must fit shared memory
+  return false;
 }
 
 // qkv: bf16 [M = batch*T][3d] (q | k | v per row), ctx: bf16 [M][d]
 cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, int d, int n_heads, cudaStream_t st,
                                 std::string* err) {
   if (!attention_tc_supported(T, d, n_heads)) { if (err) *err = "attention_tc: unsupported shape"; return cudaErrorInvalidValue; }
+  const int dh = d / n_heads, nh = dh / 64;
   const int nkb = (T + 127) / 128;
-  const size_t smem = (size_t)(1 + 2 * nkb + 2) * kAttTile + 1024;
+  const size_t smem = (size_t)(nh + 2 * nkb * nh + 2) * kAttTile + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t r = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * kAttTile + 1024);
+    cudaError_t r = cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * kAttTile + 1024);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kAttTile + 1024);
     if (r != cudaSuccess) return r;
     attr_done = true;
   }
@@ -221,7 +246,8 @@ cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, in
   AttArgs a;
   a.ctx = reinterpret_cast<bf16*>(ctx); a.ld_ctx = d; a.T = T; a.d = d; a.n_heads = n_heads;
   dim3 grid((T + kAttBM - 1) / kAttBM, n_heads, batch);
-  attention_tc_kernel<<<grid, kAttThreads, smem, st>>>(tm, a);
+  if (dh == 64) attention_tc_kernel<64><<<grid, kAttThreads, smem, st>>>(tm, a);
+  else attention_tc_kernel<128><<<grid, kAttThreads, smem, st>>>(tm, a);
   return cudaGetLastError();
 }
 

@@ -254,6 +254,7 @@ struct b200asr_nar {
   float *alphas = nullptr, *acoustic = nullptr, *dec = nullptr, *dx = nullptr, *f32buf = nullptr, *sa_in = nullptr, *dec_logits = nullptr;
   int* n_tok = nullptr; int last_rows = 0;
   // SenseVoice: the whole forward is one CUDA graph per (batch, n_samples) -- ~700 small launches are host-bound otherwise
+  bool use_attn_tc = true;
   bool use_graph = true; cudaGraphExec_t graph = nullptr; int graph_B = -1, graph_N = -1, graph_dtype = -1; int64_t graph_nodes = 0;
   int* h_pinned = nullptr;
   int max_frames = 0, max_T = 0;
@@ -335,7 +336,7 @@ int nar_block(b200asr_nar* e, const std::string& p, const std::string& fsmn_bias
   else
     fsmn_kernel<float><<<dim3(T, B), 256, 0, e->st>>>((const float*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, fsmn_bias), res_in, T, D, c.fsmn_kernel, e->resid);
   NKL(cudaGetLastError());
-  if (ad == kBF16 && c.use_tensor_cores && dh == 64 && attention_tc_supported(T, D, H)) {
+  if (ad == kBF16 && c.use_tensor_cores && e->use_attn_tc && attention_tc_supported(T, D, H)) {
     std::string msg;
     cudaError_t r = launch_attention_tc(e->qkv, e->ctx, B, T, D, H, e->st, &msg);
     e->launches++;
@@ -855,6 +856,7 @@ int64_t b200asr_nar_kernel_launches(const b200asr_nar* e) { return e ? e->launch
 int b200asr_nar_set_option(b200asr_nar* e, const char* key, int64_t value) {
   if (!e || !key) return B200ASR_E_INVALID;
   if (!strcmp(key, "graph")) { e->use_graph = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; } return B200ASR_OK; }
   return e->fail(B200ASR_E_INVALID, std::string("unknown option ") + key);
 }
 void* b200asr_nar_stream(b200asr_nar* e) { return e ? (void*)e->st : nullptr; }

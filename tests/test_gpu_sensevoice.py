@@ -84,3 +84,42 @@ def test_sensevoice_batch_and_language_selector():
     with pytest.raises(Exception, match="language_idx"):
         eng.run(clips[:1], 9)
     eng.close()
+
+
+@pytest.mark.parametrize("n_samples", [40000, 83000, 123520, 240000])
+def test_sensevoice_bf16_head128_fused_attention(n_samples):
+    """Production head width (128 = two swizzle tiles per operand in attention_tc.cu) on a two-head model: the fused
+    tcgen05 attention against the three-launch CUDA-core path of the same engine (3e-2 on O(1) LayerNorm outputs, the
+    two differ in where P is normalised) and against the fp32 oracle (0.12, the bf16 bound of this file).  The clip
+    lengths put T below one 128-key box, at a non-multiple of 16, across the box edge and near the 256-key limit."""
+    import dataclasses
+    maxs = 245000
+    dims = dataclasses.replace(D, d_model=256, n_heads=2, ffn=512)
+    odims = dataclasses.replace(so.TINY_TEST, d_model=256, n_heads=2, ffn=512)
+    assert dims.head_dim == 128
+    raw = sv.synth_sensevoice_checkpoint(dims, 5)
+    tensors = sv.fold_sensevoice(raw, dims, maxs)
+    rng = np.random.default_rng(n_samples)
+    clips = (rng.standard_normal((2, n_samples)) * 2500).clip(-32768, 32767).astype(np.int16)
+    T = dims.lfr_frames(n_samples) + 4
+    outs = []
+    for fused in (1, 0):
+        eng = sv.SenseVoiceEngine(dims, tensors, precision="bf16", max_batch=2, max_samples=maxs)
+        eng.set_option("attn_tc", fused)
+        eng.set_option("graph", 0)
+        eng.run(clips, [0, 3])
+        enc = eng.get_stage("enc_out", 2 * T * 256).reshape(2, T, 256)
+        outs.append((enc.copy(), eng.kernel_launches))
+        eng.close()
+    d = float(np.abs(outs[0][0] - outs[1][0]).max())
+    print(f"T={T}: fused vs unfused enc_out max|d| = {d:.4f}; launches {outs[0][1]} vs {outs[1][1]}")
+    assert np.isfinite(outs[0][0]).all()
+    assert d <= 3e-2
+    assert outs[0][1] < outs[1][1]
+    fw = so.fold_weights(so.make_raw_weights(odims, 5), odims, dims.lfr_frames(maxs))
+    with torch.no_grad():
+        _, st = so.transcribe(clips[1], fw, odims, 3, return_stages=True)
+    ref = st["enc_out"].numpy()
+    do = float(np.abs(outs[0][0][1] - ref).max())
+    print("vs fp32 oracle max|d| =", do)
+    assert do <= 0.12
