@@ -9,7 +9,7 @@
 namespace b200asr {
 
 enum DType : int { kF32 = 0, kBF16 = 1 };
-enum Act : int { kActNone = 0, kActGelu = 1, kActRelu = 2 };
+enum Act : int { kActNone = 0, kActGelu = 1, kActRelu = 2, kActGeluTanh = 3 };
 
 typedef __nv_bfloat16 bf16;
 
@@ -41,6 +41,12 @@ template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __flo
 // exact (erf) GELU: torch.nn.functional.gelu default, Whisper/Export_Whisper.py:428,437,662
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// tanh-approximated GELU: torch.nn.GELU(approximate="tanh"), Qwen_ASR/Export_Qwen_ASR.py:716-719,873-875
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -83,6 +83,7 @@ gemm_simt_kernel(GemmArgs g) {
       if (g.bias) v += g.bias[(int64_t)z * g.sBias + gn];
       if (g.act == kActGelu) v = gelu_erf(v);
       else if (g.act == kActRelu) v = fmaxf(v, 0.f);
+      else if (g.act == kActGeluTanh) v = gelu_tanh(v);
       if (R) v += R[(int64_t)gm * g.ldr + gn];
       C[(int64_t)gm * g.ldc + gn] = from_f<TC>(v);
     }

@@ -175,6 +175,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else if (e.act == kActRelu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (e.act == kActGeluTanh) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
             }
             if (e.residual) {      // may alias C (in-place residual add): all loads of the strip are issued before its stores
               const float4* rp = reinterpret_cast<const float4*>(e.residual + (int64_t)z * e.sR + row * e.ldr + colb);
@@ -229,6 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float v = my[rr * 33 + lane] + bv;
               if (e.act == kActGelu) v = gelu_erf(v);
               else if (e.act == kActRelu) v = fmaxf(v, 0.f);
+              else if (e.act == kActGeluTanh) v = gelu_tanh(v);
               v += res[rr];
               const int64_t o = (int64_t)z * e.sC + row * e.ldc + col;
               if (e.c_dtype == kF32) reinterpret_cast<float*>(e.C)[o] = v;
