@@ -28,6 +28,13 @@ class NarConfig(C.Structure):
         "dec_att_blocks", "dec_ffn_blocks", "dec_ffn", "cif_kernel")] + [("tail_threshold", C.c_float), ("dec_ln_eps", C.c_float)]
 
 
+class QwenConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "device", "max_batch", "max_samples", "precision", "use_tensor_cores", "n_mels", "n_fft", "hop", "enc_layers", "enc_d",
+        "enc_heads", "enc_ffn", "conv_ch", "out_dim", "chunks_per_window")] + [("enc_ln_eps", C.c_float)] + [(n, C.c_int32) for n in (
+        "vocab", "hidden", "inter", "dec_layers", "heads", "kv_heads", "head_dim", "max_seq_len")] + [("rms_eps", C.c_float)]
+
+
 # every symbol include/b200asr.h declares: (restype, argtypes)
 _P = C.c_void_p
 _I32P = C.POINTER(C.c_int32)
@@ -69,6 +76,29 @@ SYMBOLS = {
     "b200asr_nar_kernel_launches": (C.c_int64, [C.c_void_p]),
     "b200asr_nar_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "b200asr_nar_stream": (C.c_void_p, [C.c_void_p]),
+    "b200asr_qwen_create": (C.c_int, [C.POINTER(QwenConfig), C.POINTER(C.c_void_p)]),
+    "b200asr_qwen_create_error": (C.c_char_p, []),
+    "b200asr_qwen_destroy": (None, [C.c_void_p]),
+    "b200asr_qwen_last_error": (C.c_char_p, [C.c_void_p]),
+    "b200asr_qwen_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.c_int64]),
+    "b200asr_qwen_finalize_weights": (C.c_int, [C.c_void_p]),
+    "b200asr_qwen_set_prompt": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                          C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
+    "b200asr_qwen_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                      C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+    "b200asr_qwen_prefill": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "b200asr_qwen_decode_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "b200asr_qwen_decode": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+    "b200asr_qwen_transcribe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                          C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                          C.POINTER(C.c_int32)]),
+    "b200asr_qwen_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "b200asr_qwen_transcribe_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                                   C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+    "b200asr_qwen_get_stage": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64)]),
+    "b200asr_qwen_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "b200asr_qwen_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "b200asr_qwen_stream": (C.c_void_p, [C.c_void_p]),
     "b200asr_test_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F32P, _F32P, _F32P, _F32P,
                                     C.c_int32, _F32P, C.c_char_p, C.c_int32]),
 }

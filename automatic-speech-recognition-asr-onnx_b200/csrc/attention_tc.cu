@@ -35,6 +35,8 @@ using namespace ptx;
 struct AttArgs {
   bf16* ctx; int64_t ld_ctx;      // [M][d] context rows
   int T, d, n_heads;
+  const int* kv_valid;            // optional [batch]: keys >= kv_valid[b] get `mask_add` added to their score
+  float mask_add;                 // (the reference's additive -128 key mask, Qwen_ASR/Export_Qwen_ASR.py:768-775)
 };
 
 // DH = head dimension (64: Whisper; 128: SenseVoice / Paraformer).  A 128-wide head is two 64-column SWIZZLE_128B tiles per
@@ -136,6 +138,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
     const int q4 = warp & 3, half = warp >> 2;
     const int r = q4 * 32 + lane;                     // 0..127
     const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+    const int kvl = a.kv_valid ? a.kv_valid[b] : T;
+    const float madd = a.mask_add;
     mbar_wait(&bar_s, 0, "attention_tc");
     tc_fence_after();
     float m = -INFINITY;
@@ -143,7 +147,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
       uint32_t v[32];
       tmem_ld32(lane_base + (uint32_t)c0, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) if (c0 + i < T) m = fmaxf(m, __uint_as_float(v[i]));
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < T) m = fmaxf(m, __uint_as_float(v[i]) + (c0 + i >= kvl ? madd : 0.f));
     }
     s_mx[half][r] = m;
     asm volatile("bar.sync 1, %0;" ::"n"(kAttSoftmaxWarps * 32) : "memory");
@@ -163,8 +168,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float e0 = 0.f, e1 = 0.f;
-            if (c0 + i < T) e0 = exp2f(fmaf(__uint_as_float(v[i]), 1.4426950408889634f, -ml2));
-            if (c0 + i + 1 < T) e1 = exp2f(fmaf(__uint_as_float(v[i + 1]), 1.4426950408889634f, -ml2));
+            if (c0 + i < T) e0 = exp2f(fmaf(__uint_as_float(v[i]) + (c0 + i >= kvl ? madd : 0.f), 1.4426950408889634f, -ml2));
+            if (c0 + i + 1 < T) e1 = exp2f(fmaf(__uint_as_float(v[i + 1]) + (c0 + i + 1 >= kvl ? madd : 0.f), 1.4426950408889634f, -ml2));
             sum += e0 + e1;
             const __nv_bfloat162 p2 = __floats2bfloat162_rn(e0, e1);
             packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&p2);
@@ -229,7 +234,7 @@ bool attention_tc_supported(int T, int d, int n_heads) {
 
 // qkv: bf16 [M = batch*T][3d] (q | k | v per row), ctx: bf16 [M][d]
 cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, int d, int n_heads, cudaStream_t st,
-                                std::string* err) {
+                                std::string* err, const int* kv_valid, float mask_add) {
   if (!attention_tc_supported(T, d, n_heads)) { if (err) *err = "attention_tc: unsupported shape"; return cudaErrorInvalidValue; }
   const int dh = d / n_heads, nh = dh / 64;
   const int nkb = (T + 127) / 128;
@@ -244,7 +249,7 @@ cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, in
   CUtensorMap tm;
   if (!make_tmap_rows_sw128(&tm, qkv, 3 * (int64_t)d, (int64_t)batch * T, 3 * (int64_t)d, 128, err)) return cudaErrorNotSupported;
   AttArgs a;
-  a.ctx = reinterpret_cast<bf16*>(ctx); a.ld_ctx = d; a.T = T; a.d = d; a.n_heads = n_heads;
+  a.ctx = reinterpret_cast<bf16*>(ctx); a.ld_ctx = d; a.T = T; a.d = d; a.n_heads = n_heads; a.kv_valid = kv_valid; a.mask_add = mask_add;
   dim3 grid((T + kAttBM - 1) / kAttBM, n_heads, batch);
   if (dh == 64) attention_tc_kernel<64><<<grid, kAttThreads, smem, st>>>(tm, a);
   else attention_tc_kernel<128><<<grid, kAttThreads, smem, st>>>(tm, a);

@@ -100,7 +100,7 @@ struct DecState {           // lives in device memory, one per engine
 };
 struct DecLinearArgs {
   const float* x; int64_t ldx;          // fp32 rows [rows][K]
-  int ln_mode;                          // 0 none, 1 affine-less LN, 2 affine LN (gamma/beta)
+  int ln_mode;                          // 0 none, 1 affine-less LN, 2 affine LN (gamma/beta), 3 affine-less RMS norm
   const float* gamma; const float* beta; float eps;
   const void* W; int w_dtype;           // [N][K]
   const float* bias;                    // [N] or null
@@ -202,7 +202,7 @@ bool make_tmap_rows_sw128(CUtensorMap* tm, const void* base, int64_t cols, int64
 // attention_tc.cu: fused softmax(Q K^T) V per (utterance, head) on tcgen05; qkv bf16 [batch*T][3d], ctx bf16 [batch*T][d]
 bool attention_tc_supported(int T, int d, int n_heads);
 cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, int d, int n_heads, cudaStream_t st,
-                                std::string* err);
+                                std::string* err, const int* kv_valid = nullptr, float mask_add = 0.f);
 // gemm_tc.cu: plain (unswizzled) 2-D bf16 tensor map over [rows][ld] with a [box_rows][box_cols] box
 bool make_tmap_2d_plain(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_cols,
                         int box_rows, std::string* err);

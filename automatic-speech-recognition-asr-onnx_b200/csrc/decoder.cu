@@ -85,7 +85,13 @@ dec_linear_kernel(DecLinearArgs a) {
       xs[r * K + k] = a.x[(int64_t)(r0 + r) * a.ldx + k];
     }
     __syncthreads();
-    if (a.ln_mode != 0 && warp < nr) {
+    if (a.ln_mode == 3 && warp < nr) {            // RMS norm without affine (SimplifiedLayerNormalization, Export_Qwen_ASR.py:1043-1077)
+      float* xr = xs + warp * K;
+      float q = 0.f;
+      for (int k = lane; k < K; k += 32) q += xr[k] * xr[k];
+      const float rstd = rsqrtf(warp_sum(q) / (float)K + a.eps);
+      for (int k = lane; k < K; k += 32) xr[k] *= rstd;
+    } else if (a.ln_mode != 0 && warp < nr) {
       float* xr = xs + warp * K;
       float s = 0.f;
       for (int k = lane; k < K; k += 32) s += xr[k];

@@ -187,6 +187,70 @@ int64_t b200asr_nar_kernel_launches(const b200asr_nar* e);
 int b200asr_nar_set_option(b200asr_nar* e, const char* key, int64_t value);
 void* b200asr_nar_stream(b200asr_nar* e);
 
+/* ---------------------------------------------------------------------------------------------
+ * Qwen3-ASR: log-mel -> chunked Conv2d stem -> windowed audio encoder -> prompt concat -> decoder with KV cache.
+ * Replaces, in Qwen_ASR/Inference_Qwen_ASR_ONNX.py, prefill_session.run (:656: encoder + concat + rotary/mask +
+ * decoder prefill + first-token arg-max) and the per-token embed_session.run + decode_session.run pair (:703-717).
+ * Math: Qwen_ASR/Export_Qwen_ASR.py QWEN3_ASR_ENCODER.forward :850-927, QWEN3_ASR_ROTARY_MASK_* :933-1025,
+ * QWEN3_ASR_DECODER_MAIN.forward :1265-1336, ARGMAX :1418-1420, CONCAT_EMBED :1428-1435.  The reference graph is
+ * batch 1; a batch here is that many independent clips of equal length sharing one prompt.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b200asr_qwen b200asr_qwen;
+
+typedef struct b200asr_qwen_config {
+  int32_t device, max_batch, max_samples, precision, use_tensor_cores;
+  int32_t n_mels, n_fft, hop;                                   /* 128 / 400 / 160 */
+  int32_t enc_layers, enc_d, enc_heads, enc_ffn;                /* 0.6B: 18 / 896 / 14 / 3584 */
+  int32_t conv_ch, out_dim, chunks_per_window;                  /* 480 / 1024 / 8 (n_window_infer / (2 n_window)) */
+  float enc_ln_eps;                                             /* 1e-5 */
+  int32_t vocab, hidden, inter, dec_layers, heads, kv_heads, head_dim;   /* 151936 / 1024 / 3072 / 28 / 16 / 8 / 128 */
+  int32_t max_seq_len;                                          /* MAX_SEQ_LEN of the export (1024): prompt + audio + generated */
+  float rms_eps;                                                /* 1e-6 */
+} b200asr_qwen_config;
+
+int b200asr_qwen_create(const b200asr_qwen_config* cfg, b200asr_qwen** out);
+const char* b200asr_qwen_create_error(void);
+void b200asr_qwen_destroy(b200asr_qwen* e);
+const char* b200asr_qwen_last_error(const b200asr_qwen* e);
+/* tensors (fp32, folded as the exported graphs hold them; Conv2d / Linear layouts as PyTorch stores them):
+ * stft_kernel [2F][n_fft], mel_fbank [n_mels][F], conv{1,2,3}.{w,b}, conv_out.w, enc_pos [13][enc_d],
+ * enc{i}.{qkv.w,qkv.b,out.w,out.b,fc1.w,fc1.b,fc2.w,fc2.b} (LayerNorm affines and sqrt(scaling) folded, :829-848),
+ * proj1.{w,b} (ln_post folded), proj2.{w,b}, embed.w [vocab][hidden], lm_head.w (optional; absent = tied to embed.w),
+ * final_norm.g, rope_cos / rope_sin [>= max_seq_len][head_dim/2],
+ * dec{i}.{qkv.w (input_layernorm weight folded), qk_norm.g [2][head_dim] (q then k, head_dim^-0.25 folded), o.w,
+ * gate_up.w (post_attention_layernorm weight folded; gate rows then up rows), down.w} (:1141-1190) */
+int b200asr_qwen_set_tensor(b200asr_qwen* e, const char* name, const float* host_data, int64_t numel);
+int b200asr_qwen_finalize_weights(b200asr_qwen* e);
+/* token ids the exporter bakes around the audio (:1540-1586) and the stop set (:1503) */
+int b200asr_qwen_set_prompt(b200asr_qwen* e, const int32_t* head_ids, int32_t n_head, const int32_t* suffix_ids, int32_t n_suffix,
+                            const int32_t* tail_ids, int32_t n_tail, const int32_t* stop_ids, int32_t n_stop);
+/* pcm [batch][n_samples]: int16 (scaled by 1/32768 on device) or float32 in [-1,1].  Leaves the prompt embedding
+ * [head | query | suffix | audio | tail | language tail] in HBM; n_prompt_out = its length. */
+int b200asr_qwen_encode(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                        const int32_t* query_ids, int32_t n_query, const int32_t* language_tail_ids, int32_t n_language_tail,
+                        int32_t* n_prompt_out);
+/* decoder over the whole prompt; logits_out [batch][vocab] (nullable), token_out [batch] = arg-max */
+int b200asr_qwen_prefill(b200asr_qwen* e, float* logits_out, int32_t* token_out);
+/* one token: token_in [batch] (NULL = the token selected by the previous call, as the script feeds max_logits_idx back) */
+int b200asr_qwen_decode_step(b200asr_qwen* e, const int32_t* token_in, float* logits_out, int32_t* token_out);
+/* greedy loop on the device until every clip hit a stop id or generation_limit = max_seq_len - 10 - n_prompt (:666) */
+int b200asr_qwen_decode(b200asr_qwen* e, int32_t max_new, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
+/* encode + prefill + decode in one call; max_new < 0 = the script's generation_limit */
+int b200asr_qwen_transcribe(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                            const int32_t* query_ids, int32_t n_query, const int32_t* language_tail_ids, int32_t n_language_tail,
+                            int32_t max_new, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
+/* same, split so a benchmark can time with the PCM already resident in HBM */
+int b200asr_qwen_upload(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples);
+int b200asr_qwen_transcribe_resident(b200asr_qwen* e, const int32_t* query_ids, int32_t n_query, const int32_t* language_tail_ids,
+                                     int32_t n_language_tail, int32_t max_new, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
+/* "features" [B][frames][n_mels], "audio_hidden" [B][n_audio][out_dim], "prompt_embed" [B][n_prompt][hidden] (before
+ * prefill), "logits" [B][vocab] */
+int b200asr_qwen_get_stage(b200asr_qwen* e, const char* name, float* out, int64_t capacity, int64_t* numel_out);
+int64_t b200asr_qwen_kernel_launches(const b200asr_qwen* e);
+/* options: "graph" (0/1, default 1): replay a decode step as one CUDA graph; "attn_tc" (0/1): fused tcgen05 encoder attention */
+int b200asr_qwen_set_option(b200asr_qwen* e, const char* key, int64_t value);
+void* b200asr_qwen_stream(b200asr_qwen* e);
+
 #ifdef __cplusplus
 }
 #endif

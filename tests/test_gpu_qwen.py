@@ -1,0 +1,143 @@
+"""Qwen3-ASR on the CUDA engine (csrc/qwen.cu) against goldens minted from the reference's own QWEN3_ASR_* classes.
+fp32 mode: features 1e-4, audio tower output 1e-3, teacher-forced logits 1e-3 (north-star tolerance; logits are O(8)),
+greedy token streams identical, through the device loop and through the script's call-by-call protocol.
+bf16 mode (tcgen05 GEMMs, fused masked attention, bf16 KV cache): audio tower output within 0.12 and logits within
+0.35 of the fp32 reference (8 mantissa bits through 2+2 layers and a 128-wide contraction; written here), arg-max equal
+wherever the reference top-2 margin exceeds twice that."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qwen_oracle as qo
+from b200asr import qwen as qw
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted((Path(__file__).parent / "golden").glob("qwen_tiny_case*.npz"))
+D = qw.QWEN_TINY_TEST
+MAX_SAMPLES = 200000
+BF16_LOGIT_TOL = 0.35
+
+
+def _engine(seed, precision, max_batch=1, max_samples=MAX_SAMPLES):
+    raw = qw.synth_qwen_checkpoint(D, seed)
+    return qw.QwenEngine(D, qw.fold_qwen(raw, D), qw.TINY_PROMPT, precision=precision, max_batch=max_batch, max_samples=max_samples)
+
+
+def _forced(eng, pcm, q, l, forced):
+    n_prompt = eng.encode(pcm, q, l)
+    lg, tok = eng.prefill()
+    out = [lg.copy()]
+    for t in forced:
+        lg, tok = eng.decode_step(token_in=np.full(eng.batch, t, np.int32))
+        out.append(lg.copy())
+    return n_prompt, np.stack(out, axis=1)        # [B, steps, vocab]
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])
+def test_qwen_f32_vs_reference_golden(path):
+    g = dict(np.load(path))
+    eng = _engine(int(g["seed"]), "f32")
+    q, l = g["query_ids"].tolist(), g["language_tail_ids"].tolist()
+    n_prompt, lg = _forced(eng, g["pcm"], q, l, g["forced_tokens"].tolist())
+    assert n_prompt == int(g["n_prompt"])
+    d = float(np.abs(lg[0] - g["forced_logits"]).max())
+    print("f32 forced logits max|d| =", d)
+    assert d <= 1e-3
+    n_prompt = eng.encode(g["pcm"], q, l)
+    frames = len(g["pcm"]) // D.hop
+    feat = eng.get_stage("features", frames * D.n_mels).reshape(frames, D.n_mels)
+    np.testing.assert_allclose(feat.T, g["features"], atol=1e-4)
+    na = int(g["n_audio"])
+    ah = eng.get_stage("audio_hidden", na * D.out_dim).reshape(na, D.out_dim)
+    print("f32 audio_hidden max|d| =", float(np.abs(ah - g["audio_hidden"]).max()))
+    np.testing.assert_allclose(ah, g["audio_hidden"], atol=1e-3)
+    # greedy stream: device loop, explicit prefill + device loop, and the script's host-stepped protocol
+    mx = int(g["max_new"])
+    assert eng.transcribe(g["pcm"], q, l, max_new=mx)[0] == g["tokens"].tolist()
+    eng.encode(g["pcm"], q, l)
+    eng.prefill(want_logits=False)
+    assert eng.decode(mx)[0] == g["tokens"].tolist()
+    eng.set_option("graph", 0)
+    assert eng.transcribe(g["pcm"], q, l, max_new=mx)[0] == g["tokens"].tolist()
+    eng.close()
+
+
+def test_qwen_host_stepped_protocol_equals_device_loop():
+    g = dict(np.load(GOLD[3]))
+    eng = _engine(int(g["seed"]), "f32")
+    q, l = g["query_ids"].tolist(), g["language_tail_ids"].tolist()
+    a = qw.transcribe_clip(eng, g["pcm"], query_ids=q, language_tail_ids=l)
+    b = qw.transcribe_clip(eng, g["pcm"], query_ids=q, language_tail_ids=l, step_through_host=True)
+    assert a["tokens"] == b["tokens"] and a["rtf"] > 0
+    assert a["tokens"][:int(g["max_new"])] == g["tokens"].tolist()
+    fw = qo.fold_weights(qo.make_raw_weights(qo.TINY_TEST, int(g["seed"])), qo.TINY_TEST)
+    want = qo.greedy_transcribe(g["pcm"], fw, qo.TINY_TEST, qo.TINY_PROMPT, q, l)          # to a stop id or generation_limit
+    assert a["tokens"] == want
+    eng.close()
+
+
+@pytest.mark.parametrize("path", GOLD[:3], ids=[p.stem for p in GOLD[:3]])
+def test_qwen_bf16_vs_reference_golden(path):
+    g = dict(np.load(path))
+    q, l = g["query_ids"].tolist(), g["language_tail_ids"].tolist()
+    res = {}
+    for fused in (1, 0):
+        eng = _engine(int(g["seed"]), "bf16")
+        eng.set_option("attn_tc", fused)
+        _, lg = _forced(eng, g["pcm"], q, l, g["forced_tokens"].tolist())
+        eng.encode(g["pcm"], q, l)
+        na = int(g["n_audio"])
+        ah = eng.get_stage("audio_hidden", na * D.out_dim).reshape(na, D.out_dim).copy()
+        res[fused] = (lg[0], ah, eng.kernel_launches)
+        eng.close()
+    d_ah = float(np.abs(res[1][1] - g["audio_hidden"]).max())
+    d_lg = float(np.abs(res[1][0] - g["forced_logits"]).max())
+    d_fu = float(np.abs(res[1][1] - res[0][1]).max())
+    print(f"bf16: audio_hidden max|d| = {d_ah:.4f}, logits max|d| = {d_lg:.4f}, fused vs unfused attention {d_fu:.4f}")
+    assert d_ah <= 0.12 and d_fu <= 3e-2
+    assert d_lg <= BF16_LOGIT_TOL
+    assert res[1][2] < res[0][2]                 # the fused masked attention really ran
+    ref = g["forced_logits"]
+    top2 = np.sort(ref, axis=-1)[:, -2:]
+    safe = (top2[:, 1] - top2[:, 0]) > 2 * BF16_LOGIT_TOL
+    assert np.array_equal(res[1][0].argmax(-1)[safe], ref.argmax(-1)[safe])
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16"])
+def test_qwen_batch_equals_single(precision):
+    g = dict(np.load(GOLD[0]))
+    rng = np.random.default_rng(5)
+    n = 70000
+    clips = (rng.standard_normal((3, n)) * 2500).clip(-32768, 32767).astype(np.int16)
+    eng = _engine(int(g["seed"]), precision, max_batch=3)
+    forced = [11, 12, 13]
+    _, lb = _forced(eng, clips, (5, 6), (9,), forced)
+    singles = np.concatenate([_forced(eng, clips[i], (5, 6), (9,), forced)[1] for i in range(3)], axis=0)
+    d = float(np.abs(lb - singles).max())
+    print(precision, "batch vs single max|dlogit| =", d)
+    assert d <= (1e-4 if precision == "f32" else 5e-2)
+    tb = eng.transcribe(clips, (5, 6), (9,), max_new=6)
+    ts = [eng.transcribe(clips[i], (5, 6), (9,), max_new=6)[0] for i in range(3)]
+    if precision == "f32":
+        assert tb == ts
+        fw = qo.fold_weights(qo.make_raw_weights(qo.TINY_TEST, int(g["seed"])), qo.TINY_TEST)
+        assert ts[1] == qo.greedy_transcribe(clips[1], fw, qo.TINY_TEST, qo.TINY_PROMPT, (5, 6), (9,), max_new=6)
+    eng.close()
+
+
+def test_qwen_float_pcm_and_errors():
+    g = dict(np.load(GOLD[0]))
+    eng = _engine(int(g["seed"]), "f32")
+    q, l = g["query_ids"].tolist(), g["language_tail_ids"].tolist()
+    mx = int(g["max_new"])
+    f32 = g["pcm"].astype(np.float32) / 32768.0           # the reference's F32 audio mode (Inference_Qwen_ASR_ONNX.py:592-596)
+    assert eng.transcribe(f32, q, l, max_new=mx)[0] == g["tokens"].tolist()
+    with pytest.raises(Exception, match="n_samples"):
+        eng.transcribe(g["pcm"][:100])
+    with pytest.raises(Exception, match="out of range"):
+        eng.transcribe(g["pcm"], query_ids=[D.vocab + 5])
+    with pytest.raises(Exception, match="before"):
+        eng.encode(g["pcm"]); eng.decode_step()
+    eng.close()
