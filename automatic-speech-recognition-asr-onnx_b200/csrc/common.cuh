@@ -123,6 +123,7 @@ cudaError_t launch_dec_cross_attn(const float* q, const void* cross_kv /*[2L][B]
                                   float* ctx, cudaStream_t st);
 struct SelectArgs {
   float* logits; int vocab; int batch;
+  const int* cand_idx;       // optional [B][vocab]: `logits` holds per-slice maxima and the token id is cand_idx[b][arg-max] (plain arg-max heads only)
   const float* begin_bias;   // [vocab] added on the fly for the prefill head only (nullable)
   int* cur_token;            // [B] token fed to the next step
   int* tokens; int tokens_ld;// [B][tokens_ld] accepted (non-stop) tokens

@@ -482,6 +482,7 @@ select_token_kernel(SelectArgs a) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
       if (sv[w] > best || (sv[w] == best && si[w] < besti)) { best = sv[w]; besti = si[w]; }
     if (besti == 0x7fffffff) besti = 0;       // all -inf / NaN row: torch.argmax returns 0
+    if (a.cand_idx) besti = a.cand_idx[(int64_t)b * a.vocab + besti];
     const int step = a.state->step;
     a.cur_token[b] = besti;
     if (a.selected_hist && step < a.sel_ld) a.selected_hist[(int64_t)b * a.sel_ld + step] = besti;

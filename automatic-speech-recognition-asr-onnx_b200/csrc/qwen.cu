@@ -297,6 +297,306 @@ qwen_attn_kernel(const float* __restrict__ q, const KT* __restrict__ kc, const K
   for (int m = 0; m < M; ++m) dst[lane + 32 * m] = from_f<OutT>(acc[m] * inv);
 }
 
+// ---- decode-step attention, fused with the QK-norm / RoPE / cache append of the new position: one CTA per (utterance,
+//      query head).  Warps 0-2 normalise and rotate this head's q and its kv head's new k / v (every query head of a
+//      group writes the same cache row, a benign duplicate); then the keys are spread over all 512 threads for the scores
+//      and over the 16 warps for P V (lanes own head dims, unrolled so several cache rows are in flight at once) ----
+constexpr int kAttDecThreads = 512;
+template <typename KT, int DH>
+__global__ void __launch_bounds__(kAttDecThreads)
+qwen_attn_decode_kernel(const float* __restrict__ qkv /*[B][(H+2KH)*DH]*/, const float* __restrict__ g, const float* __restrict__ cosT,
+                        const float* __restrict__ sinT, float eps, KT* __restrict__ kc, KT* __restrict__ vc, int64_t cache_layer_off,
+                        int H, int KH, int max_seq, const DecState* __restrict__ state, float* __restrict__ ctx) {
+  extern __shared__ float dsm[];                 // q[DH] | k_new[DH] | v_new[DH] | scores[max_seq] | part[16][DH]
+  constexpr int NW = kAttDecThreads / 32;
+  __shared__ float red[NW];
+  constexpr int M = DH / 32, half = DH / 2, EPL = DH / 32;
+  float* qs = dsm;
+  float* kn = dsm + DH;
+  float* vn = dsm + 2 * DH;
+  float* sc = dsm + 3 * DH;
+  float* part = sc + max_seq;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int pos = state->kv_len, n_keys = pos + 1;
+  const int kh = h / (H / KH);
+  const int NHD = H + 2 * KH;
+  KT* K = kc + cache_layer_off + ((int64_t)b * KH + kh) * max_seq * DH;
+  KT* V = vc + cache_layer_off + ((int64_t)b * KH + kh) * max_seq * DH;
+  if (warp < 3) {
+    const int head = warp == 0 ? h : (warp == 1 ? H + kh : H + KH + kh);
+    const float* src = qkv + ((int64_t)b * NHD + head) * DH;
+    float v[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) v[m] = src[lane + 32 * m];
+    if (warp < 2) {
+      float ss = 0.f;
+#pragma unroll
+      for (int m = 0; m < M; ++m) ss += v[m] * v[m];
+      const float r = rsqrtf(warp_sum(ss) / (float)DH + eps);
+      const float* gg = g + (warp == 0 ? 0 : DH);
+#pragma unroll
+      for (int m = 0; m < M; ++m) v[m] *= r * gg[lane + 32 * m];
+#pragma unroll
+      for (int m = 0; m < M / 2; ++m) {
+        const int j = lane + 32 * m;
+        const float c = cosT[(int64_t)pos * half + j], sn = sinT[(int64_t)pos * half + j];
+        const float a = v[m], bb = v[m + M / 2];
+        v[m] = a * c - bb * sn;
+        v[m + M / 2] = bb * c + a * sn;
+      }
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) qs[lane + 32 * m] = v[m];
+    } else {
+      KT* dst = (warp == 1 ? K : V) + (int64_t)pos * DH;
+      float* keep = warp == 1 ? kn : vn;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const KT rv = from_f<KT>(v[m]);
+        dst[lane + 32 * m] = rv;
+        keep[lane + 32 * m] = to_f<KT>(rv);          // what later steps will read back from the cache
+      }
+    }
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < n_keys; j += kAttDecThreads) {
+    float s = 0.f;
+    if (j == pos) {
+#pragma unroll 8
+      for (int c = 0; c < DH; ++c) s = fmaf(kn[c], qs[c], s);
+    } else {
+      const KT* kr = K + (int64_t)j * DH;
+#pragma unroll
+      for (int c = 0; c < DH; c += KVec<KT>::N) {
+        float kk[KVec<KT>::N];
+        KVec<KT>::load(kr + c, kk);
+#pragma unroll
+        for (int e = 0; e < KVec<KT>::N; ++e) s = fmaf(kk[e], qs[c + e], s);
+      }
+    }
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < n_keys; j += kAttDecThreads) { const float p = expf(sc[j] - mx); sc[j] = p; sum += p; }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) sum += red[w];
+  float acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+#pragma unroll 4
+  for (int j = warp; j < pos; j += NW) {
+    const float p = sc[j];
+    const KT* vr = V + (int64_t)j * DH + lane * EPL;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, to_f<KT>(vr[e]), acc[e]);
+  }
+  if (warp == pos % NW) {
+    const float p = sc[pos];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(p, vn[lane * EPL + e], acc[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) part[warp * DH + lane * EPL + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < DH) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) o += part[w * DH + threadIdx.x];
+    ctx[((int64_t)b * H + h) * DH + threadIdx.x] = o / sum;
+  }
+}
+
+// ---- weight-streaming GEMV for a decode step: out[r][n] = (rms? rstd[r] : 1) * sum_k W[n][k] * x'[r][k] (+ residual), with
+//      x' = x or silu(x[:K]) * x[K:2K] (SwiGLU of the fused gate_up rows).  KS warps share one output column (split K) so
+//      narrow layers still fill the machine; a warp's first weight chunks are requested before the activations are
+//      staged, the RMS statistics ride along with the staging pass and scale the finished dot products ----
+struct QGemvArgs {
+  const float* x; int64_t ldx; int rms; float eps; int swiglu;
+  const void* W; const float* residual; int64_t ldr; float* out; int64_t ldo;
+  int rows, N, K;
+};
+constexpr int kGemvRows = 4;
+template <typename WT> struct W8;
+template <> struct W8<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float* o) { KVec<bf16>::load(p, o); }
+};
+template <> struct W8<float> {
+  static __device__ __forceinline__ void load(const float* p, float* o) { KVec<float>::load(p, o); KVec<float>::load(p + 4, o + 4); }
+};
+
+template <typename WT, int KS>
+__global__ void __launch_bounds__(256)
+qwen_gemv_kernel(QGemvArgs a) {
+  extern __shared__ float gx[];                  // [kGemvRows][K]
+  __shared__ float red[8][kGemvRows];
+  __shared__ float psum[8][kGemvRows];
+  constexpr int CPB = 8 / KS;                    // output columns per CTA pass
+  constexpr int PF = 4;                          // weight chunks (256 k each) requested ahead of the staging pass
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = warp % KS, cw = warp / KS;
+  const int K = a.K;
+  const WT* W = reinterpret_cast<const WT*>(a.W);
+  const int k0 = (ks * 32 + lane) * 8, kstep = KS * 256;
+  int col = blockIdx.x * CPB + cw;
+  float wpre[PF][8];
+  if (col < a.N) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int k = k0 + i * kstep;
+      if (k < K) W8<WT>::load(W + (int64_t)col * K + k, wpre[i]);
+    }
+  }
+  for (int r0 = 0; r0 < a.rows; r0 += kGemvRows) {
+    const int nr = min(kGemvRows, a.rows - r0);
+    __syncthreads();
+    float ss[kGemvRows];
+#pragma unroll
+    for (int r = 0; r < kGemvRows; ++r) {
+      ss[r] = 0.f;
+      if (r < nr) {
+        const float* xr = a.x + (int64_t)(r0 + r) * a.ldx;
+        for (int k = threadIdx.x * 4; k < K; k += 1024) {          // K % 8 == 0 and 16-byte aligned rows (checked by the launcher)
+          float4 v = *reinterpret_cast<const float4*>(xr + k);
+          if (a.swiglu) {
+            const float4 u = *reinterpret_cast<const float4*>(xr + K + k);
+            v.x = v.x / (1.0f + expf(-v.x)) * u.x; v.y = v.y / (1.0f + expf(-v.y)) * u.y;
+            v.z = v.z / (1.0f + expf(-v.z)) * u.z; v.w = v.w / (1.0f + expf(-v.w)) * u.w;
+          }
+          *reinterpret_cast<float4*>(gx + r * K + k) = v;
+          ss[r] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+      }
+    }
+    if (a.rms) {
+#pragma unroll
+      for (int r = 0; r < kGemvRows; ++r) { const float t = warp_sum(ss[r]); if (lane == 0) red[warp][r] = t; }
+    }
+    __syncthreads();
+    float rstd[kGemvRows];
+#pragma unroll
+    for (int r = 0; r < kGemvRows; ++r) {
+      rstd[r] = 1.f;
+      if (a.rms) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][r];
+        rstd[r] = rsqrtf(t / (float)K + a.eps);
+      }
+    }
+    bool first = (r0 == 0);
+    for (int c = blockIdx.x * CPB + cw; c - cw < a.N; c += gridDim.x * CPB) {      // every warp of the CTA runs the same trip count
+      float acc[kGemvRows];
+#pragma unroll
+      for (int r = 0; r < kGemvRows; ++r) acc[r] = 0.f;
+      if (c < a.N) {
+        const WT* wr = W + (int64_t)c * K;
+        auto fma8 = [&](const float* w, int k) {
+#pragma unroll
+          for (int r = 0; r < kGemvRows; ++r) {
+            if (r < nr) {
+              const float4 x0 = *reinterpret_cast<const float4*>(gx + r * K + k);
+              const float4 x1 = *reinterpret_cast<const float4*>(gx + r * K + k + 4);
+              acc[r] = fmaf(w[0], x0.x, acc[r]); acc[r] = fmaf(w[1], x0.y, acc[r]);
+              acc[r] = fmaf(w[2], x0.z, acc[r]); acc[r] = fmaf(w[3], x0.w, acc[r]);
+              acc[r] = fmaf(w[4], x1.x, acc[r]); acc[r] = fmaf(w[5], x1.y, acc[r]);
+              acc[r] = fmaf(w[6], x1.z, acc[r]); acc[r] = fmaf(w[7], x1.w, acc[r]);
+            }
+          }
+        };
+        int kb = k0;
+        if (first) {
+#pragma unroll
+          for (int i = 0; i < PF; ++i) {
+            const int k = k0 + i * kstep;
+            if (k < K) fma8(wpre[i], k);
+          }
+          kb = k0 + PF * kstep;
+        }
+#pragma unroll 4
+        for (int k = kb; k < K; k += kstep) {
+          float w[8];
+          W8<WT>::load(wr + k, w);
+          fma8(w, k);
+        }
+      }
+      first = false;
+#pragma unroll
+      for (int r = 0; r < kGemvRows; ++r) acc[r] = warp_sum(acc[r]);
+      if (KS > 1) {
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < kGemvRows; ++r) psum[warp][r] = acc[r];
+        }
+        __syncthreads();
+      }
+      if (ks == 0 && c < a.N && lane < nr) {
+        float v = 0.f;
+        if (KS > 1) {
+#pragma unroll
+          for (int q = 0; q < KS; ++q) v += psum[cw * KS + q][lane];
+        } else {
+#pragma unroll
+          for (int r = 0; r < kGemvRows; ++r) if (lane == r) v = acc[r];
+        }
+        float rs = 1.f;
+#pragma unroll
+        for (int r = 0; r < kGemvRows; ++r) if (lane == r) rs = rstd[r];
+        v *= rs;
+        const int row = r0 + lane;
+        if (a.residual) v += a.residual[(int64_t)row * a.ldr + c];
+        a.out[(int64_t)row * a.ldo + c] = v;
+      }
+      if (KS > 1) __syncthreads();
+    }
+  }
+}
+
+// ---- first stage of the vocabulary arg-max: one CTA per (slice, utterance) keeps its slice's best (value, lowest id) ----
+constexpr int kArgSlices = 128;
+__global__ void __launch_bounds__(256)
+qwen_argmax_slices_kernel(const float* __restrict__ logits, int vocab, float* __restrict__ cand_val, int* __restrict__ cand_idx) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int b = blockIdx.y, sl = blockIdx.x;
+  const int per = (vocab + kArgSlices - 1) / kArgSlices;
+  const int lo = sl * per, hi = min(vocab, lo + per);
+  const float* lg = logits + (int64_t)b * vocab;
+  float best = -INFINITY; int besti = 0x7fffffff;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    const float v = lg[i];
+    if (v > best || (v == best && i < besti)) { best = v; besti = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sv[warp] = best; si[warp] = besti; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) if (sv[w] > best || (sv[w] == best && si[w] < besti)) { best = sv[w]; besti = si[w]; }
+    cand_val[b * kArgSlices + sl] = best;
+    cand_idx[b * kArgSlices + sl] = besti == 0x7fffffff ? 0 : besti;
+  }
+}
+
 // ---- SwiGLU: silu(gate) * up on the fused gate_up rows (:1327-1329) ----
 template <typename OutT>
 __global__ void qwen_swiglu_kernel(const float* __restrict__ gu, int inter, int64_t total, OutT* __restrict__ out) {
@@ -354,7 +654,8 @@ struct b200asr_qwen {
   void *xhat = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *P = nullptr;
   int *win_valid = nullptr, *prompt_src = nullptr;
   // decoder buffers
-  float *x = nullptr, *qkvf = nullptr, *q = nullptr, *gu = nullptr, *xl = nullptr, *logits = nullptr;
+  float *x = nullptr, *qkvf = nullptr, *q = nullptr, *gu = nullptr, *xl = nullptr, *logits = nullptr, *cand_val = nullptr;
+  int* cand_idx = nullptr;
   void *xn = nullptr, *actx = nullptr, *mlp = nullptr, *kc = nullptr, *vc = nullptr;
   DecState* dstate = nullptr;
   int *cur_token = nullptr, *tokens = nullptr, *n_gen = nullptr, *finished = nullptr, *save_id = nullptr, *n_save = nullptr;
@@ -527,17 +828,23 @@ int qwen_attention_launch(b200asr_qwen* e, int layer, int rows, int n_new, bool 
   const b200asr_qwen_config& c = e->cfg;
   const int H = c.heads, KH = c.kv_heads, ad = e->act;
   const int64_t layer_off = (int64_t)layer * c.max_batch * KH * c.max_seq_len * DH;
+  const float* g = QWF(e, "dec" + std::to_string(layer) + ".qk_norm.g");
+  const float *cosT = QWF(e, "rope_cos"), *sinT = QWF(e, "rope_sin");
+  if (gemv) {        // one fused launch: QK-norm + RoPE + cache append + attention
+    const size_t dsmem = (size_t)(3 * DH + c.max_seq_len + (kAttDecThreads / 32) * DH) * sizeof(float);
+    if (ad == kBF16) qwen_attn_decode_kernel<bf16, DH><<<rows * H, kAttDecThreads, dsmem, e->st>>>(e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, e->dstate, (float*)e->actx);
+    else qwen_attn_decode_kernel<float, DH><<<rows * H, kAttDecThreads, dsmem, e->st>>>(e->qkvf, g, cosT, sinT, c.rms_eps, (float*)e->kc, (float*)e->vc, layer_off, H, KH, c.max_seq_len, e->dstate, (float*)e->actx);
+    QKL(cudaGetLastError());
+    return B200ASR_OK;
+  }
   const int total_qk = rows * (H + 2 * KH), total_at = rows * H;
   const size_t smem = (size_t)4 * (DH + c.max_seq_len) * sizeof(float);
   if (ad == kBF16) {
-    qwen_qk_rope_kernel<bf16, DH><<<(total_qk + 3) / 4, 128, 0, e->st>>>(e->qkvf, QWF(e, "dec" + std::to_string(layer) + ".qk_norm.g"), QWF(e, "rope_cos"),
-        QWF(e, "rope_sin"), c.rms_eps, n_new, H, KH, c.max_seq_len, layer_off, total_qk, e->dstate, e->q, (bf16*)e->kc, (bf16*)e->vc);
+    qwen_qk_rope_kernel<bf16, DH><<<(total_qk + 3) / 4, 128, 0, e->st>>>(e->qkvf, g, cosT, sinT, c.rms_eps, n_new, H, KH, c.max_seq_len, layer_off, total_qk, e->dstate, e->q, (bf16*)e->kc, (bf16*)e->vc);
     QKL(cudaGetLastError());
-    if (gemv) qwen_attn_kernel<bf16, float, DH><<<(total_at + 3) / 4, 128, smem, e->st>>>(e->q, (const bf16*)e->kc, (const bf16*)e->vc, layer_off, n_new, H, KH, c.max_seq_len, total_at, e->dstate, (float*)e->actx);
-    else qwen_attn_kernel<bf16, bf16, DH><<<(total_at + 3) / 4, 128, smem, e->st>>>(e->q, (const bf16*)e->kc, (const bf16*)e->vc, layer_off, n_new, H, KH, c.max_seq_len, total_at, e->dstate, (bf16*)e->actx);
+    qwen_attn_kernel<bf16, bf16, DH><<<(total_at + 3) / 4, 128, smem, e->st>>>(e->q, (const bf16*)e->kc, (const bf16*)e->vc, layer_off, n_new, H, KH, c.max_seq_len, total_at, e->dstate, (bf16*)e->actx);
   } else {
-    qwen_qk_rope_kernel<float, DH><<<(total_qk + 3) / 4, 128, 0, e->st>>>(e->qkvf, QWF(e, "dec" + std::to_string(layer) + ".qk_norm.g"), QWF(e, "rope_cos"),
-        QWF(e, "rope_sin"), c.rms_eps, n_new, H, KH, c.max_seq_len, layer_off, total_qk, e->dstate, e->q, (float*)e->kc, (float*)e->vc);
+    qwen_qk_rope_kernel<float, DH><<<(total_qk + 3) / 4, 128, 0, e->st>>>(e->qkvf, g, cosT, sinT, c.rms_eps, n_new, H, KH, c.max_seq_len, layer_off, total_qk, e->dstate, e->q, (float*)e->kc, (float*)e->vc);
     QKL(cudaGetLastError());
     qwen_attn_kernel<float, float, DH><<<(total_at + 3) / 4, 128, smem, e->st>>>(e->q, (const float*)e->kc, (const float*)e->vc, layer_off, n_new, H, KH, c.max_seq_len, total_at, e->dstate, (float*)e->actx);
   }
@@ -545,14 +852,41 @@ int qwen_attention_launch(b200asr_qwen* e, int layer, int rows, int n_new, bool 
   return B200ASR_OK;
 }
 
-DecLinearArgs qwen_gemv(b200asr_qwen* e, const float* x, int64_t ldx, int ln_mode, const std::string& wn, const float* residual, int64_t ldr,
-                        float* out, int64_t ldo, int rows, int N, int K) {
-  DecLinearArgs a{};
-  a.x = x; a.ldx = ldx; a.ln_mode = ln_mode; a.eps = e->cfg.rms_eps;
-  a.W = QW(e, wn); a.w_dtype = e->act; a.bias = nullptr; a.act = kActNone;
-  a.residual = residual; a.ldr = ldr; a.out = out; a.ldo = ldo; a.mode = 0;
+template <typename WT>
+cudaError_t qwen_gemv_launch(const QGemvArgs& a, int num_sms, cudaStream_t st) {
+  if (a.K % 8 != 0 || a.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15)) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)kGemvRows * a.K * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  // warps per output column: enough CTAs to cover the machine about four times, but at least one 256-wide k chunk per warp
+  int ks = 1;
+  while (ks < 8 && (int64_t)a.N * ks / 8 < 4 * num_sms && a.K >= ks * 2 * 256) ks *= 2;
+  const int cpb = 8 / ks;
+  int grid = (a.N + cpb - 1) / cpb;
+  if (grid > num_sms * 8) grid = num_sms * 8;          // wide layers (the vocabulary head) loop over columns inside the CTA
+  switch (ks) {
+    case 1: qwen_gemv_kernel<WT, 1><<<grid, 256, smem, st>>>(a); break;
+    case 2: qwen_gemv_kernel<WT, 2><<<grid, 256, smem, st>>>(a); break;
+    case 4: qwen_gemv_kernel<WT, 4><<<grid, 256, smem, st>>>(a); break;
+    default: qwen_gemv_kernel<WT, 8><<<grid, 256, smem, st>>>(a); break;
+  }
+  return cudaGetLastError();
+}
+
+int qwen_gemv(b200asr_qwen* e, const float* x, int64_t ldx, bool rms, bool swiglu, const std::string& wn, const float* residual, int64_t ldr,
+              float* out, int64_t ldo, int rows, int N, int K) {
+  QGemvArgs a{};
+  a.x = x; a.ldx = ldx; a.rms = rms ? 1 : 0; a.eps = e->cfg.rms_eps; a.swiglu = swiglu ? 1 : 0;
+  a.W = QW(e, wn); a.residual = residual; a.ldr = ldr; a.out = out; a.ldo = ldo;
   a.rows = rows; a.N = N; a.K = K;
-  return a;
+  QKL(e->act == kBF16 ? qwen_gemv_launch<bf16>(a, e->num_sms, e->st) : qwen_gemv_launch<float>(a, e->num_sms, e->st));
+  return B200ASR_OK;
 }
 
 // ---- decoder over `n_new` new positions per utterance (x rows = [B][n_new][hidden], fp32), then head + selection ----
@@ -564,7 +898,7 @@ int qwen_decoder(b200asr_qwen* e, int n_new) {
   for (int i = 0; i < c.dec_layers; ++i) {
     const std::string p = "dec" + std::to_string(i) + ".";
     if (gemv) {
-      QKL(launch_dec_linear(qwen_gemv(e, e->x, Hd, 3, p + "qkv.w", nullptr, 0, e->qkvf, NQ, rows, NQ, Hd), e->st));
+      QRET(qwen_gemv(e, e->x, Hd, true, false, p + "qkv.w", nullptr, 0, e->qkvf, NQ, rows, NQ, Hd));
     } else {
       if (ad == kBF16) qwen_rmsnorm_kernel<bf16><<<(rows + 7) / 8, 256, 0, e->st>>>(e->x, Hd, 1, 0, nullptr, c.rms_eps, (bf16*)e->xn, Hd, rows, Hd);
       else qwen_rmsnorm_kernel<float><<<(rows + 7) / 8, 256, 0, e->st>>>(e->x, Hd, 1, 0, nullptr, c.rms_eps, (float*)e->xn, Hd, rows, Hd);
@@ -574,11 +908,9 @@ int qwen_decoder(b200asr_qwen* e, int n_new) {
     if (dh == 128) QRET((qwen_attention_launch<128>(e, i, rows, n_new, gemv)));
     else QRET((qwen_attention_launch<64>(e, i, rows, n_new, gemv)));
     if (gemv) {
-      QKL(launch_dec_linear(qwen_gemv(e, (const float*)e->actx, H * dh, 0, p + "o.w", e->x, Hd, e->x, Hd, rows, Hd, H * dh), e->st));
-      QKL(launch_dec_linear(qwen_gemv(e, e->x, Hd, 3, p + "gate_up.w", nullptr, 0, e->gu, 2 * I, rows, 2 * I, Hd), e->st));
-      qwen_swiglu_kernel<float><<<grid_for((int64_t)rows * I), 256, 0, e->st>>>(e->gu, I, (int64_t)rows * I, (float*)e->mlp);
-      QKL(cudaGetLastError());
-      QKL(launch_dec_linear(qwen_gemv(e, (const float*)e->mlp, I, 0, p + "down.w", e->x, Hd, e->x, Hd, rows, Hd, I), e->st));
+      QRET(qwen_gemv(e, (const float*)e->actx, H * dh, false, false, p + "o.w", e->x, Hd, e->x, Hd, rows, Hd, H * dh));
+      QRET(qwen_gemv(e, e->x, Hd, true, false, p + "gate_up.w", nullptr, 0, e->gu, 2 * I, rows, 2 * I, Hd));
+      QRET(qwen_gemv(e, e->gu, 2 * I, false, true, p + "down.w", e->x, Hd, e->x, Hd, rows, Hd, I));
     } else {
       GemmArgs g = qwen_linear(e, e->actx, H * dh, p + "o.w", "", e->x, Hd, kF32, rows, Hd, H * dh);
       g.residual = e->x; g.ldr = Hd;
@@ -599,9 +931,11 @@ int qwen_decoder(b200asr_qwen* e, int n_new) {
   qwen_rmsnorm_kernel<float><<<(B + 7) / 8, 256, 0, e->st>>>(e->x, Hd, n_new, n_new - 1, QWF(e, "final_norm.g"), c.rms_eps, e->xl, Hd, B, Hd);
   QKL(cudaGetLastError());
   const std::string head = e->w.count("lm_head.w") ? "lm_head.w" : "embed.w";
-  QKL(launch_dec_linear(qwen_gemv(e, e->xl, Hd, 0, head, nullptr, 0, e->logits, c.vocab, B, c.vocab, Hd), e->st));
+  QRET(qwen_gemv(e, e->xl, Hd, false, false, head, nullptr, 0, e->logits, c.vocab, B, c.vocab, Hd));
+  qwen_argmax_slices_kernel<<<dim3(kArgSlices, B), 256, 0, e->st>>>(e->logits, c.vocab, e->cand_val, e->cand_idx);
+  QKL(cudaGetLastError());
   SelectArgs s{};
-  s.logits = e->logits; s.vocab = c.vocab; s.batch = B; s.begin_bias = nullptr;
+  s.logits = e->cand_val; s.vocab = kArgSlices; s.cand_idx = e->cand_idx; s.batch = B; s.begin_bias = nullptr;
   s.cur_token = e->cur_token; s.tokens = e->tokens; s.tokens_ld = c.max_seq_len; s.n_gen = e->n_gen;
   s.finished = e->finished; s.save_id = e->save_id; s.save_ld = c.max_seq_len; s.n_save = e->n_save;
   s.selected_hist = nullptr; s.sel_ld = 0;
@@ -792,7 +1126,7 @@ void b200asr_qwen_destroy(b200asr_qwen* e) {
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
   void* bufs[] = {e->basis_t, e->fb_start, e->fb_len, e->stage_buf, e->d_stop, e->pcm, e->mel_raw, e->max_key, e->feat, e->c1, e->col, e->c2, e->c3,
                   e->stem, e->h, e->S, e->enc_out, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->win_valid, e->prompt_src, e->x, e->qkvf, e->q, e->gu,
-                  e->xl, e->logits, e->xn, e->actx, e->mlp, e->kc, e->vc, e->dstate, e->cur_token, e->tokens, e->n_gen, e->finished, e->save_id, e->n_save};
+                  e->xl, e->logits, e->cand_val, e->cand_idx, e->xn, e->actx, e->mlp, e->kc, e->vc, e->dstate, e->cur_token, e->tokens, e->n_gen, e->finished, e->save_id, e->n_save};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -958,6 +1292,8 @@ int b200asr_qwen_finalize_weights(b200asr_qwen* e) {
     QRET(qwen_alloc(e, &e->mlp, (size_t)rows * I * 4));
     QRET(qwen_alloc(e, &e->xl, (size_t)B * Hd * 4));
     QRET(qwen_alloc(e, &e->logits, (size_t)B * c.vocab * 4));
+    QRET(qwen_alloc(e, &e->cand_val, (size_t)B * kArgSlices * 4));
+    QRET(qwen_alloc(e, &e->cand_idx, (size_t)B * kArgSlices * 4));
     const size_t kv_bytes = (size_t)c.dec_layers * B * c.kv_heads * c.max_seq_len * dh * es;
     QRET(qwen_alloc(e, &e->kc, kv_bytes));
     QRET(qwen_alloc(e, &e->vc, kv_bytes));

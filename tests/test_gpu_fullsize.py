@@ -53,3 +53,48 @@ def test_large_v3_logits_match_oracle(reference, precision, tol):
     assert np.array_equal(got.argmax(-1)[safe], want.argmax(-1)[safe])
     if precision == "f32":
         assert toks == ref["selected"][:3]
+
+
+# ---- Qwen3-ASR-0.6B dimensions (BASELINE configs[4]'s model): one 8 s clip, prefill + 2 decode steps ----
+@pytest.fixture(scope="module")
+def qwen_reference():
+    from oracle import qwen_oracle as qo
+    from b200asr import qwen as qw
+    od = qo.QwenDims(**qw.QWEN3_ASR_0_6B.to_dict())
+    fw = qo.fold_weights(qo.make_raw_weights(od, 20261), od)
+    pcm = synth_pcm(1, 128000)
+    prompt = qo.QwenPrompt(qw.QWEN3_PROMPT.head_ids, qw.QWEN3_PROMPT.suffix_ids, qw.QWEN3_PROMPT.tail_ids, ())
+    toks, st = qo.greedy_transcribe(pcm, fw, od, prompt, (), (), max_new=3, return_stages=True)
+    del fw
+    return pcm, toks, st["logits"].numpy(), st["audio_hidden"].numpy()
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 1e-3), ("bf16", 0.25)])
+def test_qwen3_asr_0_6b_logits_match_oracle(qwen_reference, precision, tol):
+    """fp32 engine within 1e-3 of the oracle on logits (north-star tolerance); bf16 engine within 0.25 (18 + 28 layers of
+    bf16 GEMM operands and a bf16 KV cache; written here), arg-max equal wherever the oracle's top-2 margin exceeds 2x."""
+    from b200asr import qwen as qw
+    pcm, toks, want, ah = qwen_reference
+    dims = qw.QWEN3_ASR_0_6B
+    prompt = qw.QwenPrompt(qw.QWEN3_PROMPT.head_ids, qw.QWEN3_PROMPT.suffix_ids, qw.QWEN3_PROMPT.tail_ids, ())
+    tensors = qw.fold_qwen(qw.synth_qwen_checkpoint(dims, 20261), dims)
+    eng = qw.QwenEngine(dims, tensors, prompt, precision=precision, max_batch=1, max_samples=128000)
+    del tensors
+    eng.encode(pcm)
+    got_ah = eng.get_stage("audio_hidden", ah.size).reshape(ah.shape)
+    lg, tok = eng.prefill()
+    rows, sel = [lg[0].copy()], [int(tok[0])]
+    for _ in range(2):
+        lg, tok = eng.decode_step()
+        rows.append(lg[0].copy()); sel.append(int(tok[0]))
+    eng.close()
+    got = np.stack(rows)
+    d = float(np.abs(got - want[:3]).max())
+    print(f"qwen3-asr-0.6b {precision}: audio_hidden max|d| = {float(np.abs(got_ah - ah).max()):.2e} (scale {float(np.abs(ah).max()):.1f}); "
+          f"logits max|d| over prefill + 2 steps = {d:.2e} (std {want.std():.2f}); tokens {sel} vs {toks}")
+    assert d <= tol
+    top2 = np.sort(want[:3], axis=-1)[:, -2:]
+    safe = (top2[:, 1] - top2[:, 0]) > 2 * tol
+    assert np.array_equal(got.argmax(-1)[safe], want[:3].argmax(-1)[safe])
+    if precision == "f32":
+        assert sel == toks

@@ -2,7 +2,7 @@
 fp32 mode: features 1e-4, audio tower output 1e-3, teacher-forced logits 1e-3 (north-star tolerance; logits are O(8)),
 greedy token streams identical, through the device loop and through the script's call-by-call protocol.
 bf16 mode (tcgen05 GEMMs, fused masked attention, bf16 KV cache): audio tower output within 0.12 and logits within
-0.35 of the fp32 reference (8 mantissa bits through 2+2 layers and a 128-wide contraction; written here), arg-max equal
+0.15 of the fp32 reference (8 mantissa bits through 2+2 layers; measured 0.06; written here), arg-max equal
 wherever the reference top-2 margin exceeds twice that."""
 from pathlib import Path
 
@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 GOLD = sorted((Path(__file__).parent / "golden").glob("qwen_tiny_case*.npz"))
 D = qw.QWEN_TINY_TEST
 MAX_SAMPLES = 200000
-BF16_LOGIT_TOL = 0.35
+BF16_LOGIT_TOL = 0.15
 
 
 def _engine(seed, precision, max_batch=1, max_samples=MAX_SAMPLES):
