@@ -421,46 +421,234 @@ qwen_attn_decode_kernel(const float* __restrict__ qkv /*[B][(H+2KH)*DH]*/, const
   }
 }
 
+// ---- decode-step attention for the bf16 cache, split over the keys: grid (utterance x query head, S key ranges of at
+//      most 128 keys).  Every cache row a CTA needs is requested into registers at kernel entry -- K: one key per thread,
+//      V: keys strided over the 8 warps with lanes on head dims -- while warps 0-2 normalise / rotate q and the new k, v,
+//      so the whole step costs one memory round trip; the CTA that finishes last (ticket counter) merges the S partial
+//      (max, sum, unnormalised output) triples into the context row ----
+constexpr int kSplitKeys = 128;
+template <int DH>
+__global__ void __launch_bounds__(256)
+qwen_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ g, const float* __restrict__ cosT,
+                       const float* __restrict__ sinT, float eps, bf16* __restrict__ kc, bf16* __restrict__ vc, int64_t cache_layer_off,
+                       int H, int KH, int max_seq, const DecState* __restrict__ state, float* __restrict__ part /*[B*H][S][DH+2]*/,
+                       int* __restrict__ counter /*[B*H]*/, float* __restrict__ ctx) {
+  constexpr int M = DH / 32, half = DH / 2, EPL = DH / 32, VK = kSplitKeys / 8;
+  __shared__ float qs[DH], kn[DH], vn[DH], sc[kSplitKeys], red[8], pw[8][DH];
+  __shared__ int s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+  const int S = gridDim.y, sp = blockIdx.y;
+  const int pos = state->kv_len, n_keys = pos + 1;
+  const int per = (n_keys + S - 1) / S;
+  const int lo = sp * per, hi = min(n_keys, lo + per);
+  const int kh = h / (H / KH);
+  const int NHD = H + 2 * KH;
+  bf16* K = kc + cache_layer_off + ((int64_t)b * KH + kh) * max_seq * DH;
+  bf16* V = vc + cache_layer_off + ((int64_t)b * KH + kh) * max_seq * DH;
+  // ---- every cache load of this CTA, up front ----
+  uint4 kreg[DH / 8];
+  const int jk = lo + threadIdx.x;
+  const bool k_cached = threadIdx.x < kSplitKeys && jk < hi && jk != pos;
+  if (k_cached) {
+    const uint4* kr = reinterpret_cast<const uint4*>(K + (int64_t)jk * DH);
+#pragma unroll
+    for (int c = 0; c < DH / 8; ++c) kreg[c] = kr[c];
+  }
+  uint32_t vreg[VK][EPL / 2];
+#pragma unroll
+  for (int i = 0; i < VK; ++i) {
+    const int j = lo + warp + 8 * i;
+    if (j < hi && j != pos) {
+      const uint32_t* vr = reinterpret_cast<const uint32_t*>(V + (int64_t)j * DH + lane * EPL);
+#pragma unroll
+      for (int e = 0; e < EPL / 2; ++e) vreg[i][e] = vr[e];
+    }
+  }
+  if (warp < 3) {
+    const int head = warp == 0 ? h : (warp == 1 ? H + kh : H + KH + kh);
+    const float* src = qkv + ((int64_t)b * NHD + head) * DH;
+    float v[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) v[m] = src[lane + 32 * m];
+    if (warp < 2) {
+      float ss = 0.f;
+#pragma unroll
+      for (int m = 0; m < M; ++m) ss += v[m] * v[m];
+      const float r = rsqrtf(warp_sum(ss) / (float)DH + eps);
+      const float* gg = g + (warp == 0 ? 0 : DH);
+#pragma unroll
+      for (int m = 0; m < M; ++m) v[m] *= r * gg[lane + 32 * m];
+#pragma unroll
+      for (int m = 0; m < M / 2; ++m) {
+        const int j = lane + 32 * m;
+        const float c = cosT[(int64_t)pos * half + j], sn = sinT[(int64_t)pos * half + j];
+        const float a = v[m], bb = v[m + M / 2];
+        v[m] = a * c - bb * sn;
+        v[m + M / 2] = bb * c + a * sn;
+      }
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) qs[lane + 32 * m] = v[m];
+    } else {
+      bf16* dst = (warp == 1 ? K : V) + (int64_t)pos * DH;
+      float* keep = warp == 1 ? kn : vn;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const bf16 rv = __float2bfloat16_rn(v[m]);
+        if (sp == 0) dst[lane + 32 * m] = rv;          // one writer per (kv head, query head); duplicates across the group are identical
+        keep[lane + 32 * m] = __bfloat162float(rv);     // what later steps will read back from the cache
+      }
+    }
+  }
+  __syncthreads();
+  float s = -INFINITY;
+  if (threadIdx.x < kSplitKeys && jk < hi) {
+    s = 0.f;
+    if (jk == pos) {
+#pragma unroll 8
+      for (int c = 0; c < DH; ++c) s = fmaf(kn[c], qs[c], s);
+    } else {
+#pragma unroll
+      for (int c = 0; c < DH / 8; ++c) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kreg[c]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h2[e]);
+          s = fmaf(f.x, qs[c * 8 + 2 * e], s);
+          s = fmaf(f.y, qs[c * 8 + 2 * e + 1], s);
+        }
+      }
+    }
+  }
+  float mx = warp_max(s);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float p = 0.f;
+  if (threadIdx.x < kSplitKeys && jk < hi) { p = expf(s - mx); sc[threadIdx.x] = p; }
+  float sum = warp_sum(p);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  float acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+#pragma unroll
+  for (int i = 0; i < VK; ++i) {
+    const int j = lo + warp + 8 * i;
+    if (j < hi) {
+      const float pj = sc[j - lo];
+      if (j == pos) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pj, vn[lane * EPL + e], acc[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL / 2; ++e) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vreg[i][e]));
+          acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
+          acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) pw[warp][lane * EPL + e] = acc[e];
+  __syncthreads();
+  float* mine = part + ((int64_t)bh * S + sp) * (DH + 2);
+  if (threadIdx.x < DH) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) o += pw[w][threadIdx.x];
+    mine[threadIdx.x] = o;
+  }
+  if (threadIdx.x == 0) { mine[DH] = mx; mine[DH + 1] = sum; }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counter[bh], 1) == S - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x < DH) {
+      const float* pb = part + (int64_t)bh * S * (DH + 2);
+      float Mx = -INFINITY;
+      for (int q = 0; q < S; ++q) Mx = fmaxf(Mx, __ldcg(pb + q * (DH + 2) + DH));
+      float num = 0.f, den = 0.f;
+      for (int q = 0; q < S; ++q) {
+        const float wq = expf(__ldcg(pb + q * (DH + 2) + DH) - Mx);
+        num = fmaf(wq, __ldcg(pb + q * (DH + 2) + threadIdx.x), num);
+        den = fmaf(wq, __ldcg(pb + q * (DH + 2) + DH + 1), den);
+      }
+      ctx[(int64_t)bh * DH + threadIdx.x] = num / den;
+    }
+    if (threadIdx.x == 0) counter[bh] = 0;             // ready for the next layer / graph replay
+  }
+}
+
 // ---- weight-streaming GEMV for a decode step: out[r][n] = (rms? rstd[r] : 1) * sum_k W[n][k] * x'[r][k] (+ residual), with
-//      x' = x or silu(x[:K]) * x[K:2K] (SwiGLU of the fused gate_up rows).  KS warps share one output column (split K) so
-//      narrow layers still fill the machine; a warp's first weight chunks are requested before the activations are
-//      staged, the RMS statistics ride along with the staging pass and scale the finished dot products ----
+//      x' = x or silu(x[:K]) * x[K:2K] (SwiGLU of the fused gate_up rows).  A layer is a few MB, so the kernel is built to
+//      have the whole matrix in flight at once: a warp owns NC output columns and 1/KS of their K range (at most four
+//      256-wide chunks), i.e. up to 8 outstanding 16-byte loads per thread, requested as raw registers BEFORE the
+//      activations are staged; the RMS statistics ride along with the staging pass and scale the finished dot products.
+//      Wide layers (the vocabulary head) loop over column passes with the next pass's loads issued ahead of the math ----
 struct QGemvArgs {
   const float* x; int64_t ldx; int rms; float eps; int swiglu;
   const void* W; const float* residual; int64_t ldr; float* out; int64_t ldo;
   int rows, N, K;
 };
 constexpr int kGemvRows = 4;
-template <typename WT> struct W8;
-template <> struct W8<bf16> {
-  static __device__ __forceinline__ void load(const bf16* p, float* o) { KVec<bf16>::load(p, o); }
+constexpr int kGemvCH = 4;                       // 256-wide k chunks per warp (K <= KS * 1024)
+template <typename WT> struct WRaw;
+template <> struct WRaw<bf16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float* o) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
 };
-template <> struct W8<float> {
-  static __device__ __forceinline__ void load(const float* p, float* o) { KVec<float>::load(p, o); KVec<float>::load(p + 4, o + 4); }
+template <> struct WRaw<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+  __device__ __forceinline__ void get(float* o) const { o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w; }
 };
 
-template <typename WT, int KS>
-__global__ void __launch_bounds__(256)
+template <typename WT, int KS, int NC>
+__global__ void __launch_bounds__(256, 2)
 qwen_gemv_kernel(QGemvArgs a) {
   extern __shared__ float gx[];                  // [kGemvRows][K]
   __shared__ float red[8][kGemvRows];
-  __shared__ float psum[8][kGemvRows];
-  constexpr int CPB = 8 / KS;                    // output columns per CTA pass
-  constexpr int PF = 4;                          // weight chunks (256 k each) requested ahead of the staging pass
+  __shared__ float psum[8][NC][kGemvRows];
+  constexpr int CPB = (8 / KS) * NC;             // output columns per CTA pass
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ks = warp % KS, cw = warp / KS;
-  const int K = a.K;
+  const int K = a.K, N = a.N;
   const WT* W = reinterpret_cast<const WT*>(a.W);
   const int k0 = (ks * 32 + lane) * 8, kstep = KS * 256;
-  int col = blockIdx.x * CPB + cw;
-  float wpre[PF][8];
-  if (col < a.N) {
+  const int n_pass = (N + CPB - 1) / CPB;
+  WRaw<WT> cur[NC][kGemvCH], nxt[NC][kGemvCH];
+  auto fetch = [&](WRaw<WT> (&buf)[NC][kGemvCH], int pass) {
+    const int c0 = pass * CPB + cw * NC;
 #pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      const int k = k0 + i * kstep;
-      if (k < K) W8<WT>::load(W + (int64_t)col * K + k, wpre[i]);
+    for (int j = 0; j < NC; ++j) {
+      if (pass < n_pass && c0 + j < N) {
+        const WT* wr = W + (int64_t)(c0 + j) * K;
+#pragma unroll
+        for (int i = 0; i < kGemvCH; ++i) {
+          const int k = k0 + i * kstep;
+          if (k < K) buf[j][i].load(wr + k);
+        }
+      }
     }
-  }
+  };
+  fetch(cur, blockIdx.x);
   for (int r0 = 0; r0 < a.rows; r0 += kGemvRows) {
     const int nr = min(kGemvRows, a.rows - r0);
     __syncthreads();
@@ -498,70 +686,86 @@ qwen_gemv_kernel(QGemvArgs a) {
         rstd[r] = rsqrtf(t / (float)K + a.eps);
       }
     }
-    bool first = (r0 == 0);
-    for (int c = blockIdx.x * CPB + cw; c - cw < a.N; c += gridDim.x * CPB) {      // every warp of the CTA runs the same trip count
-      float acc[kGemvRows];
+    if (r0 > 0) fetch(cur, blockIdx.x);                              // batches beyond four rows walk the matrix again (L2)
+    for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+      fetch(nxt, pass + gridDim.x);                                   // next pass's loads are in flight during this pass's math
+      float acc[NC][kGemvRows];
 #pragma unroll
-      for (int r = 0; r < kGemvRows; ++r) acc[r] = 0.f;
-      if (c < a.N) {
-        const WT* wr = W + (int64_t)c * K;
-        auto fma8 = [&](const float* w, int k) {
+      for (int j = 0; j < NC; ++j)
+#pragma unroll
+        for (int r = 0; r < kGemvRows; ++r) acc[j][r] = 0.f;
+      const int c0 = pass * CPB + cw * NC;
+#pragma unroll
+      for (int i = 0; i < kGemvCH; ++i) {
+        const int k = k0 + i * kstep;
+        if (k < K) {
+          float4 x0[kGemvRows], x1[kGemvRows];
 #pragma unroll
           for (int r = 0; r < kGemvRows; ++r) {
             if (r < nr) {
-              const float4 x0 = *reinterpret_cast<const float4*>(gx + r * K + k);
-              const float4 x1 = *reinterpret_cast<const float4*>(gx + r * K + k + 4);
-              acc[r] = fmaf(w[0], x0.x, acc[r]); acc[r] = fmaf(w[1], x0.y, acc[r]);
-              acc[r] = fmaf(w[2], x0.z, acc[r]); acc[r] = fmaf(w[3], x0.w, acc[r]);
-              acc[r] = fmaf(w[4], x1.x, acc[r]); acc[r] = fmaf(w[5], x1.y, acc[r]);
-              acc[r] = fmaf(w[6], x1.z, acc[r]); acc[r] = fmaf(w[7], x1.w, acc[r]);
+              x0[r] = *reinterpret_cast<const float4*>(gx + r * K + k);
+              x1[r] = *reinterpret_cast<const float4*>(gx + r * K + k + 4);
             }
           }
-        };
-        int kb = k0;
-        if (first) {
 #pragma unroll
-          for (int i = 0; i < PF; ++i) {
-            const int k = k0 + i * kstep;
-            if (k < K) fma8(wpre[i], k);
+          for (int j = 0; j < NC; ++j) {
+            if (c0 + j < N) {
+              float w[8];
+              cur[j][i].get(w);
+#pragma unroll
+              for (int r = 0; r < kGemvRows; ++r) {
+                if (r < nr) {
+                  float t = acc[j][r];
+                  t = fmaf(w[0], x0[r].x, t); t = fmaf(w[1], x0[r].y, t); t = fmaf(w[2], x0[r].z, t); t = fmaf(w[3], x0[r].w, t);
+                  t = fmaf(w[4], x1[r].x, t); t = fmaf(w[5], x1[r].y, t); t = fmaf(w[6], x1[r].z, t); t = fmaf(w[7], x1[r].w, t);
+                  acc[j][r] = t;
+                }
+              }
+            }
           }
-          kb = k0 + PF * kstep;
-        }
-#pragma unroll 4
-        for (int k = kb; k < K; k += kstep) {
-          float w[8];
-          W8<WT>::load(wr + k, w);
-          fma8(w, k);
         }
       }
-      first = false;
 #pragma unroll
-      for (int r = 0; r < kGemvRows; ++r) acc[r] = warp_sum(acc[r]);
+      for (int j = 0; j < NC; ++j)
+#pragma unroll
+        for (int r = 0; r < kGemvRows; ++r) acc[j][r] = warp_sum(acc[j][r]);
       if (KS > 1) {
         if (lane == 0) {
 #pragma unroll
-          for (int r = 0; r < kGemvRows; ++r) psum[warp][r] = acc[r];
+          for (int j = 0; j < NC; ++j)
+#pragma unroll
+            for (int r = 0; r < kGemvRows; ++r) psum[warp][j][r] = acc[j][r];
         }
         __syncthreads();
       }
-      if (ks == 0 && c < a.N && lane < nr) {
-        float v = 0.f;
-        if (KS > 1) {
+      if (ks == 0 && lane < NC * kGemvRows) {
+        const int j = lane / kGemvRows, r = lane - j * kGemvRows;
+        const int c = c0 + j;
+        if (r < nr && c < N) {
+          float v = 0.f;
+          if (KS > 1) {
 #pragma unroll
-          for (int q = 0; q < KS; ++q) v += psum[cw * KS + q][lane];
-        } else {
+            for (int q = 0; q < KS; ++q) v += psum[cw * KS + q][j][r];
+          } else {
 #pragma unroll
-          for (int r = 0; r < kGemvRows; ++r) if (lane == r) v = acc[r];
+            for (int jj = 0; jj < NC; ++jj)
+#pragma unroll
+              for (int rr = 0; rr < kGemvRows; ++rr) if (jj == j && rr == r) v = acc[jj][rr];
+          }
+          float rs = 1.f;
+#pragma unroll
+          for (int rr = 0; rr < kGemvRows; ++rr) if (rr == r) rs = rstd[rr];
+          v *= rs;
+          const int row = r0 + r;
+          if (a.residual) v += a.residual[(int64_t)row * a.ldr + c];
+          a.out[(int64_t)row * a.ldo + c] = v;
         }
-        float rs = 1.f;
-#pragma unroll
-        for (int r = 0; r < kGemvRows; ++r) if (lane == r) rs = rstd[r];
-        v *= rs;
-        const int row = r0 + lane;
-        if (a.residual) v += a.residual[(int64_t)row * a.ldr + c];
-        a.out[(int64_t)row * a.ldo + c] = v;
       }
       if (KS > 1) __syncthreads();
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+#pragma unroll
+        for (int i = 0; i < kGemvCH; ++i) cur[j][i] = nxt[j][i];
     }
   }
 }
@@ -660,7 +864,8 @@ struct b200asr_qwen {
   DecState* dstate = nullptr;
   int *cur_token = nullptr, *tokens = nullptr, *n_gen = nullptr, *finished = nullptr, *save_id = nullptr, *n_save = nullptr;
   cudaGraphExec_t step_graph = nullptr; int graph_B = -1, graph_limit = -1; int64_t graph_nodes = 0; bool use_graph = true;
-  bool use_attn_tc = true;
+  bool use_attn_tc = true, use_attn_split = true;
+  float* att_part = nullptr; int* att_counter = nullptr;
   int* h_pinned = nullptr;
 
   int fail(int code, const std::string& m) { err = m; return code; }
@@ -832,7 +1037,10 @@ int qwen_attention_launch(b200asr_qwen* e, int layer, int rows, int n_new, bool 
   const float *cosT = QWF(e, "rope_cos"), *sinT = QWF(e, "rope_sin");
   if (gemv) {        // one fused launch: QK-norm + RoPE + cache append + attention
     const size_t dsmem = (size_t)(3 * DH + c.max_seq_len + (kAttDecThreads / 32) * DH) * sizeof(float);
-    if (ad == kBF16) qwen_attn_decode_kernel<bf16, DH><<<rows * H, kAttDecThreads, dsmem, e->st>>>(e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, e->dstate, (float*)e->actx);
+    const int S = (c.max_seq_len + kSplitKeys - 1) / kSplitKeys;
+    if (ad == kBF16 && e->use_attn_split && rows * H * S <= 2 * e->num_sms) {      // larger batches already fill the machine with one CTA per head
+      qwen_attn_split_kernel<DH><<<dim3(rows * H, S), 256, 0, e->st>>>(e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, e->dstate, e->att_part, e->att_counter, (float*)e->actx);
+    } else if (ad == kBF16) qwen_attn_decode_kernel<bf16, DH><<<rows * H, kAttDecThreads, dsmem, e->st>>>(e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, e->dstate, (float*)e->actx);
     else qwen_attn_decode_kernel<float, DH><<<rows * H, kAttDecThreads, dsmem, e->st>>>(e->qkvf, g, cosT, sinT, c.rms_eps, (float*)e->kc, (float*)e->vc, layer_off, H, KH, c.max_seq_len, e->dstate, (float*)e->actx);
     QKL(cudaGetLastError());
     return B200ASR_OK;
@@ -858,23 +1066,24 @@ cudaError_t qwen_gemv_launch(const QGemvArgs& a, int num_sms, cudaStream_t st) {
   const size_t smem = (size_t)kGemvRows * a.K * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  // warps per output column: enough CTAs to cover the machine about four times, but at least one 256-wide k chunk per warp
+  // warps per column: a warp covers at most four 256-wide chunks of its columns' K range
   int ks = 1;
-  while (ks < 8 && (int64_t)a.N * ks / 8 < 4 * num_sms && a.K >= ks * 2 * 256) ks *= 2;
-  const int cpb = 8 / ks;
+  while (ks < 8 && a.K > ks * 256 * kGemvCH) ks *= 2;
+  if (a.K > 8 * 256 * kGemvCH) return cudaErrorInvalidValue;
+  const int cpb = (8 / ks) * 2;
   int grid = (a.N + cpb - 1) / cpb;
-  if (grid > num_sms * 8) grid = num_sms * 8;          // wide layers (the vocabulary head) loop over columns inside the CTA
+  if (grid > num_sms * 2) grid = num_sms * 2;          // wide layers loop over column passes inside the CTA
   switch (ks) {
-    case 1: qwen_gemv_kernel<WT, 1><<<grid, 256, smem, st>>>(a); break;
-    case 2: qwen_gemv_kernel<WT, 2><<<grid, 256, smem, st>>>(a); break;
-    case 4: qwen_gemv_kernel<WT, 4><<<grid, 256, smem, st>>>(a); break;
-    default: qwen_gemv_kernel<WT, 8><<<grid, 256, smem, st>>>(a); break;
+    case 1: qwen_gemv_kernel<WT, 1, 2><<<grid, 256, smem, st>>>(a); break;
+    case 2: qwen_gemv_kernel<WT, 2, 2><<<grid, 256, smem, st>>>(a); break;
+    case 4: qwen_gemv_kernel<WT, 4, 2><<<grid, 256, smem, st>>>(a); break;
+    default: qwen_gemv_kernel<WT, 8, 2><<<grid, 256, smem, st>>>(a); break;
   }
   return cudaGetLastError();
 }
@@ -1126,7 +1335,7 @@ void b200asr_qwen_destroy(b200asr_qwen* e) {
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
   void* bufs[] = {e->basis_t, e->fb_start, e->fb_len, e->stage_buf, e->d_stop, e->pcm, e->mel_raw, e->max_key, e->feat, e->c1, e->col, e->c2, e->c3,
                   e->stem, e->h, e->S, e->enc_out, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->win_valid, e->prompt_src, e->x, e->qkvf, e->q, e->gu,
-                  e->xl, e->logits, e->cand_val, e->cand_idx, e->xn, e->actx, e->mlp, e->kc, e->vc, e->dstate, e->cur_token, e->tokens, e->n_gen, e->finished, e->save_id, e->n_save};
+                  e->xl, e->logits, e->cand_val, e->cand_idx, e->att_part, e->att_counter, e->xn, e->actx, e->mlp, e->kc, e->vc, e->dstate, e->cur_token, e->tokens, e->n_gen, e->finished, e->save_id, e->n_save};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -1294,6 +1503,8 @@ int b200asr_qwen_finalize_weights(b200asr_qwen* e) {
     QRET(qwen_alloc(e, &e->logits, (size_t)B * c.vocab * 4));
     QRET(qwen_alloc(e, &e->cand_val, (size_t)B * kArgSlices * 4));
     QRET(qwen_alloc(e, &e->cand_idx, (size_t)B * kArgSlices * 4));
+    QRET(qwen_alloc(e, &e->att_part, (size_t)B * c.heads * ((c.max_seq_len + kSplitKeys - 1) / kSplitKeys) * (dh + 2) * 4));
+    QRET(qwen_alloc(e, &e->att_counter, (size_t)B * c.heads * 4));
     const size_t kv_bytes = (size_t)c.dec_layers * B * c.kv_heads * c.max_seq_len * dh * es;
     QRET(qwen_alloc(e, &e->kc, kv_bytes));
     QRET(qwen_alloc(e, &e->vc, kv_bytes));
@@ -1444,6 +1655,11 @@ int b200asr_qwen_set_option(b200asr_qwen* e, const char* key, int64_t value) {
   if (!e || !key) return B200ASR_E_INVALID;
   if (!strcmp(key, "graph")) { e->use_graph = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "attn_split")) {
+    e->use_attn_split = value != 0;
+    if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+    return B200ASR_OK;
+  }
   return e->fail(B200ASR_E_INVALID, std::string("unknown option ") + key);
 }
 void* b200asr_qwen_stream(b200asr_qwen* e) { return e ? (void*)e->st : nullptr; }

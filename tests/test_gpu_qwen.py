@@ -141,3 +141,22 @@ def test_qwen_float_pcm_and_errors():
     with pytest.raises(Exception, match="before"):
         eng.encode(g["pcm"]); eng.decode_step()
     eng.close()
+
+
+def test_qwen_bf16_split_attention_equals_single_cta():
+    """Key-split decode attention (register-resident cache rows, last-CTA merge) against the one-CTA-per-head kernel:
+    same bf16 cache, same fp32 math, only the summation order differs -> logits within 2e-3, greedy streams identical."""
+    g = dict(np.load(GOLD[1]))
+    q, l = g["query_ids"].tolist(), g["language_tail_ids"].tolist()
+    out = {}
+    for split in (1, 0):
+        eng = _engine(int(g["seed"]), "bf16")
+        eng.set_option("attn_split", split)
+        _, lg = _forced(eng, g["pcm"], q, l, g["forced_tokens"].tolist())
+        toks = eng.transcribe(g["pcm"], q, l, max_new=12)[0]
+        out[split] = (lg[0], toks)
+        eng.close()
+    d = float(np.abs(out[1][0] - out[0][0]).max())
+    print("split vs single-CTA decode attention max|dlogit| =", d)
+    assert d <= 2e-3
+    assert out[1][1] == out[0][1]
