@@ -218,6 +218,119 @@ __global__ void pad_rows_kernel(const float* __restrict__ src /*[B][Tn][D]*/, in
     dst[((int64_t)b * (Tn + 2 * pad) + t) * D + c] = from_f<T>((ts >= 0 && ts < Tn) ? src[((int64_t)b * Tn + ts) * D + c] : 0.f);
 }
 
+// ---- Paraformer decoder over all clips of a batch at once: the decoder rows of the clips are stacked (clip b owns rows
+//      seg_off[b] .. seg_off[b+1]), so every row-wise layer is one launch; the three kernels below are the pieces that
+//      need the clip boundaries ----
+__device__ __forceinline__ int seg_find(const int* __restrict__ seg_off, int B, int r) {
+  int b = 0;
+  while (b + 1 < B && r >= seg_off[b + 1]) ++b;
+  return b;
+}
+
+__global__ void para_gather_rows_kernel(const float* __restrict__ acoustic /*[B][T+1][D]*/, const int* __restrict__ n_tok,
+                                        const int* __restrict__ seg_off, int B, int T, int D, float* __restrict__ dst) {
+  const int r = blockIdx.x;
+  const int b = seg_find(seg_off, B, r), i = r - seg_off[b];
+  const float* src = acoustic + ((int64_t)b * (T + 1) + i) * D;
+  const bool live = i < n_tok[b];                     // zero-fire guard: a clip without fires decodes one zero row (:523-528)
+  for (int c = threadIdx.x; c < D; c += blockDim.x) dst[(int64_t)r * D + c] = live ? src[c] : 0.f;
+}
+
+__global__ void fsmn_seg_kernel(const float* __restrict__ in /*[rows][D]*/, const float* __restrict__ w /*[D][k]*/,
+                                const float* __restrict__ resid, const int* __restrict__ seg_off, int B, int D, int ksz,
+                                float* __restrict__ out) {
+  const int r = blockIdx.x;
+  const int b = seg_find(seg_off, B, r);
+  const int lo = seg_off[b], hi = seg_off[b + 1];
+  const int half = (ksz - 1) / 2;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < ksz; ++j) {
+      const int rr = r + j - half;
+      if (rr >= lo && rr < hi) acc = fmaf(w[c * ksz + j], in[(int64_t)rr * D + c], acc);
+    }
+    out[(int64_t)r * D + c] = acc + resid[(int64_t)r * D + c];
+  }
+}
+
+template <typename T> struct NVec;
+template <> struct NVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* o) { const float4 u = *reinterpret_cast<const float4*>(p); o[0] = u.x; o[1] = u.y; o[2] = u.z; o[3] = u.w; }
+};
+template <> struct NVec<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const bf16* p, float* o) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
+};
+
+// cross-attention of stacked decoder rows on their own clip's encoder memory: one warp per (row, head), keys on lanes
+// for the scores, head dims on lanes for P V; probabilities stay fp32
+template <typename T, int DH>
+__global__ void __launch_bounds__(128)
+para_cross_attn_kernel(const T* __restrict__ q /*[rows][D]*/, const T* __restrict__ kv /*[B*Tn][2D]: k | v*/, const int* __restrict__ seg_off,
+                       int B, int Tn, int H, int total, T* __restrict__ ctx /*[rows][D]*/) {
+  extern __shared__ float csm[];                 // per warp: q[DH] + scores[Tn]
+  constexpr int M = DH / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (item >= total) return;
+  const int row = item / H, h = item - row * H;
+  const int D = H * DH;
+  const int b = seg_find(seg_off, B, row);
+  float* qs = csm + warp * (DH + Tn);
+  float* sc = qs + DH;
+#pragma unroll
+  for (int m = 0; m < M; ++m) qs[lane + 32 * m] = to_f<T>(q[(int64_t)row * D + h * DH + lane + 32 * m]);
+  __syncwarp();
+  const T* K = kv + (int64_t)b * Tn * 2 * D + h * DH;
+  const T* V = K + D;
+  float mx = -INFINITY;
+  for (int j = lane; j < Tn; j += 32) {
+    const T* kr = K + (int64_t)j * 2 * D;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < DH; c += NVec<T>::N) {
+      float kk[NVec<T>::N];
+      NVec<T>::load(kr + c, kk);
+#pragma unroll
+      for (int e = 0; e < NVec<T>::N; ++e) s = fmaf(kk[e], qs[c + e], s);
+    }
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < Tn; j += 32) { const float p = expf(sc[j] - mx); sc[j] = p; sum += p; }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float acc[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < Tn; ++j) {
+    const float p = sc[j];
+    const T* vr = V + (int64_t)j * 2 * D;
+#pragma unroll
+    for (int m = 0; m < M; ++m) acc[m] = fmaf(p, to_f<T>(vr[lane + 32 * m]), acc[m]);
+  }
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int m = 0; m < M; ++m) ctx[(int64_t)row * D + h * DH + lane + 32 * m] = from_f<T>(acc[m] * inv);
+}
+
+__global__ void para_scatter_tokens_kernel(const int* __restrict__ ids, const int* __restrict__ seg_off, int B, int max_T, int rows,
+                                           int* __restrict__ tokens) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int b = seg_find(seg_off, B, r);
+  tokens[(int64_t)b * max_T + (r - seg_off[b])] = ids[r];
+}
+
 __global__ void nar_f32_to_bf16(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
@@ -252,7 +365,7 @@ struct b200asr_nar {
   // Paraformer
   void *enc_pad = nullptr, *conv_out = nullptr, *kvbuf = nullptr, *dq = nullptr;
   float *alphas = nullptr, *acoustic = nullptr, *dec = nullptr, *dx = nullptr, *f32buf = nullptr, *sa_in = nullptr, *dec_logits = nullptr;
-  int* n_tok = nullptr; int last_rows = 0;
+  int* n_tok = nullptr; int last_rows = 0; int* seg_off = nullptr; bool batched_decoder = true;
   // SenseVoice: the whole forward is one CUDA graph per (batch, n_samples) -- ~700 small launches are host-bound otherwise
   bool use_attn_tc = true;
   bool use_graph = true; cudaGraphExec_t graph = nullptr; int graph_B = -1, graph_N = -1, graph_dtype = -1; int64_t graph_nodes = 0;
@@ -472,7 +585,57 @@ int paraformer_decode_one(b200asr_nar* e, int b, int n_tok) {
   return B200ASR_OK;
 }
 
-int paraformer_forward(b200asr_nar* e) {
+// decoder of every clip in one pass (stacked rows; clip boundaries in e->seg_off)
+template <int DH>
+int paraformer_decode_all(b200asr_nar* e, int rows) {
+  const b200asr_nar_config& c = e->cfg;
+  const int D = c.d_model, H = c.n_heads, T = e->T, B = e->B, ad = e->act, Fd = c.dec_ffn;
+  para_gather_rows_kernel<<<rows, 128, 0, e->st>>>(e->acoustic, e->n_tok, e->seg_off, B, T, D, e->dec);
+  NKL(cudaGetLastError());
+  auto ffn = [&](const std::string& p, float* out) -> int {
+    NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+    {
+      GemmArgs g = nar_linear(e, e->dq, D, p + "w1.w", p + "w1.b", e->f32buf, Fd, kF32, rows, Fd, D);
+      g.act = kActRelu;
+      NRET(nar_gemm(e, g));
+    }
+    NKL(launch_layernorm(e->f32buf, Fd, nullptr, nullptr, e->ffn, ad, Fd, rows, Fd, c.dec_ln_eps, e->st));
+    return nar_gemm(e, nar_linear(e, e->ffn, Fd, p + "w2.w", p + "w2.b", out, D, kF32, rows, D, Fd));
+  };
+  const size_t smem = (size_t)4 * (DH + T) * sizeof(float);
+  for (int i = 0; i < c.dec_att_blocks; ++i) {
+    const std::string p = "dec" + std::to_string(i) + ".";
+    NRET(ffn(p, e->dx));                                                                        // x = FFN(dec)
+    NKL(launch_layernorm(e->dx, D, NWF(e, p + "norm2.g"), NWF(e, p + "norm2.b"), e->sa_in, kF32, D, rows, D, c.dec_ln_eps, e->st));
+    fsmn_seg_kernel<<<rows, 256, 0, e->st>>>(e->sa_in, NWF(e, p + "fsmn.w"), e->dec, e->seg_off, B, D, c.fsmn_kernel, e->dx);   // x = dec + fsmn(norm2(x))
+    NKL(cudaGetLastError());
+    NKL(launch_layernorm(e->dx, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+    NRET(nar_gemm(e, nar_linear(e, e->dq, D, p + "q.w", p + "q.b", e->qkv, D, ad, rows, D, D)));
+    NRET(nar_gemm(e, nar_linear(e, e->xhat, D, p + "kv.w", p + "kv.b", e->kvbuf, 2 * D, ad, B * T, 2 * D, D)));
+    const int total = rows * H;
+    if (ad == kBF16) para_cross_attn_kernel<bf16, DH><<<(total + 3) / 4, 128, smem, e->st>>>((const bf16*)e->qkv, (const bf16*)e->kvbuf, e->seg_off, B, T, H, total, (bf16*)e->ctx);
+    else para_cross_attn_kernel<float, DH><<<(total + 3) / 4, 128, smem, e->st>>>((const float*)e->qkv, (const float*)e->kvbuf, e->seg_off, B, T, H, total, (float*)e->ctx);
+    NKL(cudaGetLastError());
+    GemmArgs g = nar_linear(e, e->ctx, D, p + "cout.w", p + "cout.b", e->dec, D, kF32, rows, D, D);
+    g.residual = e->dx; g.ldr = D;
+    NRET(nar_gemm(e, g));                                                                       // dec = x + cross_out
+  }
+  for (int i = c.dec_att_blocks; i < c.dec_att_blocks + c.dec_ffn_blocks; ++i) {
+    NRET(ffn("dec" + std::to_string(i) + ".", e->dx));
+    NCK(cudaMemcpyAsync(e->dec, e->dx, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, e->st));
+  }
+  NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+  NRET(nar_gemm(e, nar_linear(e, e->dq, D, "out.w", "out.b", e->dec_logits, c.vocab, kF32, rows, c.vocab, D)));
+  row_argmax_kernel<<<(rows + 7) / 8, 256, 0, e->st>>>(e->dec_logits, rows, c.vocab, e->frame_ids);
+  NKL(cudaGetLastError());
+  para_scatter_tokens_kernel<<<(rows + 127) / 128, 128, 0, e->st>>>(e->frame_ids, e->seg_off, B, e->max_T, rows, e->tokens);
+  NKL(cudaGetLastError());
+  e->last_rows = rows;
+  return B200ASR_OK;
+}
+
+// front end + encoder + CIF up to the fire scan: fixed shapes per (batch, clip length), so it replays as one CUDA graph
+int paraformer_encoder(b200asr_nar* e) {
   const b200asr_nar_config& c = e->cfg;
   const int feat = c.n_mels * c.lfr_m, D = c.d_model, B = e->B, T = e->T, M = B * T, ad = e->act;
   NRET(nar_fbank(e));
@@ -501,28 +664,42 @@ int paraformer_forward(b200asr_nar* e) {
   NKL(cudaGetLastError());
   cif_scan_kernel<<<B, 256, (size_t)2 * (T + 1) * sizeof(float), e->st>>>(e->alphas, c.tail_threshold, e->enc_out, T, D, e->acoustic, e->n_tok);
   NKL(cudaGetLastError());
+  return B200ASR_OK;
+}
+
+int nar_graph_run(b200asr_nar* e, int (*fn)(b200asr_nar*));
+
+int paraformer_forward(b200asr_nar* e) {
+  const int B = e->B, T = e->T;
+  NRET(e->use_graph ? nar_graph_run(e, paraformer_encoder) : paraformer_encoder(e));
   // the token count sizes the decoder: one small device->host read (the reference graph has the same data-dependent shape)
   int* h_n = e->h_pinned;
   NCK(cudaMemcpyAsync(h_n, e->n_tok, (size_t)B * 4, cudaMemcpyDeviceToHost, e->st));
   NCK(cudaStreamSynchronize(e->st));
   std::vector<int> counts(h_n, h_n + B);
-  for (int b = 0; b < B; ++b) {
+  for (int b = 0; b < B; ++b)
     if (counts[b] > T + 1) return e->fail(B200ASR_E_CUDA, "CIF fired more tokens than frames");
-    NRET(paraformer_decode_one(e, b, counts[b]));
+  const int dh = e->cfg.d_model / e->cfg.n_heads;
+  if (e->batched_decoder && (dh == 64 || dh == 128)) {
+    int* h_off = e->h_pinned + B;
+    h_off[0] = 0;
+    for (int b = 0; b < B; ++b) h_off[b + 1] = h_off[b] + (counts[b] > 0 ? counts[b] : 1);
+    NCK(cudaMemcpyAsync(e->seg_off, h_off, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, e->st));
+    NRET(dh == 128 ? paraformer_decode_all<128>(e, h_off[B]) : paraformer_decode_all<64>(e, h_off[B]));
+  } else {
+    for (int b = 0; b < B; ++b) NRET(paraformer_decode_one(e, b, counts[b]));
   }
   NCK(cudaMemcpyAsync(e->lens, e->n_tok, (size_t)B * 4, cudaMemcpyDeviceToDevice, e->st));
   return B200ASR_OK;
 }
 
-int nar_forward(b200asr_nar* e) {
-  if (e->cfg.kind == B200ASR_NAR_PARAFORMER) return paraformer_forward(e);      // data-dependent decoder size: host read inside
-  if (!e->use_graph) return sensevoice_forward(e);
+int nar_graph_run(b200asr_nar* e, int (*fn)(b200asr_nar*)) {
   if (!e->graph || e->graph_B != e->B || e->graph_N != e->n_samples || e->graph_dtype != e->pcm_dtype) {
     if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
     cudaGraph_t g = nullptr;
     const int64_t before = e->launches;
     NCK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
-    const int r = sensevoice_forward(e);
+    const int r = fn(e);
     const cudaError_t ce = cudaStreamEndCapture(e->st, &g);
     e->graph_nodes = e->launches - before;
     e->launches = before;
@@ -536,6 +713,11 @@ int nar_forward(b200asr_nar* e) {
   NCK(cudaGraphLaunch(e->graph, e->st));
   e->launches += e->graph_nodes;
   return B200ASR_OK;
+}
+
+int nar_forward(b200asr_nar* e) {
+  if (e->cfg.kind == B200ASR_NAR_PARAFORMER) return paraformer_forward(e);      // data-dependent decoder size: host read inside
+  return e->use_graph ? nar_graph_run(e, sensevoice_forward) : sensevoice_forward(e);
 }
 
 }  // namespace
@@ -582,7 +764,7 @@ void b200asr_nar_destroy(b200asr_nar* e) {
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
   void* bufs[] = {e->basis_t, e->stage_buf, e->pcm, e->mel, e->feats, e->hidden, e->resid, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->S,
                   e->logits, e->enc_out, e->frame_ids, e->tokens, e->lens, e->lang, e->enc_pad, e->conv_out, e->kvbuf, e->dq, e->alphas,
-                  e->acoustic, e->dec, e->dx, e->f32buf, e->sa_in, e->dec_logits, e->n_tok};
+                  e->acoustic, e->dec, e->dx, e->f32buf, e->sa_in, e->dec_logits, e->n_tok, e->seg_off};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -738,15 +920,16 @@ int b200asr_nar_finalize_weights(b200asr_nar* e) {
       const int64_t pad = (c.cif_kernel - 1) / 2;
       NRET(nar_alloc(e, &e->enc_pad, (size_t)B * (Tm + 2 * pad) * D * es));
       NRET(nar_alloc(e, &e->conv_out, (size_t)M * D * es));
-      NRET(nar_alloc(e, &e->kvbuf, (size_t)Tm * 2 * D * es));
-      NRET(nar_alloc(e, &e->dq, (size_t)Tm * D * es));
+      NRET(nar_alloc(e, &e->kvbuf, (size_t)M * 2 * D * es));            // decoder buffers hold the stacked rows of the whole batch
+      NRET(nar_alloc(e, &e->dq, (size_t)M * D * es));
       NRET(nar_alloc(e, &e->alphas, (size_t)B * (Tm + 1) * 4));
       NRET(nar_alloc(e, &e->acoustic, (size_t)B * (Tm + 1) * D * 4));
-      NRET(nar_alloc(e, &e->dec, (size_t)Tm * D * 4));
-      NRET(nar_alloc(e, &e->dx, (size_t)Tm * D * 4));
-      NRET(nar_alloc(e, &e->sa_in, (size_t)Tm * D * 4));
-      NRET(nar_alloc(e, &e->f32buf, (size_t)Tm * c.dec_ffn * 4));
-      NRET(nar_alloc(e, &e->dec_logits, (size_t)Tm * c.vocab * 4));
+      NRET(nar_alloc(e, &e->dec, (size_t)M * D * 4));
+      NRET(nar_alloc(e, &e->dx, (size_t)M * D * 4));
+      NRET(nar_alloc(e, &e->sa_in, (size_t)M * D * 4));
+      NRET(nar_alloc(e, &e->f32buf, (size_t)M * c.dec_ffn * 4));
+      NRET(nar_alloc(e, &e->dec_logits, (size_t)M * c.vocab * 4));
+      NRET(nar_alloc(e, &e->seg_off, (size_t)(B + 1) * 4));
       NRET(nar_alloc(e, &e->n_tok, (size_t)B * 4));
     }
     NCK(cudaMallocHost(&e->h_pinned, (size_t)B * (Tm + 2) * 4 + 64));
@@ -856,6 +1039,7 @@ int64_t b200asr_nar_kernel_launches(const b200asr_nar* e) { return e ? e->launch
 int b200asr_nar_set_option(b200asr_nar* e, const char* key, int64_t value) {
   if (!e || !key) return B200ASR_E_INVALID;
   if (!strcmp(key, "graph")) { e->use_graph = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "batched_decoder")) { e->batched_decoder = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; } return B200ASR_OK; }
   return e->fail(B200ASR_E_INVALID, std::string("unknown option ") + key);
 }

@@ -64,3 +64,33 @@ def test_paraformer_bf16_and_batch():
         safe = (top2[:, 1] - top2[:, 0]) > 0.5
         assert np.array_equal(np.asarray(got[i])[safe], np.asarray(toks)[safe])
     eng.close()
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16"])
+def test_paraformer_batched_decoder_equals_per_clip(precision):
+    """The stacked-row decoder (one pass over all clips, segment-aware FSMN / cross-attention) against the per-clip
+    decoder of the same engine: fp32 same tokens and equal to the oracle clip by clip (ragged counts, silence = zero fires);
+    bf16 same token counts and at most 10 % of the ids differ (written here; random-weight logits have near-ties)."""
+    g = dict(np.load(GOLD[1]))
+    rng = np.random.default_rng(7)
+    clips = (rng.standard_normal((4, 52000)) * 2500).clip(-32768, 32767).astype(np.int16)
+    clips[2] = 0                                             # a silent clip: CIF may fire nothing -> the zero-fire guard row
+    clips[3, 20000:] //= 8
+    out = {}
+    for batched in (1, 0):
+        eng = _engine(int(g["seed"]), precision, max_batch=4)
+        eng.set_option("batched_decoder", batched)
+        out[batched] = (eng.run(clips), eng.kernel_launches)
+        eng.close()
+    if precision == "f32":
+        assert out[1][0] == out[0][0]
+    else:       # the stacked path keeps the attention probabilities in fp32 (the per-clip path rounds them to bf16): near-ties may flip
+        assert [len(t) for t in out[1][0]] == [len(t) for t in out[0][0]]
+        a, b = np.concatenate([np.asarray(t) for t in out[1][0]]), np.concatenate([np.asarray(t) for t in out[0][0]])
+        assert (a != b).mean() <= 0.1
+    assert out[1][1] < out[0][1]
+    print(precision, "tokens per clip", [len(t) for t in out[1][0]], "launches", out[1][1], "vs", out[0][1])
+    if precision == "f32":
+        fw = po.fold_weights(po.make_raw_weights(po.TINY_TEST, int(g["seed"])), po.TINY_TEST, D.lfr_frames(MAX_SAMPLES))
+        with torch.no_grad():
+            assert out[1][0] == [po.transcribe(clips[i], fw, po.TINY_TEST) for i in range(4)]
