@@ -248,7 +248,8 @@ int b200asr_qwen_transcribe_resident(b200asr_qwen* e, const int32_t* query_ids, 
 int b200asr_qwen_get_stage(b200asr_qwen* e, const char* name, float* out, int64_t capacity, int64_t* numel_out);
 int64_t b200asr_qwen_kernel_launches(const b200asr_qwen* e);
 /* options: "graph" (0/1, default 1): replay a decode step as one CUDA graph; "attn_tc" (0/1): fused tcgen05 encoder attention;
- * "attn_split" (0/1, default 1, bf16 cache): key-split decode attention with register-resident cache rows */
+ * "attn_split" (0/1, default 1, bf16 cache): key-split decode attention with register-resident cache rows;
+ * "pdl" (0/1, default 1): launch decode-step kernels as programmatic dependents (batches of 1-2 clips) */
 int b200asr_qwen_set_option(b200asr_qwen* e, const char* key, int64_t value);
 void* b200asr_qwen_stream(b200asr_qwen* e);
 

@@ -160,3 +160,27 @@ def test_qwen_bf16_split_attention_equals_single_cta():
     print("split vs single-CTA decode attention max|dlogit| =", d)
     assert d <= 2e-3
     assert out[1][1] == out[0][1]
+
+
+def test_qwen_programmatic_dependent_launch_is_transparent():
+    """Decode-step kernels launched as programmatic dependents (weight / cache requests before griddepcontrol.wait) give
+    bit-identical logits and tokens to plainly serialised launches, through the graph and through direct launches."""
+    g = dict(np.load(GOLD[1]))
+    q, l = g["query_ids"].tolist(), g["language_tail_ids"].tolist()
+    out = []
+    for pdl, graph in ((1, 1), (0, 1), (1, 0)):
+        eng = _engine(int(g["seed"]), "bf16")
+        eng.set_option("pdl", pdl)
+        eng.set_option("graph", graph)
+        eng.encode(g["pcm"], q, l)
+        lg, tok = eng.prefill()
+        rows = [lg[0].copy()]
+        for _ in range(6):
+            lg, tok = eng.decode_step()
+            rows.append(lg[0].copy())
+        toks = eng.transcribe(g["pcm"], q, l, max_new=20)[0]
+        out.append((np.stack(rows), toks))
+        eng.close()
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0])
+        assert o[1] == out[0][1]
