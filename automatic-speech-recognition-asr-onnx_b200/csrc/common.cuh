@@ -28,6 +28,7 @@ struct GemmArgs {
   int act = kActNone;
   int M = 0, N = 0, K = 0;
   int batch = 1, batch_inner = 1;
+  int pdl = 0;                        // gemm_tc only: launch as a programmatic dependent (B must be a weight matrix no kernel writes)
 };
 
 // ---- device helpers ---------------------------------------------------------
@@ -48,6 +49,10 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
   return 0.5f * x * (1.0f + tanhf(u));
 }
+
+// Programmatic dependent launch (no-ops for a kernel launched without the attribute)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -78,6 +78,7 @@ struct b200asr_engine {
   bool mega_timing = false; unsigned long long* timing = nullptr; static constexpr int kTimingCap = 16384;
   // streaming decode kernel (decoder_ring.cu)
   bool use_attn_tc = true;
+  bool use_pdl = true;
   // sampling head (TOPK_TOPP_SAMPLING); temperature <= 0 = argmax heads
   float samp_temperature = 0.f; int samp_top_k = 10; float samp_top_p = 0.95f; float samp_rep = 1.0f;
   unsigned long long samp_seed = 0; float* samp_noise = nullptr; int samp_noise_rows = 0, samp_noise_ld = 0;
@@ -187,6 +188,7 @@ GemmArgs linear_args(b200asr_engine* e, const void* A, int64_t lda, const std::s
   g.C = C; g.ldc = ldc; g.c_dtype = c_dtype;
   g.bias = bname.empty() ? nullptr : WF(e, bname);
   g.M = M; g.N = N; g.K = K;
+  g.pdl = e->use_pdl ? 1 : 0;          // B is a weight matrix: the tcgen05 GEMM may start under its predecessor's tail
   return g;
 }
 
@@ -622,6 +624,7 @@ int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "mega_timing")) { e->mega_timing = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "mega")) { e->use_mega = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "pdl")) { e->use_pdl = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring")) { e->use_ring = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_tc")) { e->ring_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_debug")) { e->ring_debug = (int)value; return B200ASR_OK; }

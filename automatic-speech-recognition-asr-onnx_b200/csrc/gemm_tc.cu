@@ -36,6 +36,7 @@ struct EpiArgs {
   int tiles_m, tiles_n;
   int a_batched, b_batched;
   int64_t sBias;
+  int pdl_b_early;                // launched as a programmatic dependent and B is a device-constant weight matrix
 };
 
 using namespace ptx;
@@ -83,23 +84,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();                     // epilogue reads bias / residual and writes C; the producer waits after its B requests
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      // Programmatic dependent launch: when B is a weight matrix (never written on the device), the first ring pass of B
+      // tiles is requested before waiting for the kernel that produces A -- the ring slots start out empty
+      int pre = 0;
+      if (e.pdl_b_early && blockIdx.x < num_tiles) {
+        const int z = blockIdx.x / tiles_per_batch;
+        const int rem = blockIdx.x - z * tiles_per_batch;
+        const int n0 = (rem / e.tiles_m) * BN;
+        pre = num_kb < kStages ? num_kb : kStages;
+        for (int kb = 0; kb < pre; ++kb) {
+          mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
+          tma_load_3d(smem + (size_t)kb * Cfg::kStageBytes + kStageBytesA, &tmB, kb * BK, n0, e.b_batched ? z : 0, &full_bar[kb]);
+        }
+      }
+      pdl_wait();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int z = tile / tiles_per_batch;
         const int rem = tile - z * tiles_per_batch;
         const int nt = rem / e.tiles_m, mt = rem - nt * e.tiles_m;
         const int m0 = mt * BM, n0 = nt * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, "gemm_tc");
           uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kStageBytesA;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_3d(sa, &tmA, kb * BK, m0, e.a_batched ? z : 0, &full_bar[stage]);
-          tma_load_3d(sb, &tmB, kb * BK, n0, e.b_batched ? z : 0, &full_bar[stage]);
+          if (tile == (int)blockIdx.x && kb < pre) {
+            tma_load_3d(sa, &tmA, kb * BK, m0, e.a_batched ? z : 0, &full_bar[stage]);
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1, "gemm_tc");
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_3d(sa, &tmA, kb * BK, m0, e.a_batched ? z : 0, &full_bar[stage]);
+            tma_load_3d(sb, &tmB, kb * BK, n0, e.b_batched ? z : 0, &full_bar[stage]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -349,8 +370,14 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t st, st
   e.tiles_m = (g.M + BM - 1) / BM; e.tiles_n = (g.N + BN - 1) / BN; e.a_batched = a_batched ? 1 : 0; e.b_batched = b_batched ? 1 : 0; e.sBias = g.sBias;
   const int tiles = e.tiles_m * e.tiles_n * g.batch;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<BN><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, e);
-  return cudaGetLastError();
+  e.pdl_b_early = g.pdl ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, tmA, tmB, e);
 }
 
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t st, std::string* err) {

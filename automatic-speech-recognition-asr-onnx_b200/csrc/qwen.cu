@@ -33,9 +33,6 @@ constexpr int kChunkTok = 13;      // tokens a full chunk yields after three str
 // Programmatic dependent launch: a decode-step kernel is allowed to start while its predecessor drains; everything that
 // does not depend on the predecessor (weight / cache-row requests) is issued first, then pdl_wait() orders the rest.
 // Both are no-ops for a kernel launched without the attribute.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -939,6 +936,7 @@ GemmArgs qwen_linear(b200asr_qwen* e, const void* A, int64_t lda, const std::str
   g.C = C; g.ldc = ldc; g.c_dtype = c_dtype;
   g.bias = bn.empty() ? nullptr : QWF(e, bn);
   g.M = M; g.N = N; g.K = K;
+  g.pdl = e->use_pdl ? 1 : 0;          // B is a weight matrix: the tcgen05 GEMM may start under its predecessor's tail
   return g;
 }
 

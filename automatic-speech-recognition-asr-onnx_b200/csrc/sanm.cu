@@ -367,7 +367,7 @@ struct b200asr_nar {
   float *alphas = nullptr, *acoustic = nullptr, *dec = nullptr, *dx = nullptr, *f32buf = nullptr, *sa_in = nullptr, *dec_logits = nullptr;
   int* n_tok = nullptr; int last_rows = 0; int* seg_off = nullptr; bool batched_decoder = true;
   // SenseVoice: the whole forward is one CUDA graph per (batch, n_samples) -- ~700 small launches are host-bound otherwise
-  bool use_attn_tc = true;
+  bool use_attn_tc = true, use_pdl = true;
   bool use_graph = true; cudaGraphExec_t graph = nullptr; int graph_B = -1, graph_N = -1, graph_dtype = -1; int64_t graph_nodes = 0;
   int* h_pinned = nullptr;
   int max_frames = 0, max_T = 0;
@@ -419,6 +419,7 @@ GemmArgs nar_linear(b200asr_nar* e, const void* A, int64_t lda, const std::strin
   g.C = C; g.ldc = ldc; g.c_dtype = c_dtype;
   g.bias = bn.empty() ? nullptr : NWF(e, bn);
   g.M = M; g.N = N; g.K = K;
+  g.pdl = e->use_pdl ? 1 : 0;          // B is a weight matrix: the tcgen05 GEMM may start under its predecessor's tail
   return g;
 }
 
@@ -1040,6 +1041,7 @@ int b200asr_nar_set_option(b200asr_nar* e, const char* key, int64_t value) {
   if (!e || !key) return B200ASR_E_INVALID;
   if (!strcmp(key, "graph")) { e->use_graph = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "batched_decoder")) { e->batched_decoder = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "pdl")) { e->use_pdl = value != 0; if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; } return B200ASR_OK; }
   if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; } return B200ASR_OK; }
   return e->fail(B200ASR_E_INVALID, std::string("unknown option ") + key);
 }

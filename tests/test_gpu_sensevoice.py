@@ -123,3 +123,18 @@ def test_sensevoice_bf16_head128_fused_attention(n_samples):
     do = float(np.abs(outs[0][0][1] - ref).max())
     print("vs fp32 oracle max|d| =", do)
     assert do <= 0.12
+
+
+def test_sensevoice_pdl_gemm_launch_is_transparent():
+    g = dict(np.load(GOLD[1]))
+    outs = []
+    for pdl, graph in ((1, 1), (0, 1), (1, 0)):
+        eng = _engine(int(g["seed"]), "bf16")
+        eng.set_option("pdl", pdl)
+        eng.set_option("graph", graph)
+        toks = eng.run(g["pcm"], int(g["language_idx"]))[0]
+        T = g["feats"].shape[0]
+        outs.append((eng.get_stage("logits", T * D.vocab).copy(), toks))
+        eng.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and o[1] == outs[0][1]

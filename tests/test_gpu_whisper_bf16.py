@@ -88,3 +88,20 @@ def test_batch_equals_single(precision):
     if precision == "f32":
         assert tb == ts
     eng.close()
+
+
+def test_pdl_gemm_launch_is_transparent():
+    """tcgen05 GEMMs launched as programmatic dependents (weight tiles requested before griddepcontrol.wait) must give
+    bit-identical encoder outputs and logits to plainly serialised launches."""
+    g, raw, tensors = load_case(GOLD[2])
+    outs = []
+    for pdl in (1, 0):
+        eng = make_engine(tensors, "bf16", tc=True)
+        eng.set_option("pdl", pdl)
+        lg = _run(eng, g["pcm"], g["prompt"], g["forced_tokens"].tolist())
+        T = (len(g["pcm"]) // 160 + 1) // 2
+        enc = eng.get_stage("enc_out", T * 256).copy()
+        outs.append((lg, enc))
+        eng.close()
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[1][0])
