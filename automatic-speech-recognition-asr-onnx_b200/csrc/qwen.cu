@@ -836,6 +836,23 @@ __global__ void qwen_f32_to_bf16(const float* __restrict__ in, bf16* __restrict_
     out[i] = __float2bfloat16_rn(in[i]);
 }
 
+// ---- penalty-greedy (the script's default strategy): logits of the last `range` selected ids *= value before the
+//      arg-max; gather-then-scatter semantics, a repeated id is scaled once (APPLY_PENALTY, Export_Qwen_ASR.py:669-694,1403-1415) ----
+__global__ void qwen_penalty_kernel(float* __restrict__ logits, int vocab, const int* __restrict__ save_id, int save_ld,
+                                    const int* __restrict__ n_save, int range, float value) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  float* lg = logits + (int64_t)b * vocab;
+  const int ns = n_save[b];
+  const int first = ns - range > 0 ? ns - range : 0;
+  for (int j = first; j < ns; ++j) {
+    const int id = save_id[(int64_t)b * save_ld + j];
+    bool seen = false;
+    for (int k = first; k < j; ++k) seen |= (save_id[(int64_t)b * save_ld + k] == id);
+    if (!seen && id >= 0 && id < vocab) lg[id] *= value;
+  }
+}
+
 __global__ void qwen_reset_kernel(DecState* st, int* n_gen, int* finished, int* n_save, int batch) {
   if (threadIdx.x == 0) { st->kv_len = 0; st->step = 0; st->all_done = 0; st->pad = 0; }
   if (threadIdx.x < batch) { n_gen[threadIdx.x] = 0; finished[threadIdx.x] = 0; n_save[threadIdx.x] = 0; }
@@ -885,6 +902,7 @@ struct b200asr_qwen {
   int *cur_token = nullptr, *tokens = nullptr, *n_gen = nullptr, *finished = nullptr, *save_id = nullptr, *n_save = nullptr;
   cudaGraphExec_t step_graph = nullptr; int graph_B = -1, graph_limit = -1; int64_t graph_nodes = 0; bool use_graph = true;
   bool use_attn_tc = true, use_attn_split = true, use_pdl = true;
+  float repeat_penalty = 1.0f; int penalty_range = 10;
   float* att_part = nullptr; int* att_counter = nullptr;
   int* h_pinned = nullptr;
 
@@ -1164,6 +1182,10 @@ int qwen_decoder(b200asr_qwen* e, int n_new) {
   QKL(cudaGetLastError());
   const std::string head = e->w.count("lm_head.w") ? "lm_head.w" : "embed.w";
   QRET(qwen_gemv(e, e->xl, Hd, false, false, head, nullptr, 0, e->logits, c.vocab, B, c.vocab, Hd));
+  if (n_new == 1 && e->repeat_penalty != 1.0f && e->penalty_range > 0) {      // decode steps only: the prefill head is a plain arg-max
+    qwen_penalty_kernel<<<B, 32, 0, e->st>>>(e->logits, c.vocab, e->save_id, c.max_seq_len, e->n_save, e->penalty_range, e->repeat_penalty);
+    QKL(cudaGetLastError());
+  }
   qwen_argmax_slices_kernel<<<dim3(kArgSlices, B), 256, 0, e->st>>>(e->logits, c.vocab, e->cand_val, e->cand_idx);
   QKL(cudaGetLastError());
   SelectArgs s{};
@@ -1451,6 +1473,14 @@ int b200asr_qwen_set_prompt(b200asr_qwen* e, const int32_t* head_ids, int32_t n_
   if (!e->d_stop) QCK(cudaMalloc(&e->d_stop, 64 * 4));
   if (n_stop) QCK(cudaMemcpy(e->d_stop, stop_ids, (size_t)n_stop * 4, cudaMemcpyHostToDevice));
   if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+  return B200ASR_OK;
+}
+
+int b200asr_qwen_set_decode_options(b200asr_qwen* e, float repeat_penalty, int32_t penalty_range) {
+  if (!e) return B200ASR_E_INVALID;
+  if (penalty_range < 0 || !(repeat_penalty > 0.f)) return e->fail(B200ASR_E_INVALID, "bad penalty options");
+  e->repeat_penalty = repeat_penalty; e->penalty_range = penalty_range;
+  if (e->step_graph) { cudaSetDevice(e->cfg.device); cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
   return B200ASR_OK;
 }
 

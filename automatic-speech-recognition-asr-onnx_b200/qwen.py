@@ -250,6 +250,7 @@ class QwenEngine:
         self.h = h
         self.batch = 0
         self.n_prompt = 0
+        self.repeat_penalty, self.penalty_range = 1.0, 10
         for name, arr in tensors.items():
             a = np.ascontiguousarray(arr, dtype=np.float32)
             self._ck(self.lib.b200asr_qwen_set_tensor(self.h, name.encode(), a.ctypes.data_as(_cabi._F32P), a.size))
@@ -278,6 +279,11 @@ class QwenEngine:
 
     def set_option(self, key: str, value: int):
         self._ck(self.lib.b200asr_qwen_set_option(self.h, key.encode(), int(value)))
+
+    def set_decode_options(self, repeat_penalty: float = 1.0, penalty_range: int = 10):
+        """repeat_penalty 1.0 = greedy; anything else = the script's penalty-greedy strategy (:90-91,369-376)."""
+        self._ck(self.lib.b200asr_qwen_set_decode_options(self.h, float(repeat_penalty), int(penalty_range)))
+        self.repeat_penalty, self.penalty_range = float(repeat_penalty), int(penalty_range)
 
     @property
     def stream_ptr(self) -> int:
@@ -362,12 +368,18 @@ class QwenEngine:
         return out[:n.value]
 
 
+REPEAT_PENALTY = 0.8         # script defaults (Inference_Qwen_ASR_ONNX.py:90-91): penalty-greedy out of the box
+PENALTY_RANGE = 10
+
+
 def transcribe_clip(engine: QwenEngine, raw_audio_int16: np.ndarray, *, query_ids: Sequence[int] = (),
-                    language_tail_ids: Sequence[int] = (), sample_rate: int = 16000, step_through_host: bool = False):
+                    language_tail_ids: Sequence[int] = (), sample_rate: int = 16000, step_through_host: bool = False,
+                    repeat_penalty: float = REPEAT_PENALTY, penalty_range: int = PENALTY_RANGE):
     """Host loop of Inference_Qwen_ASR_ONNX.py:586-745 for one clip: int16 PCM in, token ids + timing out.
     `step_through_host` walks the script's protocol call by call (prefill, then one decode_step per token with the
     stop test and generation_limit on the host, :666-737); the default runs the same loop on the device."""
     pcm = np.asarray(raw_audio_int16, dtype=np.int16).reshape(1, -1)[:, :engine.max_samples]
+    engine.set_decode_options(repeat_penalty, penalty_range)
     t0 = time.time()
     if not step_through_host:
         tokens = engine.transcribe(pcm, query_ids, language_tail_ids)[0]

@@ -224,6 +224,11 @@ int b200asr_qwen_finalize_weights(b200asr_qwen* e);
 /* token ids the exporter bakes around the audio (:1540-1586) and the stop set (:1503) */
 int b200asr_qwen_set_prompt(b200asr_qwen* e, const int32_t* head_ids, int32_t n_head, const int32_t* suffix_ids, int32_t n_suffix,
                             const int32_t* tail_ids, int32_t n_tail, const int32_t* stop_ids, int32_t n_stop);
+/* decode strategy (Inference_Qwen_ASR_ONNX.py:369-376): repeat_penalty == 1 -> greedy; otherwise penalty-greedy, the
+ * script's default (REPEAT_PENALTY 0.8, PENALTY_RANGE 10, :90-91): from the first decode step on, the logits of the last
+ * penalty_range selected ids are multiplied by repeat_penalty before the arg-max (APPLY_PENALTY, Export_Qwen_ASR.py:1403-1415).
+ * The engine starts in greedy mode. */
+int b200asr_qwen_set_decode_options(b200asr_qwen* e, float repeat_penalty, int32_t penalty_range);
 /* pcm [batch][n_samples]: int16 (scaled by 1/32768 on device) or float32 in [-1,1].  Leaves the prompt embedding
  * [head | query | suffix | audio | tail | language tail] in HBM; n_prompt_out = its length. */
 int b200asr_qwen_encode(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,

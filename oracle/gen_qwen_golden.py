@@ -92,7 +92,7 @@ def synth_pcm(seed, n):
 
 def main():
     d = qo.TINY_TEST
-    pr = qo.TINY_PROMPT
+    pr_ = qo.TINY_PROMPT
     max_audio = 480000
     ns = load_namespace(max_audio)
     cases = [(0, 32000, (), (), 6), (1, 171360, (20, 21, 22), (30, 31), 5), (2, 130000, (), (40,), 6), (3, 15999, (7,), (), 4)]
@@ -101,8 +101,8 @@ def main():
         model = build_reference_model(ns, d, raw)
         embed = model.thinker.model.embed_tokens
         with torch.no_grad():
-            enc = ns["QWEN3_ASR_ENCODER"](model.thinker.audio_tower, embed.float(), list(pr.head_ids), list(pr.tail_ids),
-                                          list(pr.suffix_ids)).eval()
+            enc = ns["QWEN3_ASR_ENCODER"](model.thinker.audio_tower, embed.float(), list(pr_.head_ids), list(pr_.tail_ids),
+                                          list(pr_.suffix_ids)).eval()
             rot_p = ns["QWEN3_ASR_ROTARY_MASK_PREFILL"](model.thinker.model, d.max_seq_len).eval()
             rot_d = ns["QWEN3_ASR_ROTARY_MASK_DECODE"](model.thinker.model, d.max_seq_len).eval()
             dec = ns["QWEN3_ASR_DECODER_MAIN"](model, d.heads, d.kv_heads, d.head_dim, d.dec_layers, d.hidden).eval()
@@ -123,7 +123,7 @@ def main():
             logits = [out[-1][0]]
             # free-running greedy stream (Inference_Qwen_ASR_ONNX.py:683-737) for max_new tokens
             max_new = 8
-            stop = set(pr.stop_ids)
+            stop = set(pr_.stop_ids)
             tok = int(argmax(out[-1]))
             tokens, count = [], 0
             state, kvl = list(out[:2 * L]), kv_len
@@ -136,6 +136,24 @@ def main():
                 tok = int(argmax(o[-1]))
                 if tok not in stop:
                     count += 1; tokens.append(tok)
+            # the script's default strategy: penalty-greedy (REPEAT_PENALTY 0.8, PENALTY_RANGE 10; Inference_Qwen_ASR_ONNX.py:90-91)
+            greedy_head, pen_head = ns["GREEDY_SEARCH"]().eval(), ns["APPLY_PENALTY"]().eval()
+            pv, pr = torch.tensor(0.8), torch.tensor(10, dtype=torch.int64)
+            p_new = 14
+            tok_t, save = greedy_head(out[-1], torch.zeros((1, 0), dtype=torch.int32))
+            tok = int(tok_t)
+            pen_tokens, count = [], 0
+            state, kvl = list(out[:2 * L]), kv_len
+            if tok not in stop:
+                count = 1; pen_tokens.append(tok)
+            while count < p_new and tok not in stop:
+                c1, s1, kvl = rot_d(kvl)
+                o = dec(*state, embed(torch.tensor([[tok]], dtype=torch.int32)).float(), c1, s1, torch.zeros(1, 1, 1, 1, 1))
+                state = list(o[:2 * L])
+                tok_t, save = greedy_head(pen_head(o[-1], save, pv, pr), save)
+                tok = int(tok_t)
+                if tok not in stop:
+                    count += 1; pen_tokens.append(tok)
             # teacher-forced logits
             forced = [int(x) for x in torch.randint(0, 400, (n_forced,), generator=torch.Generator().manual_seed(77 + seed))]
             state, kvl = list(out[:2 * L]), kv_len
@@ -145,13 +163,13 @@ def main():
                 state = list(o[:2 * L])
                 logits.append(o[-1][0])
             logits = torch.stack(logits)
-            n_head = len(pr.head_ids) + len(query_ids) + len(pr.suffix_ids)
-            n_audio = n_prompt - n_head - len(pr.tail_ids) - len(lang_tail)
+            n_head = len(pr_.head_ids) + len(query_ids) + len(pr_.suffix_ids)
+            n_audio = n_prompt - n_head - len(pr_.tail_ids) - len(lang_tail)
             audio_hidden = prompt_embed[0, n_head:n_head + n_audio]
         # ---- oracle must reproduce the reference before the file is written ----
         fw = qo.fold_weights(raw, d)
-        o_tok, st = qo.greedy_transcribe(pcm, fw, d, pr, query_ids, lang_tail, max_new=max_new, return_stages=True)
-        _, stf = qo.greedy_transcribe(pcm, fw, d, pr, query_ids, lang_tail, forced=forced, return_stages=True)
+        o_tok, st = qo.greedy_transcribe(pcm, fw, d, pr_, query_ids, lang_tail, max_new=max_new, return_stages=True)
+        _, stf = qo.greedy_transcribe(pcm, fw, d, pr_, query_ids, lang_tail, forced=forced, return_stages=True)
         assert n_audio == qo.audio_token_count(n, d), (n_audio, qo.audio_token_count(n, d))
         for name, a, b in (("audio_hidden", st["audio_hidden"], audio_hidden), ("prompt_embed", st["prompt_embed"], prompt_embed[0]),
                            ("logits", stf["logits"], logits)):
@@ -159,12 +177,15 @@ def main():
             print(f"case{case} {name}: oracle vs reference max|d| = {err:.3e}  (scale {float(b.abs().max()):.2f})")
             assert err <= 1e-3, name
         assert o_tok == tokens, (o_tok, tokens)
+        o_pen = qo.greedy_transcribe(pcm, fw, d, pr_, query_ids, lang_tail, max_new=p_new, repeat_penalty=0.8, penalty_range=10)
+        assert o_pen == pen_tokens, (o_pen, pen_tokens)
         np.savez_compressed(OUT / f"qwen_tiny_case{case}.npz", seed=seed, pcm=pcm, query_ids=np.array(query_ids, np.int32),
                             language_tail_ids=np.array(lang_tail, np.int32), n_prompt=n_prompt, n_audio=n_audio,
                             features=st["features"].numpy(), audio_hidden=audio_hidden.numpy(),
                             forced_tokens=np.array(forced, np.int32), forced_logits=logits.numpy(),
-                            tokens=np.array(tokens, np.int32), max_new=max_new)
-        print(f"case{case}: prompt {n_prompt} ({n_audio} audio tokens), greedy {tokens}")
+                            tokens=np.array(tokens, np.int32), max_new=max_new,
+                            penalty_tokens=np.array(pen_tokens, np.int32), penalty_max_new=p_new)
+        print(f"case{case}: prompt {n_prompt} ({n_audio} audio tokens), greedy {tokens}, penalty-greedy {pen_tokens}")
 
 
 if __name__ == "__main__":

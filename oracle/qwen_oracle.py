@@ -339,11 +339,24 @@ def prepare_audio(pcm_int16: np.ndarray) -> torch.Tensor:
     return torch.from_numpy(pcm_int16.astype(np.float32) / 32768.0).reshape(1, 1, -1)
 
 
+def apply_penalty(logits: torch.Tensor, save_id: Sequence[int], penalty_value: float, penalty_range: int) -> torch.Tensor:
+    """APPLY_PENALTY / PENALIZE_LOGITS (Export_Qwen_ASR.py:669-694,1403-1415): the logits of the last `penalty_range`
+    selected ids are multiplied by `penalty_value`; gather-then-scatter, so a repeated id is scaled once."""
+    ids = list(save_id)[-penalty_range:]
+    out = logits.clone()
+    for i in set(ids):
+        out[i] = logits[i] * penalty_value
+    return out
+
+
 def greedy_transcribe(pcm_int16: np.ndarray, fw, d: QwenDims, prompt: QwenPrompt, query_ids: Sequence[int] = (),
                       language_tail_ids: Sequence[int] = (), max_new: int | None = None, forced: Sequence[int] | None = None,
-                      return_stages: bool = False):
+                      return_stages: bool = False, repeat_penalty: float = 1.0, penalty_range: int = 10):
     """Greedy host loop of Inference_Qwen_ASR_ONNX.py:656-737.  `forced` feeds the given ids instead of the arg-max
-    (teacher forcing for logit comparison; stop test skipped)."""
+    (teacher forcing for logit comparison; stop test skipped).  repeat_penalty != 1 = the script's penalty_greedy
+    strategy (its default, REPEAT_PENALTY = 0.8 / PENALTY_RANGE = 10, :90-91,369-376): the prefill head is a plain
+    arg-max, every decode step scales the logits of the last `penalty_range` selected ids first
+    (merge_decode_penalty_greedy, Qwen_ASR/Shared_Merged.py:806-840)."""
     with torch.no_grad():
         st: Dict[str, torch.Tensor] = {}
         feat = features(prepare_audio(pcm_int16), fw, d)
@@ -366,6 +379,7 @@ def greedy_transcribe(pcm_int16: np.ndarray, fw, d: QwenDims, prompt: QwenPrompt
                 kv_len += 1
                 all_logits.append(logits)
         else:
+            save_id = [tok]
             if tok not in stop:
                 count = 1
                 tokens.append(tok)
@@ -373,7 +387,10 @@ def greedy_transcribe(pcm_int16: np.ndarray, fw, d: QwenDims, prompt: QwenPrompt
                 logits, kv = decoder(fw["embed.w"][tok].unsqueeze(0), kv_len, kv, fw, d)
                 kv_len += 1
                 all_logits.append(logits)
+                if repeat_penalty != 1.0:
+                    logits = apply_penalty(logits, save_id, repeat_penalty, penalty_range)
                 tok = int(torch.argmax(logits))
+                save_id.append(tok)
                 if tok not in stop:
                     count += 1
                     tokens.append(tok)

@@ -68,8 +68,8 @@ def test_qwen_host_stepped_protocol_equals_device_loop():
     g = dict(np.load(GOLD[3]))
     eng = _engine(int(g["seed"]), "f32")
     q, l = g["query_ids"].tolist(), g["language_tail_ids"].tolist()
-    a = qw.transcribe_clip(eng, g["pcm"], query_ids=q, language_tail_ids=l)
-    b = qw.transcribe_clip(eng, g["pcm"], query_ids=q, language_tail_ids=l, step_through_host=True)
+    a = qw.transcribe_clip(eng, g["pcm"], query_ids=q, language_tail_ids=l, repeat_penalty=1.0)
+    b = qw.transcribe_clip(eng, g["pcm"], query_ids=q, language_tail_ids=l, step_through_host=True, repeat_penalty=1.0)
     assert a["tokens"] == b["tokens"] and a["rtf"] > 0
     assert a["tokens"][:int(g["max_new"])] == g["tokens"].tolist()
     fw = qo.fold_weights(qo.make_raw_weights(qo.TINY_TEST, int(g["seed"])), qo.TINY_TEST)
@@ -184,3 +184,24 @@ def test_qwen_programmatic_dependent_launch_is_transparent():
     for o in out[1:]:
         assert np.array_equal(o[0], out[0][0])
         assert o[1] == out[0][1]
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])
+def test_qwen_penalty_greedy_vs_reference_golden(path):
+    """The script's default strategy (REPEAT_PENALTY 0.8, PENALTY_RANGE 10): streams minted with the reference's
+    APPLY_PENALTY + GREEDY_SEARCH modules; device loop, host-stepped protocol and graph-free path all reproduce them."""
+    g = dict(np.load(path))
+    eng = _engine(int(g["seed"]), "f32")
+    q, l = g["query_ids"].tolist(), g["language_tail_ids"].tolist()
+    mx = int(g["penalty_max_new"])
+    eng.set_decode_options(0.8, 10)
+    assert eng.transcribe(g["pcm"], q, l, max_new=mx)[0] == g["penalty_tokens"].tolist()
+    eng.set_option("graph", 0)
+    assert eng.transcribe(g["pcm"], q, l, max_new=mx)[0] == g["penalty_tokens"].tolist()
+    eng.set_option("graph", 1)
+    r = qw.transcribe_clip(eng, g["pcm"], query_ids=q, language_tail_ids=l, step_through_host=True)      # script defaults
+    want = g["penalty_tokens"].tolist()
+    assert r["tokens"][:len(want)] == want          # the protocol runs on to a stop id or generation_limit
+    eng.set_decode_options(1.0, 10)
+    assert eng.transcribe(g["pcm"], q, l, max_new=int(g["max_new"]))[0] == g["tokens"].tolist()
+    eng.close()

@@ -27,6 +27,8 @@ def test_oracle_reproduces_reference_golden(path):
     np.testing.assert_allclose(st["features"].numpy(), g["features"], atol=1e-5)
     np.testing.assert_allclose(st["audio_hidden"].numpy(), g["audio_hidden"], atol=1e-4)
     assert st["prompt_embed"].shape[0] == int(g["n_prompt"]) and st["audio_hidden"].shape[0] == int(g["n_audio"])
+    pen = qo.greedy_transcribe(g["pcm"], fw, d, qo.TINY_PROMPT, q, l, max_new=int(g["penalty_max_new"]), repeat_penalty=0.8, penalty_range=10)
+    assert pen == g["penalty_tokens"].tolist()
     _, sf = qo.greedy_transcribe(g["pcm"], fw, d, qo.TINY_PROMPT, q, l, forced=g["forced_tokens"].tolist(), return_stages=True)
     np.testing.assert_allclose(sf["logits"].numpy(), g["forced_logits"], atol=1e-3)
 
