@@ -5,6 +5,10 @@
 (/root/reference/Whisper/Inference_Whisper_ONNX.py:37-53) becomes
 
     python -m b200asr.cli whisper --model-folder DIR [--tokenizer-path P] --audio clip.wav [more.wav ...]
+    python -m b200asr.cli qwen    --model-folder DIR [--tokenizer-path P] --audio clip.wav [--language English] [--prompt "..."]
+
+(the second = /root/reference/Qwen_ASR/Inference_Qwen_ASR_ONNX.py:44-60; DIR = the Qwen3-ASR checkpoint folder with the
+tokenizer files, REPEAT_PENALTY / PENALTY_RANGE via --set as in the script's configuration block :84-91)
 
 where DIR is the HF checkpoint folder the exporter starts from (`config.json`, `model.safetensors`,
 `generation_config.json`; Export_Whisper.py:14).  Behaviour constants keep the script's names (`--set REPEAT_PENALTY=1.0
@@ -62,7 +66,18 @@ def main(argv=None) -> int:
     w.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     w.add_argument("--device", type=int, default=0)
     w.add_argument("--set", nargs="*", default=[], metavar="NAME=VALUE", help="script constants, e.g. REPEAT_PENALTY=1.0")
+    qp = sub.add_parser("qwen")
+    qp.add_argument("--model-folder", "--onnx-folder", dest="folder", required=True)
+    qp.add_argument("--tokenizer-path", default=None)
+    qp.add_argument("--audio", nargs="+", required=True)
+    qp.add_argument("--language", default="", help="force a language (its name + <asr_text> is appended to the prompt); empty = detect")
+    qp.add_argument("--prompt", default="", help="task / context prompt placed in the system turn")
+    qp.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
+    qp.add_argument("--device", type=int, default=0)
+    qp.add_argument("--set", nargs="*", default=[], metavar="NAME=VALUE", help="REPEAT_PENALTY=1.0 PENALTY_RANGE=10")
     args = ap.parse_args(argv)
+    if args.model == "qwen":
+        return _main_qwen(args)
 
     dims, state, gen = ingest.load_hf_whisper(args.folder)
     tensors = fold_whisper(state, dims, gen.get("suppress_tokens") or [], gen.get("begin_suppress_tokens") or [])
@@ -87,6 +102,37 @@ def main(argv=None) -> int:
         res = pipe.transcribe_pcm(x, verbose=True)
         text = tokenizer.decode(res.tokens, skip_special_tokens=True) if tokenizer is not None else " ".join(map(str, res.tokens))
         print(pipe.report(res, text))
+    eng.close()
+    return 0
+
+
+def _main_qwen(args) -> int:
+    """Inference_Qwen_ASR_ONNX.py main(): checkpoint folder + tokenizer -> per clip `ASR Result` / `RTF` (:745-760)."""
+    from . import qwen as qw
+    from transformers import AutoTokenizer
+    consts = {"REPEAT_PENALTY": qw.REPEAT_PENALTY, "PENALTY_RANGE": qw.PENALTY_RANGE}
+    for pair in args.set or []:
+        k, _, v = pair.partition("=")
+        if k not in consts:
+            raise SystemExit(f"unknown option {k}; choose from {sorted(consts)}")
+        consts[k] = type(consts[k])(v)
+    dims, state, tied = ingest.load_hf_qwen3_asr(args.folder)
+    tokenizer = AutoTokenizer.from_pretrained(str(args.tokenizer_path or args.folder))      # prompt ids come from the tokenizer: required
+    prompt, tails = ingest.qwen_prompt_from_tokenizer(tokenizer, [args.language] if args.language else [])
+    tensors = qw.fold_qwen(state, dims, tie_lm_head=tied)
+    del state
+    clips = [ingest.read_wav(p) for p in args.audio]
+    pcm = [ingest.to_model_rate(x, r, dims.sample_rate) for x, r in clips]
+    eng = qw.QwenEngine(dims, tensors, prompt, precision=args.precision, max_batch=1,
+                        max_samples=max(480000, max(len(x) for x in pcm)), device=args.device)
+    query = [int(i) for i in tokenizer.encode(args.prompt, add_special_tokens=False)] if args.prompt else []
+    for path, x in zip(args.audio, pcm):
+        print(f"\nTest audio : {path}   ({len(x) / dims.sample_rate:.2f} s)")
+        print("-" * 70)
+        res = qw.transcribe_clip(eng, x, query_ids=query, language_tail_ids=tails.get(args.language, ()), sample_rate=dims.sample_rate,
+                                 repeat_penalty=float(consts["REPEAT_PENALTY"]), penalty_range=int(consts["PENALTY_RANGE"]))
+        text = tokenizer.decode(res["tokens"], skip_special_tokens=True)
+        print(f"\nASR Result:\n{text}\n\nRTF: {res['rtf']:.4f}")
     eng.close()
     return 0
 

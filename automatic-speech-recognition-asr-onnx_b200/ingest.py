@@ -144,3 +144,58 @@ def to_model_rate(pcm: np.ndarray, rate: int, target: int = 16000) -> np.ndarray
     g = gcd(int(rate), int(target))
     y = resample_poly(pcm.astype(np.float64), target // g, rate // g)
     return np.clip(np.rint(y), -32768, 32767).astype(np.int16)
+
+
+# ---------------------------------------------------------------------------------------------
+def qwen_dims_from_hf_config(cfg: dict):
+    """HF `config.json` of a Qwen3-ASR checkpoint (thinker_config.{audio_config,text_config}; field names as the
+    exporter's config classes, Qwen_ASR/Export_Qwen_ASR.py:145-236) -> engine dimensions."""
+    from .qwen import CHUNK, QwenDims
+    th = cfg.get("thinker_config", cfg)
+    a, t = th["audio_config"], th["text_config"]
+    n_window = int(a.get("n_window", 50))
+    if 2 * n_window != CHUNK:
+        raise ValueError(f"n_window {n_window}: the exporter's length formula assumes {CHUNK}-frame chunks (Export_Qwen_ASR.py:519-527)")
+    rope = t.get("rope_theta")
+    if rope is None and t.get("rope_scaling"):
+        rope = t["rope_scaling"].get("rope_theta")
+    hidden, heads = int(t["hidden_size"]), int(t["num_attention_heads"])
+    return QwenDims(n_mels=int(a.get("num_mel_bins", 128)), enc_layers=int(a["encoder_layers"]), enc_d=int(a["d_model"]),
+                    enc_heads=int(a["encoder_attention_heads"]), enc_ffn=int(a["encoder_ffn_dim"]),
+                    conv_ch=int(a.get("downsample_hidden_size", 480)), out_dim=int(a["output_dim"]),
+                    chunks_per_window=int(a.get("n_window_infer", 400)) // CHUNK,
+                    max_source_positions=int(a.get("max_source_positions", 1500)), vocab=int(t["vocab_size"]), hidden=hidden,
+                    inter=int(t["intermediate_size"]), dec_layers=int(t["num_hidden_layers"]), heads=heads,
+                    kv_heads=int(t.get("num_key_value_heads", heads)), head_dim=int(t.get("head_dim", hidden // heads)),
+                    rope_theta=float(rope if rope is not None else 10000.0), rms_eps=float(t.get("rms_norm_eps", 1e-6)))
+
+
+def load_hf_qwen3_asr(folder):
+    """(dims, HF-named state dict, tied?) from a Qwen3-ASR checkpoint folder (what the exporter loads, :1470-1480); sharded
+    checkpoints are followed.  `tied` = the checkpoint stores no separate lm_head (tie_word_embeddings)."""
+    folder = Path(folder)
+    dims = qwen_dims_from_hf_config(json.loads((folder / "config.json").read_text()))
+    index = folder / "model.safetensors.index.json"
+    files = sorted(set(json.loads(index.read_text())["weight_map"].values())) if index.exists() else ["model.safetensors"]
+    state: Dict[str, np.ndarray] = {}
+    for fn in files:
+        state.update(read_safetensors(folder / fn))
+    tied = "thinker.lm_head.weight" not in state
+    return dims, state, tied
+
+
+def qwen_prompt_from_tokenizer(tokenizer, languages=()):
+    """The ids the exporter bakes around the audio and the per-language tails (Export_Qwen_ASR.py:1500-1586):
+    returns (QwenPrompt, {language name: prompt_token_ids})."""
+    from .qwen import QwenPrompt
+    vocab = tokenizer.get_vocab()
+    enc = lambda text: [int(i) for i in tokenizer.encode(text, add_special_tokens=False)]
+    im_start, im_end = int(vocab["<|im_start|>"]), int(vocab["<|im_end|>"])
+    nl = enc("\n")[0]
+    head = [im_start, enc("system")[0], nl]
+    suffix = [im_end, nl, im_start, enc("user")[0], nl, int(vocab["<|audio_start|>"])]
+    tail = [int(vocab["<|audio_end|>"]), im_end, nl, im_start, enc("assistant")[0], nl] + enc("language ")
+    stop = [int(vocab["<|endoftext|>"]), im_end]
+    asr_text = [int(vocab["<asr_text>"])]
+    tails = {name: enc(name) + asr_text for name in languages}
+    return QwenPrompt(tuple(head), tuple(suffix), tuple(tail), tuple(stop)), tails

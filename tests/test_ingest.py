@@ -92,3 +92,50 @@ def test_cli_metadata_and_options():
     assert o.REPEAT_PENALTY == 1.0 and o.DETECT_LANGUAGE is False and o.PENALTY_RANGE == 7 and o.TARGET_LANGUAGE == "zh"
     with pytest.raises(SystemExit):
         _options(["NOPE=1"])
+
+
+def test_qwen_hf_folder_to_engine_tensors(tmp_path):
+    """A Qwen3-ASR checkpoint folder (config.json + safetensors under the HF names) -> dims + folded engine tensors, equal to
+    folding the in-memory state dict; a tied checkpoint (no lm_head) folds without lm_head.w."""
+    import json
+    from b200asr import qwen as qw
+    d = qw.QWEN_TINY_TEST
+    raw = qw.synth_qwen_checkpoint(d, 4)
+    cfg = {"thinker_config": {
+        "audio_config": {"num_mel_bins": d.n_mels, "encoder_layers": d.enc_layers, "encoder_attention_heads": d.enc_heads,
+                         "encoder_ffn_dim": d.enc_ffn, "d_model": d.enc_d, "max_source_positions": d.max_source_positions,
+                         "n_window": 50, "n_window_infer": 800, "output_dim": d.out_dim, "downsample_hidden_size": d.conv_ch},
+        "text_config": {"vocab_size": d.vocab, "hidden_size": d.hidden, "intermediate_size": d.inter, "num_hidden_layers": d.dec_layers,
+                        "num_attention_heads": d.heads, "num_key_value_heads": d.kv_heads, "head_dim": d.head_dim,
+                        "rope_theta": d.rope_theta, "rms_norm_eps": d.rms_eps}}}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    ingest.write_safetensors(tmp_path / "model.safetensors", {k: v.numpy() for k, v in raw.items()})
+    dims, state, tied = ingest.load_hf_qwen3_asr(tmp_path)
+    assert not tied
+    assert dims.to_dict() == {**d.to_dict(), "max_seq_len": qw.QwenDims().max_seq_len}
+    got, want = qw.fold_qwen(state, d), qw.fold_qwen(raw, d)
+    assert got.keys() == want.keys()
+    for k in want:
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+    ingest.write_safetensors(tmp_path / "model.safetensors", {k: v.numpy() for k, v in raw.items() if k != "thinker.lm_head.weight"})
+    _, state2, tied2 = ingest.load_hf_qwen3_asr(tmp_path)
+    assert tied2 and "lm_head.w" not in qw.fold_qwen(state2, d, tie_lm_head=tied2)
+    with pytest.raises(ValueError, match="n_window"):
+        cfg["thinker_config"]["audio_config"]["n_window"] = 100
+        ingest.qwen_dims_from_hf_config(cfg)
+
+
+def test_qwen_prompt_from_tokenizer():
+    """Prompt layout of Export_Qwen_ASR.py:1540-1586 from a tokenizer object (stub with the calls the exporter makes)."""
+    class Tok:
+        words = {"system": [11], "user": [12], "assistant": [13], "\n": [14], "language ": [15, 16], "English": [17], "Chinese": [18, 19]}
+        def get_vocab(self):
+            return {"<|im_start|>": 1, "<|im_end|>": 2, "<|audio_start|>": 3, "<|audio_end|>": 4, "<|endoftext|>": 5, "<asr_text>": 6}
+        def encode(self, text, add_special_tokens=False):
+            return self.words[text]
+    prompt, tails = ingest.qwen_prompt_from_tokenizer(Tok(), ["English", "Chinese"])
+    assert prompt.head_ids == (1, 11, 14)
+    assert prompt.suffix_ids == (2, 14, 1, 12, 14, 3)
+    assert prompt.tail_ids == (4, 2, 14, 1, 13, 14, 15, 16)
+    assert prompt.stop_ids == (5, 2)
+    assert tails == {"English": [17, 6], "Chinese": [18, 19, 6]}
