@@ -311,6 +311,90 @@ qwen_attn_kernel(const float* __restrict__ q, const KT* __restrict__ kc, const K
   for (int m = 0; m < M; ++m) dst[lane + 32 * m] = from_f<OutT>(acc[m] * inv);
 }
 
+// ---- prefill attention, tiled: one CTA per (utterance, query head, 8 consecutive rows).  K / V tiles of 32 positions are
+//      staged once in shared memory (rows padded by 16 bytes: a lane reads its own key row conflict-free) and shared by the
+//      8 warps, each of which owns one query row with an online soft-max; lanes hold the keys for the scores and the head
+//      dims for P V.  Causal: a row stops at its own position (see qwen_attn_kernel on the -128 mask) ----
+constexpr int kPfRows = 8, kPfKeys = 32;
+template <typename KT, typename OutT, int DH>
+__global__ void __launch_bounds__(kPfRows * 32)
+qwen_attn_prefill_kernel(const float* __restrict__ q, const KT* __restrict__ kc, const KT* __restrict__ vc, int64_t cache_layer_off,
+                         int n_new, int H, int KH, int max_seq, const DecState* __restrict__ state, OutT* __restrict__ ctx) {
+  constexpr int EPL = DH / 32, LDK = DH + 16 / (int)sizeof(KT);
+  __shared__ __align__(16) KT sk[kPfKeys * LDK];
+  __shared__ __align__(16) KT sv[kPfKeys * DH];
+  __shared__ float sq[kPfRows][DH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int i = tile * kPfRows + warp;                 // this warp's row within the utterance's new positions
+  const bool live = i < n_new;
+  const int base = state->kv_len;
+  const int row = b * n_new + i;
+  const int kh = h / (H / KH);
+  const int my_keys = base + i + 1;                    // causal extent of this row
+  const int last_row = min(n_new, (tile + 1) * kPfRows) - 1;
+  const int cta_keys = base + last_row + 1;
+  if (live) {
+    const float* qr = q + ((int64_t)row * H + h) * DH;
+#pragma unroll
+    for (int m = 0; m < EPL; ++m) sq[warp][lane + 32 * m] = qr[lane + 32 * m];
+  }
+  const KT* K = kc + cache_layer_off + ((int64_t)b * KH + kh) * max_seq * DH;
+  const KT* V = vc + cache_layer_off + ((int64_t)b * KH + kh) * max_seq * DH;
+  float mx = -INFINITY, sum = 0.f, acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  constexpr int VPR = DH * (int)sizeof(KT) / 16;        // 16-byte vectors per cache row
+  for (int j0 = 0; j0 < cta_keys; j0 += kPfKeys) {
+    __syncthreads();
+    for (int v = threadIdx.x; v < kPfKeys * VPR; v += kPfRows * 32) {
+      const int r = v / VPR, c = v - r * VPR;
+      uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
+      if (j0 + r < cta_keys) {
+        kk = reinterpret_cast<const uint4*>(K + (int64_t)(j0 + r) * DH)[c];
+        vv = reinterpret_cast<const uint4*>(V + (int64_t)(j0 + r) * DH)[c];
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<char*>(sk) + (size_t)r * LDK * sizeof(KT) + c * 16) = kk;
+      *reinterpret_cast<uint4*>(reinterpret_cast<char*>(sv) + (size_t)r * DH * sizeof(KT) + c * 16) = vv;
+    }
+    __syncthreads();
+    if (!live || j0 >= my_keys) continue;
+    const int j = j0 + lane;
+    float s = -INFINITY;
+    if (j < my_keys) {
+      const KT* kr = sk + lane * LDK;
+      s = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH; c += KVec<KT>::N) {
+        float kk[KVec<KT>::N];
+        KVec<KT>::load(kr + c, kk);
+#pragma unroll
+        for (int e = 0; e < KVec<KT>::N; ++e) s = fmaf(kk[e], sq[warp][c + e], s);
+      }
+    }
+    const float m_new = fmaxf(mx, warp_max(s));
+    const float scale = expf(mx - m_new);              // 0 on the first tile (mx = -inf)
+    const float p = j < my_keys ? expf(s - m_new) : 0.f;
+    sum = sum * scale + warp_sum(p);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] *= scale;
+    mx = m_new;
+    const int n_here = min(kPfKeys, my_keys - j0);
+    for (int t = 0; t < n_here; ++t) {
+      const float pt = __shfl_sync(0xffffffffu, p, t);
+      const KT* vr = sv + t * DH + lane * EPL;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pt, to_f<KT>(vr[e]), acc[e]);
+    }
+  }
+  if (live) {
+    const float inv = 1.0f / sum;
+    OutT* dst = ctx + ((int64_t)row * H + h) * DH + lane * EPL;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) dst[e] = from_f<OutT>(acc[e] * inv);
+  }
+}
+
 // ---- decode-step attention, fused with the QK-norm / RoPE / cache append of the new position: one CTA per (utterance,
 //      query head).  Warps 0-2 normalise and rotate this head's q and its kv head's new k / v (every query head of a
 //      group writes the same cache row, a benign duplicate); then the keys are spread over all 512 threads for the scores
@@ -901,7 +985,7 @@ struct b200asr_qwen {
   DecState* dstate = nullptr;
   int *cur_token = nullptr, *tokens = nullptr, *n_gen = nullptr, *finished = nullptr, *save_id = nullptr, *n_save = nullptr;
   cudaGraphExec_t step_graph = nullptr; int graph_B = -1, graph_limit = -1; int64_t graph_nodes = 0; bool use_graph = true;
-  bool use_attn_tc = true, use_attn_split = true, use_pdl = true;
+  bool use_attn_tc = true, use_attn_split = true, use_pdl = true, use_attn_tiled = true;
   float repeat_penalty = 1.0f; int penalty_range = 10;
   float* att_part = nullptr; int* att_counter = nullptr;
   int* h_pinned = nullptr;
@@ -1090,11 +1174,13 @@ int qwen_attention_launch(b200asr_qwen* e, int layer, int rows, int n_new, bool 
   if (ad == kBF16) {
     qwen_qk_rope_kernel<bf16, DH><<<(total_qk + 3) / 4, 128, 0, e->st>>>(e->qkvf, g, cosT, sinT, c.rms_eps, n_new, H, KH, c.max_seq_len, layer_off, total_qk, e->dstate, e->q, (bf16*)e->kc, (bf16*)e->vc);
     QKL(cudaGetLastError());
-    qwen_attn_kernel<bf16, bf16, DH><<<(total_at + 3) / 4, 128, smem, e->st>>>(e->q, (const bf16*)e->kc, (const bf16*)e->vc, layer_off, n_new, H, KH, c.max_seq_len, total_at, e->dstate, (bf16*)e->actx);
+    if (e->use_attn_tiled) qwen_attn_prefill_kernel<bf16, bf16, DH><<<dim3((n_new + kPfRows - 1) / kPfRows, H, rows / n_new), kPfRows * 32, 0, e->st>>>(e->q, (const bf16*)e->kc, (const bf16*)e->vc, layer_off, n_new, H, KH, c.max_seq_len, e->dstate, (bf16*)e->actx);
+    else qwen_attn_kernel<bf16, bf16, DH><<<(total_at + 3) / 4, 128, smem, e->st>>>(e->q, (const bf16*)e->kc, (const bf16*)e->vc, layer_off, n_new, H, KH, c.max_seq_len, total_at, e->dstate, (bf16*)e->actx);
   } else {
     qwen_qk_rope_kernel<float, DH><<<(total_qk + 3) / 4, 128, 0, e->st>>>(e->qkvf, g, cosT, sinT, c.rms_eps, n_new, H, KH, c.max_seq_len, layer_off, total_qk, e->dstate, e->q, (float*)e->kc, (float*)e->vc);
     QKL(cudaGetLastError());
-    qwen_attn_kernel<float, float, DH><<<(total_at + 3) / 4, 128, smem, e->st>>>(e->q, (const float*)e->kc, (const float*)e->vc, layer_off, n_new, H, KH, c.max_seq_len, total_at, e->dstate, (float*)e->actx);
+    if (e->use_attn_tiled) qwen_attn_prefill_kernel<float, float, DH><<<dim3((n_new + kPfRows - 1) / kPfRows, H, rows / n_new), kPfRows * 32, 0, e->st>>>(e->q, (const float*)e->kc, (const float*)e->vc, layer_off, n_new, H, KH, c.max_seq_len, e->dstate, (float*)e->actx);
+    else qwen_attn_kernel<float, float, DH><<<(total_at + 3) / 4, 128, smem, e->st>>>(e->q, (const float*)e->kc, (const float*)e->vc, layer_off, n_new, H, KH, c.max_seq_len, total_at, e->dstate, (float*)e->actx);
   }
   QKL(cudaGetLastError());
   return B200ASR_OK;
@@ -1708,6 +1794,7 @@ int b200asr_qwen_set_option(b200asr_qwen* e, const char* key, int64_t value) {
   if (!e || !key) return B200ASR_E_INVALID;
   if (!strcmp(key, "graph")) { e->use_graph = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "attn_tiled")) { e->use_attn_tiled = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "pdl")) {
     e->use_pdl = value != 0;
     if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }

@@ -163,7 +163,7 @@ def _sinusoids(length: int, channels: int) -> torch.Tensor:
 def fold_qwen(state: Dict[str, torch.Tensor], d: QwenDims, tie_lm_head: bool = False) -> Dict[str, np.ndarray]:
     """HF state dict (fp32 tensors) -> the tensors include/b200asr.h names.  `tie_lm_head` drops lm_head.w so the
     engine projects with the embedding table (tied checkpoints store the table once, :1179-1190)."""
-    st = {k: (v.detach().float() if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v)).float()) for k, v in state.items()}
+    st = {k: (v.detach().float() if isinstance(v, torch.Tensor) else torch.from_numpy(np.array(v, dtype=np.float32))) for k, v in state.items()}
     out: Dict[str, torch.Tensor] = {}
     out["stft_kernel"] = torch.from_numpy(hann_dft_kernel(d.nfft, 1.0))
     out["mel_fbank"] = torch.from_numpy(slaney_mel_filterbank(d.nfft // 2 + 1, d.n_mels, d.sample_rate))

@@ -205,3 +205,27 @@ def test_qwen_penalty_greedy_vs_reference_golden(path):
     eng.set_decode_options(1.0, 10)
     assert eng.transcribe(g["pcm"], q, l, max_new=int(g["max_new"]))[0] == g["tokens"].tolist()
     eng.close()
+
+
+@pytest.mark.parametrize("precision", ["f32", "bf16"])
+def test_qwen_tiled_prefill_attention_equals_row_kernel(precision):
+    """Tiled causal prefill attention (K/V tiles in shared memory, online soft-max) against the warp-per-row kernel on the
+    same cache: only the summation order differs -> prefill logits within 5e-5 in fp32 (and the same greedy stream); in bf16 the
+    context rows are rounded to bf16 after the differently ordered sums, so logits agree to 1e-2 (measured 3e-3)."""
+    g = dict(np.load(GOLD[1]))
+    q, l = g["query_ids"].tolist(), g["language_tail_ids"].tolist()
+    clips = np.stack([g["pcm"], g["pcm"][::-1].copy()])
+    out = {}
+    for tiled in (1, 0):
+        eng = _engine(int(g["seed"]), precision, max_batch=2)
+        eng.set_option("attn_tiled", tiled)
+        eng.encode(clips, q, l)
+        lg, _ = eng.prefill()
+        toks = eng.transcribe(clips, q, l, max_new=8)
+        out[tiled] = (lg.copy(), toks)
+        eng.close()
+    d = float(np.abs(out[1][0] - out[0][0]).max())
+    print(precision, "tiled vs row prefill attention max|dlogit| =", d)
+    assert d <= (5e-5 if precision == "f32" else 1e-2)
+    if precision == "f32":
+        assert out[1][1] == out[0][1]
