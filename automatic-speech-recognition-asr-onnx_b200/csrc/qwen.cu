@@ -722,8 +722,9 @@ template <> struct WRaw<float> {
   __device__ __forceinline__ void get(float* o) const { o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w; }
 };
 
-template <typename WT, int KS, int NC>
-__global__ void __launch_bounds__(256, 2)
+// LOOP = false: the grid covers every column pass (one resident wave at 3 CTAs per SM), no second register buffer
+template <typename WT, int KS, int NC, bool LOOP>
+__global__ void __launch_bounds__(256, LOOP ? 2 : 3)
 qwen_gemv_kernel(QGemvArgs a) {
   extern __shared__ float gx[];                  // [kGemvRows][K]
   __shared__ float red[8][kGemvRows];
@@ -735,8 +736,8 @@ qwen_gemv_kernel(QGemvArgs a) {
   const WT* W = reinterpret_cast<const WT*>(a.W);
   const int k0 = (ks * 32 + lane) * 8, kstep = KS * 256;
   const int n_pass = (N + CPB - 1) / CPB;
-  WRaw<WT> cur[NC][kGemvCH], nxt[NC][kGemvCH];
-  auto fetch = [&](WRaw<WT> (&buf)[NC][kGemvCH], int pass) {
+  WRaw<WT> cur[NC][kGemvCH], nxt[LOOP ? NC : 1][LOOP ? kGemvCH : 1];
+  auto fetch = [&](auto& buf, int pass) {
     const int c0 = pass * CPB + cw * NC;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
@@ -792,7 +793,7 @@ qwen_gemv_kernel(QGemvArgs a) {
     }
     if (r0 > 0) fetch(cur, blockIdx.x);                              // batches beyond four rows walk the matrix again (L2)
     for (int pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
-      fetch(nxt, pass + gridDim.x);                                   // next pass's loads are in flight during this pass's math
+      if (LOOP) fetch(nxt, pass + gridDim.x);                         // next pass's loads are in flight during this pass's math
       float acc[NC][kGemvRows];
 #pragma unroll
       for (int j = 0; j < NC; ++j)
@@ -803,27 +804,20 @@ qwen_gemv_kernel(QGemvArgs a) {
       for (int i = 0; i < kGemvCH; ++i) {
         const int k = k0 + i * kstep;
         if (k < K) {
-          float4 x0[kGemvRows], x1[kGemvRows];
+          float w[NC][8];
+#pragma unroll
+          for (int j = 0; j < NC; ++j) cur[j][i].get(w[j]);
 #pragma unroll
           for (int r = 0; r < kGemvRows; ++r) {
             if (r < nr) {
-              x0[r] = *reinterpret_cast<const float4*>(gx + r * K + k);
-              x1[r] = *reinterpret_cast<const float4*>(gx + r * K + k + 4);
-            }
-          }
+              const float4 x0 = *reinterpret_cast<const float4*>(gx + r * K + k);
+              const float4 x1 = *reinterpret_cast<const float4*>(gx + r * K + k + 4);
 #pragma unroll
-          for (int j = 0; j < NC; ++j) {
-            if (c0 + j < N) {
-              float w[8];
-              cur[j][i].get(w);
-#pragma unroll
-              for (int r = 0; r < kGemvRows; ++r) {
-                if (r < nr) {
-                  float t = acc[j][r];
-                  t = fmaf(w[0], x0[r].x, t); t = fmaf(w[1], x0[r].y, t); t = fmaf(w[2], x0[r].z, t); t = fmaf(w[3], x0[r].w, t);
-                  t = fmaf(w[4], x1[r].x, t); t = fmaf(w[5], x1[r].y, t); t = fmaf(w[6], x1[r].z, t); t = fmaf(w[7], x1[r].w, t);
-                  acc[j][r] = t;
-                }
+              for (int j = 0; j < NC; ++j) {
+                float t = acc[j][r];
+                t = fmaf(w[j][0], x0.x, t); t = fmaf(w[j][1], x0.y, t); t = fmaf(w[j][2], x0.z, t); t = fmaf(w[j][3], x0.w, t);
+                t = fmaf(w[j][4], x1.x, t); t = fmaf(w[j][5], x1.y, t); t = fmaf(w[j][6], x1.z, t); t = fmaf(w[j][7], x1.w, t);
+                acc[j][r] = t;
               }
             }
           }
@@ -866,10 +860,12 @@ qwen_gemv_kernel(QGemvArgs a) {
         }
       }
       if (KS > 1) __syncthreads();
+      if (LOOP) {
 #pragma unroll
-      for (int j = 0; j < NC; ++j)
+        for (int j = 0; j < NC; ++j)
 #pragma unroll
-        for (int i = 0; i < kGemvCH; ++i) cur[j][i] = nxt[j][i];
+          for (int i = 0; i < kGemvCH; ++i) cur[j][i] = nxt[LOOP ? j : 0][LOOP ? i : 0];
+      }
     }
   }
 }
@@ -987,6 +983,7 @@ struct b200asr_qwen {
   cudaGraphExec_t step_graph = nullptr; int graph_B = -1, graph_limit = -1; int64_t graph_nodes = 0; bool use_graph = true;
   bool use_attn_tc = true, use_attn_split = true, use_pdl = true, use_attn_tiled = true;
   float repeat_penalty = 1.0f; int penalty_range = 10;
+  bool pdl_all = false;
   float* att_part = nullptr; int* att_counter = nullptr;
   int* h_pinned = nullptr;
 
@@ -1162,11 +1159,11 @@ int qwen_attention_launch(b200asr_qwen* e, int layer, int rows, int n_new, bool 
     const size_t dsmem = (size_t)(3 * DH + c.max_seq_len + (kAttDecThreads / 32) * DH) * sizeof(float);
     const int S = (c.max_seq_len + kSplitKeys - 1) / kSplitKeys;
     if (ad == kBF16 && e->use_attn_split && rows * H * S <= 2 * e->num_sms) {      // larger batches already fill the machine with one CTA per head
-      QKL(launch_pdl(qwen_attn_split_kernel<DH>, dim3(rows * H, S), dim3(256), 0, e->st, e->use_pdl && rows <= 2, (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, e->att_part, e->att_counter, (float*)e->actx));
+      QKL(launch_pdl(qwen_attn_split_kernel<DH>, dim3(rows * H, S), dim3(256), 0, e->st, e->use_pdl && (rows <= 2 || e->pdl_all), (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, e->att_part, e->att_counter, (float*)e->actx));
       return B200ASR_OK;
     }
-    if (ad == kBF16) QKL(launch_pdl(qwen_attn_decode_kernel<bf16, DH>, dim3(rows * H), dim3(kAttDecThreads), dsmem, e->st, e->use_pdl && rows <= 2, (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (float*)e->actx));
-    else QKL(launch_pdl(qwen_attn_decode_kernel<float, DH>, dim3(rows * H), dim3(kAttDecThreads), dsmem, e->st, e->use_pdl && rows <= 2, (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (float*)e->kc, (float*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (float*)e->actx));
+    if (ad == kBF16) QKL(launch_pdl(qwen_attn_decode_kernel<bf16, DH>, dim3(rows * H), dim3(kAttDecThreads), dsmem, e->st, e->use_pdl && (rows <= 2 || e->pdl_all), (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (float*)e->actx));
+    else QKL(launch_pdl(qwen_attn_decode_kernel<float, DH>, dim3(rows * H), dim3(kAttDecThreads), dsmem, e->st, e->use_pdl && (rows <= 2 || e->pdl_all), (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (float*)e->kc, (float*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (float*)e->actx));
     return B200ASR_OK;
   }
   const int total_qk = rows * (H + 2 * KH), total_at = rows * H;
@@ -1186,32 +1183,36 @@ int qwen_attention_launch(b200asr_qwen* e, int layer, int rows, int n_new, bool 
   return B200ASR_OK;
 }
 
+template <typename WT, int KS>
+cudaError_t qwen_gemv_launch_ks(const QGemvArgs& a, int num_sms, size_t smem, cudaStream_t st, bool pdl) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(qwen_gemv_kernel<WT, KS, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(qwen_gemv_kernel<WT, KS, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  const int cpb = (8 / KS) * 2;
+  const int n_pass = (a.N + cpb - 1) / cpb;
+  // layers that fit one resident wave (3 CTAs per SM without the second register buffer) run without a column loop;
+  // wider ones (the vocabulary head) loop inside 2 CTAs per SM with the next pass's loads issued ahead of the math
+  if (n_pass <= 3 * num_sms) return launch_pdl(qwen_gemv_kernel<WT, KS, 2, false>, dim3(n_pass), dim3(256), smem, st, pdl, a);
+  return launch_pdl(qwen_gemv_kernel<WT, KS, 2, true>, dim3(2 * num_sms), dim3(256), smem, st, pdl, a);
+}
+
 template <typename WT>
 cudaError_t qwen_gemv_launch(const QGemvArgs& a, int num_sms, cudaStream_t st, bool pdl) {
   if (a.K % 8 != 0 || a.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15)) return cudaErrorInvalidValue;
   const size_t smem = (size_t)kGemvRows * a.K * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(qwen_gemv_kernel<WT, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
   // warps per column: a warp covers at most four 256-wide chunks of its columns' K range
   int ks = 1;
   while (ks < 8 && a.K > ks * 256 * kGemvCH) ks *= 2;
   if (a.K > 8 * 256 * kGemvCH) return cudaErrorInvalidValue;
-  const int cpb = (8 / ks) * 2;
-  int grid = (a.N + cpb - 1) / cpb;
-  if (grid > num_sms * 2) grid = num_sms * 2;          // wide layers loop over column passes inside the CTA
   switch (ks) {
-    case 1: return launch_pdl(qwen_gemv_kernel<WT, 1, 2>, dim3(grid), dim3(256), smem, st, pdl, a);
-    case 2: return launch_pdl(qwen_gemv_kernel<WT, 2, 2>, dim3(grid), dim3(256), smem, st, pdl, a);
-    case 4: return launch_pdl(qwen_gemv_kernel<WT, 4, 2>, dim3(grid), dim3(256), smem, st, pdl, a);
-    default: return launch_pdl(qwen_gemv_kernel<WT, 8, 2>, dim3(grid), dim3(256), smem, st, pdl, a);
+    case 1: return qwen_gemv_launch_ks<WT, 1>(a, num_sms, smem, st, pdl);
+    case 2: return qwen_gemv_launch_ks<WT, 2>(a, num_sms, smem, st, pdl);
+    case 4: return qwen_gemv_launch_ks<WT, 4>(a, num_sms, smem, st, pdl);
+    default: return qwen_gemv_launch_ks<WT, 8>(a, num_sms, smem, st, pdl);
   }
-  return cudaGetLastError();
 }
 
 int qwen_gemv(b200asr_qwen* e, const float* x, int64_t ldx, bool rms, bool swiglu, const std::string& wn, const float* residual, int64_t ldr,
@@ -1220,7 +1221,7 @@ int qwen_gemv(b200asr_qwen* e, const float* x, int64_t ldx, bool rms, bool swigl
   a.x = x; a.ldx = ldx; a.rms = rms ? 1 : 0; a.eps = e->cfg.rms_eps; a.swiglu = swiglu ? 1 : 0;
   a.W = QW(e, wn); a.residual = residual; a.ldr = ldr; a.out = out; a.ldo = ldo;
   a.rows = rows; a.N = N; a.K = K;
-  const bool pdl = e->use_pdl && rows <= 2;      // measured: helps at 1-2 rows (1.22 -> 1.09 ms/step), hurts at 4 (1.86 -> 2.10)
+  const bool pdl = e->use_pdl && (rows <= 2 || e->pdl_all);      // measured: helps at 1-2 rows (1.22 -> 1.09 ms/step), hurts at 4 (1.86 -> 2.10)
   QKL(e->act == kBF16 ? qwen_gemv_launch<bf16>(a, e->num_sms, e->st, pdl) : qwen_gemv_launch<float>(a, e->num_sms, e->st, pdl));
   return B200ASR_OK;
 }
@@ -1796,7 +1797,7 @@ int b200asr_qwen_set_option(b200asr_qwen* e, const char* key, int64_t value) {
   if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "attn_tiled")) { e->use_attn_tiled = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "pdl")) {
-    e->use_pdl = value != 0;
+    e->use_pdl = value != 0; e->pdl_all = value == 2;
     if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
     return B200ASR_OK;
   }
