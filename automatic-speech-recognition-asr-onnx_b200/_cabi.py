@@ -85,6 +85,7 @@ SYMBOLS = {
     "b200asr_qwen_set_prompt": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                           C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
     "b200asr_qwen_set_decode_options": (C.c_int, [C.c_void_p, C.c_float, C.c_int32]),
+    "b200asr_qwen_set_sampling": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_uint64, C.POINTER(C.c_float), C.c_int32]),
     "b200asr_qwen_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                       C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "b200asr_qwen_prefill": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

@@ -983,6 +983,8 @@ struct b200asr_qwen {
   cudaGraphExec_t step_graph = nullptr; int graph_B = -1, graph_limit = -1; int64_t graph_nodes = 0; bool use_graph = true;
   bool use_attn_tc = true, use_attn_split = true, use_pdl = true, use_attn_tiled = true;
   float repeat_penalty = 1.0f; int penalty_range = 10;
+  float samp_temperature = 0.f, samp_top_p = 1.f, samp_rep = 1.f; int samp_top_k = 0; unsigned long long samp_seed = 0;
+  float* samp_noise = nullptr; int samp_noise_rows = 0;
   bool pdl_all = false;
   float* att_part = nullptr; int* att_counter = nullptr;
   int* h_pinned = nullptr;
@@ -1269,20 +1271,27 @@ int qwen_decoder(b200asr_qwen* e, int n_new) {
   QKL(cudaGetLastError());
   const std::string head = e->w.count("lm_head.w") ? "lm_head.w" : "embed.w";
   QRET(qwen_gemv(e, e->xl, Hd, false, false, head, nullptr, 0, e->logits, c.vocab, B, c.vocab, Hd));
-  if (n_new == 1 && e->repeat_penalty != 1.0f && e->penalty_range > 0) {      // decode steps only: the prefill head is a plain arg-max
+  const bool sampling = e->samp_temperature > 0.f;
+  if (!sampling && n_new == 1 && e->repeat_penalty != 1.0f && e->penalty_range > 0) {      // decode steps only: the prefill head is a plain arg-max
     qwen_penalty_kernel<<<B, 32, 0, e->st>>>(e->logits, c.vocab, e->save_id, c.max_seq_len, e->n_save, e->penalty_range, e->repeat_penalty);
     QKL(cudaGetLastError());
   }
-  qwen_argmax_slices_kernel<<<dim3(kArgSlices, B), 256, 0, e->st>>>(e->logits, c.vocab, e->cand_val, e->cand_idx);
-  QKL(cudaGetLastError());
   SelectArgs s{};
-  s.logits = e->cand_val; s.vocab = kArgSlices; s.cand_idx = e->cand_idx; s.batch = B; s.begin_bias = nullptr;
+  if (!sampling) {
+    qwen_argmax_slices_kernel<<<dim3(kArgSlices, B), 256, 0, e->st>>>(e->logits, c.vocab, e->cand_val, e->cand_idx);
+    QKL(cudaGetLastError());
+    s.logits = e->cand_val; s.vocab = kArgSlices; s.cand_idx = e->cand_idx;
+  } else {                       // TOPK_TOPP_SAMPLING (:1348-1400) works on the full row, on the prefill head as well (:640-644)
+    s.logits = e->logits; s.vocab = c.vocab; s.cand_idx = nullptr;
+  }
+  s.batch = B; s.begin_bias = nullptr;
   s.cur_token = e->cur_token; s.tokens = e->tokens; s.tokens_ld = c.max_seq_len; s.n_gen = e->n_gen;
   s.finished = e->finished; s.save_id = e->save_id; s.save_ld = c.max_seq_len; s.n_save = e->n_save;
   s.selected_hist = nullptr; s.sel_ld = 0;
   s.stop_ids = e->d_stop; s.n_stop = (int)e->stop_ids.size(); s.limit = e->limit;
   s.penalty_value = 1.0f; s.penalty_range = 0; s.state = e->dstate; s.n_new = n_new;
-  s.temperature = 0.f; s.top_k = 0; s.top_p = 1.f; s.rep_penalty = 1.f; s.seed = 0; s.noise = nullptr; s.noise_ld = 0; s.noise_rows = 0;
+  s.temperature = e->samp_temperature; s.top_k = e->samp_top_k; s.top_p = e->samp_top_p; s.rep_penalty = e->samp_rep;
+  s.seed = e->samp_seed; s.noise = e->samp_noise; s.noise_ld = e->samp_top_k; s.noise_rows = e->samp_noise_rows;
   QKL(launch_select_token(s, e->st));
   e->launches++;
   return B200ASR_OK;
@@ -1467,7 +1476,7 @@ void b200asr_qwen_destroy(b200asr_qwen* e) {
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
   void* bufs[] = {e->basis_t, e->fb_start, e->fb_len, e->stage_buf, e->d_stop, e->pcm, e->mel_raw, e->max_key, e->feat, e->c1, e->col, e->c2, e->c3,
                   e->stem, e->h, e->S, e->enc_out, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->win_valid, e->prompt_src, e->x, e->qkvf, e->q, e->gu,
-                  e->xl, e->logits, e->cand_val, e->cand_idx, e->att_part, e->att_counter, e->xn, e->actx, e->mlp, e->kc, e->vc, e->dstate, e->cur_token, e->tokens, e->n_gen, e->finished, e->save_id, e->n_save};
+                  e->xl, e->logits, e->cand_val, e->cand_idx, e->att_part, e->att_counter, e->samp_noise, e->xn, e->actx, e->mlp, e->kc, e->vc, e->dstate, e->cur_token, e->tokens, e->n_gen, e->finished, e->save_id, e->n_save};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -1568,6 +1577,25 @@ int b200asr_qwen_set_decode_options(b200asr_qwen* e, float repeat_penalty, int32
   if (penalty_range < 0 || !(repeat_penalty > 0.f)) return e->fail(B200ASR_E_INVALID, "bad penalty options");
   e->repeat_penalty = repeat_penalty; e->penalty_range = penalty_range;
   if (e->step_graph) { cudaSetDevice(e->cfg.device); cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+  return B200ASR_OK;
+}
+
+int b200asr_qwen_set_sampling(b200asr_qwen* e, float temperature, int32_t top_k, float top_p, float repetition_penalty, uint64_t seed,
+                              const float* noise_host, int32_t noise_rows) {
+  if (!e) return B200ASR_E_INVALID;
+  QCK(cudaSetDevice(e->cfg.device));
+  if (temperature > 0.f && (top_k < 1 || top_k > 64 || top_k > e->cfg.vocab || !(top_p > 0.f) || !(repetition_penalty > 0.f)))
+    return e->fail(B200ASR_E_INVALID, "bad sampling options (1 <= top_k <= 64, top_p > 0, repetition_penalty > 0)");
+  e->samp_temperature = temperature; e->samp_top_k = top_k; e->samp_top_p = top_p; e->samp_rep = repetition_penalty; e->samp_seed = seed;
+  if (e->samp_noise) { cudaFree(e->samp_noise); e->samp_noise = nullptr; }
+  e->samp_noise_rows = 0;
+  if (temperature > 0.f && noise_host && noise_rows > 0) {
+    const size_t n = (size_t)noise_rows * e->cfg.max_batch * top_k;
+    QCK(cudaMalloc(&e->samp_noise, n * 4));
+    QCK(cudaMemcpy(e->samp_noise, noise_host, n * 4, cudaMemcpyHostToDevice));
+    e->samp_noise_rows = noise_rows;
+  }
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
   return B200ASR_OK;
 }
 

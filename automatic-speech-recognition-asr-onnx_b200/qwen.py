@@ -285,6 +285,19 @@ class QwenEngine:
         self._ck(self.lib.b200asr_qwen_set_decode_options(self.h, float(repeat_penalty), int(penalty_range)))
         self.repeat_penalty, self.penalty_range = float(repeat_penalty), int(penalty_range)
 
+    def set_sampling(self, temperature: float = 0.0, top_k: int = 10, top_p: float = 0.95, repetition_penalty: float = 1.0,
+                     seed: int = 0, noise: Optional[np.ndarray] = None):
+        """temperature > 0 = the script's sampling strategy (USE_SAMPLING, :85-89); noise [launch][max_batch][top_k] in (0,1)
+        replaces the head's random draw for reproducible runs."""
+        nz, rows = None, 0
+        if noise is not None:
+            nz = np.ascontiguousarray(noise, dtype=np.float32)
+            if nz.ndim != 3 or nz.shape[1] != self.max_batch or nz.shape[2] != top_k:
+                raise ValueError("noise must be [launch][max_batch][top_k]")
+            rows = nz.shape[0]
+        self._ck(self.lib.b200asr_qwen_set_sampling(self.h, float(temperature), int(top_k), float(top_p), float(repetition_penalty),
+                                                    int(seed), nz.ctypes.data_as(_cabi._F32P) if nz is not None else None, rows))
+
     @property
     def stream_ptr(self) -> int:
         return int(self.lib.b200asr_qwen_stream(self.h) or 0)

@@ -229,6 +229,11 @@ int b200asr_qwen_set_prompt(b200asr_qwen* e, const int32_t* head_ids, int32_t n_
  * penalty_range selected ids are multiplied by repeat_penalty before the arg-max (APPLY_PENALTY, Export_Qwen_ASR.py:1403-1415).
  * The engine starts in greedy mode. */
 int b200asr_qwen_set_decode_options(b200asr_qwen* e, float repeat_penalty, int32_t penalty_range);
+/* sampling strategy (USE_SAMPLING, Inference_Qwen_ASR_ONNX.py:85-89): temperature > 0 selects TOPK_TOPP_SAMPLING
+ * (Export_Qwen_ASR.py:1348-1400, the same head as Whisper's) on the prefill and every decode head; temperature <= 0 returns to
+ * the arg-max heads.  noise_host [noise_rows][max_batch][top_k] uniform (0,1) makes a run reproducible (NULL = counter hash of seed). */
+int b200asr_qwen_set_sampling(b200asr_qwen* e, float temperature, int32_t top_k, float top_p, float repetition_penalty, uint64_t seed,
+                              const float* noise_host, int32_t noise_rows);
 /* pcm [batch][n_samples]: int16 (scaled by 1/32768 on device) or float32 in [-1,1].  Leaves the prompt embedding
  * [head | query | suffix | audio | tail | language tail] in HBM; n_prompt_out = its length. */
 int b200asr_qwen_encode(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,

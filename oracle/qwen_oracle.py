@@ -398,3 +398,36 @@ def greedy_transcribe(pcm_int16: np.ndarray, fw, d: QwenDims, prompt: QwenPrompt
             st.update(features=feat, audio_hidden=audio_hidden, prompt_embed=emb, logits=torch.stack(all_logits))
             return tokens, st
         return tokens
+
+
+def sampling_transcribe(pcm_int16: np.ndarray, fw, d: QwenDims, prompt: QwenPrompt, query_ids: Sequence[int], language_tail_ids: Sequence[int],
+                        max_new: int, temperature: float, top_k: int, top_p: float, repetition_penalty: float, noise: np.ndarray):
+    """The script's `sampling` strategy (Inference_Qwen_ASR_ONNX.py:369-376,640-644,697-737): TOPK_TOPP_SAMPLING
+    (Export_Qwen_ASR.py:1348-1400 -- line for line the Whisper head, restated in whisper_oracle.topk_topp_sample and pinned
+    there to the reference class) on the prefill logits with an empty history, then on every decode step with all ids
+    selected so far.  noise [launch][top_k] replaces the head's rand_like draw."""
+    with torch.no_grad():
+        feat = features(prepare_audio(pcm_int16), fw, d)
+        emb = build_prompt_embed(audio_encoder(feat, fw, d), fw, prompt, query_ids, language_tail_ids)
+        limit = min(max(d.max_seq_len - 10 - emb.shape[0], 0), int(max_new))
+        stop = set(int(s) for s in prompt.stop_ids)
+        logits, kv = decoder(emb, 0, empty_kv(d), fw, d)
+        kv_len = emb.shape[0]
+        save_id = torch.zeros(1, 0, dtype=torch.int32)
+        sampled, save_id = wo.topk_topp_sample(logits.unsqueeze(0), temperature, top_k, top_p, repetition_penalty, save_id, noise[0:1])
+        tok = int(sampled[0, 0])
+        tokens, count, step = [], 0, 0
+        if tok not in stop and limit > 0:
+            count = 1
+            tokens.append(tok)
+        while count < limit and tok not in stop:
+            logits, kv = decoder(fw["embed.w"][tok].unsqueeze(0), kv_len, kv, fw, d)
+            kv_len += 1
+            step += 1
+            sampled, save_id = wo.topk_topp_sample(logits.unsqueeze(0), temperature, top_k, top_p, repetition_penalty, save_id,
+                                                   noise[step:step + 1])
+            tok = int(sampled[0, 0])
+            if tok not in stop:
+                count += 1
+                tokens.append(tok)
+        return tokens

@@ -229,3 +229,24 @@ def test_qwen_tiled_prefill_attention_equals_row_kernel(precision):
     assert d <= (5e-5 if precision == "f32" else 1e-2)
     if precision == "f32":
         assert out[1][1] == out[0][1]
+
+
+@pytest.mark.parametrize("t,k,p,rp", [(0.8, 10, 0.95, 1.0), (1.3, 6, 0.7, 1.2)])
+def test_qwen_sampling_strategy_vs_oracle(t, k, p, rp):
+    """USE_SAMPLING strategy with the head's uniform noise supplied: the device loop picks the oracle's ids (the head is the
+    Whisper TOPK_TOPP_SAMPLING, pinned to the reference class in tests/golden/whisper_heads.npz)."""
+    g = dict(np.load(GOLD[3]))
+    q, l = g["query_ids"].tolist(), g["language_tail_ids"].tolist()
+    noise = np.random.default_rng(3).uniform(0.01, 0.99, size=(14, k)).astype(np.float32)
+    fw = qo.fold_weights(qo.make_raw_weights(qo.TINY_TEST, int(g["seed"])), qo.TINY_TEST)
+    want = qo.sampling_transcribe(g["pcm"], fw, qo.TINY_TEST, qo.TINY_PROMPT, q, l, 10, t, k, p, rp, noise)
+    eng = _engine(int(g["seed"]), "f32")
+    eng.set_sampling(temperature=t, top_k=k, top_p=p, repetition_penalty=rp, noise=noise.reshape(14, 1, k))
+    got = eng.transcribe(g["pcm"], q, l, max_new=10)[0]
+    assert got == want
+    eng.set_sampling(temperature=t, top_k=k, top_p=p, repetition_penalty=rp, seed=5)        # hashed noise: reproducible per seed
+    a, b = eng.transcribe(g["pcm"], q, l, max_new=8)[0], eng.transcribe(g["pcm"], q, l, max_new=8)[0]
+    assert a == b
+    eng.set_sampling(temperature=0.0)
+    assert eng.transcribe(g["pcm"], q, l, max_new=int(g["max_new"]))[0] == g["tokens"].tolist()
+    eng.close()
