@@ -59,31 +59,52 @@ __global__ void qwen_feat_kernel(const float* __restrict__ mel_raw, const int* _
   }
 }
 
-// ---- conv2d1 (1 -> C, 3x3, stride 2, pad 1) + tanh-GELU, channel-last output [chunk][50][64][C] ----
+// ---- conv2d1 (1 -> C, 3x3, stride 2, pad 1) + tanh-GELU, channel-last output [chunk][50][64][C]: weights and bias live in
+//      shared memory, a thread keeps the 9 input taps of one output position in registers and emits 8 channels per store ----
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 qwen_conv1_kernel(const float* __restrict__ feat /*[chunks][100][n_mels]*/, const float* __restrict__ w /*[C][3 mel][3 time]*/,
-                  const float* __restrict__ bias, int n_mels, int C, int To, int Fo, int64_t total, OutT* __restrict__ out) {
+                  const float* __restrict__ bias, int n_mels, int C, int To, int Fo, int64_t total /*positions x C/8*/, OutT* __restrict__ out) {
+  extern __shared__ float cw[];                  // [C][9] weights | [C] bias
+  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) cw[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) cw[C * 9 + i] = bias[i];
+  __syncthreads();
+  // work item -> (channel group, position): gw neighbouring lanes take neighbouring 8-channel groups of one position (one
+  // contiguous store run), the next lanes the next positions; a group block [gw] is the slowest index so the weight reads of a
+  // warp touch few distinct rows
+  const int cg = C / 8;
+  const int gw = (cg % 4 == 0) ? 4 : ((cg % 2 == 0) ? 2 : 1);
+  const int64_t n_pos = total / cg;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int co = (int)(i % C);
-    int64_t r = i / C;
+    const int g_lo = (int)(i % gw);
+    int64_t r = (i / gw) % n_pos;
+    const int c0 = ((int)(i / (gw * n_pos)) * gw + g_lo) * 8;
     const int fo = (int)(r % Fo); r /= Fo;
     const int to = (int)(r % To);
     const int64_t chunk = r / To;
     const float* in = feat + chunk * kChunk * n_mels;
-    float acc = bias[co];
+    float tap[9];
 #pragma unroll
     for (int kf = 0; kf < 3; ++kf) {
       const int f = 2 * fo - 1 + kf;
-      if (f < 0 || f >= n_mels) continue;
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
         const int t = 2 * to - 1 + kt;
-        if (t < 0 || t >= kChunk) continue;
-        acc = fmaf(w[co * 9 + kf * 3 + kt], in[t * n_mels + f], acc);
+        tap[kf * 3 + kt] = (f >= 0 && f < n_mels && t >= 0 && t < kChunk) ? in[t * n_mels + f] : 0.f;
       }
     }
-    out[i] = from_f<OutT>(gelu_tanh(acc));
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float* wc = cw + (c0 + c) * 9;
+      float acc = cw[C * 9 + c0 + c];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc = fmaf(wc[k], tap[k], acc);
+      o[c] = gelu_tanh(acc);
+    }
+    OutT* dst = out + ((chunk * To + to) * Fo + fo) * (int64_t)C + c0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dst[c] = from_f<OutT>(o[c]);
   }
 }
 
@@ -1071,9 +1092,10 @@ int qwen_encoder(b200asr_qwen* e) {
   const int T1 = 50, T2 = 25, T3 = 13;
   const int F1 = (c.n_mels + 1) / 2, F2 = (F1 + 1) / 2, F3 = (F2 + 1) / 2;
   {
-    const int64_t total = chunks * T1 * F1 * C;
-    if (ad == kBF16) qwen_conv1_kernel<bf16><<<grid_for(total, 256, 148 * 32), 256, 0, e->st>>>(e->feat, QWF(e, "conv1.w"), QWF(e, "conv1.b"), c.n_mels, C, T1, F1, total, (bf16*)e->c1);
-    else qwen_conv1_kernel<float><<<grid_for(total, 256, 148 * 32), 256, 0, e->st>>>(e->feat, QWF(e, "conv1.w"), QWF(e, "conv1.b"), c.n_mels, C, T1, F1, total, (float*)e->c1);
+    const int64_t total = chunks * T1 * F1 * (C / 8);
+    const size_t csm = (size_t)C * 10 * sizeof(float);
+    if (ad == kBF16) qwen_conv1_kernel<bf16><<<grid_for(total, 256, 148 * 8), 256, csm, e->st>>>(e->feat, QWF(e, "conv1.w"), QWF(e, "conv1.b"), c.n_mels, C, T1, F1, total, (bf16*)e->c1);
+    else qwen_conv1_kernel<float><<<grid_for(total, 256, 148 * 8), 256, csm, e->st>>>(e->feat, QWF(e, "conv1.w"), QWF(e, "conv1.b"), c.n_mels, C, T1, F1, total, (float*)e->c1);
     QKL(cudaGetLastError());
   }
   auto conv = [&](const void* in, int Ti, int Fi, int To, int Fo, const char* wn, const char* bn, void* out) -> int {

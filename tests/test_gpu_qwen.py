@@ -250,3 +250,25 @@ def test_qwen_sampling_strategy_vs_oracle(t, k, p, rp):
     eng.set_sampling(temperature=0.0)
     assert eng.transcribe(g["pcm"], q, l, max_new=int(g["max_new"]))[0] == g["tokens"].tolist()
     eng.close()
+
+
+@pytest.mark.parametrize("n_samples", [480, 1599, 16000, 31999, 128000, 128160, 129600, 200000])
+def test_qwen_clip_length_edges_vs_oracle(n_samples):
+    """Chunk / window bookkeeping at its edges (Export_Qwen_ASR.py:860-897): shortest clip the STFT accepts, 9 frames (one
+    token), exactly one 100-frame chunk, one frame short of two chunks, exactly one 8-chunk window, one frame into the second
+    window (a window with a single valid key), a partial second window, and the longest clip of this engine -- fp32 engine
+    against the oracle: token count, audio tower output, prefill logits (1e-3) and the greedy stream."""
+    rng = np.random.default_rng(n_samples)
+    pcm = (rng.standard_normal(n_samples) * 3000).clip(-32768, 32767).astype(np.int16)
+    fw = qo.fold_weights(qo.make_raw_weights(qo.TINY_TEST, 6), qo.TINY_TEST)
+    want, st = qo.greedy_transcribe(pcm, fw, qo.TINY_TEST, qo.TINY_PROMPT, (3,), (), max_new=6, return_stages=True)
+    eng = _engine(6, "f32")
+    n_prompt = eng.encode(pcm, (3,), ())
+    na = D.audio_tokens(n_samples)
+    assert na == st["audio_hidden"].shape[0] and n_prompt == st["prompt_embed"].shape[0]
+    ah = eng.get_stage("audio_hidden", max(na, 1) * D.out_dim)[:na * D.out_dim].reshape(na, D.out_dim)
+    np.testing.assert_allclose(ah, st["audio_hidden"].numpy(), atol=1e-3)
+    lg, _ = eng.prefill()
+    np.testing.assert_allclose(lg[0], st["logits"][0].numpy(), atol=1e-3)
+    assert eng.transcribe(pcm, (3,), (), max_new=6)[0] == want
+    eng.close()
