@@ -548,14 +548,16 @@ qwen_attn_decode_kernel(const float* __restrict__ qkv /*[B][(H+2KH)*DH]*/, const
 //      so the whole step costs one memory round trip; the CTA that finishes last (ticket counter) merges the S partial
 //      (max, sum, unnormalised output) triples into the context row ----
 constexpr int kSplitKeys = 128;
-template <int DH>
-__global__ void __launch_bounds__(256)
+// SK = keys per range (<= 256 = one per thread); VPF = V rows requested into registers up front (SK 128) or walked in an
+// unrolled loop (SK 256: batches of 3-4 clips, where 4 ranges per head keep the grid inside one resident wave)
+template <int DH, int SK, bool VPF>
+__global__ void __launch_bounds__(256, VPF ? 1 : 2)
 qwen_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ g, const float* __restrict__ cosT,
                        const float* __restrict__ sinT, float eps, bf16* __restrict__ kc, bf16* __restrict__ vc, int64_t cache_layer_off,
                        int H, int KH, int max_seq, const DecState* __restrict__ state, float* __restrict__ part /*[B*H][S][DH+2]*/,
                        int* __restrict__ counter /*[B*H]*/, float* __restrict__ ctx) {
-  constexpr int M = DH / 32, half = DH / 2, EPL = DH / 32, VK = kSplitKeys / 8;
-  __shared__ float qs[DH], kn[DH], vn[DH], sc[kSplitKeys], red[8], pw[8][DH];
+  constexpr int M = DH / 32, half = DH / 2, EPL = DH / 32, VK = SK / 8;
+  __shared__ float qs[DH], kn[DH], vn[DH], sc[SK], red[8], pw[8][DH];
   __shared__ int s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
@@ -570,20 +572,22 @@ qwen_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ 
   // ---- every cache load of this CTA, up front ----
   uint4 kreg[DH / 8];
   const int jk = lo + threadIdx.x;
-  const bool k_cached = threadIdx.x < kSplitKeys && jk < hi && jk != pos;
+  const bool k_cached = threadIdx.x < SK && jk < hi && jk != pos;
   if (k_cached) {
     const uint4* kr = reinterpret_cast<const uint4*>(K + (int64_t)jk * DH);
 #pragma unroll
     for (int c = 0; c < DH / 8; ++c) kreg[c] = kr[c];
   }
-  uint32_t vreg[VK][EPL / 2];
+  uint32_t vreg[VPF ? VK : 1][EPL / 2];
+  if (VPF) {
 #pragma unroll
-  for (int i = 0; i < VK; ++i) {
-    const int j = lo + warp + 8 * i;
-    if (j < hi && j != pos) {
-      const uint32_t* vr = reinterpret_cast<const uint32_t*>(V + (int64_t)j * DH + lane * EPL);
+    for (int i = 0; i < VK; ++i) {
+      const int j = lo + warp + 8 * i;
+      if (j < hi && j != pos) {
+        const uint32_t* vr = reinterpret_cast<const uint32_t*>(V + (int64_t)j * DH + lane * EPL);
 #pragma unroll
-      for (int e = 0; e < EPL / 2; ++e) vreg[i][e] = vr[e];
+        for (int e = 0; e < EPL / 2; ++e) vreg[VPF ? i : 0][e] = vr[e];
+      }
     }
   }
   pdl_launch_dependents();
@@ -627,7 +631,7 @@ qwen_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ 
   }
   __syncthreads();
   float s = -INFINITY;
-  if (threadIdx.x < kSplitKeys && jk < hi) {
+  if (threadIdx.x < SK && jk < hi) {
     s = 0.f;
     if (jk == pos) {
 #pragma unroll 8
@@ -653,7 +657,7 @@ qwen_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ 
   for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
   __syncthreads();
   float p = 0.f;
-  if (threadIdx.x < kSplitKeys && jk < hi) { p = expf(s - mx); sc[threadIdx.x] = p; }
+  if (threadIdx.x < SK && jk < hi) { p = expf(s - mx); sc[threadIdx.x] = p; }
   float sum = warp_sum(p);
   if (lane == 0) red[warp] = sum;
   __syncthreads();
@@ -663,21 +667,38 @@ qwen_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ 
   float acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  auto pv_step = [&](int j, const uint32_t* vv) {
+    const float pj = sc[j - lo];
+    if (j == pos) {
 #pragma unroll
-  for (int i = 0; i < VK; ++i) {
-    const int j = lo + warp + 8 * i;
-    if (j < hi) {
-      const float pj = sc[j - lo];
-      if (j == pos) {
+      for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pj, vn[lane * EPL + e], acc[e]);
+    } else {
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pj, vn[lane * EPL + e], acc[e]);
-      } else {
+      for (int e = 0; e < EPL / 2; ++e) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[e]));
+        acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
+        acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
+      }
+    }
+  };
+  if constexpr (VPF) {
 #pragma unroll
-        for (int e = 0; e < EPL / 2; ++e) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vreg[i][e]));
-          acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
-          acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
+    for (int i = 0; i < VK; ++i) {
+      const int j = lo + warp + 8 * i;
+      if (j < hi) pv_step(j, vreg[i]);
+    }
+  } else {
+#pragma unroll 8
+    for (int i = 0; i < VK; ++i) {
+      const int j = lo + warp + 8 * i;
+      if (j < hi) {
+        uint32_t vv[EPL / 2];
+        if (j != pos) {
+          const uint32_t* vr = reinterpret_cast<const uint32_t*>(V + (int64_t)j * DH + lane * EPL);
+#pragma unroll
+          for (int e = 0; e < EPL / 2; ++e) vv[e] = vr[e];
         }
+        pv_step(j, vv);
       }
     }
   }
@@ -1181,9 +1202,14 @@ int qwen_attention_launch(b200asr_qwen* e, int layer, int rows, int n_new, bool 
   const float *cosT = QWF(e, "rope_cos"), *sinT = QWF(e, "rope_sin");
   if (gemv) {        // one fused launch: QK-norm + RoPE + cache append + attention
     const size_t dsmem = (size_t)(3 * DH + c.max_seq_len + (kAttDecThreads / 32) * DH) * sizeof(float);
-    const int S = (c.max_seq_len + kSplitKeys - 1) / kSplitKeys;
-    if (ad == kBF16 && e->use_attn_split && rows * H * S <= 2 * e->num_sms) {      // larger batches already fill the machine with one CTA per head
-      QKL(launch_pdl(qwen_attn_split_kernel<DH>, dim3(rows * H, S), dim3(256), 0, e->st, e->use_pdl && (rows <= 2 || e->pdl_all), (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, e->att_part, e->att_counter, (float*)e->actx));
+    const int S = (c.max_seq_len + kSplitKeys - 1) / kSplitKeys, S2 = (c.max_seq_len + 2 * kSplitKeys - 1) / (2 * kSplitKeys);
+    const bool pdl_att = e->use_pdl && (rows <= 2 || e->pdl_all);
+    if (ad == kBF16 && e->use_attn_split && rows * H * S <= 2 * e->num_sms) {      // 1-2 clips: (head, 128-key range) CTAs with every cache row in registers (measured better than 256-key ranges at 2 clips: 1.10 vs 1.16 ms/step)
+      QKL(launch_pdl(qwen_attn_split_kernel<DH, kSplitKeys, true>, dim3(rows * H, S), dim3(256), 0, e->st, pdl_att, (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, e->att_part, e->att_counter, (float*)e->actx));
+      return B200ASR_OK;
+    }
+    if (ad == kBF16 && e->use_attn_split && rows * H * S2 <= 2 * e->num_sms) {     // 3-4 clips: 256-key ranges keep the grid inside one wave
+      QKL(launch_pdl(qwen_attn_split_kernel<DH, 2 * kSplitKeys, false>, dim3(rows * H, S2), dim3(256), 0, e->st, pdl_att, (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, e->att_part, e->att_counter, (float*)e->actx));
       return B200ASR_OK;
     }
     if (ad == kBF16) QKL(launch_pdl(qwen_attn_decode_kernel<bf16, DH>, dim3(rows * H), dim3(kAttDecThreads), dsmem, e->st, e->use_pdl && (rows <= 2 || e->pdl_all), (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (float*)e->actx));
