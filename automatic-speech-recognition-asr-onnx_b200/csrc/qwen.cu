@@ -1409,6 +1409,11 @@ int qwen_encode_resident(b200asr_qwen* e, const int32_t* query_ids, int32_t n_qu
   for (int i = 0; i < e->n_audio; ++i) src.push_back(-i - 1);
   push_ids(e->tail_ids.data(), e->tail_ids.size());
   push_ids(lang_ids, (size_t)n_lang);
+  for (int i = 0; i < n_query; ++i) if (query_ids[i] < 0) return e->fail(B200ASR_E_INVALID, "prompt token id out of range");
+  for (int i = 0; i < n_lang; ++i) if (lang_ids[i] < 0) return e->fail(B200ASR_E_INVALID, "prompt token id out of range");
+  for (int v : e->head_ids) if (v < 0) return e->fail(B200ASR_E_INVALID, "prompt token id out of range");
+  for (int v : e->suffix_ids) if (v < 0) return e->fail(B200ASR_E_INVALID, "prompt token id out of range");
+  for (int v : e->tail_ids) if (v < 0) return e->fail(B200ASR_E_INVALID, "prompt token id out of range");
   for (int v : src) if (v >= c.vocab) return e->fail(B200ASR_E_INVALID, "prompt token id out of range");
   e->n_prompt = (int)src.size();
   if (e->n_prompt > c.max_seq_len) return e->fail(B200ASR_E_INVALID, "prompt longer than max_seq_len");

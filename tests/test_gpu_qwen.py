@@ -138,6 +138,8 @@ def test_qwen_float_pcm_and_errors():
         eng.transcribe(g["pcm"][:100])
     with pytest.raises(Exception, match="out of range"):
         eng.transcribe(g["pcm"], query_ids=[D.vocab + 5])
+    with pytest.raises(Exception, match="out of range"):
+        eng.transcribe(g["pcm"], language_tail_ids=[-3])
     with pytest.raises(Exception, match="before"):
         eng.encode(g["pcm"]); eng.decode_step()
     eng.close()
