@@ -42,7 +42,8 @@ struct AttArgs {
 // DH = head dimension (64: Whisper; 128: SenseVoice / Paraformer).  A 128-wide head is two 64-column SWIZZLE_128B tiles per
 // operand: the Q K^T contraction walks both (8 k16 steps), V is an MN-major B operand with two 64-wide N blocks LBO apart,
 // O takes 128 TMEM columns (scores then fit T <= 384; shared memory holds K and V for T <= 256).
-template <int DH>
+// MASK = the optional additive key mask (kv_valid) is compiled in; the unmasked instantiation keeps the soft-max loops lean
+template <int DH, bool MASK>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) {
   constexpr int NH = DH / 64;                         // 64-column tiles per operand row
@@ -138,8 +139,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
     const int q4 = warp & 3, half = warp >> 2;
     const int r = q4 * 32 + lane;                     // 0..127
     const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
-    const int kvl = a.kv_valid ? a.kv_valid[b] : T;
-    const float madd = a.mask_add;
+    const int kvl = MASK ? a.kv_valid[b] : T;
+    const float madd = MASK ? a.mask_add : 0.f;
     mbar_wait(&bar_s, 0, "attention_tc");
     tc_fence_after();
     float m = -INFINITY;
@@ -148,7 +149,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
       tmem_ld32(lane_base + (uint32_t)c0, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (c0 + i < T) m = fmaxf(m, __uint_as_float(v[i]) + (c0 + i >= kvl ? madd : 0.f));
+        if (c0 + i < T) m = fmaxf(m, __uint_as_float(v[i]) + ((MASK && c0 + i >= kvl) ? madd : 0.f));
     }
     s_mx[half][r] = m;
     asm volatile("bar.sync 1, %0;" ::"n"(kAttSoftmaxWarps * 32) : "memory");
@@ -168,8 +169,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttArgs a) 
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float e0 = 0.f, e1 = 0.f;
-            if (c0 + i < T) e0 = exp2f(fmaf(__uint_as_float(v[i]) + (c0 + i >= kvl ? madd : 0.f), 1.4426950408889634f, -ml2));
-            if (c0 + i + 1 < T) e1 = exp2f(fmaf(__uint_as_float(v[i + 1]) + (c0 + i + 1 >= kvl ? madd : 0.f), 1.4426950408889634f, -ml2));
+            if (c0 + i < T) e0 = exp2f(fmaf(__uint_as_float(v[i]) + ((MASK && c0 + i >= kvl) ? madd : 0.f), 1.4426950408889634f, -ml2));
+            if (c0 + i + 1 < T) e1 = exp2f(fmaf(__uint_as_float(v[i + 1]) + ((MASK && c0 + i + 1 >= kvl) ? madd : 0.f), 1.4426950408889634f, -ml2));
             sum += e0 + e1;
             const __nv_bfloat162 p2 = __floats2bfloat162_rn(e0, e1);
             packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&p2);
@@ -241,8 +242,10 @@ cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, in
   const size_t smem = (size_t)(nh + 2 * nkb * nh + 2) * kAttTile + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t r = cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * kAttTile + 1024);
-    if (r == cudaSuccess) r = cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kAttTile + 1024);
+    cudaError_t r = cudaFuncSetAttribute(attention_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * kAttTile + 1024);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(attention_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * kAttTile + 1024);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(attention_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kAttTile + 1024);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(attention_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kAttTile + 1024);
     if (r != cudaSuccess) return r;
     attr_done = true;
   }
@@ -251,8 +254,13 @@ cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, in
   AttArgs a;
   a.ctx = reinterpret_cast<bf16*>(ctx); a.ld_ctx = d; a.T = T; a.d = d; a.n_heads = n_heads; a.kv_valid = kv_valid; a.mask_add = mask_add;
   dim3 grid((T + kAttBM - 1) / kAttBM, n_heads, batch);
-  if (dh == 64) attention_tc_kernel<64><<<grid, kAttThreads, smem, st>>>(tm, a);
-  else attention_tc_kernel<128><<<grid, kAttThreads, smem, st>>>(tm, a);
+  if (dh == 64) {
+    if (kv_valid) attention_tc_kernel<64, true><<<grid, kAttThreads, smem, st>>>(tm, a);
+    else attention_tc_kernel<64, false><<<grid, kAttThreads, smem, st>>>(tm, a);
+  } else {
+    if (kv_valid) attention_tc_kernel<128, true><<<grid, kAttThreads, smem, st>>>(tm, a);
+    else attention_tc_kernel<128, false><<<grid, kAttThreads, smem, st>>>(tm, a);
+  }
   return cudaGetLastError();
 }
 
