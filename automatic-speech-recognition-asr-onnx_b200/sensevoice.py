@@ -289,3 +289,45 @@ def transcribe_clip(engine: SenseVoiceEngine, raw_audio_int16: np.ndarray, langu
     elapsed = time.time() - t0
     audio_s = pcm.shape[1] / sample_rate
     return dict(tokens=tokens, language=code, elapsed_s=elapsed, rtf=elapsed / audio_s)
+
+
+def transcribe_long(engine, raw_audio_int16: np.ndarray, language: str = "auto", *, input_audio_length: Optional[int] = None,
+                    sliding_window: int = 0, sample_rate: int = 16000):
+    """The scripts' window loop (Inference_SenseVoice_ONNX.py:236-260,290-307; Paraformer :233-257,284-300): a graph exported
+    with a static audio length sees the clip as windows of `input_audio_length` samples, stride `sliding_window` (<= 0: the
+    window length), the tail zero-padded; the per-window token ids are concatenated.  `input_audio_length=None` = the dynamic
+    axis (one window = the whole clip).  The windows are independent, so they go through the engine as batches of up to
+    `engine.max_batch` clips instead of one run per window.  Works for SenseVoiceEngine and ParaformerEngine."""
+    import time
+    from .ort_io import resolve_supported_language
+    from .whisper_infer import plan_windows
+    sel = 0
+    code = None
+    if not isinstance(engine, _paraformer_engine_type()):
+        code, entry = resolve_supported_language(build_supported_languages(), language)
+        sel = entry["selector_index"]
+    pcm = np.asarray(raw_audio_int16, dtype=np.int16).reshape(-1)
+    audio_len = pcm.shape[0]
+    win = audio_len if input_audio_length is None else int(input_audio_length)
+    if win > engine.max_samples:
+        raise ValueError(f"window of {win} samples exceeds the engine's max_samples {engine.max_samples}")
+    n_win, stride, aligned = plan_windows(audio_len, win, sliding_window)
+    padded = np.zeros(aligned, np.int16)
+    padded[:audio_len] = pcm
+    clips = np.stack([padded[i * stride:i * stride + win] for i in range(n_win)])
+    t0 = time.time()
+    tokens: List[int] = []
+    per_window: List[List[int]] = []
+    for i in range(0, n_win, engine.max_batch):
+        for toks in engine.run(clips[i:i + engine.max_batch], sel):
+            per_window.append(toks)
+            tokens.extend(toks)
+    elapsed = time.time() - t0
+    return dict(tokens=tokens, per_window=per_window, windows=n_win, language=code, elapsed_s=elapsed,
+                rtf=elapsed / (audio_len / sample_rate))
+
+
+def _paraformer_engine_type():
+    from .paraformer import ParaformerEngine
+    return ParaformerEngine
+

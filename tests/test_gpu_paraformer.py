@@ -94,3 +94,21 @@ def test_paraformer_batched_decoder_equals_per_clip(precision):
         fw = po.fold_weights(po.make_raw_weights(po.TINY_TEST, int(g["seed"])), po.TINY_TEST, D.lfr_frames(MAX_SAMPLES))
         with torch.no_grad():
             assert out[1][0] == [po.transcribe(clips[i], fw, po.TINY_TEST) for i in range(4)]
+
+
+def test_paraformer_sliding_windows_vs_oracle():
+    from b200asr import sensevoice as sv
+    g = dict(np.load(GOLD[0]))
+    rng = np.random.default_rng(4)
+    pcm = (rng.standard_normal(90000) * 2500).clip(-32768, 32767).astype(np.int16)
+    eng = _engine(int(g["seed"]), "f32", max_batch=2)
+    res = sv.transcribe_long(eng, pcm, input_audio_length=40000, sliding_window=0)
+    fw = po.fold_weights(po.make_raw_weights(po.TINY_TEST, int(g["seed"])), po.TINY_TEST, D.lfr_frames(MAX_SAMPLES))
+    padded = np.zeros(120000, np.int16)
+    padded[:90000] = pcm
+    want = []
+    with torch.no_grad():
+        for i in range(3):
+            want.extend(po.transcribe(padded[i * 40000:(i + 1) * 40000], fw, po.TINY_TEST))
+    assert res["windows"] == 3 and res["tokens"] == want
+    eng.close()

@@ -138,3 +138,27 @@ def test_sensevoice_pdl_gemm_launch_is_transparent():
         eng.close()
     for o in outs[1:]:
         assert np.array_equal(o[0], outs[0][0]) and o[1] == outs[0][1]
+
+
+@pytest.mark.parametrize("window,stride", [(32000, 0), (32000, 20000), (None, 0)])
+def test_sensevoice_sliding_windows_vs_oracle(window, stride):
+    """The script's window loop (static-length export): windows batched through the engine == the oracle run window by window
+    on the zero-padded clip, ids concatenated in order."""
+    g = dict(np.load(GOLD[0]))
+    rng = np.random.default_rng(9)
+    pcm = (rng.standard_normal(100000) * 2500).clip(-32768, 32767).astype(np.int16)
+    eng = _engine(int(g["seed"]), "f32", max_batch=3)
+    res = sv.transcribe_long(eng, pcm, "English", input_audio_length=window, sliding_window=stride)
+    fw = so.fold_weights(so.make_raw_weights(so.TINY_TEST, int(g["seed"])), so.TINY_TEST, D.lfr_frames(MAX_SAMPLES))
+    win = len(pcm) if window is None else window
+    st = win if stride <= 0 else stride
+    n_win = 1 if len(pcm) <= win else int(np.ceil((len(pcm) - win) / st)) + 1
+    padded = np.zeros((n_win - 1) * st + win, np.int16)
+    padded[:len(pcm)] = pcm
+    want = []
+    with torch.no_grad():
+        for i in range(n_win):
+            want.extend(so.transcribe(padded[i * st:i * st + win], fw, so.TINY_TEST, 2))
+    assert res["windows"] == n_win and res["language"] == "en"
+    assert res["tokens"] == want
+    eng.close()
