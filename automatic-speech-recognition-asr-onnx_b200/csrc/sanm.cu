@@ -5,8 +5,9 @@
 // /root/reference/SenseVoice/Export_SenseVoice.py:271-296 (block :227-258, folds :208-220, front end :139-169).
 //
 // Linear layers run on the engine's GEMMs (tcgen05 in bf16 mode, CUDA cores in the fp32 parity mode); attention uses
-// the fused tcgen05 kernel when the head dimension is 64 and the unfused batched products otherwise (SenseVoiceSmall
-// has head_dim 128); the kernels in this file are the HBM-bound pieces around them.
+// the fused tcgen05 kernel (64- and 128-wide heads; SenseVoiceSmall / Paraformer have 128) up to 256 positions and the
+// unfused batched products beyond or in fp32 mode; the kernels in this file are the HBM-bound pieces around them.  The
+// Paraformer decoder runs once over the stacked token rows of all clips of a batch (segment-aware FSMN / cross-attention).
 #include "common.cuh"
 #include "../../include/b200asr.h"
 
