@@ -22,7 +22,8 @@ using namespace b200asr;
 namespace {
 
 constexpr int kFbFrames = 8;          // frames per CTA of the fbank kernel
-constexpr int kFbThreads = 288;       // >= nfft/2 + 1 = 257 frequency bins
+constexpr int kFbBins = 288;          // >= nfft/2 + 1 = 257 frequency bins
+constexpr int kFbThreads = 2 * kFbBins;   // two thread groups split the window taps (the loop is bound by the basis reads)
 
 // ---- Kaldi fbank: conv1d with the folded [2F][win] basis (stride hop, snip-edges) -> power -> mel -> log ----
 __global__ void __launch_bounds__(kFbThreads)
@@ -43,12 +44,14 @@ kaldi_fbank_kernel(const void* __restrict__ pcm, int pcm_is_f32, int n_samples, 
     xs[i] = v;
   }
   __syncthreads();
-  const int f = threadIdx.x;
-  if (f < F) {
-    float re[kFbFrames], im[kFbFrames];
+  const int grp = threadIdx.x / kFbBins, f = threadIdx.x - grp * kFbBins;
+  float re[kFbFrames], im[kFbFrames];
 #pragma unroll
-    for (int j = 0; j < kFbFrames; ++j) { re[j] = 0.f; im[j] = 0.f; }
-    for (int k = 0; k < win; ++k) {
+  for (int j = 0; j < kFbFrames; ++j) { re[j] = 0.f; im[j] = 0.f; }
+  if (f < F) {
+    const int k_lo = grp ? win / 2 : 0, k_hi = grp ? win : win / 2;
+#pragma unroll 4
+    for (int k = k_lo; k < k_hi; ++k) {
       const float c = basis_t[(int64_t)k * 2 * F + f];
       const float s = basis_t[(int64_t)k * 2 * F + F + f];
 #pragma unroll
@@ -58,8 +61,19 @@ kaldi_fbank_kernel(const void* __restrict__ pcm, int pcm_is_f32, int n_samples, 
         im[j] = fmaf(s, x, im[j]);
       }
     }
+  }
+  float* part = pw + kFbFrames * F;      // [kFbFrames][F][2] partial sums of the second tap group
+  if (grp == 1 && f < F) {
 #pragma unroll
-    for (int j = 0; j < kFbFrames; ++j) pw[j * F + f] = re[j] * re[j] + im[j] * im[j];
+    for (int j = 0; j < kFbFrames; ++j) { part[(j * F + f) * 2] = re[j]; part[(j * F + f) * 2 + 1] = im[j]; }
+  }
+  __syncthreads();
+  if (grp == 0 && f < F) {
+#pragma unroll
+    for (int j = 0; j < kFbFrames; ++j) {
+      const float r = re[j] + part[(j * F + f) * 2], i = im[j] + part[(j * F + f) * 2 + 1];
+      pw[j * F + f] = r * r + i * i;
+    }
   }
   __syncthreads();
   for (int o = threadIdx.x; o < kFbFrames * n_mels; o += blockDim.x) {
@@ -493,7 +507,7 @@ int nar_fbank(b200asr_nar* e) {
   const b200asr_nar_config& c = e->cfg;
   const int F = c.nfft / 2 + 1, B = e->B;
   const int span = (kFbFrames - 1) * c.hop + c.win;
-  const size_t smem = (size_t)(span + kFbFrames * F) * sizeof(float);
+  const size_t smem = (size_t)(span + 3 * kFbFrames * F) * sizeof(float);
   dim3 grid((e->frames + kFbFrames - 1) / kFbFrames, B);
   kaldi_fbank_kernel<<<grid, kFbThreads, smem, e->st>>>(e->pcm, e->pcm_dtype == B200ASR_PCM_F32, e->n_samples, e->basis_t,
                                                         NWF(e, "mel_filters"), c.win, c.hop, F, c.n_mels, e->frames,
@@ -735,7 +749,7 @@ int b200asr_nar_create(const b200asr_nar_config* cfg, b200asr_nar** out) {
   if (cfg->kind == B200ASR_NAR_PARAFORMER && (cfg->dec_att_blocks < 0 || cfg->dec_ffn_blocks < 0 || cfg->dec_ffn <= 0 || cfg->dec_ffn % 8 || cfg->dec_ffn > 2048 ||
                                               cfg->cif_kernel < 1 || (cfg->cif_kernel & 1) == 0)) { g_nar_create_error = "invalid Paraformer decoder dimensions"; return B200ASR_E_INVALID; }
   if (cfg->d_model <= 0 || cfg->n_heads <= 0 || cfg->d_model % cfg->n_heads || cfg->d_model % 8 || cfg->ffn % 8 ||
-      (cfg->n_mels * cfg->lfr_m) % 8 || cfg->nfft / 2 + 1 > kFbThreads || cfg->win <= 0 || cfg->hop <= 0 || cfg->vocab <= 0 ||
+      (cfg->n_mels * cfg->lfr_m) % 8 || cfg->nfft / 2 + 1 > kFbBins || cfg->win <= 0 || cfg->hop <= 0 || cfg->vocab <= 0 ||
       cfg->max_batch <= 0 || cfg->max_samples < cfg->win || cfg->n_prompt < 0 || cfg->fsmn_kernel < 1 || (cfg->fsmn_kernel & 1) == 0) {
     g_nar_create_error = "invalid model dimensions"; return B200ASR_E_INVALID;
   }
@@ -936,7 +950,7 @@ int b200asr_nar_finalize_weights(b200asr_nar* e) {
     }
     NCK(cudaMallocHost(&e->h_pinned, (size_t)B * (Tm + 2) * 4 + 64));
     const int span = (kFbFrames - 1) * c.hop + c.win;
-    NCK(cudaFuncSetAttribute(kaldi_fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((span + kFbFrames * F) * sizeof(float))));
+    NCK(cudaFuncSetAttribute(kaldi_fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((span + 3 * kFbFrames * F) * sizeof(float))));
   }
   NCK(cudaStreamSynchronize(e->st));
   e->finalized = true;
