@@ -96,3 +96,37 @@ def test_paraformer_product_folds_equal_oracle_folds():
         assert np.array_equal(fp[k], fo[k].numpy()), k
     assert pf.tokens_to_text([0, 1, 2], ["hel@@", "lo", "world"], "en") == "hello world"
     assert pf.tokens_to_text([0, 1], ["你", "好"], "zh") == "你好"
+
+
+def test_transcribe_long_window_plan_with_stub_engine():
+    """Host-side window loop of the SenseVoice / Paraformer scripts (Inference_SenseVoice_ONNX.py:236-260,290-307) on a stub
+    engine: window count, stride, zero-padded tail, batching by max_batch, order of concatenation."""
+    import numpy as np
+    from b200asr import sensevoice as sv
+
+    class Stub:
+        max_batch, max_samples = 2, 50000
+        def __init__(self):
+            self.calls = []
+        def run(self, clips, sel):
+            self.calls.append((clips.shape, sel))
+            return [[int(c[0]), int(c[-1]), int(np.count_nonzero(c))] for c in clips]        # first sample, last sample, non-zero count
+
+    pcm = np.arange(1, 100001, dtype=np.int64).astype(np.int16)          # wraps, but deterministic
+    eng = Stub()
+    res = sv.transcribe_long(eng, pcm, "Korean", input_audio_length=32000, sliding_window=20000)
+    # reference arithmetic: ceil((100000 - 32000) / 20000) + 1 = 5 windows, aligned length 4 * 20000 + 32000 = 112000
+    assert res["windows"] == 5 and res["language"] == "ko"
+    assert [c[0] for c in eng.calls] == [(2, 32000), (2, 32000), (1, 32000)] and all(c[1] == 5 for c in eng.calls)
+    padded = np.zeros(112000, np.int16); padded[:100000] = pcm
+    want = []
+    for i in range(5):
+        w = padded[i * 20000:i * 20000 + 32000]
+        want += [int(w[0]), int(w[-1]), int(np.count_nonzero(w))]
+    assert res["tokens"] == want and len(res["per_window"]) == 5
+    # dynamic axis: one window = the whole clip; a window longer than the engine accepts is refused
+    eng = Stub(); eng.max_samples = 200000
+    assert sv.transcribe_long(eng, pcm, "auto")["windows"] == 1 and eng.calls[0][0] == (1, 100000)
+    import pytest
+    with pytest.raises(ValueError, match="max_samples"):
+        sv.transcribe_long(Stub(), pcm, "auto")
