@@ -11,8 +11,10 @@
 // [chunk*13][16*C] operand of conv_out (its weight columns are permuted once on the host); conv2/conv3 are im2col +
 // tcgen05 GEMM with the tanh-GELU in the epilogue; the residual streams stay fp32, GEMM operands are bf16 in bf16 mode.
 // KV cache: [layer][utterance][kv_head][position][head_dim] in the activation dtype.  The prefill runs through the
-// engine's GEMMs; a decode step (M = batch rows) streams every weight once through the warp-per-column kernel of
-// decoder.cu and is replayed as one CUDA graph -- positions come from the device-side DecState, not launch arguments.
+// engine's GEMMs and a tiled causal attention; a decode step (M = batch rows) is 5 launches per layer -- four
+// qwen_gemv_kernel launches that keep a whole weight matrix in flight (raw-register prefetch, one resident wave) and one
+// attention launch fused with QK-norm / RoPE / cache append -- replayed as one CUDA graph with programmatic dependent
+// launches; positions come from the device-side DecState, not launch arguments.
 #include "common.cuh"
 #include "../../include/b200asr.h"
 

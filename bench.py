@@ -360,7 +360,7 @@ def run_qwen(args):
                     "h2d_bytes_per_step": int(pcm.nbytes), "d2h_bytes_per_step": int(B * (dims.max_seq_len + 1) * 4)},
             "gpu_launches": int(launches), "clocks": clocks,
             "phases_ms": {"encoder_prefill_first_token": ms_first / steps, "decode_step": step_ms},
-            "roofline": {"kernel": "decode step (CUDA graph of warp-per-column weight-streaming kernels)", "bound": "hbm",
+            "roofline": {"kernel": "decode step (CUDA graph: 4 qwen_gemv_kernel + 1 attention launch per layer, weights streamed once)", "bound": "hbm",
                          "achieved": (wbytes + kvbytes) / (step_ms / 1e3) / 1e9, "peak": 6650.0, "unit": "GB/s",
                          "frac": (wbytes + kvbytes) / (step_ms / 1e3) / 1e9 / 6650.0, "traffic": None,
                          "algorithmic_bytes_per_launch": wbytes + kvbytes},
