@@ -6,6 +6,7 @@
 
     python -m b200asr.cli whisper --model-folder DIR [--tokenizer-path P] --audio clip.wav [more.wav ...]
     python -m b200asr.cli qwen    --model-folder DIR [--tokenizer-path P] --audio clip.wav [--language English] [--prompt "..."]
+    python -m b200asr.cli sensevoice --model-folder DIR [--tokenizer-path model.bpe] --audio clip.wav [--language auto]
 
 (the second = /root/reference/Qwen_ASR/Inference_Qwen_ASR_ONNX.py:44-60; DIR = the Qwen3-ASR checkpoint folder with the
 tokenizer files, REPEAT_PENALTY / PENALTY_RANGE via --set as in the script's configuration block :84-91)
@@ -75,9 +76,19 @@ def main(argv=None) -> int:
     qp.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     qp.add_argument("--device", type=int, default=0)
     qp.add_argument("--set", nargs="*", default=[], metavar="NAME=VALUE", help="REPEAT_PENALTY=1.0 PENALTY_RANGE=10")
+    svp = sub.add_parser("sensevoice")
+    svp.add_argument("--model-folder", "--onnx-folder", dest="folder", required=True)
+    svp.add_argument("--tokenizer-path", default=None, help="SentencePiece model (default: chn_jpn_yue_eng_ko_spectok.bpe.model in the folder)")
+    svp.add_argument("--audio", nargs="+", required=True)
+    svp.add_argument("--language", default="auto")
+    svp.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
+    svp.add_argument("--device", type=int, default=0)
+    svp.add_argument("--set", nargs="*", default=[], metavar="NAME=VALUE", help="INPUT_AUDIO_LENGTH=0 SLIDING_WINDOW=0 (0 = dynamic axis / window stride)")
     args = ap.parse_args(argv)
     if args.model == "qwen":
         return _main_qwen(args)
+    if args.model == "sensevoice":
+        return _main_sensevoice(args)
 
     dims, state, gen = ingest.load_hf_whisper(args.folder)
     tensors = fold_whisper(state, dims, gen.get("suppress_tokens") or [], gen.get("begin_suppress_tokens") or [])
@@ -133,6 +144,41 @@ def _main_qwen(args) -> int:
                                  repeat_penalty=float(consts["REPEAT_PENALTY"]), penalty_range=int(consts["PENALTY_RANGE"]))
         text = tokenizer.decode(res["tokens"], skip_special_tokens=True)
         print(f"\nASR Result:\n{text}\n\nRTF: {res['rtf']:.4f}")
+    eng.close()
+    return 0
+
+
+def _main_sensevoice(args) -> int:
+    """Inference_SenseVoice_ONNX.py: FunASR folder (`model.pt`, `am.mvn`, SentencePiece model) -> per clip `ASR Result` / `RTF`
+    (:236-310); INPUT_AUDIO_LENGTH / SLIDING_WINDOW as in the script's configuration block."""
+    from . import sensevoice as sv
+    consts = {"INPUT_AUDIO_LENGTH": 0, "SLIDING_WINDOW": 0}
+    for pair in args.set or []:
+        k, _, v = pair.partition("=")
+        if k not in consts:
+            raise SystemExit(f"unknown option {k}; choose from {sorted(consts)}")
+        consts[k] = int(v)
+    dims, raw = ingest.load_funasr_sensevoice(args.folder)
+    clips = [ingest.read_wav(p) for p in args.audio]
+    pcm = [ingest.to_model_rate(x, r, dims.sample_rate) for x, r in clips]
+    win = consts["INPUT_AUDIO_LENGTH"] or None
+    max_samples = win or max(len(x) for x in pcm)
+    eng = sv.SenseVoiceEngine(dims, sv.fold_sensevoice(raw, dims, max_samples), precision=args.precision, max_batch=8,
+                              max_samples=max_samples, device=args.device)
+    sp = None
+    tok_path = Path(args.tokenizer_path) if args.tokenizer_path else Path(args.folder) / "chn_jpn_yue_eng_ko_spectok.bpe.model"
+    try:
+        import sentencepiece
+        sp = sentencepiece.SentencePieceProcessor(model_file=str(tok_path))
+    except Exception as exc:
+        print(f"(tokenizer not loaded from {tok_path}: {exc.__class__.__name__}; printing token ids)", file=sys.stderr)
+    for path, x in zip(args.audio, pcm):
+        print("-" * 106)
+        print(f"\nTest Input Audio: {path}")
+        res = sv.transcribe_long(eng, x, args.language, input_audio_length=win, sliding_window=consts["SLIDING_WINDOW"],
+                                 sample_rate=dims.sample_rate)
+        text = sp.decode(res["tokens"]) if sp is not None else " ".join(map(str, res["tokens"]))
+        print(f"\nASR Result:\n{text}\n\nRTF: {res['rtf']:.4f}\n")
     eng.close()
     return 0
 

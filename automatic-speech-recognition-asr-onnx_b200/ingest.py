@@ -199,3 +199,78 @@ def qwen_prompt_from_tokenizer(tokenizer, languages=()):
     asr_text = [int(vocab["<asr_text>"])]
     tails = {name: enc(name) + asr_text for name in languages}
     return QwenPrompt(tuple(head), tuple(suffix), tuple(tail), tuple(stop)), tails
+
+
+# ---------------------------------------------------------------------------------------------
+def read_kaldi_cmvn(path):
+    """`am.mvn` of a FunASR model folder (Kaldi nnet text: <AddShift> row = negated means, <Rescale> row = inverse standard
+    deviations) -> (means, vars) as the front end applies them, (x + means) * vars -- what `frontend.cmvn` holds in the
+    exporter (SenseVoice/Export_SenseVoice.py:363-364)."""
+    lines = Path(path).read_text().splitlines()
+    means = scales = None
+    for i, line in enumerate(lines):
+        tag = line.split()[0] if line.split() else ""
+        if tag in ("<AddShift>", "<Rescale>") and i + 1 < len(lines):
+            items = lines[i + 1].split()
+            lo, hi = items.index("[") + 1, items.index("]")
+            vals = np.asarray([float(v) for v in items[lo:hi]], dtype=np.float32)
+            if tag == "<AddShift>":
+                means = vals
+            else:
+                scales = vals
+    if means is None or scales is None:
+        raise ValueError(f"{path}: no <AddShift> / <Rescale> rows")
+    return means, scales
+
+
+def load_funasr_sensevoice(folder):
+    """(dims, checkpoint dict under the names `sensevoice.fold_sensevoice` expects) from a FunASR SenseVoiceSmall folder
+    (`model.pt` + `am.mvn`, what `AutoModel(model=...)` loads at Export_SenseVoice.py:356-364).  State-dict keys follow the
+    module tree the exporter walks (:208-266): encoder.encoders0 / encoders / tp_encoders [.self_attn.{linear_q_k_v,
+    linear_out, fsmn_block}, .feed_forward.{w_1, w_2}, .norm1, .norm2], encoder.after_norm, encoder.tp_norm, ctc.ctc_lo, embed."""
+    import torch
+    from .sensevoice import SenseVoiceDims
+    folder = Path(folder)
+    sd = torch.load(folder / "model.pt", map_location="cpu", weights_only=True)
+    sd = sd.get("state_dict", sd)
+    t = lambda k: sd[k].detach().float()
+    groups = []
+    for grp in ("encoders0", "encoders", "tp_encoders"):
+        n = 0
+        while f"encoder.{grp}.{n}.norm1.weight" in sd:
+            groups.append(f"encoder.{grp}.{n}.")
+            n += 1
+    n0 = sum(1 for g in groups if ".encoders0." in g)
+    ntp = sum(1 for g in groups if ".tp_encoders." in g)
+    d_model = int(t(groups[0] + "self_attn.linear_out.weight").shape[0])
+    means, scales = read_kaldi_cmvn(folder / "am.mvn")
+    feat = int(means.shape[0])
+    ffn = int(t(groups[0] + "feed_forward.w_1.weight").shape[0])
+    k = int(t(groups[0] + "self_attn.fsmn_block.weight").shape[-1])
+    vocab = int(t("ctc.ctc_lo.weight").shape[0])
+    n_embed = int(t("embed.weight").shape[0])
+    base = SenseVoiceDims()
+    heads = base.n_heads
+    if (folder / "config.yaml").exists():            # FunASR model config: encoder_conf.attention_heads (4 for SenseVoiceSmall)
+        import yaml
+        conf = yaml.safe_load((folder / "config.yaml").read_text()) or {}
+        heads = int((conf.get("encoder_conf") or {}).get("attention_heads", heads))
+    if feat % base.lfr_m:
+        raise ValueError("am.mvn width is not a multiple of the LFR stack")
+    dims = SenseVoiceDims(n_mels=feat // base.lfr_m, d_model=d_model, n_heads=heads, ffn=ffn, n_blocks0=n0,
+                          n_blocks=len(groups) - n0 - ntp, n_tp_blocks=ntp, vocab=vocab, fsmn_kernel=k, n_embed=n_embed)
+    raw = {"embed": t("embed.weight"), "cmvn_means": torch.from_numpy(means), "cmvn_vars": torch.from_numpy(scales)}
+    for i, g in enumerate(groups):
+        p = f"blk{i}."
+        raw[p + "norm1.g"], raw[p + "norm1.b"] = t(g + "norm1.weight"), t(g + "norm1.bias")
+        raw[p + "norm2.g"], raw[p + "norm2.b"] = t(g + "norm2.weight"), t(g + "norm2.bias")
+        raw[p + "qkv.w"], raw[p + "qkv.b"] = t(g + "self_attn.linear_q_k_v.weight"), t(g + "self_attn.linear_q_k_v.bias")
+        raw[p + "out.w"], raw[p + "out.b"] = t(g + "self_attn.linear_out.weight"), t(g + "self_attn.linear_out.bias")
+        raw[p + "fsmn.w"] = t(g + "self_attn.fsmn_block.weight").reshape(d_model, k)
+        raw[p + "w1.w"], raw[p + "w1.b"] = t(g + "feed_forward.w_1.weight"), t(g + "feed_forward.w_1.bias")
+        raw[p + "w2.w"], raw[p + "w2.b"] = t(g + "feed_forward.w_2.weight"), t(g + "feed_forward.w_2.bias")
+    for n, key in (("after_norm", "encoder.after_norm"), ("tp_norm", "encoder.tp_norm")):
+        raw[n + ".g"], raw[n + ".b"] = t(key + ".weight"), t(key + ".bias")
+    raw["ctc.w"], raw["ctc.b"] = t("ctc.ctc_lo.weight"), t("ctc.ctc_lo.bias")
+    return dims, raw
+
