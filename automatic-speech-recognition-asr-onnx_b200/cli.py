@@ -7,6 +7,7 @@
     python -m b200asr.cli whisper --model-folder DIR [--tokenizer-path P] --audio clip.wav [more.wav ...]
     python -m b200asr.cli qwen    --model-folder DIR [--tokenizer-path P] --audio clip.wav [--language English] [--prompt "..."]
     python -m b200asr.cli sensevoice --model-folder DIR [--tokenizer-path model.bpe] --audio clip.wav [--language auto]
+    python -m b200asr.cli paraformer --model-folder DIR [--vocab-path tokens.json] --audio clip.wav
 
 (the second = /root/reference/Qwen_ASR/Inference_Qwen_ASR_ONNX.py:44-60; DIR = the Qwen3-ASR checkpoint folder with the
 tokenizer files, REPEAT_PENALTY / PENALTY_RANGE via --set as in the script's configuration block :84-91)
@@ -84,11 +85,20 @@ def main(argv=None) -> int:
     svp.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     svp.add_argument("--device", type=int, default=0)
     svp.add_argument("--set", nargs="*", default=[], metavar="NAME=VALUE", help="INPUT_AUDIO_LENGTH=0 SLIDING_WINDOW=0 (0 = dynamic axis / window stride)")
+    pfp = sub.add_parser("paraformer")
+    pfp.add_argument("--model-folder", "--onnx-folder", dest="folder", required=True)
+    pfp.add_argument("--vocab-path", "--tokenizer-path", dest="tokenizer_path", default=None, help="tokens.json / Vocab_Paraformer.txt (default: looked up in the folder)")
+    pfp.add_argument("--audio", nargs="+", required=True)
+    pfp.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
+    pfp.add_argument("--device", type=int, default=0)
+    pfp.add_argument("--set", nargs="*", default=[], metavar="NAME=VALUE", help="INPUT_AUDIO_LENGTH=0 SLIDING_WINDOW=0 DECODE_MODE=zh")
     args = ap.parse_args(argv)
     if args.model == "qwen":
         return _main_qwen(args)
     if args.model == "sensevoice":
         return _main_sensevoice(args)
+    if args.model == "paraformer":
+        return _main_paraformer(args)
 
     dims, state, gen = ingest.load_hf_whisper(args.folder)
     tensors = fold_whisper(state, dims, gen.get("suppress_tokens") or [], gen.get("begin_suppress_tokens") or [])
@@ -178,6 +188,41 @@ def _main_sensevoice(args) -> int:
         res = sv.transcribe_long(eng, x, args.language, input_audio_length=win, sliding_window=consts["SLIDING_WINDOW"],
                                  sample_rate=dims.sample_rate)
         text = sp.decode(res["tokens"]) if sp is not None else " ".join(map(str, res["tokens"]))
+        print(f"\nASR Result:\n{text}\n\nRTF: {res['rtf']:.4f}\n")
+    eng.close()
+    return 0
+
+
+def _main_paraformer(args) -> int:
+    """Paraformer/Non-Streaming/Inference_Paraformer_ONNX.py: FunASR folder + vocabulary -> per clip `ASR Result` / `RTF` (:233-302)."""
+    from . import paraformer as pfm
+    from . import sensevoice as sv
+    consts = {"INPUT_AUDIO_LENGTH": 0, "SLIDING_WINDOW": 0, "DECODE_MODE": "zh"}
+    for pair in args.set or []:
+        k, _, v = pair.partition("=")
+        if k not in consts:
+            raise SystemExit(f"unknown option {k}; choose from {sorted(consts)}")
+        consts[k] = type(consts[k])(v)
+    dims, raw = ingest.load_funasr_paraformer(args.folder)
+    clips = [ingest.read_wav(p) for p in args.audio]
+    pcm = [ingest.to_model_rate(x, r, dims.sample_rate) for x, r in clips]
+    win = consts["INPUT_AUDIO_LENGTH"] or None
+    max_samples = win or max(len(x) for x in pcm)
+    eng = pfm.ParaformerEngine(dims, pfm.fold_paraformer(raw, dims, max_samples), precision=args.precision, max_batch=8,
+                               max_samples=max_samples, device=args.device)
+    vocab = None
+    cands = [Path(args.tokenizer_path)] if args.tokenizer_path else [Path(args.folder) / n for n in ("Vocab_Paraformer.txt", "tokens.json", "tokens.txt")]
+    for cand in cands:
+        if cand.exists():
+            vocab = ingest.read_vocab(cand)
+            break
+    if vocab is None:
+        print("(vocabulary not found; printing token ids)", file=sys.stderr)
+    for path, x in zip(args.audio, pcm):
+        print("-" * 106)
+        print(f"\nTest Input Audio: {path}")
+        res = sv.transcribe_long(eng, x, input_audio_length=win, sliding_window=consts["SLIDING_WINDOW"], sample_rate=dims.sample_rate)
+        text = pfm.tokens_to_text(res["tokens"], vocab, consts["DECODE_MODE"]).strip() if vocab is not None else " ".join(map(str, res["tokens"]))
         print(f"\nASR Result:\n{text}\n\nRTF: {res['rtf']:.4f}\n")
     eng.close()
     return 0

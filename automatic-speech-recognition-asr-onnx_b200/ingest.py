@@ -274,3 +274,82 @@ def load_funasr_sensevoice(folder):
     raw["ctc.w"], raw["ctc.b"] = t("ctc.ctc_lo.weight"), t("ctc.ctc_lo.bias")
     return dims, raw
 
+
+def load_funasr_paraformer(folder):
+    """(dims, checkpoint dict under the names `paraformer.fold_paraformer` expects) from a FunASR Paraformer-large folder
+    (`model.pt` + `am.mvn` [+ `config.yaml`]).  Keys follow the module tree `PARAFORMER.__init__` walks
+    (Paraformer/Non-Streaming/Export_Paraformer.py:385-465): encoder.encoders0 / encoders, encoder.after_norm,
+    predictor.{cif_conv1d, cif_output}, decoder.decoders [.feed_forward.{w_1, w_2, norm}, .norm1-3, .self_attn.fsmn_block,
+    .src_attn.{linear_q, linear_k_v, linear_out}], decoder.decoders3, decoder.after_norm, decoder.output_layer."""
+    import torch
+    from .paraformer import ParaformerDims
+    folder = Path(folder)
+    sd = torch.load(folder / "model.pt", map_location="cpu", weights_only=True)
+    sd = sd.get("state_dict", sd)
+    t = lambda k: sd[k].detach().float()
+
+    def count(prefix, probe):
+        n = 0
+        while f"{prefix}.{n}.{probe}" in sd:
+            n += 1
+        return n
+
+    n0, n1 = count("encoder.encoders0", "norm1.weight"), count("encoder.encoders", "norm1.weight")
+    na, nf = count("decoder.decoders", "norm1.weight"), count("decoder.decoders3", "norm1.weight")
+    enc = [f"encoder.encoders0.{i}." for i in range(n0)] + [f"encoder.encoders.{i}." for i in range(n1)]
+    dec = [f"decoder.decoders.{i}." for i in range(na)] + [f"decoder.decoders3.{i}." for i in range(nf)]
+    means, scales = read_kaldi_cmvn(folder / "am.mvn")
+    base = ParaformerDims()
+    heads, tail = base.n_heads, base.tail_threshold
+    if (folder / "config.yaml").exists():
+        import yaml
+        conf = yaml.safe_load((folder / "config.yaml").read_text()) or {}
+        heads = int((conf.get("encoder_conf") or {}).get("attention_heads", heads))
+        tail = float((conf.get("predictor_conf") or {}).get("tail_threshold", tail))
+    D = int(t(enc[0] + "self_attn.linear_out.weight").shape[0])
+    feat = int(means.shape[0])
+    dims = ParaformerDims(n_mels=feat // base.lfr_m, d_model=D, n_heads=heads, ffn=int(t(enc[0] + "feed_forward.w_1.weight").shape[0]),
+                          n_blocks0=n0, n_blocks=n1, dec_att_blocks=na, dec_ffn_blocks=nf,
+                          dec_ffn=int(t(dec[0] + "feed_forward.w_1.weight").shape[0]), vocab=int(t("decoder.output_layer.weight").shape[0]),
+                          fsmn_kernel=int(t(enc[0] + "self_attn.fsmn_block.weight").shape[-1]),
+                          cif_kernel=int(t("predictor.cif_conv1d.weight").shape[-1]), tail_threshold=tail)
+    raw = {"cmvn_means": torch.from_numpy(means), "cmvn_vars": torch.from_numpy(scales)}
+
+    def norm(dst, src):
+        raw[dst + ".g"], raw[dst + ".b"] = t(src + ".weight"), t(src + ".bias")
+
+    for i, g in enumerate(enc):
+        p = f"enc{i}."
+        norm(p + "norm1", g + "norm1"); norm(p + "norm2", g + "norm2")
+        raw[p + "qkv.w"], raw[p + "qkv.b"] = t(g + "self_attn.linear_q_k_v.weight"), t(g + "self_attn.linear_q_k_v.bias")
+        raw[p + "out.w"], raw[p + "out.b"] = t(g + "self_attn.linear_out.weight"), t(g + "self_attn.linear_out.bias")
+        raw[p + "fsmn.w"] = t(g + "self_attn.fsmn_block.weight").reshape(D, -1)
+        raw[p + "w1.w"], raw[p + "w1.b"] = t(g + "feed_forward.w_1.weight"), t(g + "feed_forward.w_1.bias")
+        raw[p + "w2.w"], raw[p + "w2.b"] = t(g + "feed_forward.w_2.weight"), t(g + "feed_forward.w_2.bias")
+    norm("enc_after_norm", "encoder.after_norm")
+    raw["cif.conv.w"], raw["cif.conv.b"] = t("predictor.cif_conv1d.weight"), t("predictor.cif_conv1d.bias")
+    raw["cif.out.w"], raw["cif.out.b"] = t("predictor.cif_output.weight"), t("predictor.cif_output.bias")
+    for i, g in enumerate(dec):
+        p = f"dec{i}."
+        norm(p + "norm1", g + "norm1"); norm(p + "ffn_norm", g + "feed_forward.norm")
+        raw[p + "w1.w"], raw[p + "w1.b"] = t(g + "feed_forward.w_1.weight"), t(g + "feed_forward.w_1.bias")
+        raw[p + "w2.w"] = t(g + "feed_forward.w_2.weight")
+        if i < na:
+            norm(p + "norm2", g + "norm2"); norm(p + "norm3", g + "norm3")
+            raw[p + "fsmn.w"] = t(g + "self_attn.fsmn_block.weight").reshape(D, -1)
+            raw[p + "q.w"], raw[p + "q.b"] = t(g + "src_attn.linear_q.weight"), t(g + "src_attn.linear_q.bias")
+            raw[p + "kv.w"], raw[p + "kv.b"] = t(g + "src_attn.linear_k_v.weight"), t(g + "src_attn.linear_k_v.bias")
+            raw[p + "cout.w"], raw[p + "cout.b"] = t(g + "src_attn.linear_out.weight"), t(g + "src_attn.linear_out.bias")
+    norm("dec_after_norm", "decoder.after_norm")
+    raw["out.w"], raw["out.b"] = t("decoder.output_layer.weight"), t("decoder.output_layer.bias")
+    return dims, raw
+
+
+def read_vocab(path):
+    """Vocabulary of the Paraformer driver: one token per line (`Vocab_Paraformer.txt`, Inference_Paraformer_ONNX.py:181-183),
+    or FunASR's `tokens.json` list."""
+    path = Path(path)
+    if path.suffix == ".json":
+        return [str(x) for x in json.loads(path.read_text(encoding="utf-8"))]
+    return [line.rstrip("\n") for line in path.read_text(encoding="utf-8").splitlines()]
+

@@ -112,3 +112,23 @@ def test_paraformer_sliding_windows_vs_oracle():
             want.extend(po.transcribe(padded[i * 40000:(i + 1) * 40000], fw, po.TINY_TEST))
     assert res["windows"] == 3 and res["tokens"] == want
     eng.close()
+
+
+def test_paraformer_cli_end_to_end_from_funasr_folder_and_wav(tmp_path, capsys):
+    """`python -m b200asr.cli paraformer --model-folder F --audio x.wav`: FunASR-style folder + vocabulary + WAV in, the
+    script's `ASR Result` block out (zh mode: vocabulary pieces joined); the ids behind it must be the oracle's."""
+    import json, wave
+    from funasr_folders import write_paraformer_folder
+    from b200asr import cli, paraformer as pfm
+    g = dict(np.load(GOLD[0]))
+    seed = int(g["seed"])
+    write_paraformer_folder(tmp_path, D, pfm.synth_paraformer_checkpoint(D, seed))
+    vocab = [f"<{i}>" for i in range(D.vocab)]
+    (tmp_path / "tokens.json").write_text(json.dumps(vocab))
+    with wave.open(str(tmp_path / "clip.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(g["pcm"].astype("<i2").tobytes())
+    rc = cli.main(["paraformer", "--model-folder", str(tmp_path), "--audio", str(tmp_path / "clip.wav"), "--precision", "f32"])
+    out = capsys.readouterr().out
+    assert rc == 0 and "ASR Result:" in out and "RTF:" in out
+    text = out.split("ASR Result:\n")[1].split("\n")[0]
+    assert text == "".join(vocab[t] for t in g["tokens"].tolist())

@@ -173,26 +173,8 @@ def test_sensevoice_cli_end_to_end_from_funasr_folder_and_wav(tmp_path, capsys):
     g = dict(np.load(GOLD[0]))
     seed = int(g["seed"])
     raw = sv.synth_sensevoice_checkpoint(D, seed)
-    sd = {"embed.weight": raw["embed"], "ctc.ctc_lo.weight": raw["ctc.w"], "ctc.ctc_lo.bias": raw["ctc.b"]}
-    names = [f"encoder.encoders0.{i}." for i in range(D.n_blocks0)] + [f"encoder.encoders.{i}." for i in range(D.n_blocks)] + \
-            [f"encoder.tp_encoders.{i}." for i in range(D.n_tp_blocks)]
-    for i, k in enumerate(names):
-        p = f"blk{i}."
-        sd[k + "norm1.weight"], sd[k + "norm1.bias"] = raw[p + "norm1.g"], raw[p + "norm1.b"]
-        sd[k + "norm2.weight"], sd[k + "norm2.bias"] = raw[p + "norm2.g"], raw[p + "norm2.b"]
-        sd[k + "self_attn.linear_q_k_v.weight"], sd[k + "self_attn.linear_q_k_v.bias"] = raw[p + "qkv.w"], raw[p + "qkv.b"]
-        sd[k + "self_attn.linear_out.weight"], sd[k + "self_attn.linear_out.bias"] = raw[p + "out.w"], raw[p + "out.b"]
-        sd[k + "self_attn.fsmn_block.weight"] = raw[p + "fsmn.w"].reshape(D.d_model, 1, D.fsmn_kernel)
-        sd[k + "feed_forward.w_1.weight"], sd[k + "feed_forward.w_1.bias"] = raw[p + "w1.w"], raw[p + "w1.b"]
-        sd[k + "feed_forward.w_2.weight"], sd[k + "feed_forward.w_2.bias"] = raw[p + "w2.w"], raw[p + "w2.b"]
-    for n, key in (("after_norm", "encoder.after_norm"), ("tp_norm", "encoder.tp_norm")):
-        sd[key + ".weight"], sd[key + ".bias"] = raw[n + ".g"], raw[n + ".b"]
-    torch.save(sd, tmp_path / "model.pt")
-    row = lambda v: " ".join(f"{float(x):.9g}" for x in v)
-    (tmp_path / "am.mvn").write_text(
-        f"<Nnet>\n<AddShift> {D.feat} {D.feat}\n<LearnRateCoef> 0 [ {row(raw['cmvn_means'])} ]\n"
-        f"<Rescale> {D.feat} {D.feat}\n<LearnRateCoef> 0 [ {row(raw['cmvn_vars'])} ]\n</Nnet>\n")
-    (tmp_path / "config.yaml").write_text(f"encoder_conf:\n  attention_heads: {D.n_heads}\n")
+    from funasr_folders import write_sensevoice_folder
+    write_sensevoice_folder(tmp_path, D, raw)
     with wave.open(str(tmp_path / "clip.wav"), "wb") as w:
         w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(g["pcm"].astype("<i2").tobytes())
     rc = cli.main(["sensevoice", "--model-folder", str(tmp_path), "--audio", str(tmp_path / "clip.wav"), "--precision", "f32",

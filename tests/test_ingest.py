@@ -147,26 +147,8 @@ def test_funasr_sensevoice_folder_to_engine_tensors(tmp_path):
     from b200asr import sensevoice as sv
     d = sv.SENSEVOICE_TINY_TEST
     raw = sv.synth_sensevoice_checkpoint(d, 2)
-    sd = {"embed.weight": raw["embed"], "ctc.ctc_lo.weight": raw["ctc.w"], "ctc.ctc_lo.bias": raw["ctc.b"]}
-    names = [f"encoder.encoders0.{i}." for i in range(d.n_blocks0)] + [f"encoder.encoders.{i}." for i in range(d.n_blocks)] + \
-            [f"encoder.tp_encoders.{i}." for i in range(d.n_tp_blocks)]
-    for i, g in enumerate(names):
-        p = f"blk{i}."
-        sd[g + "norm1.weight"], sd[g + "norm1.bias"] = raw[p + "norm1.g"], raw[p + "norm1.b"]
-        sd[g + "norm2.weight"], sd[g + "norm2.bias"] = raw[p + "norm2.g"], raw[p + "norm2.b"]
-        sd[g + "self_attn.linear_q_k_v.weight"], sd[g + "self_attn.linear_q_k_v.bias"] = raw[p + "qkv.w"], raw[p + "qkv.b"]
-        sd[g + "self_attn.linear_out.weight"], sd[g + "self_attn.linear_out.bias"] = raw[p + "out.w"], raw[p + "out.b"]
-        sd[g + "self_attn.fsmn_block.weight"] = raw[p + "fsmn.w"].reshape(d.d_model, 1, d.fsmn_kernel)
-        sd[g + "feed_forward.w_1.weight"], sd[g + "feed_forward.w_1.bias"] = raw[p + "w1.w"], raw[p + "w1.b"]
-        sd[g + "feed_forward.w_2.weight"], sd[g + "feed_forward.w_2.bias"] = raw[p + "w2.w"], raw[p + "w2.b"]
-    for n, key in (("after_norm", "encoder.after_norm"), ("tp_norm", "encoder.tp_norm")):
-        sd[key + ".weight"], sd[key + ".bias"] = raw[n + ".g"], raw[n + ".b"]
-    torch.save(sd, tmp_path / "model.pt")
-    row = lambda v: " ".join(f"{float(x):.9g}" for x in v)
-    (tmp_path / "am.mvn").write_text(
-        f"<Nnet>\n<Splice> {d.feat} {d.feat}\n[ 0 ]\n<AddShift> {d.feat} {d.feat}\n<LearnRateCoef> 0 [ {row(raw['cmvn_means'])} ]\n"
-        f"<Rescale> {d.feat} {d.feat}\n<LearnRateCoef> 0 [ {row(raw['cmvn_vars'])} ]\n</Nnet>\n")
-    (tmp_path / "config.yaml").write_text("encoder_conf:\n  attention_heads: %d\n  output_size: %d\n" % (d.n_heads, d.d_model))
+    from funasr_folders import write_sensevoice_folder
+    write_sensevoice_folder(tmp_path, d, raw)
     dims, got = ingest.load_funasr_sensevoice(tmp_path)
     assert dims.n_heads == d.n_heads
     assert (dims.d_model, dims.ffn, dims.n_blocks0, dims.n_blocks, dims.n_tp_blocks, dims.vocab, dims.fsmn_kernel, dims.n_mels) == \
@@ -178,3 +160,22 @@ def test_funasr_sensevoice_folder_to_engine_tensors(tmp_path):
     with pytest.raises(ValueError, match="AddShift"):
         (tmp_path / "bad.mvn").write_text("<Nnet>\n</Nnet>\n")
         ingest.read_kaldi_cmvn(tmp_path / "bad.mvn")
+
+
+def test_funasr_paraformer_folder_to_engine_tensors(tmp_path):
+    """A FunASR Paraformer folder -> dims and the checkpoint dict `fold_paraformer` takes; folding equals the in-memory fold."""
+    from funasr_folders import write_paraformer_folder
+    from b200asr import paraformer as pfm
+    d = pfm.PARAFORMER_TINY_TEST
+    raw = pfm.synth_paraformer_checkpoint(d, 3)
+    write_paraformer_folder(tmp_path, d, raw)
+    dims, got = ingest.load_funasr_paraformer(tmp_path)
+    assert dims == d
+    assert got.keys() == raw.keys()
+    a, b = pfm.fold_paraformer(got, d, 32000), pfm.fold_paraformer(raw, d, 32000)
+    for k in b:
+        np.testing.assert_allclose(a[k], b[k], rtol=2e-6, atol=1e-6, err_msg=k)
+    (tmp_path / "tokens.json").write_text(json.dumps(["<blank>", "a", "b@@", "c"]))
+    assert ingest.read_vocab(tmp_path / "tokens.json") == ["<blank>", "a", "b@@", "c"]
+    (tmp_path / "Vocab_Paraformer.txt").write_text("x\ny\n", encoding="utf-8")
+    assert ingest.read_vocab(tmp_path / "Vocab_Paraformer.txt") == ["x", "y"]
