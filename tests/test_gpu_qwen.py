@@ -274,3 +274,48 @@ def test_qwen_clip_length_edges_vs_oracle(n_samples):
     np.testing.assert_allclose(lg[0], st["logits"][0].numpy(), atol=1e-3)
     assert eng.transcribe(pcm, (3,), (), max_new=6)[0] == want
     eng.close()
+
+
+def test_qwen_cli_end_to_end_from_hf_folder_tokenizer_and_wav(tmp_path, capsys):
+    """`python -m b200asr.cli qwen --model-folder F --audio x.wav --language English`: HF-style folder (config.json,
+    model.safetensors, tokenizer files) + WAV in, the script's `ASR Result` block out.  The prompt ids come from the tokenizer
+    as the exporter derives them (Export_Qwen_ASR.py:1500-1586); the text must be the oracle's greedy stream, detokenised."""
+    import json, wave
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+    from b200asr import cli, ingest
+    words = ["system", "user", "assistant", "\n", "language", " ", "English", "hello", "world"]
+    specials = ["<|im_start|>", "<|im_end|>", "<|audio_start|>", "<|audio_end|>", "<|endoftext|>", "<asr_text>", "<unk>"]
+    vocab = {w: i for i, w in enumerate(words + specials)}
+    for i in range(len(vocab), D.vocab):
+        vocab[f"w{i}"] = i
+    tk = Tokenizer(models.WordLevel(vocab, unk_token="<unk>"))
+    tk.pre_tokenizer = pre_tokenizers.Split(pattern=" ", behavior="isolated")
+    fast = PreTrainedTokenizerFast(tokenizer_object=tk, unk_token="<unk>", additional_special_tokens=specials[:-1])
+    fast.save_pretrained(str(tmp_path))
+    raw = qw.synth_qwen_checkpoint(D, 8)
+    cfg = {"thinker_config": {
+        "audio_config": {"num_mel_bins": D.n_mels, "encoder_layers": D.enc_layers, "encoder_attention_heads": D.enc_heads,
+                         "encoder_ffn_dim": D.enc_ffn, "d_model": D.enc_d, "max_source_positions": D.max_source_positions,
+                         "n_window": 50, "n_window_infer": 800, "output_dim": D.out_dim, "downsample_hidden_size": D.conv_ch},
+        "text_config": {"vocab_size": D.vocab, "hidden_size": D.hidden, "intermediate_size": D.inter, "num_hidden_layers": D.dec_layers,
+                        "num_attention_heads": D.heads, "num_key_value_heads": D.kv_heads, "head_dim": D.head_dim,
+                        "rope_theta": D.rope_theta, "rms_norm_eps": D.rms_eps}}}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    ingest.write_safetensors(tmp_path / "model.safetensors", {k: v.numpy() for k, v in raw.items()})
+    pcm = dict(np.load(GOLD[0]))["pcm"]
+    with wave.open(str(tmp_path / "clip.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.astype("<i2").tobytes())
+    rc = cli.main(["qwen", "--model-folder", str(tmp_path), "--audio", str(tmp_path / "clip.wav"), "--precision", "f32",
+                   "--language", "English", "--prompt", "hello world", "--set", "REPEAT_PENALTY=1.0"])
+    out = capsys.readouterr().out
+    assert rc == 0 and "ASR Result:" in out and "RTF:" in out
+    prompt, tails = ingest.qwen_prompt_from_tokenizer(fast, ["English"])
+    assert prompt.head_ids == (9, 0, 3) and tails["English"] == [6, 14]
+    dims = ingest.qwen_dims_from_hf_config(cfg)
+    od = qo.QwenDims(**dims.to_dict())
+    fw = qo.fold_weights(qo.make_raw_weights(od, 8), od)
+    want = qo.greedy_transcribe(pcm, fw, od, qo.QwenPrompt(prompt.head_ids, prompt.suffix_ids, prompt.tail_ids, prompt.stop_ids),
+                                fast.encode("hello world", add_special_tokens=False), tails["English"])
+    text = out.split("ASR Result:\n")[1].split("\n\nRTF")[0]
+    assert text == fast.decode(want, skip_special_tokens=True)
