@@ -324,3 +324,42 @@ class WhisperSessions:
         out.update(self._head_outputs(tok, kind))
         out["decode_kv_seq_len_next"] = OrtValue(np.asarray([self.kv_len], np.int64))
         return out
+
+
+class NarSessions:
+    """The single graph of the SenseVoice / Paraformer drivers as an ORT-shaped session (`.session`): inputs `audio`
+    [1, 1, audio_len] (+ `language_idx` [1] for SenseVoice), outputs `token_ids` [num_token] and `num_id` [1]
+    (SenseVoice/Export_SenseVoice.py:375-376, Paraformer/Non-Streaming/Export_Paraformer.py:600-601), driven the way the
+    scripts drive it (Inference_SenseVoice_ONNX.py:284-305: bind_cpu_input / bind_ortvalue_input, `_iobinding.bind_output`,
+    `run_with_iobinding`, `get_outputs()[0].numpy()`).  `engine` is a SenseVoiceEngine or ParaformerEngine."""
+
+    def __init__(self, engine, metadata: Optional[Dict[str, str]] = None, *, audio_dtype=np.int16):
+        from .paraformer import ParaformerEngine
+        self.engine = engine
+        self.metadata = dict(metadata or {})
+        self.audio_dtype = np.dtype(audio_dtype)
+        self.has_language = not isinstance(engine, ParaformerEngine)
+        self.session = InferenceSession("nar", self)
+
+    def _signature(self, kind):
+        ins = [NodeArg("audio", [1, 1, "audio_len"], _TYPE_OF[self.audio_dtype])]
+        if self.has_language:
+            ins.append(NodeArg("language_idx", [1], "tensor(int32)"))
+        outs = [NodeArg("token_ids", ["num_token"], "tensor(int32)"), NodeArg("num_id", [1], "tensor(int32)")]
+        return ins, outs
+
+    def _run(self, kind, feeds: Dict[str, OrtValue]) -> Dict[str, OrtValue]:
+        audio = feeds["audio"].numpy()
+        if audio.ndim != 3 or audio.shape[0] != 1 or audio.shape[1] != 1:
+            raise ValueError(f"audio must be [1, 1, audio_len], got {list(audio.shape)}")
+        if audio.dtype != self.audio_dtype:
+            raise ValueError(f"audio must be {_TYPE_OF[self.audio_dtype]}, got {audio.dtype}")
+        lang = 0
+        if self.has_language:
+            li = feeds["language_idx"].numpy()
+            if li.shape != (1,) or li.dtype != np.int32:
+                raise ValueError("language_idx must be int32 [1]")
+            lang = int(li[0])
+        toks = self.engine.run(np.ascontiguousarray(audio.reshape(1, -1)), lang)[0]
+        return {"token_ids": OrtValue(np.asarray(toks, dtype=np.int32)), "num_id": OrtValue(np.asarray([len(toks)], dtype=np.int32))}
+

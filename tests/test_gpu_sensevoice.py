@@ -186,3 +186,28 @@ def test_sensevoice_cli_end_to_end_from_funasr_folder_and_wav(tmp_path, capsys):
     with torch.no_grad():
         want = so.transcribe(g["pcm"], fw, so.TINY_TEST, 0)
     assert ids == want
+
+
+def test_nar_session_shim_drives_like_the_script():
+    """ORT-shaped session over the engine: the names, shapes and call sequence of Inference_SenseVoice_ONNX.py:196-305."""
+    from b200asr.session import NarSessions, OrtValue
+    g = dict(np.load(GOLD[0]))
+    eng = _engine(int(g["seed"]), "f32")
+    sess = NarSessions(eng, {"sample_rate": "16000"}).session
+    assert [m.name for m in sess.get_inputs()] == ["audio", "language_idx"]
+    assert [m.name for m in sess.get_outputs()] == ["token_ids", "num_id"]
+    assert sess.get_inputs()[0].shape == [1, 1, "audio_len"] and sess.get_inputs()[0].type == "tensor(int16)"
+    assert sess.get_modelmeta().custom_metadata_map["sample_rate"] == "16000"
+    binding = sess.io_binding()
+    binding.bind_cpu_input("audio", g["pcm"].reshape(1, 1, -1))
+    binding.bind_ortvalue_input("language_idx", OrtValue.ortvalue_from_numpy(np.array([int(g["language_idx"])], np.int32)))
+    binding._iobinding.bind_output("token_ids", None)
+    sess.run_with_iobinding(binding)
+    assert binding.get_outputs()[0].numpy().tolist() == g["tokens"].tolist()
+    tok, num = sess.run(None, {"audio": g["pcm"].reshape(1, 1, -1), "language_idx": np.array([int(g["language_idx"])], np.int32)})
+    assert tok.tolist() == g["tokens"].tolist() and num.tolist() == [len(g["tokens"])]
+    with pytest.raises(ValueError, match="no input named"):
+        binding.bind_cpu_input("audio_in", g["pcm"])
+    with pytest.raises(ValueError, match=r"\[1, 1, audio_len\]"):
+        sess.run(None, {"audio": g["pcm"], "language_idx": np.array([0], np.int32)})
+    eng.close()
