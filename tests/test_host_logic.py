@@ -77,3 +77,29 @@ def test_synth_pcm_is_deterministic_int16():
     a, b = synth_pcm(3, 16000), synth_pcm(3, 16000)
     assert a.dtype == np.int16 and np.array_equal(a, b) and a.std() > 1000
     assert "whisper-large-v3" in PRESETS
+
+
+def test_header_is_a_plain_c_header():
+    """include/b200asr.h is the C ABI a cgo / JNI / ctypes binding includes: it must compile as C99 and as C++ on its own."""
+    import shutil
+    import subprocess
+    hdr = str(ROOT / "include" / "b200asr.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", hdr], check=True)
+    subprocess.run(["g++", "-x", "c++", "-std=c++17", "-fsyntax-only", hdr], check=True)
+
+
+def test_engines_of_every_family_fail_loudly_without_gpu():
+    """No CPU fallback anywhere: creating a SenseVoice / Paraformer / Qwen3-ASR engine without a B200 raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from b200asr import paraformer as pfm, qwen as qw, sensevoice as sv
+    from b200asr.engine import B200AsrError
+    with pytest.raises(B200AsrError):
+        sv.SenseVoiceEngine(sv.SENSEVOICE_TINY_TEST, {}, max_samples=32000)
+    with pytest.raises(B200AsrError):
+        pfm.ParaformerEngine(pfm.PARAFORMER_TINY_TEST, {}, max_samples=32000)
+    with pytest.raises(B200AsrError):
+        qw.QwenEngine(qw.QWEN_TINY_TEST, {}, qw.TINY_PROMPT, max_samples=32000)
