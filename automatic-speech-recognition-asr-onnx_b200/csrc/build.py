@@ -19,7 +19,7 @@ PKG = CSRC.parent
 ROOT = PKG.parent
 OUT = PKG / "libb200asr.so"
 OBJ = ROOT / "build" / "b200asr"
-SOURCES = ["frontend.cu", "gemm_simt.cu", "gemm_tc.cu", "layers.cu", "decoder.cu", "decoder_mega.cu", "decoder_ring.cu", "attention_tc.cu", "sanm.cu", "qwen.cu", "engine.cu"]
+SOURCES = ["frontend.cu", "gemm_simt.cu", "gemm_tc.cu", "layers.cu", "decoder.cu", "decoder_mega.cu", "decoder_ring.cu", "decoder_stream.cu", "attention_tc.cu", "sanm.cu", "qwen.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -202,6 +202,41 @@ bool ring_plan(const MegaArgs& a, int num_sms, bool tc, RingArgs* ra, size_t* sm
 size_t ring_exchange_words(int batch, int d, int ffn, int num_sms);
 cudaError_t launch_decoder_ring(const RingArgs& ra, const CUtensorMap& cross_map, int num_sms, size_t smem_bytes,
                                 cudaStream_t st);
+// decoder_stream.cu: split-K tensor-core streaming decode kernel (tcgen05 on a TMA-fed weight ring, fixed-point
+// accumulate-in-L2 exchanges); bf16, batch <= 8.  The product path for the Whisper greedy loop and prefill.
+struct StreamLayer {        // fp32 vectors of one decoder layer: biases and the LayerNorm-fold row sums (sum_k W[n][k])
+  const float *qkv_b, *qkv_ws, *out_b, *cq_b, *cq_ws, *cout_b, *fc1_b, *fc1_ws, *fc2_b;
+};
+struct StreamArgs {
+  MegaArgs m;                          // model dims, device pointers, token bookkeeping (shared with the other decoder kernels)
+  const StreamLayer* sl;               // [L]
+  const CUtensorMap* wmaps;            // [6L + 1] SWIZZLE_128B maps, box [128 rows][64 k]: qkv, out, cq, cout, fc1, fc2 per layer, then the tied head
+  const float* head_g; const float* head_b;   // [vocab] sum_k E[n][k] gamma[k], sum_k E[n][k] beta[k] (final LayerNorm folded around the tied head)
+  unsigned long long* acc;             // [2][set_words] accumulator words (12-bit count | 52-bit fixed point), zero at launch
+  long long set_words, layer_words;
+  unsigned long long* cand;            // [2][grid][NRT][2] flag-in-data arg-max candidates
+  const int2* sched;                   // [grid][6L + 1] atom ranges (head: tile ranges)
+  const unsigned char* cnt;            // [L][3][cnt_ld] contributors per 128-row output tile of qkv / cq / fc1
+  const unsigned short* xexp;          // [L][3][xt] cumulative contributors per residual-stream tile after out / cout / fc2
+  int cnt_ld, xt;
+  int n_stages, n_slots;               // ring stages (16 KB each); B-operand k-atom slots
+  int task_inv;                        // inverse (mod grid) of the attention-task -> CTA stride
+  int l2_hint;                         // 1: weight / KV boxes are loaded with an L2 evict-first policy
+  int debug;
+};
+constexpr int kStreamMaxBatch = 8;
+bool stream_supported(int batch, int d, int ffn, int n_heads, int vocab, int T, int num_sms);
+// host-side plan: schedule tables (filled into the vectors), shared-memory size; false when the shape does not fit
+struct StreamPlan {
+  int n_stages = 0, n_slots = 0, cnt_ld = 0, xt = 0, nrt = 0;
+  size_t smem_bytes = 0; long long set_words = 0, layer_words = 0; size_t cand_words = 0;
+};
+bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers, int T, int max_target, int num_sms,
+                 StreamPlan* plan, void* sched_out /*std::vector<int2>*/, void* cnt_out /*std::vector<unsigned char>*/,
+                 void* xexp_out /*std::vector<unsigned short>*/);
+cudaError_t launch_decoder_stream(const StreamArgs& sa, const CUtensorMap& cross_map, const CUtensorMap& kc_map,
+                                  const CUtensorMap& vc_map, int nrt, int num_sms, size_t smem_bytes, cudaStream_t st);
+cudaError_t launch_rowdot_bf16(const void* W, const float* vec /*nullable: ones*/, float* out, int N, int K, cudaStream_t st);
 // gemm_tc.cu: SWIZZLE_128B bf16 tensor map over [rows][ld] with a [box_rows][64] box (3-D form, batch 1)
 bool make_tmap_rows_sw128(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_rows,
                           std::string* err);

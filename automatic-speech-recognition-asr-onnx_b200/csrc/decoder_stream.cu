@@ -1,0 +1,1081 @@
+// Split-K tensor-core streaming decode kernel: the whole greedy loop of
+// /root/reference/Whisper/Inference_Whisper_ONNX.py:584-663 (one DECODE_SESSION launch per token, 64 KV rebinds, a
+// `.numpy()` sync per token) and the prompt prefill (:437-583) as ONE cooperative launch of 148 CTAs.  The math is
+// WHISPER_DECODER.forward, /root/reference/Whisper/Export_Whisper.py:614-667, heads :228-240,318-331.
+//
+// Why this shape.  A decode step reads 1.6 GB of bf16 weights for a handful of activation rows; the step is a chain of
+// 257 dependent phases (6 skinny linears + 2 attentions per layer, then the tied head).  The predecessor
+// (decoder_ring.cu) split every linear by output columns and did the dot products on CUDA cores: ~900 instructions per
+// warp per phase, cost proportional to the number of utterances, 22 % of the HBM roofline.  Here:
+//
+//   * every linear is split along K as well as N: the unit of work is an "atom" = 128 weight rows x 64 k (one 16 KB
+//     SWIZZLE_128B TMA box).  A CTA owns a contiguous run of atoms of each phase (host-built schedule, balanced to one
+//     atom cumulatively), so every byte the tensor core pulls out of shared memory is a useful weight byte;
+//   * the dot products run on tcgen05: A = the weight box straight off the TMA ring (M = 128), B = the activation
+//     slice as a 16-row bf16 tile (each utterance contributes a hi and a lo row: x = hi + lo keeps ~16 mantissa bits,
+//     so the activations are not rounded to bf16), D = fp32 in TMEM.  One elected lane issues; the cost of a phase is
+//     independent of the number of utterances (up to 8);
+//   * partial sums meet in L2: an epilogue thread converts its row's sum to 52-bit fixed point and adds
+//     (1 << 52 | value) to the output word with one RED.  Integer adds commute, so the result is bit-reproducible
+//     whatever the arrival order; the top 12 bits count contributors, which is how a reader knows the word is complete
+//     (flag-in-data, no grid barrier, no fence).  The residual stream lives in such words for the whole step: out /
+//     cross-out / fc2 add straight into it;
+//   * LayerNorm is folded around the GEMM: sum_k W[n][k] (x[k] - mu) rstd = rstd (sum_k W[n][k] x[k] - mu ws[n]) with
+//     ws = row sums of W (computed once at load).  The statistics are accumulated by the readers of x into two more
+//     words per utterance and are only needed one phase later, so no phase waits on a reduction;
+//   * attention (one CTA per (utterance, head) task, rotating over the grid by layer) streams K / V boxes through the
+//     same ring (cross K/V and the resident self-KV cache alike) and runs a warp-local online soft-max;
+//   * one producer lane walks the CTA's share of the step's read stream in consumption order and runs ahead of the
+//     consumers by the ring's capacity, across phase and token boundaries, so HBM never waits on the token's chain.
+//
+// Accumulator words are double-buffered by step parity; while a step runs on one set every CTA zeroes its share of
+// the other (last read one step earlier, all CTAs pass the per-step arg-max exchange in between).
+#include "common.cuh"
+#include "ptx.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+namespace b200asr {
+
+constexpr int kStWorkerWarps = 8;
+constexpr int kStWorkers = kStWorkerWarps * 32;       // 256
+constexpr int kStThreads = kStWorkers + 64;           // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: workers
+constexpr int kStStage = 16384;                       // one atom / one 128-row K or V box
+constexpr int kStMaxStages = 12;
+constexpr int kStSlot = 2048;                         // B operand of one k-atom: 16 rows x 128 bytes
+constexpr int kStPartLd = 68;
+constexpr float kFixScale = 16777216.0f;              // 2^24: accumulator resolution 6e-8, range +-1.3e8
+constexpr float kFixInv = 1.0f / 16777216.0f;
+constexpr float kSqScale = 4096.0f;                   // 2^12 for sums of squares (range 5e11)
+constexpr long long kStSpin = 6000000000LL;           // ~3 s: a protocol bug traps instead of hanging the box
+
+typedef unsigned long long u64;
+
+namespace {
+
+using namespace ptx;
+
+__device__ __forceinline__ void wbar() { asm volatile("bar.sync 1, %0;" ::"n"(kStWorkers) : "memory"); }
+
+__device__ __forceinline__ u64 ld_w(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ld_w2(const u64* p, u64& a, u64& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_w(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void st_zero2(u64* p) {
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %1};" ::"l"(p), "l"(0ull) : "memory");
+}
+__device__ __forceinline__ void red_add(u64* p, u64 v) { asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+// accumulator word = (contributors << 52) + two's-complement fixed-point sum
+__device__ __forceinline__ u64 enc_fix(float v, float scale) { return (1ull << 52) + (u64)__float2ll_rn(v * scale); }
+__device__ __forceinline__ unsigned acc_cnt(u64 w) { return (unsigned)((w + (1ull << 51)) >> 52); }
+__device__ __forceinline__ long long acc_raw(u64 w, unsigned c) { return (long long)(w - ((u64)c << 52)); }
+__device__ __forceinline__ float acc_val(u64 w, unsigned c) { return (float)acc_raw(w, c) * kFixInv; }
+
+__device__ __noinline__ void st_timeout(int where, int x, int y) {
+  printf("b200asr decoder_stream: wait timed out (where %d, block %d thread %d, %d %d)\n", where, blockIdx.x, threadIdx.x, x, y);
+  __trap();
+}
+
+__device__ __forceinline__ void swait(uint64_t* bar, uint32_t parity, int where) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > kStSpin) st_timeout(where, (int)parity, 0);
+}
+
+// poll one accumulator word until `expect` contributors have arrived
+__device__ __forceinline__ u64 poll_w(const u64* p, unsigned expect, int where) {
+  u64 w = ld_w(p);
+  if (acc_cnt(w) == expect) return w;
+  const long long t0 = clock64();
+  for (;;) {
+    w = ld_w(p);
+    if (acc_cnt(w) == expect) return w;
+    if (clock64() - t0 > kStSpin) st_timeout(where, (int)expect, (int)acc_cnt(w));
+  }
+}
+
+__device__ __forceinline__ void tma_2d_hint(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t pol, bool hint) {
+  if (hint)
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol) : "memory");
+  else
+    tma_load_2d(dst, tm, c0, c1, bar);
+}
+__device__ __forceinline__ void tma_3d_hint(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t pol, bool hint) {
+  if (hint)
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(0), "l"(pol) : "memory");
+  else
+    tma_load_3d(dst, tm, c0, c1, 0, bar);
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct RingPos { int stage; uint32_t phase; };
+__device__ __forceinline__ void ring_adv(RingPos& p, int n, int NS) {
+  int s = p.stage + n;
+  while (s >= NS) { s -= NS; p.phase ^= 1u; }
+  p.stage = s;
+}
+
+// linear phase p6 (0 qkv, 1 out, 2 cq, 3 cout, 4 fc1, 5 fc2): k-atoms per weight row
+__device__ __forceinline__ int phase_ka(int p6, int d, int ffn) { return (p6 == 5 ? ffn : d) >> 6; }
+
+// first attention task (utterance * H + head) owned by this CTA in layer l (kind 0 self, 1 cross); further tasks at + grid
+__device__ __forceinline__ int first_task(int l, int kind, int task_inv) {
+  const int G = gridDim.x;
+  const int off = (l * 37 + (kind ? G / 2 : 0)) % G;
+  const int rel = ((int)blockIdx.x - off + G) % G;
+  return (int)(((long long)rel * task_inv) % G);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+template <int NRT>
+__global__ void __launch_bounds__(kStThreads, 1)
+decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_constant__ CUtensorMap kc_map,
+                      const __grid_constant__ CUtensorMap vc_map, const __grid_constant__ StreamArgs sa) {
+  const MegaArgs& a = sa.m;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int NS = sa.n_stages, L = a.n_layers, G = gridDim.x, d = a.d, ffn = a.ffn, B = a.batch, H = a.n_heads, T = a.T;
+  const int n_sched = 6 * L + 1;
+  const int n_cnt = L * 3 * sa.cnt_ld, n_xexp = L * 3 * sa.xt;
+  uint8_t* ring = base;
+  uint8_t* bbuf = ring + (size_t)NS * kStStage;
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  int2* s_sched = reinterpret_cast<int2*>(bbuf + (size_t)sa.n_slots * kStSlot);
+  unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_sched) + up16((size_t)n_sched * 8);
+  unsigned short* s_xexp = reinterpret_cast<unsigned short*>(s_cnt + up16((size_t)n_cnt));
+  float* s_cand = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_xexp) + up16((size_t)n_xexp * 2));   // [G][NRT][2]
+  float* s_part = s_cand + (((size_t)G * NRT * 2 + 3) & ~(size_t)3);             // [8][68] per-warp (max, sum, o[64]) + [8*68] new-token score
+  float* s_qs = s_part + kStWorkerWarps * kStPartLd + 4;                         // [64]
+  float* s_knv = s_qs + 64;                                                      // [2][64]
+  float* s_best = s_knv + 128;                                                   // [8][NRT][2]
+
+  __shared__ uint64_t full_bar[kStMaxStages], empty_bar[kStMaxStages];
+  __shared__ uint64_t b_ready, acc_full[2], acc_empty[2], step_bar;
+  __shared__ int box_cnt[kStMaxStages];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_tok[8], s_ngen[8], s_fin[8], s_nsave[8];
+  __shared__ int s_pen[8 * 32], s_hist[8 * 32];
+  __shared__ int s_pen_n;
+  __shared__ volatile int s_go, s_stop, s_prog;      // s_prog: self-attention phases this CTA has completed (it * L + l + 1)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KAd = d >> 6;                                  // k-atoms of a d-wide row
+  const int n_first = a.first_n_new > 0 ? a.first_n_new : 1;
+  const int total_iters = a.n_iters + n_first - 1;         // leading forced (prompt) tokens, then n_iters heads
+  const int ntask = B * H;
+  const long long xreg = sa.set_words - (long long)L * sa.layer_words;   // residual-stream words + head statistics
+  const int kv0 = a.state->kv_len;
+  constexpr int kEpiWarps = NRT > 4 ? 8 : 4;
+  const int n_vtiles = (a.vocab + 127) >> 7;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); box_cnt[s] = 0; }
+    mbar_init(&b_ready, kStWorkers);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
+    mbar_init(&step_bar, 1);
+    mbar_fence_init();
+    prefetch_tensormap(&cross_map); prefetch_tensormap(&kc_map); prefetch_tensormap(&vc_map);
+    s_stop = 0; s_go = 0; s_prog = 0;
+  }
+  for (int i = tid; i < n_sched; i += kStThreads) s_sched[i] = sa.sched[(size_t)blockIdx.x * n_sched + i];
+  for (int i = tid; i < n_cnt; i += kStThreads) s_cnt[i] = sa.cnt[i];
+  for (int i = tid; i < n_xexp; i += kStThreads) s_xexp[i] = sa.xexp[i];
+  for (int i = tid; i < sa.n_slots * kStSlot / 16; i += kStThreads) reinterpret_cast<uint4*>(bbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < B) {
+    s_ngen[tid] = a.n_gen[tid]; s_fin[tid] = a.finished[tid]; s_nsave[tid] = a.n_save[tid]; s_tok[tid] = 0;
+    const int ns = a.n_save[tid];
+    for (int j = max(0, ns - 32); j < ns; ++j) s_hist[tid * 32 + (j & 31)] = a.save_id[(long long)tid * a.save_ld + j];
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 32u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // =======================================================================
+    // producer: one lane streams this CTA's share of every step's read stream, in consumption order
+    // =======================================================================
+    if (lane == 0) {
+      uint64_t pol = 0;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      const bool hint = sa.l2_hint != 0;
+      RingPos p{0, 0};
+      long long issued = 0;
+      bool stop = false;
+      auto acquire = [&]() -> bool {
+        if (s_stop) return false;
+        if (!mbar_try_wait(&empty_bar[p.stage], p.phase ^ 1u)) {
+          const long long t0 = clock64();
+          while (!mbar_try_wait(&empty_bar[p.stage], p.phase ^ 1u)) {
+            if (s_stop) return false;
+            if (clock64() - t0 > kStSpin) st_timeout(1, p.stage, 0);
+          }
+        }
+        return true;
+      };
+      auto weights = [&](const CUtensorMap* tm, int a0, int a1, int KA) {
+        if (a0 >= a1) return;
+        int tile = a0 / KA, ka = a0 - tile * KA;
+        for (int at = a0; at < a1; ++at) {
+          if (!acquire()) { stop = true; return; }
+          mbar_expect_tx(&full_bar[p.stage], kStStage);
+          tma_3d_hint(ring + (size_t)p.stage * kStStage, tm, ka * 64, tile * 128, &full_bar[p.stage], pol, hint);
+          ++issued; ring_adv(p, 1, NS);
+          if (++ka == KA) { ka = 0; ++tile; }
+        }
+      };
+      auto kvbox = [&](const CUtensorMap* tm, int c0, int row) -> bool {
+        if (!acquire()) { stop = true; return false; }
+        mbar_expect_tx(&full_bar[p.stage], kStStage);
+        tma_2d_hint(ring + (size_t)p.stage * kStStage, tm, c0, row, &full_bar[p.stage], pol, hint);
+        ++issued; ring_adv(p, 1, NS);
+        return true;
+      };
+      for (int it = 0; it < total_iters && !stop; ++it) {
+        const int kv = kv0 + it;
+        const bool head_on = it >= n_first - 1;
+        for (int l = 0; l < L && !stop; ++l) {
+          for (int ph = 0; ph < 8 && !stop; ++ph) {
+            if (ph == 1) {                      // resident self-KV rows [0, kv) of my (utterance, head) tasks: K_i, V_i interleaved
+              const int nb = (kv + 127) >> 7;
+              const int t0 = first_task(l, 0, sa.task_inv);
+              if (t0 < ntask && it > 0) {
+                // the newest cache row was appended by this CTA's workers in the previous step's phase: a short model lets
+                // the ring run more than a step ahead, so wait until they are past it
+                const int need = (it - 1) * L + l + 1;
+                const long long tw = clock64();
+                while (s_prog < need && !s_stop)
+                  if (clock64() - tw > kStSpin) st_timeout(7, need, s_prog);
+              }
+              for (int t = t0; t < ntask && !stop; t += G) {
+                const int b = t / H, h = t - b * H;
+                const int row0 = ((l * B + b) * H + h) * a.max_target;
+                for (int i = 0; i < nb; ++i) {
+                  if (!kvbox(&kc_map, 0, row0 + i * 128)) break;
+                  if (!kvbox(&vc_map, 0, row0 + i * 128)) break;
+                }
+              }
+            } else if (ph == 4) {               // cross K / V of my tasks
+              const int nb = (T + 127) >> 7;
+              for (int t = first_task(l, 1, sa.task_inv); t < ntask && !stop; t += G) {
+                const int b = t / H, h = t - b * H;
+                const int rk = (l * B + b) * T, rv = ((L + l) * B + b) * T;
+                for (int i = 0; i < nb; ++i) {
+                  if (!kvbox(&cross_map, h * 64, rk + i * 128)) break;
+                  if (!kvbox(&cross_map, h * 64, rv + i * 128)) break;
+                }
+              }
+            } else {
+              const int p6 = ph == 0 ? 0 : (ph == 2 ? 1 : (ph == 3 ? 2 : ph - 2));
+              const int2 r = s_sched[l * 6 + p6];
+              weights(&sa.wmaps[l * 6 + p6], r.x, r.y, phase_ka(p6, d, ffn));
+            }
+          }
+        }
+        if (head_on && !stop) {
+          const int2 r = s_sched[6 * L];
+          weights(&sa.wmaps[6 * L], r.x * KAd, r.y * KAd, KAd);
+        }
+      }
+      // drain: every copy that was issued must have landed before the CTA may exit
+      for (int s = 0; s < NS; ++s) {
+        if (issued > s) {
+          const uint32_t par = (s < p.stage) ? p.phase : (p.phase ^ 1u);
+          swait(&full_bar[s], par, 2);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =======================================================================
+    // MMA issuer: one lane; D[128 weight rows][16] (+)= A[128][64] (ring stage) . B[16][64] (activation slot)
+    // =======================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, 16);
+      RingPos p{0, 0};
+      uint32_t bpar = 0;
+      int tctr = 0;
+      const uint32_t ring_u = smem_u32(ring), bbuf_u = smem_u32(bbuf);
+      auto linear = [&](int a0, int a1, int KA) {
+        swait(&b_ready, bpar, 3); bpar ^= 1u;
+        tc_fence_after();
+        if (a0 >= a1) return;
+        int tile = a0 / KA, ka = a0 - tile * KA;
+        const int ka0 = ka;
+        bool fresh = true;
+        for (int at = a0; at < a1; ++at) {
+          const int buf = tctr & 1;
+          if (fresh) { swait(&acc_empty[buf], (uint32_t)(((tctr >> 1) & 1) ^ 1), 4); tc_fence_after(); }
+          swait(&full_bar[p.stage], p.phase, 5);
+          tc_fence_after();
+          int slot = ka - ka0; if (slot < 0) slot += KA;
+          const uint64_t adesc = smem_desc_sw128(ring_u + (uint32_t)p.stage * kStStage);
+          const uint64_t bdesc = smem_desc_sw128(bbuf_u + (uint32_t)slot * kStSlot);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem + (uint32_t)(buf * 16), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (fresh && k == 0) ? 0u : 1u);
+          fresh = false;
+          tc_commit(&empty_bar[p.stage]);
+          ring_adv(p, 1, NS);
+          ++ka;
+          if (ka == KA || at + 1 == a1) {
+            tc_commit(&acc_full[buf]);
+            ++tctr; fresh = true;
+            if (ka == KA) { ka = 0; ++tile; }
+          }
+        }
+      };
+      for (int it = 0; it < total_iters; ++it) {
+        swait(&step_bar, (uint32_t)(it & 1), 6);
+        if (s_go == 2) break;
+        const int kv = kv0 + it;
+        const bool head_on = it >= n_first - 1;
+        for (int l = 0; l < L; ++l) {
+          for (int ph = 0; ph < 8; ++ph) {
+            if (ph == 1 || ph == 4) {             // attention stages are consumed by the workers: skip over them
+              const int nb = ph == 1 ? ((kv + 127) >> 7) : ((T + 127) >> 7);
+              int n = 0;
+              for (int t = first_task(l, ph == 4, sa.task_inv); t < ntask; t += G) n += 2 * nb;
+              ring_adv(p, n, NS);
+            } else {
+              const int p6 = ph == 0 ? 0 : (ph == 2 ? 1 : (ph == 3 ? 2 : ph - 2));
+              const int2 r = s_sched[l * 6 + p6];
+              linear(r.x, r.y, phase_ka(p6, d, ffn));
+            }
+          }
+        }
+        if (head_on) {
+          const int2 r = s_sched[6 * L];
+          linear(r.x * KAd, r.y * KAd, KAd);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =======================================================================
+    // workers (256 threads): activation gather -> B tiles, TMEM epilogue -> RED, attention, arg-max
+    // =======================================================================
+    const int wt = tid - 64, ww = wt >> 5;
+    const int r_mine = ww % NRT;                         // the utterance this warp stages
+    const int g_mine = ww / NRT;                         // slot group
+    constexpr int NG = kStWorkerWarps / NRT;             // slot groups
+    const bool row_ok = r_mine < B;
+    const int q_tm = warp & 3;                           // TMEM lane quarter this warp may read
+    const int set_tm = ww >> 2;                          // 0: utterances 0-3 (columns 0-7), 1: utterances 4-7 (columns 8-15)
+    const bool epi_warp = ww < kEpiWarps;
+    RingPos pos{0, 0};
+    int tctr = 0;
+    int step = a.state->step;
+    int it_done = 0;
+    unsigned long long* tstamp = a.timing;
+    int t_idx = 0;
+    auto stamp = [&]() {
+      if (tstamp && blockIdx.x == 0 && wt == 0 && t_idx < a.timing_cap) {
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        tstamp[t_idx++] = t;
+      }
+    };
+    stamp();
+
+    for (int it = 0; it < total_iters; ++it) {
+      const int kv = kv0 + it;
+      const bool head_on = it >= n_first - 1;
+      const bool begin_on = head_on && it == n_first - 1 && a.first_is_prefill && a.begin_bias != nullptr;
+      if (wt == 0) {
+        int done = 1;
+        for (int b = 0; b < B; ++b) done &= (s_fin[b] != 0);
+        if (it < n_first && a.first_is_prefill) done = 0;          // the prefill always runs
+        s_go = done ? 2 : 1;
+      }
+      if (wt < B && it < n_first) s_tok[wt] = a.first_tokens[wt * n_first + it];
+      wbar();
+      if (wt == 0) mbar_arrive(&step_bar);
+      if (s_go == 2) break;
+      u64* set = sa.acc + (size_t)(it & 1) * sa.set_words;
+      u64* oset = sa.acc + (size_t)((it + 1) & 1) * sa.set_words;
+      u64* xw = set;                                               // [NRT][d] residual stream, then [NRT][2] head statistics
+
+      // ---- B-operand staging of one linear phase.  mode 0: x0 = embedding + position (layer 0), 1: residual words,
+      //      2: attention context words, 3: fc1 words -> LN fold + GELU, 4: residual words x gamma (head) ----
+      auto prep = [&](int mode, int a0, int a1, int KA, const u64* src, long long src_ld, int exp_row /*table row*/,
+                      u64* stat_out /*[NRT][2] or null*/, const u64* stat_in, const float* fold_ws, const float* fold_b) {
+        const int nat = a1 - a0;
+        const int nslot = nat < KA ? nat : KA;
+        int ka0 = 0;
+        if (nat > 0) ka0 = a0 % KA;
+        const int stat_slots = (stat_out && mode != 4 && a0 < KA) ? ((a1 < KA ? a1 : KA) - a0) : 0;
+        float mean = 0.f, rstd = 1.f;
+        if (mode == 3 && row_ok && g_mine < nslot) {
+          const u64 w0 = poll_w(stat_in + r_mine * 2, (unsigned)KAd, 10);
+          const u64 w1 = poll_w(stat_in + r_mine * 2 + 1, (unsigned)KAd, 11);
+          const double sm = (double)acc_raw(w0, KAd) * (1.0 / 16777216.0), sq = (double)acc_raw(w1, KAd) * (1.0 / 4096.0);
+          const double mu = sm / (double)d;
+          mean = (float)mu;
+          rstd = rsqrtf((float)fmax(sq / (double)d - mu * mu, 0.0) + a.eps);
+        }
+        const u64* srow = src + (long long)r_mine * src_ld;
+        for (int s0 = g_mine; s0 < nslot && row_ok; s0 += 4 * NG) {
+          u64 w[4][2];
+          int kk[4];
+          unsigned ex[4];
+          unsigned pend = 0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int s = s0 + u * NG;
+            kk[u] = 0; ex[u] = 0;
+            if (s < nslot) {
+              int ka = ka0 + s; if (ka >= KA) ka -= KA;
+              kk[u] = ka * 64 + 2 * lane;
+              if (mode == 1 || mode == 4) ex[u] = s_xexp[exp_row * sa.xt + (kk[u] >> 7)];
+              else if (mode == 3) ex[u] = s_cnt[exp_row * sa.cnt_ld + (kk[u] >> 7)];
+              else ex[u] = 1;
+              pend |= 1u << u;
+            }
+          }
+          if (mode != 0) {
+            unsigned todo = pend;
+            long long t0 = 0;
+            while (todo) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) if (todo & (1u << u)) ld_w2(srow + kk[u], w[u][0], w[u][1]);
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if ((todo & (1u << u)) && acc_cnt(w[u][0]) == ex[u] && acc_cnt(w[u][1]) == ex[u]) todo &= ~(1u << u);
+              if (todo) {
+                if (t0 == 0) t0 = clock64();
+                else if (clock64() - t0 > kStSpin) st_timeout(12 + mode, kk[0], (int)acc_cnt(w[0][0]));
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (!(pend & (1u << u))) continue;
+            const int s = s0 + u * NG;
+            const int k = kk[u];
+            float f0, f1;
+            if (mode == 0) {
+              const float2 e2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
+                  reinterpret_cast<const bf16*>(a.embed) + (long long)s_tok[r_mine] * d + k));
+              const float2 p2 = *reinterpret_cast<const float2*>(a.pos + (long long)kv * d + k);
+              f0 = p2.x + e2.x; f1 = p2.y + e2.y;
+            } else {
+              f0 = acc_val(w[u][0], ex[u]); f1 = acc_val(w[u][1], ex[u]);
+            }
+            if (s < stat_slots || (mode == 4 && (k >> 6) % n_vtiles >= a0 / KA && (k >> 6) % n_vtiles < a1 / KA)) {
+              // LayerNorm statistics of this k-atom (64 values of utterance r_mine): one RED pair per (atom, utterance)
+              const float sv = warp_sum(f0 + f1);
+              const float qv = warp_sum(fmaf(f0, f0, f1 * f1));
+              if (lane == 0) red_add(stat_out + r_mine * 2, enc_fix(sv, kFixScale));
+              if (lane == 1) red_add(stat_out + r_mine * 2 + 1, enc_fix(qv, kSqScale));
+            }
+            if (mode == 3) {
+              const float2 ws2 = *reinterpret_cast<const float2*>(fold_ws + k);
+              const float2 b2 = *reinterpret_cast<const float2*>(fold_b + k);
+              f0 = gelu_erf(fmaf(rstd, f0 - mean * ws2.x, b2.x));
+              f1 = gelu_erf(fmaf(rstd, f1 - mean * ws2.y, b2.y));
+            } else if (mode == 4) {
+              const float2 g2 = *reinterpret_cast<const float2*>(fold_ws + k);
+              f0 *= g2.x; f1 *= g2.y;
+            }
+            // x = hi + lo, both bf16: rows 2r (hi) and 2r + 1 (lo) of the slot's 16-row K-major SWIZZLE_128B tile
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(f0, f1);
+            const float2 hf = __bfloat1622float2(hi);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(f0 - hf.x, f1 - hf.y);
+            uint8_t* slotp = bbuf + (size_t)s * kStSlot;
+            const int rh = 2 * r_mine, rl = rh + 1;
+            const int chunk = lane >> 2, within = (lane & 3) * 4;
+            *reinterpret_cast<__nv_bfloat162*>(slotp + (rh >> 3) * 1024 + (rh & 7) * 128 + ((chunk ^ (rh & 7)) << 4) + within) = hi;
+            *reinterpret_cast<__nv_bfloat162*>(slotp + (rl >> 3) * 1024 + (rl & 7) * 128 + ((chunk ^ (rl & 7)) << 4) + within) = lo;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&b_ready);
+      };
+
+      // ---- TMEM epilogue of one linear phase: row sums (hi + lo) -> fixed point -> RED into the output words.
+      //      `bias` (and x0 at layer 0) is added by the contributor that owns k-atom 0 of the tile. ----
+      auto epilogue = [&](int a0, int a1, int KA, int Nrows, u64* dst, long long dst_ld, const float* bias, bool add_x0) {
+        if (a0 >= a1) return;
+        int tile = a0 / KA;
+        int at = a0;
+        while (at < a1) {
+          const int tend = min(a1, (tile + 1) * KA);
+          const bool desig = at == tile * KA;
+          const int n = tile * 128 + q_tm * 32 + lane;
+          float bv = 0.f, x0v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (epi_warp && desig && n < Nrows) {
+            if (bias) bv = bias[n];
+            if (add_x0) {
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) {
+                const int r = set_tm * 4 + rr;
+                if (r < B) x0v[rr] = a.pos[(long long)kv * d + n] +
+                                     __bfloat162float(reinterpret_cast<const bf16*>(a.embed)[(long long)s_tok[r] * d + n]);
+              }
+            }
+          }
+          const int buf = tctr & 1;
+          swait(&acc_full[buf], (uint32_t)((tctr >> 1) & 1), 20);     // every worker: the B slots are free again after this
+          if (epi_warp) {
+            tc_fence_after();
+            uint32_t v[8];
+            tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 16 + set_tm * 8), v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (n < Nrows) {
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) {
+                const int r = set_tm * 4 + rr;
+                if (r < B) {
+                  float val = __uint_as_float(v[2 * rr]) + __uint_as_float(v[2 * rr + 1]);
+                  if (desig) val += bv + x0v[rr];
+                  red_add(dst + (long long)r * dst_ld + n, enc_fix(val, kFixScale));
+                }
+              }
+            }
+          }
+          ++tctr; at = tend; ++tile;
+        }
+      };
+
+      // ---- attention of my (utterance, head) tasks of layer l.  kind 0: self (resident cache rows [0, kv) off the
+      //      ring + the new position from the exchange), kind 1: cross (T rows off the ring) ----
+      auto attention = [&](int kind, int l) {
+        u64* lay = set + xreg + (long long)l * sa.layer_words;
+        const StreamLayer& slr = sa.sl[l];
+        const int nvalid = kind ? T : kv;
+        const int nb = (nvalid + 127) >> 7;
+        for (int t = first_task(l, kind, sa.task_inv); t < ntask; t += G) {
+          const int b = t / H, h = t - b * H;
+          if (wt < (kind ? 64 : 192)) {
+            const int which = wt >> 6, dd = wt & 63;
+            const int n = which * d + h * 64 + dd;
+            const u64* p = lay + (kind ? (long long)NRT * 4 * d + (long long)b * d : (long long)b * 3 * d) + n;
+            const u64* stp = lay + (long long)NRT * (6 * d + ffn) + ((kind ? 1 : 0) * NRT + b) * 2;
+            const unsigned ex = s_cnt[(l * 3 + kind) * sa.cnt_ld + (n >> 7)];
+            const float wsn = (kind ? slr.cq_ws : slr.qkv_ws)[n], bn = (kind ? slr.cq_b : slr.qkv_b)[n];
+            const u64 w0 = poll_w(stp, (unsigned)KAd, 30);
+            const u64 w1 = poll_w(stp + 1, (unsigned)KAd, 31);
+            const u64 wv = poll_w(p, ex, 32);
+            const double sm = (double)acc_raw(w0, KAd) * (1.0 / 16777216.0), sq = (double)acc_raw(w1, KAd) * (1.0 / 4096.0);
+            const double mu = sm / (double)d;
+            const float rstd = rsqrtf((float)fmax(sq / (double)d - mu * mu, 0.0) + a.eps);
+            const float val = fmaf(rstd, acc_val(wv, ex) - (float)mu * wsn, bn);
+            if (which == 0) {
+              s_qs[dd] = val;
+            } else {
+              const bf16 hb = __float2bfloat16_rn(val);
+              bf16* cache = reinterpret_cast<bf16*>(which == 1 ? a.kcache : a.vcache);
+              cache[((((long long)l * B + b) * H + h) * a.max_target + kv) * 64 + dd] = hb;     // append for the later tokens
+              s_knv[(which - 1) * 64 + dd] = __bfloat162float(hb);
+            }
+          }
+          wbar();
+          // warp ww takes rows [16 ww, 16 ww + 16) of every 128-row box; two lanes per row (32 dims each), the row's 16-byte
+          // chunks rotated by the row index so the quarter-warp phases of the 128-bit loads are conflict-free
+          const int rowl = lane >> 1, half = lane & 1;
+          float qh[32];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int cc = (c + rowl) & 3;
+            const float4 qa = *reinterpret_cast<const float4*>(s_qs + half * 32 + cc * 8);
+            const float4 qb = *reinterpret_cast<const float4*>(s_qs + half * 32 + cc * 8 + 4);
+            qh[c * 8 + 0] = qa.x; qh[c * 8 + 1] = qa.y; qh[c * 8 + 2] = qa.z; qh[c * 8 + 3] = qa.w;
+            qh[c * 8 + 4] = qb.x; qh[c * 8 + 5] = qb.y; qh[c * 8 + 6] = qb.z; qh[c * 8 + 7] = qb.w;
+          }
+          float m = -INFINITY, lsum = 0.f, o0 = 0.f, o1 = 0.f;
+          for (int i = 0; i < nb; ++i) {
+            swait(&full_bar[pos.stage], pos.phase, 33);
+            const bf16* kb = reinterpret_cast<const bf16*>(ring + (size_t)pos.stage * kStStage);
+            const int row = ww * 16 + rowl;
+            const bf16* kr = kb + row * 64 + half * 32;
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int cc = (c + rowl) & 3;
+              const uint4 u = *reinterpret_cast<const uint4*>(kr + cc * 8);
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+              float2 f = __bfloat1622float2(hh[0]); s = fmaf(f.x, qh[c * 8 + 0], s); s = fmaf(f.y, qh[c * 8 + 1], s);
+              f = __bfloat1622float2(hh[1]); s = fmaf(f.x, qh[c * 8 + 2], s); s = fmaf(f.y, qh[c * 8 + 3], s);
+              f = __bfloat1622float2(hh[2]); s = fmaf(f.x, qh[c * 8 + 4], s); s = fmaf(f.y, qh[c * 8 + 5], s);
+              f = __bfloat1622float2(hh[3]); s = fmaf(f.x, qh[c * 8 + 6], s); s = fmaf(f.y, qh[c * 8 + 7], s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (i * 128 + row >= nvalid) s = -INFINITY;
+            const float mnew = fmaxf(m, warp_max(s));
+            const float msafe = mnew == -INFINITY ? 0.f : mnew;
+            const float sc = __expf(m - msafe);
+            const float pr = __expf(s - msafe);
+            lsum = lsum * sc + warp_sum(half == 0 ? pr : 0.f);
+            o0 *= sc; o1 *= sc; m = mnew;
+            __syncwarp();
+            if (lane == 0) {
+              if (atomicAdd(&box_cnt[pos.stage], 1) == kStWorkerWarps - 1) { box_cnt[pos.stage] = 0; mbar_arrive(&empty_bar[pos.stage]); }
+            }
+            ring_adv(pos, 1, NS);
+            swait(&full_bar[pos.stage], pos.phase, 34);
+            const bf16* vb = reinterpret_cast<const bf16*>(ring + (size_t)pos.stage * kStStage) + (ww * 16) * 64 + 2 * lane;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float pj = __shfl_sync(0xffffffffu, pr, 2 * j);
+              const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + j * 64));
+              o0 = fmaf(pj, v.x, o0); o1 = fmaf(pj, v.y, o1);
+            }
+            __syncwarp();
+            if (lane == 0) {
+              if (atomicAdd(&box_cnt[pos.stage], 1) == kStWorkerWarps - 1) { box_cnt[pos.stage] = 0; mbar_arrive(&empty_bar[pos.stage]); }
+            }
+            ring_adv(pos, 1, NS);
+          }
+          float* pw = s_part + ww * kStPartLd;
+          if (lane == 0) { pw[0] = m; pw[1] = lsum; }
+          pw[4 + 2 * lane] = o0; pw[5 + 2 * lane] = o1;
+          if (kind == 0 && ww == 0) {                      // score of the new position
+            const float sn = warp_sum(fmaf(s_knv[lane], s_qs[lane], s_knv[lane + 32] * s_qs[lane + 32]));
+            if (lane == 0) s_part[kStWorkerWarps * kStPartLd] = sn;
+          }
+          wbar();
+          if (wt < 64) {
+            const float s_new = kind == 0 ? s_part[kStWorkerWarps * kStPartLd] : -INFINITY;
+            float M = s_new;
+#pragma unroll
+            for (int w = 0; w < kStWorkerWarps; ++w) M = fmaxf(M, s_part[w * kStPartLd]);
+            float Lt = 0.f, o = 0.f;
+#pragma unroll
+            for (int w = 0; w < kStWorkerWarps; ++w) {
+              const float e = __expf(s_part[w * kStPartLd] - M);
+              Lt = fmaf(e, s_part[w * kStPartLd + 1], Lt);
+              o = fmaf(e, s_part[w * kStPartLd + 4 + wt], o);
+            }
+            if (kind == 0) { const float e = __expf(s_new - M); Lt += e; o = fmaf(e, s_knv[64 + wt], o); }
+            u64* dst = lay + (long long)NRT * (kind ? 5 : 3) * d + (long long)b * d + h * 64 + wt;
+            st_w(dst, enc_fix(o / Lt, kFixScale));
+          }
+          if (kind == 0) asm volatile("fence.proxy.async;" ::: "memory");   // appended cache rows -> visible to later TMA reads
+          wbar();
+        }
+        if (kind == 0 && wt == 0) s_prog = it * L + l + 1;
+      };
+
+      // =====================================================================
+      // one call site per phase body: the phases run one after the other, so every inlined copy would be a separate,
+      // cold stretch of the instruction stream
+      const int n_idx = 8 * L + (head_on ? 1 : 0);
+      const int2 rh = s_sched[6 * L];
+      u64* hstats = xw + (long long)NRT * d;
+      for (int idx = 0; idx < n_idx; ++idx) {
+        const int l = idx >> 3, ph = idx & 7;
+        const bool is_head = idx == 8 * L;
+        u64* lay = set + xreg + (long long)(is_head ? 0 : l) * sa.layer_words;
+        if (!is_head && ph == 1) {
+          // zero this CTA's share of the other set's layer-l words (and, at layer 0, of its residual-stream words)
+          {
+            const long long ngran = sa.layer_words >> 1;
+            const long long g0 = ngran * blockIdx.x / G, g1 = ngran * (blockIdx.x + 1) / G;
+            u64* zb = oset + xreg + (long long)l * sa.layer_words;
+            for (long long i = g0 + wt; i < g1; i += kStWorkers) st_zero2(zb + 2 * i);
+            if (l == 0) {
+              const long long xg = xreg >> 1;
+              const long long x0 = xg * blockIdx.x / G, x1 = xg * (blockIdx.x + 1) / G;
+              for (long long i = x0 + wt; i < x1; i += kStWorkers) st_zero2(oset + 2 * i);
+            }
+          }
+          attention(0, l);
+        } else if (!is_head && ph == 4) {
+          attention(1, l);
+        } else {
+          u64* stats = lay + (long long)NRT * (6 * d + ffn);
+          const StreamLayer& slr = sa.sl[is_head ? 0 : l];
+          const int p6 = ph == 0 ? 0 : (ph == 2 ? 1 : (ph == 3 ? 2 : ph - 2));
+          int2 r = s_sched[is_head ? 6 * L : l * 6 + p6];
+          int KA = KAd, mode, exp_row = 0, Nrows = d;
+          const u64* src = xw; long long src_ld = d;
+          u64* stat_out = nullptr; const u64* stat_in = nullptr;
+          const float* fold_ws = nullptr; const float* fold_b = nullptr;
+          u64* dst = xw; long long dst_ld = d; const float* bias = nullptr; bool add_x0 = false;
+          if (is_head) {
+            r.x *= KAd; r.y *= KAd; mode = 4; exp_row = (L - 1) * 3 + 2; stat_out = hstats; fold_ws = a.ln_g;
+            if (wt == 0) {
+              // sliding-window penalty ids (APPLY_PENALTY, Export_Whisper.py:318-331): active once generated >= penalty_range
+              int nmax = 0;
+              if (a.penalty_value != 1.0f && !begin_on) {
+                for (int b = 0; b < B; ++b) {
+                  const bool act = s_ngen[b] >= a.penalty_range;
+                  const int ns = s_nsave[b];
+                  const int first = max(0, ns - a.penalty_range);
+                  int cntp = 0;
+                  if (act) for (int j = first; j < ns && cntp < 32; ++j) s_pen[b * 32 + cntp++] = s_hist[b * 32 + (j & 31)];
+                  for (int j = cntp; j < 32; ++j) s_pen[b * 32 + j] = -1;
+                  nmax = max(nmax, cntp);
+                }
+              }
+              s_pen_n = nmax;
+            }
+          } else if (p6 == 0) {
+            mode = l == 0 ? 0 : 1; exp_row = l > 0 ? (l - 1) * 3 + 2 : 0; stat_out = stats;
+            Nrows = 3 * d; dst = lay; dst_ld = 3 * d;
+          } else if (p6 == 1) {
+            mode = 2; src = lay + (long long)NRT * 3 * d; bias = slr.out_b; add_x0 = l == 0;
+          } else if (p6 == 2) {
+            mode = 1; exp_row = l * 3; stat_out = stats + 2 * NRT; dst = lay + (long long)NRT * 4 * d;
+          } else if (p6 == 3) {
+            mode = 2; src = lay + (long long)NRT * 5 * d; bias = slr.cout_b;
+          } else if (p6 == 4) {
+            mode = 1; exp_row = l * 3 + 1; stat_out = stats + 4 * NRT; Nrows = ffn; dst = lay + (long long)NRT * 6 * d; dst_ld = ffn;
+          } else {
+            KA = ffn >> 6; mode = 3; src = lay + (long long)NRT * 6 * d; src_ld = ffn; exp_row = l * 3 + 2; stat_in = stats + 4 * NRT;
+            fold_ws = slr.fc1_ws; fold_b = slr.fc1_b; bias = slr.fc2_b;
+          }
+          prep(mode, r.x, r.y, KA, src, src_ld, exp_row, stat_out, stat_in, fold_ws, fold_b);
+          if (!is_head) {
+            epilogue(r.x, r.y, KA, Nrows, dst, dst_ld, bias, add_x0);
+            ring_adv(pos, r.y - r.x, NS);
+          }
+        }
+        if (!is_head) stamp();
+      }
+
+      // ---- tied lm head: whole 128-row vocabulary tiles per CTA; final LayerNorm folded around the GEMM ----
+      float cv = -INFINITY; int ci = 0x7fffffff;              // this thread's candidate (threads wt < NRT publish)
+      if (head_on) {
+        const int2 r = rh;
+        wbar();                                             // s_pen / s_pen_n visible
+        const bool pen_on = s_pen_n > 0;
+        float mean[4], rstd[4], bvv[4]; int bii[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) { mean[rr] = 0.f; rstd[rr] = 1.f; bvv[rr] = -INFINITY; bii[rr] = 0x7fffffff; }
+        if (epi_warp && r.x < r.y) {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const int rq = set_tm * 4 + rr;
+            if (rq < B) {
+              const u64 w0 = poll_w(hstats + rq * 2, (unsigned)KAd, 40);
+              const u64 w1 = poll_w(hstats + rq * 2 + 1, (unsigned)KAd, 41);
+              const double sm = (double)acc_raw(w0, KAd) * (1.0 / 16777216.0), sq = (double)acc_raw(w1, KAd) * (1.0 / 4096.0);
+              const double mu = sm / (double)d;
+              mean[rr] = (float)mu;
+              rstd[rr] = rsqrtf((float)fmax(sq / (double)d - mu * mu, 0.0) + a.eps);
+            }
+          }
+        }
+        for (int tile = r.x; tile < r.y; ++tile) {
+          const int n = tile * 128 + q_tm * 32 + lane;
+          float gn = 0.f, btn = 0.f, bg = 0.f;
+          if (epi_warp && n < a.vocab) {
+            gn = sa.head_g[n]; btn = sa.head_b[n] + a.suppress_bias[n];
+            if (begin_on) bg = a.begin_bias[n];
+          }
+          const int buf = tctr & 1;
+          swait(&acc_full[buf], (uint32_t)((tctr >> 1) & 1), 42);
+          if (epi_warp) {
+            tc_fence_after();
+            uint32_t v[8];
+            tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 16 + set_tm * 8), v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (n < a.vocab) {
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) {
+                const int rq = set_tm * 4 + rr;
+                if (rq < B) {
+                  float val = fmaf(rstd[rr], (__uint_as_float(v[2 * rr]) + __uint_as_float(v[2 * rr + 1])) - mean[rr] * gn, btn);
+                  if (pen_on) {
+                    bool hit = false;
+                    for (int qq = 0; qq < s_pen_n; ++qq) hit |= (s_pen[rq * 32 + qq] == n);
+                    if (hit) val *= a.penalty_value;
+                  }
+                  if (a.logits) a.logits[(long long)rq * a.vocab + n] = val;
+                  val += bg;
+                  if (val > bvv[rr] || (val == bvv[rr] && n < bii[rr])) { bvv[rr] = val; bii[rr] = n; }
+                }
+              }
+            }
+          }
+          ++tctr;
+        }
+        ring_adv(pos, (r.y - r.x) * KAd, NS);
+        if (epi_warp) {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            float bv = bvv[rr]; int bi = bii[rr];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            const int rq = set_tm * 4 + rr;
+            if (lane == 0 && rq < NRT) { s_best[(ww * NRT + rq) * 2] = bv; s_best[(ww * NRT + rq) * 2 + 1] = __int_as_float(bi); }
+          }
+        }
+        __threadfence();                                   // the zero stores of this step before the candidate goes out
+        asm volatile("fence.proxy.async;" ::: "memory");  // cache rows appended this step, read by TMA in the next one
+        wbar();
+        if (wt < NRT) {
+          for (int w = (wt >> 2) * 4; w < (wt >> 2) * 4 + 4; ++w) {
+            const float v = s_best[(w * NRT + wt) * 2]; const int i = __float_as_int(s_best[(w * NRT + wt) * 2 + 1]);
+            if (v > cv || (v == cv && i < ci)) { cv = v; ci = i; }
+          }
+        }
+      } else {
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        wbar();
+      }
+      stamp();
+
+      // ---- per-step exchange: every CTA publishes its candidate per utterance (flag-in-data, sequence = iteration + 1),
+      //      gathers all of them and reduces identically.  Also the step's full synchronisation point. ----
+      {
+        u64* cbuf = sa.cand + (size_t)(it & 1) * G * NRT * 2;
+        const unsigned seq = (unsigned)it + 1u;
+        if (wt < NRT) {
+          st_w(cbuf + (size_t)(blockIdx.x * NRT + wt) * 2, ((u64)seq << 32) | (u64)__float_as_uint(cv));
+          st_w(cbuf + (size_t)(blockIdx.x * NRT + wt) * 2 + 1, ((u64)seq << 32) | (u64)(unsigned)ci);
+        }
+        const int nw = G * NRT * 2;
+        for (int i0 = wt; i0 < nw; i0 += kStWorkers * 4) {
+          u64 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { const int i = i0 + u * kStWorkers; if (i < nw) v[u] = ld_w(cbuf + i); }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kStWorkers;
+            if (i < nw) {
+              if ((unsigned)(v[u] >> 32) != seq) {
+                const long long t0 = clock64();
+                do {
+                  v[u] = ld_w(cbuf + i);
+                  if (clock64() - t0 > kStSpin) st_timeout(50, i, (int)(v[u] >> 32));
+                } while ((unsigned)(v[u] >> 32) != seq);
+              }
+              s_cand[i] = __uint_as_float((unsigned)v[u]);
+            }
+          }
+        }
+        __threadfence();
+        wbar();
+        if (head_on && ww < B) {
+          float bv = -INFINITY; int bi = 0x7fffffff;
+          for (int c = lane; c < G; c += 32) {
+            const float v = s_cand[(c * NRT + ww) * 2];
+            const int i = __float_as_int(s_cand[(c * NRT + ww) * 2 + 1]);
+            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+          if (lane == 0) {
+            if (bi == 0x7fffffff) bi = 0;
+            const int b = ww;
+            s_tok[b] = bi;
+            const int gen = s_ngen[b];
+            const int ns = s_nsave[b];
+            const bool g0 = blockIdx.x == 0;
+            if (g0) {
+              a.cur_token[b] = bi;
+              if (step < a.sel_ld) a.selected_hist[(long long)b * a.sel_ld + step] = bi;
+              if (ns < a.save_ld) a.save_id[(long long)b * a.save_ld + ns] = bi;
+            }
+            if (ns < a.save_ld) { s_hist[b * 32 + (ns & 31)] = bi; s_nsave[b] = ns + 1; }
+            if (!s_fin[b]) {
+              bool stopf = false;
+              for (int s = 0; s < a.n_stop; ++s) stopf |= (a.stop_ids[s] == bi);
+              if (stopf || a.limit <= 0) {
+                s_fin[b] = 1;
+              } else {
+                if (g0) a.tokens[(long long)b * a.tokens_ld + gen] = bi;
+                s_ngen[b] = gen + 1;
+                if (gen + 1 >= a.limit) s_fin[b] = 1;
+              }
+            }
+          }
+        }
+        if (head_on) step += 1;
+        wbar();
+      }
+      ++it_done;
+      stamp();
+    }
+    // ---- wind down: release the MMA issuer if it is still waiting for a step, stop the producer ----
+    wbar();
+    if (wt == 0) s_stop = 1;
+    if (blockIdx.x == 0 && wt < B) {
+      a.n_gen[wt] = s_ngen[wt];
+      a.finished[wt] = s_fin[wt];
+      a.n_save[wt] = s_nsave[wt];
+    }
+    if (blockIdx.x == 0 && wt == 0) {
+      int done = 1;
+      for (int b = 0; b < B; ++b) done &= (s_fin[b] != 0);
+      a.state->kv_len = kv0 + it_done; a.state->step = step; a.state->all_done = done;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 32u);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+// out[n] = sum_k bf16(W[n][k]) * vec[k]   (vec == nullptr: plain row sums) -- the LayerNorm-fold operands, computed once
+__global__ void rowdot_bf16_kernel(const bf16* __restrict__ W, const float* __restrict__ vec, float* __restrict__ out, int N, int K) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const bf16* wr = W + (long long)row * K;
+  double acc = 0.0;
+  for (int k = lane * 2; k < K; k += 64) {
+    const float2 w2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(wr + k));
+    acc += (double)w2.x * (double)(vec ? vec[k] : 1.f) + (double)w2.y * (double)(vec ? vec[k + 1] : 1.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = (float)acc;
+}
+cudaError_t launch_rowdot_bf16(const void* W, const float* vec, float* out, int N, int K, cudaStream_t st) {
+  rowdot_bf16_kernel<<<(N + 7) / 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(W), vec, out, N, K);
+  return cudaGetLastError();
+}
+
+static int stream_nrt(int batch) { return batch <= 1 ? 1 : (batch <= 2 ? 2 : (batch <= 4 ? 4 : 8)); }
+
+bool stream_supported(int batch, int d, int ffn, int n_heads, int vocab, int T, int num_sms) {
+  return batch >= 1 && batch <= kStreamMaxBatch && d % 64 == 0 && ffn % 64 == 0 && d == n_heads * 64 && vocab >= 1 && T >= 1 &&
+         num_sms >= 8 && num_sms % kRingTaskMul != 0;
+}
+
+// Schedule: for every linear phase the atoms (128 rows x 64 k, tile-major then k) are dealt to the CTAs as contiguous runs
+// of floor / ceil(A / G) atoms; the CTAs with the smallest cumulative load take the ceil, so every CTA's share of the
+// step's read stream stays within one atom of the mean.  The head deals whole vocabulary tiles the same way.
+bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers, int T, int max_target, int num_sms,
+                 StreamPlan* plan, void* sched_out, void* cnt_out, void* xexp_out) {
+  (void)T; (void)max_target; (void)n_heads;
+  const int G = num_sms, L = n_layers;
+  const int nrt = stream_nrt(batch);
+  const int KAd = d / 64, KAf = ffn / 64;
+  auto tiles = [](int n) { return (n + 127) / 128; };
+  const int rowsN[6] = {3 * d, d, d, d, ffn, d};
+  const int kas[6] = {KAd, KAd, KAd, KAd, KAd, KAf};
+  const int n_sched = 6 * L + 1;
+  std::vector<int2> sched((size_t)G * n_sched);
+  const int cnt_ld = std::max(tiles(3 * d), tiles(ffn)), xt = tiles(d);
+  std::vector<unsigned char> cnt((size_t)L * 3 * cnt_ld, 0);
+  std::vector<unsigned short> xexp((size_t)L * 3 * xt, 0);
+  std::vector<long long> load(G, 0);
+  std::vector<int> order(G);
+  std::vector<int> xcum(xt, 0);
+  int max_slots = 1;
+  int rot = 0;
+  auto deal = [&](int A, int unit, int col, std::vector<int>& n_of) {
+    // n_of[c] = units for CTA c; the `rem` least-loaded CTAs (ties: rotating start) take one more
+    const int q = A / G, rem = A % G;
+    for (int c = 0; c < G; ++c) { order[c] = (c + rot) % G; n_of[c] = q; }
+    rot = (rot + 53) % G;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return load[x] < load[y]; });
+    for (int i = 0; i < rem; ++i) n_of[order[i]] += 1;
+    int start = 0;
+    for (int c = 0; c < G; ++c) {
+      sched[(size_t)c * n_sched + col] = make_int2(start, start + n_of[c]);
+      start += n_of[c];
+      load[c] += (long long)n_of[c] * unit;
+    }
+  };
+  std::vector<int> n_of(G);
+  for (int l = 0; l < L; ++l) {
+    for (int p6 = 0; p6 < 6; ++p6) {
+      const int KA = kas[p6], nt = tiles(rowsN[p6]);
+      deal(nt * KA, 1, l * 6 + p6, n_of);
+      std::vector<int> c_of(nt, 0);
+      for (int c = 0; c < G; ++c) {
+        const int2 r = sched[(size_t)c * n_sched + l * 6 + p6];
+        if (r.y <= r.x) continue;
+        for (int t = r.x / KA; t <= (r.y - 1) / KA; ++t) c_of[t] += 1;
+        max_slots = std::max(max_slots, std::min(KA, r.y - r.x));
+      }
+      for (int t = 0; t < nt; ++t) if (c_of[t] > 255) return false;
+      if (p6 == 0 || p6 == 2 || p6 == 4) {
+        const int row = l * 3 + (p6 >> 1);
+        for (int t = 0; t < nt; ++t) cnt[(size_t)row * cnt_ld + t] = (unsigned char)c_of[t];
+      } else {
+        const int row = l * 3 + (p6 == 1 ? 0 : (p6 == 3 ? 1 : 2));
+        for (int t = 0; t < xt; ++t) {
+          xcum[t] += c_of[t];
+          if (xcum[t] > 4000) return false;                 // 12-bit contributor count
+          xexp[(size_t)row * xt + t] = (unsigned short)xcum[t];
+        }
+      }
+    }
+  }
+  deal(tiles(vocab), KAd, 6 * L, n_of);
+  max_slots = std::max(max_slots, KAd);
+  if (plan) {
+    plan->nrt = nrt; plan->cnt_ld = cnt_ld; plan->xt = xt; plan->n_slots = max_slots;
+    long long lw = (long long)nrt * (6 * d + ffn) + 6 * nrt;
+    lw = (lw + 15) / 16 * 16;
+    long long xr = (long long)nrt * d + 2 * nrt;
+    xr = (xr + 15) / 16 * 16;
+    plan->layer_words = lw; plan->set_words = xr + (long long)L * lw;
+    plan->cand_words = (size_t)2 * G * nrt * 2;
+    const int n_cnt = L * 3 * cnt_ld, n_xexp = L * 3 * xt;
+    auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t fixed = 1024 /*alignment*/ + (size_t)max_slots * kStSlot + up16((size_t)n_sched * 8) + up16((size_t)n_cnt) +
+                         up16((size_t)n_xexp * 2) +
+                         4 * ((((size_t)G * nrt * 2 + 3) & ~(size_t)3) + kStWorkerWarps * kStPartLd + 4 + 64 + 128 + (size_t)kStWorkerWarps * nrt * 2 + 16);
+    const size_t budget = 227 * 1024 - 3072;           // static __shared__ + slack
+    if (fixed + 3 * (size_t)kStStage > budget) return false;
+    int ns = (int)((budget - fixed) / kStStage);
+    if (ns > kStMaxStages) ns = kStMaxStages;
+    plan->n_stages = ns;
+    plan->smem_bytes = fixed + (size_t)ns * kStStage;
+  }
+  if (sched_out) *reinterpret_cast<std::vector<int2>*>(sched_out) = sched;
+  if (cnt_out) *reinterpret_cast<std::vector<unsigned char>*>(cnt_out) = cnt;
+  if (xexp_out) *reinterpret_cast<std::vector<unsigned short>*>(xexp_out) = xexp;
+  return true;
+}
+
+cudaError_t launch_decoder_stream(const StreamArgs& sa_in, const CUtensorMap& cross_map, const CUtensorMap& kc_map,
+                                  const CUtensorMap& vc_map, int nrt, int num_sms, size_t smem_bytes, cudaStream_t st) {
+  void* fns[4] = {(void*)decoder_stream_kernel<1>, (void*)decoder_stream_kernel<2>, (void*)decoder_stream_kernel<4>,
+                  (void*)decoder_stream_kernel<8>};
+  const int slot = nrt == 1 ? 0 : (nrt == 2 ? 1 : (nrt == 4 ? 2 : 3));
+  void* fn = fns[slot];
+  // the attribute is per device: set it on every launch (a host-side table lookup) rather than caching a process-wide flag
+  cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 3072);
+  if (r != cudaSuccess) return r;
+  StreamArgs sa = sa_in;
+  CUtensorMap m0 = cross_map, m1 = kc_map, m2 = vc_map;
+  void* params[] = {&m0, &m1, &m2, &sa};
+  return cudaLaunchCooperativeKernel(fn, dim3(num_sms), dim3(kStThreads), params, smem_bytes, st);
+}
+
+}  // namespace b200asr

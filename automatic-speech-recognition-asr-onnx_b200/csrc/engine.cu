@@ -85,6 +85,14 @@ struct b200asr_engine {
   bool use_ring = true; bool ring_tc = false;   // mma.sync dot products: correct but measured slower than the CUDA-core path
    bool ring_fine = false; int ring_debug = 0; unsigned long long* ring_ll = nullptr; size_t ring_ll_words = 0;
   CUtensorMap cross_map{}; int cmap_B = -1, cmap_T = -1, cmap_rows = -1; int ring_task_inv = 0;
+  // split-K tensor-core streaming decode kernel (decoder_stream.cu): the product path for prefill + greedy loop
+  bool use_stream = true; bool stream_l2_hint = true; int stream_debug = 0;
+  StreamLayer* st_layers = nullptr; CUtensorMap* st_wmaps = nullptr; float* st_fold = nullptr;   // fold vectors (row sums, head g / b)
+  float* st_head_g = nullptr; float* st_head_b = nullptr;
+  unsigned long long* st_acc = nullptr; size_t st_acc_words = 0; unsigned long long* st_cand = nullptr; size_t st_cand_words = 0;
+  int2* st_sched = nullptr; unsigned char* st_cnt = nullptr; unsigned short* st_xexp = nullptr;
+  StreamPlan st_plan{}; int st_plan_B = -1, st_plan_T = -1;
+  CUtensorMap st_cross{}, st_kc{}, st_vc{}; int st_map_B = -1, st_map_T = -1;
   std::string graph_key;
 
   int fail(int code, const std::string& m) { err = m; return code; }
@@ -514,6 +522,113 @@ int run_ring(b200asr_engine* e, int n_iters, bool want_logits) {
   return B200ASR_OK;
 }
 
+// ---- split-K tensor-core streaming decode kernel plumbing (decoder_stream.cu) -------------------
+bool stream_ok(b200asr_engine* e) {
+  const b200asr_config& c = e->cfg;
+  if (!e->use_stream || e->samp_temperature > 0.f || e->act_dtype != kBF16 || e->penalty_range > 32) return false;
+  if (!stream_supported(e->B, c.d_model, c.ffn, c.n_heads, c.vocab, e->T_enc, e->num_sms)) return false;
+  if (e->st_plan_B == e->B && e->st_plan_T == e->T_enc) return true;
+  StreamPlan pl;
+  return stream_plan(e->B, c.d_model, c.ffn, c.n_heads, c.vocab, c.dec_layers, e->T_enc, c.max_target, e->num_sms, &pl,
+                     nullptr, nullptr, nullptr);
+}
+
+int build_stream_tables(b200asr_engine* e) {
+  const b200asr_config& c = e->cfg;
+  const int L = c.dec_layers, d = c.d_model, f = c.ffn;
+  if (!e->st_layers) {
+    // LayerNorm-fold operands: row sums of the LN-consuming matrices, and the final LayerNorm folded around the tied head
+    const size_t per_layer = (size_t)3 * d + d + f;
+    CK(cudaMalloc(&e->st_fold, (per_layer * L + 2 * (size_t)c.vocab) * sizeof(float)));
+    std::vector<StreamLayer> hl(L);
+    std::vector<CUtensorMap> maps((size_t)6 * L + 1);
+    std::string msg;
+    for (int l = 0; l < L; ++l) {
+      const std::string p = "dec.L" + std::to_string(l) + ".";
+      float* base = e->st_fold + per_layer * l;
+      KL(launch_rowdot_bf16(W(e, p + "qkv.w"), nullptr, base, 3 * d, d, e->st));
+      KL(launch_rowdot_bf16(W(e, p + "cq.w"), nullptr, base + 3 * d, d, d, e->st));
+      KL(launch_rowdot_bf16(W(e, p + "fc1.w"), nullptr, base + 4 * d, f, d, e->st));
+      hl[l].qkv_b = WF(e, p + "qkv.b"); hl[l].qkv_ws = base; hl[l].out_b = WF(e, p + "out.b");
+      hl[l].cq_b = WF(e, p + "cq.b"); hl[l].cq_ws = base + 3 * d; hl[l].cout_b = WF(e, p + "cout.b");
+      hl[l].fc1_b = WF(e, p + "fc1.b"); hl[l].fc1_ws = base + 4 * d; hl[l].fc2_b = WF(e, p + "fc2.b");
+      const char* names[6] = {"qkv.w", "out.w", "cq.w", "cout.w", "fc1.w", "fc2.w"};
+      const int rows[6] = {3 * d, d, d, d, f, d}, cols[6] = {d, d, d, d, d, f};
+      for (int i = 0; i < 6; ++i)
+        if (!make_tmap_rows_sw128(&maps[(size_t)l * 6 + i], W(e, p + names[i]), cols[i], rows[i], cols[i], 128, &msg))
+          return e->fail(B200ASR_E_CUDA, "decoder_stream: " + msg);
+    }
+    if (!make_tmap_rows_sw128(&maps[(size_t)6 * L], W(e, "dec.embed"), d, c.vocab, d, 128, &msg))
+      return e->fail(B200ASR_E_CUDA, "decoder_stream: " + msg);
+    e->st_head_g = e->st_fold + per_layer * L; e->st_head_b = e->st_head_g + c.vocab;
+    KL(launch_rowdot_bf16(W(e, "dec.embed"), WF(e, "dec.ln.g"), e->st_head_g, c.vocab, d, e->st));
+    KL(launch_rowdot_bf16(W(e, "dec.embed"), WF(e, "dec.ln.b"), e->st_head_b, c.vocab, d, e->st));
+    CK(cudaMalloc(&e->st_layers, sizeof(StreamLayer) * L));
+    CK(b200_copy_sync(e, e->st_layers, hl.data(), sizeof(StreamLayer) * L, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&e->st_wmaps, sizeof(CUtensorMap) * maps.size()));
+    CK(b200_copy_sync(e, e->st_wmaps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice));
+    int inv = 0;
+    for (int i = 1; i < e->num_sms; ++i) if ((i * kRingTaskMul) % e->num_sms == 1) inv = i;
+    e->ring_task_inv = inv;
+  }
+  if (e->st_plan_B != e->B || e->st_plan_T != e->T_enc) {
+    std::vector<int2> sched; std::vector<unsigned char> cnt; std::vector<unsigned short> xexp;
+    StreamPlan pl;
+    if (!stream_plan(e->B, d, f, c.n_heads, c.vocab, L, e->T_enc, c.max_target, e->num_sms, &pl, &sched, &cnt, &xexp))
+      return e->fail(B200ASR_E_INVALID, "decoder_stream: plan does not fit");
+    CK(cudaStreamSynchronize(e->st));
+    if (e->st_sched) { cudaFree(e->st_sched); cudaFree(e->st_cnt); cudaFree(e->st_xexp); }
+    CK(cudaMalloc(&e->st_sched, sched.size() * sizeof(int2)));
+    CK(cudaMalloc(&e->st_cnt, cnt.size() + 16));
+    CK(cudaMalloc(&e->st_xexp, xexp.size() * 2 + 16));
+    CK(b200_copy_sync(e, e->st_sched, sched.data(), sched.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CK(b200_copy_sync(e, e->st_cnt, cnt.data(), cnt.size(), cudaMemcpyHostToDevice));
+    CK(b200_copy_sync(e, e->st_xexp, xexp.data(), xexp.size() * 2, cudaMemcpyHostToDevice));
+    const size_t words = (size_t)pl.set_words * 2;
+    if (words > e->st_acc_words) {
+      if (e->st_acc) cudaFree(e->st_acc);
+      CK(cudaMalloc(&e->st_acc, words * 8));
+      e->st_acc_words = words;
+    }
+    if (pl.cand_words > e->st_cand_words) {
+      if (e->st_cand) cudaFree(e->st_cand);
+      CK(cudaMalloc(&e->st_cand, pl.cand_words * 8));
+      e->st_cand_words = pl.cand_words;
+    }
+    e->st_plan = pl; e->st_plan_B = e->B; e->st_plan_T = e->T_enc;
+  }
+  if (e->st_map_B != e->B || e->st_map_T != e->T_enc) {
+    std::string msg;
+    const int64_t crows = (int64_t)2 * L * e->B * e->T_enc;
+    const int64_t krows = (int64_t)L * e->B * c.n_heads * c.max_target;
+    if (!make_tmap_2d_plain(&e->st_cross, e->cross_kv, d, crows, d, 64, 128, &msg) ||
+        !make_tmap_2d_plain(&e->st_kc, e->kcache, 64, krows, 64, 64, 128, &msg) ||
+        !make_tmap_2d_plain(&e->st_vc, e->vcache, 64, krows, 64, 64, 128, &msg))
+      return e->fail(B200ASR_E_CUDA, "decoder_stream: " + msg);
+    e->st_map_B = e->B; e->st_map_T = e->T_enc;
+  }
+  return B200ASR_OK;
+}
+
+// one cooperative launch: n_first forced tokens per utterance ([B][n_first] on device; the last one feeds the first head),
+// then n_heads - 1 further greedy iterations.  first_is_prefill: the first head applies the begin-suppress bias.
+int run_stream(b200asr_engine* e, int n_heads_iters, const int* first_tokens, int n_first, bool first_is_prefill, bool want_logits) {
+  RET(build_stream_tables(e));
+  StreamArgs sa{};
+  fill_mega_args(e, sa.m, n_heads_iters, first_tokens, n_first, first_is_prefill, want_logits);
+  RET(arm_timing(e, sa.m));
+  const StreamPlan& pl = e->st_plan;
+  sa.sl = e->st_layers; sa.wmaps = e->st_wmaps; sa.head_g = e->st_head_g; sa.head_b = e->st_head_b;
+  sa.acc = e->st_acc; sa.set_words = pl.set_words; sa.layer_words = pl.layer_words;
+  sa.cand = e->st_cand; sa.sched = e->st_sched; sa.cnt = e->st_cnt; sa.xexp = e->st_xexp;
+  sa.cnt_ld = pl.cnt_ld; sa.xt = pl.xt; sa.n_stages = pl.n_stages; sa.n_slots = pl.n_slots;
+  sa.task_inv = e->ring_task_inv; sa.l2_hint = e->stream_l2_hint ? 1 : 0; sa.debug = e->stream_debug;
+  CK(cudaMemsetAsync(e->st_acc, 0, (size_t)pl.set_words * 2 * 8, e->st));
+  CK(cudaMemsetAsync(e->st_cand, 0, pl.cand_words * 8, e->st));
+  KL(launch_decoder_stream(sa, e->st_cross, e->st_kc, e->st_vc, pl.nrt, e->num_sms, pl.smem_bytes, e->st));
+  return B200ASR_OK;
+}
+
 int do_upload(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples) {
   const b200asr_config& c = e->cfg;
   if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
@@ -535,6 +650,8 @@ int do_prefill(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt, i
   if (!e->encoded) return e->fail(B200ASR_E_INVALID, "prefill before encode");
   if (!prompt_ids || n_prompt <= 0 || n_prompt >= c.max_target) return e->fail(B200ASR_E_INVALID, "bad prompt");
   const int B = e->B;
+  for (int i = 0; i < B * n_prompt; ++i)
+    if (prompt_ids[i] < 0 || prompt_ids[i] >= c.vocab) return e->fail(B200ASR_E_INVALID, "prompt id out of range [0, vocab)");
   CK(cudaMemcpyAsync(e->d_prompt, prompt_ids, (size_t)B * n_prompt * 4, cudaMemcpyHostToDevice, e->st));
   CK(cudaMemsetAsync(e->dstate, 0, sizeof(DecState), e->st));
   CK(cudaMemsetAsync(e->n_gen, 0, (size_t)B * 4, e->st));
@@ -548,7 +665,8 @@ int do_prefill(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt, i
     e->prefilled = true;
     return B200ASR_OK;
   }
-  if (mega_ok(e, n_prompt)) RET(run_mega(e, 1 + extra_iters, e->d_prompt, n_prompt, true, true));
+  if (stream_ok(e)) RET(run_stream(e, 1 + extra_iters, e->d_prompt, n_prompt, true, true));
+  else if (mega_ok(e, n_prompt)) RET(run_mega(e, 1 + extra_iters, e->d_prompt, n_prompt, true, true));
   else RET(enqueue_decoder(e, e->d_prompt, n_prompt, true));
   e->prefilled = true;
   return B200ASR_OK;
@@ -611,7 +729,8 @@ void b200asr_destroy(b200asr_engine* e) {
                   e->hidden, e->stem, e->xhat, e->qkv, e->ctx, e->ffn, e->S, e->P, e->cross_kv, e->kcache, e->vcache,
                   e->dx, e->dq, e->dctx, e->dffn, e->logits, e->prob, e->d_prompt, e->cur_token, e->tokens, e->n_gen,
                   e->finished, e->save_id, e->n_save, e->selected_hist, e->d_stop, e->dstate, e->mega_layers, e->pf_blocks,
-                  e->mega_bar, e->cand_val, e->cand_idx, e->timing, e->ring_ll, e->samp_noise};
+                  e->mega_bar, e->cand_val, e->cand_idx, e->timing, e->ring_ll, e->samp_noise,
+                  e->st_layers, e->st_wmaps, e->st_fold, e->st_acc, e->st_cand, e->st_sched, e->st_cnt, e->st_xexp};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -625,6 +744,9 @@ int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "mega")) { e->use_mega = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "pdl")) { e->use_pdl = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "stream")) { e->use_stream = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "stream_l2_hint")) { e->stream_l2_hint = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "stream_debug")) { e->stream_debug = (int)value; return B200ASR_OK; }
   if (!strcmp(key, "ring")) { e->use_ring = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_tc")) { e->ring_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_debug")) { e->ring_debug = (int)value; return B200ASR_OK; }
@@ -677,6 +799,14 @@ int b200asr_set_tensor(b200asr_engine* e, const char* name_c, const float* host,
   }
   e->w[name] = t;
   e->finalized = false;
+  // tables that cache weight pointers (tensor maps, fold vectors, layer tables) are rebuilt on the next decoder launch
+  if (e->st_layers) {
+    cudaFree(e->st_layers); cudaFree(e->st_wmaps); cudaFree(e->st_fold);
+    e->st_layers = nullptr; e->st_wmaps = nullptr; e->st_fold = nullptr;
+  }
+  if (e->mega_layers) { cudaFree(e->mega_layers); e->mega_layers = nullptr; cudaFree(e->pf_blocks); e->pf_blocks = nullptr;
+                        cudaFree(e->mega_bar); e->mega_bar = nullptr; cudaFree(e->cand_val); e->cand_val = nullptr;
+                        cudaFree(e->cand_idx); e->cand_idx = nullptr; e->pf_B = -1; e->pf_T = -1; }
   return B200ASR_OK;
 }
 
@@ -839,8 +969,13 @@ int b200asr_decode_step(b200asr_engine* e, const int32_t* token_in, float* logit
   CK(cudaMemcpyAsync(&hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost, e->st));
   CK(cudaStreamSynchronize(e->st));
   if (hs.kv_len + 1 > e->cfg.max_target) return e->fail(B200ASR_E_INVALID, "KV cache full");
-  if (token_in) CK(cudaMemcpyAsync(e->cur_token, token_in, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->st));
-  if (ring_ok(e)) RET(run_ring(e, 1, true));
+  if (token_in) {
+    for (int b = 0; b < e->B; ++b)
+      if (token_in[b] < 0 || token_in[b] >= e->cfg.vocab) return e->fail(B200ASR_E_INVALID, "token id out of range [0, vocab)");
+    CK(cudaMemcpyAsync(e->cur_token, token_in, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->st));
+  }
+  if (stream_ok(e)) RET(run_stream(e, 1, e->cur_token, 1, false, true));
+  else if (ring_ok(e)) RET(run_ring(e, 1, true));
   else if (mega_ok(e, 1)) RET(run_mega(e, 1, e->cur_token, 1, false, true));
   else RET(launch_step(e));
   if (logits_out) CK(cudaMemcpyAsync(logits_out, e->logits, (size_t)e->B * e->cfg.vocab * 4, cudaMemcpyDeviceToHost, e->st));
@@ -860,8 +995,10 @@ static int decode_loop(b200asr_engine* e, int max_steps, int32_t* tokens_out, in
   const int room = c.max_target - e->n_prompt;    // cache positions left after the prompt
   if (steps > room) steps = room;
   int* h_done = e->h_pinned;
-  if (steps > 0 && ring_ok(e)) {
-    RET(run_ring(e, steps, false));                             // the kernel leaves the loop itself when all latched
+  if (steps > 0 && stream_ok(e)) {
+    RET(run_stream(e, steps, e->cur_token, 1, false, false));   // the kernel leaves the loop itself when all latched
+  } else if (steps > 0 && ring_ok(e)) {
+    RET(run_ring(e, steps, false));
   } else if (steps > 0 && mega_ok(e, 1)) {
     RET(run_mega(e, steps, e->cur_token, 1, false, false));
   } else {
@@ -931,6 +1068,20 @@ int b200asr_transcribe_resident(b200asr_engine* e, const int32_t* prompt_ids, in
   const int saved = e->limit_cfg;
   if (max_new > 0 && (saved == 0 || max_new < saved)) e->limit_cfg = max_new;
   int r;
+  if (stream_ok(e)) {
+    // prompt prefill + the whole greedy loop in one launch of the streaming kernel
+    r = do_prefill(e, prompt_ids, n_prompt, -1);                 // reset + upload the prompt only
+    if (r == B200ASR_OK) {
+      int heads = e->limit;                                      // first head = token #1, then limit - 1 further launches
+      const int room = e->cfg.max_target - n_prompt + 1;
+      if (heads > room) heads = room;
+      if (heads < 1) heads = 1;
+      r = run_stream(e, heads, e->d_prompt, n_prompt, true, false);
+    }
+    e->limit_cfg = saved;
+    RET(r);
+    return fetch_tokens(e, tokens_out, tokens_ld, lens_out);
+  }
   if (mega_ok(e, n_prompt)) {
     r = do_prefill(e, prompt_ids, n_prompt, -1);                 // reset + upload the prompt only
     if (r == B200ASR_OK && ring_ok(e)) {
@@ -1030,6 +1181,17 @@ int b200asr_get_stage(b200asr_engine* e, const char* name_c, float* out, int64_t
     CK(b200_copy_sync(e, ht.data(), e->timing, ht.size() * 8, cudaMemcpyDeviceToHost));
     n = 0;
     for (size_t i = 1; i < ht.size() && ht[i] != 0 && n < capacity; ++i) out[n++] = (float)((double)(ht[i] - ht[i - 1]) * 1e-3);
+  } else if (name == "stream_acc_val" || name == "stream_acc_cnt") {   // debug: decoded accumulator words of both step sets
+    if (!e->st_acc) return e->fail(B200ASR_E_INVALID, "the streaming decode kernel has not run");
+    n = (int64_t)e->st_plan.set_words * 2;
+    if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
+    std::vector<unsigned long long> hw((size_t)n);
+    CK(b200_copy_sync(e, hw.data(), e->st_acc, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) {
+      const unsigned long long w = hw[(size_t)i];
+      const unsigned long long cnt = (w + (1ull << 51)) >> 52;
+      out[i] = name == "stream_acc_cnt" ? (float)cnt : (float)((double)(long long)(w - (cnt << 52)) / 16777216.0);
+    }
   } else if (name == "selected") {                          // [B][step] as float
     DecState hs;
     CK(b200_copy_sync(e, &hs, e->dstate, sizeof hs, cudaMemcpyDeviceToHost));

@@ -34,6 +34,7 @@ def test_ring_vs_mega_logits_and_tokens(path):
     res = {}
     for ring in (1, 0):
         eng = make_engine(tensors, "bf16")
+        eng.set_option("stream", 0)
         eng.set_option("ring", ring)
         eng.set_option("ring_tc", 0)
         lg = _forced(eng, g["pcm"], g["prompt"], g["forced_tokens"].tolist())
@@ -78,6 +79,7 @@ def test_ring_tc_vs_mega_and_golden(path):
     out = {}
     for ring in (1, 0):
         eng = make_engine(tensors, "bf16")
+        eng.set_option("stream", 0)
         eng.set_option("ring", ring)
         eng.set_option("ring_tc", 1)
         forced = _forced(eng, g["pcm"], g["prompt"], g["forced_tokens"].tolist())[0]
@@ -107,6 +109,7 @@ def test_ring_tc_vs_mega_and_golden(path):
 def test_ring_stop_latch():
     g, raw, tensors = load_case(GOLD[0])
     eng = make_engine(tensors, "bf16")
+    eng.set_option("stream", 0)
     eng.set_decode_options(stop_ids=[], generate_limit=10)
     free = eng.transcribe(g["pcm"], g["prompt"], max_new=10)[0]
     stop = free[3]
@@ -126,6 +129,7 @@ def test_ring_batch(nb):
     out = {}
     for ring in (1, 0):
         eng = make_engine(tensors, "bf16", max_batch=nb)
+        eng.set_option("stream", 0)
         eng.set_option("ring", ring)
         eng.set_option("ring_tc", 0)
         lg = _forced(eng, clips, g["prompt"], forced)
@@ -148,6 +152,7 @@ def test_ring_tc_batch_equals_single(nb):
     clips = np.stack([synth_pcm(30 + i, n) for i in range(nb)])
     forced = g["forced_tokens"].tolist()[:4]
     eng = make_engine(tensors, "bf16", max_batch=nb)
+    eng.set_option("stream", 0)
     eng.set_option("ring_tc", 1)
     lb = _forced(eng, clips, g["prompt"], forced)
     singles = np.concatenate([_forced(eng, clips[i], g["prompt"], forced) for i in range(nb)], axis=0)
