@@ -215,7 +215,7 @@ struct StreamArgs {
   unsigned long long* acc;             // [2][set_words] accumulator words (12-bit count | 52-bit fixed point), zero at launch
   long long set_words, layer_words;
   unsigned long long* cand;            // [2][grid][NRT][2] flag-in-data arg-max candidates
-  const int2* sched;                   // [grid][6L + 1] atom ranges (head: tile ranges)
+  const int4* sched;                   // [grid][6L + 1] {atom begin, atom end, first tile, first k-atom}
   const unsigned char* cnt;            // [L][3][cnt_ld] contributors per 128-row output tile of qkv / cq / fc1
   const unsigned short* xexp;          // [L][3][xt] cumulative contributors per residual-stream tile after out / cout / fc2
   int cnt_ld, xt;
@@ -232,7 +232,7 @@ struct StreamPlan {
   size_t smem_bytes = 0; long long set_words = 0, layer_words = 0; size_t cand_words = 0;
 };
 bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers, int T, int max_target, int num_sms,
-                 StreamPlan* plan, void* sched_out /*std::vector<int2>*/, void* cnt_out /*std::vector<unsigned char>*/,
+                 StreamPlan* plan, void* sched_out /*std::vector<int4>*/, void* cnt_out /*std::vector<unsigned char>*/,
                  void* xexp_out /*std::vector<unsigned short>*/);
 cudaError_t launch_decoder_stream(const StreamArgs& sa, const CUtensorMap& cross_map, const CUtensorMap& kc_map,
                                   const CUtensorMap& vc_map, int nrt, int num_sms, size_t smem_bytes, cudaStream_t st);

@@ -73,55 +73,51 @@ __device__ __forceinline__ void st_zero2(u64* p) {
 __device__ __forceinline__ void red_add(u64* p, u64 v) { asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
 // accumulator word = (contributors << 52) + two's-complement fixed-point sum
-__device__ __forceinline__ u64 enc_fix(float v, float scale) { return (1ull << 52) + (u64)__float2ll_rn(v * scale); }
+__device__ __forceinline__ u64 enc_fix(float v, float scale, unsigned n = 1u) { return ((u64)n << 52) + (u64)__float2ll_rn(v * scale); }
 __device__ __forceinline__ unsigned acc_cnt(u64 w) { return (unsigned)((w + (1ull << 51)) >> 52); }
 __device__ __forceinline__ long long acc_raw(u64 w, unsigned c) { return (long long)(w - ((u64)c << 52)); }
 __device__ __forceinline__ float acc_val(u64 w, unsigned c) { return (float)acc_raw(w, c) * kFixInv; }
 
+// Everything that is not on the per-phase path is kept out of line: the step is a chain of ~260 short phases and the
+// instruction stream of a phase has to stay cache-resident (a 264 KB first version of this kernel ran every phase cold).
 __device__ __noinline__ void st_timeout(int where, int x, int y) {
   printf("b200asr decoder_stream: wait timed out (where %d, block %d thread %d, %d %d)\n", where, blockIdx.x, threadIdx.x, x, y);
   __trap();
 }
-
-__device__ __forceinline__ void swait(uint64_t* bar, uint32_t parity, int where) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void swait_slow(uint64_t* bar, uint32_t parity, int where) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity))
     if (clock64() - t0 > kStSpin) st_timeout(where, (int)parity, 0);
 }
+__device__ __forceinline__ void swait(uint64_t* bar, uint32_t parity, int where) {
+  if (!mbar_try_wait(bar, parity)) swait_slow(bar, parity, where);
+}
+__device__ __noinline__ float2 gelu2(float a, float b) { return make_float2(gelu_erf(a), gelu_erf(b)); }
 
-// poll one accumulator word until `expect` contributors have arrived
-__device__ __forceinline__ u64 poll_w(const u64* p, unsigned expect, int where) {
-  u64 w = ld_w(p);
-  if (acc_cnt(w) == expect) return w;
-  const long long t0 = clock64();
-  for (;;) {
-    w = ld_w(p);
-    if (acc_cnt(w) == expect) return w;
-    if (clock64() - t0 > kStSpin) st_timeout(where, (int)expect, (int)acc_cnt(w));
-  }
+// (mean, rstd) from the two statistics words of a row (sum x in 2^-24, sum x^2 in 2^-12 fixed point)
+__device__ __noinline__ float2 ln_stats(u64 w0, u64 w1, unsigned cnt, float inv_d, float eps) {
+  const double sm = (double)acc_raw(w0, cnt) * (1.0 / 16777216.0), sq = (double)acc_raw(w1, cnt) * (1.0 / 4096.0);
+  const double mu = sm * (double)inv_d;
+  return make_float2((float)mu, rsqrtf((float)fmax(sq * (double)inv_d - mu * mu, 0.0) + eps));
 }
 
-__device__ __forceinline__ void tma_2d_hint(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t pol, bool hint) {
-  if (hint)
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol) : "memory");
-  else
-    tma_load_2d(dst, tm, c0, c1, bar);
+__device__ __forceinline__ void tma_2d_hint(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void tma_3d_hint(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t pol, bool hint) {
-  if (hint)
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
-                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(0), "l"(pol) : "memory");
-  else
-    tma_load_3d(dst, tm, c0, c1, 0, bar);
+__device__ __forceinline__ void tma_3d_hint(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(0), "l"(pol) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* r) {
+  uint32_t u[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
                : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(u[j]);
 }
 
 struct RingPos { int stage; uint32_t phase; };
@@ -133,6 +129,7 @@ __device__ __forceinline__ void ring_adv(RingPos& p, int n, int NS) {
 
 // linear phase p6 (0 qkv, 1 out, 2 cq, 3 cout, 4 fc1, 5 fc2): k-atoms per weight row
 __device__ __forceinline__ int phase_ka(int p6, int d, int ffn) { return (p6 == 5 ? ffn : d) >> 6; }
+__device__ __forceinline__ int phase_p6(int ph) { return ph == 0 ? 0 : (ph == 2 ? 1 : (ph == 3 ? 2 : ph - 2)); }
 
 // first attention task (utterance * H + head) owned by this CTA in layer l (kind 0 self, 1 cross); further tasks at + grid
 __device__ __forceinline__ int first_task(int l, int kind, int task_inv) {
@@ -145,7 +142,8 @@ __device__ __forceinline__ int first_task(int l, int kind, int task_inv) {
 }  // namespace
 
 // ---------------------------------------------------------------------------
-template <int NRT>
+// DBG: per-phase time stamps into a.timing (block 0), compiled only into the instrumented instantiation
+template <int NRT, bool DBG>
 __global__ void __launch_bounds__(kStThreads, 1)
 decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_constant__ CUtensorMap kc_map,
                       const __grid_constant__ CUtensorMap vc_map, const __grid_constant__ StreamArgs sa) {
@@ -158,8 +156,8 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   uint8_t* ring = base;
   uint8_t* bbuf = ring + (size_t)NS * kStStage;
   auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  int2* s_sched = reinterpret_cast<int2*>(bbuf + (size_t)sa.n_slots * kStSlot);
-  unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_sched) + up16((size_t)n_sched * 8);
+  int4* s_sched = reinterpret_cast<int4*>(bbuf + (size_t)sa.n_slots * kStSlot);     // {atom begin, atom end, first tile, first k-atom}
+  unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_sched) + (size_t)n_sched * 16;
   unsigned short* s_xexp = reinterpret_cast<unsigned short*>(s_cnt + up16((size_t)n_cnt));
   float* s_cand = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_xexp) + up16((size_t)n_xexp * 2));   // [G][NRT][2]
   float* s_part = s_cand + (((size_t)G * NRT * 2 + 3) & ~(size_t)3);             // [8][68] per-warp (max, sum, o[64]) + [8*68] new-token score
@@ -184,7 +182,6 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   const long long xreg = sa.set_words - (long long)L * sa.layer_words;   // residual-stream words + head statistics
   const int kv0 = a.state->kv_len;
   constexpr int kEpiWarps = NRT > 4 ? 8 : 4;
-  const int n_vtiles = (a.vocab + 127) >> 7;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); box_cnt[s] = 0; }
@@ -217,8 +214,8 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
     // =======================================================================
     if (lane == 0) {
       uint64_t pol = 0;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-      const bool hint = sa.l2_hint != 0;
+      if (sa.l2_hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
       RingPos p{0, 0};
       long long issued = 0;
       bool stop = false;
@@ -233,23 +230,21 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
         }
         return true;
       };
-      auto weights = [&](const CUtensorMap* tm, int a0, int a1, int KA) {
-        if (a0 >= a1) return;
-        int tile = a0 / KA, ka = a0 - tile * KA;
-        for (int at = a0; at < a1; ++at) {
+      auto weights = [&](const CUtensorMap* tm, int4 r, int KA) {
+        int tile = r.z, ka = r.w;
+        for (int at = r.x; at < r.y; ++at) {
           if (!acquire()) { stop = true; return; }
           mbar_expect_tx(&full_bar[p.stage], kStStage);
-          tma_3d_hint(ring + (size_t)p.stage * kStStage, tm, ka * 64, tile * 128, &full_bar[p.stage], pol, hint);
+          tma_3d_hint(ring + (size_t)p.stage * kStStage, tm, ka * 64, tile * 128, &full_bar[p.stage], pol);
           ++issued; ring_adv(p, 1, NS);
           if (++ka == KA) { ka = 0; ++tile; }
         }
       };
-      auto kvbox = [&](const CUtensorMap* tm, int c0, int row) -> bool {
-        if (!acquire()) { stop = true; return false; }
+      auto kvbox = [&](const CUtensorMap* tm, int c0, int row) {
+        if (!acquire()) { stop = true; return; }
         mbar_expect_tx(&full_bar[p.stage], kStStage);
-        tma_2d_hint(ring + (size_t)p.stage * kStStage, tm, c0, row, &full_bar[p.stage], pol, hint);
+        tma_2d_hint(ring + (size_t)p.stage * kStStage, tm, c0, row, &full_bar[p.stage], pol);
         ++issued; ring_adv(p, 1, NS);
-        return true;
       };
       for (int it = 0; it < total_iters && !stop; ++it) {
         const int kv = kv0 + it;
@@ -270,32 +265,22 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               for (int t = t0; t < ntask && !stop; t += G) {
                 const int b = t / H, h = t - b * H;
                 const int row0 = ((l * B + b) * H + h) * a.max_target;
-                for (int i = 0; i < nb; ++i) {
-                  if (!kvbox(&kc_map, 0, row0 + i * 128)) break;
-                  if (!kvbox(&vc_map, 0, row0 + i * 128)) break;
-                }
+                for (int i = 0; i < nb && !stop; ++i) { kvbox(&kc_map, 0, row0 + i * 128); kvbox(&vc_map, 0, row0 + i * 128); }
               }
             } else if (ph == 4) {               // cross K / V of my tasks
               const int nb = (T + 127) >> 7;
               for (int t = first_task(l, 1, sa.task_inv); t < ntask && !stop; t += G) {
                 const int b = t / H, h = t - b * H;
                 const int rk = (l * B + b) * T, rv = ((L + l) * B + b) * T;
-                for (int i = 0; i < nb; ++i) {
-                  if (!kvbox(&cross_map, h * 64, rk + i * 128)) break;
-                  if (!kvbox(&cross_map, h * 64, rv + i * 128)) break;
-                }
+                for (int i = 0; i < nb && !stop; ++i) { kvbox(&cross_map, h * 64, rk + i * 128); kvbox(&cross_map, h * 64, rv + i * 128); }
               }
             } else {
-              const int p6 = ph == 0 ? 0 : (ph == 2 ? 1 : (ph == 3 ? 2 : ph - 2));
-              const int2 r = s_sched[l * 6 + p6];
-              weights(&sa.wmaps[l * 6 + p6], r.x, r.y, phase_ka(p6, d, ffn));
+              const int p6 = phase_p6(ph);
+              weights(&sa.wmaps[l * 6 + p6], s_sched[l * 6 + p6], phase_ka(p6, d, ffn));
             }
           }
         }
-        if (head_on && !stop) {
-          const int2 r = s_sched[6 * L];
-          weights(&sa.wmaps[6 * L], r.x * KAd, r.y * KAd, KAd);
-        }
+        if (head_on && !stop) weights(&sa.wmaps[6 * L], s_sched[6 * L], KAd);
       }
       // drain: every copy that was issued must have landed before the CTA may exit
       for (int s = 0; s < NS; ++s) {
@@ -316,19 +301,17 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
       uint32_t bpar = 0;
       int tctr = 0;
       const uint32_t ring_u = smem_u32(ring), bbuf_u = smem_u32(bbuf);
-      auto linear = [&](int a0, int a1, int KA) {
+      auto linear = [&](int4 r, int KA) {
         swait(&b_ready, bpar, 3); bpar ^= 1u;
         tc_fence_after();
-        if (a0 >= a1) return;
-        int tile = a0 / KA, ka = a0 - tile * KA;
-        const int ka0 = ka;
+        int ka = r.w;
         bool fresh = true;
-        for (int at = a0; at < a1; ++at) {
+        for (int at = r.x; at < r.y; ++at) {
           const int buf = tctr & 1;
           if (fresh) { swait(&acc_empty[buf], (uint32_t)(((tctr >> 1) & 1) ^ 1), 4); tc_fence_after(); }
           swait(&full_bar[p.stage], p.phase, 5);
           tc_fence_after();
-          int slot = ka - ka0; if (slot < 0) slot += KA;
+          int slot = ka - r.w; if (slot < 0) slot += KA;
           const uint64_t adesc = smem_desc_sw128(ring_u + (uint32_t)p.stage * kStStage);
           const uint64_t bdesc = smem_desc_sw128(bbuf_u + (uint32_t)slot * kStSlot);
 #pragma unroll
@@ -338,10 +321,10 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           tc_commit(&empty_bar[p.stage]);
           ring_adv(p, 1, NS);
           ++ka;
-          if (ka == KA || at + 1 == a1) {
+          if (ka == KA || at + 1 == r.y) {
             tc_commit(&acc_full[buf]);
             ++tctr; fresh = true;
-            if (ka == KA) { ka = 0; ++tile; }
+            if (ka == KA) ka = 0;
           }
         }
       };
@@ -358,16 +341,12 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               for (int t = first_task(l, ph == 4, sa.task_inv); t < ntask; t += G) n += 2 * nb;
               ring_adv(p, n, NS);
             } else {
-              const int p6 = ph == 0 ? 0 : (ph == 2 ? 1 : (ph == 3 ? 2 : ph - 2));
-              const int2 r = s_sched[l * 6 + p6];
-              linear(r.x, r.y, phase_ka(p6, d, ffn));
+              const int p6 = phase_p6(ph);
+              linear(s_sched[l * 6 + p6], phase_ka(p6, d, ffn));
             }
           }
         }
-        if (head_on) {
-          const int2 r = s_sched[6 * L];
-          linear(r.x * KAd, r.y * KAd, KAd);
-        }
+        if (head_on) linear(s_sched[6 * L], KAd);
       }
     }
     __syncwarp();
@@ -379,20 +358,21 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
     const int r_mine = ww % NRT;                         // the utterance this warp stages
     const int g_mine = ww / NRT;                         // slot group
     constexpr int NG = kStWorkerWarps / NRT;             // slot groups
+    constexpr int U = NRT <= 2 ? 1 : (NRT == 4 ? 2 : 4); // k-atoms a thread polls together
     const bool row_ok = r_mine < B;
     const int q_tm = warp & 3;                           // TMEM lane quarter this warp may read
     const int set_tm = ww >> 2;                          // 0: utterances 0-3 (columns 0-7), 1: utterances 4-7 (columns 8-15)
     const bool epi_warp = ww < kEpiWarps;
+    const float inv_d = 1.0f / (float)d;
     RingPos pos{0, 0};
     int tctr = 0;
     int step = a.state->step;
     int it_done = 0;
-    unsigned long long* tstamp = a.timing;
     int t_idx = 0;
     auto stamp = [&]() {
-      if (tstamp && blockIdx.x == 0 && wt == 0 && t_idx < a.timing_cap) {
+      if (DBG && a.timing && blockIdx.x == 0 && wt == 0 && t_idx < a.timing_cap) {
         unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        tstamp[t_idx++] = t;
+        a.timing[t_idx++] = t;
       }
     };
     stamp();
@@ -414,283 +394,25 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
       u64* set = sa.acc + (size_t)(it & 1) * sa.set_words;
       u64* oset = sa.acc + (size_t)((it + 1) & 1) * sa.set_words;
       u64* xw = set;                                               // [NRT][d] residual stream, then [NRT][2] head statistics
-
-      // ---- B-operand staging of one linear phase.  mode 0: x0 = embedding + position (layer 0), 1: residual words,
-      //      2: attention context words, 3: fc1 words -> LN fold + GELU, 4: residual words x gamma (head) ----
-      auto prep = [&](int mode, int a0, int a1, int KA, const u64* src, long long src_ld, int exp_row /*table row*/,
-                      u64* stat_out /*[NRT][2] or null*/, const u64* stat_in, const float* fold_ws, const float* fold_b) {
-        const int nat = a1 - a0;
-        const int nslot = nat < KA ? nat : KA;
-        int ka0 = 0;
-        if (nat > 0) ka0 = a0 % KA;
-        const int stat_slots = (stat_out && mode != 4 && a0 < KA) ? ((a1 < KA ? a1 : KA) - a0) : 0;
-        float mean = 0.f, rstd = 1.f;
-        if (mode == 3 && row_ok && g_mine < nslot) {
-          const u64 w0 = poll_w(stat_in + r_mine * 2, (unsigned)KAd, 10);
-          const u64 w1 = poll_w(stat_in + r_mine * 2 + 1, (unsigned)KAd, 11);
-          const double sm = (double)acc_raw(w0, KAd) * (1.0 / 16777216.0), sq = (double)acc_raw(w1, KAd) * (1.0 / 4096.0);
-          const double mu = sm / (double)d;
-          mean = (float)mu;
-          rstd = rsqrtf((float)fmax(sq / (double)d - mu * mu, 0.0) + a.eps);
-        }
-        const u64* srow = src + (long long)r_mine * src_ld;
-        for (int s0 = g_mine; s0 < nslot && row_ok; s0 += 4 * NG) {
-          u64 w[4][2];
-          int kk[4];
-          unsigned ex[4];
-          unsigned pend = 0;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int s = s0 + u * NG;
-            kk[u] = 0; ex[u] = 0;
-            if (s < nslot) {
-              int ka = ka0 + s; if (ka >= KA) ka -= KA;
-              kk[u] = ka * 64 + 2 * lane;
-              if (mode == 1 || mode == 4) ex[u] = s_xexp[exp_row * sa.xt + (kk[u] >> 7)];
-              else if (mode == 3) ex[u] = s_cnt[exp_row * sa.cnt_ld + (kk[u] >> 7)];
-              else ex[u] = 1;
-              pend |= 1u << u;
-            }
-          }
-          if (mode != 0) {
-            unsigned todo = pend;
-            long long t0 = 0;
-            while (todo) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) if (todo & (1u << u)) ld_w2(srow + kk[u], w[u][0], w[u][1]);
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if ((todo & (1u << u)) && acc_cnt(w[u][0]) == ex[u] && acc_cnt(w[u][1]) == ex[u]) todo &= ~(1u << u);
-              if (todo) {
-                if (t0 == 0) t0 = clock64();
-                else if (clock64() - t0 > kStSpin) st_timeout(12 + mode, kk[0], (int)acc_cnt(w[0][0]));
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (!(pend & (1u << u))) continue;
-            const int s = s0 + u * NG;
-            const int k = kk[u];
-            float f0, f1;
-            if (mode == 0) {
-              const float2 e2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
-                  reinterpret_cast<const bf16*>(a.embed) + (long long)s_tok[r_mine] * d + k));
-              const float2 p2 = *reinterpret_cast<const float2*>(a.pos + (long long)kv * d + k);
-              f0 = p2.x + e2.x; f1 = p2.y + e2.y;
-            } else {
-              f0 = acc_val(w[u][0], ex[u]); f1 = acc_val(w[u][1], ex[u]);
-            }
-            if (s < stat_slots || (mode == 4 && (k >> 6) % n_vtiles >= a0 / KA && (k >> 6) % n_vtiles < a1 / KA)) {
-              // LayerNorm statistics of this k-atom (64 values of utterance r_mine): one RED pair per (atom, utterance)
-              const float sv = warp_sum(f0 + f1);
-              const float qv = warp_sum(fmaf(f0, f0, f1 * f1));
-              if (lane == 0) red_add(stat_out + r_mine * 2, enc_fix(sv, kFixScale));
-              if (lane == 1) red_add(stat_out + r_mine * 2 + 1, enc_fix(qv, kSqScale));
-            }
-            if (mode == 3) {
-              const float2 ws2 = *reinterpret_cast<const float2*>(fold_ws + k);
-              const float2 b2 = *reinterpret_cast<const float2*>(fold_b + k);
-              f0 = gelu_erf(fmaf(rstd, f0 - mean * ws2.x, b2.x));
-              f1 = gelu_erf(fmaf(rstd, f1 - mean * ws2.y, b2.y));
-            } else if (mode == 4) {
-              const float2 g2 = *reinterpret_cast<const float2*>(fold_ws + k);
-              f0 *= g2.x; f1 *= g2.y;
-            }
-            // x = hi + lo, both bf16: rows 2r (hi) and 2r + 1 (lo) of the slot's 16-row K-major SWIZZLE_128B tile
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(f0, f1);
-            const float2 hf = __bfloat1622float2(hi);
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(f0 - hf.x, f1 - hf.y);
-            uint8_t* slotp = bbuf + (size_t)s * kStSlot;
-            const int rh = 2 * r_mine, rl = rh + 1;
-            const int chunk = lane >> 2, within = (lane & 3) * 4;
-            *reinterpret_cast<__nv_bfloat162*>(slotp + (rh >> 3) * 1024 + (rh & 7) * 128 + ((chunk ^ (rh & 7)) << 4) + within) = hi;
-            *reinterpret_cast<__nv_bfloat162*>(slotp + (rl >> 3) * 1024 + (rl & 7) * 128 + ((chunk ^ (rl & 7)) << 4) + within) = lo;
-          }
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&b_ready);
-      };
-
-      // ---- TMEM epilogue of one linear phase: row sums (hi + lo) -> fixed point -> RED into the output words.
-      //      `bias` (and x0 at layer 0) is added by the contributor that owns k-atom 0 of the tile. ----
-      auto epilogue = [&](int a0, int a1, int KA, int Nrows, u64* dst, long long dst_ld, const float* bias, bool add_x0) {
-        if (a0 >= a1) return;
-        int tile = a0 / KA;
-        int at = a0;
-        while (at < a1) {
-          const int tend = min(a1, (tile + 1) * KA);
-          const bool desig = at == tile * KA;
-          const int n = tile * 128 + q_tm * 32 + lane;
-          float bv = 0.f, x0v[4] = {0.f, 0.f, 0.f, 0.f};
-          if (epi_warp && desig && n < Nrows) {
-            if (bias) bv = bias[n];
-            if (add_x0) {
-#pragma unroll
-              for (int rr = 0; rr < 4; ++rr) {
-                const int r = set_tm * 4 + rr;
-                if (r < B) x0v[rr] = a.pos[(long long)kv * d + n] +
-                                     __bfloat162float(reinterpret_cast<const bf16*>(a.embed)[(long long)s_tok[r] * d + n]);
-              }
-            }
-          }
-          const int buf = tctr & 1;
-          swait(&acc_full[buf], (uint32_t)((tctr >> 1) & 1), 20);     // every worker: the B slots are free again after this
-          if (epi_warp) {
-            tc_fence_after();
-            uint32_t v[8];
-            tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 16 + set_tm * 8), v);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            if (n < Nrows) {
-#pragma unroll
-              for (int rr = 0; rr < 4; ++rr) {
-                const int r = set_tm * 4 + rr;
-                if (r < B) {
-                  float val = __uint_as_float(v[2 * rr]) + __uint_as_float(v[2 * rr + 1]);
-                  if (desig) val += bv + x0v[rr];
-                  red_add(dst + (long long)r * dst_ld + n, enc_fix(val, kFixScale));
-                }
-              }
-            }
-          }
-          ++tctr; at = tend; ++tile;
-        }
-      };
-
-      // ---- attention of my (utterance, head) tasks of layer l.  kind 0: self (resident cache rows [0, kv) off the
-      //      ring + the new position from the exchange), kind 1: cross (T rows off the ring) ----
-      auto attention = [&](int kind, int l) {
-        u64* lay = set + xreg + (long long)l * sa.layer_words;
-        const StreamLayer& slr = sa.sl[l];
-        const int nvalid = kind ? T : kv;
-        const int nb = (nvalid + 127) >> 7;
-        for (int t = first_task(l, kind, sa.task_inv); t < ntask; t += G) {
-          const int b = t / H, h = t - b * H;
-          if (wt < (kind ? 64 : 192)) {
-            const int which = wt >> 6, dd = wt & 63;
-            const int n = which * d + h * 64 + dd;
-            const u64* p = lay + (kind ? (long long)NRT * 4 * d + (long long)b * d : (long long)b * 3 * d) + n;
-            const u64* stp = lay + (long long)NRT * (6 * d + ffn) + ((kind ? 1 : 0) * NRT + b) * 2;
-            const unsigned ex = s_cnt[(l * 3 + kind) * sa.cnt_ld + (n >> 7)];
-            const float wsn = (kind ? slr.cq_ws : slr.qkv_ws)[n], bn = (kind ? slr.cq_b : slr.qkv_b)[n];
-            const u64 w0 = poll_w(stp, (unsigned)KAd, 30);
-            const u64 w1 = poll_w(stp + 1, (unsigned)KAd, 31);
-            const u64 wv = poll_w(p, ex, 32);
-            const double sm = (double)acc_raw(w0, KAd) * (1.0 / 16777216.0), sq = (double)acc_raw(w1, KAd) * (1.0 / 4096.0);
-            const double mu = sm / (double)d;
-            const float rstd = rsqrtf((float)fmax(sq / (double)d - mu * mu, 0.0) + a.eps);
-            const float val = fmaf(rstd, acc_val(wv, ex) - (float)mu * wsn, bn);
-            if (which == 0) {
-              s_qs[dd] = val;
-            } else {
-              const bf16 hb = __float2bfloat16_rn(val);
-              bf16* cache = reinterpret_cast<bf16*>(which == 1 ? a.kcache : a.vcache);
-              cache[((((long long)l * B + b) * H + h) * a.max_target + kv) * 64 + dd] = hb;     // append for the later tokens
-              s_knv[(which - 1) * 64 + dd] = __bfloat162float(hb);
-            }
-          }
-          wbar();
-          // warp ww takes rows [16 ww, 16 ww + 16) of every 128-row box; two lanes per row (32 dims each), the row's 16-byte
-          // chunks rotated by the row index so the quarter-warp phases of the 128-bit loads are conflict-free
-          const int rowl = lane >> 1, half = lane & 1;
-          float qh[32];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int cc = (c + rowl) & 3;
-            const float4 qa = *reinterpret_cast<const float4*>(s_qs + half * 32 + cc * 8);
-            const float4 qb = *reinterpret_cast<const float4*>(s_qs + half * 32 + cc * 8 + 4);
-            qh[c * 8 + 0] = qa.x; qh[c * 8 + 1] = qa.y; qh[c * 8 + 2] = qa.z; qh[c * 8 + 3] = qa.w;
-            qh[c * 8 + 4] = qb.x; qh[c * 8 + 5] = qb.y; qh[c * 8 + 6] = qb.z; qh[c * 8 + 7] = qb.w;
-          }
-          float m = -INFINITY, lsum = 0.f, o0 = 0.f, o1 = 0.f;
-          for (int i = 0; i < nb; ++i) {
-            swait(&full_bar[pos.stage], pos.phase, 33);
-            const bf16* kb = reinterpret_cast<const bf16*>(ring + (size_t)pos.stage * kStStage);
-            const int row = ww * 16 + rowl;
-            const bf16* kr = kb + row * 64 + half * 32;
-            float s = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int cc = (c + rowl) & 3;
-              const uint4 u = *reinterpret_cast<const uint4*>(kr + cc * 8);
-              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
-              float2 f = __bfloat1622float2(hh[0]); s = fmaf(f.x, qh[c * 8 + 0], s); s = fmaf(f.y, qh[c * 8 + 1], s);
-              f = __bfloat1622float2(hh[1]); s = fmaf(f.x, qh[c * 8 + 2], s); s = fmaf(f.y, qh[c * 8 + 3], s);
-              f = __bfloat1622float2(hh[2]); s = fmaf(f.x, qh[c * 8 + 4], s); s = fmaf(f.y, qh[c * 8 + 5], s);
-              f = __bfloat1622float2(hh[3]); s = fmaf(f.x, qh[c * 8 + 6], s); s = fmaf(f.y, qh[c * 8 + 7], s);
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (i * 128 + row >= nvalid) s = -INFINITY;
-            const float mnew = fmaxf(m, warp_max(s));
-            const float msafe = mnew == -INFINITY ? 0.f : mnew;
-            const float sc = __expf(m - msafe);
-            const float pr = __expf(s - msafe);
-            lsum = lsum * sc + warp_sum(half == 0 ? pr : 0.f);
-            o0 *= sc; o1 *= sc; m = mnew;
-            __syncwarp();
-            if (lane == 0) {
-              if (atomicAdd(&box_cnt[pos.stage], 1) == kStWorkerWarps - 1) { box_cnt[pos.stage] = 0; mbar_arrive(&empty_bar[pos.stage]); }
-            }
-            ring_adv(pos, 1, NS);
-            swait(&full_bar[pos.stage], pos.phase, 34);
-            const bf16* vb = reinterpret_cast<const bf16*>(ring + (size_t)pos.stage * kStStage) + (ww * 16) * 64 + 2 * lane;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float pj = __shfl_sync(0xffffffffu, pr, 2 * j);
-              const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + j * 64));
-              o0 = fmaf(pj, v.x, o0); o1 = fmaf(pj, v.y, o1);
-            }
-            __syncwarp();
-            if (lane == 0) {
-              if (atomicAdd(&box_cnt[pos.stage], 1) == kStWorkerWarps - 1) { box_cnt[pos.stage] = 0; mbar_arrive(&empty_bar[pos.stage]); }
-            }
-            ring_adv(pos, 1, NS);
-          }
-          float* pw = s_part + ww * kStPartLd;
-          if (lane == 0) { pw[0] = m; pw[1] = lsum; }
-          pw[4 + 2 * lane] = o0; pw[5 + 2 * lane] = o1;
-          if (kind == 0 && ww == 0) {                      // score of the new position
-            const float sn = warp_sum(fmaf(s_knv[lane], s_qs[lane], s_knv[lane + 32] * s_qs[lane + 32]));
-            if (lane == 0) s_part[kStWorkerWarps * kStPartLd] = sn;
-          }
-          wbar();
-          if (wt < 64) {
-            const float s_new = kind == 0 ? s_part[kStWorkerWarps * kStPartLd] : -INFINITY;
-            float M = s_new;
-#pragma unroll
-            for (int w = 0; w < kStWorkerWarps; ++w) M = fmaxf(M, s_part[w * kStPartLd]);
-            float Lt = 0.f, o = 0.f;
-#pragma unroll
-            for (int w = 0; w < kStWorkerWarps; ++w) {
-              const float e = __expf(s_part[w * kStPartLd] - M);
-              Lt = fmaf(e, s_part[w * kStPartLd + 1], Lt);
-              o = fmaf(e, s_part[w * kStPartLd + 4 + wt], o);
-            }
-            if (kind == 0) { const float e = __expf(s_new - M); Lt += e; o = fmaf(e, s_knv[64 + wt], o); }
-            u64* dst = lay + (long long)NRT * (kind ? 5 : 3) * d + (long long)b * d + h * 64 + wt;
-            st_w(dst, enc_fix(o / Lt, kFixScale));
-          }
-          if (kind == 0) asm volatile("fence.proxy.async;" ::: "memory");   // appended cache rows -> visible to later TMA reads
-          wbar();
-        }
-        if (kind == 0 && wt == 0) s_prog = it * L + l + 1;
-      };
-
-      // =====================================================================
-      // one call site per phase body: the phases run one after the other, so every inlined copy would be a separate,
-      // cold stretch of the instruction stream
-      const int n_idx = 8 * L + (head_on ? 1 : 0);
-      const int2 rh = s_sched[6 * L];
       u64* hstats = xw + (long long)NRT * d;
+
+      const int n_idx = 8 * L + (head_on ? 1 : 0);
+#pragma unroll 1
       for (int idx = 0; idx < n_idx; ++idx) {
         const int l = idx >> 3, ph = idx & 7;
         const bool is_head = idx == 8 * L;
         u64* lay = set + xreg + (long long)(is_head ? 0 : l) * sa.layer_words;
-        if (!is_head && ph == 1) {
-          // zero this CTA's share of the other set's layer-l words (and, at layer 0, of its residual-stream words)
-          {
+        u64* stats = lay + (long long)NRT * (6 * d + ffn);
+        const StreamLayer& slr = sa.sl[is_head ? 0 : l];
+
+        if (!is_head && (ph == 1 || ph == 4)) {
+          // =================================================================
+          // attention of my (utterance, head) tasks of layer l.  ph 1: self (resident cache rows [0, kv) off the ring + the
+          // new position from the exchange), ph 4: cross (T rows off the ring)
+          // =================================================================
+          const int kind = ph == 4;
+          if (!kind) {
+            // zero this CTA's share of the other set's layer-l words (and, at layer 0, of its residual-stream words)
             const long long ngran = sa.layer_words >> 1;
             const long long g0 = ngran * blockIdx.x / G, g1 = ngran * (blockIdx.x + 1) / G;
             u64* zb = oset + xreg + (long long)l * sa.layer_words;
@@ -701,65 +423,329 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               for (long long i = x0 + wt; i < x1; i += kStWorkers) st_zero2(oset + 2 * i);
             }
           }
-          attention(0, l);
-        } else if (!is_head && ph == 4) {
-          attention(1, l);
+          const int nvalid = kind ? T : kv;
+          const int nb = (nvalid + 127) >> 7;
+#pragma unroll 1
+          for (int t = first_task(l, kind, sa.task_inv); t < ntask; t += G) {
+            const int b = t / H, h = t - b * H;
+            if (wt < (kind ? 64 : 192)) {
+              const int which = wt >> 6, dd = wt & 63;
+              const int n = which * d + h * 64 + dd;
+              const u64* p = lay + (kind ? (long long)NRT * 4 * d + (long long)b * d : (long long)b * 3 * d) + n;
+              const u64* stp = stats + (kind * NRT + b) * 2;
+              const unsigned ex = s_cnt[(l * 3 + kind) * sa.cnt_ld + (n >> 7)];
+              const float wsn = (kind ? slr.cq_ws : slr.qkv_ws)[n], bn = (kind ? slr.cq_b : slr.qkv_b)[n];
+              u64 w0, w1, wv;
+              long long t0 = 0;
+              for (;;) {
+                ld_w2(stp, w0, w1);
+                wv = ld_w(p);
+                if (acc_cnt(w0) == (unsigned)KAd && acc_cnt(w1) == (unsigned)KAd && acc_cnt(wv) == ex) break;
+                if (t0 == 0) t0 = clock64();
+                else if (clock64() - t0 > kStSpin) st_timeout(30, (int)acc_cnt(w0), (int)acc_cnt(wv));
+              }
+              const float2 ms = ln_stats(w0, w1, (unsigned)KAd, inv_d, a.eps);
+              const float val = fmaf(ms.y, acc_val(wv, ex) - ms.x * wsn, bn);
+              if (which == 0) {
+                s_qs[dd] = val;
+              } else {
+                const bf16 hb = __float2bfloat16_rn(val);
+                bf16* cache = reinterpret_cast<bf16*>(which == 1 ? a.kcache : a.vcache);
+                cache[((((long long)l * B + b) * H + h) * a.max_target + kv) * 64 + dd] = hb;     // append for the later tokens
+                s_knv[(which - 1) * 64 + dd] = __bfloat162float(hb);
+              }
+            }
+            wbar();
+            // warp ww takes rows [16 ww, 16 ww + 16) of every 128-row box; two lanes per row (32 dims each), the row's 16-byte
+            // chunks rotated by the row index so the quarter-warp phases of the 128-bit loads are conflict-free
+            const int rowl = lane >> 1, half = lane & 1;
+            float qh[32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int cc = (c + rowl) & 3;
+              const float4 qa = *reinterpret_cast<const float4*>(s_qs + half * 32 + cc * 8);
+              const float4 qb = *reinterpret_cast<const float4*>(s_qs + half * 32 + cc * 8 + 4);
+              qh[c * 8 + 0] = qa.x; qh[c * 8 + 1] = qa.y; qh[c * 8 + 2] = qa.z; qh[c * 8 + 3] = qa.w;
+              qh[c * 8 + 4] = qb.x; qh[c * 8 + 5] = qb.y; qh[c * 8 + 6] = qb.z; qh[c * 8 + 7] = qb.w;
+            }
+            float m = -INFINITY, lsum = 0.f, o0 = 0.f, o1 = 0.f;
+            const int row = ww * 16 + rowl;
+#pragma unroll 1
+            for (int i = 0; i < nb; ++i) {
+              swait(&full_bar[pos.stage], pos.phase, 33);
+              const bf16* kr = reinterpret_cast<const bf16*>(ring + (size_t)pos.stage * kStStage) + row * 64 + half * 32;
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int cc = (c + rowl) & 3;
+                const uint4 u = *reinterpret_cast<const uint4*>(kr + cc * 8);
+                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+                float2 f = __bfloat1622float2(hh[0]); s0 = fmaf(f.x, qh[c * 8 + 0], s0); s1 = fmaf(f.y, qh[c * 8 + 1], s1);
+                f = __bfloat1622float2(hh[1]); s0 = fmaf(f.x, qh[c * 8 + 2], s0); s1 = fmaf(f.y, qh[c * 8 + 3], s1);
+                f = __bfloat1622float2(hh[2]); s0 = fmaf(f.x, qh[c * 8 + 4], s0); s1 = fmaf(f.y, qh[c * 8 + 5], s1);
+                f = __bfloat1622float2(hh[3]); s0 = fmaf(f.x, qh[c * 8 + 6], s0); s1 = fmaf(f.y, qh[c * 8 + 7], s1);
+              }
+              float s = s0 + s1;
+              s += __shfl_xor_sync(0xffffffffu, s, 1);
+              if (i * 128 + row >= nvalid) s = -INFINITY;
+              const float mnew = fmaxf(m, warp_max(s));
+              const float msafe = mnew == -INFINITY ? 0.f : mnew;
+              const float sc = __expf(m - msafe);
+              const float pr = __expf(s - msafe);
+              lsum = lsum * sc + warp_sum(half == 0 ? pr : 0.f);
+              o0 *= sc; o1 *= sc; m = mnew;
+              __syncwarp();
+              if (lane == 0 && atomicAdd(&box_cnt[pos.stage], 1) == kStWorkerWarps - 1) { box_cnt[pos.stage] = 0; mbar_arrive(&empty_bar[pos.stage]); }
+              ring_adv(pos, 1, NS);
+              swait(&full_bar[pos.stage], pos.phase, 34);
+              const bf16* vb = reinterpret_cast<const bf16*>(ring + (size_t)pos.stage * kStStage) + (ww * 16) * 64 + 2 * lane;
+#pragma unroll 4
+              for (int j = 0; j < 16; ++j) {
+                const float pj = __shfl_sync(0xffffffffu, pr, 2 * j);
+                const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + j * 64));
+                o0 = fmaf(pj, v.x, o0); o1 = fmaf(pj, v.y, o1);
+              }
+              __syncwarp();
+              if (lane == 0 && atomicAdd(&box_cnt[pos.stage], 1) == kStWorkerWarps - 1) { box_cnt[pos.stage] = 0; mbar_arrive(&empty_bar[pos.stage]); }
+              ring_adv(pos, 1, NS);
+            }
+            float* pw = s_part + ww * kStPartLd;
+            if (lane == 0) { pw[0] = m; pw[1] = lsum; }
+            pw[4 + 2 * lane] = o0; pw[5 + 2 * lane] = o1;
+            if (kind == 0 && ww == 0) {                      // score of the new position
+              const float sn = warp_sum(fmaf(s_knv[lane], s_qs[lane], s_knv[lane + 32] * s_qs[lane + 32]));
+              if (lane == 0) s_part[kStWorkerWarps * kStPartLd] = sn;
+            }
+            wbar();
+            if (wt < 64) {
+              const float s_new = kind == 0 ? s_part[kStWorkerWarps * kStPartLd] : -INFINITY;
+              float M = s_new;
+#pragma unroll
+              for (int w = 0; w < kStWorkerWarps; ++w) M = fmaxf(M, s_part[w * kStPartLd]);
+              float Lt = 0.f, o = 0.f;
+#pragma unroll
+              for (int w = 0; w < kStWorkerWarps; ++w) {
+                const float e = __expf(s_part[w * kStPartLd] - M);
+                Lt = fmaf(e, s_part[w * kStPartLd + 1], Lt);
+                o = fmaf(e, s_part[w * kStPartLd + 4 + wt], o);
+              }
+              if (kind == 0) { const float e = __expf(s_new - M); Lt += e; o = fmaf(e, s_knv[64 + wt], o); }
+              u64* dst = lay + (long long)NRT * (kind ? 5 : 3) * d + (long long)b * d + h * 64 + wt;
+              st_w(dst, enc_fix(o / Lt, kFixScale));
+            }
+            if (kind == 0) asm volatile("fence.proxy.async;" ::: "memory");   // appended cache rows -> visible to later TMA reads
+            wbar();
+          }
+          if (kind == 0 && wt == 0) s_prog = it * L + l + 1;
+          stamp();
+          continue;
+        }
+
+        // ===================================================================
+        // linear phase (or the head): stage the B operand, then reduce the accumulator tiles into the output words
+        // ===================================================================
+        const int p6 = phase_p6(ph);
+        const int4 r = s_sched[is_head ? 6 * L : l * 6 + p6];
+        // mode 0: x0 = embedding + position (layer 0 qkv), 1: residual words, 2: attention context words,
+        //      3: fc1 words -> LN fold + GELU, 4: residual words x gamma (head)
+        int KA = KAd, mode, exp_row = 0, Nrows = d;
+        const u64* src = xw; long long src_ld = d;
+        u64* stat_out = nullptr; const u64* stat_in = nullptr;
+        const float* fold_ws = nullptr; const float* fold_b = nullptr;
+        u64* dst = xw; long long dst_ld = d; const float* bias = nullptr; bool add_x0 = false;
+        if (is_head) {
+          mode = 4; exp_row = (L - 1) * 3 + 2; stat_out = hstats; fold_ws = a.ln_g;
+          if (wt == 0) {
+            // sliding-window penalty ids (APPLY_PENALTY, Export_Whisper.py:318-331): active once generated >= penalty_range
+            int nmax = 0;
+            if (a.penalty_value != 1.0f && !begin_on) {
+              for (int b = 0; b < B; ++b) {
+                const bool act = s_ngen[b] >= a.penalty_range;
+                const int ns = s_nsave[b];
+                const int first = max(0, ns - a.penalty_range);
+                int cntp = 0;
+                if (act) for (int j = first; j < ns && cntp < 32; ++j) s_pen[b * 32 + cntp++] = s_hist[b * 32 + (j & 31)];
+                for (int j = cntp; j < 32; ++j) s_pen[b * 32 + j] = -1;
+                nmax = max(nmax, cntp);
+              }
+            }
+            s_pen_n = nmax;
+          }
+        } else if (p6 == 0) {
+          mode = l == 0 ? 0 : 1; exp_row = l > 0 ? (l - 1) * 3 + 2 : 0; stat_out = stats;
+          Nrows = 3 * d; dst = lay; dst_ld = 3 * d;
+        } else if (p6 == 1) {
+          mode = 2; src = lay + (long long)NRT * 3 * d; bias = slr.out_b; add_x0 = l == 0;
+        } else if (p6 == 2) {
+          mode = 1; exp_row = l * 3; stat_out = stats + 2 * NRT; dst = lay + (long long)NRT * 4 * d;
+        } else if (p6 == 3) {
+          mode = 2; src = lay + (long long)NRT * 5 * d; bias = slr.cout_b;
+        } else if (p6 == 4) {
+          mode = 1; exp_row = l * 3 + 1; stat_out = stats + 4 * NRT; Nrows = ffn; dst = lay + (long long)NRT * 6 * d; dst_ld = ffn;
         } else {
-          u64* stats = lay + (long long)NRT * (6 * d + ffn);
-          const StreamLayer& slr = sa.sl[is_head ? 0 : l];
-          const int p6 = ph == 0 ? 0 : (ph == 2 ? 1 : (ph == 3 ? 2 : ph - 2));
-          int2 r = s_sched[is_head ? 6 * L : l * 6 + p6];
-          int KA = KAd, mode, exp_row = 0, Nrows = d;
-          const u64* src = xw; long long src_ld = d;
-          u64* stat_out = nullptr; const u64* stat_in = nullptr;
-          const float* fold_ws = nullptr; const float* fold_b = nullptr;
-          u64* dst = xw; long long dst_ld = d; const float* bias = nullptr; bool add_x0 = false;
-          if (is_head) {
-            r.x *= KAd; r.y *= KAd; mode = 4; exp_row = (L - 1) * 3 + 2; stat_out = hstats; fold_ws = a.ln_g;
-            if (wt == 0) {
-              // sliding-window penalty ids (APPLY_PENALTY, Export_Whisper.py:318-331): active once generated >= penalty_range
-              int nmax = 0;
-              if (a.penalty_value != 1.0f && !begin_on) {
-                for (int b = 0; b < B; ++b) {
-                  const bool act = s_ngen[b] >= a.penalty_range;
-                  const int ns = s_nsave[b];
-                  const int first = max(0, ns - a.penalty_range);
-                  int cntp = 0;
-                  if (act) for (int j = first; j < ns && cntp < 32; ++j) s_pen[b * 32 + cntp++] = s_hist[b * 32 + (j & 31)];
-                  for (int j = cntp; j < 32; ++j) s_pen[b * 32 + j] = -1;
-                  nmax = max(nmax, cntp);
+          KA = ffn >> 6; mode = 3; src = lay + (long long)NRT * 6 * d; src_ld = ffn; exp_row = l * 3 + 2; stat_in = stats + 4 * NRT;
+          fold_ws = slr.fc1_ws; fold_b = slr.fc1_b; bias = slr.fc2_b;
+        }
+
+        // ---- B-operand staging ----
+        {
+          const int nat = r.y - r.x;
+          const int nslot = nat < KA ? nat : KA;
+          const int ka0 = r.w;
+          // LayerNorm statistics: the k-atoms of tile 0 (head: the k-atoms whose index is one of my vocabulary tiles) are
+          // reduced by whoever stages them -- exactly one contributor per atom, d / 64 contributions per word
+          const int st_n = (stat_out && mode != 4 && r.z == 0) ? min(nat, KA - r.x) : 0;     // my slots [0, st_n) are tile-0 atoms
+          const int ht0 = r.z, ht1 = mode == 4 ? r.z + nat / KA : 0;                          // head: my vocabulary tiles
+          float mean = 0.f, rstd = 1.f;
+          bool need_stats = mode == 3 && row_ok && g_mine < nslot;
+          const u64* srow = src + (long long)r_mine * src_ld;
+          float ssum = 0.f, ssq = 0.f;
+          unsigned nstat = 0;
+#pragma unroll 1
+          for (int s0 = g_mine; s0 < nslot && row_ok; s0 += U * NG) {
+            u64 w[U][2];
+            int kk[U];
+            unsigned ex[U];
+            float2 pa[U], pb[U];                              // per-unit parameters, requested before the poll
+            unsigned pend = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int s = s0 + u * NG;
+              kk[u] = 0; ex[u] = 0; pa[u] = make_float2(0.f, 0.f); pb[u] = make_float2(0.f, 0.f);
+              if (s < nslot) {
+                int ka = ka0 + s; if (ka >= KA) ka -= KA;
+                kk[u] = ka * 64 + 2 * lane;
+                if (mode == 1 || mode == 4) ex[u] = s_xexp[exp_row * sa.xt + (kk[u] >> 7)];
+                else if (mode == 3) ex[u] = s_cnt[exp_row * sa.cnt_ld + (kk[u] >> 7)];
+                else ex[u] = 1;
+                pend |= 1u << u;
+                if (mode == 0) {
+                  pa[u] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
+                      reinterpret_cast<const bf16*>(a.embed) + (long long)s_tok[r_mine] * d + kk[u]));
+                  pb[u] = *reinterpret_cast<const float2*>(a.pos + (long long)kv * d + kk[u]);
+                } else if (mode >= 3) {
+                  pa[u] = *reinterpret_cast<const float2*>(fold_ws + kk[u]);
+                  if (mode == 3) pb[u] = *reinterpret_cast<const float2*>(fold_b + kk[u]);
                 }
               }
-              s_pen_n = nmax;
             }
-          } else if (p6 == 0) {
-            mode = l == 0 ? 0 : 1; exp_row = l > 0 ? (l - 1) * 3 + 2 : 0; stat_out = stats;
-            Nrows = 3 * d; dst = lay; dst_ld = 3 * d;
-          } else if (p6 == 1) {
-            mode = 2; src = lay + (long long)NRT * 3 * d; bias = slr.out_b; add_x0 = l == 0;
-          } else if (p6 == 2) {
-            mode = 1; exp_row = l * 3; stat_out = stats + 2 * NRT; dst = lay + (long long)NRT * 4 * d;
-          } else if (p6 == 3) {
-            mode = 2; src = lay + (long long)NRT * 5 * d; bias = slr.cout_b;
-          } else if (p6 == 4) {
-            mode = 1; exp_row = l * 3 + 1; stat_out = stats + 4 * NRT; Nrows = ffn; dst = lay + (long long)NRT * 6 * d; dst_ld = ffn;
-          } else {
-            KA = ffn >> 6; mode = 3; src = lay + (long long)NRT * 6 * d; src_ld = ffn; exp_row = l * 3 + 2; stat_in = stats + 4 * NRT;
-            fold_ws = slr.fc1_ws; fold_b = slr.fc1_b; bias = slr.fc2_b;
+            if (mode != 0) {
+              unsigned todo = pend | (need_stats ? 16u : 0u);
+              u64 sw0 = 0, sw1 = 0;
+              long long t0 = 0;
+              while (todo) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (todo & (1u << u)) ld_w2(srow + kk[u], w[u][0], w[u][1]);
+                if (todo & 16u) ld_w2(stat_in + r_mine * 2, sw0, sw1);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                  if ((todo & (1u << u)) && acc_cnt(w[u][0]) == ex[u] && acc_cnt(w[u][1]) == ex[u]) todo &= ~(1u << u);
+                if ((todo & 16u) && acc_cnt(sw0) == (unsigned)KAd && acc_cnt(sw1) == (unsigned)KAd) todo &= ~16u;
+                if (todo) {
+                  if (t0 == 0) t0 = clock64();
+                  else if (clock64() - t0 > kStSpin) st_timeout(12 + mode, kk[0], (int)todo);
+                }
+              }
+              if (need_stats) {
+                need_stats = false;
+                const float2 ms = ln_stats(sw0, sw1, (unsigned)KAd, inv_d, a.eps);
+                mean = ms.x; rstd = ms.y;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (!(pend & (1u << u))) continue;
+              const int s = s0 + u * NG;
+              float f0, f1;
+              if (mode == 0) {
+                f0 = pb[u].x + pa[u].x; f1 = pb[u].y + pa[u].y;
+              } else {
+                f0 = acc_val(w[u][0], ex[u]); f1 = acc_val(w[u][1], ex[u]);
+              }
+              const int ka = kk[u] >> 6;
+              if (s < st_n || (mode == 4 && ka >= ht0 && ka < ht1)) { ssum += f0 + f1; ssq += fmaf(f0, f0, f1 * f1); nstat += 1; }
+              if (mode == 3) {
+                const float2 g2 = gelu2(fmaf(rstd, f0 - mean * pa[u].x, pb[u].x), fmaf(rstd, f1 - mean * pa[u].y, pb[u].y));
+                f0 = g2.x; f1 = g2.y;
+              } else if (mode == 4) {
+                f0 *= pa[u].x; f1 *= pa[u].y;
+              }
+              // x = hi + lo, both bf16: rows 2r (hi) and 2r + 1 (lo) of the slot's 16-row K-major SWIZZLE_128B tile
+              const __nv_bfloat162 hi = __floats2bfloat162_rn(f0, f1);
+              const float2 hf = __bfloat1622float2(hi);
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(f0 - hf.x, f1 - hf.y);
+              uint8_t* slotp = bbuf + (size_t)s * kStSlot;
+              const int rh = 2 * r_mine, rl = rh + 1;
+              const int chunk = lane >> 2, within = (lane & 3) * 4;
+              *reinterpret_cast<__nv_bfloat162*>(slotp + (rh >> 3) * 1024 + (rh & 7) * 128 + ((chunk ^ (rh & 7)) << 4) + within) = hi;
+              *reinterpret_cast<__nv_bfloat162*>(slotp + (rl >> 3) * 1024 + (rl & 7) * 128 + ((chunk ^ (rl & 7)) << 4) + within) = lo;
+            }
           }
-          prep(mode, r.x, r.y, KA, src, src_ld, exp_row, stat_out, stat_in, fold_ws, fold_b);
-          if (!is_head) {
-            epilogue(r.x, r.y, KA, Nrows, dst, dst_ld, bias, add_x0);
-            ring_adv(pos, r.y - r.x, NS);
+          fence_proxy_async_smem();
+          mbar_arrive(&b_ready);
+          // statistics after the MMA has been released: the readers need them one phase later.  One RED pair per warp,
+          // counting the k-atoms it covers (nstat is warp-uniform)
+          if (nstat) {
+            const float sv = warp_sum(ssum), qv = warp_sum(ssq);
+            if (lane == 0) red_add(stat_out + r_mine * 2, enc_fix(sv, kFixScale, nstat));
+            if (lane == 1) red_add(stat_out + r_mine * 2 + 1, enc_fix(qv, kSqScale, nstat));
           }
         }
-        if (!is_head) stamp();
+
+        if (!is_head) {
+          // ---- TMEM epilogue: row sums (hi + lo) -> fixed point -> RED into the output words.  `bias` (and x0 at layer 0) is
+          //      added by the contributor that owns k-atom 0 of the tile. ----
+          int tile = r.z, at = r.x;
+#pragma unroll 1
+          while (at < r.y) {
+            const int tend = min(r.y, at + KA - (at == r.x ? r.w : 0));
+            const bool desig = at != r.x || r.w == 0;
+            const int n = tile * 128 + q_tm * 32 + lane;
+            float bv = 0.f, x0v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (epi_warp && desig && n < Nrows) {
+              if (bias) bv = bias[n];
+              if (add_x0) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                  const int rq = set_tm * 4 + rr;
+                  if (rq < B) x0v[rr] = a.pos[(long long)kv * d + n] +
+                                        __bfloat162float(reinterpret_cast<const bf16*>(a.embed)[(long long)s_tok[rq] * d + n]);
+                }
+              }
+            }
+            const int buf = tctr & 1;
+            swait(&acc_full[buf], (uint32_t)((tctr >> 1) & 1), 20);     // every worker: the B slots are free again after this
+            if (epi_warp) {
+              tc_fence_after();
+              float v[8];
+              tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 16 + set_tm * 8), v);
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&acc_empty[buf]);
+              if (n < Nrows) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                  const int rq = set_tm * 4 + rr;
+                  if (rq < B) {
+                    float val = v[2 * rr] + v[2 * rr + 1];
+                    if (desig) val += bv + x0v[rr];
+                    red_add(dst + (long long)rq * dst_ld + n, enc_fix(val, kFixScale));
+                  }
+                }
+              }
+            }
+            ++tctr; at = tend; ++tile;
+          }
+          ring_adv(pos, r.y - r.x, NS);
+          stamp();
+        }
       }
 
-      // ---- tied lm head: whole 128-row vocabulary tiles per CTA; final LayerNorm folded around the GEMM ----
+      // ---- tied lm head epilogue: whole 128-row vocabulary tiles per CTA; final LayerNorm folded around the GEMM ----
       float cv = -INFINITY; int ci = 0x7fffffff;              // this thread's candidate (threads wt < NRT publish)
       if (head_on) {
-        const int2 r = rh;
+        const int4 r = s_sched[6 * L];
+        const int t_end = r.z + (r.y - r.x) / KAd;
         wbar();                                             // s_pen / s_pen_n visible
         const bool pen_on = s_pen_n > 0;
         float mean[4], rstd[4], bvv[4]; int bii[4];
@@ -770,16 +756,21 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           for (int rr = 0; rr < 4; ++rr) {
             const int rq = set_tm * 4 + rr;
             if (rq < B) {
-              const u64 w0 = poll_w(hstats + rq * 2, (unsigned)KAd, 40);
-              const u64 w1 = poll_w(hstats + rq * 2 + 1, (unsigned)KAd, 41);
-              const double sm = (double)acc_raw(w0, KAd) * (1.0 / 16777216.0), sq = (double)acc_raw(w1, KAd) * (1.0 / 4096.0);
-              const double mu = sm / (double)d;
-              mean[rr] = (float)mu;
-              rstd[rr] = rsqrtf((float)fmax(sq / (double)d - mu * mu, 0.0) + a.eps);
+              u64 w0, w1;
+              long long t0 = 0;
+              for (;;) {
+                ld_w2(hstats + rq * 2, w0, w1);
+                if (acc_cnt(w0) == (unsigned)KAd && acc_cnt(w1) == (unsigned)KAd) break;
+                if (t0 == 0) t0 = clock64();
+                else if (clock64() - t0 > kStSpin) st_timeout(40, (int)acc_cnt(w0), (int)acc_cnt(w1));
+              }
+              const float2 ms = ln_stats(w0, w1, (unsigned)KAd, inv_d, a.eps);
+              mean[rr] = ms.x; rstd[rr] = ms.y;
             }
           }
         }
-        for (int tile = r.x; tile < r.y; ++tile) {
+#pragma unroll 1
+        for (int tile = r.z; tile < t_end; ++tile) {
           const int n = tile * 128 + q_tm * 32 + lane;
           float gn = 0.f, btn = 0.f, bg = 0.f;
           if (epi_warp && n < a.vocab) {
@@ -790,7 +781,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           swait(&acc_full[buf], (uint32_t)((tctr >> 1) & 1), 42);
           if (epi_warp) {
             tc_fence_after();
-            uint32_t v[8];
+            float v[8];
             tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 16 + set_tm * 8), v);
             tc_fence_before();
             __syncwarp();
@@ -800,7 +791,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               for (int rr = 0; rr < 4; ++rr) {
                 const int rq = set_tm * 4 + rr;
                 if (rq < B) {
-                  float val = fmaf(rstd[rr], (__uint_as_float(v[2 * rr]) + __uint_as_float(v[2 * rr + 1])) - mean[rr] * gn, btn);
+                  float val = fmaf(rstd[rr], (v[2 * rr] + v[2 * rr + 1]) - mean[rr] * gn, btn);
                   if (pen_on) {
                     bool hit = false;
                     for (int qq = 0; qq < s_pen_n; ++qq) hit |= (s_pen[rq * 32 + qq] == n);
@@ -815,7 +806,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           }
           ++tctr;
         }
-        ring_adv(pos, (r.y - r.x) * KAd, NS);
+        ring_adv(pos, r.y - r.x, NS);
         if (epi_warp) {
 #pragma unroll
           for (int rr = 0; rr < 4; ++rr) {
@@ -830,19 +821,15 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             if (lane == 0 && rq < NRT) { s_best[(ww * NRT + rq) * 2] = bv; s_best[(ww * NRT + rq) * 2 + 1] = __int_as_float(bi); }
           }
         }
-        __threadfence();                                   // the zero stores of this step before the candidate goes out
-        asm volatile("fence.proxy.async;" ::: "memory");  // cache rows appended this step, read by TMA in the next one
-        wbar();
-        if (wt < NRT) {
-          for (int w = (wt >> 2) * 4; w < (wt >> 2) * 4 + 4; ++w) {
-            const float v = s_best[(w * NRT + wt) * 2]; const int i = __float_as_int(s_best[(w * NRT + wt) * 2 + 1]);
-            if (v > cv || (v == cv && i < ci)) { cv = v; ci = i; }
-          }
+      }
+      __threadfence();                                     // the zero stores of this step before the candidate goes out
+      asm volatile("fence.proxy.async;" ::: "memory");    // cache rows appended this step, read by TMA in the next one
+      wbar();
+      if (head_on && wt < NRT) {
+        for (int w = (wt >> 2) * 4; w < (wt >> 2) * 4 + 4; ++w) {
+          const float v = s_best[(w * NRT + wt) * 2]; const int i = __float_as_int(s_best[(w * NRT + wt) * 2 + 1]);
+          if (v > cv || (v == cv && i < ci)) { cv = v; ci = i; }
         }
-      } else {
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        wbar();
       }
       stamp();
 
@@ -856,24 +843,17 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           st_w(cbuf + (size_t)(blockIdx.x * NRT + wt) * 2 + 1, ((u64)seq << 32) | (u64)(unsigned)ci);
         }
         const int nw = G * NRT * 2;
-        for (int i0 = wt; i0 < nw; i0 += kStWorkers * 4) {
-          u64 v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) { const int i = i0 + u * kStWorkers; if (i < nw) v[u] = ld_w(cbuf + i); }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * kStWorkers;
-            if (i < nw) {
-              if ((unsigned)(v[u] >> 32) != seq) {
-                const long long t0 = clock64();
-                do {
-                  v[u] = ld_w(cbuf + i);
-                  if (clock64() - t0 > kStSpin) st_timeout(50, i, (int)(v[u] >> 32));
-                } while ((unsigned)(v[u] >> 32) != seq);
-              }
-              s_cand[i] = __uint_as_float((unsigned)v[u]);
-            }
+#pragma unroll 1
+        for (int i = wt; i < nw; i += kStWorkers) {
+          u64 v = ld_w(cbuf + i);
+          if ((unsigned)(v >> 32) != seq) {
+            const long long t0 = clock64();
+            do {
+              v = ld_w(cbuf + i);
+              if (clock64() - t0 > kStSpin) st_timeout(50, i, (int)(v >> 32));
+            } while ((unsigned)(v >> 32) != seq);
           }
+          s_cand[i] = __uint_as_float((unsigned)v);
         }
         __threadfence();
         wbar();
@@ -922,7 +902,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
       ++it_done;
       stamp();
     }
-    // ---- wind down: release the MMA issuer if it is still waiting for a step, stop the producer ----
+    // ---- wind down: stop the producer, write the loop state back ----
     wbar();
     if (wt == 0) s_stop = 1;
     if (blockIdx.x == 0 && wt < B) {
@@ -969,7 +949,7 @@ cudaError_t launch_rowdot_bf16(const void* W, const float* vec, float* out, int 
 static int stream_nrt(int batch) { return batch <= 1 ? 1 : (batch <= 2 ? 2 : (batch <= 4 ? 4 : 8)); }
 
 bool stream_supported(int batch, int d, int ffn, int n_heads, int vocab, int T, int num_sms) {
-  return batch >= 1 && batch <= kStreamMaxBatch && d % 64 == 0 && ffn % 64 == 0 && d == n_heads * 64 && vocab >= 1 && T >= 1 &&
+  return batch >= 1 && batch <= kStreamMaxBatch && d % 64 == 0 && ffn % 64 == 0 && d == n_heads * 64 && vocab >= 2 * d && T >= 1 &&
          num_sms >= 8 && num_sms % kRingTaskMul != 0;
 }
 
@@ -986,7 +966,7 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
   const int rowsN[6] = {3 * d, d, d, d, ffn, d};
   const int kas[6] = {KAd, KAd, KAd, KAd, KAd, KAf};
   const int n_sched = 6 * L + 1;
-  std::vector<int2> sched((size_t)G * n_sched);
+  std::vector<int4> sched((size_t)G * n_sched);
   const int cnt_ld = std::max(tiles(3 * d), tiles(ffn)), xt = tiles(d);
   std::vector<unsigned char> cnt((size_t)L * 3 * cnt_ld, 0);
   std::vector<unsigned short> xexp((size_t)L * 3 * xt, 0);
@@ -995,7 +975,7 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
   std::vector<int> xcum(xt, 0);
   int max_slots = 1;
   int rot = 0;
-  auto deal = [&](int A, int unit, int col, std::vector<int>& n_of) {
+  auto deal = [&](int A, int unit, int col, int KA, std::vector<int>& n_of) {
     // n_of[c] = units for CTA c; the `rem` least-loaded CTAs (ties: rotating start) take one more
     const int q = A / G, rem = A % G;
     for (int c = 0; c < G; ++c) { order[c] = (c + rot) % G; n_of[c] = q; }
@@ -1004,7 +984,7 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
     for (int i = 0; i < rem; ++i) n_of[order[i]] += 1;
     int start = 0;
     for (int c = 0; c < G; ++c) {
-      sched[(size_t)c * n_sched + col] = make_int2(start, start + n_of[c]);
+      sched[(size_t)c * n_sched + col] = make_int4(start, start + n_of[c], start / KA, start % KA);
       start += n_of[c];
       load[c] += (long long)n_of[c] * unit;
     }
@@ -1013,10 +993,10 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
   for (int l = 0; l < L; ++l) {
     for (int p6 = 0; p6 < 6; ++p6) {
       const int KA = kas[p6], nt = tiles(rowsN[p6]);
-      deal(nt * KA, 1, l * 6 + p6, n_of);
+      deal(nt * KA, 1, l * 6 + p6, KA, n_of);
       std::vector<int> c_of(nt, 0);
       for (int c = 0; c < G; ++c) {
-        const int2 r = sched[(size_t)c * n_sched + l * 6 + p6];
+        const int4 r = sched[(size_t)c * n_sched + l * 6 + p6];
         if (r.y <= r.x) continue;
         for (int t = r.x / KA; t <= (r.y - 1) / KA; ++t) c_of[t] += 1;
         max_slots = std::max(max_slots, std::min(KA, r.y - r.x));
@@ -1035,7 +1015,11 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
       }
     }
   }
-  deal(tiles(vocab), KAd, 6 * L, n_of);
+  deal(tiles(vocab), KAd, 6 * L, 1, n_of);
+  for (int c = 0; c < G; ++c) {            // head: whole tiles -> atom range [t0 * KAd, t1 * KAd), first tile t0, first k-atom 0
+    int4& r = sched[(size_t)c * n_sched + 6 * L];
+    r = make_int4(r.x * KAd, r.y * KAd, r.x, 0);
+  }
   max_slots = std::max(max_slots, KAd);
   if (plan) {
     plan->nrt = nrt; plan->cnt_ld = cnt_ld; plan->xt = xt; plan->n_slots = max_slots;
@@ -1047,17 +1031,17 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
     plan->cand_words = (size_t)2 * G * nrt * 2;
     const int n_cnt = L * 3 * cnt_ld, n_xexp = L * 3 * xt;
     auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t fixed = 1024 /*alignment*/ + (size_t)max_slots * kStSlot + up16((size_t)n_sched * 8) + up16((size_t)n_cnt) +
+    const size_t fixed = 1024 /*alignment*/ + (size_t)max_slots * kStSlot + (size_t)n_sched * 16 + up16((size_t)n_cnt) +
                          up16((size_t)n_xexp * 2) +
                          4 * ((((size_t)G * nrt * 2 + 3) & ~(size_t)3) + kStWorkerWarps * kStPartLd + 4 + 64 + 128 + (size_t)kStWorkerWarps * nrt * 2 + 16);
     const size_t budget = 227 * 1024 - 3072;           // static __shared__ + slack
-    if (fixed + 3 * (size_t)kStStage > budget) return false;
+    if (fixed + 6 * (size_t)kStStage > budget) return false;   // an attention group holds up to 4 key boxes before releasing any
     int ns = (int)((budget - fixed) / kStStage);
     if (ns > kStMaxStages) ns = kStMaxStages;
     plan->n_stages = ns;
     plan->smem_bytes = fixed + (size_t)ns * kStStage;
   }
-  if (sched_out) *reinterpret_cast<std::vector<int2>*>(sched_out) = sched;
+  if (sched_out) *reinterpret_cast<std::vector<int4>*>(sched_out) = sched;
   if (cnt_out) *reinterpret_cast<std::vector<unsigned char>*>(cnt_out) = cnt;
   if (xexp_out) *reinterpret_cast<std::vector<unsigned short>*>(xexp_out) = xexp;
   return true;
@@ -1065,9 +1049,10 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
 
 cudaError_t launch_decoder_stream(const StreamArgs& sa_in, const CUtensorMap& cross_map, const CUtensorMap& kc_map,
                                   const CUtensorMap& vc_map, int nrt, int num_sms, size_t smem_bytes, cudaStream_t st) {
-  void* fns[4] = {(void*)decoder_stream_kernel<1>, (void*)decoder_stream_kernel<2>, (void*)decoder_stream_kernel<4>,
-                  (void*)decoder_stream_kernel<8>};
-  const int slot = nrt == 1 ? 0 : (nrt == 2 ? 1 : (nrt == 4 ? 2 : 3));
+  void* fns[8] = {(void*)decoder_stream_kernel<1, false>, (void*)decoder_stream_kernel<2, false>, (void*)decoder_stream_kernel<4, false>,
+                  (void*)decoder_stream_kernel<8, false>, (void*)decoder_stream_kernel<1, true>, (void*)decoder_stream_kernel<2, true>,
+                  (void*)decoder_stream_kernel<4, true>, (void*)decoder_stream_kernel<8, true>};
+  const int slot = (nrt == 1 ? 0 : (nrt == 2 ? 1 : (nrt == 4 ? 2 : 3))) + (sa_in.m.timing ? 4 : 0);
   void* fn = fns[slot];
   // the attribute is per device: set it on every launch (a host-side table lookup) rather than caching a process-wide flag
   cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 3072);

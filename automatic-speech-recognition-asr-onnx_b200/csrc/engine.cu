@@ -90,7 +90,7 @@ struct b200asr_engine {
   StreamLayer* st_layers = nullptr; CUtensorMap* st_wmaps = nullptr; float* st_fold = nullptr;   // fold vectors (row sums, head g / b)
   float* st_head_g = nullptr; float* st_head_b = nullptr;
   unsigned long long* st_acc = nullptr; size_t st_acc_words = 0; unsigned long long* st_cand = nullptr; size_t st_cand_words = 0;
-  int2* st_sched = nullptr; unsigned char* st_cnt = nullptr; unsigned short* st_xexp = nullptr;
+  int4* st_sched = nullptr; unsigned char* st_cnt = nullptr; unsigned short* st_xexp = nullptr;
   StreamPlan st_plan{}; int st_plan_B = -1, st_plan_T = -1;
   CUtensorMap st_cross{}, st_kc{}, st_vc{}; int st_map_B = -1, st_map_T = -1;
   std::string graph_key;
@@ -572,16 +572,16 @@ int build_stream_tables(b200asr_engine* e) {
     e->ring_task_inv = inv;
   }
   if (e->st_plan_B != e->B || e->st_plan_T != e->T_enc) {
-    std::vector<int2> sched; std::vector<unsigned char> cnt; std::vector<unsigned short> xexp;
+    std::vector<int4> sched; std::vector<unsigned char> cnt; std::vector<unsigned short> xexp;
     StreamPlan pl;
     if (!stream_plan(e->B, d, f, c.n_heads, c.vocab, L, e->T_enc, c.max_target, e->num_sms, &pl, &sched, &cnt, &xexp))
       return e->fail(B200ASR_E_INVALID, "decoder_stream: plan does not fit");
     CK(cudaStreamSynchronize(e->st));
     if (e->st_sched) { cudaFree(e->st_sched); cudaFree(e->st_cnt); cudaFree(e->st_xexp); }
-    CK(cudaMalloc(&e->st_sched, sched.size() * sizeof(int2)));
+    CK(cudaMalloc(&e->st_sched, sched.size() * sizeof(int4)));
     CK(cudaMalloc(&e->st_cnt, cnt.size() + 16));
     CK(cudaMalloc(&e->st_xexp, xexp.size() * 2 + 16));
-    CK(b200_copy_sync(e, e->st_sched, sched.data(), sched.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CK(b200_copy_sync(e, e->st_sched, sched.data(), sched.size() * sizeof(int4), cudaMemcpyHostToDevice));
     CK(b200_copy_sync(e, e->st_cnt, cnt.data(), cnt.size(), cudaMemcpyHostToDevice));
     CK(b200_copy_sync(e, e->st_xexp, xexp.data(), xexp.size() * 2, cudaMemcpyHostToDevice));
     const size_t words = (size_t)pl.set_words * 2;
@@ -1175,6 +1175,10 @@ int b200asr_get_stage(b200asr_engine* e, const char* name_c, float* out, int64_t
       for (int64_t bh = 0; bh < Bm * H; ++bh)
         memcpy(out + (size_t)((l * Bm * H + bh) * kv * 64), h.data() + (size_t)(bh * mt * 64), (size_t)kv * 64 * 4);
     }
+  } else if (name == "mega_timing_raw") {                   // the raw 64-bit stamps, two floats' worth of bits each
+    if (!e->timing) return e->fail(B200ASR_E_INVALID, "set option mega_timing=1 first");
+    n = capacity < 2 * (int64_t)b200asr_engine::kTimingCap ? capacity : 2 * (int64_t)b200asr_engine::kTimingCap;
+    CK(b200_copy_sync(e, out, e->timing, (size_t)n * 4, cudaMemcpyDeviceToHost));
   } else if (name == "mega_timing") {                       // us between consecutive grid barriers of the last launch
     if (!e->timing) return e->fail(B200ASR_E_INVALID, "set option mega_timing=1 first");
     std::vector<unsigned long long> ht(b200asr_engine::kTimingCap);
