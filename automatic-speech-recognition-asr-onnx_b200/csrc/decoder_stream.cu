@@ -192,13 +192,18 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
     prefetch_tensormap(&cross_map); prefetch_tensormap(&kc_map); prefetch_tensormap(&vc_map);
     s_stop = 0; s_go = 0; s_prog = 0;
   }
+#pragma unroll 1
   for (int i = tid; i < n_sched; i += kStThreads) s_sched[i] = sa.sched[(size_t)blockIdx.x * n_sched + i];
+#pragma unroll 1
   for (int i = tid; i < n_cnt; i += kStThreads) s_cnt[i] = sa.cnt[i];
+#pragma unroll 1
   for (int i = tid; i < n_xexp; i += kStThreads) s_xexp[i] = sa.xexp[i];
+#pragma unroll 1
   for (int i = tid; i < sa.n_slots * kStSlot / 16; i += kStThreads) reinterpret_cast<uint4*>(bbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid < B) {
     s_ngen[tid] = a.n_gen[tid]; s_fin[tid] = a.finished[tid]; s_nsave[tid] = a.n_save[tid]; s_tok[tid] = 0;
     const int ns = a.n_save[tid];
+#pragma unroll 1
     for (int j = max(0, ns - 32); j < ns; ++j) s_hist[tid * 32 + (j & 31)] = a.save_id[(long long)tid * a.save_ld + j];
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 32u);
@@ -359,6 +364,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
     const int g_mine = ww / NRT;                         // slot group
     constexpr int NG = kStWorkerWarps / NRT;             // slot groups
     constexpr int U = NRT <= 2 ? 1 : (NRT == 4 ? 2 : 4); // k-atoms a thread polls together
+    constexpr int RR = NRT < 4 ? NRT : 4;                // utterances an epilogue thread handles
     const bool row_ok = r_mine < B;
     const int q_tm = warp & 3;                           // TMEM lane quarter this warp may read
     const int set_tm = ww >> 2;                          // 0: utterances 0-3 (columns 0-7), 1: utterances 4-7 (columns 8-15)
@@ -416,10 +422,12 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             const long long ngran = sa.layer_words >> 1;
             const long long g0 = ngran * blockIdx.x / G, g1 = ngran * (blockIdx.x + 1) / G;
             u64* zb = oset + xreg + (long long)l * sa.layer_words;
+#pragma unroll 1
             for (long long i = g0 + wt; i < g1; i += kStWorkers) st_zero2(zb + 2 * i);
             if (l == 0) {
               const long long xg = xreg >> 1;
               const long long x0 = xg * blockIdx.x / G, x1 = xg * (blockIdx.x + 1) / G;
+#pragma unroll 1
               for (long long i = x0 + wt; i < x1; i += kStWorkers) st_zero2(oset + 2 * i);
             }
           }
@@ -701,12 +709,14 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             const int tend = min(r.y, at + KA - (at == r.x ? r.w : 0));
             const bool desig = at != r.x || r.w == 0;
             const int n = tile * 128 + q_tm * 32 + lane;
-            float bv = 0.f, x0v[4] = {0.f, 0.f, 0.f, 0.f};
+            float bv = 0.f, x0v[RR];
+#pragma unroll
+            for (int rr = 0; rr < RR; ++rr) x0v[rr] = 0.f;
             if (epi_warp && desig && n < Nrows) {
               if (bias) bv = bias[n];
               if (add_x0) {
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
+                for (int rr = 0; rr < RR; ++rr) {
                   const int rq = set_tm * 4 + rr;
                   if (rq < B) x0v[rr] = a.pos[(long long)kv * d + n] +
                                         __bfloat162float(reinterpret_cast<const bf16*>(a.embed)[(long long)s_tok[rq] * d + n]);
@@ -724,7 +734,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               if (lane == 0) mbar_arrive(&acc_empty[buf]);
               if (n < Nrows) {
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
+                for (int rr = 0; rr < RR; ++rr) {
                   const int rq = set_tm * 4 + rr;
                   if (rq < B) {
                     float val = v[2 * rr] + v[2 * rr + 1];
@@ -748,12 +758,12 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
         const int t_end = r.z + (r.y - r.x) / KAd;
         wbar();                                             // s_pen / s_pen_n visible
         const bool pen_on = s_pen_n > 0;
-        float mean[4], rstd[4], bvv[4]; int bii[4];
+        float mean[RR], rstd[RR], bvv[RR]; int bii[RR];
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) { mean[rr] = 0.f; rstd[rr] = 1.f; bvv[rr] = -INFINITY; bii[rr] = 0x7fffffff; }
+        for (int rr = 0; rr < RR; ++rr) { mean[rr] = 0.f; rstd[rr] = 1.f; bvv[rr] = -INFINITY; bii[rr] = 0x7fffffff; }
         if (epi_warp && r.x < r.y) {
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
+          for (int rr = 0; rr < RR; ++rr) {
             const int rq = set_tm * 4 + rr;
             if (rq < B) {
               u64 w0, w1;
@@ -788,12 +798,13 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
             if (n < a.vocab) {
 #pragma unroll
-              for (int rr = 0; rr < 4; ++rr) {
+              for (int rr = 0; rr < RR; ++rr) {
                 const int rq = set_tm * 4 + rr;
                 if (rq < B) {
                   float val = fmaf(rstd[rr], (v[2 * rr] + v[2 * rr + 1]) - mean[rr] * gn, btn);
                   if (pen_on) {
                     bool hit = false;
+#pragma unroll 1
                     for (int qq = 0; qq < s_pen_n; ++qq) hit |= (s_pen[rq * 32 + qq] == n);
                     if (hit) val *= a.penalty_value;
                   }
@@ -809,7 +820,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
         ring_adv(pos, r.y - r.x, NS);
         if (epi_warp) {
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
+          for (int rr = 0; rr < RR; ++rr) {
             float bv = bvv[rr]; int bi = bii[rr];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -859,6 +870,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
         wbar();
         if (head_on && ww < B) {
           float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 1
           for (int c = lane; c < G; c += 32) {
             const float v = s_cand[(c * NRT + ww) * 2];
             const int i = __float_as_int(s_cand[(c * NRT + ww) * 2 + 1]);
