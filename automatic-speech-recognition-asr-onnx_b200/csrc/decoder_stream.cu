@@ -164,6 +164,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   float* s_qs = s_part + kStWorkerWarps * kStPartLd + 4;                         // [64]
   float* s_knv = s_qs + 64;                                                      // [2][64]
   float* s_best = s_knv + 128;                                                   // [8][NRT][2]
+  float* s_sc = s_best + kStWorkerWarps * NRT * 2 + ((4 - ((kStWorkerWarps * NRT * 2) & 3)) & 3);   // [8 warps][64] attention scores / probabilities
 
   __shared__ uint64_t full_bar[kStMaxStages], empty_bar[kStMaxStages];
   __shared__ uint64_t b_ready, acc_full[2], acc_empty[2], step_bar;
@@ -270,14 +271,22 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               for (int t = t0; t < ntask && !stop; t += G) {
                 const int b = t / H, h = t - b * H;
                 const int row0 = ((l * B + b) * H + h) * a.max_target;
-                for (int i = 0; i < nb && !stop; ++i) { kvbox(&kc_map, 0, row0 + i * 128); kvbox(&vc_map, 0, row0 + i * 128); }
+                for (int g0 = 0; g0 < nb && !stop; g0 += 4) {          // groups of <= 4 boxes: the K boxes, then the matching V boxes
+                  const int ge = min(nb, g0 + 4);
+                  for (int i = g0; i < ge && !stop; ++i) kvbox(&kc_map, 0, row0 + i * 128);
+                  for (int i = g0; i < ge && !stop; ++i) kvbox(&vc_map, 0, row0 + i * 128);
+                }
               }
             } else if (ph == 4) {               // cross K / V of my tasks
               const int nb = (T + 127) >> 7;
               for (int t = first_task(l, 1, sa.task_inv); t < ntask && !stop; t += G) {
                 const int b = t / H, h = t - b * H;
                 const int rk = (l * B + b) * T, rv = ((L + l) * B + b) * T;
-                for (int i = 0; i < nb && !stop; ++i) { kvbox(&cross_map, h * 64, rk + i * 128); kvbox(&cross_map, h * 64, rv + i * 128); }
+                for (int g0 = 0; g0 < nb && !stop; g0 += 4) {
+                  const int ge = min(nb, g0 + 4);
+                  for (int i = g0; i < ge && !stop; ++i) kvbox(&cross_map, h * 64, rk + i * 128);
+                  for (int i = g0; i < ge && !stop; ++i) kvbox(&cross_map, h * 64, rv + i * 128);
+                }
               }
             } else {
               const int p6 = phase_p6(ph);
@@ -478,44 +487,72 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             }
             float m = -INFINITY, lsum = 0.f, o0 = 0.f, o1 = 0.f;
             const int row = ww * 16 + rowl;
+            float* sc_w = s_sc + ww * 64;                    // this warp's scores / probabilities: [4 boxes][16 rows]
 #pragma unroll 1
-            for (int i = 0; i < nb; ++i) {
-              swait(&full_bar[pos.stage], pos.phase, 33);
-              const bf16* kr = reinterpret_cast<const bf16*>(ring + (size_t)pos.stage * kStStage) + row * 64 + half * 32;
-              float s0 = 0.f, s1 = 0.f;
+            for (int g0 = 0; g0 < nb; g0 += 4) {
+              // a group of <= 4 key boxes, then their value boxes.  Pass 1 only leaves raw scores in the warp's strip of shared
+              // memory, so the max / exp / sum chain runs once per group instead of once per box
+              const int nbg = min(4, nb - g0);
+#pragma unroll 1
+              for (int j = 0; j < nbg; ++j) {
+                if (DBG && a.timing && wt == 0) {            // instrumented build: how long do attention stages make us wait?
+                  const long long c0 = clock64();
+                  const bool ready = mbar_try_wait(&full_bar[pos.stage], pos.phase);
+                  swait(&full_bar[pos.stage], pos.phase, 33);
+                  atomicAdd(&a.timing[a.timing_cap - 4 + kind * 2], (unsigned long long)(clock64() - c0));
+                  atomicAdd(&a.timing[a.timing_cap - 3 + kind * 2], ready ? 1ull : (1ull << 32) + 1ull);
+                }
+                swait(&full_bar[pos.stage], pos.phase, 33);
+                const bf16* kr = reinterpret_cast<const bf16*>(ring + (size_t)pos.stage * kStStage) + row * 64 + half * 32;
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int cc = (c + rowl) & 3;
-                const uint4 u = *reinterpret_cast<const uint4*>(kr + cc * 8);
-                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
-                float2 f = __bfloat1622float2(hh[0]); s0 = fmaf(f.x, qh[c * 8 + 0], s0); s1 = fmaf(f.y, qh[c * 8 + 1], s1);
-                f = __bfloat1622float2(hh[1]); s0 = fmaf(f.x, qh[c * 8 + 2], s0); s1 = fmaf(f.y, qh[c * 8 + 3], s1);
-                f = __bfloat1622float2(hh[2]); s0 = fmaf(f.x, qh[c * 8 + 4], s0); s1 = fmaf(f.y, qh[c * 8 + 5], s1);
-                f = __bfloat1622float2(hh[3]); s0 = fmaf(f.x, qh[c * 8 + 6], s0); s1 = fmaf(f.y, qh[c * 8 + 7], s1);
+                for (int c = 0; c < 4; ++c) {
+                  const int cc = (c + rowl) & 3;
+                  const uint4 u = *reinterpret_cast<const uint4*>(kr + cc * 8);
+                  const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+                  float2 f = __bfloat1622float2(hh[0]); s0 = fmaf(f.x, qh[c * 8 + 0], s0); s1 = fmaf(f.y, qh[c * 8 + 1], s1);
+                  f = __bfloat1622float2(hh[1]); s0 = fmaf(f.x, qh[c * 8 + 2], s0); s1 = fmaf(f.y, qh[c * 8 + 3], s1);
+                  f = __bfloat1622float2(hh[2]); s0 = fmaf(f.x, qh[c * 8 + 4], s0); s1 = fmaf(f.y, qh[c * 8 + 5], s1);
+                  f = __bfloat1622float2(hh[3]); s0 = fmaf(f.x, qh[c * 8 + 6], s0); s1 = fmaf(f.y, qh[c * 8 + 7], s1);
+                }
+                float sv = s0 + s1;
+                sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+                if ((g0 + j) * 128 + row >= nvalid) sv = -INFINITY;
+                if (half == 0) sc_w[j * 16 + rowl] = sv;
+                __syncwarp();
+                if (lane == 0 && atomicAdd(&box_cnt[pos.stage], 1) == kStWorkerWarps - 1) { box_cnt[pos.stage] = 0; mbar_arrive(&empty_bar[pos.stage]); }
+                ring_adv(pos, 1, NS);
               }
-              float s = s0 + s1;
-              s += __shfl_xor_sync(0xffffffffu, s, 1);
-              if (i * 128 + row >= nvalid) s = -INFINITY;
-              const float mnew = fmaxf(m, warp_max(s));
+              // the group's soft-max statistics: lanes 0..31 and 32..63 of the strip
+              const float sa0 = lane < nbg * 16 ? sc_w[lane] : -INFINITY;
+              const float sa1 = lane + 32 < nbg * 16 ? sc_w[lane + 32] : -INFINITY;
+              const float mnew = fmaxf(m, warp_max(fmaxf(sa0, sa1)));
               const float msafe = mnew == -INFINITY ? 0.f : mnew;
-              const float sc = __expf(m - msafe);
-              const float pr = __expf(s - msafe);
-              lsum = lsum * sc + warp_sum(half == 0 ? pr : 0.f);
-              o0 *= sc; o1 *= sc; m = mnew;
+              const float scl = __expf(m - msafe);
+              const float p0 = __expf(sa0 - msafe), p1 = __expf(sa1 - msafe);
               __syncwarp();
-              if (lane == 0 && atomicAdd(&box_cnt[pos.stage], 1) == kStWorkerWarps - 1) { box_cnt[pos.stage] = 0; mbar_arrive(&empty_bar[pos.stage]); }
-              ring_adv(pos, 1, NS);
-              swait(&full_bar[pos.stage], pos.phase, 34);
-              const bf16* vb = reinterpret_cast<const bf16*>(ring + (size_t)pos.stage * kStStage) + (ww * 16) * 64 + 2 * lane;
-#pragma unroll 4
-              for (int j = 0; j < 16; ++j) {
-                const float pj = __shfl_sync(0xffffffffu, pr, 2 * j);
-                const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + j * 64));
-                o0 = fmaf(pj, v.x, o0); o1 = fmaf(pj, v.y, o1);
+              sc_w[lane] = p0; sc_w[lane + 32] = p1;
+              lsum = lsum * scl + warp_sum(p0 + p1);
+              o0 *= scl; o1 *= scl; m = mnew;
+              __syncwarp();
+#pragma unroll 1
+              for (int j = 0; j < nbg; ++j) {
+                swait(&full_bar[pos.stage], pos.phase, 34);
+                const bf16* vb = reinterpret_cast<const bf16*>(ring + (size_t)pos.stage * kStStage) + (ww * 16) * 64 + 2 * lane;
+                float oa0 = 0.f, oa1 = 0.f, ob0 = 0.f, ob1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                  const float pa_ = sc_w[j * 16 + i], pb_ = sc_w[j * 16 + i + 1];
+                  const float2 va = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + i * 64));
+                  const float2 vb2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + (i + 1) * 64));
+                  oa0 = fmaf(pa_, va.x, oa0); oa1 = fmaf(pa_, va.y, oa1);
+                  ob0 = fmaf(pb_, vb2.x, ob0); ob1 = fmaf(pb_, vb2.y, ob1);
+                }
+                o0 += oa0 + ob0; o1 += oa1 + ob1;
+                __syncwarp();
+                if (lane == 0 && atomicAdd(&box_cnt[pos.stage], 1) == kStWorkerWarps - 1) { box_cnt[pos.stage] = 0; mbar_arrive(&empty_bar[pos.stage]); }
+                ring_adv(pos, 1, NS);
               }
-              __syncwarp();
-              if (lane == 0 && atomicAdd(&box_cnt[pos.stage], 1) == kStWorkerWarps - 1) { box_cnt[pos.stage] = 0; mbar_arrive(&empty_bar[pos.stage]); }
-              ring_adv(pos, 1, NS);
             }
             float* pw = s_part + ww * kStPartLd;
             if (lane == 0) { pw[0] = m; pw[1] = lsum; }
@@ -1045,7 +1082,7 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
     auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t fixed = 1024 /*alignment*/ + (size_t)max_slots * kStSlot + (size_t)n_sched * 16 + up16((size_t)n_cnt) +
                          up16((size_t)n_xexp * 2) +
-                         4 * ((((size_t)G * nrt * 2 + 3) & ~(size_t)3) + kStWorkerWarps * kStPartLd + 4 + 64 + 128 + (size_t)kStWorkerWarps * nrt * 2 + 16);
+                         4 * ((((size_t)G * nrt * 2 + 3) & ~(size_t)3) + kStWorkerWarps * kStPartLd + 4 + 64 + 128 + (size_t)kStWorkerWarps * nrt * 2 + 16 + kStWorkerWarps * 64 + 4);
     const size_t budget = 227 * 1024 - 3072;           // static __shared__ + slack
     if (fixed + 6 * (size_t)kStStage > budget) return false;   // an attention group holds up to 4 key boxes before releasing any
     int ns = (int)((budget - fixed) / kStStage);

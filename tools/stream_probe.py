@@ -65,3 +65,9 @@ step = t[per:2 * per]
 for j, nme in enumerate(names):
     print(f"  {nme:6s} mean {step[j:8 * L:8].mean():7.2f} us  min {step[j:8 * L:8].min():7.2f}  max {step[j:8 * L:8].max():7.2f}")
 print(f"  head   {step[8 * L]:7.2f} us   exchange {step[8 * L + 1]:7.2f} us")
+raw = eng.get_stage("mega_timing_raw", 2 * 16384).view(np.uint32).astype(np.uint64)
+raw = (raw[0::2] | (raw[1::2] << np.uint64(32)))
+for kind, nme in ((0, "self"), (1, "cross")):
+    cyc, cnt = int(raw[16384 - 4 + kind * 2]), int(raw[16384 - 3 + kind * 2])
+    n, late = cnt & 0xffffffff, cnt >> 32
+    if n: print(f"  {nme}-attention K stages over 3 steps: {n} waits, {late} not ready on arrival, mean wait {cyc / n:.0f} cycles")
