@@ -107,6 +107,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_peaks():
+    """(hbm GB/s, bf16 TFLOP/s, source): MEASURED_PEAKS.json when the driver has written it, else the profiling recipe's fallback."""
+    try:
+        pk = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        return float(pk["hbm_gbs"]), float(pk["bf16_tflops"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
 def algorithmic_bytes_per_decode_step(dims, batch, T_enc, kv_mid):
     """HBM bytes one decode launch must move in bf16 (DESIGN.md 'Roofline'): every decoder weight once,
     the tied lm-head once, cross-KV of every utterance, the self-KV read so far."""
@@ -172,7 +181,7 @@ def run_reference(args, dims):
     print(json.dumps(line), flush=True)
 
 
-def run_sensevoice(args):
+def run_sensevoice(args, emit=True, reduce_max=None):
     """Parity-case leg (BASELINE config 0): SenseVoiceSmall, 8 s clips, one run = front end + 70 SANM blocks + CTC.
     Not the headline: `python bench.py --preset sensevoice-small [--precision f32|bf16] [--batch-per-gpu B]`."""
     from b200asr import sensevoice as sv
@@ -214,18 +223,21 @@ def run_sensevoice(args):
     steps = args.steps if args.steps is not None else 20
     warm = max(3, args.warmup if args.warmup is not None else 3)
     B = args.batch_per_gpu
-    torch.cuda.set_device(0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    hbm_peak, tf_peak, peak_src = measured_peaks()
     t0 = time.time()
     if para:
         tensors = pfm.fold_paraformer(pfm.synth_paraformer_checkpoint(dims, SEED), dims, N_SAMPLES)
-        eng = pfm.ParaformerEngine(dims, tensors, precision=args.precision, max_batch=B, max_samples=N_SAMPLES)
+        eng = pfm.ParaformerEngine(dims, tensors, precision=args.precision, max_batch=B, max_samples=N_SAMPLES, device=dev)
     else:
         tensors = sv.fold_sensevoice(sv.synth_sensevoice_checkpoint(dims, SEED), dims, N_SAMPLES)
-        eng = sv.SenseVoiceEngine(dims, tensors, precision=args.precision, max_batch=B, max_samples=N_SAMPLES)
+        eng = sv.SenseVoiceEngine(dims, tensors, precision=args.precision, max_batch=B, max_samples=N_SAMPLES, device=dev)
     del tensors
     setup_s = time.time() - t0
-    pcm = torch.from_numpy(synth_batch(B, N_SAMPLES)).pin_memory().numpy()
-    stream = torch.cuda.ExternalStream(eng.stream_ptr)
+    pcm = torch.from_numpy(synth_batch(B, N_SAMPLES, first_index=B * int(os.environ.get("RANK", "0")))).pin_memory().numpy()
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
 
     def timed(fn, n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -233,7 +245,8 @@ def run_sensevoice(args):
         for _ in range(n):
             fn()
         e1.record(stream); torch.cuda.synchronize()
-        return e0.elapsed_time(e1)
+        ms = e0.elapsed_time(e1)
+        return reduce_max(ms) if reduce_max else ms
 
     eng.upload(pcm, 0)
     for _ in range(warm):
@@ -244,7 +257,7 @@ def run_sensevoice(args):
     launches = eng.kernel_launches - l0
     clocks = sampler.stop()
     ms_e2e = timed(lambda: eng.run(pcm, 0), steps)
-    audio = N_SAMPLES / dims.sample_rate * B * steps
+    audio = N_SAMPLES / dims.sample_rate * B * steps * (world if reduce_max else 1)
     T = dims.lfr_frames(N_SAMPLES) + (0 if para else 4)
     d, f = dims.d_model, dims.ffn
     nblk = dims.enc_blocks if para else dims.total_blocks
@@ -252,29 +265,32 @@ def run_sensevoice(args):
                  + nblk * 4 * T * T * d + 2 * dims.frames(N_SAMPLES) * dims.win * (dims.nfft + 2) + (0 if para else 2 * T * d * dims.vocab))
     wbytes = (2 if args.precision == "bf16" else 4) * (nblk * (4 * d * d + 2 * d * f) + d * dims.vocab
                                                        + (dims.dec_att_blocks * (4 * d * d + 2 * d * dims.dec_ffn) + 3 * d * d if para else 0))
-    line = {"metric": "xRT (audio_s/wall_s)", "value": audio / (ms / 1e3), "unit": "x real time", "n_gpus": 1, "steps": steps,
+    line = {"metric": "xRT (audio_s/wall_s)", "value": audio / (ms / 1e3), "unit": "x real time", "n_gpus": world if reduce_max else 1, "steps": steps,
             "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic", "impl": "b200",
-            "config": {"workload": f"{args.preset} {args.precision}, batch={B}, 8 s clips, 1xB200: fbank + LFR + {nblk} SANM blocks + "
+            "config": {"workload": f"{args.preset} {args.precision}, batch={B}/GPU, 8 s clips, {world if reduce_max else 1}xB200: fbank + LFR + {nblk} SANM blocks + "
                                    + ("CIF + FSMN/cross-attention decoder" if para else "CTC"),
                        "weights": "seeded random init", "l2": "weights (~0.45 GB bf16 / ~0.9 GB f32) exceed the 126 MB L2"},
             "e2e": {"value": audio / (ms_e2e / 1e3), "unit": "x real time", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": int(pcm.nbytes + 4 * B), "d2h_bytes_per_step": int(B * (T + 1) * 4)},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"kernel": "whole run (launch-bound at batch 1: ~9 launches per block)", "bound": "hbm",
-                         "achieved": wbytes / (ms / steps / 1e3) / 1e9, "peak": 6650.0, "unit": "GB/s",
-                         "frac": wbytes / (ms / steps / 1e3) / 1e9 / 6650.0, "traffic": None, "algorithmic_bytes_per_launch": wbytes,
-                         "tflops": flops / (ms / steps / 1e3) / 1e12},
+                         "achieved": wbytes / (ms / steps / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": wbytes / (ms / steps / 1e3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": wbytes,
+                         "peak_source": peak_src, "tflops": flops / (ms / steps / 1e3) / 1e12,
+                         "frac_of_bf16_peak": flops / (ms / steps / 1e3) / 1e12 / tf_peak},
             "setup_s": setup_s, "tokens": len(toks[0])}
-    print(json.dumps(line), flush=True)
     eng.close()
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
 QWEN_SAMPLES = 480000        # BASELINE config 4: 30 s long-form clips
 QWEN_NEW = 128               # fixed decode length for random-weight decoders
 
 
-def run_qwen(args):
+def run_qwen(args, emit=True, reduce_max=None):
     """Secondary leg (BASELINE config 4's model): Qwen3-ASR-0.6B greedy, 30 s clips, 128 generated tokens per clip.
     `python bench.py --preset qwen3-asr-0.6b [--precision f32|bf16] [--batch-per-gpu B]`.  The reference ships no
     beam search (SURVEY note 4), so the decode strategy is the script's greedy arg-max."""
@@ -314,14 +330,17 @@ def run_qwen(args):
     steps = args.steps if args.steps is not None else 10
     warm = max(3, args.warmup if args.warmup is not None else 3)
     B = args.batch_per_gpu
-    torch.cuda.set_device(0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    hbm_peak, tf_peak, peak_src = measured_peaks()
     t0 = time.time()
     tensors = qw.fold_qwen(qw.synth_qwen_checkpoint(dims, SEED), dims)
-    eng = qw.QwenEngine(dims, tensors, prompt, precision=args.precision, max_batch=B, max_samples=QWEN_SAMPLES)
+    eng = qw.QwenEngine(dims, tensors, prompt, precision=args.precision, max_batch=B, max_samples=QWEN_SAMPLES, device=dev)
     del tensors
     setup_s = time.time() - t0
-    pcm = torch.from_numpy(synth_batch(B, QWEN_SAMPLES)).pin_memory().numpy()
-    stream = torch.cuda.ExternalStream(eng.stream_ptr)
+    pcm = torch.from_numpy(synth_batch(B, QWEN_SAMPLES, first_index=B * rank)).pin_memory().numpy()
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
 
     def timed(fn, n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -329,7 +348,8 @@ def run_qwen(args):
         for _ in range(n):
             fn()
         e1.record(stream); torch.cuda.synchronize()
-        return e0.elapsed_time(e1)
+        ms = e0.elapsed_time(e1)
+        return reduce_max(ms) if reduce_max else ms
 
     eng.upload(pcm)
     for _ in range(warm):
@@ -348,11 +368,11 @@ def run_qwen(args):
                    + dims.vocab * dims.hidden)
     n_prompt = len(prompt.head_ids) + len(prompt.suffix_ids) + len(prompt.tail_ids) + dims.audio_tokens(QWEN_SAMPLES)
     kvbytes = B * es * 2 * dims.dec_layers * dims.kv_heads * dims.head_dim * (n_prompt + QWEN_NEW // 2)
-    audio = audio_s * B * steps
-    line = {"metric": "xRT (audio_s/wall_s)", "value": audio / (ms / 1e3), "unit": "x real time", "n_gpus": 1, "steps": steps,
+    audio = audio_s * B * steps * (world if reduce_max else 1)
+    line = {"metric": "xRT (audio_s/wall_s)", "value": audio / (ms / 1e3), "unit": "x real time", "n_gpus": world if reduce_max else 1, "steps": steps,
             "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic", "impl": "b200",
-            "config": {"workload": f"{args.preset} {args.precision} greedy, batch={B}, 30 s clips, 1xB200: log-mel + conv stem + "
+            "config": {"workload": f"{args.preset} {args.precision} greedy, batch={B}/GPU, 30 s clips, {world if reduce_max else 1}xB200: log-mel + conv stem + "
                                    f"{dims.enc_layers} windowed encoder layers + {n_prompt}-token prefill + {QWEN_NEW - 1} decode steps "
                                    f"({dims.dec_layers} layers)", "weights": "seeded random init",
                        "l2": "decoder weights (1.19 GB bf16) exceed the 126 MB L2"},
@@ -361,12 +381,14 @@ def run_qwen(args):
             "gpu_launches": int(launches), "clocks": clocks,
             "phases_ms": {"encoder_prefill_first_token": ms_first / steps, "decode_step": step_ms},
             "roofline": {"kernel": "decode step (CUDA graph: 4 qwen_gemv_kernel + 1 attention launch per layer, weights streamed once)", "bound": "hbm",
-                         "achieved": (wbytes + kvbytes) / (step_ms / 1e3) / 1e9, "peak": 6650.0, "unit": "GB/s",
-                         "frac": (wbytes + kvbytes) / (step_ms / 1e3) / 1e9 / 6650.0, "traffic": None,
+                         "achieved": (wbytes + kvbytes) / (step_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": (wbytes + kvbytes) / (step_ms / 1e3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": wbytes + kvbytes},
             "setup_s": setup_s, "tokens": len(toks[0])}
-    print(json.dumps(line), flush=True)
     eng.close()
+    if emit:
+        print(json.dumps(line), flush=True)
+    return line
 
 
 def main():
@@ -379,6 +401,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE config 3/4/5 sub-objects (default run includes them)")
     args = ap.parse_args()
     if args.preset.startswith("sensevoice") or args.preset.startswith("paraformer"):
         return run_sensevoice(args)
@@ -410,12 +433,14 @@ def main():
     from b200asr.sharding import gather_tokens
 
     B = args.batch_per_gpu
+    extras = not args.no_extra_configs and args.preset == "whisper-large-v3" and args.precision == "bf16" and B == 1
+    max_b = max(B, 8) if extras else B
     sup, beg = _suppress(dims)
     t0 = time.time()
     raw = synth_whisper_checkpoint(dims, SEED)
     tensors = fold_whisper(raw, dims, sup, beg)
     del raw
-    eng = WhisperEngine(dims, tensors, precision=args.precision, max_batch=B, max_samples=N_SAMPLES, device=local_rank)
+    eng = WhisperEngine(dims, tensors, precision=args.precision, max_batch=max_b, max_samples=N_SAMPLES, device=local_rank)
     del tensors
     setup_s = time.time() - t0
     prompt = _prompt(dims)
@@ -493,16 +518,87 @@ def main():
     e2e = total_audio / (ms_e2e / 1e3)
     T_mel = N_SAMPLES // dims.hop
     T_enc = (T_mel + 1) // 2
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+    hbm_peak, tf_peak, peak_src = measured_peaks()
     bytes_step = algorithmic_bytes_per_decode_step(dims, B, T_enc, len(prompt) + DECODE_LAUNCHES // 2)
     achieved = bytes_step / (ms_dec / 1e3) / 1e9
     enc_tf = encoder_flops(dims, T_mel, T_enc) * B / (ms_enc / 1e3) / 1e12
+
+    # ---- BASELINE configs 3 / 4 / 5 at their stated per-GPU load, measured in this same run (sub-objects of the line) ----
+    extra = {}
+    if extras:
+        def reduce_max(ms):
+            if world > 1:
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t.item())
+            return ms
+
+        def whisper_batch(nclips, steps):
+            """`nclips` clips per GPU in launches of <= 8 (the decode kernel's batch cap): resident and end-to-end xRT, decode ms/step."""
+            groups = [min(8, nclips - g) for g in range(0, nclips, 8)]
+            pcs = [torch.from_numpy(synth_batch(g, N_SAMPLES, first_index=(rank * nclips + i * 8) % 4096)).pin_memory().numpy()
+                   for i, g in enumerate(groups)]
+            outs = {}
+
+            def go_e2e():
+                for pc in pcs:
+                    outs["t"] = finish_any(eng.transcribe(pc, prompt, max_new=MAX_NEW), pc.shape[0])
+
+            def go_res():
+                for pc in pcs:       # resident arm: PCM is re-uploaded outside the timed region only when one launch holds the batch
+                    outs["t"] = finish_any(eng.transcribe_resident(prompt, max_new=MAX_NEW), pc.shape[0])
+
+            for _ in range(3):
+                go_e2e()
+            ms_e = timed(go_e2e, steps)
+            res_ms = None
+            if len(groups) == 1:
+                eng.upload_pcm(pcs[0])
+                go_res()
+                res_ms = timed(go_res, steps)
+            g0 = groups[0]
+            eng.upload_pcm(pcs[0]); eng.encode_resident()
+            eng.prefill(prompt, want_logits=False); eng.decode(max_steps=4)
+            eng.prefill(prompt, want_logits=False)
+            dec = timed(lambda: eng.decode(max_steps=DECODE_LAUNCHES), 1) / DECODE_LAUNCHES
+            bs = algorithmic_bytes_per_decode_step(dims, g0, T_enc, len(prompt) + DECODE_LAUNCHES // 2)
+            tot = audio_s * nclips * world * steps
+            o = {"clips_per_gpu": nclips, "global_batch": nclips * world, "launch_batches": groups,
+                 "e2e": {"value": tot / (ms_e / 1e3), "unit": "x real time", "ms_per_step": ms_e / steps,
+                         "h2d_bytes_per_step": int(sum(pc.nbytes for pc in pcs) + nclips * len(prompt) * 4),
+                         "d2h_bytes_per_step": int(nclips * (dims.max_target + 1) * 4)},
+                 "roofline": {"kernel": f"decoder_stream_kernel, batch {g0}", "bound": "hbm", "achieved": bs / (dec / 1e3) / 1e9, "peak": hbm_peak,
+                              "unit": "GB/s", "frac": bs / (dec / 1e3) / 1e9 / hbm_peak, "ms_per_launch": dec, "algorithmic_bytes_per_launch": bs,
+                              "traffic": None, "peak_source": peak_src}}
+            if res_ms is not None:
+                o["value"] = tot / (res_ms / 1e3); o["unit"] = "x real time"; o["ms_per_step"] = res_ms / steps
+            return o
+
+        def finish_any(tokens, nb):
+            if world > 1:
+                idx = list(range(rank * nb, rank * nb + nb))
+                return gather_tokens(tokens, idx, nb * world, dims.max_target, device=f"cuda:{local_rank}")
+            return tokens
+
+        extra["config3"] = whisper_batch(4, max(3, args.steps // 2))
+        extra["config3"]["workload"] = (f"BASELINE config 3's per-GPU load: whisper-large-v3 bf16 greedy, 4 clips/GPU x {world} GPU(s) "
+                                        f"(= batch 32 over 8xB200 at --gpus 8)")
+        if 32 % world == 0:
+            extra["config3_global32"] = whisper_batch(32 // world, 2)
+            extra["config3_global32"]["workload"] = f"fixed global batch 32: {32 // world} clips/GPU x {world} GPU(s), launches of <= 8 clips"
+        eng.close()
+        import copy
+        pa = copy.copy(args); pa.preset = "paraformer-large"; pa.batch_per_gpu = 8; pa.steps = 10; pa.warmup = 3
+        ln = run_sensevoice(pa, emit=False, reduce_max=reduce_max)
+        extra["config4"] = {"workload": ln["config"]["workload"] + " (BASELINE config 4's per-GPU load: batch 64 over 8xB200)",
+                            "value": ln["value"], "unit": ln["unit"], "ms_per_step": ln["ms_per_step"], "e2e": ln["e2e"],
+                            "roofline": ln["roofline"], "gpu_launches": ln["gpu_launches"]}
+        qa = copy.copy(args); qa.preset = "qwen3-asr-0.6b"; qa.batch_per_gpu = 4; qa.steps = 3; qa.warmup = 3
+        ln = run_qwen(qa, emit=False, reduce_max=reduce_max)
+        extra["config5"] = {"workload": ln["config"]["workload"] + " (BASELINE config 5's per-GPU load: batch 16 over 4xB200; greedy -- the "
+                                        "reference ships no beam search)",
+                            "value": ln["value"], "unit": ln["unit"], "ms_per_step": ln["ms_per_step"], "e2e": ln["e2e"],
+                            "roofline": ln["roofline"], "phases_ms": ln["phases_ms"], "gpu_launches": ln["gpu_launches"]}
 
     if rank == 0:
         line = {
@@ -524,24 +620,41 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "kernel": "decoder_ring_kernel<NR> (streaming greedy-decode kernel: TMA weight ring + flag-in-data "
-                          "exchanges; one greedy step = all decoder weights streamed once)",
+                "kernel": "decoder_stream_kernel<NRT> (split-K tcgen05 streaming decode kernel: TMA weight ring, fixed-point "
+                          "accumulate-in-L2 exchanges; one greedy step = all decoder weights streamed once)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (8 greedy steps in
-                # one launch, profiles/ncu_r01_summary.md) divided by its 8 steps: bytes per greedy step, like `achieved`
-                "traffic": (13.371254e9 + 11.967e6) / 8 if (B == 1 and args.preset == "whisper-large-v3" and args.precision == "bf16") else None,
-                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+                # not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the `ncu --set full` capture of this
+                # kernel committed under profiles/ (per greedy step, like `achieved`); None when no capture matches the config
+                "traffic": profile_traffic(B, args),
+                "traffic_source": "profiles/ncu_r02_stream_summary.md (one ncu --set full capture, bytes per greedy step)",
+                "peak_source": peak_src,
                 "ms_per_launch": ms_dec, "algorithmic_bytes_per_launch": bytes_step,
             },
             "encoder": {"ms": ms_enc, "tflops": enc_tf, "frac_of_bf16_peak": enc_tf / tf_peak},
             "setup_s": setup_s, "tokens_head": result["tokens"][0][:8],
         }
+        line.update(extra)
         if not args.no_cpu_baseline and world == 1 and args.preset == "whisper-large-v3":
             line["cpu_baseline"] = cpu_baseline(dims, prompt, result["tokens"][0])
+            for k in ("config3", "config3_global32"):
+                if k in line:
+                    line[k]["vs_cpu_port_e2e"] = line[k]["e2e"]["value"] / line["cpu_baseline"]["value"]
         print(json.dumps(line), flush=True)
-    eng.close()
+    if not extras:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def profile_traffic(B, args):
+    """Measured DRAM bytes per greedy step of the dominant kernel, from the committed ncu capture (profiles/ncu_r02_stream.json)."""
+    try:
+        d = json.loads((ROOT / "profiles" / "ncu_r02_stream.json").read_text())
+        if args.preset == d.get("preset") and args.precision == d.get("precision"):
+            return d["dram_bytes_per_step"].get(str(B))
+    except Exception:
+        pass
+    return None
 
 
 def cpu_baseline(dims, prompt, gpu_tokens):
