@@ -24,11 +24,13 @@ def synth_batch(batch: int, n_samples: int = 128000, first_index: int = 0) -> np
     return np.stack([synth_pcm(first_index + i, n_samples) for i in range(batch)])
 
 
-def synth_whisper_checkpoint(dims, seed: int):
+def synth_whisper_checkpoint(dims, seed: int, pos_scale: float = 1.0):
     """Seeded random Whisper checkpoint with HF state-dict key names (no real
     checkpoints exist offline).  Linear ~ N(0, 1/fan_in), LayerNorm gamma ~ 1+0.1N,
     beta ~ 0.1N, token embedding ~ 0.05N; draw order is part of the contract
-    (tests pin it against the oracle's generator)."""
+    (tests pin it against the oracle's generator).  pos_scale multiplies the decoder position table after the draw:
+    100 gives non-degenerate greedy streams (20+ distinct ids in 33 steps) while the random net stays in the regime
+    where rounding errors do not amplify (oracle/whisper_oracle.py: make_raw_weights)."""
     import math
     g = torch.Generator().manual_seed(int(seed))
     d, f = dims.d_model, dims.ffn
@@ -65,7 +67,7 @@ def synth_whisper_checkpoint(dims, seed: int):
     norm(e + "layer_norm")
     dd = "model.decoder."
     w[dd + "embed_tokens.weight"] = rn(dims.vocab, d, std=0.05)
-    w[dd + "embed_positions.weight"] = rn(dims.max_target, d, std=0.05)
+    w[dd + "embed_positions.weight"] = rn(dims.max_target, d, std=0.05) * float(pos_scale)
     for i in range(dims.dec_layers):
         p = f"{dd}layers.{i}."
         attn(p + "self_attn"); norm(p + "self_attn_layer_norm")

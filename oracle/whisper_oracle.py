@@ -70,8 +70,14 @@ TINY_TEST = WhisperDims(n_mels=128, d_model=256, n_heads=4, ffn=512, enc_layers=
 # --------------------------------------------------------------------------
 # Seeded synthetic checkpoint (HF WhisperForConditionalGeneration key names)
 # --------------------------------------------------------------------------
-def make_raw_weights(dims: WhisperDims, seed: int) -> Dict[str, torch.Tensor]:
+def make_raw_weights(dims: WhisperDims, seed: int, pos_scale: float = 1.0) -> Dict[str, torch.Tensor]:
     """Deterministic random checkpoint with HF state-dict names.
+
+    pos_scale multiplies the decoder's learned position table after the draw (the draw order never changes).  With
+    the default scales a random decoder is in the "ordered" regime: its output barely depends on the fed-back token
+    or the position, so greedy streams repeat one id; pos_scale = 100 makes the position term comparable to the
+    32 layers of residual updates and the streams take 20+ distinct ids in 33 steps, without scaling the weight
+    matrices (which would push the net into the chaotic regime where rounding errors explode).
 
     There are no real checkpoints offline, so weights are drawn
     here.  Scales are chosen so activations stay O(1): Linear ~ N(0, 1/fan_in),
@@ -117,7 +123,7 @@ def make_raw_weights(dims: WhisperDims, seed: int) -> Dict[str, torch.Tensor]:
 
     dd = "model.decoder."
     w[dd + "embed_tokens.weight"] = rn(dims.vocab, d, std=0.05)
-    w[dd + "embed_positions.weight"] = rn(dims.max_target, d, std=0.05)
+    w[dd + "embed_positions.weight"] = rn(dims.max_target, d, std=0.05) * float(pos_scale)
     for i in range(dims.dec_layers):
         p = f"{dd}layers.{i}."
         attn(p + "self_attn")

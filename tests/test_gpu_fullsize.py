@@ -1,7 +1,7 @@
 """Full-size parity (BASELINE configs[1] dimensions): Whisper-large-v3 with seeded weights, one 8 s clip, the CUDA engine
 against the CPU oracle on the same inputs.  fp32 engine: prefill and first decode-step logits within 1e-3 of the oracle
-(north_star's tolerance) and the same first tokens; bf16 engine: within 0.15 on logits of standard deviation 2.8 (32 + 32 layers of bf16
-GEMM inputs; measured 0.05), written here, and the same arg-max wherever the oracle's top-2 margin exceeds twice that."""
+(north_star's tolerance) and the same first tokens; bf16 engine: within 0.075 on logits of standard deviation 2.8 (32 + 32 layers of bf16
+GEMM inputs; 1.5 x the 0.050 measured on B200: a bound tied to the measurement), written here, and the same arg-max wherever the oracle's top-2 margin exceeds twice that."""
 import numpy as np
 import pytest
 import torch
@@ -14,6 +14,8 @@ from b200asr.weights import fold_whisper
 
 pytestmark = pytest.mark.gpu
 PROMPT = [50258, 50259, 50360, 50364]
+POS_SCALE = 100.0          # non-degenerate greedy streams (b200asr.synth.synth_whisper_checkpoint)
+N_STEPS = 8                # prefill + 7 decode steps
 SUP, BEG = [1, 2, 7, 8, 9, 10, 14, 25, 50358, 50359, 50360, 50361, 50362, 50363], [220, 50257]
 
 
@@ -21,18 +23,18 @@ SUP, BEG = [1, 2, 7, 8, 9, 10, 14, 25, 50358, 50359, 50360, 50361, 50362, 50363]
 def reference():
     torch.set_num_threads(max(1, torch.get_num_threads()))
     od = wo.WhisperDims(**DIMS.to_dict())
-    fw = wo.fold_weights(wo.make_raw_weights(od, 20260), od, SUP, BEG)
+    fw = wo.fold_weights(wo.make_raw_weights(od, 20260, pos_scale=POS_SCALE), od, SUP, BEG)
     pcm = synth_pcm(0, 128000)
     with torch.no_grad():
-        ref = wo.greedy_transcribe(pcm, fw, od, PROMPT, stop_tokens=[], max_new=3, return_logits=True)
+        ref = wo.greedy_transcribe(pcm, fw, od, PROMPT, stop_tokens=[], max_new=N_STEPS, return_logits=True)
     del fw
     return pcm, ref
 
 
-@pytest.mark.parametrize("precision,tol", [("f32", 1e-3), ("bf16", 0.15)])
+@pytest.mark.parametrize("precision,tol", [("f32", 1e-3), ("bf16", 0.075)])
 def test_large_v3_logits_match_oracle(reference, precision, tol):
     pcm, ref = reference
-    tensors = fold_whisper(synth_whisper_checkpoint(DIMS, 20260), DIMS, SUP, BEG)
+    tensors = fold_whisper(synth_whisper_checkpoint(DIMS, 20260, pos_scale=POS_SCALE), DIMS, SUP, BEG)
     eng = WhisperEngine(DIMS, tensors, precision=precision, max_batch=1, max_samples=128000)
     del tensors
     eng.set_decode_options(stop_ids=[], generate_limit=0)
@@ -40,19 +42,23 @@ def test_large_v3_logits_match_oracle(reference, precision, tol):
     logits, tok = eng.prefill(PROMPT)
     rows = [logits[0].copy()]
     toks = [int(tok[0])]
-    for _ in range(2):
-        logits, tok = eng.decode_step()
+    # teacher-forced on the oracle's stream so every step compares the same context
+    for i in range(1, N_STEPS):
+        logits, tok = eng.decode_step(token_in=np.array([ref["selected"][i - 1]], np.int32))
         rows.append(logits[0].copy()); toks.append(int(tok[0]))
     eng.close()
-    got, want = np.stack(rows), ref["step_logits"][:3]
+    got, want = np.stack(rows), np.asarray(ref["step_logits"][:N_STEPS])
     d = float(np.abs(got - want).max())
-    print(f"large-v3 {precision}: max |dlogit| over prefill + 2 steps = {d:.2e} (logit std {want.std():.2f}); tokens {toks} vs {ref['selected'][:3]}")
-    assert d <= tol
     top2 = np.sort(want, axis=-1)[:, -2:]
-    safe = (top2[:, 1] - top2[:, 0]) > 2 * tol
+    margins = top2[:, 1] - top2[:, 0]
+    print(f"large-v3 {precision}: max |dlogit| over prefill + {N_STEPS - 1} steps = {d:.2e} (logit std {want.std():.2f}); "
+          f"{len(set(ref['selected'][:N_STEPS]))} distinct ids, fp32 margins min {margins.min():.3f}; tokens {toks} vs {ref['selected'][:N_STEPS]}")
+    assert len(set(ref["selected"][:N_STEPS])) >= 5, "the synthetic checkpoint must give a non-degenerate greedy stream"
+    assert d <= tol
+    safe = margins > 2 * tol
     assert np.array_equal(got.argmax(-1)[safe], want.argmax(-1)[safe])
     if precision == "f32":
-        assert toks == ref["selected"][:3]
+        assert toks == ref["selected"][:N_STEPS]
 
 
 # ---- Qwen3-ASR-0.6B dimensions (BASELINE configs[4]'s model): one 8 s clip, prefill + 2 decode steps ----
@@ -69,9 +75,9 @@ def qwen_reference():
     return pcm, toks, st["logits"].numpy(), st["audio_hidden"].numpy()
 
 
-@pytest.mark.parametrize("precision,tol", [("f32", 1e-3), ("bf16", 0.25)])
+@pytest.mark.parametrize("precision,tol", [("f32", 1e-3), ("bf16", 0.19)])
 def test_qwen3_asr_0_6b_logits_match_oracle(qwen_reference, precision, tol):
-    """fp32 engine within 1e-3 of the oracle on logits (north-star tolerance); bf16 engine within 0.25 (18 + 28 layers of
+    """fp32 engine within 1e-3 of the oracle on logits (north-star tolerance); bf16 engine within 0.19 (1.5 x the 0.125 measured on B200; 18 + 28 layers of
     bf16 GEMM operands and a bf16 KV cache; written here), arg-max equal wherever the oracle's top-2 margin exceeds 2x."""
     from b200asr import qwen as qw
     pcm, toks, want, ah = qwen_reference

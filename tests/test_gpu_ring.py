@@ -5,7 +5,7 @@ ring_tc=0 (CUDA-core dot products): same bf16 weights, fp32 activations and fp32
 kernel, only the summation order differs: logits agree to 5e-3 and token streams are identical.
 ring_tc=1 (optional mma.sync dot products; measured slower than the CUDA-core path on B200, so not the default): the activation rows are rounded to bf16 as the B operand,
 like every GEMM input of the encoder: logits agree with the barrier kernel to 6e-2 (written here; measured
-~1e-2 on logits of std 1.8) and with the fp32 goldens to the bf16 bound 0.08; arg-max ids agree wherever the
+~1e-2 on logits of std 1.8) and with the fp32 goldens to the bf16 bound 0.03 (tests/test_gpu_whisper_bf16.py); arg-max ids agree wherever the
 reference top-2 margin exceeds 2x that, and a free-running stream may only leave the reference stream at a
 step whose margin is below it."""
 import numpy as np
@@ -52,7 +52,7 @@ def test_ring_vs_mega_logits_and_tokens(path):
     d = maxdiff(res[1][0], res[0][0])
     print("ring vs mega max |dlogit| =", d)
     assert d <= 5e-3
-    assert maxdiff(res[1][0][0], g["forced_logits"]) <= 0.08
+    assert maxdiff(res[1][0][0], g["forced_logits"]) <= 0.03
     assert res[1][1] == res[0][1]
     assert res[1][2] == res[0][2]
     assert res[1][3] == res[0][3]
@@ -91,7 +91,7 @@ def test_ring_tc_vs_mega_and_golden(path):
     d = maxdiff(out[1][0], out[0][0])
     print("ring(tc) vs mega max |dlogit| =", d, " vs golden", maxdiff(out[1][0], g["forced_logits"]))
     assert d <= TC_TOL
-    assert maxdiff(out[1][0], g["forced_logits"]) <= 0.08
+    assert maxdiff(out[1][0], g["forced_logits"]) <= 0.035      # bf16 activation rows on this path: 1.5 x the 0.0222 measured
     ref = out[0][0]
     top2 = np.sort(ref, axis=-1)[:, -2:]
     safe = (top2[:, 1] - top2[:, 0]) > 2 * TC_TOL

@@ -53,7 +53,7 @@ def test_stream_vs_mega_logits_and_tokens(path):
     d = maxdiff(res[1][0], res[0][0])
     print("stream vs mega max |dlogit| =", d, " vs golden", maxdiff(res[1][0][0], g["forced_logits"]))
     assert d <= 5e-3
-    assert maxdiff(res[1][0][0], g["forced_logits"]) <= 0.08
+    assert maxdiff(res[1][0][0], g["forced_logits"]) <= 0.03      # tests/test_gpu_whisper_bf16.py: the bf16 bound
     assert res[1][1] == res[0][1]
     assert res[1][2] == res[0][2]
     assert res[1][3] == res[0][3]

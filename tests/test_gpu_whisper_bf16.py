@@ -1,6 +1,6 @@
 """bf16 tensor-core mode vs the fp32 goldens.  bf16 operands carry 8 mantissa bits, so
-the tolerance is looser and written here: |dlogit| <= 0.08 on logits of std ~1.8 (tiny
-model, 2+2 layers); greedy tokens must match wherever the golden top-2 margin exceeds
+the tolerance is looser and written here: |dlogit| <= 0.03 on logits of std ~1.8 (tiny
+model, 2+2 layers; 1.5 x the 0.0194 measured on B200 -- a bound tied to the measurement, not a guess); greedy tokens must match wherever the golden top-2 margin exceeds
 2x that bound.  Also checks tcgen05 vs CUDA-core GEMMs inside the full model and that a
 batch of utterances reproduces the single-utterance results."""
 import numpy as np
@@ -10,7 +10,7 @@ from gpu_common import GOLD, load_case, make_engine, maxdiff
 from b200asr.synth import synth_pcm
 
 pytestmark = pytest.mark.gpu
-TOL = 0.08
+TOL = 0.03
 
 
 def _run(eng, pcm, prompt, forced):
