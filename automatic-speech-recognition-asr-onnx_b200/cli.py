@@ -187,7 +187,9 @@ def _main_sensevoice(args) -> int:
         print(f"\nTest Input Audio: {path}")
         res = sv.transcribe_long(eng, x, args.language, input_audio_length=win, sliding_window=consts["SLIDING_WINDOW"],
                                  sample_rate=dims.sample_rate)
-        text = sp.decode(res["tokens"]) if sp is not None else " ".join(map(str, res["tokens"]))
+        # the script detokenises window by window and concatenates the text (Inference_SenseVoice_ONNX.py:303-305); SentencePiece
+        # strips the leading word-boundary mark of every decode call, so decoding the concatenated ids would add a space per window
+        text = ("".join(sp.decode(w) for w in res["per_window"]) if sp is not None else " ".join(map(str, res["tokens"])))
         print(f"\nASR Result:\n{text}\n\nRTF: {res['rtf']:.4f}\n")
     eng.close()
     return 0
@@ -222,7 +224,9 @@ def _main_paraformer(args) -> int:
         print("-" * 106)
         print(f"\nTest Input Audio: {path}")
         res = sv.transcribe_long(eng, x, input_audio_length=win, sliding_window=consts["SLIDING_WINDOW"], sample_rate=dims.sample_rate)
-        text = pfm.tokens_to_text(res["tokens"], vocab, consts["DECODE_MODE"]).strip() if vocab is not None else " ".join(map(str, res["tokens"]))
+        # per window, then concatenated, as the script does
+        text = ("".join(pfm.tokens_to_text(w, vocab, consts["DECODE_MODE"]) for w in res["per_window"]).strip()
+                if vocab is not None else " ".join(map(str, res["tokens"])))
         print(f"\nASR Result:\n{text}\n\nRTF: {res['rtf']:.4f}\n")
     eng.close()
     return 0

@@ -240,14 +240,13 @@ cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, in
   const int dh = d / n_heads, nh = dh / 64;
   const int nkb = (T + 127) / 128;
   const size_t smem = (size_t)(nh + 2 * nkb * nh + 2) * kAttTile + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static AttrOnce attr;
+  if (attr.need()) {
     cudaError_t r = cudaFuncSetAttribute(attention_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * kAttTile + 1024);
     if (r == cudaSuccess) r = cudaFuncSetAttribute(attention_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * kAttTile + 1024);
     if (r == cudaSuccess) r = cudaFuncSetAttribute(attention_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kAttTile + 1024);
     if (r == cudaSuccess) r = cudaFuncSetAttribute(attention_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * kAttTile + 1024);
     if (r != cudaSuccess) return r;
-    attr_done = true;
   }
   CUtensorMap tm;
   if (!make_tmap_rows_sw128(&tm, qkv, 3 * (int64_t)d, (int64_t)batch * T, 3 * (int64_t)d, 128, err)) return cudaErrorNotSupported;

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 
 namespace b200asr {
@@ -29,6 +30,18 @@ struct GemmArgs {
   int M = 0, N = 0, K = 0;
   int batch = 1, batch_inner = 1;
   int pdl = 0;                        // gemm_tc only: launch as a programmatic dependent (B must be a weight matrix no kernel writes)
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: a process-wide "done" flag would leave a second engine on
+// another GPU without it.  One bit per (device, slot), set atomically; returns true when the caller must set the attribute.
+struct AttrOnce {
+  std::atomic<unsigned long long> bits[64];
+  bool need(int slot = 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const unsigned long long m = 1ull << (slot & 63);
+    return (bits[dev].fetch_or(m) & m) == 0;
+  }
 };
 
 // ---- device helpers ---------------------------------------------------------
@@ -143,7 +156,8 @@ struct SelectArgs {
   DecState* state; int n_new;               // state->kv_len += n_new, step += 1
   // TOPK_TOPP_SAMPLING (Export_Whisper.py:263-307); temperature <= 0 selects the argmax heads above
   float temperature; int top_k; float top_p; float rep_penalty; unsigned long long seed;
-  const float* noise; int noise_ld; int noise_rows;   // optional uniform noise [launch][B][top_k] (reproducible runs)
+  const float* noise; int noise_ld; int noise_rows;   // optional uniform noise [launch][max_batch][top_k] (reproducible runs)
+  int noise_batch;                                    // max_batch: the row stride of `noise` in utterances
 };
 cudaError_t launch_select_token(const SelectArgs& a, cudaStream_t st);
 cudaError_t launch_softmax_pick(const float* logits, const float* add_bias, int vocab, int batch, int index,

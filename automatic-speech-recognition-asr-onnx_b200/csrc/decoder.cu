@@ -163,12 +163,12 @@ cudaError_t launch_dec_linear(const DecLinearArgs& a, cudaStream_t st) {
   const int nwarps = kDecThreads / 32;
   int grid = (a.N + nwarps - 1) / nwarps;
   if (grid > 148 * 8) grid = 148 * 8;
-  static bool attr_done[2] = {false, false};
+  static AttrOnce attr;
   if (a.w_dtype == kF32) {
-    if (!attr_done[0]) { cudaFuncSetAttribute(dec_linear_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done[0] = true; }
+    if (attr.need(0)) cudaFuncSetAttribute(dec_linear_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dec_linear_kernel<float><<<grid, kDecThreads, smem, st>>>(a);
   } else {
-    if (!attr_done[1]) { cudaFuncSetAttribute(dec_linear_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done[1] = true; }
+    if (attr.need(1)) cudaFuncSetAttribute(dec_linear_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dec_linear_kernel<bf16><<<grid, kDecThreads, smem, st>>>(a);
   }
   return cudaGetLastError();
@@ -450,7 +450,7 @@ select_token_kernel(SelectArgs a) {
         const bool keep = (cum - p) <= a.top_p;
         float u;
         if (a.noise && launch < a.noise_rows) {
-          u = a.noise[((int64_t)launch * a.batch + b) * a.noise_ld + k];
+          u = a.noise[((int64_t)launch * a.noise_batch + b) * a.noise_ld + k];   // rows are laid out [launch][max_batch][top_k]
         } else {                                       // counter-based hash (splitmix64) keyed by (seed, launch, b, k)
           unsigned long long z = a.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(((int64_t)launch * a.batch + b) * 64 + k + 1);
           z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;

@@ -705,11 +705,10 @@ bool mega_supported(int batch, int first_n_new, int d, int ffn) {
 cudaError_t launch_decoder_mega(const MegaArgs& a, int w_dtype, int num_sms, cudaStream_t st) {
   const size_t smem = mega_smem_bytes(a.d, a.ffn, a.T, a.max_target);
   void* fn = w_dtype == kF32 ? (void*)decoder_mega_kernel<float> : (void*)decoder_mega_kernel<bf16>;
-  static bool done[2] = {false, false};
-  if (!done[w_dtype == kF32 ? 0 : 1]) {
+  static AttrOnce attr;
+  if (attr.need(w_dtype == kF32 ? 0 : 1)) {
     cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (r != cudaSuccess) return r;
-    done[w_dtype == kF32 ? 0 : 1] = true;
   }
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
   MegaArgs args = a;

@@ -1013,14 +1013,13 @@ cudaError_t launch_decoder_ring(const RingArgs& ra_in, const CUtensorMap& cross_
   void* fns[9] = {(void*)decoder_ring_kernel<1, false, true>,  (void*)decoder_ring_kernel<2, false, true>,  (void*)decoder_ring_kernel<4, false, true>,
                   (void*)decoder_ring_kernel<1, false, false>, (void*)decoder_ring_kernel<2, false, false>, (void*)decoder_ring_kernel<4, false, false>,
                   (void*)decoder_ring_kernel<1, true, false>,  (void*)decoder_ring_kernel<2, true, false>,  (void*)decoder_ring_kernel<4, true, false>};
-  static bool done[9] = {false, false, false, false, false, false, false, false, false};
+  static AttrOnce attr;
   if (dbg && ra_in.tc && ra_in.debug != 32) return cudaErrorInvalidValue;   // the instrumented build exists for the CUDA-core path only
   const int slot = (NR == 1 ? 0 : (NR == 2 ? 1 : 2)) + (ra_in.tc ? 0 : (dbg ? 6 : 3));
   void* fn = fns[slot];
-  if (!done[slot]) {
+  if (attr.need(slot)) {
     cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
     if (r != cudaSuccess) return r;
-    done[slot] = true;
   }
   RingArgs ra = ra_in;
   CUtensorMap tm = cross_map;

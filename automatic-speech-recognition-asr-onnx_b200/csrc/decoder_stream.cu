@@ -1103,9 +1103,11 @@ cudaError_t launch_decoder_stream(const StreamArgs& sa_in, const CUtensorMap& cr
                   (void*)decoder_stream_kernel<4, true>, (void*)decoder_stream_kernel<8, true>};
   const int slot = (nrt == 1 ? 0 : (nrt == 2 ? 1 : (nrt == 4 ? 2 : 3))) + (sa_in.m.timing ? 4 : 0);
   void* fn = fns[slot];
-  // the attribute is per device: set it on every launch (a host-side table lookup) rather than caching a process-wide flag
-  cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 3072);
-  if (r != cudaSuccess) return r;
+  static AttrOnce attr;
+  if (attr.need(slot)) {
+    cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 3072);
+    if (r != cudaSuccess) return r;
+  }
   StreamArgs sa = sa_in;
   CUtensorMap m0 = cross_map, m1 = kc_map, m2 = vc_map;
   void* params[] = {&m0, &m1, &m2, &sa};

@@ -346,6 +346,7 @@ int enqueue_decoder(b200asr_engine* e, const int* tokens_dev, int n_new, bool fi
   s.state = e->dstate; s.n_new = n_new;
   s.temperature = e->samp_temperature; s.top_k = e->samp_top_k; s.top_p = e->samp_top_p; s.rep_penalty = e->samp_rep;
   s.seed = e->samp_seed; s.noise = e->samp_noise; s.noise_ld = e->samp_noise_ld; s.noise_rows = e->samp_noise_rows;
+  s.noise_batch = e->cfg.max_batch;
   KL(launch_select_token(s, e->st));
   e->launches++;   // select = 2 kernels
   return B200ASR_OK;

@@ -352,11 +352,10 @@ bool gemm_tc_supported(const GemmArgs& g) {
 template <int BN>
 static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t st, std::string* err) {
   using Cfg = TcCfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static AttrOnce smem_attr;
+  if (smem_attr.need()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   CUtensorMap tmA, tmB;
   const bool a_batched = g.sAo != 0 && g.batch > 1;

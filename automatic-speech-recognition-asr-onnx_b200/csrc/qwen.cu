@@ -1237,11 +1237,10 @@ int qwen_attention_launch(b200asr_qwen* e, int layer, int rows, int n_new, bool 
 
 template <typename WT, int KS>
 cudaError_t qwen_gemv_launch_ks(const QGemvArgs& a, int num_sms, size_t smem, cudaStream_t st, bool pdl) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static AttrOnce attr;
+  if (attr.need()) {
     cudaFuncSetAttribute(qwen_gemv_kernel<WT, KS, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(qwen_gemv_kernel<WT, KS, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
   }
   const int cpb = (8 / KS) * 2;
   const int n_pass = (a.N + cpb - 1) / cpb;

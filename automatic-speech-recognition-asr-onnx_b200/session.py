@@ -190,9 +190,19 @@ class WhisperSessions:
     reference graphs: Whisper/Export_Whisper.py:432)."""
 
     def __init__(self, engine: WhisperEngine, metadata: Dict[str, str], *, strategy: str = "greedy",
-                 no_speech_token: Optional[int] = None, audio_dtype=np.int16):
+                 no_speech_token: Optional[int] = None, audio_dtype=np.int16, repeat_penalty: float = 1.0,
+                 penalty_range: int = 20, stop_ids: Sequence[int] = (), generate_limit: int = 0):
         if strategy not in ("greedy", "penalty_greedy"):
             raise ValueError("strategy must be 'greedy' or 'penalty_greedy'")
+        if strategy == "greedy" and repeat_penalty != 1.0:
+            raise ValueError("strategy 'greedy' has no penalty head; use strategy='penalty_greedy'")
+        # the penalty head of the merged graph takes its value / range as bound inputs every step
+        # (Inference_Whisper_ONNX.py:629-633); the engine applies them inside the decode kernel, so they are configured here
+        # and the bound tensors are checked against them in _run
+        self.repeat_penalty = float(repeat_penalty) if strategy == "penalty_greedy" else 1.0
+        self.penalty_range = int(penalty_range)
+        engine.set_decode_options(stop_ids=list(stop_ids), generate_limit=generate_limit, repeat_penalty=self.repeat_penalty,
+                                  penalty_range=self.penalty_range)
         self.engine = engine
         self.metadata = dict(metadata)
         self.strategy = strategy
@@ -317,6 +327,16 @@ class WhisperSessions:
                     raise ValueError(f"{n}: not the self-KV produced by this engine's previous launch")
         if int(feeds["decode_kv_seq_len"].numpy().reshape(-1)[0]) != self.kv_len:
             raise ValueError("decode_kv_seq_len does not match the resident cache length")
+        if self.strategy == "penalty_greedy":
+            # the driver binds penalty_on (value, range) once generated >= range and penalty_off (1.0) before that; the engine
+            # switches at the same step, so either the configured value or the neutral 1.0 is acceptable -- anything else
+            # would silently not be applied
+            pv = float(feeds["penalty_penalty_value"].numpy().reshape(-1)[0])
+            pr = int(feeds["penalty_penalty_range"].numpy().reshape(-1)[0])
+            if not (abs(pv - 1.0) < 1e-6 or abs(pv - self.repeat_penalty) < 1e-6):
+                raise ValueError(f"penalty_penalty_value {pv} differs from the configured repeat_penalty {self.repeat_penalty}")
+            if abs(pv - 1.0) >= 1e-6 and pr != self.penalty_range:
+                raise ValueError(f"penalty_penalty_range {pr} differs from the configured penalty_range {self.penalty_range}")
         _, tok = eng.decode_step(token_in=ids.reshape(-1), want_logits=False)
         self.kv_epoch += 1
         self.kv_len += 1
