@@ -236,6 +236,7 @@ struct StreamArgs {
   int n_stages, n_slots;               // ring stages (16 KB each); B-operand k-atom slots
   int task_inv;                        // inverse (mod grid) of the attention-task -> CTA stride
   int l2_hint;                         // 1: weight / KV boxes are loaded with an L2 evict-first policy
+  int multi;                           // 1: the m.first_n_new prompt positions of every clip run as rows of ONE iteration (single-iteration launch)
   int debug;
 };
 constexpr int kStreamMaxBatch = 8;

@@ -161,9 +161,9 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   unsigned short* s_xexp = reinterpret_cast<unsigned short*>(s_cnt + up16((size_t)n_cnt));
   float* s_cand = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_xexp) + up16((size_t)n_xexp * 2));   // [G][NRT][2]
   float* s_part = s_cand + (((size_t)G * NRT * 2 + 3) & ~(size_t)3);             // [8][68] per-warp (max, sum, o[64]) + [8*68] new-token score
-  float* s_qs = s_part + kStWorkerWarps * kStPartLd + 4;                         // [64]
+  float* s_qs = s_part + kStWorkerWarps * kStPartLd + 8;                         // [64]
   float* s_knv = s_qs + 64;                                                      // [2][64]
-  float* s_best = s_knv + 128;                                                   // [8][NRT][2]
+  float* s_best = s_knv + 1024;                                                  // [8][NRT][2]   (s_knv: [k | v][8 new positions][64])
   float* s_sc = s_best + kStWorkerWarps * NRT * 2 + ((4 - ((kStWorkerWarps * NRT * 2) & 3)) & 3);   // [8 warps][64] attention scores / probabilities
 
   __shared__ uint64_t full_bar[kStMaxStages], empty_bar[kStMaxStages];
@@ -178,8 +178,13 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KAd = d >> 6;                                  // k-atoms of a d-wide row
   const int n_first = a.first_n_new > 0 ? a.first_n_new : 1;
-  const int total_iters = a.n_iters + n_first - 1;         // leading forced (prompt) tokens, then n_iters heads
-  const int ntask = B * H;
+  // sa.multi: the n_first prompt positions of every utterance are processed together in ONE iteration, as NF "virtual
+  // utterances" per clip (row vu = utterance * NF + position; causal self-attention among a clip's rows).  Such a launch has
+  // a single iteration (the host follows it with a plain decode launch), so the row count is a launch constant.
+  const int NF = sa.multi ? n_first : 1;
+  const int R = B * NF;                                    // activation rows of this launch
+  const int total_iters = sa.multi ? 1 : a.n_iters + n_first - 1;   // otherwise: leading forced (prompt) tokens, then n_iters heads
+  const int ntask = R * H;
   const long long xreg = sa.set_words - (long long)L * sa.layer_words;   // residual-stream words + head statistics
   const int kv0 = a.state->kv_len;
   constexpr int kEpiWarps = NRT > 4 ? 8 : 4;
@@ -254,7 +259,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
       };
       for (int it = 0; it < total_iters && !stop; ++it) {
         const int kv = kv0 + it;
-        const bool head_on = it >= n_first - 1;
+        const bool head_on = sa.multi || it >= n_first - 1;
         for (int l = 0; l < L && !stop; ++l) {
           for (int ph = 0; ph < 8 && !stop; ++ph) {
             if (ph == 1) {                      // resident self-KV rows [0, kv) of my (utterance, head) tasks: K_i, V_i interleaved
@@ -269,7 +274,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                   if (clock64() - tw > kStSpin) st_timeout(7, need, s_prog);
               }
               for (int t = t0; t < ntask && !stop; t += G) {
-                const int b = t / H, h = t - b * H;
+                const int vu = t / H, h = t - vu * H, b = vu / NF;
                 const int row0 = ((l * B + b) * H + h) * a.max_target;
                 for (int g0 = 0; g0 < nb && !stop; g0 += 4) {          // groups of <= 4 boxes: the K boxes, then the matching V boxes
                   const int ge = min(nb, g0 + 4);
@@ -280,7 +285,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             } else if (ph == 4) {               // cross K / V of my tasks
               const int nb = (T + 127) >> 7;
               for (int t = first_task(l, 1, sa.task_inv); t < ntask && !stop; t += G) {
-                const int b = t / H, h = t - b * H;
+                const int vu = t / H, h = t - vu * H, b = vu / NF;
                 const int rk = (l * B + b) * T, rv = ((L + l) * B + b) * T;
                 for (int g0 = 0; g0 < nb && !stop; g0 += 4) {
                   const int ge = min(nb, g0 + 4);
@@ -346,7 +351,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
         swait(&step_bar, (uint32_t)(it & 1), 6);
         if (s_go == 2) break;
         const int kv = kv0 + it;
-        const bool head_on = it >= n_first - 1;
+        const bool head_on = sa.multi || it >= n_first - 1;
         for (int l = 0; l < L; ++l) {
           for (int ph = 0; ph < 8; ++ph) {
             if (ph == 1 || ph == 4) {             // attention stages are consumed by the workers: skip over them
@@ -374,7 +379,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
     constexpr int NG = kStWorkerWarps / NRT;             // slot groups
     constexpr int U = NRT <= 2 ? 1 : (NRT == 4 ? 2 : 4); // k-atoms a thread polls together
     constexpr int RR = NRT < 4 ? NRT : 4;                // utterances an epilogue thread handles
-    const bool row_ok = r_mine < B;
+    const bool row_ok = r_mine < R;
     const int q_tm = warp & 3;                           // TMEM lane quarter this warp may read
     const int set_tm = ww >> 2;                          // 0: utterances 0-3 (columns 0-7), 1: utterances 4-7 (columns 8-15)
     const bool epi_warp = ww < kEpiWarps;
@@ -394,15 +399,15 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
 
     for (int it = 0; it < total_iters; ++it) {
       const int kv = kv0 + it;
-      const bool head_on = it >= n_first - 1;
-      const bool begin_on = head_on && it == n_first - 1 && a.first_is_prefill && a.begin_bias != nullptr;
+      const bool head_on = sa.multi || it >= n_first - 1;
+      const bool begin_on = head_on && (sa.multi || it == n_first - 1) && a.first_is_prefill && a.begin_bias != nullptr;
       if (wt == 0) {
         int done = 1;
         for (int b = 0; b < B; ++b) done &= (s_fin[b] != 0);
         if (it < n_first && a.first_is_prefill) done = 0;          // the prefill always runs
         s_go = done ? 2 : 1;
       }
-      if (wt < B && it < n_first) s_tok[wt] = a.first_tokens[wt * n_first + it];
+      if (wt < R && it < n_first) s_tok[wt] = a.first_tokens[sa.multi ? wt : wt * n_first + it];
       wbar();
       if (wt == 0) mbar_arrive(&step_bar);
       if (s_go == 2) break;
@@ -444,12 +449,18 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           const int nb = (nvalid + 127) >> 7;
 #pragma unroll 1
           for (int t = first_task(l, kind, sa.task_inv); t < ntask; t += G) {
-            const int b = t / H, h = t - b * H;
-            if (wt < (kind ? 64 : 192)) {
-              const int which = wt >> 6, dd = wt & 63;
+            const int vu = t / H, h = t - vu * H;            // row (virtual utterance) and head
+            const int ub = vu / NF, pi = vu - ub * NF;       // clip and position within this launch's new rows
+            // q of my row, and (self-attention) k / v of the clip's new rows 0..pi: the causal part that is not in the cache yet
+            const int nitems = kind ? 64 : 64 + (pi + 1) * 128;
+#pragma unroll 1
+            for (int idx = wt; idx < nitems; idx += kStWorkers) {
+              const int e = idx - 64;
+              const int which = idx < 64 ? 0 : 1 + ((e >> 6) & 1), dd = idx & 63, j = idx < 64 ? pi : e >> 7;
+              const int row = ub * NF + j;
               const int n = which * d + h * 64 + dd;
-              const u64* p = lay + (kind ? (long long)NRT * 4 * d + (long long)b * d : (long long)b * 3 * d) + n;
-              const u64* stp = stats + (kind * NRT + b) * 2;
+              const u64* p = lay + (kind ? (long long)NRT * 4 * d + (long long)row * d : (long long)row * 3 * d) + n;
+              const u64* stp = stats + (kind * NRT + row) * 2;
               const unsigned ex = s_cnt[(l * 3 + kind) * sa.cnt_ld + (n >> 7)];
               const float wsn = (kind ? slr.cq_ws : slr.qkv_ws)[n], bn = (kind ? slr.cq_b : slr.qkv_b)[n];
               u64 w0, w1, wv;
@@ -467,9 +478,11 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                 s_qs[dd] = val;
               } else {
                 const bf16 hb = __float2bfloat16_rn(val);
-                bf16* cache = reinterpret_cast<bf16*>(which == 1 ? a.kcache : a.vcache);
-                cache[((((long long)l * B + b) * H + h) * a.max_target + kv) * 64 + dd] = hb;     // append for the later tokens
-                s_knv[(which - 1) * 64 + dd] = __bfloat162float(hb);
+                if (j == pi) {                               // my own position: append for the later tokens
+                  bf16* cache = reinterpret_cast<bf16*>(which == 1 ? a.kcache : a.vcache);
+                  cache[((((long long)l * B + ub) * H + h) * a.max_target + kv + pi) * 64 + dd] = hb;
+                }
+                s_knv[((which - 1) * 8 + j) * 64 + dd] = __bfloat162float(hb);
               }
             }
             wbar();
@@ -557,14 +570,17 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             float* pw = s_part + ww * kStPartLd;
             if (lane == 0) { pw[0] = m; pw[1] = lsum; }
             pw[4 + 2 * lane] = o0; pw[5 + 2 * lane] = o1;
-            if (kind == 0 && ww == 0) {                      // score of the new position
-              const float sn = warp_sum(fmaf(s_knv[lane], s_qs[lane], s_knv[lane + 32] * s_qs[lane + 32]));
-              if (lane == 0) s_part[kStWorkerWarps * kStPartLd] = sn;
+            if (kind == 0 && ww <= pi) {                     // warp j: score of new position j (j <= pi < 8 warps)
+              const float* kn = s_knv + ww * 64;
+              const float sn = warp_sum(fmaf(kn[lane], s_qs[lane], kn[lane + 32] * s_qs[lane + 32]));
+              if (lane == 0) s_part[kStWorkerWarps * kStPartLd + ww] = sn;
             }
             wbar();
             if (wt < 64) {
-              const float s_new = kind == 0 ? s_part[kStWorkerWarps * kStPartLd] : -INFINITY;
-              float M = s_new;
+              const int nnew = kind == 0 ? pi + 1 : 0;
+              float M = -INFINITY;
+#pragma unroll 1
+              for (int j = 0; j < nnew; ++j) M = fmaxf(M, s_part[kStWorkerWarps * kStPartLd + j]);
 #pragma unroll
               for (int w = 0; w < kStWorkerWarps; ++w) M = fmaxf(M, s_part[w * kStPartLd]);
               float Lt = 0.f, o = 0.f;
@@ -574,8 +590,12 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                 Lt = fmaf(e, s_part[w * kStPartLd + 1], Lt);
                 o = fmaf(e, s_part[w * kStPartLd + 4 + wt], o);
               }
-              if (kind == 0) { const float e = __expf(s_new - M); Lt += e; o = fmaf(e, s_knv[64 + wt], o); }
-              u64* dst = lay + (long long)NRT * (kind ? 5 : 3) * d + (long long)b * d + h * 64 + wt;
+#pragma unroll 1
+              for (int j = 0; j < nnew; ++j) {
+                const float e = __expf(s_part[kStWorkerWarps * kStPartLd + j] - M);
+                Lt += e; o = fmaf(e, s_knv[(8 + j) * 64 + wt], o);
+              }
+              u64* dst = lay + (long long)NRT * (kind ? 5 : 3) * d + (long long)vu * d + h * 64 + wt;
               st_w(dst, enc_fix(o / Lt, kFixScale));
             }
             if (kind == 0) asm volatile("fence.proxy.async;" ::: "memory");   // appended cache rows -> visible to later TMA reads
@@ -667,7 +687,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                 if (mode == 0) {
                   pa[u] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
                       reinterpret_cast<const bf16*>(a.embed) + (long long)s_tok[r_mine] * d + kk[u]));
-                  pb[u] = *reinterpret_cast<const float2*>(a.pos + (long long)kv * d + kk[u]);
+                  pb[u] = *reinterpret_cast<const float2*>(a.pos + (long long)(kv + r_mine % NF) * d + kk[u]);
                 } else if (mode >= 3) {
                   pa[u] = *reinterpret_cast<const float2*>(fold_ws + kk[u]);
                   if (mode == 3) pb[u] = *reinterpret_cast<const float2*>(fold_b + kk[u]);
@@ -755,7 +775,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
 #pragma unroll
                 for (int rr = 0; rr < RR; ++rr) {
                   const int rq = set_tm * 4 + rr;
-                  if (rq < B) x0v[rr] = a.pos[(long long)kv * d + n] +
+                  if (rq < R) x0v[rr] = a.pos[(long long)(kv + rq % NF) * d + n] +
                                         __bfloat162float(reinterpret_cast<const bf16*>(a.embed)[(long long)s_tok[rq] * d + n]);
                 }
               }
@@ -773,7 +793,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
 #pragma unroll
                 for (int rr = 0; rr < RR; ++rr) {
                   const int rq = set_tm * 4 + rr;
-                  if (rq < B) {
+                  if (rq < R) {
                     float val = v[2 * rr] + v[2 * rr + 1];
                     if (desig) val += bv + x0v[rr];
                     red_add(dst + (long long)rq * dst_ld + n, enc_fix(val, kFixScale));
@@ -802,7 +822,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
 #pragma unroll
           for (int rr = 0; rr < RR; ++rr) {
             const int rq = set_tm * 4 + rr;
-            if (rq < B) {
+            if (rq < R && rq % NF == NF - 1) {              // only a clip's last row feeds the head
               u64 w0, w1;
               long long t0 = 0;
               for (;;) {
@@ -837,15 +857,16 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
 #pragma unroll
               for (int rr = 0; rr < RR; ++rr) {
                 const int rq = set_tm * 4 + rr;
-                if (rq < B) {
+                if (rq < R && rq % NF == NF - 1) {
+                  const int ub = rq / NF;
                   float val = fmaf(rstd[rr], (v[2 * rr] + v[2 * rr + 1]) - mean[rr] * gn, btn);
                   if (pen_on) {
                     bool hit = false;
 #pragma unroll 1
-                    for (int qq = 0; qq < s_pen_n; ++qq) hit |= (s_pen[rq * 32 + qq] == n);
+                    for (int qq = 0; qq < s_pen_n; ++qq) hit |= (s_pen[ub * 32 + qq] == n);
                     if (hit) val *= a.penalty_value;
                   }
-                  if (a.logits) a.logits[(long long)rq * a.vocab + n] = val;
+                  if (a.logits) a.logits[(long long)ub * a.vocab + n] = val;
                   val += bg;
                   if (val > bvv[rr] || (val == bvv[rr] && n < bii[rr])) { bvv[rr] = val; bii[rr] = n; }
                 }
@@ -866,16 +887,17 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
             const int rq = set_tm * 4 + rr;
-            if (lane == 0 && rq < NRT) { s_best[(ww * NRT + rq) * 2] = bv; s_best[(ww * NRT + rq) * 2 + 1] = __int_as_float(bi); }
+            if (lane == 0 && rq < NRT) { s_best[(ww * NRT + rq) * 2] = bv; s_best[(ww * NRT + rq) * 2 + 1] = __int_as_float(bi); }   // by row
           }
         }
       }
       __threadfence();                                     // the zero stores of this step before the candidate goes out
       asm volatile("fence.proxy.async;" ::: "memory");    // cache rows appended this step, read by TMA in the next one
       wbar();
-      if (head_on && wt < NRT) {
-        for (int w = (wt >> 2) * 4; w < (wt >> 2) * 4 + 4; ++w) {
-          const float v = s_best[(w * NRT + wt) * 2]; const int i = __float_as_int(s_best[(w * NRT + wt) * 2 + 1]);
+      if (head_on && wt < B) {                             // utterance wt: its last row's candidates from the four warps that read it
+        const int rl = wt * NF + NF - 1;
+        for (int w = (rl >> 2) * 4; w < (rl >> 2) * 4 + 4; ++w) {
+          const float v = s_best[(w * NRT + rl) * 2]; const int i = __float_as_int(s_best[(w * NRT + rl) * 2 + 1]);
           if (v > cv || (v == cv && i < ci)) { cv = v; ci = i; }
         }
       }
@@ -962,7 +984,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
     if (blockIdx.x == 0 && wt == 0) {
       int done = 1;
       for (int b = 0; b < B; ++b) done &= (s_fin[b] != 0);
-      a.state->kv_len = kv0 + it_done; a.state->step = step; a.state->all_done = done;
+      a.state->kv_len = kv0 + it_done * NF; a.state->step = step; a.state->all_done = done;
     }
   }
   tc_fence_before();
@@ -1082,7 +1104,7 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
     auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t fixed = 1024 /*alignment*/ + (size_t)max_slots * kStSlot + (size_t)n_sched * 16 + up16((size_t)n_cnt) +
                          up16((size_t)n_xexp * 2) +
-                         4 * ((((size_t)G * nrt * 2 + 3) & ~(size_t)3) + kStWorkerWarps * kStPartLd + 4 + 64 + 128 + (size_t)kStWorkerWarps * nrt * 2 + 16 + kStWorkerWarps * 64 + 4);
+                         4 * ((((size_t)G * nrt * 2 + 3) & ~(size_t)3) + kStWorkerWarps * kStPartLd + 8 + 64 + 1024 + (size_t)kStWorkerWarps * nrt * 2 + 16 + kStWorkerWarps * 64 + 4);
     const size_t budget = 227 * 1024 - 3072;           // static __shared__ + slack
     if (fixed + 6 * (size_t)kStStage > budget) return false;   // an attention group holds up to 4 key boxes before releasing any
     int ns = (int)((budget - fixed) / kStStage);

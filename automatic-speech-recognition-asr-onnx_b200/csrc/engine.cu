@@ -86,12 +86,12 @@ struct b200asr_engine {
    bool ring_fine = false; int ring_debug = 0; unsigned long long* ring_ll = nullptr; size_t ring_ll_words = 0;
   CUtensorMap cross_map{}; int cmap_B = -1, cmap_T = -1, cmap_rows = -1; int ring_task_inv = 0;
   // split-K tensor-core streaming decode kernel (decoder_stream.cu): the product path for prefill + greedy loop
-  bool use_stream = true; bool stream_l2_hint = true; int stream_debug = 0;
+  bool use_stream = true; bool stream_l2_hint = true; int stream_debug = 0; bool stream_multi = true;
   StreamLayer* st_layers = nullptr; CUtensorMap* st_wmaps = nullptr; float* st_fold = nullptr;   // fold vectors (row sums, head g / b)
   float* st_head_g = nullptr; float* st_head_b = nullptr;
   unsigned long long* st_acc = nullptr; size_t st_acc_words = 0; unsigned long long* st_cand = nullptr; size_t st_cand_words = 0;
   int4* st_sched = nullptr; unsigned char* st_cnt = nullptr; unsigned short* st_xexp = nullptr;
-  StreamPlan st_plan{}; int st_plan_B = -1, st_plan_T = -1;
+  StreamPlan st_plans[4]; bool st_plan_ok[4] = {false, false, false, false}; bool st_tables = false;   // one plan per row-count class (1, 2, 4, 8)
   CUtensorMap st_cross{}, st_kc{}, st_vc{}; int st_map_B = -1, st_map_T = -1;
   std::string graph_key;
 
@@ -528,13 +528,14 @@ bool stream_ok(b200asr_engine* e) {
   const b200asr_config& c = e->cfg;
   if (!e->use_stream || e->samp_temperature > 0.f || e->act_dtype != kBF16 || e->penalty_range > 32) return false;
   if (!stream_supported(e->B, c.d_model, c.ffn, c.n_heads, c.vocab, e->T_enc, e->num_sms)) return false;
-  if (e->st_plan_B == e->B && e->st_plan_T == e->T_enc) return true;
+  const int slot = e->B <= 1 ? 0 : (e->B <= 2 ? 1 : (e->B <= 4 ? 2 : 3));
+  if (e->st_plan_ok[slot]) return true;
   StreamPlan pl;
   return stream_plan(e->B, c.d_model, c.ffn, c.n_heads, c.vocab, c.dec_layers, e->T_enc, c.max_target, e->num_sms, &pl,
                      nullptr, nullptr, nullptr);
 }
 
-int build_stream_tables(b200asr_engine* e) {
+int build_stream_tables(b200asr_engine* e, int rows) {
   const b200asr_config& c = e->cfg;
   const int L = c.dec_layers, d = c.d_model, f = c.ffn;
   if (!e->st_layers) {
@@ -572,19 +573,23 @@ int build_stream_tables(b200asr_engine* e) {
     for (int i = 1; i < e->num_sms; ++i) if ((i * kRingTaskMul) % e->num_sms == 1) inv = i;
     e->ring_task_inv = inv;
   }
-  if (e->st_plan_B != e->B || e->st_plan_T != e->T_enc) {
+  const int slot = rows <= 1 ? 0 : (rows <= 2 ? 1 : (rows <= 4 ? 2 : 3));
+  if (!e->st_plan_ok[slot]) {
+    // the schedule tables depend on the model dimensions only; the plan (shared-memory split, accumulator sizes) on the row class
     std::vector<int4> sched; std::vector<unsigned char> cnt; std::vector<unsigned short> xexp;
     StreamPlan pl;
-    if (!stream_plan(e->B, d, f, c.n_heads, c.vocab, L, e->T_enc, c.max_target, e->num_sms, &pl, &sched, &cnt, &xexp))
+    if (!stream_plan(rows, d, f, c.n_heads, c.vocab, L, e->T_enc, c.max_target, e->num_sms, &pl, &sched, &cnt, &xexp))
       return e->fail(B200ASR_E_INVALID, "decoder_stream: plan does not fit");
     CK(cudaStreamSynchronize(e->st));
-    if (e->st_sched) { cudaFree(e->st_sched); cudaFree(e->st_cnt); cudaFree(e->st_xexp); }
-    CK(cudaMalloc(&e->st_sched, sched.size() * sizeof(int4)));
-    CK(cudaMalloc(&e->st_cnt, cnt.size() + 16));
-    CK(cudaMalloc(&e->st_xexp, xexp.size() * 2 + 16));
-    CK(b200_copy_sync(e, e->st_sched, sched.data(), sched.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    CK(b200_copy_sync(e, e->st_cnt, cnt.data(), cnt.size(), cudaMemcpyHostToDevice));
-    CK(b200_copy_sync(e, e->st_xexp, xexp.data(), xexp.size() * 2, cudaMemcpyHostToDevice));
+    if (!e->st_tables) {
+      CK(cudaMalloc(&e->st_sched, sched.size() * sizeof(int4)));
+      CK(cudaMalloc(&e->st_cnt, cnt.size() + 16));
+      CK(cudaMalloc(&e->st_xexp, xexp.size() * 2 + 16));
+      CK(b200_copy_sync(e, e->st_sched, sched.data(), sched.size() * sizeof(int4), cudaMemcpyHostToDevice));
+      CK(b200_copy_sync(e, e->st_cnt, cnt.data(), cnt.size(), cudaMemcpyHostToDevice));
+      CK(b200_copy_sync(e, e->st_xexp, xexp.data(), xexp.size() * 2, cudaMemcpyHostToDevice));
+      e->st_tables = true;
+    }
     const size_t words = (size_t)pl.set_words * 2;
     if (words > e->st_acc_words) {
       if (e->st_acc) cudaFree(e->st_acc);
@@ -596,7 +601,7 @@ int build_stream_tables(b200asr_engine* e) {
       CK(cudaMalloc(&e->st_cand, pl.cand_words * 8));
       e->st_cand_words = pl.cand_words;
     }
-    e->st_plan = pl; e->st_plan_B = e->B; e->st_plan_T = e->T_enc;
+    e->st_plans[slot] = pl; e->st_plan_ok[slot] = true;
   }
   if (e->st_map_B != e->B || e->st_map_T != e->T_enc) {
     std::string msg;
@@ -613,21 +618,37 @@ int build_stream_tables(b200asr_engine* e) {
 
 // one cooperative launch: n_first forced tokens per utterance ([B][n_first] on device; the last one feeds the first head),
 // then n_heads - 1 further greedy iterations.  first_is_prefill: the first head applies the begin-suppress bias.
-int run_stream(b200asr_engine* e, int n_heads_iters, const int* first_tokens, int n_first, bool first_is_prefill, bool want_logits) {
-  RET(build_stream_tables(e));
+static int launch_stream(b200asr_engine* e, int rows, int n_heads_iters, const int* first_tokens, int n_first, bool first_is_prefill,
+                         bool want_logits, bool multi) {
+  RET(build_stream_tables(e, rows));
+  const int slot = rows <= 1 ? 0 : (rows <= 2 ? 1 : (rows <= 4 ? 2 : 3));
+  const StreamPlan& pl = e->st_plans[slot];
   StreamArgs sa{};
   fill_mega_args(e, sa.m, n_heads_iters, first_tokens, n_first, first_is_prefill, want_logits);
   RET(arm_timing(e, sa.m));
-  const StreamPlan& pl = e->st_plan;
   sa.sl = e->st_layers; sa.wmaps = e->st_wmaps; sa.head_g = e->st_head_g; sa.head_b = e->st_head_b;
   sa.acc = e->st_acc; sa.set_words = pl.set_words; sa.layer_words = pl.layer_words;
   sa.cand = e->st_cand; sa.sched = e->st_sched; sa.cnt = e->st_cnt; sa.xexp = e->st_xexp;
   sa.cnt_ld = pl.cnt_ld; sa.xt = pl.xt; sa.n_stages = pl.n_stages; sa.n_slots = pl.n_slots;
-  sa.task_inv = e->ring_task_inv; sa.l2_hint = e->stream_l2_hint ? 1 : 0; sa.debug = e->stream_debug;
+  sa.task_inv = e->ring_task_inv; sa.l2_hint = e->stream_l2_hint ? 1 : 0; sa.debug = e->stream_debug; sa.multi = multi ? 1 : 0;
   CK(cudaMemsetAsync(e->st_acc, 0, (size_t)pl.set_words * 2 * 8, e->st));
   CK(cudaMemsetAsync(e->st_cand, 0, pl.cand_words * 8, e->st));
   KL(launch_decoder_stream(sa, e->st_cross, e->st_kc, e->st_vc, pl.nrt, e->num_sms, pl.smem_bytes, e->st));
   return B200ASR_OK;
+}
+
+// n_first forced tokens per utterance ([B][n_first] on device; the last one feeds the first head), then n_heads - 1 further
+// greedy iterations.  first_is_prefill: the first head applies the begin-suppress bias.  When the prompt rows of all clips fit
+// the kernel's 8 activation rows, they run together as one multi-row iteration (its own launch), followed by a decode launch;
+// otherwise the prompt is fed token by token inside a single launch.
+int run_stream(b200asr_engine* e, int n_heads_iters, const int* first_tokens, int n_first, bool first_is_prefill, bool want_logits) {
+  const int B = e->B;
+  if (n_first > 1 && B * n_first <= kStreamMaxBatch && e->stream_multi) {
+    RET(launch_stream(e, B * n_first, 1, first_tokens, n_first, first_is_prefill, want_logits, true));
+    if (n_heads_iters > 1) RET(launch_stream(e, B, n_heads_iters - 1, e->cur_token, 1, false, want_logits, false));
+    return B200ASR_OK;
+  }
+  return launch_stream(e, B, n_heads_iters, first_tokens, n_first, first_is_prefill, want_logits, false);
 }
 
 int do_upload(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples) {
@@ -748,6 +769,7 @@ int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "stream")) { e->use_stream = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "stream_l2_hint")) { e->stream_l2_hint = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "stream_debug")) { e->stream_debug = (int)value; return B200ASR_OK; }
+  if (!strcmp(key, "stream_multi")) { e->stream_multi = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring")) { e->use_ring = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_tc")) { e->ring_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_debug")) { e->ring_debug = (int)value; return B200ASR_OK; }
@@ -1188,7 +1210,7 @@ int b200asr_get_stage(b200asr_engine* e, const char* name_c, float* out, int64_t
     for (size_t i = 1; i < ht.size() && ht[i] != 0 && n < capacity; ++i) out[n++] = (float)((double)(ht[i] - ht[i - 1]) * 1e-3);
   } else if (name == "stream_acc_val" || name == "stream_acc_cnt") {   // debug: decoded accumulator words of both step sets
     if (!e->st_acc) return e->fail(B200ASR_E_INVALID, "the streaming decode kernel has not run");
-    n = (int64_t)e->st_plan.set_words * 2;
+    n = (int64_t)e->st_acc_words;
     if (n > capacity) return e->fail(B200ASR_E_INVALID, "stage buffer too small");
     std::vector<unsigned long long> hw((size_t)n);
     CK(b200_copy_sync(e, hw.data(), e->st_acc, (size_t)n * 8, cudaMemcpyDeviceToHost));

@@ -93,18 +93,23 @@ def test_stream_batch(nb):
     assert out[1][1] == out[0][1]
 
 
+@pytest.mark.parametrize("multi", [0, 1])
 @pytest.mark.parametrize("nb", [2, 4, 8])
-def test_stream_batch_equals_single_exactly(nb):
+def test_stream_batch_equals_single_exactly(nb, multi):
+    """A clip's logits do not depend on its batch mates: bit-identical when both runs prefill the same way (multi = 0: the
+    prompt token by token); with the multi-row prefill (default) a batch of 4+ clips prefills token by token while a single
+    clip prefills its 4 rows together, which only changes the order the new positions' scores are summed in (<= 2e-4)."""
     g, raw, tensors = load_case(GOLD[1])
     n = 24160
     clips = np.stack([synth_pcm(30 + i, n) for i in range(nb)])
     forced = g["forced_tokens"].tolist()[:4]
     eng = _mk(tensors, 1, max_batch=nb)
+    eng.set_option("stream_multi", multi)
     lb = _forced(eng, clips, g["prompt"], forced)
     singles = np.concatenate([_forced(eng, clips[i], g["prompt"], forced) for i in range(nb)], axis=0)
     d = maxdiff(lb, singles)
-    print(f"stream batch {nb} vs single max |dlogit| =", d)
-    assert d == 0.0
+    print(f"stream batch {nb} vs single (multi-row prefill {multi}) max |dlogit| =", d)
+    assert d == 0.0 if multi == 0 else d <= 2e-4
     eng.close()
 
 
@@ -115,3 +120,27 @@ def test_stream_is_reproducible():
     b = _forced(eng, g["pcm"], g["prompt"], g["forced_tokens"].tolist())
     assert maxdiff(a, b) == 0.0
     eng.close()
+
+
+@pytest.mark.parametrize("nb", [1, 2, 3])
+def test_stream_multi_row_prefill_equals_token_by_token(nb):
+    """The prompt rows of all clips as one multi-row iteration (rows = clips x prompt length <= 8; three clips fall back to the
+    token-by-token prefill) against feeding the prompt one token per iteration: same arithmetic per row except the order in
+    which the new positions' scores are summed, so logits agree to 1e-4 and the streams are identical."""
+    g, raw, tensors = load_case(GOLD[1])
+    n = 24160
+    clips = np.stack([synth_pcm(40 + i, n) for i in range(nb)])
+    forced = g["forced_tokens"].tolist()[:3]
+    out = {}
+    for multi in (1, 0):
+        eng = _mk(tensors, 1, max_batch=nb)
+        eng.set_option("stream_multi", multi)
+        lg = _forced(eng, clips, g["prompt"], forced)
+        eng.set_decode_options(stop_ids=[], generate_limit=8)
+        toks = eng.transcribe(clips, g["prompt"], max_new=8)
+        out[multi] = (lg, toks)
+        eng.close()
+    d = maxdiff(out[1][0], out[0][0])
+    print(f"batch {nb}: multi-row vs token-by-token prefill max |dlogit| =", d)
+    assert d <= 1e-4
+    assert out[1][1] == out[0][1]

@@ -14,6 +14,7 @@ d, f, H, L, V = dims.d_model, dims.ffn, dims.n_heads, dims.dec_layers, dims.voca
 eng.encode(g["pcm"])
 T = eng.T_enc
 eng.set_decode_options(stop_ids=[])
+eng.set_option("stream_multi", 0)        # this tool reads the one-row accumulator layout
 NTOK = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 toks = [int(t) for t in g["prompt"].reshape(-1)[:NTOK]]
 logits, first = eng.prefill(np.array([toks], np.int32))
