@@ -115,7 +115,12 @@ int b200asr_transcribe_resident(b200asr_engine* e, const int32_t* prompt_ids, in
  * "cross_k"/"cross_v" [B][L][H][T_enc][64], "self_k"/"self_v" [L][B][H][kv][64].
  * Returns the number of floats written through *numel_out. */
 int b200asr_get_stage(b200asr_engine* e, const char* name, float* out, int64_t capacity, int64_t* numel_out);
-/* options: "keep_stages" (0/1) keeps a copy of the conv-stem output for get_stage("stem") */
+/* options: "keep_stages" (0/1) keeps a copy of the conv-stem output for get_stage("stem");
+ * decoder kernel selection (bf16 mode; all default 1): "stream" = the split-K tensor-core streaming kernel (prefill + greedy loop,
+ * batch <= 8), "stream_multi" = prompt rows of all clips as one multi-row prefill iteration, "stream_l2_hint" = L2 evict-first
+ * policy on the streamed boxes; with "stream" 0: "ring" = round 1's CUDA-core streaming kernel (batch <= 4), else "mega" = the
+ * grid-barrier kernel, else the per-op CUDA graph.  "mega_timing" 1 selects the instrumented build (per-phase stamps, read back
+ * with get_stage("mega_timing")). */
 int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value);
 void* b200asr_stream(b200asr_engine* e);                 /* cudaStream_t of the engine */
 int b200asr_synchronize(b200asr_engine* e);
