@@ -40,7 +40,7 @@ namespace b200asr {
 
 constexpr int kStWorkerWarps = 8;
 constexpr int kStWorkers = kStWorkerWarps * 32;       // 256
-constexpr int kStThreads = kStWorkers + 64;           // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: workers
+constexpr int kStThreads = kStWorkers + 96;           // warp 0: TMA producer, warp 1: MMA lane 0, warps 2..9: workers, warp 10: MMA lane 1
 constexpr int kStStage = 16384;                       // one atom / one 128-row K or V box
 constexpr int kStMaxStages = 12;
 constexpr int kStSlot = 2048;                         // B operand of one k-atom: 16 rows x 128 bytes
@@ -192,7 +192,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); box_cnt[s] = 0; }
     mbar_init(&b_ready, kStWorkers);
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 2); mbar_init(&acc_empty[s], kEpiWarps); }
     mbar_init(&step_bar, 1);
     mbar_fence_init();
     prefetch_tensormap(&cross_map); prefetch_tensormap(&kc_map); prefetch_tensormap(&vc_map);
@@ -212,7 +212,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
 #pragma unroll 1
     for (int j = max(0, ns - 32); j < ns; ++j) s_hist[tid * 32 + (j & 31)] = a.save_id[(long long)tid * a.save_ld + j];
   }
-  if (warp == 1) tmem_alloc(&tmem_slot, 32u);
+  if (warp == 1) tmem_alloc(&tmem_slot, 64u);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -310,9 +310,9 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 10) {
     // =======================================================================
-    // MMA issuer: one lane; D[128 weight rows][16] (+)= A[128][64] (ring stage) . B[16][64] (activation slot)
+    // MMA issuers: two lanes (warps 1 and 10) on alternate atoms of the CTA's run, each with its own accumulator; D[128 weight rows][16] (+)= A[128][64] (ring stage) . B[16][64] (activation slot)
     // =======================================================================
     if (lane == 0) {
       constexpr uint32_t idesc = idesc_bf16(128, 16);
@@ -320,37 +320,43 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
       uint32_t bpar = 0;
       int tctr = 0;
       const uint32_t ring_u = smem_u32(ring), bbuf_u = smem_u32(bbuf);
+      const int ml = warp == 10;                          // my lane: atoms whose offset in the run has my parity
       auto linear = [&](int4 r, int KA) {
-        // everything that does not depend on this phase's activations happens before the wait for them: the weight stages
-        // of the phase (streamed ahead by the producer) and the first accumulator buffer are confirmed here, so the section
+        // everything that does not depend on this phase's activations happens before the wait for them: my weight stages of
+        // the phase (streamed ahead by the producer) and the first accumulator buffer are confirmed here, so the section
         // between "B operand staged" and "accumulator ready" is MMA issue only (measured: 0.91 -> 0.86 ms per step)
         const int npre = min(r.y - r.x, NS - 2);           // (the head's tiles exceed the ring: the rest is confirmed in the loop)
         {
           RingPos q = p;
-          for (int i = 0; i < npre; ++i) { swait(&full_bar[q.stage], q.phase, 5); ring_adv(q, 1, NS); }
+          for (int i = 0; i < npre; ++i) { if ((i & 1) == ml) swait(&full_bar[q.stage], q.phase, 5); ring_adv(q, 1, NS); }
           if (r.x < r.y) swait(&acc_empty[tctr & 1], (uint32_t)(((tctr >> 1) & 1) ^ 1), 4);
         }
         swait(&b_ready, bpar, 3); bpar ^= 1u;
         tc_fence_after();
         int ka = r.w;
-        bool fresh = true;
+        bool tile_start = true, fresh = true;
         for (int at = r.x; at < r.y; ++at) {
           const int buf = tctr & 1;
-          if (fresh && at != r.x) { swait(&acc_empty[buf], (uint32_t)(((tctr >> 1) & 1) ^ 1), 4); tc_fence_after(); }
-          if (at - r.x >= npre) { swait(&full_bar[p.stage], p.phase, 5); tc_fence_after(); }
-          int slot = ka - r.w; if (slot < 0) slot += KA;
-          const uint64_t adesc = smem_desc_sw128(ring_u + (uint32_t)p.stage * kStStage);
-          const uint64_t bdesc = smem_desc_sw128(bbuf_u + (uint32_t)slot * kStSlot);
+          if (tile_start && at != r.x) { swait(&acc_empty[buf], (uint32_t)(((tctr >> 1) & 1) ^ 1), 4); tc_fence_after(); }
+          tile_start = false;
+          if (((at - r.x) & 1) == ml) {
+            if (at - r.x >= npre) { swait(&full_bar[p.stage], p.phase, 5); tc_fence_after(); }
+            int slot = ka - r.w; if (slot < 0) slot += KA;
+            const uint64_t adesc = smem_desc_sw128(ring_u + (uint32_t)p.stage * kStStage);
+            const uint64_t bdesc = smem_desc_sw128(bbuf_u + (uint32_t)slot * kStSlot);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem + (uint32_t)(buf * 16), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (fresh && k == 0) ? 0u : 1u);
-          fresh = false;
-          tc_commit(&empty_bar[p.stage]);
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(tmem + (uint32_t)(buf * 32 + ml * 16), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (fresh && k == 0) ? 0u : 1u);
+            fresh = false;
+            tc_commit(&empty_bar[p.stage]);
+          }
           ring_adv(p, 1, NS);
           ++ka;
           if (ka == KA || at + 1 == r.y) {
-            tc_commit(&acc_full[buf]);
-            ++tctr; fresh = true;
+            // my MMAs of this tile are tracked by the commit; a lane that had no atom in the tile just arrives (the epilogue
+            // skips its accumulator: same parity rule)
+            if (!fresh) tc_commit(&acc_full[buf]); else mbar_arrive(&acc_full[buf]);
+            ++tctr; fresh = true; tile_start = true;
             if (ka == KA) ka = 0;
           }
         }
@@ -812,8 +818,17 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             swait(&acc_full[buf], (uint32_t)((tctr >> 1) & 1), 20);     // every worker: the B slots are free again after this
             if (epi_warp) {
               tc_fence_after();
-              float v[8];
-              tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 16 + set_tm * 8), v);
+              // the tile's atoms alternate between the two MMA lanes' accumulators; a lane without an atom in this tile left its
+              // accumulator untouched
+              const int o0 = at - r.x, nt = tend - at;
+              const bool use0 = nt >= 2 || (o0 & 1) == 0, use1 = nt >= 2 || (o0 & 1) == 1;
+              float v[8], v1[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j] = 0.f; v1[j] = 0.f; }
+              if (use0) tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + set_tm * 8), v);
+              if (use1) tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + 16 + set_tm * 8), v1);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += v1[j];
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -876,8 +891,13 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           swait(&acc_full[buf], (uint32_t)((tctr >> 1) & 1), 42);
           if (epi_warp) {
             tc_fence_after();
-            float v[8];
-            tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 16 + set_tm * 8), v);
+            float v[8], v1[8];                               // head tiles are whole (KAd >= 2 atoms): both lanes contribute
+            tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + set_tm * 8), v);
+            if (KAd >= 2) {
+              tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + 16 + set_tm * 8), v1);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += v1[j];
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -1019,7 +1039,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 32u);
+    tmem_dealloc(tmem, 64u);
   }
 }
 
