@@ -167,13 +167,16 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   float* s_sc = s_best + kStWorkerWarps * NRT * 2 + ((4 - ((kStWorkerWarps * NRT * 2) & 3)) & 3);   // [8 warps][64] attention scores / probabilities
 
   __shared__ uint64_t full_bar[kStMaxStages], empty_bar[kStMaxStages];
-  __shared__ uint64_t b_ready, acc_full[2], acc_empty[2], step_bar;
+  __shared__ uint64_t b_ready, acc_full[2], acc_empty[2];
   __shared__ int box_cnt[kStMaxStages];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_tok[8], s_ngen[8], s_fin[8], s_nsave[8];
   __shared__ int s_pen[8 * 32], s_hist[8 * 32];
   __shared__ int s_pen_n;
   __shared__ volatile int s_go, s_stop, s_prog;      // s_prog: self-attention phases this CTA has completed (it * L + l + 1)
+  // monotonic hand-off of the step loop to the MMA lanes (a parity barrier would alias: on a CTA without atoms nothing else
+  // keeps the workers from running two steps ahead of an MMA lane): steps started so far, and the iteration the loop ended at
+  __shared__ volatile int s_step, s_break_it;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KAd = d >> 6;                                  // k-atoms of a d-wide row
@@ -192,11 +195,10 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); box_cnt[s] = 0; }
     mbar_init(&b_ready, kStWorkers);
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 2); mbar_init(&acc_empty[s], kEpiWarps); }
-    mbar_init(&step_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 2); mbar_init(&acc_empty[s], kStWorkerWarps); }
     mbar_fence_init();
     prefetch_tensormap(&cross_map); prefetch_tensormap(&kc_map); prefetch_tensormap(&vc_map);
-    s_stop = 0; s_go = 0; s_prog = 0;
+    s_stop = 0; s_go = 0; s_prog = 0; s_step = 0; s_break_it = 0x7fffffff;
   }
 #pragma unroll 1
   for (int i = tid; i < n_sched; i += kStThreads) s_sched[i] = sa.sched[(size_t)blockIdx.x * n_sched + i];
@@ -331,6 +333,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           for (int i = 0; i < npre; ++i) { if ((i & 1) == ml) swait(&full_bar[q.stage], q.phase, 5); ring_adv(q, 1, NS); }
           if (r.x < r.y) swait(&acc_empty[tctr & 1], (uint32_t)(((tctr >> 1) & 1) ^ 1), 4);
         }
+        if (r.x >= r.y) return;                            // no atoms of this phase here: no hand-shake either (workers skip it too)
         swait(&b_ready, bpar, 3); bpar ^= 1u;
         tc_fence_after();
         int ka = r.w;
@@ -362,8 +365,12 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
         }
       };
       for (int it = 0; it < total_iters; ++it) {
-        swait(&step_bar, (uint32_t)(it & 1), 6);
-        if (s_go == 2) break;
+        {
+          const long long t0 = clock64();
+          while (s_step <= it && s_break_it > it)
+            if (clock64() - t0 > kStSpin) st_timeout(6, it, s_step);
+          if (s_break_it <= it) break;
+        }
         const int kv = kv0 + it;
         const bool head_on = sa.multi || it >= n_first - 1;
         for (int l = 0; l < L; ++l) {
@@ -423,7 +430,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
       }
       if (wt < R && it < n_first) s_tok[wt] = a.first_tokens[sa.multi ? wt : wt * n_first + it];
       wbar();
-      if (wt == 0) mbar_arrive(&step_bar);
+      if (wt == 0) { if (s_go == 2) s_break_it = it; else s_step = it + 1; }
       if (s_go == 2) break;
       u64* set = sa.acc + (size_t)(it & 1) * sa.set_words;
       u64* oset = sa.acc + (size_t)((it + 1) & 1) * sa.set_words;
@@ -780,8 +787,10 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               *reinterpret_cast<__nv_bfloat162*>(slotp + (rl >> 3) * 1024 + (rl & 7) * 128 + ((chunk ^ (rl & 7)) << 4) + within) = lo;
             }
           }
-          fence_proxy_async_smem();
-          mbar_arrive(&b_ready);
+          if (nat > 0) {                                     // phases without atoms here have no MMA side to hand over to
+            fence_proxy_async_smem();
+            mbar_arrive(&b_ready);
+          }
           // statistics after the MMA has been released: the readers need them one phase later.  One RED pair per warp,
           // counting the k-atoms it covers (nstat is warp-uniform)
           if (nstat) {
@@ -844,6 +853,9 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                 }
               }
             }
+            // every worker warp releases the buffer (not only the ones that read it): a warp that merely waited could otherwise be
+            // lapped by two more tiles on the same buffer and wait on an aliased parity
+            if (!epi_warp) { __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
             ++tctr; at = tend; ++tile;
           }
           ring_adv(pos, r.y - r.x, NS);
@@ -921,6 +933,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               }
             }
           }
+          if (!epi_warp) { __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
           ++tctr;
         }
         ring_adv(pos, r.y - r.x, NS);

@@ -40,8 +40,8 @@ def test_shortest_clips_match_oracle(n_samples):
 
 
 def test_thirty_second_clip_beyond_fused_attention_limit():
-    """T_enc = 1500 > 448: the encoder falls back to the unfused attention products, the streaming decoder walks ten
-    K/V boxes per head; bf16 against the fp32 parity mode of the same engine."""
+    """T_enc = 1500 > 448: the encoder's attention runs the two-pass streaming tcgen05 kernel (round 1: unfused CUDA-core
+    products), the streaming decoder walks twelve K/V boxes per head; bf16 against the fp32 parity mode of the same engine."""
     g, raw, tensors = load_case(GOLD[0])
     pcm = synth_pcm(5, 480000)
     out = {}

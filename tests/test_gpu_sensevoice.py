@@ -86,14 +86,15 @@ def test_sensevoice_batch_and_language_selector():
     eng.close()
 
 
-@pytest.mark.parametrize("n_samples", [40000, 83000, 123520, 240000])
+@pytest.mark.parametrize("n_samples", [40000, 83000, 123520, 240000, 255000, 330000, 480000])
 def test_sensevoice_bf16_head128_fused_attention(n_samples):
     """Production head width (128 = two swizzle tiles per operand in attention_tc.cu) on a two-head model: the fused
     tcgen05 attention against the three-launch CUDA-core path of the same engine (3e-2 on O(1) LayerNorm outputs, the
     two differ in where P is normalised) and against the fp32 oracle (0.12, the bf16 bound of this file).  The clip
-    lengths put T below one 128-key box, at a non-multiple of 16, across the box edge and near the 256-key limit."""
+    lengths put T below one 128-key box, at a non-multiple of 16, across the box edge, near the 256-key limit of the
+    single-pass kernel, and beyond it (two-pass streaming kernel: 269, 347 and 504 positions)."""
     import dataclasses
-    maxs = 245000
+    maxs = max(245000, n_samples)       # beyond 256 positions the 128-wide heads take the two-pass streaming kernel (30 s = 504)
     dims = dataclasses.replace(D, d_model=256, n_heads=2, ffn=512)
     odims = dataclasses.replace(so.TINY_TEST, d_model=256, n_heads=2, ffn=512)
     assert dims.head_dim == 128
