@@ -70,6 +70,7 @@ struct b200asr_engine {
   std::vector<int> stop_ids; int limit = 0; int limit_cfg = 0; float repeat_penalty = 1.0f; int penalty_range = 20;
   int n_prompt = 0; bool prefilled = false; bool encoded = false;
   cudaGraphExec_t step_graph = nullptr; int64_t step_graph_nodes = 0;
+  cudaGraphExec_t enc_graph = nullptr; int64_t enc_graph_nodes = 0; std::string enc_graph_key; bool use_enc_graph = true;
   // persistent decoder kernel state
   bool use_mega = true; long long pf_ahead = 0;
   MegaLayer* mega_layers = nullptr; PfBlock* pf_blocks = nullptr; int n_pf_blocks = 0; long long pf_total = 0;
@@ -200,7 +201,7 @@ GemmArgs linear_args(b200asr_engine* e, const void* A, int64_t lda, const std::s
   return g;
 }
 
-int run_encoder(b200asr_engine* e) {
+int enqueue_encoder(b200asr_engine* e) {
   const b200asr_config& c = e->cfg;
   const int B = e->B, d = c.d_model, H = c.n_heads, Tm = e->T_mel, T = e->T_enc, L = c.dec_layers;
   const int M = B * T;
@@ -278,6 +279,37 @@ int run_encoder(b200asr_engine* e) {
     GemmArgs g = linear_args(e, e->xhat, d, "enc.cross_kv.w", "enc.cross_kv.b", e->cross_kv, d, ad, M, d, d);
     g.batch = 2 * L; g.sAo = 0; g.sBo = (int64_t)d * d; g.sCo = (int64_t)M * d; g.sBias = d;
     RET(gemm(e, g));
+  }
+  return B200ASR_OK;
+}
+
+// The encoder as one CUDA graph per (batch, clip length, options): ~230 launches, each GEMM's two tensor maps encoded on the host,
+// are built once instead of per call (the maps are kernel parameters, so they live in the graph's nodes).
+int run_encoder(b200asr_engine* e) {
+  char key[160];
+  snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d/%d", e->B, e->n_samples, e->pcm_dtype, e->keep_stages ? 1 : 0, e->use_attn_tc ? 1 : 0,
+           e->use_pdl ? 1 : 0, e->cfg.use_tensor_cores);
+  if (e->use_enc_graph && e->act_dtype == kBF16) {
+    if (!e->enc_graph || e->enc_graph_key != key) {
+      if (e->enc_graph) { cudaGraphExecDestroy(e->enc_graph); e->enc_graph = nullptr; }
+      cudaGraph_t graph = nullptr;
+      const int64_t before = e->launches;
+      CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
+      const int r = enqueue_encoder(e);
+      const cudaError_t ce = cudaStreamEndCapture(e->st, &graph);
+      e->enc_graph_nodes = e->launches - before;
+      e->launches = before;
+      if (r != B200ASR_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+      if (ce != cudaSuccess) return e->cuda_fail(ce, "cudaStreamEndCapture (encoder)");
+      const cudaError_t ci = cudaGraphInstantiate(&e->enc_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ci != cudaSuccess) { e->enc_graph = nullptr; return e->cuda_fail(ci, "cudaGraphInstantiate (encoder)"); }
+      e->enc_graph_key = key;
+    }
+    CK(cudaGraphLaunch(e->enc_graph, e->st));
+    e->launches += e->enc_graph_nodes;
+  } else {
+    RET(enqueue_encoder(e));
   }
   e->encoded = true;
   e->prefilled = false;
@@ -746,6 +778,7 @@ void b200asr_destroy(b200asr_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->st);
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
+  if (e->enc_graph) cudaGraphExecDestroy(e->enc_graph);
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
   void* bufs[] = {e->stage_buf, e->basis_t, e->fb_start, e->fb_len, e->pcm, e->mel_raw, e->max_key, e->mel_pad, e->h1_pad,
                   e->hidden, e->stem, e->xhat, e->qkv, e->ctx, e->ffn, e->S, e->P, e->cross_kv, e->kcache, e->vcache,
@@ -766,6 +799,7 @@ int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "mega")) { e->use_mega = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "pdl")) { e->use_pdl = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "enc_graph")) { e->use_enc_graph = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "stream")) { e->use_stream = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "stream_l2_hint")) { e->stream_l2_hint = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "stream_debug")) { e->stream_debug = (int)value; return B200ASR_OK; }
@@ -822,6 +856,7 @@ int b200asr_set_tensor(b200asr_engine* e, const char* name_c, const float* host,
   }
   e->w[name] = t;
   e->finalized = false;
+  if (e->enc_graph) { cudaGraphExecDestroy(e->enc_graph); e->enc_graph = nullptr; }      // weight pointers are baked into its nodes
   // tables that cache weight pointers (tensor maps, fold vectors, layer tables) are rebuilt on the next decoder launch
   if (e->st_layers) {
     cudaFree(e->st_layers); cudaFree(e->st_wmaps); cudaFree(e->st_fold);
