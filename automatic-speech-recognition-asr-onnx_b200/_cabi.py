@@ -48,6 +48,10 @@ SYMBOLS = {
     "b200asr_encode": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32]),
     "b200asr_upload_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32]),
     "b200asr_encode_resident": (C.c_int, [_P]),
+    "b200asr_encode_ragged": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _I32P]),
+    "b200asr_upload_pcm_ragged": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _I32P]),
+    "b200asr_transcribe_ragged": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _I32P, _I32P, C.c_int32, C.c_int32, _I32P,
+                                            C.c_int32, _I32P]),
     "b200asr_set_decode_options": (C.c_int, [_P, _I32P, C.c_int32, C.c_int32, C.c_float, C.c_int32]),
     "b200asr_set_sampling": (C.c_int, [_P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_uint64, _F32P, C.c_int32]),
     "b200asr_prefill": (C.c_int, [_P, _I32P, C.c_int32, _F32P, _I32P]),

@@ -92,9 +92,12 @@ __device__ __forceinline__ float key_to_float(int k) {
 cudaError_t launch_logmel(const void* pcm, int pcm_is_f32, int batch, int n_samples, int64_t pcm_stride,
                           const float* basis_t /*[n_fft][2F]*/, const float* fbank /*[n_mels][F]*/,
                           const int* fb_start, const int* fb_len, int n_fft, int hop, int n_mels,
-                          float* mel_raw /*[B][T][n_mels]*/, int* max_key /*[B]*/, cudaStream_t st);
+                          float* mel_raw /*[B][T][n_mels]*/, int* max_key /*[B]*/, cudaStream_t st,
+                          const int* n_per_clip = nullptr /*ragged batch: samples per clip (device)*/);
+cudaError_t launch_zero_tail_rows(void* buf, int dtype, const int* n_per_clip, int hop, int batch, int T, int d, cudaStream_t st);
 cudaError_t launch_mel_finalize(const float* mel_raw, const int* max_key, int batch, int T, int n_mels,
-                                void* mel_pad /*[B][T+2][n_mels]*/, int out_dtype, cudaStream_t st);
+                                void* mel_pad /*[B][T+2][n_mels]*/, int out_dtype, cudaStream_t st,
+                                const int* n_per_clip = nullptr, int hop = 1);
 cudaError_t launch_fill_i32(int* p, int v, int n, cudaStream_t st);
 
 // gemm_simt.cu
@@ -107,7 +110,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t st, std:
 // layers.cu
 cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, void* out,
                              int out_dtype, int64_t ldo, int rows, int d, float eps, cudaStream_t st);
-cudaError_t launch_softmax_rows(const float* s, void* p, int p_dtype, int64_t rows, int cols, cudaStream_t st);
+cudaError_t launch_softmax_rows(const float* s, void* p, int p_dtype, int64_t rows, int cols, cudaStream_t st,
+                                const int* valid = nullptr /*[entries]: key columns per entry*/, int64_t rows_per_entry = 1);
 
 // decoder.cu
 struct DecState {           // lives in device memory, one per engine
@@ -138,7 +142,7 @@ cudaError_t launch_dec_self_attn(const float* q /*[rows][d]*/, const void* kcach
                                  const DecState* state, float* ctx /*[rows][d]*/, cudaStream_t st);
 cudaError_t launch_dec_cross_attn(const float* q, const void* cross_kv /*[2L][B][T][d]: K layers then V layers*/, int kv_dtype, int layer,
                                   int n_layers, int batch, int n_new, int n_heads, int head_dim, int T,
-                                  float* ctx, cudaStream_t st);
+                                  float* ctx, cudaStream_t st, const int* t_valid = nullptr /*[batch]: keys per clip (ragged batch)*/);
 struct SelectArgs {
   float* logits; int vocab; int batch;
   const int* cand_idx;       // optional [B][vocab]: `logits` holds per-slice maxima and the token id is cand_idx[b][arg-max] (plain arg-max heads only)
@@ -177,6 +181,7 @@ struct MegaArgs {
   const void* embed; const float* pos; const float* ln_g; const float* ln_b;
   const float* suppress_bias; const float* begin_bias;
   void* kcache; void* vcache; const void* cross_kv; int T;
+  const int* t_valid;                    // ragged batch: encoder positions per clip [batch] (device); nullptr = T for every clip
   int batch, d, ffn, n_heads, vocab, max_target;
   float* x; float* q; float* ctx; float* f; float* logits;     // logits may be null
   const int* first_tokens; int first_n_new;                      // iteration 0: [B][first_n_new]

@@ -284,19 +284,20 @@ constexpr int kCrossThreads = 128;
 template <typename KT>
 __global__ void __launch_bounds__(kCrossThreads)
 dec_cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, int layer, int n_layers,
-                      int n_new, int n_heads, int T, float* __restrict__ ctx) {
+                      int n_new, int n_heads, int T_ld, const int* __restrict__ t_valid, float* __restrict__ ctx) {
   extern __shared__ float sm[];            // q[64] + scores[T] + red[kCrossThreads/32] + part[4][64]
   float* qs = sm;
   float* sc = sm + 64;
-  float* red = sc + T;
+  float* red = sc + T_ld;
   float* part = red + 8;
   const int row = blockIdx.x, h = blockIdx.y;
   const int b = row / n_new;
   const int d = n_heads * 64;
   const int64_t ld = d;
   const int B = gridDim.x / n_new;
-  const KT* kb = ckv + (((int64_t)layer * B + b) * T) * d + h * 64;
-  const KT* vb = ckv + (((int64_t)(n_layers + layer) * B + b) * T) * d + h * 64;
+  const int T = t_valid ? min(T_ld, max(1, t_valid[b])) : T_ld;     // ragged batch: this clip's own encoder positions
+  const KT* kb = ckv + (((int64_t)layer * B + b) * T_ld) * d + h * 64;
+  const KT* vb = ckv + (((int64_t)(n_layers + layer) * B + b) * T_ld) * d + h * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < 64) qs[threadIdx.x] = q[(int64_t)row * d + h * 64 + threadIdx.x];
   __syncthreads();
@@ -334,16 +335,16 @@ dec_cross_attn_kernel(const float* __restrict__ q, const KT* __restrict__ ckv, i
 
 cudaError_t launch_dec_cross_attn(const float* q, const void* cross_kv, int kv_dtype, int layer, int n_layers,
                                   int batch, int n_new, int n_heads, int head_dim, int T, float* ctx,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, const int* t_valid) {
   if (head_dim != 64) return cudaErrorInvalidValue;
   dim3 grid(batch * n_new, n_heads);
   const size_t smem = (size_t)(64 + T + 8 + 4 * 64) * sizeof(float);
   if (kv_dtype == kF32)
     dec_cross_attn_kernel<float><<<grid, kCrossThreads, smem, st>>>(q, (const float*)cross_kv, layer, n_layers, n_new,
-                                                                    n_heads, T, ctx);
+                                                                    n_heads, T, t_valid, ctx);
   else
     dec_cross_attn_kernel<bf16><<<grid, kCrossThreads, smem, st>>>(q, (const bf16*)cross_kv, layer, n_layers, n_new,
-                                                                   n_heads, T, ctx);
+                                                                   n_heads, T, t_valid, ctx);
   return cudaGetLastError();
 }
 

@@ -472,7 +472,8 @@ __device__ void cross_attn_phase(const MegaArgs& a, const Iter& it, int layer, f
     const WT* ck = reinterpret_cast<const WT*>(a.cross_kv);
     const WT* kb = ck + (((long long)layer * a.batch + b) * a.T) * a.d + h * 64;
     const WT* vb = ck + (((long long)(a.n_layers + layer) * a.batch + b) * a.T) * a.d + h * 64;
-    attn_task<WT>(a.q + (long long)row * a.d + h * 64, kb, vb, a.d, a.T, a.ctx + (long long)row * a.d + h * 64, sm);
+    attn_task<WT>(a.q + (long long)row * a.d + h * 64, kb, vb, a.d, a.t_valid ? min(a.T, max(1, a.t_valid[b])) : a.T,
+                  a.ctx + (long long)row * a.d + h * 64, sm);
   }
 }
 

@@ -466,12 +466,12 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               for (long long i = x0 + wt; i < x1; i += kStWorkers) st_zero2(oset + 2 * i);
             }
           }
-          const int nvalid = kind ? T : kv;
-          const int nb = (nvalid + 127) >> 7;
+          const int nb = ((kind ? T : kv) + 127) >> 7;         // boxes are streamed for the batch maximum; a clip's own length masks
 #pragma unroll 1
           for (int t = first_task(l, kind, sa.task_inv); t < ntask; t += G) {
             const int vu = t / H, h = t - vu * H;            // row (virtual utterance) and head
             const int ub = vu / NF, pi = vu - ub * NF;       // clip and position within this launch's new rows
+            const int nvalid = kind ? (a.t_valid ? a.t_valid[ub] : T) : kv;
             // q of my row, and (self-attention) k / v of the clip's new rows 0..pi: the causal part that is not in the cache yet
             const int nitems = kind ? 64 : 64 + (pi + 1) * 128;
 #pragma unroll 1

@@ -53,6 +53,10 @@ struct b200asr_engine {
   // encoder state
   int B = 0, n_samples = 0, T_mel = 0, T_enc = 0, pcm_dtype = B200ASR_PCM_I16;
   void* pcm = nullptr; void* pcm_pinned = nullptr;
+  // ragged batch (b200asr_*_ragged): samples per clip and encoder positions per clip, device [2][max_batch]; ragged = in force
+  int* d_lens = nullptr; bool ragged = false; std::vector<int> h_lens;
+  const int* dev_nsamp() const { return ragged ? d_lens : nullptr; }
+  const int* dev_tvalid() const { return ragged ? d_lens + cfg.max_batch : nullptr; }
   float* mel_raw = nullptr; int* max_key = nullptr;
   void* mel_pad = nullptr; void* h1_pad = nullptr;
   float* hidden = nullptr; float* stem = nullptr;
@@ -210,20 +214,22 @@ int enqueue_encoder(b200asr_engine* e) {
   // ---- front end ----
   KL(launch_fill_i32(e->max_key, INT_MIN, B, e->st));
   KL(launch_logmel(e->pcm, e->pcm_dtype == B200ASR_PCM_F32, B, e->n_samples, e->n_samples, e->basis_t,
-                   WF(e, "mel_fbank"), e->fb_start, e->fb_len, c.n_fft, c.hop, c.n_mels, e->mel_raw, e->max_key, e->st));
+                   WF(e, "mel_fbank"), e->fb_start, e->fb_len, c.n_fft, c.hop, c.n_mels, e->mel_raw, e->max_key, e->st, e->dev_nsamp()));
   // zero the conv padding rows (row 0 and row Tm+1 of every utterance)
   CK(cudaMemset2DAsync(e->mel_pad, (size_t)(Tm + 2) * c.n_mels * es, 0, (size_t)c.n_mels * es, B, e->st));
   CK(cudaMemset2DAsync((char*)e->mel_pad + (size_t)(Tm + 1) * c.n_mels * es, (size_t)(Tm + 2) * c.n_mels * es, 0,
                        (size_t)c.n_mels * es, B, e->st));
   CK(cudaMemset2DAsync(e->h1_pad, (size_t)(Tm + 2) * d * es, 0, (size_t)d * es, B, e->st));
   CK(cudaMemset2DAsync((char*)e->h1_pad + (size_t)(Tm + 1) * d * es, (size_t)(Tm + 2) * d * es, 0, (size_t)d * es, B, e->st));
-  KL(launch_mel_finalize(e->mel_raw, e->max_key, B, Tm, c.n_mels, e->mel_pad, ad, e->st));
+  KL(launch_mel_finalize(e->mel_raw, e->max_key, B, Tm, c.n_mels, e->mel_pad, ad, e->st, e->dev_nsamp(), c.hop));
   // ---- conv stem as strided-view GEMMs (Export_Whisper.py:428-429) ----
   {
     GemmArgs g = linear_args(e, e->mel_pad, c.n_mels, "enc.conv1.w", "enc.conv1.b", (char*)e->h1_pad + (size_t)d * es, d,
                              ad, Tm, d, 3 * c.n_mels);
     g.sAo = (int64_t)(Tm + 2) * c.n_mels; g.sCo = (int64_t)(Tm + 2) * d; g.batch = B; g.act = kActGelu;
     RET(gemm(e, g));
+    // ragged batch: conv2 must see its `padding=1` zero row right after each clip's own last frame
+    if (e->ragged) KL(launch_zero_tail_rows(e->h1_pad, ad, e->dev_nsamp(), c.hop, B, Tm, d, e->st));
     GemmArgs g2 = linear_args(e, e->h1_pad, 2 * d, "enc.conv2.w", "enc.conv2.b", e->hidden, d, kF32, T, d, 3 * d);
     g2.sAo = (int64_t)(Tm + 2) * d; g2.sCo = (int64_t)T * d; g2.batch = B; g2.act = kActGelu;
     g2.residual = WF(e, "enc.pos"); g2.ldr = d; g2.sRo = 0;
@@ -238,7 +244,7 @@ int enqueue_encoder(b200asr_engine* e) {
     if (ad == kBF16 && c.use_tensor_cores && e->use_attn_tc && attention_tc_supported(T, d, H)) {
       // fused softmax(Q K^T) V on tcgen05: scores and probabilities never leave the SM
       std::string msg;
-      cudaError_t r = launch_attention_tc(e->qkv, e->ctx, B, T, d, H, e->st, &msg);
+      cudaError_t r = launch_attention_tc(e->qkv, e->ctx, B, T, d, H, e->st, &msg, e->dev_tvalid(), -1e30f);
       e->launches++;
       if (r != cudaSuccess) return e->fail(B200ASR_E_CUDA, "attention_tc: " + (msg.empty() ? std::string(cudaGetErrorString(r)) : msg));
     } else {  // per-(utterance, head) softmax(Q K^T) V ; scale pre-folded into q and k
@@ -248,7 +254,7 @@ int enqueue_encoder(b200asr_engine* e) {
       s.C = e->S; s.ldc = T; s.sCo = (int64_t)H * T * T; s.sCi = (int64_t)T * T; s.c_dtype = kF32;
       s.M = T; s.N = T; s.K = 64; s.batch = B * H; s.batch_inner = H;
       KL(launch_gemm_simt(s, e->st));
-      KL(launch_softmax_rows(e->S, e->P, ad, (int64_t)B * H * T, T, e->st));
+      KL(launch_softmax_rows(e->S, e->P, ad, (int64_t)B * H * T, T, e->st, e->dev_tvalid(), (int64_t)H * T));
       GemmArgs o;
       o.A = e->P; o.lda = T; o.sAo = (int64_t)H * T * T; o.sAi = (int64_t)T * T; o.a_dtype = ad;
       o.B = (char*)e->qkv + (size_t)2 * d * es; o.ldb = 3 * d; o.sBo = (int64_t)T * 3 * d; o.sBi = 64; o.b_dtype = ad;
@@ -287,8 +293,8 @@ int enqueue_encoder(b200asr_engine* e) {
 // are built once instead of per call (the maps are kernel parameters, so they live in the graph's nodes).
 int run_encoder(b200asr_engine* e) {
   char key[160];
-  snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d/%d", e->B, e->n_samples, e->pcm_dtype, e->keep_stages ? 1 : 0, e->use_attn_tc ? 1 : 0,
-           e->use_pdl ? 1 : 0, e->cfg.use_tensor_cores);
+  snprintf(key, sizeof key, "%d/%d/%d/%d/%d/%d/%d/%d", e->B, e->n_samples, e->pcm_dtype, e->keep_stages ? 1 : 0, e->use_attn_tc ? 1 : 0,
+           e->use_pdl ? 1 : 0, e->cfg.use_tensor_cores, e->ragged ? 1 : 0);   // (per-clip lengths are read from device memory: one graph serves every ragged batch of this shape)
   if (e->use_enc_graph && e->act_dtype == kBF16) {
     if (!e->enc_graph || e->enc_graph_key != key) {
       if (e->enc_graph) { cudaGraphExecDestroy(e->enc_graph); e->enc_graph = nullptr; }
@@ -344,7 +350,7 @@ int enqueue_decoder(b200asr_engine* e, const int* tokens_dev, int n_new, bool fi
     cq.x = e->dx; cq.ldx = d; cq.ln_mode = 1; cq.W = W(e, p + "cq.w"); cq.bias = WF(e, p + "cq.b");
     cq.out = e->dq; cq.ldo = d; cq.N = d; cq.K = d;
     KL(launch_dec_linear(cq, e->st));
-    KL(launch_dec_cross_attn(e->dq, e->cross_kv, wd, l, L, B, n_new, H, 64, T, e->dctx, e->st));
+    KL(launch_dec_cross_attn(e->dq, e->cross_kv, wd, l, L, B, n_new, H, 64, T, e->dctx, e->st, e->dev_tvalid()));
     DecLinearArgs co = a;
     co.x = e->dctx; co.ldx = d; co.W = W(e, p + "cout.w"); co.bias = WF(e, p + "cout.b"); co.residual = e->dx; co.ldr = d;
     co.out = e->dx; co.ldo = d; co.N = d; co.K = d;
@@ -471,7 +477,7 @@ void fill_mega_args(b200asr_engine* e, MegaArgs& a, int n_iters, const int* firs
   a.layers = e->mega_layers; a.n_layers = c.dec_layers;
   a.embed = W(e, "dec.embed"); a.pos = WF(e, "dec.pos"); a.ln_g = WF(e, "dec.ln.g"); a.ln_b = WF(e, "dec.ln.b");
   a.suppress_bias = WF(e, "dec.suppress_bias"); a.begin_bias = WF(e, "dec.begin_suppress_bias");
-  a.kcache = e->kcache; a.vcache = e->vcache; a.cross_kv = e->cross_kv; a.T = e->T_enc;
+  a.kcache = e->kcache; a.vcache = e->vcache; a.cross_kv = e->cross_kv; a.T = e->T_enc; a.t_valid = e->dev_tvalid();
   a.batch = e->B; a.d = c.d_model; a.ffn = c.ffn; a.n_heads = c.n_heads; a.vocab = c.vocab; a.max_target = c.max_target;
   a.x = e->dx; a.q = e->dq; a.ctx = e->dctx; a.f = e->dffn; a.logits = want_logits ? e->logits : nullptr;
   a.first_tokens = first_tokens; a.first_n_new = first_n_new;
@@ -511,6 +517,7 @@ int run_mega(b200asr_engine* e, int n_iters, const int* first_tokens, int first_
 bool ring_ok(b200asr_engine* e) {
   const b200asr_config& c = e->cfg;
   if (!e->use_ring || !e->use_mega || e->samp_temperature > 0.f || e->act_dtype != kBF16 || e->penalty_range > 32) return false;
+  if (e->ragged) return false;                   // round-1 kernel: no per-clip key count (the tensor-core kernel and the barrier kernel have one)
   if (e->num_sms % kRingTaskMul == 0) return false;
   if (!ring_supported(e->B, c.d_model, c.ffn, c.n_heads, c.vocab, e->num_sms)) return false;
   if (c.d_model / 8 > 256) return false;         // TMA box rows
@@ -683,7 +690,9 @@ int run_stream(b200asr_engine* e, int n_heads_iters, const int* first_tokens, in
   return launch_stream(e, B, n_heads_iters, first_tokens, n_first, first_is_prefill, want_logits, false);
 }
 
-int do_upload(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples) {
+// lens: optional samples per clip (ragged batch); n_samples is then the row stride of pcm_host and the batch maximum
+int do_upload(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+              const int32_t* lens = nullptr) {
   const b200asr_config& c = e->cfg;
   if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
   if (!pcm_host || batch <= 0 || batch > c.max_batch) return e->fail(B200ASR_E_INVALID, "batch out of range");
@@ -692,6 +701,23 @@ int do_upload(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_
   const int Tm = n_samples / c.hop;
   const int T = (Tm + 1) / 2;
   if (T > c.max_source) return e->fail(B200ASR_E_INVALID, "audio longer than max_source positions");
+  bool ragged = false;
+  if (lens) {
+    int longest = 0;
+    for (int b = 0; b < batch; ++b) {
+      if (lens[b] < c.n_fft || lens[b] > n_samples) return e->fail(B200ASR_E_INVALID, "per-clip length out of [n_fft, n_samples]");
+      longest = std::max(longest, (int)lens[b]);
+      ragged |= lens[b] != n_samples;
+    }
+    if (ragged) {
+      // the encoder grid is sized by n_samples; a shorter maximum would only run padding rows, so ask for the tight stride
+      if (longest / c.hop != Tm) return e->fail(B200ASR_E_INVALID, "n_samples must be the longest clip's length (rounded up within one hop)");
+      e->h_lens.assign((size_t)2 * c.max_batch, 0);
+      for (int b = 0; b < batch; ++b) { e->h_lens[b] = lens[b]; e->h_lens[c.max_batch + b] = (lens[b] / c.hop + 1) / 2; }
+      CK(cudaMemcpyAsync(e->d_lens, e->h_lens.data(), e->h_lens.size() * sizeof(int), cudaMemcpyHostToDevice, e->st));
+    }
+  }
+  e->ragged = ragged;
   e->B = batch; e->n_samples = n_samples; e->T_mel = Tm; e->T_enc = T; e->pcm_dtype = pcm_dtype;
   const size_t bytes = (size_t)batch * n_samples * (pcm_dtype == B200ASR_PCM_F32 ? 4 : 2);
   CK(cudaMemcpyAsync(e->pcm, pcm_host, bytes, cudaMemcpyHostToDevice, e->st));
@@ -780,7 +806,7 @@ void b200asr_destroy(b200asr_engine* e) {
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
   if (e->enc_graph) cudaGraphExecDestroy(e->enc_graph);
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
-  void* bufs[] = {e->stage_buf, e->basis_t, e->fb_start, e->fb_len, e->pcm, e->mel_raw, e->max_key, e->mel_pad, e->h1_pad,
+  void* bufs[] = {e->stage_buf, e->basis_t, e->fb_start, e->fb_len, e->pcm, e->d_lens, e->mel_raw, e->max_key, e->mel_pad, e->h1_pad,
                   e->hidden, e->stem, e->xhat, e->qkv, e->ctx, e->ffn, e->S, e->P, e->cross_kv, e->kcache, e->vcache,
                   e->dx, e->dq, e->dctx, e->dffn, e->logits, e->prob, e->d_prompt, e->cur_token, e->tokens, e->n_gen,
                   e->finished, e->save_id, e->n_save, e->selected_hist, e->d_stop, e->dstate, e->mega_layers, e->pf_blocks,
@@ -906,6 +932,7 @@ int b200asr_finalize_weights(b200asr_engine* e) {
     const int64_t B = c.max_batch, Tm = c.max_samples / c.hop, T = (Tm + 1) / 2, M = B * T, H = c.n_heads;
     const int64_t rows = B * 8;    // decoder rows: up to 8 prompt tokens per utterance
     RET(dmalloc(e, &e->pcm, (size_t)B * c.max_samples * 4));
+    RET(dmalloc(e, &e->d_lens, (size_t)2 * B * 4));
     RET(dmalloc(e, &e->mel_raw, (size_t)B * Tm * c.n_mels * 4));
     RET(dmalloc(e, &e->max_key, (size_t)B * 4));
     RET(dmalloc(e, &e->mel_pad, (size_t)B * (Tm + 2) * c.n_mels * es));
@@ -966,6 +993,30 @@ int b200asr_encode(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, i
   if (!e) return B200ASR_E_INVALID;
   CK(cudaSetDevice(e->cfg.device));
   RET(do_upload(e, pcm_host, pcm_dtype, batch, n_samples));
+  RET(run_encoder(e));
+  CK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+
+// Ragged batch: clip b has lens[b] samples, rows of pcm_host are n_samples apart (n_samples = the longest clip).  Every clip
+// is processed exactly as if it were encoded alone (its own reflect pad, mel maximum, conv zero pad, attention keys), which is
+// what the reference's dynamic audio axis (Export_Whisper.py:743) gives a caller who runs the clips one by one.
+int b200asr_upload_pcm_ragged(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                              const int32_t* lens) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (!lens) return e->fail(B200ASR_E_INVALID, "null lens");
+  RET(do_upload(e, pcm_host, pcm_dtype, batch, n_samples, lens));
+  CK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+
+int b200asr_encode_ragged(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                          const int32_t* lens) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (!lens) return e->fail(B200ASR_E_INVALID, "null lens");
+  RET(do_upload(e, pcm_host, pcm_dtype, batch, n_samples, lens));
   RET(run_encoder(e));
   CK(cudaStreamSynchronize(e->st));
   return B200ASR_OK;
@@ -1168,6 +1219,16 @@ int b200asr_transcribe(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtyp
   if (!e) return B200ASR_E_INVALID;
   CK(cudaSetDevice(e->cfg.device));
   RET(do_upload(e, pcm_host, pcm_dtype, batch, n_samples));
+  return b200asr_transcribe_resident(e, prompt_ids, n_prompt, max_new, tokens_out, tokens_ld, lens_out);
+}
+
+int b200asr_transcribe_ragged(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                              const int32_t* lens, const int32_t* prompt_ids, int32_t n_prompt, int32_t max_new,
+                              int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  if (!e) return B200ASR_E_INVALID;
+  CK(cudaSetDevice(e->cfg.device));
+  if (!lens) return e->fail(B200ASR_E_INVALID, "null lens");
+  RET(do_upload(e, pcm_host, pcm_dtype, batch, n_samples, lens));
   return b200asr_transcribe_resident(e, prompt_ids, n_prompt, max_new, tokens_out, tokens_ld, lens_out);
 }
 

@@ -20,7 +20,7 @@ constexpr int kFrontThreads = 256;
 // smem: span of PCM covering 16 frames, then 16 x F power values.
 template <bool kF32In>
 __global__ void __launch_bounds__(kFrontThreads)
-logmel_kernel(const void* __restrict__ pcm_v, int n_samples, int64_t pcm_stride,
+logmel_kernel(const void* __restrict__ pcm_v, int n_samples_max, const int* __restrict__ n_per_clip, int64_t pcm_stride,
               const float* __restrict__ basis_t, const float* __restrict__ fbank,
               const int* __restrict__ fb_start, const int* __restrict__ fb_len,
               int n_fft, int hop, int n_mels, int T,
@@ -31,6 +31,8 @@ logmel_kernel(const void* __restrict__ pcm_v, int n_samples, int64_t pcm_stride,
   float* xs = smem;                 // [span]
   float* pw = smem + ((span + 3) & ~3);   // [16][F]
   const int b = blockIdx.y;
+  const int n_samples = n_per_clip ? n_per_clip[b] : n_samples_max;     // ragged batch: this clip's own length (reflect pad at ITS end)
+  const int Tb = n_samples / hop;                                       // frames of this clip; later rows of the batch grid are padding
   const int f0 = blockIdx.x * kFramesPerCta;
   const int half = n_fft / 2;
   const int64_t start = (int64_t)f0 * hop - half;   // first original-sample index of the span
@@ -104,7 +106,7 @@ logmel_kernel(const void* __restrict__ pcm_v, int n_samples, int64_t pcm_stride,
     for (int k = 0; k < len; ++k) acc = fmaf(w[k], p[k], acc);
     const float v = log10f(fmaxf(acc, 1e-10f));
     mel_raw[((int64_t)b * T + (f0 + r)) * n_mels + m] = v;
-    local_max = fmaxf(local_max, v);
+    if (f0 + r < Tb) local_max = fmaxf(local_max, v);
   }
   local_max = warp_max(local_max);
   if ((threadIdx.x & 31) == 0 && local_max > -INFINITY) atomicMax(max_key + b, float_to_key(local_max));
@@ -113,14 +115,15 @@ logmel_kernel(const void* __restrict__ pcm_v, int n_samples, int64_t pcm_stride,
 // y = (max(x, max-8) + 4) / 4  written time-major into the zero-padded conv input
 // (row 0 and row T+1 are the conv "padding=1" rows).  Export_Whisper.py:426-427.
 template <typename OutT>
-__global__ void mel_finalize_kernel(const float* __restrict__ mel_raw, const int* __restrict__ max_key,
-                                    int T, int n_mels, OutT* __restrict__ mel_pad) {
+__global__ void mel_finalize_kernel(const float* __restrict__ mel_raw, const int* __restrict__ max_key, const int* __restrict__ n_per_clip,
+                                    int hop, int T, int n_mels, OutT* __restrict__ mel_pad) {
   const int b = blockIdx.y;
+  const int64_t nvalid = n_per_clip ? (int64_t)(n_per_clip[b] / hop) * n_mels : (int64_t)T * n_mels;   // rows past the clip's end stay zero
   const float floor_v = key_to_float(max_key[b]) - 8.0f;
   const int64_t n = (int64_t)T * n_mels;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = mel_raw[b * n + i];
-    v = (fmaxf(v, floor_v) + 4.0f) * 0.25f;
+    v = i < nvalid ? (fmaxf(v, floor_v) + 4.0f) * 0.25f : 0.f;
     mel_pad[(int64_t)b * (T + 2) * n_mels + n_mels + i] = from_f<OutT>(v);
   }
 }
@@ -135,30 +138,47 @@ cudaError_t launch_fill_i32(int* p, int v, int n, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// rows [first[b], T) of a [B][T + 2][d] time-major, zero-padded activation buffer (row 0 = left pad) set to zero: in a ragged batch
+// the conv stem must see zeros past each clip's end, exactly like the `padding=1` of the reference's per-clip convolution
+template <typename OutT>
+__global__ void zero_tail_rows_kernel(OutT* __restrict__ buf, const int* __restrict__ n_per_clip, int hop, int T, int d) {
+  const int b = blockIdx.y;
+  const int first = n_per_clip[b] / hop;
+  const int64_t n = (int64_t)(T - first) * d;
+  OutT* p = buf + ((int64_t)b * (T + 2) + 1 + first) * d;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = from_f<OutT>(0.f);
+}
+cudaError_t launch_zero_tail_rows(void* buf, int dtype, const int* n_per_clip, int hop, int batch, int T, int d, cudaStream_t st) {
+  dim3 grid(32, batch);
+  if (dtype == kF32) zero_tail_rows_kernel<float><<<grid, 256, 0, st>>>((float*)buf, n_per_clip, hop, T, d);
+  else zero_tail_rows_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)buf, n_per_clip, hop, T, d);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_logmel(const void* pcm, int pcm_is_f32, int batch, int n_samples, int64_t pcm_stride,
                           const float* basis_t, const float* fbank, const int* fb_start, const int* fb_len,
-                          int n_fft, int hop, int n_mels, float* mel_raw, int* max_key, cudaStream_t st) {
+                          int n_fft, int hop, int n_mels, float* mel_raw, int* max_key, cudaStream_t st, const int* n_per_clip) {
   const int T = n_samples / hop;
   const int F = n_fft / 2 + 1;
   const int span = (kFramesPerCta - 1) * hop + n_fft;
   const size_t smem = (((span + 3) & ~3) + (size_t)kFramesPerCta * F) * sizeof(float);
   dim3 grid((T + kFramesPerCta - 1) / kFramesPerCta, batch);
   if (pcm_is_f32)
-    logmel_kernel<true><<<grid, kFrontThreads, smem, st>>>(pcm, n_samples, pcm_stride, basis_t, fbank, fb_start,
+    logmel_kernel<true><<<grid, kFrontThreads, smem, st>>>(pcm, n_samples, n_per_clip, pcm_stride, basis_t, fbank, fb_start,
                                                             fb_len, n_fft, hop, n_mels, T, mel_raw, max_key);
   else
-    logmel_kernel<false><<<grid, kFrontThreads, smem, st>>>(pcm, n_samples, pcm_stride, basis_t, fbank, fb_start,
+    logmel_kernel<false><<<grid, kFrontThreads, smem, st>>>(pcm, n_samples, n_per_clip, pcm_stride, basis_t, fbank, fb_start,
                                                              fb_len, n_fft, hop, n_mels, T, mel_raw, max_key);
   return cudaGetLastError();
 }
 
 cudaError_t launch_mel_finalize(const float* mel_raw, const int* max_key, int batch, int T, int n_mels,
-                                void* mel_pad, int out_dtype, cudaStream_t st) {
+                                void* mel_pad, int out_dtype, cudaStream_t st, const int* n_per_clip, int hop) {
   dim3 grid((unsigned)min((int64_t)64, ((int64_t)T * n_mels + 255) / 256), batch);
   if (out_dtype == kF32)
-    mel_finalize_kernel<float><<<grid, 256, 0, st>>>(mel_raw, max_key, T, n_mels, (float*)mel_pad);
+    mel_finalize_kernel<float><<<grid, 256, 0, st>>>(mel_raw, max_key, n_per_clip, hop, T, n_mels, (float*)mel_pad);
   else
-    mel_finalize_kernel<bf16><<<grid, 256, 0, st>>>(mel_raw, max_key, T, n_mels, (bf16*)mel_pad);
+    mel_finalize_kernel<bf16><<<grid, 256, 0, st>>>(mel_raw, max_key, n_per_clip, hop, T, n_mels, (bf16*)mel_pad);
   return cudaGetLastError();
 }
 

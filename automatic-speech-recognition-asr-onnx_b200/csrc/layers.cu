@@ -58,30 +58,35 @@ cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* gamma, co
   return cudaGetLastError();
 }
 
-// p[row] = softmax(s[row]) ; one warp per row, fp32 math (no mask: encoder self-attention).
+// p[row] = softmax(s[row]) ; one warp per row, fp32 math (encoder self-attention; optional per-entry key count).
 template <typename OutT>
 __global__ void __launch_bounds__(256)
-softmax_rows_kernel(const float* __restrict__ s, OutT* __restrict__ p, int64_t rows, int cols) {
+softmax_rows_kernel(const float* __restrict__ s, OutT* __restrict__ p, int64_t rows, int cols,
+                    const int* __restrict__ valid, int64_t rows_per_entry) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const float* sr = s + row * cols;
+  // ragged batch: only the first valid[entry] columns are keys of this entry; the rest get probability 0
+  const int nv = valid ? min(cols, max(1, valid[row / rows_per_entry])) : cols;
   float m = -INFINITY;
-  for (int c = lane; c < cols; c += 32) m = fmaxf(m, sr[c]);
+  for (int c = lane; c < nv; c += 32) m = fmaxf(m, sr[c]);
   m = warp_max(m);
   float sum = 0.f;
-  for (int c = lane; c < cols; c += 32) sum += expf(sr[c] - m);
+  for (int c = lane; c < nv; c += 32) sum += expf(sr[c] - m);
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
   OutT* pr = p + row * cols;
-  for (int c = lane; c < cols; c += 32) pr[c] = from_f<OutT>(expf(sr[c] - m) * inv);
+  for (int c = lane; c < cols; c += 32) pr[c] = from_f<OutT>(c < nv ? expf(sr[c] - m) * inv : 0.f);
 }
 
-cudaError_t launch_softmax_rows(const float* s, void* p, int p_dtype, int64_t rows, int cols, cudaStream_t st) {
+cudaError_t launch_softmax_rows(const float* s, void* p, int p_dtype, int64_t rows, int cols, cudaStream_t st,
+                                const int* valid, int64_t rows_per_entry) {
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-  if (p_dtype == kF32) softmax_rows_kernel<float><<<grid, wpb * 32, 0, st>>>(s, (float*)p, rows, cols);
-  else softmax_rows_kernel<bf16><<<grid, wpb * 32, 0, st>>>(s, (bf16*)p, rows, cols);
+  if (rows_per_entry <= 0) rows_per_entry = 1;
+  if (p_dtype == kF32) softmax_rows_kernel<float><<<grid, wpb * 32, 0, st>>>(s, (float*)p, rows, cols, valid, rows_per_entry);
+  else softmax_rows_kernel<bf16><<<grid, wpb * 32, 0, st>>>(s, (bf16*)p, rows, cols, valid, rows_per_entry);
   return cudaGetLastError();
 }
 

@@ -101,17 +101,45 @@ class WhisperEngine:
         return pcm, code
 
     # -- encoder ------------------------------------------------------------
-    def encode(self, pcm: np.ndarray):
-        pcm, code = self._pcm(pcm)
-        self.batch = pcm.shape[0]
-        self.T_enc = (pcm.shape[1] // self.dims.hop + 1) // 2
-        self._ck(self.lib.b200asr_encode(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1]))
+    def _lens(self, lens, pcm: np.ndarray) -> np.ndarray:
+        lens = np.ascontiguousarray(np.asarray(lens, np.int32).reshape(-1))
+        if lens.shape[0] != pcm.shape[0]:
+            raise ValueError(f"lens has {lens.shape[0]} entries for a batch of {pcm.shape[0]}")
+        return lens
 
-    def upload_pcm(self, pcm: np.ndarray):
+    @staticmethod
+    def pad_ragged(clips: Sequence[np.ndarray]):
+        """Clips of different lengths -> ([B][longest] array, lens) for the `lens=` arguments below."""
+        lens = np.asarray([len(c) for c in clips], np.int32)
+        out = np.zeros((len(clips), int(lens.max())), np.asarray(clips[0]).dtype)
+        for b, c in enumerate(clips):
+            out[b, :len(c)] = c
+        return out, lens
+
+    def valid_positions(self, lens) -> np.ndarray:
+        """Encoder positions of each clip of a ragged batch (rows beyond are padding)."""
+        return (np.asarray(lens, np.int64) // self.dims.hop + 1) // 2
+
+    def encode(self, pcm: np.ndarray, lens=None):
+        """lens: samples per clip for a ragged batch (pcm rows zero-padded to the longest clip)."""
         pcm, code = self._pcm(pcm)
         self.batch = pcm.shape[0]
         self.T_enc = (pcm.shape[1] // self.dims.hop + 1) // 2
-        self._ck(self.lib.b200asr_upload_pcm(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1]))
+        if lens is None:
+            self._ck(self.lib.b200asr_encode(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1]))
+        else:
+            self._ck(self.lib.b200asr_encode_ragged(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1],
+                                                    _i32p(self._lens(lens, pcm))))
+
+    def upload_pcm(self, pcm: np.ndarray, lens=None):
+        pcm, code = self._pcm(pcm)
+        self.batch = pcm.shape[0]
+        self.T_enc = (pcm.shape[1] // self.dims.hop + 1) // 2
+        if lens is None:
+            self._ck(self.lib.b200asr_upload_pcm(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1]))
+        else:
+            self._ck(self.lib.b200asr_upload_pcm_ragged(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0],
+                                                        pcm.shape[1], _i32p(self._lens(lens, pcm))))
 
     def encode_resident(self):
         self._ck(self.lib.b200asr_encode_resident(self.h))
@@ -171,17 +199,22 @@ class WhisperEngine:
 
     # -- whole path ---------------------------------------------------------
     def transcribe(self, pcm: np.ndarray, prompt, max_new: int = 0, out_tokens: Optional[np.ndarray] = None,
-                   out_lens: Optional[np.ndarray] = None):
+                   out_lens: Optional[np.ndarray] = None, lens=None):
         pcm, code = self._pcm(pcm)
         self.batch = pcm.shape[0]
         self.T_enc = (pcm.shape[1] // self.dims.hop + 1) // 2
         p = self._prompt(prompt)
         ld = self.dims.max_target
         toks = out_tokens if out_tokens is not None else np.zeros((self.batch, ld), np.int32)
-        lens = out_lens if out_lens is not None else np.zeros(self.batch, np.int32)
-        self._ck(self.lib.b200asr_transcribe(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1],
-                                             _i32p(p), p.shape[1], max_new, _i32p(toks), toks.shape[1], _i32p(lens)))
-        return [toks[b, :lens[b]].tolist() for b in range(self.batch)]
+        nout = out_lens if out_lens is not None else np.zeros(self.batch, np.int32)
+        if lens is None:
+            self._ck(self.lib.b200asr_transcribe(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1],
+                                                 _i32p(p), p.shape[1], max_new, _i32p(toks), toks.shape[1], _i32p(nout)))
+        else:
+            self._ck(self.lib.b200asr_transcribe_ragged(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1],
+                                                        _i32p(self._lens(lens, pcm)), _i32p(p), p.shape[1], max_new,
+                                                        _i32p(toks), toks.shape[1], _i32p(nout)))
+        return [toks[b, :nout[b]].tolist() for b in range(self.batch)]
 
     def transcribe_resident(self, prompt, max_new: int = 0):
         p = self._prompt(prompt)

@@ -23,12 +23,20 @@ def shard_indices(lengths: Sequence[int], world: int, rank: int) -> List[int]:
 
 
 def group_by_length(indices: Sequence[int], lengths: Sequence[int]) -> List[Tuple[int, List[int]]]:
-    """The engine batches clips of equal sample count (the reference graphs are batch-1, so a
-    batch must not change per-clip semantics such as the per-clip mel max)."""
+    """Batches of equal sample count (the uniform `encode` / `transcribe` calls); mixed lengths go through
+    `ragged_batches` and the `lens=` arguments instead."""
     groups = {}
     for i in indices:
         groups.setdefault(int(lengths[i]), []).append(i)
     return sorted(groups.items())
+
+
+def ragged_batches(indices: Sequence[int], lengths: Sequence[int], max_batch: int) -> List[List[int]]:
+    """Batches for `WhisperEngine.transcribe(..., lens=)`: the engine gives every clip of a ragged batch its single-clip
+    semantics (own reflect pad, mel maximum, attention key range), so clips of any lengths may share a batch; neighbours in
+    length order are put together because the batch runs at its longest clip's row count."""
+    order = sorted(indices, key=lambda i: (-int(lengths[i]), i))
+    return [order[k:k + max_batch] for k in range(0, len(order), max_batch)]
 
 
 def gather_tokens(local_tokens: Sequence[Sequence[int]], local_indices: Sequence[int], n_total: int, max_len: int,

@@ -75,6 +75,14 @@ int b200asr_encode(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, i
 /* same, split so a benchmark can time with inputs already resident */
 int b200asr_upload_pcm(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples);
 int b200asr_encode_resident(b200asr_engine* e);
+/* ragged batch: clip b has lens[b] samples (n_fft <= lens[b] <= n_samples), rows of pcm_host are n_samples apart and n_samples is
+ * the longest clip.  Replaces running the reference's dynamic-length graph (audio axis: Whisper/Export_Whisper.py:743) clip by
+ * clip: each clip gets its own reflect pad, log-mel maximum, conv zero padding and attention key range, so its tokens are what
+ * it gets when encoded alone.  Rows >= (lens[b] / hop + 1) / 2 of that clip's "enc_out" / cross-KV stage are padding. */
+int b200asr_encode_ragged(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                          const int32_t* lens);
+int b200asr_upload_pcm_ragged(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                              const int32_t* lens);
 
 /* decoder: prefill resets the self-KV cache and the token bookkeeping.
  * prompt_ids [batch][n_prompt]; logits_out (optional) [batch][vocab] raw logits
@@ -106,7 +114,10 @@ int b200asr_no_speech_prob(b200asr_engine* e, int32_t no_speech_token, float* pr
 int b200asr_transcribe(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
                        const int32_t* prompt_ids, int32_t n_prompt, int32_t max_new, int32_t* tokens_out,
                        int32_t tokens_ld, int32_t* lens_out);
-/* same with PCM already uploaded (b200asr_upload_pcm): device-resident timing */
+int b200asr_transcribe_ragged(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                              const int32_t* lens, const int32_t* prompt_ids, int32_t n_prompt, int32_t max_new,
+                              int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
+/* same with PCM already uploaded (b200asr_upload_pcm / _ragged): device-resident timing */
 int b200asr_transcribe_resident(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt, int32_t max_new,
                                 int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
 

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from b200asr.sharding import gather_tokens, group_by_length, shard_indices
+from b200asr.sharding import gather_tokens, group_by_length, ragged_batches, shard_indices
 
 
 def _free_port():
@@ -60,3 +60,13 @@ def test_shard_balance_and_grouping():
 def test_gather_single_process():
     out = gather_tokens([[1, 2], [3]], [1, 0], 2, max_len=4)
     assert out == [[3], [1, 2]]
+
+
+def test_ragged_batches_cover_every_clip_once_and_keep_neighbours_together():
+    lengths = [16000, 128000, 8000, 64000, 64160, 127840, 9000]
+    batches = ragged_batches(range(len(lengths)), lengths, 3)
+    assert sorted(i for b in batches for i in b) == list(range(len(lengths)))
+    assert all(len(b) <= 3 for b in batches)
+    assert batches[0] == [1, 5, 4]                      # the three longest share a batch
+    spans = [max(lengths[i] for i in b) - min(lengths[i] for i in b) for b in batches]
+    assert spans[0] < 64000
