@@ -104,6 +104,10 @@ def main(argv=None) -> int:
     tensors = fold_whisper(state, dims, gen.get("suppress_tokens") or [], gen.get("begin_suppress_tokens") or [])
     del state
     md = whisper_metadata(dims, gen)
+    md_path = Path(args.folder) / "ASR_Metadata.onnx"
+    if md_path.exists():                     # an exported folder's own run-time constants win (Inference_Whisper_ONNX.py:270-289)
+        from . import onnx_io
+        md.update(onnx_io.read_metadata(md_path))
     tokenizer = None
     tok_dir = Path(args.tokenizer_path) if args.tokenizer_path else Path(args.folder)
     try:
