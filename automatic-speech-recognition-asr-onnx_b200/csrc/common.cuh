@@ -225,12 +225,14 @@ cudaError_t launch_decoder_ring(const RingArgs& ra, const CUtensorMap& cross_map
 // accumulate-in-L2 exchanges); bf16, batch <= 8.  The product path for the Whisper greedy loop and prefill.
 struct StreamLayer {        // fp32 vectors of one decoder layer: biases and the LayerNorm-fold row sums (sum_k W[n][k])
   const float *qkv_b, *qkv_ws, *out_b, *cq_b, *cq_ws, *cout_b, *fc1_b, *fc1_ws, *fc2_b;
+  const float *qkv_s, *out_s, *cq_s, *cout_s, *fc1_s, *fc2_s;     // FP8 weight path: per-row scales (nullptr in bf16 mode)
 };
 struct StreamArgs {
   MegaArgs m;                          // model dims, device pointers, token bookkeeping (shared with the other decoder kernels)
   const StreamLayer* sl;               // [L]
   const CUtensorMap* wmaps;            // [6L + 1] SWIZZLE_128B maps, box [128 rows][64 k]: qkv, out, cq, cout, fc1, fc2 per layer, then the tied head
   const float* head_g; const float* head_b;   // [vocab] sum_k E[n][k] gamma[k], sum_k E[n][k] beta[k] (final LayerNorm folded around the tied head)
+  const float* head_s; int fp8;               // FP8 weight path (E4M3 weights + per-row scale, atoms of 128 k): head scales; 1 = on
   unsigned long long* acc;             // [2][set_words] accumulator words (12-bit count | 52-bit fixed point), zero at launch
   long long set_words, layer_words;
   unsigned long long* cand;            // [2][grid][NRT][2] flag-in-data arg-max candidates
@@ -253,13 +255,18 @@ struct StreamPlan {
 };
 bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers, int T, int max_target, int num_sms,
                  StreamPlan* plan, void* sched_out /*std::vector<int4>*/, void* cnt_out /*std::vector<unsigned char>*/,
-                 void* xexp_out /*std::vector<unsigned short>*/);
+                 void* xexp_out /*std::vector<unsigned short>*/, int fp8 = 0);
+cudaError_t launch_quant_rows_e4m3(const void* W_bf16, void* W8, float* scale, int N, int K, cudaStream_t st);
+cudaError_t launch_rowdot_e4m3(const void* W8, const float* scale, const float* vec /*nullable: ones*/, float* out, int N, int K, cudaStream_t st);
 cudaError_t launch_decoder_stream(const StreamArgs& sa, const CUtensorMap& cross_map, const CUtensorMap& kc_map,
                                   const CUtensorMap& vc_map, int nrt, int num_sms, size_t smem_bytes, cudaStream_t st);
 cudaError_t launch_rowdot_bf16(const void* W, const float* vec /*nullable: ones*/, float* out, int N, int K, cudaStream_t st);
 // gemm_tc.cu: SWIZZLE_128B bf16 tensor map over [rows][ld] with a [box_rows][64] box (3-D form, batch 1)
 bool make_tmap_rows_sw128(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_rows,
                           std::string* err);
+// same over bytes (fp8 weights): [rows][ld] bytes with a [box_rows][128] box
+bool make_tmap_rows_sw128_u8(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_rows,
+                             std::string* err);
 // attention_tc.cu: fused softmax(Q K^T) V per (utterance, head) on tcgen05; qkv bf16 [batch*T][3d], ctx bf16 [batch*T][d]
 bool attention_tc_supported(int T, int d, int n_heads);
 cudaError_t launch_attention_tc(const void* qkv, void* ctx, int batch, int T, int d, int n_heads, cudaStream_t st,

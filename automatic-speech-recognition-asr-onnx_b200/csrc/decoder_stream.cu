@@ -32,6 +32,8 @@
 // the other (last read one step earlier, all CTAs pass the per-step arg-max exchange in between).
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <algorithm>
 #include <cstdio>
 #include <vector>
@@ -120,6 +122,42 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* r) {
   for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(u[j]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
+  uint32_t u[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                 "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 16; ++j) r[j] = __uint_as_float(u[j]);
+}
+// FP8 weights (E4M3 A operand, per-row scale) x activations split into four E5M2 rows (B operand): K = 32 per instruction
+__device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// instruction descriptor for kind::f8f6f4: D = f32 (bit 4), A = E4M3 (0 @7), B = E5M2 (1 @10), K-major both, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t idesc_f8_e4m3_e5m2(int m, int n) {
+  return (1u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// x ~= sum of four E5M2 values (3 significant bits each): byte j of the result is component j
+__device__ __forceinline__ uint32_t split_e5m2x4(float x) {
+  uint32_t out = 0;
+  float r = x;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_fp8_storage_t q = __nv_cvt_float_to_fp8(r, __NV_SATFINITE, __NV_E5M2);
+    const float back = __half2float(__half(__nv_cvt_fp8_to_halfraw(q, __NV_E5M2)));
+    r -= back;
+    out |= (uint32_t)q << (8 * j);
+  }
+  return out;
+}
+
 struct RingPos { int stage; uint32_t phase; };
 __device__ __forceinline__ void ring_adv(RingPos& p, int n, int NS) {
   int s = p.stage + n;
@@ -128,7 +166,7 @@ __device__ __forceinline__ void ring_adv(RingPos& p, int n, int NS) {
 }
 
 // linear phase p6 (0 qkv, 1 out, 2 cq, 3 cout, 4 fc1, 5 fc2): k-atoms per weight row
-__device__ __forceinline__ int phase_ka(int p6, int d, int ffn) { return (p6 == 5 ? ffn : d) >> 6; }
+__device__ __forceinline__ int phase_ka(int p6, int d, int ffn, int ksh) { return (p6 == 5 ? ffn : d) >> ksh; }
 __device__ __forceinline__ int phase_p6(int ph) { return ph == 0 ? 0 : (ph == 2 ? 1 : (ph == 3 ? 2 : ph - 2)); }
 
 // first attention task (utterance * H + head) owned by this CTA in layer l (kind 0 self, 1 cross); further tasks at + grid
@@ -143,7 +181,9 @@ __device__ __forceinline__ int first_task(int l, int kind, int task_inv) {
 
 // ---------------------------------------------------------------------------
 // DBG: per-phase time stamps into a.timing (block 0), compiled only into the instrumented instantiation
-template <int NRT, bool DBG>
+// F8: the weight ring carries E4M3 bytes (atom = 128 rows x 128 k), activations are staged as four E5M2 rows per utterance,
+//     the epilogue multiplies by the per-row weight scale (NRT <= 4)
+template <int NRT, bool DBG, bool F8>
 __global__ void __launch_bounds__(kStThreads, 1)
 decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_constant__ CUtensorMap kc_map,
                       const __grid_constant__ CUtensorMap vc_map, const __grid_constant__ StreamArgs sa) {
@@ -179,7 +219,9 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   __shared__ volatile int s_step, s_break_it;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int KAd = d >> 6;                                  // k-atoms of a d-wide row
+  constexpr int KSH = F8 ? 7 : 6;                          // log2(k per atom): a 128-byte swizzle row holds 64 bf16 or 128 fp8 weights
+  const int KAd = d >> KSH;                                // k-atoms of a d-wide row
+  const int KUd = d >> 6;                                  // 64-wide activation units of a d-wide row (who stages a unit contributes its statistics)
   const int n_first = a.first_n_new > 0 ? a.first_n_new : 1;
   // sa.multi: the n_first prompt positions of every utterance are processed together in ONE iteration, as NF "virtual
   // utterances" per clip (row vu = utterance * NF + position; causal self-attention among a clip's rows).  Such a launch has
@@ -248,7 +290,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
         for (int at = r.x; at < r.y; ++at) {
           if (!acquire()) { stop = true; return; }
           mbar_expect_tx(&full_bar[p.stage], kStStage);
-          tma_3d_hint(ring + (size_t)p.stage * kStStage, tm, ka * 64, tile * 128, &full_bar[p.stage], pol);
+          tma_3d_hint(ring + (size_t)p.stage * kStStage, tm, ka << KSH, tile * 128, &full_bar[p.stage], pol);
           ++issued; ring_adv(p, 1, NS);
           if (++ka == KA) { ka = 0; ++tile; }
         }
@@ -297,7 +339,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               }
             } else {
               const int p6 = phase_p6(ph);
-              weights(&sa.wmaps[l * 6 + p6], s_sched[l * 6 + p6], phase_ka(p6, d, ffn));
+              weights(&sa.wmaps[l * 6 + p6], s_sched[l * 6 + p6], phase_ka(p6, d, ffn, KSH));
             }
           }
         }
@@ -317,7 +359,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
     // MMA issuers: two lanes (warps 1 and 10) on alternate atoms of the CTA's run, each with its own accumulator; D[128 weight rows][16] (+)= A[128][64] (ring stage) . B[16][64] (activation slot)
     // =======================================================================
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16(128, 16);
+      constexpr uint32_t idesc = F8 ? idesc_f8_e4m3_e5m2(128, 16) : idesc_bf16(128, 16);
       RingPos p{0, 0};
       uint32_t bpar = 0;
       int tctr = 0;
@@ -348,8 +390,10 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             const uint64_t adesc = smem_desc_sw128(ring_u + (uint32_t)p.stage * kStStage);
             const uint64_t bdesc = smem_desc_sw128(bbuf_u + (uint32_t)slot * kStSlot);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_bf16(tmem + (uint32_t)(buf * 32 + ml * 16), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (fresh && k == 0) ? 0u : 1u);
+            for (int k = 0; k < 4; ++k) {
+              if (F8) tc_mma_f8(tmem + (uint32_t)(buf * 32 + ml * 16), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (fresh && k == 0) ? 0u : 1u);
+              else tc_mma_bf16(tmem + (uint32_t)(buf * 32 + ml * 16), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (fresh && k == 0) ? 0u : 1u);
+            }
             fresh = false;
             tc_commit(&empty_bar[p.stage]);
           }
@@ -382,7 +426,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               ring_adv(p, n, NS);
             } else {
               const int p6 = phase_p6(ph);
-              linear(s_sched[l * 6 + p6], phase_ka(p6, d, ffn));
+              linear(s_sched[l * 6 + p6], phase_ka(p6, d, ffn, KSH));
             }
           }
         }
@@ -400,6 +444,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
     constexpr int NG = kStWorkerWarps / NRT;             // slot groups
     constexpr int U = NRT <= 2 ? 1 : (NRT == 4 ? 2 : 4); // k-atoms a thread polls together
     constexpr int RR = NRT < 4 ? NRT : 4;                // utterances an epilogue thread handles
+    constexpr int NC = F8 ? 16 : 8, CPR = F8 ? 4 : 2;    // accumulator columns an epilogue thread reads; columns per utterance
     const bool row_ok = r_mine < R;
     const int q_tm = warp & 3;                           // TMEM lane quarter this warp may read
     const int set_tm = ww >> 2;                          // 0: utterances 0-3 (columns 0-7), 1: utterances 4-7 (columns 8-15)
@@ -489,11 +534,11 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               for (;;) {
                 ld_w2(stp, w0, w1);
                 wv = ld_w(p);
-                if (acc_cnt(w0) == (unsigned)KAd && acc_cnt(w1) == (unsigned)KAd && acc_cnt(wv) == ex) break;
+                if (acc_cnt(w0) == (unsigned)KUd && acc_cnt(w1) == (unsigned)KUd && acc_cnt(wv) == ex) break;
                 if (t0 == 0) t0 = clock64();
                 else if (clock64() - t0 > kStSpin) st_timeout(30, (int)acc_cnt(w0), (int)acc_cnt(wv));
               }
-              const float2 ms = ln_stats(w0, w1, (unsigned)KAd, inv_d, a.eps);
+              const float2 ms = ln_stats(w0, w1, (unsigned)KUd, inv_d, a.eps);
               const float val = fmaf(ms.y, acc_val(wv, ex) - ms.x * wsn, bn);
               if (which == 0) {
                 s_qs[dd] = val;
@@ -634,13 +679,14 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
         const int4 r = s_sched[is_head ? 6 * L : l * 6 + p6];
         // mode 0: x0 = embedding + position (layer 0 qkv), 1: residual words, 2: attention context words,
         //      3: fc1 words -> LN fold + GELU, 4: residual words x gamma (head)
-        int KA = KAd, mode, exp_row = 0, Nrows = d;
+        int KA = KAd, KU = KUd, mode, exp_row = 0, Nrows = d;     // atoms / 64-wide activation units per weight row
+        const float* wscale = nullptr;                            // F8: per-row weight scale
         const u64* src = xw; long long src_ld = d;
         u64* stat_out = nullptr; const u64* stat_in = nullptr;
         const float* fold_ws = nullptr; const float* fold_b = nullptr;
         u64* dst = xw; long long dst_ld = d; const float* bias = nullptr; bool add_x0 = false;
         if (is_head) {
-          mode = 4; exp_row = (L - 1) * 3 + 2; stat_out = hstats; fold_ws = a.ln_g;
+          mode = 4; exp_row = (L - 1) * 3 + 2; stat_out = hstats; fold_ws = a.ln_g; wscale = sa.head_s;
           if (wt == 0) {
             // sliding-window penalty ids (APPLY_PENALTY, Export_Whisper.py:318-331): active once generated >= penalty_range
             int nmax = 0;
@@ -659,28 +705,29 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           }
         } else if (p6 == 0) {
           mode = l == 0 ? 0 : 1; exp_row = l > 0 ? (l - 1) * 3 + 2 : 0; stat_out = stats;
-          Nrows = 3 * d; dst = lay; dst_ld = 3 * d;
+          Nrows = 3 * d; dst = lay; dst_ld = 3 * d; wscale = slr.qkv_s;
         } else if (p6 == 1) {
-          mode = 2; src = lay + (long long)NRT * 3 * d; bias = slr.out_b; add_x0 = l == 0;
+          mode = 2; src = lay + (long long)NRT * 3 * d; bias = slr.out_b; add_x0 = l == 0; wscale = slr.out_s;
         } else if (p6 == 2) {
-          mode = 1; exp_row = l * 3; stat_out = stats + 2 * NRT; dst = lay + (long long)NRT * 4 * d;
+          mode = 1; exp_row = l * 3; stat_out = stats + 2 * NRT; dst = lay + (long long)NRT * 4 * d; wscale = slr.cq_s;
         } else if (p6 == 3) {
-          mode = 2; src = lay + (long long)NRT * 5 * d; bias = slr.cout_b;
+          mode = 2; src = lay + (long long)NRT * 5 * d; bias = slr.cout_b; wscale = slr.cout_s;
         } else if (p6 == 4) {
           mode = 1; exp_row = l * 3 + 1; stat_out = stats + 4 * NRT; Nrows = ffn; dst = lay + (long long)NRT * 6 * d; dst_ld = ffn;
+          wscale = slr.fc1_s;
         } else {
-          KA = ffn >> 6; mode = 3; src = lay + (long long)NRT * 6 * d; src_ld = ffn; exp_row = l * 3 + 2; stat_in = stats + 4 * NRT;
+          KA = ffn >> KSH; KU = ffn >> 6; mode = 3; wscale = slr.fc2_s; src = lay + (long long)NRT * 6 * d; src_ld = ffn; exp_row = l * 3 + 2; stat_in = stats + 4 * NRT;
           fold_ws = slr.fc1_ws; fold_b = slr.fc1_b; bias = slr.fc2_b;
         }
 
         // ---- B-operand staging ----
         {
           const int nat = r.y - r.x;
-          const int nslot = nat < KA ? nat : KA;
-          const int ka0 = r.w;
+          const int nslot = (nat < KA ? nat : KA) * (F8 ? 2 : 1);     // in 64-wide units: an fp8 slot (128 k) is two of them
+          const int ka0 = r.w * (F8 ? 2 : 1);
           // LayerNorm statistics: the k-atoms of tile 0 (head: the k-atoms whose index is one of my vocabulary tiles) are
           // reduced by whoever stages them -- exactly one contributor per atom, d / 64 contributions per word
-          const int st_n = (stat_out && mode != 4 && r.z == 0) ? min(nat, KA - r.x) : 0;     // my slots [0, st_n) are tile-0 atoms
+          const int st_n = (stat_out && mode != 4 && r.z == 0) ? min(nat, KA - r.x) * (F8 ? 2 : 1) : 0;   // my units [0, st_n) are tile-0 atoms
           const int ht0 = r.z, ht1 = mode == 4 ? r.z + nat / KA : 0;                          // head: my vocabulary tiles
           float mean = 0.f, rstd = 1.f;
           bool need_stats = mode == 3 && row_ok && g_mine < nslot;
@@ -699,7 +746,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               const int s = s0 + u * NG;
               kk[u] = 0; ex[u] = 0; pa[u] = make_float2(0.f, 0.f); pb[u] = make_float2(0.f, 0.f);
               if (s < nslot) {
-                int ka = ka0 + s; if (ka >= KA) ka -= KA;
+                int ka = ka0 + s; if (ka >= KU) ka -= KU;
                 kk[u] = ka * 64 + 2 * lane;
                 if (mode == 1 || mode == 4) ex[u] = s_xexp[exp_row * sa.xt + (kk[u] >> 7)];
                 else if (mode == 3) ex[u] = s_cnt[exp_row * sa.cnt_ld + (kk[u] >> 7)];
@@ -735,8 +782,8 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                   if ((todo & (1u << u)) && acc_cnt(w[u][0]) == ex[u] && acc_cnt(w[u][1]) == ex[u]) {
                     fv[u][0] = acc_val(w[u][0], ex[u]); fv[u][1] = acc_val(w[u][1], ex[u]); todo &= ~(1u << u);
                   }
-                if ((todo & 16u) && acc_cnt(sa0) == (unsigned)KAd && acc_cnt(sa1) == (unsigned)KAd) {
-                  const float2 ms = ln_stats(sa0, sa1, (unsigned)KAd, inv_d, a.eps);
+                if ((todo & 16u) && acc_cnt(sa0) == (unsigned)KUd && acc_cnt(sa1) == (unsigned)KUd) {
+                  const float2 ms = ln_stats(sa0, sa1, (unsigned)KUd, inv_d, a.eps);
                   mean = ms.x; rstd = ms.y; todo &= ~16u;
                 }
                 if (!todo) break;
@@ -748,8 +795,8 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                   if ((todo & (1u << u)) && acc_cnt(wb[u][0]) == ex[u] && acc_cnt(wb[u][1]) == ex[u]) {
                     fv[u][0] = acc_val(wb[u][0], ex[u]); fv[u][1] = acc_val(wb[u][1], ex[u]); todo &= ~(1u << u);
                   }
-                if ((todo & 16u) && acc_cnt(sb0) == (unsigned)KAd && acc_cnt(sb1) == (unsigned)KAd) {
-                  const float2 ms = ln_stats(sb0, sb1, (unsigned)KAd, inv_d, a.eps);
+                if ((todo & 16u) && acc_cnt(sb0) == (unsigned)KUd && acc_cnt(sb1) == (unsigned)KUd) {
+                  const float2 ms = ln_stats(sb0, sb1, (unsigned)KUd, inv_d, a.eps);
                   mean = ms.x; rstd = ms.y; todo &= ~16u;
                 }
                 if (!todo) break;
@@ -776,6 +823,19 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               } else if (mode == 4) {
                 f0 *= pa[u].x; f1 *= pa[u].y;
               }
+              if (F8) {
+                // x = sum of four E5M2 values: rows 4r .. 4r + 3 of the slot's 16-row K-major SWIZZLE_128B tile (one byte per k);
+                // unit s is the (s & 1) half of slot s >> 1
+                const uint32_t q0 = split_e5m2x4(f0), q1 = split_e5m2x4(f1);
+                uint8_t* slotp = bbuf + (size_t)(s >> 1) * kStSlot;
+                const int colb = (s & 1) * 64 + 2 * lane, chunk = colb >> 4, within = colb & 15;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int rw = 4 * r_mine + j;
+                  *reinterpret_cast<unsigned short*>(slotp + (rw >> 3) * 1024 + (rw & 7) * 128 + ((chunk ^ (rw & 7)) << 4) + within) =
+                      (unsigned short)(((q0 >> (8 * j)) & 0xffu) | (((q1 >> (8 * j)) & 0xffu) << 8));
+                }
+              } else {
               // x = hi + lo, both bf16: rows 2r (hi) and 2r + 1 (lo) of the slot's 16-row K-major SWIZZLE_128B tile
               const __nv_bfloat162 hi = __floats2bfloat162_rn(f0, f1);
               const float2 hf = __bfloat1622float2(hi);
@@ -785,6 +845,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               const int chunk = lane >> 2, within = (lane & 3) * 4;
               *reinterpret_cast<__nv_bfloat162*>(slotp + (rh >> 3) * 1024 + (rh & 7) * 128 + ((chunk ^ (rh & 7)) << 4) + within) = hi;
               *reinterpret_cast<__nv_bfloat162*>(slotp + (rl >> 3) * 1024 + (rl & 7) * 128 + ((chunk ^ (rl & 7)) << 4) + within) = lo;
+              }
             }
           }
           if (nat > 0) {                                     // phases without atoms here have no MMA side to hand over to
@@ -809,9 +870,10 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             const int tend = min(r.y, at + KA - (at == r.x ? r.w : 0));
             const bool desig = at != r.x || r.w == 0;
             const int n = tile * 128 + q_tm * 32 + lane;
-            float bv = 0.f, x0v[RR];
+            float bv = 0.f, x0v[RR], wsc = 1.f;
 #pragma unroll
             for (int rr = 0; rr < RR; ++rr) x0v[rr] = 0.f;
+            if (F8 && epi_warp && n < Nrows) wsc = wscale[n];
             if (epi_warp && desig && n < Nrows) {
               if (bias) bv = bias[n];
               if (add_x0) {
@@ -831,13 +893,18 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               // accumulator untouched
               const int o0 = at - r.x, nt = tend - at;
               const bool use0 = nt >= 2 || (o0 & 1) == 0, use1 = nt >= 2 || (o0 & 1) == 1;
-              float v[8], v1[8];
+              float v[NC], v1[NC];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { v[j] = 0.f; v1[j] = 0.f; }
-              if (use0) tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + set_tm * 8), v);
-              if (use1) tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + 16 + set_tm * 8), v1);
+              for (int j = 0; j < NC; ++j) { v[j] = 0.f; v1[j] = 0.f; }
+              if (F8) {
+                if (use0) tmem_ld16(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32), v);
+                if (use1) tmem_ld16(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + 16), v1);
+              } else {
+                if (use0) tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + set_tm * 8), v);
+                if (use1) tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + 16 + set_tm * 8), v1);
+              }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += v1[j];
+              for (int j = 0; j < NC; ++j) v[j] += v1[j];
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -846,7 +913,10 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                 for (int rr = 0; rr < RR; ++rr) {
                   const int rq = set_tm * 4 + rr;
                   if (rq < R) {
-                    float val = v[2 * rr] + v[2 * rr + 1];
+                    float val = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < CPR; ++cc) val += v[CPR * rr + cc];
+                    if (F8) val *= wsc;
                     if (desig) val += bv + x0v[rr];
                     red_add(dst + (long long)rq * dst_ld + n, enc_fix(val, kFixScale));
                   }
@@ -868,6 +938,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
       if (head_on) {
         const int4 r = s_sched[6 * L];
         const int t_end = r.z + (r.y - r.x) / KAd;
+        const float* wscale = sa.head_s;
         wbar();                                             // s_pen / s_pen_n visible
         const bool pen_on = s_pen_n > 0;
         float mean[RR], rstd[RR], bvv[RR]; int bii[RR];
@@ -882,11 +953,11 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               long long t0 = 0;
               for (;;) {
                 ld_w2(hstats + rq * 2, w0, w1);
-                if (acc_cnt(w0) == (unsigned)KAd && acc_cnt(w1) == (unsigned)KAd) break;
+                if (acc_cnt(w0) == (unsigned)KUd && acc_cnt(w1) == (unsigned)KUd) break;
                 if (t0 == 0) t0 = clock64();
                 else if (clock64() - t0 > kStSpin) st_timeout(40, (int)acc_cnt(w0), (int)acc_cnt(w1));
               }
-              const float2 ms = ln_stats(w0, w1, (unsigned)KAd, inv_d, a.eps);
+              const float2 ms = ln_stats(w0, w1, (unsigned)KUd, inv_d, a.eps);
               mean[rr] = ms.x; rstd[rr] = ms.y;
             }
           }
@@ -894,21 +965,24 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
 #pragma unroll 1
         for (int tile = r.z; tile < t_end; ++tile) {
           const int n = tile * 128 + q_tm * 32 + lane;
-          float gn = 0.f, btn = 0.f, bg = 0.f;
+          float gn = 0.f, btn = 0.f, bg = 0.f, wsc = 1.f;
           if (epi_warp && n < a.vocab) {
             gn = sa.head_g[n]; btn = sa.head_b[n] + a.suppress_bias[n];
+            if (F8) wsc = wscale[n];
             if (begin_on) bg = a.begin_bias[n];
           }
           const int buf = tctr & 1;
           swait(&acc_full[buf], (uint32_t)((tctr >> 1) & 1), 42);
           if (epi_warp) {
             tc_fence_after();
-            float v[8], v1[8];                               // head tiles are whole (KAd >= 2 atoms): both lanes contribute
-            tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + set_tm * 8), v);
+            float v[NC], v1[NC];                             // head tiles are whole (KAd >= 2 atoms): both lanes contribute
+            if (F8) tmem_ld16(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32), v);
+            else tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + set_tm * 8), v);
             if (KAd >= 2) {
-              tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + 16 + set_tm * 8), v1);
+              if (F8) tmem_ld16(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + 16), v1);
+              else tmem_ld8(tmem + ((uint32_t)(q_tm * 32) << 16) + (uint32_t)(buf * 32 + 16 + set_tm * 8), v1);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += v1[j];
+              for (int j = 0; j < NC; ++j) v[j] += v1[j];
             }
             tc_fence_before();
             __syncwarp();
@@ -919,7 +993,11 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                 const int rq = set_tm * 4 + rr;
                 if (rq < R && rq % NF == NF - 1) {
                   const int ub = rq / NF;
-                  float val = fmaf(rstd[rr], (v[2 * rr] + v[2 * rr + 1]) - mean[rr] * gn, btn);
+                  float dot = 0.f;
+#pragma unroll
+                  for (int cc = 0; cc < CPR; ++cc) dot += v[CPR * rr + cc];
+                  if (F8) dot *= wsc;
+                  float val = fmaf(rstd[rr], dot - mean[rr] * gn, btn);
                   if (pen_on) {
                     bool hit = false;
 #pragma unroll 1
@@ -1078,6 +1156,45 @@ cudaError_t launch_rowdot_bf16(const void* W, const float* vec, float* out, int 
   return cudaGetLastError();
 }
 
+// ---- FP8 weight path: W[n][k] ~= scale[n] * e4m3(W8[n][k]), scale[n] = max_k |W[n][k]| / 448 (one warp per row) ----
+__global__ void quant_rows_e4m3_kernel(const bf16* __restrict__ W, uint8_t* __restrict__ W8, float* __restrict__ scale, int N, int K) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const bf16* wr = W + (long long)row * K;
+  float amax = 0.f;
+  for (int k = lane; k < K; k += 32) amax = fmaxf(amax, fabsf(__bfloat162float(wr[k])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  const float sc = amax > 0.f ? amax / 448.0f : 1.0f;
+  const float inv = 1.0f / sc;
+  for (int k = lane; k < K; k += 32)
+    W8[(long long)row * K + k] = (uint8_t)__nv_cvt_float_to_fp8(__bfloat162float(wr[k]) * inv, __NV_SATFINITE, __NV_E4M3);
+  if (lane == 0) scale[row] = sc;
+}
+cudaError_t launch_quant_rows_e4m3(const void* W, void* W8, float* scale, int N, int K, cudaStream_t st) {
+  quant_rows_e4m3_kernel<<<(N + 7) / 8, 256, 0, st>>>(reinterpret_cast<const bf16*>(W), reinterpret_cast<uint8_t*>(W8), scale, N, K);
+  return cudaGetLastError();
+}
+// out[n] = scale[n] * sum_k e4m3(W8[n][k]) * vec[k]: the LayerNorm-fold operands of the quantised matrices
+__global__ void rowdot_e4m3_kernel(const uint8_t* __restrict__ W8, const float* __restrict__ scale, const float* __restrict__ vec,
+                                   float* __restrict__ out, int N, int K) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const uint8_t* wr = W8 + (long long)row * K;
+  double acc = 0.0;
+  for (int k = lane; k < K; k += 32) {
+    const float w = __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)wr[k], __NV_E4M3)));
+    acc += (double)w * (double)(vec ? vec[k] : 1.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = (float)(acc * (double)scale[row]);
+}
+cudaError_t launch_rowdot_e4m3(const void* W8, const float* scale, const float* vec, float* out, int N, int K, cudaStream_t st) {
+  rowdot_e4m3_kernel<<<(N + 7) / 8, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(W8), scale, vec, out, N, K);
+  return cudaGetLastError();
+}
+
 static int stream_nrt(int batch) { return batch <= 1 ? 1 : (batch <= 2 ? 2 : (batch <= 4 ? 4 : 8)); }
 
 bool stream_supported(int batch, int d, int ffn, int n_heads, int vocab, int T, int num_sms) {
@@ -1089,11 +1206,13 @@ bool stream_supported(int batch, int d, int ffn, int n_heads, int vocab, int T, 
 // of floor / ceil(A / G) atoms; the CTAs with the smallest cumulative load take the ceil, so every CTA's share of the
 // step's read stream stays within one atom of the mean.  The head deals whole vocabulary tiles the same way.
 bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers, int T, int max_target, int num_sms,
-                 StreamPlan* plan, void* sched_out, void* cnt_out, void* xexp_out) {
+                 StreamPlan* plan, void* sched_out, void* cnt_out, void* xexp_out, int fp8) {
   (void)T; (void)max_target; (void)n_heads;
   const int G = num_sms, L = n_layers;
   const int nrt = stream_nrt(batch);
-  const int KAd = d / 64, KAf = ffn / 64;
+  const int kpa = fp8 ? 128 : 64;                  // k per atom (one 128-byte swizzle row of weights)
+  if (fp8 && (nrt > 4 || d % 128 || ffn % 128)) return false;
+  const int KAd = d / kpa, KAf = ffn / kpa;
   auto tiles = [](int n) { return (n + 127) / 128; };
   const int rowsN[6] = {3 * d, d, d, d, ffn, d};
   const int kas[6] = {KAd, KAd, KAd, KAd, KAd, KAf};
@@ -1181,10 +1300,15 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
 
 cudaError_t launch_decoder_stream(const StreamArgs& sa_in, const CUtensorMap& cross_map, const CUtensorMap& kc_map,
                                   const CUtensorMap& vc_map, int nrt, int num_sms, size_t smem_bytes, cudaStream_t st) {
-  void* fns[8] = {(void*)decoder_stream_kernel<1, false>, (void*)decoder_stream_kernel<2, false>, (void*)decoder_stream_kernel<4, false>,
-                  (void*)decoder_stream_kernel<8, false>, (void*)decoder_stream_kernel<1, true>, (void*)decoder_stream_kernel<2, true>,
-                  (void*)decoder_stream_kernel<4, true>, (void*)decoder_stream_kernel<8, true>};
-  const int slot = (nrt == 1 ? 0 : (nrt == 2 ? 1 : (nrt == 4 ? 2 : 3))) + (sa_in.m.timing ? 4 : 0);
+  void* fns[11] = {(void*)decoder_stream_kernel<1, false, false>, (void*)decoder_stream_kernel<2, false, false>,
+                   (void*)decoder_stream_kernel<4, false, false>, (void*)decoder_stream_kernel<8, false, false>,
+                   (void*)decoder_stream_kernel<1, true, false>, (void*)decoder_stream_kernel<2, true, false>,
+                   (void*)decoder_stream_kernel<4, true, false>, (void*)decoder_stream_kernel<8, true, false>,
+                   (void*)decoder_stream_kernel<1, false, true>, (void*)decoder_stream_kernel<2, false, true>,
+                   (void*)decoder_stream_kernel<4, false, true>};
+  if (sa_in.fp8 && (nrt > 4 || sa_in.m.timing)) return cudaErrorInvalidValue;
+  const int slot = sa_in.fp8 ? 8 + (nrt == 1 ? 0 : (nrt == 2 ? 1 : 2))
+                             : (nrt == 1 ? 0 : (nrt == 2 ? 1 : (nrt == 4 ? 2 : 3))) + (sa_in.m.timing ? 4 : 0);
   void* fn = fns[slot];
   static AttrOnce attr;
   if (attr.need(slot)) {

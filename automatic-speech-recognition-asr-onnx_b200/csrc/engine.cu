@@ -92,11 +92,16 @@ struct b200asr_engine {
   CUtensorMap cross_map{}; int cmap_B = -1, cmap_T = -1, cmap_rows = -1; int ring_task_inv = 0;
   // split-K tensor-core streaming decode kernel (decoder_stream.cu): the product path for prefill + greedy loop
   bool use_stream = true; bool stream_l2_hint = true; int stream_debug = 0; bool stream_multi = true;
-  StreamLayer* st_layers = nullptr; CUtensorMap* st_wmaps = nullptr; float* st_fold = nullptr;   // fold vectors (row sums, head g / b)
-  float* st_head_g = nullptr; float* st_head_b = nullptr;
+  // per weight format (0: bf16, 1: FP8 E4M3 + per-row scale, `set_option("fp8", 1)`): tensor maps, fold vectors, schedule
+  struct StreamTables {
+    StreamLayer* layers = nullptr; CUtensorMap* wmaps = nullptr; float* fold = nullptr;   // fold vectors (row sums, head g / b)
+    float* head_g = nullptr; float* head_b = nullptr; float* head_s = nullptr;
+    uint8_t* w8 = nullptr; float* scales = nullptr;                                        // FP8: quantised decoder matrices + tied head, their row scales
+    int4* sched = nullptr; unsigned char* cnt = nullptr; unsigned short* xexp = nullptr;
+    StreamPlan plans[4]; bool plan_ok[4] = {false, false, false, false}; bool tables = false;   // one plan per row-count class (1, 2, 4, 8)
+  } stt[2];
+  bool use_fp8 = false;
   unsigned long long* st_acc = nullptr; size_t st_acc_words = 0; unsigned long long* st_cand = nullptr; size_t st_cand_words = 0;
-  int4* st_sched = nullptr; unsigned char* st_cnt = nullptr; unsigned short* st_xexp = nullptr;
-  StreamPlan st_plans[4]; bool st_plan_ok[4] = {false, false, false, false}; bool st_tables = false;   // one plan per row-count class (1, 2, 4, 8)
   CUtensorMap st_cross{}, st_kc{}, st_vc{}; int st_map_B = -1, st_map_T = -1;
   std::string graph_key;
 
@@ -568,66 +573,104 @@ bool stream_ok(b200asr_engine* e) {
   if (!e->use_stream || e->samp_temperature > 0.f || e->act_dtype != kBF16 || e->penalty_range > 32) return false;
   if (!stream_supported(e->B, c.d_model, c.ffn, c.n_heads, c.vocab, e->T_enc, e->num_sms)) return false;
   const int slot = e->B <= 1 ? 0 : (e->B <= 2 ? 1 : (e->B <= 4 ? 2 : 3));
-  if (e->st_plan_ok[slot]) return true;
+  if (e->stt[e->use_fp8 ? 1 : 0].plan_ok[slot]) return true;
   StreamPlan pl;
   return stream_plan(e->B, c.d_model, c.ffn, c.n_heads, c.vocab, c.dec_layers, e->T_enc, c.max_target, e->num_sms, &pl,
-                     nullptr, nullptr, nullptr);
+                     nullptr, nullptr, nullptr, e->use_fp8 ? 1 : 0);
 }
 
 int build_stream_tables(b200asr_engine* e, int rows) {
   const b200asr_config& c = e->cfg;
   const int L = c.dec_layers, d = c.d_model, f = c.ffn;
-  if (!e->st_layers) {
+  const bool fp8 = e->use_fp8;
+  b200asr_engine::StreamTables& t = e->stt[fp8 ? 1 : 0];
+  if (!t.layers) {
     // LayerNorm-fold operands: row sums of the LN-consuming matrices, and the final LayerNorm folded around the tied head
     const size_t per_layer = (size_t)3 * d + d + f;
-    CK(cudaMalloc(&e->st_fold, (per_layer * L + 2 * (size_t)c.vocab) * sizeof(float)));
+    CK(cudaMalloc(&t.fold, (per_layer * L + 2 * (size_t)c.vocab) * sizeof(float)));
     std::vector<StreamLayer> hl(L);
     std::vector<CUtensorMap> maps((size_t)6 * L + 1);
     std::string msg;
+    const char* names[6] = {"qkv.w", "out.w", "cq.w", "cout.w", "fc1.w", "fc2.w"};
+    const int rowsN[6] = {3 * d, d, d, d, f, d}, cols[6] = {d, d, d, d, d, f};
+    const size_t layer_rows = (size_t)3 * d + 3 * (size_t)d + f + d;           // weight rows of one layer = scale entries
+    const size_t layer_bytes = (size_t)3 * d * d + 3 * (size_t)d * d + 2 * (size_t)f * d;
+    if (fp8) {
+      // FP8 weight path (the reference's q8 plans: Optimize_ONNX_Common.py:3860-4100): E4M3 with one scale per
+      // weight row, quantised once from the bf16 matrices; halves the bytes a greedy step streams
+      CK(cudaMalloc(&t.w8, layer_bytes * L + (size_t)c.vocab * d));
+      CK(cudaMalloc(&t.scales, (layer_rows * L + (size_t)c.vocab) * sizeof(float)));
+    }
     for (int l = 0; l < L; ++l) {
       const std::string p = "dec.L" + std::to_string(l) + ".";
-      float* base = e->st_fold + per_layer * l;
-      KL(launch_rowdot_bf16(W(e, p + "qkv.w"), nullptr, base, 3 * d, d, e->st));
-      KL(launch_rowdot_bf16(W(e, p + "cq.w"), nullptr, base + 3 * d, d, d, e->st));
-      KL(launch_rowdot_bf16(W(e, p + "fc1.w"), nullptr, base + 4 * d, f, d, e->st));
+      float* base = t.fold + per_layer * l;
+      hl[l] = StreamLayer{};
       hl[l].qkv_b = WF(e, p + "qkv.b"); hl[l].qkv_ws = base; hl[l].out_b = WF(e, p + "out.b");
       hl[l].cq_b = WF(e, p + "cq.b"); hl[l].cq_ws = base + 3 * d; hl[l].cout_b = WF(e, p + "cout.b");
       hl[l].fc1_b = WF(e, p + "fc1.b"); hl[l].fc1_ws = base + 4 * d; hl[l].fc2_b = WF(e, p + "fc2.b");
-      const char* names[6] = {"qkv.w", "out.w", "cq.w", "cout.w", "fc1.w", "fc2.w"};
-      const int rows[6] = {3 * d, d, d, d, f, d}, cols[6] = {d, d, d, d, d, f};
-      for (int i = 0; i < 6; ++i)
-        if (!make_tmap_rows_sw128(&maps[(size_t)l * 6 + i], W(e, p + names[i]), cols[i], rows[i], cols[i], 128, &msg))
-          return e->fail(B200ASR_E_CUDA, "decoder_stream: " + msg);
+      if (!fp8) {
+        KL(launch_rowdot_bf16(W(e, p + "qkv.w"), nullptr, base, 3 * d, d, e->st));
+        KL(launch_rowdot_bf16(W(e, p + "cq.w"), nullptr, base + 3 * d, d, d, e->st));
+        KL(launch_rowdot_bf16(W(e, p + "fc1.w"), nullptr, base + 4 * d, f, d, e->st));
+        for (int i = 0; i < 6; ++i)
+          if (!make_tmap_rows_sw128(&maps[(size_t)l * 6 + i], W(e, p + names[i]), cols[i], rowsN[i], cols[i], 128, &msg))
+            return e->fail(B200ASR_E_CUDA, "decoder_stream: " + msg);
+      } else {
+        uint8_t* wq = t.w8 + layer_bytes * l;
+        float* sc = t.scales + layer_rows * l;
+        const float* scs[6];
+        for (int i = 0; i < 6; ++i) {
+          KL(launch_quant_rows_e4m3(W(e, p + names[i]), wq, sc, rowsN[i], cols[i], e->st));
+          if (!make_tmap_rows_sw128_u8(&maps[(size_t)l * 6 + i], wq, cols[i], rowsN[i], cols[i], 128, &msg))
+            return e->fail(B200ASR_E_CUDA, "decoder_stream: " + msg);
+          if (i == 0) KL(launch_rowdot_e4m3(wq, sc, nullptr, base, 3 * d, d, e->st));
+          if (i == 2) KL(launch_rowdot_e4m3(wq, sc, nullptr, base + 3 * d, d, d, e->st));
+          if (i == 4) KL(launch_rowdot_e4m3(wq, sc, nullptr, base + 4 * d, f, d, e->st));
+          scs[i] = sc;
+          wq += (size_t)rowsN[i] * cols[i]; sc += rowsN[i];
+        }
+        hl[l].qkv_s = scs[0]; hl[l].out_s = scs[1]; hl[l].cq_s = scs[2]; hl[l].cout_s = scs[3]; hl[l].fc1_s = scs[4]; hl[l].fc2_s = scs[5];
+      }
     }
-    if (!make_tmap_rows_sw128(&maps[(size_t)6 * L], W(e, "dec.embed"), d, c.vocab, d, 128, &msg))
-      return e->fail(B200ASR_E_CUDA, "decoder_stream: " + msg);
-    e->st_head_g = e->st_fold + per_layer * L; e->st_head_b = e->st_head_g + c.vocab;
-    KL(launch_rowdot_bf16(W(e, "dec.embed"), WF(e, "dec.ln.g"), e->st_head_g, c.vocab, d, e->st));
-    KL(launch_rowdot_bf16(W(e, "dec.embed"), WF(e, "dec.ln.b"), e->st_head_b, c.vocab, d, e->st));
-    CK(cudaMalloc(&e->st_layers, sizeof(StreamLayer) * L));
-    CK(b200_copy_sync(e, e->st_layers, hl.data(), sizeof(StreamLayer) * L, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&e->st_wmaps, sizeof(CUtensorMap) * maps.size()));
-    CK(b200_copy_sync(e, e->st_wmaps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice));
+    t.head_g = t.fold + per_layer * L; t.head_b = t.head_g + c.vocab;
+    if (!fp8) {
+      if (!make_tmap_rows_sw128(&maps[(size_t)6 * L], W(e, "dec.embed"), d, c.vocab, d, 128, &msg))
+        return e->fail(B200ASR_E_CUDA, "decoder_stream: " + msg);
+      KL(launch_rowdot_bf16(W(e, "dec.embed"), WF(e, "dec.ln.g"), t.head_g, c.vocab, d, e->st));
+      KL(launch_rowdot_bf16(W(e, "dec.embed"), WF(e, "dec.ln.b"), t.head_b, c.vocab, d, e->st));
+    } else {
+      uint8_t* wq = t.w8 + layer_bytes * L;
+      t.head_s = t.scales + layer_rows * L;
+      KL(launch_quant_rows_e4m3(W(e, "dec.embed"), wq, t.head_s, c.vocab, d, e->st));
+      if (!make_tmap_rows_sw128_u8(&maps[(size_t)6 * L], wq, d, c.vocab, d, 128, &msg))
+        return e->fail(B200ASR_E_CUDA, "decoder_stream: " + msg);
+      KL(launch_rowdot_e4m3(wq, t.head_s, WF(e, "dec.ln.g"), t.head_g, c.vocab, d, e->st));
+      KL(launch_rowdot_e4m3(wq, t.head_s, WF(e, "dec.ln.b"), t.head_b, c.vocab, d, e->st));
+    }
+    CK(cudaMalloc(&t.layers, sizeof(StreamLayer) * L));
+    CK(b200_copy_sync(e, t.layers, hl.data(), sizeof(StreamLayer) * L, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&t.wmaps, sizeof(CUtensorMap) * maps.size()));
+    CK(b200_copy_sync(e, t.wmaps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice));
     int inv = 0;
     for (int i = 1; i < e->num_sms; ++i) if ((i * kRingTaskMul) % e->num_sms == 1) inv = i;
     e->ring_task_inv = inv;
   }
   const int slot = rows <= 1 ? 0 : (rows <= 2 ? 1 : (rows <= 4 ? 2 : 3));
-  if (!e->st_plan_ok[slot]) {
+  if (!t.plan_ok[slot]) {
     // the schedule tables depend on the model dimensions only; the plan (shared-memory split, accumulator sizes) on the row class
     std::vector<int4> sched; std::vector<unsigned char> cnt; std::vector<unsigned short> xexp;
     StreamPlan pl;
-    if (!stream_plan(rows, d, f, c.n_heads, c.vocab, L, e->T_enc, c.max_target, e->num_sms, &pl, &sched, &cnt, &xexp))
+    if (!stream_plan(rows, d, f, c.n_heads, c.vocab, L, e->T_enc, c.max_target, e->num_sms, &pl, &sched, &cnt, &xexp, fp8 ? 1 : 0))
       return e->fail(B200ASR_E_INVALID, "decoder_stream: plan does not fit");
     CK(cudaStreamSynchronize(e->st));
-    if (!e->st_tables) {
-      CK(cudaMalloc(&e->st_sched, sched.size() * sizeof(int4)));
-      CK(cudaMalloc(&e->st_cnt, cnt.size() + 16));
-      CK(cudaMalloc(&e->st_xexp, xexp.size() * 2 + 16));
-      CK(b200_copy_sync(e, e->st_sched, sched.data(), sched.size() * sizeof(int4), cudaMemcpyHostToDevice));
-      CK(b200_copy_sync(e, e->st_cnt, cnt.data(), cnt.size(), cudaMemcpyHostToDevice));
-      CK(b200_copy_sync(e, e->st_xexp, xexp.data(), xexp.size() * 2, cudaMemcpyHostToDevice));
-      e->st_tables = true;
+    if (!t.tables) {
+      CK(cudaMalloc(&t.sched, sched.size() * sizeof(int4)));
+      CK(cudaMalloc(&t.cnt, cnt.size() + 16));
+      CK(cudaMalloc(&t.xexp, xexp.size() * 2 + 16));
+      CK(b200_copy_sync(e, t.sched, sched.data(), sched.size() * sizeof(int4), cudaMemcpyHostToDevice));
+      CK(b200_copy_sync(e, t.cnt, cnt.data(), cnt.size(), cudaMemcpyHostToDevice));
+      CK(b200_copy_sync(e, t.xexp, xexp.data(), xexp.size() * 2, cudaMemcpyHostToDevice));
+      t.tables = true;
     }
     const size_t words = (size_t)pl.set_words * 2;
     if (words > e->st_acc_words) {
@@ -640,7 +683,7 @@ int build_stream_tables(b200asr_engine* e, int rows) {
       CK(cudaMalloc(&e->st_cand, pl.cand_words * 8));
       e->st_cand_words = pl.cand_words;
     }
-    e->st_plans[slot] = pl; e->st_plan_ok[slot] = true;
+    t.plans[slot] = pl; t.plan_ok[slot] = true;
   }
   if (e->st_map_B != e->B || e->st_map_T != e->T_enc) {
     std::string msg;
@@ -661,13 +704,14 @@ static int launch_stream(b200asr_engine* e, int rows, int n_heads_iters, const i
                          bool want_logits, bool multi) {
   RET(build_stream_tables(e, rows));
   const int slot = rows <= 1 ? 0 : (rows <= 2 ? 1 : (rows <= 4 ? 2 : 3));
-  const StreamPlan& pl = e->st_plans[slot];
+  const b200asr_engine::StreamTables& t = e->stt[e->use_fp8 ? 1 : 0];
+  const StreamPlan& pl = t.plans[slot];
   StreamArgs sa{};
   fill_mega_args(e, sa.m, n_heads_iters, first_tokens, n_first, first_is_prefill, want_logits);
   RET(arm_timing(e, sa.m));
-  sa.sl = e->st_layers; sa.wmaps = e->st_wmaps; sa.head_g = e->st_head_g; sa.head_b = e->st_head_b;
+  sa.sl = t.layers; sa.wmaps = t.wmaps; sa.head_g = t.head_g; sa.head_b = t.head_b; sa.head_s = t.head_s; sa.fp8 = e->use_fp8 ? 1 : 0;
   sa.acc = e->st_acc; sa.set_words = pl.set_words; sa.layer_words = pl.layer_words;
-  sa.cand = e->st_cand; sa.sched = e->st_sched; sa.cnt = e->st_cnt; sa.xexp = e->st_xexp;
+  sa.cand = e->st_cand; sa.sched = t.sched; sa.cnt = t.cnt; sa.xexp = t.xexp;
   sa.cnt_ld = pl.cnt_ld; sa.xt = pl.xt; sa.n_stages = pl.n_stages; sa.n_slots = pl.n_slots;
   sa.task_inv = e->ring_task_inv; sa.l2_hint = e->stream_l2_hint ? 1 : 0; sa.debug = e->stream_debug; sa.multi = multi ? 1 : 0;
   CK(cudaMemsetAsync(e->st_acc, 0, (size_t)pl.set_words * 2 * 8, e->st));
@@ -682,7 +726,8 @@ static int launch_stream(b200asr_engine* e, int rows, int n_heads_iters, const i
 // otherwise the prompt is fed token by token inside a single launch.
 int run_stream(b200asr_engine* e, int n_heads_iters, const int* first_tokens, int n_first, bool first_is_prefill, bool want_logits) {
   const int B = e->B;
-  if (n_first > 1 && B * n_first <= kStreamMaxBatch && e->stream_multi) {
+  const int max_rows = e->use_fp8 ? 4 : kStreamMaxBatch;      // the FP8 kernel stages four E5M2 rows per activation row: 16 / 4
+  if (n_first > 1 && B * n_first <= max_rows && e->stream_multi) {
     RET(launch_stream(e, B * n_first, 1, first_tokens, n_first, first_is_prefill, want_logits, true));
     if (n_heads_iters > 1) RET(launch_stream(e, B, n_heads_iters - 1, e->cur_token, 1, false, want_logits, false));
     return B200ASR_OK;
@@ -725,9 +770,17 @@ int do_upload(b200asr_engine* e, const void* pcm_host, int32_t pcm_dtype, int32_
   return B200ASR_OK;
 }
 
+// set_option("fp8", 1) is a request for the FP8 streaming kernel: no silent fall-back to a bf16 decoder
+int fp8_guard(b200asr_engine* e) {
+  if (e->use_fp8 && !stream_ok(e))
+    return e->fail(B200ASR_E_INVALID, "fp8 weights run in the streaming decode kernel only: bf16 engine, batch <= 4, d_model and ffn multiples of 128, arg-max heads");
+  return B200ASR_OK;
+}
+
 int do_prefill(b200asr_engine* e, const int32_t* prompt_ids, int32_t n_prompt, int extra_iters = 0) {
   const b200asr_config& c = e->cfg;
   if (!e->encoded) return e->fail(B200ASR_E_INVALID, "prefill before encode");
+  RET(fp8_guard(e));
   if (!prompt_ids || n_prompt <= 0 || n_prompt >= c.max_target) return e->fail(B200ASR_E_INVALID, "bad prompt");
   const int B = e->B;
   for (int i = 0; i < B * n_prompt; ++i)
@@ -811,7 +864,10 @@ void b200asr_destroy(b200asr_engine* e) {
                   e->dx, e->dq, e->dctx, e->dffn, e->logits, e->prob, e->d_prompt, e->cur_token, e->tokens, e->n_gen,
                   e->finished, e->save_id, e->n_save, e->selected_hist, e->d_stop, e->dstate, e->mega_layers, e->pf_blocks,
                   e->mega_bar, e->cand_val, e->cand_idx, e->timing, e->ring_ll, e->samp_noise,
-                  e->st_layers, e->st_wmaps, e->st_fold, e->st_acc, e->st_cand, e->st_sched, e->st_cnt, e->st_xexp};
+                  e->st_acc, e->st_cand,
+                  e->stt[0].layers, e->stt[0].wmaps, e->stt[0].fold, e->stt[0].sched, e->stt[0].cnt, e->stt[0].xexp,
+                  e->stt[1].layers, e->stt[1].wmaps, e->stt[1].fold, e->stt[1].sched, e->stt[1].cnt, e->stt[1].xexp,
+                  e->stt[1].w8, e->stt[1].scales};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -830,6 +886,7 @@ int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "stream_l2_hint")) { e->stream_l2_hint = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "stream_debug")) { e->stream_debug = (int)value; return B200ASR_OK; }
   if (!strcmp(key, "stream_multi")) { e->stream_multi = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "fp8")) { e->use_fp8 = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring")) { e->use_ring = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_tc")) { e->ring_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_debug")) { e->ring_debug = (int)value; return B200ASR_OK; }
@@ -884,9 +941,11 @@ int b200asr_set_tensor(b200asr_engine* e, const char* name_c, const float* host,
   e->finalized = false;
   if (e->enc_graph) { cudaGraphExecDestroy(e->enc_graph); e->enc_graph = nullptr; }      // weight pointers are baked into its nodes
   // tables that cache weight pointers (tensor maps, fold vectors, layer tables) are rebuilt on the next decoder launch
-  if (e->st_layers) {
-    cudaFree(e->st_layers); cudaFree(e->st_wmaps); cudaFree(e->st_fold);
-    e->st_layers = nullptr; e->st_wmaps = nullptr; e->st_fold = nullptr;
+  for (auto& t : e->stt) {
+    if (!t.layers) continue;
+    cudaFree(t.layers); cudaFree(t.wmaps); cudaFree(t.fold);
+    t.layers = nullptr; t.wmaps = nullptr; t.fold = nullptr;
+    if (t.w8) { cudaFree(t.w8); cudaFree(t.scales); t.w8 = nullptr; t.scales = nullptr; t.head_s = nullptr; }
   }
   if (e->mega_layers) { cudaFree(e->mega_layers); e->mega_layers = nullptr; cudaFree(e->pf_blocks); e->pf_blocks = nullptr;
                         cudaFree(e->mega_bar); e->mega_bar = nullptr; cudaFree(e->cand_val); e->cand_val = nullptr;

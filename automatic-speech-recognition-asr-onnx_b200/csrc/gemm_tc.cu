@@ -322,6 +322,24 @@ bool make_tmap_rows_sw128(CUtensorMap* tm, const void* base, int64_t cols, int64
   return make_tmap(tm, base, cols, rows, 1, ld, 0, box_rows, err);
 }
 
+bool make_tmap_rows_sw128_u8(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_rows,
+                             std::string* err) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { if (err) *err = "cuTensorMapEncodeTiled entry point not found"; return false; }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)ld * (cuuint64_t)rows};
+  cuuint32_t box[3] = {128, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled (u8) failed with CUresult " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
+
 bool make_tmap_2d_plain(CUtensorMap* tm, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_cols,
                         int box_rows, std::string* err) {
   EncodeTiledFn fn = get_encode_fn();
