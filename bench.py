@@ -118,12 +118,14 @@ def measured_peaks():
         return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes_per_decode_step(dims, batch, T_enc, kv_mid):
-    """HBM bytes one decode launch must move in bf16 (DESIGN.md 'Roofline'): every decoder weight once,
-    the tied lm-head once, cross-KV of every utterance, the self-KV read so far."""
+def algorithmic_bytes_per_decode_step(dims, batch, T_enc, kv_mid, weight_bytes=2):
+    """HBM bytes one decode launch must move (DESIGN.md 'Roofline'): every decoder weight once (bf16, or 1 byte + a row scale
+    with FP8 weights), the tied lm-head once, cross-KV of every utterance, the self-KV read so far (bf16)."""
     d, f, L = dims.d_model, dims.ffn, dims.dec_layers
     per_layer = (3 * d * d) + (d * d) * 3 + 2 * d * f           # qkv, out, cq, cout, fc1, fc2
-    weights = (L * per_layer + dims.vocab * d) * 2
+    weights = (L * per_layer + dims.vocab * d) * weight_bytes
+    if weight_bytes == 1:
+        weights += 4 * (L * (3 * d + 3 * d + f + d) + dims.vocab)
     cross = batch * L * 2 * T_enc * d * 2
     self_kv = batch * L * 2 * kv_mid * d * 2
     return weights + cross + self_kv
@@ -622,6 +624,24 @@ def main():
         if 32 % world == 0:
             extra["config3_global32"] = whisper_batch(32 // world, 2)
             extra["config3_global32"]["workload"] = f"fixed global batch 32: {32 // world} clips/GPU x {world} GPU(s), launches of <= 8 clips"
+        # low-bit weight option: the same workload with E4M3 decoder weights; NOT the headline (BASELINE's dtype is bf16)
+        eng.set_option("fp8", 1)
+        for _ in range(3):
+            step_e2e()
+        ms8 = timed(step_e2e, max(3, args.steps // 2)) / max(3, args.steps // 2)
+        eng.upload_pcm(pcm_np); eng.encode_resident()
+        eng.prefill(prompt, want_logits=False); eng.decode(max_steps=4)
+        eng.prefill(prompt, want_logits=False)
+        dec8 = timed(lambda: eng.decode(max_steps=DECODE_LAUNCHES), 1) / DECODE_LAUNCHES
+        bytes8 = algorithmic_bytes_per_decode_step(dims, B, T_enc, len(prompt) + DECODE_LAUNCHES // 2, weight_bytes=1)
+        extra["fp8_weights"] = {
+            "workload": "headline workload with set_option('fp8', 1): decoder matrices + tied head as E4M3 with per-row scales through "
+                        "tcgen05.mma kind::f8f6f4 (encoder, K/V caches, residual stream unchanged); parity statement in tests/test_gpu_fp8.py",
+            "e2e": {"value": audio_s * B * world / (ms8 / 1e3), "unit": "x real time", "ms_per_step": ms8},
+            "roofline": {"kernel": "decoder_stream_kernel<NRT, F8>", "bound": "hbm", "achieved": bytes8 / (dec8 / 1e3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": bytes8 / (dec8 / 1e3) / 1e9 / hbm_peak, "ms_per_launch": dec8,
+                         "algorithmic_bytes_per_launch": bytes8, "traffic": None, "peak_source": peak_src}}
+        eng.set_option("fp8", 0)
         eng.close()
         import copy
         pa = copy.copy(args); pa.preset = "paraformer-large"; pa.batch_per_gpu = 8; pa.steps = 10; pa.warmup = 3
