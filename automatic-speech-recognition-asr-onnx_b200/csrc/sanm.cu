@@ -89,9 +89,11 @@ kaldi_fbank_kernel(const void* __restrict__ pcm, int pcm_is_f32, int n_samples, 
 __global__ void lfr_cmvn_kernel(const float* __restrict__ mel, int frames, int n_mels, int lfr_m, int lfr_n, int T_lfr, int n_prompt,
                                 const float* __restrict__ means, const float* __restrict__ vars, const float* __restrict__ pos,
                                 const float* __restrict__ lang_embed, const float* __restrict__ sys_embed,
-                                const int* __restrict__ lang_idx, float* __restrict__ x /*[B][n_prompt + T_lfr][feat]*/) {
+                                const int* __restrict__ lang_idx, float* __restrict__ x /*[B][n_prompt + T_lfr][feat]*/,
+                                const int* __restrict__ frames_per_clip /*ragged batch: fbank frames of each clip, or null*/) {
   const int feat = n_mels * lfr_m;
   const int t = blockIdx.x, b = blockIdx.y;
+  const int frames_b = frames_per_clip ? frames_per_clip[b] : frames;     // the clamped gather repeats the clip's OWN last frame
   float* xr = x + ((int64_t)b * (n_prompt + T_lfr) + t) * feat;
   if (t < n_prompt) {
     const float* src = t == 0 ? lang_embed + (int64_t)lang_idx[b] * feat : sys_embed + (int64_t)(t - 1) * feat;
@@ -103,7 +105,7 @@ __global__ void lfr_cmvn_kernel(const float* __restrict__ mel, int frames, int n
   for (int c = threadIdx.x; c < feat; c += blockDim.x) {
     const int j = c / n_mels, m = c - j * n_mels;
     int fr = tl * lfr_n + j - half;
-    fr = max(0, min(fr, frames - 1));
+    fr = max(0, min(fr, frames_b - 1));
     const float v = mel[((int64_t)b * frames + fr) * n_mels + m];
     xr[c] = (means ? (v + means[c]) * vars[c] : v * vars[c]) + pos[(int64_t)tl * feat + c];
   }
@@ -113,15 +115,16 @@ __global__ void lfr_cmvn_kernel(const float* __restrict__ mel, int frames, int n
 template <typename T>
 __global__ void fsmn_kernel(const T* __restrict__ qkv, int64_t ld_qkv, int v_off, const float* __restrict__ w /*[D][k]*/,
                             const float* __restrict__ bias, const float* __restrict__ resid /*[M][D] or null*/, int Tn, int D, int ksz,
-                            float* __restrict__ out /*[M][D]*/) {
+                            float* __restrict__ out /*[M][D]*/, const int* __restrict__ t_valid = nullptr /*ragged batch: rows per clip*/) {
   const int t = blockIdx.x, b = blockIdx.y;
   const int half = (ksz - 1) / 2;
   const int64_t row0 = (int64_t)b * Tn;
+  const int Tv = t_valid ? t_valid[b] : Tn;             // the conv's zero padding starts at the clip's own end
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float acc = bias[c];
     for (int j = 0; j < ksz; ++j) {
       const int tt = t + j - half;
-      if (tt >= 0 && tt < Tn) acc = fmaf(w[c * ksz + j], to_f<T>(qkv[(row0 + tt) * ld_qkv + v_off + c]), acc);
+      if (tt >= 0 && tt < Tv) acc = fmaf(w[c * ksz + j], to_f<T>(qkv[(row0 + tt) * ld_qkv + v_off + c]), acc);
     }
     if (resid) acc += resid[(row0 + t) * D + c];
     out[(row0 + t) * D + c] = acc;
@@ -147,13 +150,14 @@ row_argmax_kernel(const float* __restrict__ logits, int rows, int vocab, int* __
 }
 // keep frame t when id[t] != id[(t+1) % T] and id[t] != blank (Export_SenseVoice.py:289-294)
 __global__ void ctc_collapse_kernel(const int* __restrict__ ids, int Tn, int blank, int* __restrict__ tokens, int tokens_ld,
-                                    int* __restrict__ lens) {
+                                    int* __restrict__ lens, const int* __restrict__ t_valid) {
   const int b = blockIdx.x;
   if (threadIdx.x != 0) return;
   const int* r = ids + (int64_t)b * Tn;
+  const int Tv = t_valid ? t_valid[b] : Tn;             // ragged batch: the clip's own frames (the roll wraps at ITS end)
   int n = 0;
-  for (int t = 0; t < Tn; ++t) {
-    const int id = r[t], nx = r[t + 1 == Tn ? 0 : t + 1];
+  for (int t = 0; t < Tv; ++t) {
+    const int id = r[t], nx = r[t + 1 == Tv ? 0 : t + 1];
     if (id != nx && id != blank && n < tokens_ld) tokens[(int64_t)b * tokens_ld + n++] = id;
   }
   lens[b] = n;
@@ -180,12 +184,14 @@ cif_alpha_kernel(const T* __restrict__ conv, const float* __restrict__ w, const 
 // difference of the weighted hidden prefix sums completed at consecutive fires.  One CTA per utterance.
 __global__ void __launch_bounds__(256)
 cif_scan_kernel(float* __restrict__ alphas /*[B][Tn+1]: tail written here*/, float tail, const float* __restrict__ enc /*[B][Tn][D]*/,
-                int Tn, int D, float* __restrict__ acoustic /*[B][Tn+1][D]*/, int* __restrict__ n_tok) {
+                int Tn_ld, int D, float* __restrict__ acoustic /*[B][Tn+1][D]*/, int* __restrict__ n_tok,
+                const int* __restrict__ t_valid /*ragged batch: encoder frames per clip, or null*/) {
   extern __shared__ float cs[];            // prefix[Tn+1] | fire flags as float [Tn+1]
   float* prefix = cs;
-  float* fire = cs + Tn + 1;
+  float* fire = cs + Tn_ld + 1;
   const int b = blockIdx.x;
-  float* a = alphas + (int64_t)b * (Tn + 1);
+  const int Tn = t_valid ? t_valid[b] : Tn_ld;          // the tail threshold is appended after the clip's own last frame
+  float* a = alphas + (int64_t)b * (Tn_ld + 1);
   if (threadIdx.x == 0) {
     a[Tn] = tail;
     double acc = 0.0;
@@ -201,8 +207,8 @@ cif_scan_kernel(float* __restrict__ alphas /*[B][Tn+1]: tail written here*/, flo
     n_tok[b] = (int)floorf(prefix[Tn]);
   }
   __syncthreads();
-  const float* h = enc + (int64_t)b * Tn * D;
-  float* out = acoustic + (int64_t)b * (Tn + 1) * D;
+  const float* h = enc + (int64_t)b * Tn_ld * D;
+  float* out = acoustic + (int64_t)b * (Tn_ld + 1) * D;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     double acc = 0.0;                       // torch's CPU cumsum accumulates float32 inputs in double
     float prev = 0.f;
@@ -226,11 +232,13 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, int n, int rows,
   for (int c = threadIdx.x; c < D; c += blockDim.x) dst[(int64_t)r * D + c] = r < n ? src[(int64_t)r * D + c] : 0.f;
 }
 template <typename T>
-__global__ void pad_rows_kernel(const float* __restrict__ src /*[B][Tn][D]*/, int Tn, int D, int pad, T* __restrict__ dst /*[B][Tn+2*pad][D]*/) {
+__global__ void pad_rows_kernel(const float* __restrict__ src /*[B][Tn][D]*/, int Tn, int D, int pad, T* __restrict__ dst /*[B][Tn+2*pad][D]*/,
+                                const int* __restrict__ t_valid) {
   const int t = blockIdx.x, b = blockIdx.y;      // t in [0, Tn + 2*pad)
   const int ts = t - pad;
+  const int Tv = t_valid ? t_valid[b] : Tn;      // ragged batch: zeros from the clip's own end on
   for (int c = threadIdx.x; c < D; c += blockDim.x)
-    dst[((int64_t)b * (Tn + 2 * pad) + t) * D + c] = from_f<T>((ts >= 0 && ts < Tn) ? src[((int64_t)b * Tn + ts) * D + c] : 0.f);
+    dst[((int64_t)b * (Tn + 2 * pad) + t) * D + c] = from_f<T>((ts >= 0 && ts < Tv) ? src[((int64_t)b * Tn + ts) * D + c] : 0.f);
 }
 
 // ---- Paraformer decoder over all clips of a batch at once: the decoder rows of the clips are stacked (clip b owns rows
@@ -288,7 +296,7 @@ template <> struct NVec<bf16> {
 template <typename T, int DH>
 __global__ void __launch_bounds__(128)
 para_cross_attn_kernel(const T* __restrict__ q /*[rows][D]*/, const T* __restrict__ kv /*[B*Tn][2D]: k | v*/, const int* __restrict__ seg_off,
-                       int B, int Tn, int H, int total, T* __restrict__ ctx /*[rows][D]*/) {
+                       int B, int Tn_ld, int H, int total, T* __restrict__ ctx /*[rows][D]*/, const int* __restrict__ t_valid) {
   extern __shared__ float csm[];                 // per warp: q[DH] + scores[Tn]
   constexpr int M = DH / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -297,12 +305,13 @@ para_cross_attn_kernel(const T* __restrict__ q /*[rows][D]*/, const T* __restric
   const int row = item / H, h = item - row * H;
   const int D = H * DH;
   const int b = seg_find(seg_off, B, row);
-  float* qs = csm + warp * (DH + Tn);
+  const int Tn = t_valid ? t_valid[b] : Tn_ld;          // ragged batch: the clip's own encoder memory
+  float* qs = csm + warp * (DH + Tn_ld);
   float* sc = qs + DH;
 #pragma unroll
   for (int m = 0; m < M; ++m) qs[lane + 32 * m] = to_f<T>(q[(int64_t)row * D + h * DH + lane + 32 * m]);
   __syncwarp();
-  const T* K = kv + (int64_t)b * Tn * 2 * D + h * DH;
+  const T* K = kv + (int64_t)b * Tn_ld * 2 * D + h * DH;
   const T* V = K + D;
   float mx = -INFINITY;
   for (int j = lane; j < Tn; j += 32) {
@@ -386,6 +395,10 @@ struct b200asr_nar {
   bool use_graph = true; cudaGraphExec_t graph = nullptr; int graph_B = -1, graph_N = -1, graph_dtype = -1; int64_t graph_nodes = 0;
   int* h_pinned = nullptr;
   int max_frames = 0, max_T = 0;
+  // ragged batch (b200asr_nar_*_ragged): device [2][max_batch] = fbank frames per clip | encoder rows per clip (prompt rows included)
+  int* d_meta = nullptr; bool ragged = false; std::vector<int> h_meta;
+  const int* dev_frames() const { return ragged ? d_meta : nullptr; }
+  const int* dev_tvalid() const { return ragged ? d_meta + cfg.max_batch : nullptr; }
 
   int fail(int code, const std::string& m) { err = m; return code; }
   int cuda_fail(cudaError_t e, const char* what) { err = std::string(what) + ": " + cudaGetErrorString(e); return B200ASR_E_CUDA; }
@@ -461,13 +474,13 @@ int nar_block(b200asr_nar* e, const std::string& p, const std::string& fsmn_bias
   // FSMN memory (+ x when the block keeps its width) -> the fp32 residual the out-projection adds
   const float* res_in = (din == D) ? x_in : nullptr;
   if (ad == kBF16)
-    fsmn_kernel<bf16><<<dim3(T, B), 256, 0, e->st>>>((const bf16*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, fsmn_bias), res_in, T, D, c.fsmn_kernel, e->resid);
+    fsmn_kernel<bf16><<<dim3(T, B), 256, 0, e->st>>>((const bf16*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, fsmn_bias), res_in, T, D, c.fsmn_kernel, e->resid, e->dev_tvalid());
   else
-    fsmn_kernel<float><<<dim3(T, B), 256, 0, e->st>>>((const float*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, fsmn_bias), res_in, T, D, c.fsmn_kernel, e->resid);
+    fsmn_kernel<float><<<dim3(T, B), 256, 0, e->st>>>((const float*)e->qkv, 3 * D, 2 * D, NWF(e, p + "fsmn.w"), NWF(e, fsmn_bias), res_in, T, D, c.fsmn_kernel, e->resid, e->dev_tvalid());
   NKL(cudaGetLastError());
   if (ad == kBF16 && c.use_tensor_cores && e->use_attn_tc && attention_tc_supported(T, D, H)) {
     std::string msg;
-    cudaError_t r = launch_attention_tc(e->qkv, e->ctx, B, T, D, H, e->st, &msg);
+    cudaError_t r = launch_attention_tc(e->qkv, e->ctx, B, T, D, H, e->st, &msg, e->dev_tvalid(), -1e30f);
     e->launches++;
     if (r != cudaSuccess) return e->fail(B200ASR_E_CUDA, "attention_tc: " + (msg.empty() ? std::string(cudaGetErrorString(r)) : msg));
   } else {
@@ -477,7 +490,7 @@ int nar_block(b200asr_nar* e, const std::string& p, const std::string& fsmn_bias
     s.C = e->S; s.ldc = T; s.sCo = (int64_t)H * T * T; s.sCi = (int64_t)T * T; s.c_dtype = kF32;
     s.M = T; s.N = T; s.K = dh; s.batch = B * H; s.batch_inner = H;
     NKL(launch_gemm_simt(s, e->st));
-    NKL(launch_softmax_rows(e->S, e->P, ad, (int64_t)B * H * T, T, e->st));
+    NKL(launch_softmax_rows(e->S, e->P, ad, (int64_t)B * H * T, T, e->st, e->dev_tvalid(), (int64_t)H * T));
     GemmArgs o;
     o.A = e->P; o.lda = T; o.sAo = (int64_t)H * T * T; o.sAi = (int64_t)T * T; o.a_dtype = ad;
     o.B = (char*)e->qkv + (size_t)2 * D * es; o.ldb = 3 * D; o.sBo = (int64_t)T * 3 * D; o.sBi = dh; o.b_dtype = ad;
@@ -522,7 +535,7 @@ int sensevoice_forward(b200asr_nar* e) {
   NRET(nar_fbank(e));
   lfr_cmvn_kernel<<<dim3(T, B), 256, 0, e->st>>>(e->mel, e->frames, c.n_mels, c.lfr_m, c.lfr_n, e->T_lfr, c.n_prompt,
                                                  NWF(e, "cmvn_means"), NWF(e, "cmvn_vars"), NWF(e, "speech_position"),
-                                                 NWF(e, "language_embed"), NWF(e, "system_embed"), e->lang, e->feats);
+                                                 NWF(e, "language_embed"), NWF(e, "system_embed"), e->lang, e->feats, e->dev_frames());
   NKL(cudaGetLastError());
   const int n_main = c.n_blocks0 + c.n_blocks, n_all = n_main + c.n_tp_blocks;
   for (int i = 0; i < n_all; ++i) {
@@ -536,7 +549,7 @@ int sensevoice_forward(b200asr_nar* e) {
   NRET(nar_gemm(e, nar_linear(e, e->xhat, D, "ctc.w", "ctc.b", e->logits, c.vocab, kF32, M, c.vocab, D)));
   row_argmax_kernel<<<(M + 7) / 8, 256, 0, e->st>>>(e->logits, M, c.vocab, e->frame_ids);
   NKL(cudaGetLastError());
-  ctc_collapse_kernel<<<B, 32, 0, e->st>>>(e->frame_ids, T, c.blank_id, e->tokens, e->max_T, e->lens);
+  ctc_collapse_kernel<<<B, 32, 0, e->st>>>(e->frame_ids, T, c.blank_id, e->tokens, e->max_T, e->lens, e->dev_tvalid());
   NKL(cudaGetLastError());
   return B200ASR_OK;
 }
@@ -578,7 +591,7 @@ int paraformer_decode_one(b200asr_nar* e, int b, int n_tok) {
     sgm.C = e->S; sgm.ldc = T; sgm.sCi = (int64_t)rows * T; sgm.c_dtype = kF32;
     sgm.M = rows; sgm.N = T; sgm.K = dh; sgm.batch = H; sgm.batch_inner = H;
     NKL(launch_gemm_simt(sgm, e->st));
-    NKL(launch_softmax_rows(e->S, e->P, ad, (int64_t)H * rows, T, e->st));
+    NKL(launch_softmax_rows(e->S, e->P, ad, (int64_t)H * rows, T, e->st, e->ragged ? e->dev_tvalid() + b : nullptr, (int64_t)H * rows));
     GemmArgs o;
     o.A = e->P; o.lda = T; o.sAi = (int64_t)rows * T; o.a_dtype = ad;
     o.B = (char*)e->kvbuf + (size_t)D * es; o.ldb = 2 * D; o.sBi = dh; o.b_dtype = ad; o.transB = 1;
@@ -629,8 +642,8 @@ int paraformer_decode_all(b200asr_nar* e, int rows) {
     NRET(nar_gemm(e, nar_linear(e, e->dq, D, p + "q.w", p + "q.b", e->qkv, D, ad, rows, D, D)));
     NRET(nar_gemm(e, nar_linear(e, e->xhat, D, p + "kv.w", p + "kv.b", e->kvbuf, 2 * D, ad, B * T, 2 * D, D)));
     const int total = rows * H;
-    if (ad == kBF16) para_cross_attn_kernel<bf16, DH><<<(total + 3) / 4, 128, smem, e->st>>>((const bf16*)e->qkv, (const bf16*)e->kvbuf, e->seg_off, B, T, H, total, (bf16*)e->ctx);
-    else para_cross_attn_kernel<float, DH><<<(total + 3) / 4, 128, smem, e->st>>>((const float*)e->qkv, (const float*)e->kvbuf, e->seg_off, B, T, H, total, (float*)e->ctx);
+    if (ad == kBF16) para_cross_attn_kernel<bf16, DH><<<(total + 3) / 4, 128, smem, e->st>>>((const bf16*)e->qkv, (const bf16*)e->kvbuf, e->seg_off, B, T, H, total, (bf16*)e->ctx, e->dev_tvalid());
+    else para_cross_attn_kernel<float, DH><<<(total + 3) / 4, 128, smem, e->st>>>((const float*)e->qkv, (const float*)e->kvbuf, e->seg_off, B, T, H, total, (float*)e->ctx, e->dev_tvalid());
     NKL(cudaGetLastError());
     GemmArgs g = nar_linear(e, e->ctx, D, p + "cout.w", p + "cout.b", e->dec, D, kF32, rows, D, D);
     g.residual = e->dx; g.ldr = D;
@@ -656,7 +669,7 @@ int paraformer_encoder(b200asr_nar* e) {
   const int feat = c.n_mels * c.lfr_m, D = c.d_model, B = e->B, T = e->T, M = B * T, ad = e->act;
   NRET(nar_fbank(e));
   lfr_cmvn_kernel<<<dim3(T, B), 256, 0, e->st>>>(e->mel, e->frames, c.n_mels, c.lfr_m, c.lfr_n, e->T_lfr, 0, nullptr,
-                                                 NWF(e, "cmvn_vars"), NWF(e, "encoder_input_bias"), nullptr, nullptr, e->lang, e->feats);
+                                                 NWF(e, "cmvn_vars"), NWF(e, "encoder_input_bias"), nullptr, nullptr, e->lang, e->feats, e->dev_frames());
   NKL(cudaGetLastError());
   const int n_enc = c.n_blocks0 + c.n_blocks;
   for (int i = 0; i < n_enc; ++i) {
@@ -667,8 +680,8 @@ int paraformer_encoder(b200asr_nar* e) {
   NKL(launch_layernorm(e->hidden, D, NWF(e, "enc_after_norm.g"), NWF(e, "enc_after_norm.b"), e->xhat, ad, D, M, D, c.ln_eps, e->st));
   // CIF: conv k over time as a GEMM on the zero-padded, overlapping-row view (row t = k*D contiguous values from padded row t)
   const int pad = (c.cif_kernel - 1) / 2;
-  if (ad == kBF16) pad_rows_kernel<bf16><<<dim3(T + 2 * pad, B), 128, 0, e->st>>>(e->enc_out, T, D, pad, (bf16*)e->enc_pad);
-  else pad_rows_kernel<float><<<dim3(T + 2 * pad, B), 128, 0, e->st>>>(e->enc_out, T, D, pad, (float*)e->enc_pad);
+  if (ad == kBF16) pad_rows_kernel<bf16><<<dim3(T + 2 * pad, B), 128, 0, e->st>>>(e->enc_out, T, D, pad, (bf16*)e->enc_pad, e->dev_tvalid());
+  else pad_rows_kernel<float><<<dim3(T + 2 * pad, B), 128, 0, e->st>>>(e->enc_out, T, D, pad, (float*)e->enc_pad, e->dev_tvalid());
   NKL(cudaGetLastError());
   {
     GemmArgs g = nar_linear(e, e->enc_pad, D, "cif.conv.w", "cif.conv.b", e->conv_out, D, ad, T, D, c.cif_kernel * D);
@@ -678,7 +691,7 @@ int paraformer_encoder(b200asr_nar* e) {
   if (ad == kBF16) cif_alpha_kernel<bf16><<<(M + 7) / 8, 256, 0, e->st>>>((const bf16*)e->conv_out, NWF(e, "cif.out.w"), NWF(e, "cif.out.b"), M, D, e->alphas, T);
   else cif_alpha_kernel<float><<<(M + 7) / 8, 256, 0, e->st>>>((const float*)e->conv_out, NWF(e, "cif.out.w"), NWF(e, "cif.out.b"), M, D, e->alphas, T);
   NKL(cudaGetLastError());
-  cif_scan_kernel<<<B, 256, (size_t)2 * (T + 1) * sizeof(float), e->st>>>(e->alphas, c.tail_threshold, e->enc_out, T, D, e->acoustic, e->n_tok);
+  cif_scan_kernel<<<B, 256, (size_t)2 * (T + 1) * sizeof(float), e->st>>>(e->alphas, c.tail_threshold, e->enc_out, T, D, e->acoustic, e->n_tok, e->dev_tvalid());
   NKL(cudaGetLastError());
   return B200ASR_OK;
 }
@@ -710,7 +723,8 @@ int paraformer_forward(b200asr_nar* e) {
 }
 
 int nar_graph_run(b200asr_nar* e, int (*fn)(b200asr_nar*)) {
-  if (!e->graph || e->graph_B != e->B || e->graph_N != e->n_samples || e->graph_dtype != e->pcm_dtype) {
+  const int dtype_key = e->pcm_dtype + (e->ragged ? 16 : 0);          // (per-clip lengths are read from device memory: one graph per shape)
+  if (!e->graph || e->graph_B != e->B || e->graph_N != e->n_samples || e->graph_dtype != dtype_key) {
     if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
     cudaGraph_t g = nullptr;
     const int64_t before = e->launches;
@@ -724,7 +738,7 @@ int nar_graph_run(b200asr_nar* e, int (*fn)(b200asr_nar*)) {
     const cudaError_t ci = cudaGraphInstantiate(&e->graph, g, 0);
     cudaGraphDestroy(g);
     if (ci != cudaSuccess) return e->cuda_fail(ci, "cudaGraphInstantiate");
-    e->graph_B = e->B; e->graph_N = e->n_samples; e->graph_dtype = e->pcm_dtype;
+    e->graph_B = e->B; e->graph_N = e->n_samples; e->graph_dtype = dtype_key;
   }
   NCK(cudaGraphLaunch(e->graph, e->st));
   e->launches += e->graph_nodes;
@@ -778,7 +792,7 @@ void b200asr_nar_destroy(b200asr_nar* e) {
   cudaStreamSynchronize(e->st);
   if (e->graph) cudaGraphExecDestroy(e->graph);
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
-  void* bufs[] = {e->basis_t, e->stage_buf, e->pcm, e->mel, e->feats, e->hidden, e->resid, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->S,
+  void* bufs[] = {e->d_meta, e->basis_t, e->stage_buf, e->pcm, e->mel, e->feats, e->hidden, e->resid, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->S,
                   e->logits, e->enc_out, e->frame_ids, e->tokens, e->lens, e->lang, e->enc_pad, e->conv_out, e->kvbuf, e->dq, e->alphas,
                   e->acoustic, e->dec, e->dx, e->f32buf, e->sa_in, e->dec_logits, e->n_tok, e->seg_off};
   for (void* p : bufs) if (p) cudaFree(p);
@@ -932,6 +946,7 @@ int b200asr_nar_finalize_weights(b200asr_nar* e) {
     NRET(nar_alloc(e, &e->tokens, (size_t)B * Tm * 4));
     NRET(nar_alloc(e, &e->lens, (size_t)B * 4));
     NRET(nar_alloc(e, &e->lang, (size_t)B * 4));
+    NRET(nar_alloc(e, &e->d_meta, (size_t)2 * B * 4));
     if (c.kind == B200ASR_NAR_PARAFORMER) {
       const int64_t pad = (c.cif_kernel - 1) / 2;
       NRET(nar_alloc(e, &e->enc_pad, (size_t)B * (Tm + 2 * pad) * D * es));
@@ -958,7 +973,7 @@ int b200asr_nar_finalize_weights(b200asr_nar* e) {
 }
 
 static int nar_upload(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
-                      const int32_t* language_idx) {
+                      const int32_t* language_idx, const int32_t* lens = nullptr) {
   const b200asr_nar_config& c = e->cfg;
   if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
   const bool para = c.kind == B200ASR_NAR_PARAFORMER;
@@ -973,6 +988,26 @@ static int nar_upload(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, i
   e->frames = (n_samples - c.win) / c.hop + 1;
   e->T_lfr = (e->frames + c.lfr_n - 1) / c.lfr_n;
   e->T = e->T_lfr + c.n_prompt;
+  bool ragged = false;
+  if (lens) {
+    int longest = 0;
+    for (int b = 0; b < batch; ++b) {
+      if (lens[b] < c.win || lens[b] > n_samples) return e->fail(B200ASR_E_INVALID, "per-clip length out of [win, n_samples]");
+      longest = longest > lens[b] ? longest : lens[b];
+      ragged |= lens[b] != n_samples;
+    }
+    if (ragged) {
+      if ((longest - c.win) / c.hop + 1 != e->frames) return e->fail(B200ASR_E_INVALID, "n_samples must be the longest clip's length (within one hop)");
+      e->h_meta.assign((size_t)2 * c.max_batch, 0);
+      for (int b = 0; b < batch; ++b) {
+        const int fr = (lens[b] - c.win) / c.hop + 1;
+        e->h_meta[b] = fr;
+        e->h_meta[c.max_batch + b] = (fr + c.lfr_n - 1) / c.lfr_n + c.n_prompt;
+      }
+      NCK(cudaMemcpyAsync(e->d_meta, e->h_meta.data(), e->h_meta.size() * sizeof(int), cudaMemcpyHostToDevice, e->st));
+    }
+  }
+  e->ragged = ragged;
   NCK(cudaMemcpyAsync(e->pcm, pcm_host, (size_t)batch * n_samples * (pcm_dtype == B200ASR_PCM_F32 ? 4 : 2), cudaMemcpyHostToDevice, e->st));
   if (!para) NCK(cudaMemcpyAsync(e->lang, language_idx, (size_t)batch * 4, cudaMemcpyHostToDevice, e->st));
   return B200ASR_OK;
@@ -1001,6 +1036,29 @@ int b200asr_nar_run(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int
   NRET(nar_upload(e, pcm_host, pcm_dtype, batch, n_samples, language_idx));
   NRET(nar_forward(e));
   return nar_fetch(e, tokens_out, tokens_ld, lens_out);
+}
+
+// Ragged batch: clip b has lens[b] samples; rows of pcm_host are n_samples (= the longest clip) apart.  Every clip gets the
+// result of running the reference's dynamic-length graph on it alone: its own frame count, LFR tail, FSMN / CIF-conv zero
+// padding, attention keys, CTC roll and CIF tail.
+int b200asr_nar_run_ragged(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                           const int32_t* lens, const int32_t* language_idx, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  if (!e) return B200ASR_E_INVALID;
+  NCK(cudaSetDevice(e->cfg.device));
+  if (!lens) return e->fail(B200ASR_E_INVALID, "null lens");
+  NRET(nar_upload(e, pcm_host, pcm_dtype, batch, n_samples, language_idx, lens));
+  NRET(nar_forward(e));
+  return nar_fetch(e, tokens_out, tokens_ld, lens_out);
+}
+
+int b200asr_nar_upload_ragged(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                              const int32_t* lens, const int32_t* language_idx) {
+  if (!e) return B200ASR_E_INVALID;
+  NCK(cudaSetDevice(e->cfg.device));
+  if (!lens) return e->fail(B200ASR_E_INVALID, "null lens");
+  NRET(nar_upload(e, pcm_host, pcm_dtype, batch, n_samples, language_idx, lens));
+  NCK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
 }
 
 int b200asr_nar_upload(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,

@@ -224,7 +224,8 @@ class ParaformerEngine(SenseVoiceEngine):
         return self.dims.lfr_frames(self.max_samples) + 1
 
     def run(self, pcm: np.ndarray, language_idx=0, out_tokens: Optional[np.ndarray] = None,
-            out_lens: Optional[np.ndarray] = None) -> List[List[int]]:
+            out_lens: Optional[np.ndarray] = None, clip_lens=None) -> List[List[int]]:
+        """clip_lens: samples per clip of a ragged batch (pcm rows zero-padded to the longest clip)."""
         pcm = np.ascontiguousarray(pcm)
         if pcm.ndim == 1:
             pcm = pcm[None]
@@ -236,8 +237,13 @@ class ParaformerEngine(SenseVoiceEngine):
         B, N = pcm.shape
         toks = out_tokens if out_tokens is not None else np.zeros((B, self._ld()), np.int32)
         lens = out_lens if out_lens is not None else np.zeros(B, np.int32)
-        self._ck(self.lib.b200asr_nar_run(self.h, pcm.ctypes.data_as(C.c_void_p), code, B, N, None,
-                                          toks.ctypes.data_as(_cabi._I32P), toks.shape[1], lens.ctypes.data_as(_cabi._I32P)))
+        if clip_lens is None:
+            self._ck(self.lib.b200asr_nar_run(self.h, pcm.ctypes.data_as(C.c_void_p), code, B, N, None,
+                                              toks.ctypes.data_as(_cabi._I32P), toks.shape[1], lens.ctypes.data_as(_cabi._I32P)))
+        else:
+            cl = np.ascontiguousarray(np.asarray(clip_lens, np.int32).reshape(B))
+            self._ck(self.lib.b200asr_nar_run_ragged(self.h, pcm.ctypes.data_as(C.c_void_p), code, B, N, cl.ctypes.data_as(_cabi._I32P), None,
+                                                     toks.ctypes.data_as(_cabi._I32P), toks.shape[1], lens.ctypes.data_as(_cabi._I32P)))
         self.batch, self.n_samples = B, N
         return [toks[b, :lens[b]].tolist() for b in range(B)]
 

@@ -229,8 +229,9 @@ class SenseVoiceEngine:
         return int(self.lib.b200asr_nar_stream(self.h) or 0)
 
     def run(self, pcm: np.ndarray, language_idx=0, out_tokens: Optional[np.ndarray] = None,
-            out_lens: Optional[np.ndarray] = None) -> List[List[int]]:
-        """pcm [B][N] (or [N], or the reference's [B,1,N]): int16, or float32 carrying int16-range values."""
+            out_lens: Optional[np.ndarray] = None, clip_lens=None) -> List[List[int]]:
+        """pcm [B][N] (or [N], or the reference's [B,1,N]): int16, or float32 carrying int16-range values.
+        clip_lens: samples per clip of a ragged batch (pcm rows zero-padded to the longest clip)."""
         pcm = np.ascontiguousarray(pcm)
         if pcm.ndim == 1:
             pcm = pcm[None]
@@ -248,8 +249,14 @@ class SenseVoiceEngine:
         ld = self.dims.lfr_frames(self.max_samples) + 1 + len(SYSTEM_PROMPT_IDS)
         toks = out_tokens if out_tokens is not None else np.zeros((B, ld), np.int32)
         lens = out_lens if out_lens is not None else np.zeros(B, np.int32)
-        self._ck(self.lib.b200asr_nar_run(self.h, pcm.ctypes.data_as(C.c_void_p), code, B, N, lang.ctypes.data_as(_cabi._I32P),
-                                          toks.ctypes.data_as(_cabi._I32P), toks.shape[1], lens.ctypes.data_as(_cabi._I32P)))
+        if clip_lens is None:
+            self._ck(self.lib.b200asr_nar_run(self.h, pcm.ctypes.data_as(C.c_void_p), code, B, N, lang.ctypes.data_as(_cabi._I32P),
+                                              toks.ctypes.data_as(_cabi._I32P), toks.shape[1], lens.ctypes.data_as(_cabi._I32P)))
+        else:
+            cl = np.ascontiguousarray(np.asarray(clip_lens, np.int32).reshape(B))
+            self._ck(self.lib.b200asr_nar_run_ragged(self.h, pcm.ctypes.data_as(C.c_void_p), code, B, N, cl.ctypes.data_as(_cabi._I32P),
+                                                     lang.ctypes.data_as(_cabi._I32P), toks.ctypes.data_as(_cabi._I32P), toks.shape[1],
+                                                     lens.ctypes.data_as(_cabi._I32P)))
         self.batch, self.n_samples = B, N
         return [toks[b, :lens[b]].tolist() for b in range(B)]
 

@@ -196,6 +196,15 @@ int b200asr_nar_run(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int
 int b200asr_nar_upload(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
                        const int32_t* language_idx);
 int b200asr_nar_run_resident(b200asr_nar* e, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
+/* ragged batch: clip b has lens[b] samples (win <= lens[b] <= n_samples), rows of pcm_host are n_samples (= the longest clip)
+ * apart.  Each clip gets what the reference's dynamic-length graph (audio axis: SenseVoice/Export_SenseVoice.py:19,379,
+ * Paraformer/Non-Streaming/Export_Paraformer.py:74,603) gives it when run alone: its own frame count, LFR tail, FSMN and
+ * CIF-conv zero padding, attention key range, CTC roll and CIF tail threshold position. */
+int b200asr_nar_run_ragged(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                           const int32_t* lens, const int32_t* language_idx, int32_t* tokens_out, int32_t tokens_ld,
+                           int32_t* lens_out);
+int b200asr_nar_upload_ragged(b200asr_nar* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples,
+                              const int32_t* lens, const int32_t* language_idx);
 /* "mel" [B][frames][n_mels], "feats" [B][T][feat], "enc_out" [B][T][d], "logits" [B][T][vocab], "frame_ids" [B][T] */
 int b200asr_nar_get_stage(b200asr_nar* e, const char* name, float* out, int64_t capacity, int64_t* numel_out);
 int64_t b200asr_nar_kernel_launches(const b200asr_nar* e);
