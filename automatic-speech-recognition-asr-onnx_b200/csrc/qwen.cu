@@ -1341,6 +1341,7 @@ int qwen_decoder(b200asr_qwen* e, int n_new) {
   s.penalty_value = 1.0f; s.penalty_range = 0; s.state = e->dstate; s.n_new = n_new;
   s.temperature = e->samp_temperature; s.top_k = e->samp_top_k; s.top_p = e->samp_top_p; s.rep_penalty = e->samp_rep;
   s.seed = e->samp_seed; s.noise = e->samp_noise; s.noise_ld = e->samp_top_k; s.noise_rows = e->samp_noise_rows;
+  s.noise_batch = e->cfg.max_batch;          // noise rows are laid out [launch][max_batch][top_k]
   QKL(launch_select_token(s, e->st));
   e->launches++;
   return B200ASR_OK;
