@@ -26,3 +26,22 @@ def make_engine(tensors, precision, max_batch=1, max_samples=32000, tc=True):
 
 def maxdiff(a, b):
     return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))))
+
+
+def dequantised_e4m3(tensors):
+    """The engine's quantiser (csrc/decoder_stream.cu: quant_rows_e4m3_kernel) replayed on the host: bf16 weights, row scale =
+    amax / 448, E4M3 round-to-nearest-even of w * (1 / scale); returns the tensors with the decoder matrices replaced by
+    scale * e4m3(...)."""
+    import torch
+    out = dict(tensors)
+    for name, w in tensors.items():
+        if not (name == "dec.embed" or (name.startswith("dec.L") and name.endswith(".w"))):
+            continue
+        t = torch.from_numpy(np.ascontiguousarray(w, np.float32))
+        shape = t.shape
+        t = t.reshape(shape[0], -1).to(torch.bfloat16).to(torch.float32)
+        amax = t.abs().amax(dim=1, keepdim=True)
+        sc = torch.where(amax > 0, amax / 448.0, torch.ones_like(amax))
+        q = (t * (1.0 / sc)).to(torch.float8_e4m3fn).to(torch.float32)
+        out[name] = (q * sc).reshape(shape).numpy()
+    return out

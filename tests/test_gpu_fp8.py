@@ -14,9 +14,8 @@ scale in the epilogue.  Two statements, tolerances written here:
 Greedy tokens must agree with the dequantised-weight fp32 engine wherever its top-2 margin exceeds twice bound 1."""
 import numpy as np
 import pytest
-import torch
 
-from gpu_common import GOLD, load_case, make_engine, maxdiff
+from gpu_common import GOLD, dequantised_e4m3, load_case, make_engine, maxdiff
 from b200asr.synth import synth_pcm
 
 pytestmark = pytest.mark.gpu
@@ -34,29 +33,11 @@ def _forced(eng, pcm, prompt, forced):
     return np.stack(out, axis=1)
 
 
-def _dequantised(tensors):
-    """The engine's quantiser (csrc/decoder_stream.cu: quant_rows_e4m3_kernel) replayed on the host: bf16 weights, row scale =
-    amax / 448, E4M3 round-to-nearest-even of w * (1 / scale); returns the tensors with the decoder matrices replaced by
-    scale * e4m3(...)."""
-    out = dict(tensors)
-    for name, w in tensors.items():
-        if not (name == "dec.embed" or (name.startswith("dec.L") and name.endswith(".w"))):
-            continue
-        t = torch.from_numpy(np.ascontiguousarray(w, np.float32))
-        shape = t.shape
-        t = t.reshape(shape[0], -1).to(torch.bfloat16).to(torch.float32)
-        amax = t.abs().amax(dim=1, keepdim=True)
-        sc = torch.where(amax > 0, amax / 448.0, torch.ones_like(amax))
-        q = (t * (1.0 / sc)).to(torch.float8_e4m3fn).to(torch.float32)
-        out[name] = (q * sc).reshape(shape).numpy()
-    return out
-
-
 @pytest.mark.parametrize("path", GOLD[:2], ids=[p.stem for p in GOLD[:2]])
 def test_fp8_kernel_equals_fp32_engine_on_dequantised_weights(path):
     g, raw, tensors = load_case(path)
     forced = g["forced_tokens"].tolist()
-    ref_eng = make_engine(_dequantised(tensors), "f32")
+    ref_eng = make_engine(dequantised_e4m3(tensors), "f32")
     ref = _forced(ref_eng, g["pcm"], g["prompt"], forced)[0]
     ref_eng.set_decode_options(stop_ids=[], generate_limit=10)
     ref_toks = ref_eng.transcribe(g["pcm"], g["prompt"], max_new=10)[0]
