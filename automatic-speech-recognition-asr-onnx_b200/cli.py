@@ -68,6 +68,8 @@ def main(argv=None) -> int:
     w.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     w.add_argument("--device", type=int, default=0)
     w.add_argument("--set", nargs="*", default=[], metavar="NAME=VALUE", help="script constants, e.g. REPEAT_PENALTY=1.0")
+    w.add_argument("--batch", type=int, default=1, help="transcribe the files in ragged batches of up to N clips (single-window clips; "
+                                                        "every clip keeps its single-clip result)")
     qp = sub.add_parser("qwen")
     qp.add_argument("--model-folder", "--onnx-folder", dest="folder", required=True)
     qp.add_argument("--tokenizer-path", default=None)
@@ -118,9 +120,27 @@ def main(argv=None) -> int:
     clips = [ingest.read_wav(p) for p in args.audio]
     sr = int(md["sample_rate"])
     pcm = [ingest.to_model_rate(x, r, sr) for x, r in clips]
-    eng = WhisperEngine(dims, tensors, precision=args.precision, max_batch=1, max_samples=max(480000, max(len(x) for x in pcm)),
+    opts = _options(args.set)
+    nb = max(1, min(args.batch, 8, len(pcm)))
+    eng = WhisperEngine(dims, tensors, precision=args.precision, max_batch=nb, max_samples=max(480000, max(len(x) for x in pcm)),
                         device=args.device)
-    pipe = WhisperPipeline(eng, md, _options(args.set))
+    pipe = WhisperPipeline(eng, md, opts)
+    if nb > 1 and opts.INPUT_AUDIO_LENGTH <= 0:
+        # ragged batches: neighbours in length share a batch (the batch runs at its longest clip's row count)
+        from .sharding import ragged_batches
+        results = {}
+        for group in ragged_batches(range(len(pcm)), [len(x) for x in pcm], nb):
+            for i, res in zip(group, pipe.transcribe_batch([pcm[i] for i in group])):
+                results[i] = res
+        for i, path in enumerate(args.audio):
+            res = results[i]
+            print("-" * 106)
+            print(f"\nTest Input Audio: {path}")
+            print(f"Detected Language: {res.language}")
+            text = tokenizer.decode(res.tokens, skip_special_tokens=True) if tokenizer is not None else " ".join(map(str, res.tokens))
+            print(pipe.report(res, text))
+        eng.close()
+        return 0
     for path, x in zip(args.audio, pcm):
         print("-" * 106)
         print(f"\nTest Input Audio: {path}")

@@ -205,6 +205,56 @@ class WhisperPipeline:
                           no_speech=no_speech, elapsed_s=elapsed, audio_s=audio_len / self.sample_rate,
                           decode_steps=steps, windows=windows)
 
+    def transcribe_batch(self, clips: Sequence[np.ndarray], language: Optional[str] = None) -> List[ClipResult]:
+        """The same protocol for several clips of DIFFERENT lengths in one ragged batch (`lens=`: every clip keeps its
+        single-clip semantics, so the ids are the ones `transcribe_pcm` gives clip by clip): one encoder launch, one
+        probe prefill, per-clip language / no-speech decisions on the host, one prefill with per-clip prompts, one
+        device-resident decode.  Single-window clips only (INPUT_AUDIO_LENGTH = 0, the dynamic audio axis); a clip
+        classified as silence keeps an empty token list.  The reference has no batched driver (its graphs are batch 1,
+        :722-768): this is the throughput path the ragged C-ABI entry points exist for."""
+        o = self.opt
+        if o.INPUT_AUDIO_LENGTH > 0:
+            raise ValueError("transcribe_batch handles single-window clips (INPUT_AUDIO_LENGTH = 0); use transcribe_pcm for windows")
+        raws = [np.asarray(c, dtype=np.int16).reshape(-1) for c in clips]
+        B = len(raws)
+        language = language or o.TARGET_LANGUAGE
+        language, entry = resolve_supported_language(self.languages, language)
+        prepared = [prepare_audio_input(r.reshape(1, 1, -1), np.int16, audio_pcm_scale=self.audio_pcm_scale,
+                                        use_normalise_audio=o.USE_NORMALISE_AUDIO).reshape(-1) for r in raws]
+        pcm, lens = WhisperEngine.pad_ragged(prepared)
+        langs = [language] * B
+        lang_ids = [int(entry["token_id"])] * B
+        probs: List[Optional[float]] = [None] * B
+        silent = [False] * B
+        t0 = time.time()
+        self._configure(max(0, self.max_seq_len - 4))
+        self.engine.encode(pcm, lens=lens)
+        if o.DETECT_LANGUAGE or o.NO_SPEECH_DETECTION:
+            logits, _ = self.engine.prefill([[self.start_token]] * B)
+            if o.DETECT_LANGUAGE:
+                for b in range(B):
+                    detected = int(self.lang_token_ids[np.argmax(logits[b][self.lang_token_ids])])
+                    langs[b] = self.lang_token_to_code.get(detected, langs[b])
+                    lang_ids[b] = detected
+            if o.NO_SPEECH_DETECTION and self.no_speech_token is not None:
+                pr = self.engine.no_speech_prob(int(self.no_speech_token))
+                for b in range(B):
+                    probs[b] = float(pr[b])
+                    silent[b] = probs[b] >= o.NO_SPEECH_THRESHOLD
+        prompts = [[self.start_token, lang_ids[b], self.task_token, self.no_timestamps] for b in range(B)]
+        self.engine.prefill(prompts, want_logits=False)
+        toks = self.engine.decode()
+        elapsed = time.time() - t0
+        out = []
+        for b in range(B):
+            t = [] if silent[b] else list(toks[b])
+            if o.REMOVE_REPEATED_PARTS and t:
+                t = list(remove_repeated_parts(t, 3, len(t)))
+            out.append(ClipResult(tokens=t, language=langs[b], language_token=lang_ids[b], no_speech_probability=probs[b],
+                                  no_speech=silent[b], elapsed_s=elapsed / B, audio_s=raws[b].size / self.sample_rate,
+                                  decode_steps=max(0, len(t) - 1), windows=1))
+        return out
+
     def report(self, res: ClipResult, text: str) -> str:
         """The reference's result block (:836-841)."""
         body = "[no speech detected]" if res.no_speech else text

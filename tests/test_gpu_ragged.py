@@ -125,3 +125,28 @@ def test_ragged_argument_checks():
     with pytest.raises(ValueError):
         eng.encode(pcm, lens=[16000])
     eng.close()
+
+
+def test_pipeline_transcribe_batch_equals_clip_by_clip():
+    """WhisperPipeline.transcribe_batch: the reference's default protocol (probe -> language -> no-speech -> prefill -> penalty-greedy
+    decode, Inference_Whisper_ONNX.py:766-827) for four clips of different lengths in ONE ragged batch gives every clip the
+    result of running it alone through `transcribe_pcm` (fp32 engine: ids, detected language and no-speech probability)."""
+    from b200asr.cli import whisper_metadata
+    from b200asr.config import WHISPER_TINY_TEST as dims
+    from b200asr.whisper_infer import InferenceOptions, WhisperPipeline
+    g, raw, tensors = load_case(GOLD[0])
+    p = g["prompt"].tolist()
+    gen = {"lang_to_id": {f"<|l{int(t)}|>": int(t) for t in g["lang_ids"]} | {"<|en|>": p[1]}, "task_to_id": {"transcribe": p[2]},
+           "no_timestamps_token_id": p[3], "decoder_start_token_id": p[0], "eos_token_id": 2, "no_speech_token_id": 13}
+    md = whisper_metadata(dims, gen)
+    clips = _clips()
+    eng = make_engine(tensors, "f32", max_batch=4)
+    pipe = WhisperPipeline(eng, md, InferenceOptions(NO_SPEECH_THRESHOLD=2.0, PENALTY_RANGE=3))
+    batch = pipe.transcribe_batch(clips)
+    for b, clip in enumerate(clips):
+        one = pipe.transcribe_pcm(clip)
+        assert batch[b].tokens == one.tokens, b
+        assert batch[b].language_token == one.language_token
+        assert abs(batch[b].no_speech_probability - one.no_speech_probability) <= 1e-5
+    assert len({r.language_token for r in batch}) >= 1 and all(len(r.tokens) > 0 for r in batch)
+    eng.close()
