@@ -109,7 +109,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t st, std:
 
 // layers.cu
 cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, void* out,
-                             int out_dtype, int64_t ldo, int rows, int d, float eps, cudaStream_t st);
+                             int out_dtype, int64_t ldo, int rows, int d, float eps, cudaStream_t st, int pdl = 0 /*1: launched as a programmatic dependent of the kernel that writes x*/);
 cudaError_t launch_softmax_rows(const float* s, void* p, int p_dtype, int64_t rows, int cols, cudaStream_t st,
                                 const int* valid = nullptr /*[entries]: key columns per entry*/, int64_t rows_per_entry = 1);
 

@@ -244,7 +244,7 @@ int enqueue_encoder(b200asr_engine* e) {
   // ---- encoder layers (Export_Whisper.py:430-437) ----
   for (int l = 0; l < c.enc_layers; ++l) {
     const std::string p = "enc.L" + std::to_string(l) + ".";
-    KL(launch_layernorm(e->hidden, d, nullptr, nullptr, e->xhat, ad, d, M, d, 1e-5f, e->st));
+    KL(launch_layernorm(e->hidden, d, nullptr, nullptr, e->xhat, ad, d, M, d, 1e-5f, e->st, e->use_pdl ? 1 : 0));
     RET(gemm(e, linear_args(e, e->xhat, d, p + "qkv.w", p + "qkv.b", e->qkv, 3 * d, ad, M, 3 * d, d)));
     if (ad == kBF16 && c.use_tensor_cores && e->use_attn_tc && attention_tc_supported(T, d, H)) {
       // fused softmax(Q K^T) V on tcgen05: scores and probabilities never leave the SM
@@ -273,7 +273,7 @@ int enqueue_encoder(b200asr_engine* e) {
       g.residual = e->hidden; g.ldr = d;
       RET(gemm(e, g));
     }
-    KL(launch_layernorm(e->hidden, d, nullptr, nullptr, e->xhat, ad, d, M, d, 1e-5f, e->st));
+    KL(launch_layernorm(e->hidden, d, nullptr, nullptr, e->xhat, ad, d, M, d, 1e-5f, e->st, e->use_pdl ? 1 : 0));
     {
       GemmArgs g = linear_args(e, e->xhat, d, p + "fc1.w", p + "fc1.b", e->ffn, c.ffn, ad, M, c.ffn, d);
       g.act = kActGelu;
@@ -284,7 +284,7 @@ int enqueue_encoder(b200asr_engine* e) {
     }
   }
   // ---- final LN (affine) + fused cross-KV projection (Export_Whisper.py:438-447) ----
-  KL(launch_layernorm(e->hidden, d, WF(e, "enc.ln_post.g"), WF(e, "enc.ln_post.b"), e->xhat, ad, d, M, d, 1e-5f, e->st));
+  KL(launch_layernorm(e->hidden, d, WF(e, "enc.ln_post.g"), WF(e, "enc.ln_post.b"), e->xhat, ad, d, M, d, 1e-5f, e->st, e->use_pdl ? 1 : 0));
   {  // 2L projections of the same rows: batched over z = (kind, layer) so each layer's K / V lands contiguous:
      // cross_kv[z][b*T + t][d], z = l for K (pre-scaled), z = L + l for V
     GemmArgs g = linear_args(e, e->xhat, d, "enc.cross_kv.w", "enc.cross_kv.b", e->cross_kv, d, ad, M, d, d);

@@ -12,6 +12,10 @@ template <typename OutT, int kMaxPerLane>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, OutT* __restrict__ out, int64_t ldo, int rows, int d, float eps) {
+  // programmatic dependent launch (both calls are no-ops for a plain launch): let the next kernel become resident now (a
+  // tcgen05 GEMM requests its weight tiles before it waits for us), and wait for the kernel that produces x
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -46,11 +50,17 @@ layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
 }
 
 cudaError_t launch_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, void* out,
-                             int out_dtype, int64_t ldo, int rows, int d, float eps, cudaStream_t st) {
+                             int out_dtype, int64_t ldo, int rows, int d, float eps, cudaStream_t st, int pdl) {
   if (d > 32 * 64) return cudaErrorInvalidValue;
   const int wpb = 8;
   dim3 grid((rows + wpb - 1) / wpb);
-#define LN_LAUNCH(T, N) layernorm_kernel<T, N><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (T*)out, ldo, rows, d, eps)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(wpb * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+#define LN_LAUNCH(T, N) do { cudaError_t le = cudaLaunchKernelEx(&cfg, layernorm_kernel<T, N>, x, ldx, gamma, beta, (T*)out, ldo, rows, d, eps); if (le != cudaSuccess) return le; } while (0)
   if (d <= 32 * 8) { if (out_dtype == kF32) LN_LAUNCH(float, 8); else LN_LAUNCH(bf16, 8); }
   else if (d <= 32 * 40) { if (out_dtype == kF32) LN_LAUNCH(float, 40); else LN_LAUNCH(bf16, 40); }
   else { if (out_dtype == kF32) LN_LAUNCH(float, 64); else LN_LAUNCH(bf16, 64); }

@@ -469,7 +469,7 @@ int nar_block(b200asr_nar* e, const std::string& p, const std::string& fsmn_bias
   const b200asr_nar_config& c = e->cfg;
   const int D = c.d_model, H = c.n_heads, dh = D / H, T = e->T, B = e->B, M = B * T, ad = e->act;
   const size_t es = e->es;
-  NKL(launch_layernorm(x_in, din, NWF_opt(e, p + "norm1.g"), NWF_opt(e, p + "norm1.b"), e->xhat, ad, din, M, din, c.ln_eps, e->st));
+  NKL(launch_layernorm(x_in, din, NWF_opt(e, p + "norm1.g"), NWF_opt(e, p + "norm1.b"), e->xhat, ad, din, M, din, c.ln_eps, e->st, e->use_pdl ? 1 : 0));
   NRET(nar_gemm(e, nar_linear(e, e->xhat, din, p + "qkv.w", p + "qkv.b", e->qkv, 3 * D, ad, M, 3 * D, din)));
   // FSMN memory (+ x when the block keeps its width) -> the fp32 residual the out-projection adds
   const float* res_in = (din == D) ? x_in : nullptr;
@@ -504,7 +504,7 @@ int nar_block(b200asr_nar* e, const std::string& p, const std::string& fsmn_bias
     g.residual = e->resid; g.ldr = D;
     NRET(nar_gemm(e, g));
   }
-  NKL(launch_layernorm(e->hidden, D, NWF_opt(e, p + "norm2.g"), NWF_opt(e, p + "norm2.b"), e->xhat, ad, D, M, D, c.ln_eps, e->st));
+  NKL(launch_layernorm(e->hidden, D, NWF_opt(e, p + "norm2.g"), NWF_opt(e, p + "norm2.b"), e->xhat, ad, D, M, D, c.ln_eps, e->st, e->use_pdl ? 1 : 0));
   {
     GemmArgs g = nar_linear(e, e->xhat, D, p + "w1.w", p + "w1.b", e->ffn, c.ffn, ad, M, c.ffn, D);
     g.act = kActRelu;
@@ -542,10 +542,10 @@ int sensevoice_forward(b200asr_nar* e) {
     const std::string p = "blk" + std::to_string(i) + ".";
     NRET(nar_block(e, p, p + "fsmn.b", i == 0 ? e->feats : e->hidden, i == 0 ? feat : D));
     if (i == n_main - 1)      // after_norm between the encoder blocks and the transformer-postnet blocks (:266)
-      NKL(launch_layernorm(e->hidden, D, NWF(e, "after_norm.g"), NWF(e, "after_norm.b"), e->hidden, kF32, D, M, D, c.ln_eps, e->st));
+      NKL(launch_layernorm(e->hidden, D, NWF(e, "after_norm.g"), NWF(e, "after_norm.b"), e->hidden, kF32, D, M, D, c.ln_eps, e->st, e->use_pdl ? 1 : 0));
   }
-  NKL(launch_layernorm(e->hidden, D, NWF(e, "tp_norm.g"), NWF(e, "tp_norm.b"), e->enc_out, kF32, D, M, D, c.ln_eps, e->st));
-  NKL(launch_layernorm(e->hidden, D, NWF(e, "tp_norm.g"), NWF(e, "tp_norm.b"), e->xhat, e->act, D, M, D, c.ln_eps, e->st));
+  NKL(launch_layernorm(e->hidden, D, NWF(e, "tp_norm.g"), NWF(e, "tp_norm.b"), e->enc_out, kF32, D, M, D, c.ln_eps, e->st, e->use_pdl ? 1 : 0));
+  NKL(launch_layernorm(e->hidden, D, NWF(e, "tp_norm.g"), NWF(e, "tp_norm.b"), e->xhat, e->act, D, M, D, c.ln_eps, e->st, e->use_pdl ? 1 : 0));
   NRET(nar_gemm(e, nar_linear(e, e->xhat, D, "ctc.w", "ctc.b", e->logits, c.vocab, kF32, M, c.vocab, D)));
   row_argmax_kernel<<<(M + 7) / 8, 256, 0, e->st>>>(e->logits, M, c.vocab, e->frame_ids);
   NKL(cudaGetLastError());
@@ -564,13 +564,13 @@ int paraformer_decode_one(b200asr_nar* e, int b, int n_tok) {
   NKL(cudaGetLastError());
   const char* memory = (const char*)e->xhat + (size_t)b * T * D * es;           // encoder_out of utterance b in the activation dtype
   auto ffn = [&](const std::string& p, float* out, const float* resid) -> int {
-    NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+    NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st, e->use_pdl ? 1 : 0));
     {
       GemmArgs g = nar_linear(e, e->dq, D, p + "w1.w", p + "w1.b", e->f32buf, Fd, kF32, rows, Fd, D);
       g.act = kActRelu;
       NRET(nar_gemm(e, g));
     }
-    NKL(launch_layernorm(e->f32buf, Fd, nullptr, nullptr, e->ffn, ad, Fd, rows, Fd, c.dec_ln_eps, e->st));
+    NKL(launch_layernorm(e->f32buf, Fd, nullptr, nullptr, e->ffn, ad, Fd, rows, Fd, c.dec_ln_eps, e->st, e->use_pdl ? 1 : 0));
     GemmArgs g2 = nar_linear(e, e->ffn, Fd, p + "w2.w", p + "w2.b", out, D, kF32, rows, D, Fd);
     if (resid) { g2.residual = resid; g2.ldr = D; }
     return nar_gemm(e, g2);
@@ -578,11 +578,11 @@ int paraformer_decode_one(b200asr_nar* e, int b, int n_tok) {
   for (int i = 0; i < c.dec_att_blocks; ++i) {
     const std::string p = "dec" + std::to_string(i) + ".";
     NRET(ffn(p, e->dx, nullptr));                                                               // x = FFN(dec)
-    NKL(launch_layernorm(e->dx, D, NWF(e, p + "norm2.g"), NWF(e, p + "norm2.b"), e->sa_in, kF32, D, rows, D, c.dec_ln_eps, e->st));
+    NKL(launch_layernorm(e->dx, D, NWF(e, p + "norm2.g"), NWF(e, p + "norm2.b"), e->sa_in, kF32, D, rows, D, c.dec_ln_eps, e->st, e->use_pdl ? 1 : 0));
     fsmn_kernel<float><<<dim3(rows, 1), 256, 0, e->st>>>(e->sa_in, D, 0, NWF(e, p + "fsmn.w"), NWF(e, "zero_bias"), e->dec, rows, D,
                                                        c.fsmn_kernel, e->dx);                  // x = dec + fsmn(norm2(x))
     NKL(cudaGetLastError());
-    NKL(launch_layernorm(e->dx, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+    NKL(launch_layernorm(e->dx, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st, e->use_pdl ? 1 : 0));
     NRET(nar_gemm(e, nar_linear(e, e->dq, D, p + "q.w", p + "q.b", e->qkv, D, ad, rows, D, D)));
     NRET(nar_gemm(e, nar_linear(e, memory, D, p + "kv.w", p + "kv.b", e->kvbuf, 2 * D, ad, T, 2 * D, D)));
     GemmArgs sgm;
@@ -606,7 +606,7 @@ int paraformer_decode_one(b200asr_nar* e, int b, int n_tok) {
     NRET(ffn("dec" + std::to_string(i) + ".", e->dx, nullptr));
     NCK(cudaMemcpyAsync(e->dec, e->dx, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, e->st));
   }
-  NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+  NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st, e->use_pdl ? 1 : 0));
   NRET(nar_gemm(e, nar_linear(e, e->dq, D, "out.w", "out.b", e->dec_logits, c.vocab, kF32, rows, c.vocab, D)));
   row_argmax_kernel<<<(rows + 7) / 8, 256, 0, e->st>>>(e->dec_logits, rows, c.vocab, e->tokens + (int64_t)b * e->max_T);
   NKL(cudaGetLastError());
@@ -622,23 +622,23 @@ int paraformer_decode_all(b200asr_nar* e, int rows) {
   para_gather_rows_kernel<<<rows, 128, 0, e->st>>>(e->acoustic, e->n_tok, e->seg_off, B, T, D, e->dec);
   NKL(cudaGetLastError());
   auto ffn = [&](const std::string& p, float* out) -> int {
-    NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+    NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st, e->use_pdl ? 1 : 0));
     {
       GemmArgs g = nar_linear(e, e->dq, D, p + "w1.w", p + "w1.b", e->f32buf, Fd, kF32, rows, Fd, D);
       g.act = kActRelu;
       NRET(nar_gemm(e, g));
     }
-    NKL(launch_layernorm(e->f32buf, Fd, nullptr, nullptr, e->ffn, ad, Fd, rows, Fd, c.dec_ln_eps, e->st));
+    NKL(launch_layernorm(e->f32buf, Fd, nullptr, nullptr, e->ffn, ad, Fd, rows, Fd, c.dec_ln_eps, e->st, e->use_pdl ? 1 : 0));
     return nar_gemm(e, nar_linear(e, e->ffn, Fd, p + "w2.w", p + "w2.b", out, D, kF32, rows, D, Fd));
   };
   const size_t smem = (size_t)4 * (DH + T) * sizeof(float);
   for (int i = 0; i < c.dec_att_blocks; ++i) {
     const std::string p = "dec" + std::to_string(i) + ".";
     NRET(ffn(p, e->dx));                                                                        // x = FFN(dec)
-    NKL(launch_layernorm(e->dx, D, NWF(e, p + "norm2.g"), NWF(e, p + "norm2.b"), e->sa_in, kF32, D, rows, D, c.dec_ln_eps, e->st));
+    NKL(launch_layernorm(e->dx, D, NWF(e, p + "norm2.g"), NWF(e, p + "norm2.b"), e->sa_in, kF32, D, rows, D, c.dec_ln_eps, e->st, e->use_pdl ? 1 : 0));
     fsmn_seg_kernel<<<rows, 256, 0, e->st>>>(e->sa_in, NWF(e, p + "fsmn.w"), e->dec, e->seg_off, B, D, c.fsmn_kernel, e->dx);   // x = dec + fsmn(norm2(x))
     NKL(cudaGetLastError());
-    NKL(launch_layernorm(e->dx, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+    NKL(launch_layernorm(e->dx, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st, e->use_pdl ? 1 : 0));
     NRET(nar_gemm(e, nar_linear(e, e->dq, D, p + "q.w", p + "q.b", e->qkv, D, ad, rows, D, D)));
     NRET(nar_gemm(e, nar_linear(e, e->xhat, D, p + "kv.w", p + "kv.b", e->kvbuf, 2 * D, ad, B * T, 2 * D, D)));
     const int total = rows * H;
@@ -653,7 +653,7 @@ int paraformer_decode_all(b200asr_nar* e, int rows) {
     NRET(ffn("dec" + std::to_string(i) + ".", e->dx));
     NCK(cudaMemcpyAsync(e->dec, e->dx, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, e->st));
   }
-  NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st));
+  NKL(launch_layernorm(e->dec, D, nullptr, nullptr, e->dq, ad, D, rows, D, c.dec_ln_eps, e->st, e->use_pdl ? 1 : 0));
   NRET(nar_gemm(e, nar_linear(e, e->dq, D, "out.w", "out.b", e->dec_logits, c.vocab, kF32, rows, c.vocab, D)));
   row_argmax_kernel<<<(rows + 7) / 8, 256, 0, e->st>>>(e->dec_logits, rows, c.vocab, e->frame_ids);
   NKL(cudaGetLastError());
@@ -676,8 +676,8 @@ int paraformer_encoder(b200asr_nar* e) {
     const std::string p = "enc" + std::to_string(i) + ".";
     NRET(nar_block(e, p, p + "out.b", i == 0 ? e->feats : e->hidden, i == 0 ? feat : D));
   }
-  NKL(launch_layernorm(e->hidden, D, NWF(e, "enc_after_norm.g"), NWF(e, "enc_after_norm.b"), e->enc_out, kF32, D, M, D, c.ln_eps, e->st));
-  NKL(launch_layernorm(e->hidden, D, NWF(e, "enc_after_norm.g"), NWF(e, "enc_after_norm.b"), e->xhat, ad, D, M, D, c.ln_eps, e->st));
+  NKL(launch_layernorm(e->hidden, D, NWF(e, "enc_after_norm.g"), NWF(e, "enc_after_norm.b"), e->enc_out, kF32, D, M, D, c.ln_eps, e->st, e->use_pdl ? 1 : 0));
+  NKL(launch_layernorm(e->hidden, D, NWF(e, "enc_after_norm.g"), NWF(e, "enc_after_norm.b"), e->xhat, ad, D, M, D, c.ln_eps, e->st, e->use_pdl ? 1 : 0));
   // CIF: conv k over time as a GEMM on the zero-padded, overlapping-row view (row t = k*D contiguous values from padded row t)
   const int pad = (c.cif_kernel - 1) / 2;
   if (ad == kBF16) pad_rows_kernel<bf16><<<dim3(T + 2 * pad, B), 128, 0, e->st>>>(e->enc_out, T, D, pad, (bf16*)e->enc_pad, e->dev_tvalid());
