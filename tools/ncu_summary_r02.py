@@ -25,7 +25,7 @@ out.append("| kernel | launches | total us | share | avg us |\n|---|---:|---:|--
 for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| `{k}` | {n} | {v / 1e3:.1f} | {100 * v / tot:.1f}% | {v / n / 1e3:.1f} |")
 traffic = {}
-for rep, b in (("prof_stream_b1_r02.ncu-rep", 1), ("prof_stream_b4_r02.ncu-rep", 4)):
+for rep, b in (("prof_stream_b1_r02.ncu-rep", 1), ("prof_stream_b4_r02.ncu-rep", 4), ("prof_stream_b1_fp8_r02.ncu-rep", "1_fp8")):
     if not (OUT / rep).exists():
         continue
     recs, units = raw(OUT / rep)
@@ -40,6 +40,18 @@ for rep, b in (("prof_stream_b1_r02.ncu-rep", 1), ("prof_stream_b4_r02.ncu-rep",
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
         traffic[str(b)] = (val("dram__bytes_read.sum") + val("dram__bytes_write.sum")) / STEPS
         out.append(f"\nDRAM bytes per greedy step (read + write) = {traffic[str(b)] / 1e9:.4f} GB\n")
+for rep, title in (("prof_attn_b4_r02.ncu-rep", "fused encoder attention, 4 clips x 8 s (first launch of the step)"),
+                   ("prof_gemm_b4_r02.ncu-rep", "encoder GEMMs, 4 clips x 8 s (first three launches: conv1, conv2, layer-0 QKV)")):
+    if not (OUT / rep).exists():
+        continue
+    recs, units = raw(OUT / rep)
+    out.append(f"\n## `--set full`: {title}\n")
+    for r in recs:
+        out.append("| metric | value |\n|---|---|")
+        for k in KEYS:
+            if k in r and r[k] != "":
+                out.append(f"| {k} | {r[k]} {units.get(k, '')} |")
+        out.append("")
 (ROOT / "profiles" / "ncu_r02_stream_summary.md").write_text("\n".join(out) + "\n" + (sys.argv[1] if len(sys.argv) > 1 else ""))
 (ROOT / "profiles" / "ncu_r02_stream.json").write_text(json.dumps(
     {"preset": "whisper-large-v3", "precision": "bf16", "steps_per_launch": STEPS, "dram_bytes_per_step": traffic,
