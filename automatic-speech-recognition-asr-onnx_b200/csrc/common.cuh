@@ -182,6 +182,9 @@ struct MegaArgs {
   const float* suppress_bias; const float* begin_bias;
   void* kcache; void* vcache; const void* cross_kv; int T;
   const int* t_valid;                    // ragged batch: encoder positions per clip [batch] (device); nullptr = T for every clip
+  // streaming kernel, sub-batch launch (multi-row prefill of a batch in groups): the launch covers clips [clip0, clip0 + batch) of a
+  // batch of batch_stride clips -- per-clip arrays arrive offset by clip0, the K/V caches and cross-KV keep the whole batch's strides
+  int batch_stride, clip0;               // batch_stride 0 = batch
   int batch, d, ffn, n_heads, vocab, max_target;
   float* x; float* q; float* ctx; float* f; float* logits;     // logits may be null
   const int* first_tokens; int first_n_new;                      // iteration 0: [B][first_n_new]
@@ -244,6 +247,7 @@ struct StreamArgs {
   int task_inv;                        // inverse (mod grid) of the attention-task -> CTA stride
   int l2_hint;                         // 1: weight / KV boxes are loaded with an L2 evict-first policy
   int multi;                           // 1: the m.first_n_new prompt positions of every clip run as rows of ONE iteration (single-iteration launch)
+  int keep_state;                      // 1: leave DecState (kv_len, step) as it is -- another sub-batch launch of the same positions follows
   int debug;
 };
 constexpr int kStreamMaxBatch = 8;

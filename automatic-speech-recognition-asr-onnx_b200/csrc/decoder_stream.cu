@@ -191,6 +191,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int NS = sa.n_stages, L = a.n_layers, G = gridDim.x, d = a.d, ffn = a.ffn, B = a.batch, H = a.n_heads, T = a.T;
+  const int Bs = a.batch_stride > 0 ? a.batch_stride : B, b0c = a.clip0;   // K/V strides and first clip of a sub-batch launch
   const int n_sched = 6 * L + 1;
   const int n_cnt = L * 3 * sa.cnt_ld, n_xexp = L * 3 * sa.xt;
   uint8_t* ring = base;
@@ -319,7 +320,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               }
               for (int t = t0; t < ntask && !stop; t += G) {
                 const int vu = t / H, h = t - vu * H, b = vu / NF;
-                const int row0 = ((l * B + b) * H + h) * a.max_target;
+                const int row0 = ((l * Bs + b0c + b) * H + h) * a.max_target;
                 for (int g0 = 0; g0 < nb && !stop; g0 += 4) {          // groups of <= 4 boxes: the K boxes, then the matching V boxes
                   const int ge = min(nb, g0 + 4);
                   for (int i = g0; i < ge && !stop; ++i) kvbox(&kc_map, 0, row0 + i * 128);
@@ -330,7 +331,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               const int nb = (T + 127) >> 7;
               for (int t = first_task(l, 1, sa.task_inv); t < ntask && !stop; t += G) {
                 const int vu = t / H, h = t - vu * H, b = vu / NF;
-                const int rk = (l * B + b) * T, rv = ((L + l) * B + b) * T;
+                const int rk = (l * Bs + b0c + b) * T, rv = ((L + l) * Bs + b0c + b) * T;
                 for (int g0 = 0; g0 < nb && !stop; g0 += 4) {
                   const int ge = min(nb, g0 + 4);
                   for (int i = g0; i < ge && !stop; ++i) kvbox(&cross_map, h * 64, rk + i * 128);
@@ -546,7 +547,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                 const bf16 hb = __float2bfloat16_rn(val);
                 if (j == pi) {                               // my own position: append for the later tokens
                   bf16* cache = reinterpret_cast<bf16*>(which == 1 ? a.kcache : a.vcache);
-                  cache[((((long long)l * B + ub) * H + h) * a.max_target + kv + pi) * 64 + dd] = hb;
+                  cache[((((long long)l * Bs + b0c + ub) * H + h) * a.max_target + kv + pi) * 64 + dd] = hb;
                 }
                 s_knv[((which - 1) * 8 + j) * 64 + dd] = __bfloat162float(hb);
               }
@@ -1123,7 +1124,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
     if (blockIdx.x == 0 && wt == 0) {
       int done = 1;
       for (int b = 0; b < B; ++b) done &= (s_fin[b] != 0);
-      a.state->kv_len = kv0 + it_done * NF; a.state->step = step; a.state->all_done = done;
+      if (!sa.keep_state) { a.state->kv_len = kv0 + it_done * NF; a.state->step = step; a.state->all_done = done; }
     }
   }
   tc_fence_before();

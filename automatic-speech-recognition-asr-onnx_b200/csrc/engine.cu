@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "../../include/b200asr.h"
 
+#include <algorithm>
 #include <climits>
 #include <cstdio>
 #include <cstring>
@@ -700,8 +701,9 @@ int build_stream_tables(b200asr_engine* e, int rows) {
 
 // one cooperative launch: n_first forced tokens per utterance ([B][n_first] on device; the last one feeds the first head),
 // then n_heads - 1 further greedy iterations.  first_is_prefill: the first head applies the begin-suppress bias.
+// clip0 / nclips: a sub-batch launch over clips [clip0, clip0 + nclips) of the engine's batch (nclips 0 = the whole batch)
 static int launch_stream(b200asr_engine* e, int rows, int n_heads_iters, const int* first_tokens, int n_first, bool first_is_prefill,
-                         bool want_logits, bool multi) {
+                         bool want_logits, bool multi, int clip0 = 0, int nclips = 0, bool keep_state = false) {
   RET(build_stream_tables(e, rows));
   const int slot = rows <= 1 ? 0 : (rows <= 2 ? 1 : (rows <= 4 ? 2 : 3));
   const b200asr_engine::StreamTables& t = e->stt[e->use_fp8 ? 1 : 0];
@@ -714,6 +716,16 @@ static int launch_stream(b200asr_engine* e, int rows, int n_heads_iters, const i
   sa.cand = e->st_cand; sa.sched = t.sched; sa.cnt = t.cnt; sa.xexp = t.xexp;
   sa.cnt_ld = pl.cnt_ld; sa.xt = pl.xt; sa.n_stages = pl.n_stages; sa.n_slots = pl.n_slots;
   sa.task_inv = e->ring_task_inv; sa.l2_hint = e->stream_l2_hint ? 1 : 0; sa.debug = e->stream_debug; sa.multi = multi ? 1 : 0;
+  sa.keep_state = keep_state ? 1 : 0;
+  if (nclips > 0 && nclips < e->B) {
+    MegaArgs& m = sa.m;
+    const b200asr_config& c = e->cfg;
+    m.batch_stride = e->B; m.clip0 = clip0; m.batch = nclips;
+    m.cur_token += clip0; m.n_gen += clip0; m.finished += clip0; m.n_save += clip0;
+    m.tokens += (size_t)clip0 * m.tokens_ld; m.save_id += (size_t)clip0 * m.save_ld; m.selected_hist += (size_t)clip0 * m.sel_ld;
+    if (m.logits) m.logits += (size_t)clip0 * c.vocab;
+    if (m.t_valid) m.t_valid += clip0;
+  }
   CK(cudaMemsetAsync(e->st_acc, 0, (size_t)pl.set_words * 2 * 8, e->st));
   CK(cudaMemsetAsync(e->st_cand, 0, pl.cand_words * 8, e->st));
   KL(launch_decoder_stream(sa, e->st_cross, e->st_kc, e->st_vc, pl.nrt, e->num_sms, pl.smem_bytes, e->st));
@@ -727,8 +739,15 @@ static int launch_stream(b200asr_engine* e, int rows, int n_heads_iters, const i
 int run_stream(b200asr_engine* e, int n_heads_iters, const int* first_tokens, int n_first, bool first_is_prefill, bool want_logits) {
   const int B = e->B;
   const int max_rows = e->use_fp8 ? 4 : kStreamMaxBatch;      // the FP8 kernel stages four E5M2 rows per activation row: 16 / 4
-  if (n_first > 1 && B * n_first <= max_rows && e->stream_multi) {
-    RET(launch_stream(e, B * n_first, 1, first_tokens, n_first, first_is_prefill, want_logits, true));
+  if (n_first > 1 && n_first <= max_rows && e->stream_multi) {
+    // multi-row prefill: the prompt rows of as many clips as fit the kernel's rows per launch (all of them when B * n_first fits;
+    // e.g. 4 clips x 4 prompt tokens = two launches of 8 rows: 2.2 ms instead of 3.9 ms token by token), then the decode launch
+    const int per = max_rows / n_first;
+    for (int b0 = 0; b0 < B; b0 += per) {
+      const int nb = std::min(per, B - b0);
+      RET(launch_stream(e, nb * n_first, 1, first_tokens + (size_t)b0 * n_first, n_first, first_is_prefill, want_logits, true,
+                        b0, nb, b0 + nb < B));
+    }
     if (n_heads_iters > 1) RET(launch_stream(e, B, n_heads_iters - 1, e->cur_token, 1, false, want_logits, false));
     return B200ASR_OK;
   }

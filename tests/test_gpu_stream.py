@@ -97,8 +97,8 @@ def test_stream_batch(nb):
 @pytest.mark.parametrize("nb", [2, 4, 8])
 def test_stream_batch_equals_single_exactly(nb, multi):
     """A clip's logits do not depend on its batch mates: bit-identical when both runs prefill the same way (multi = 0: the
-    prompt token by token); with the multi-row prefill (default) a batch of 4+ clips prefills token by token while a single
-    clip prefills its 4 rows together, which only changes the order the new positions' scores are summed in (<= 2e-4)."""
+    prompt token by token); with the multi-row prefill (default) a batch prefills in sub-batches of two clips (8 rows) while a
+    single clip prefills its 4 rows alone -- another row class of the kernel, same integer accumulation (<= 2e-4 allowed)."""
     g, raw, tensors = load_case(GOLD[1])
     n = 24160
     clips = np.stack([synth_pcm(30 + i, n) for i in range(nb)])
@@ -122,11 +122,12 @@ def test_stream_is_reproducible():
     eng.close()
 
 
-@pytest.mark.parametrize("nb", [1, 2, 3])
+@pytest.mark.parametrize("nb", [1, 2, 3, 4, 8])
 def test_stream_multi_row_prefill_equals_token_by_token(nb):
-    """The prompt rows of all clips as one multi-row iteration (rows = clips x prompt length <= 8; three clips fall back to the
-    token-by-token prefill) against feeding the prompt one token per iteration: same arithmetic per row except the order in
-    which the new positions' scores are summed, so logits agree to 1e-4 and the streams are identical."""
+    """The prompt rows as multi-row iterations (as many clips per launch as fit the kernel's 8 rows: two clips x 4 prompt tokens;
+    larger batches run sub-batch launches over clips [b0, b0 + 2) that keep the whole batch's K/V strides and leave the decode
+    state to the last one) against feeding the prompt one token per iteration: same arithmetic per row except the order in
+    which the new positions' scores are summed, so logits agree to 5e-4 (measured 1.0e-4 at batches 1-4, 3.0e-4 at batch 8; the bf16 bound itself is 3e-2) and the streams are identical."""
     g, raw, tensors = load_case(GOLD[1])
     n = 24160
     clips = np.stack([synth_pcm(40 + i, n) for i in range(nb)])
@@ -142,5 +143,5 @@ def test_stream_multi_row_prefill_equals_token_by_token(nb):
         eng.close()
     d = maxdiff(out[1][0], out[0][0])
     print(f"batch {nb}: multi-row vs token-by-token prefill max |dlogit| =", d)
-    assert d <= 1e-4
+    assert d <= 5e-4
     assert out[1][1] == out[0][1]
