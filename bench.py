@@ -607,7 +607,8 @@ def main():
                          "d2h_bytes_per_step": int(nclips * (dims.max_target + 1) * 4)},
                  "roofline": {"kernel": f"decoder_stream_kernel, batch {g0}", "bound": "hbm", "achieved": bs / (dec / 1e3) / 1e9, "peak": hbm_peak,
                               "unit": "GB/s", "frac": bs / (dec / 1e3) / 1e9 / hbm_peak, "ms_per_launch": dec, "algorithmic_bytes_per_launch": bs,
-                              "traffic": None, "peak_source": peak_src}}
+                              "traffic": profile_traffic(g0, args), "traffic_source": "profiles/ncu_r02_stream.json (ncu --set full, bytes per greedy step)",
+                              "peak_source": peak_src}}
             if res_ms is not None:
                 o["value"] = tot / (res_ms / 1e3); o["unit"] = "x real time"; o["ms_per_step"] = res_ms / steps
             return o
@@ -640,7 +641,8 @@ def main():
             "e2e": {"value": audio_s * B * world / (ms8 / 1e3), "unit": "x real time", "ms_per_step": ms8},
             "roofline": {"kernel": "decoder_stream_kernel<NRT, F8>", "bound": "hbm", "achieved": bytes8 / (dec8 / 1e3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": bytes8 / (dec8 / 1e3) / 1e9 / hbm_peak, "ms_per_launch": dec8,
-                         "algorithmic_bytes_per_launch": bytes8, "traffic": None, "peak_source": peak_src}}
+                         "algorithmic_bytes_per_launch": bytes8, "traffic": profile_traffic("1_fp8", args),
+                         "traffic_source": "profiles/ncu_r02_stream.json", "peak_source": peak_src}}
         eng.set_option("fp8", 0)
         eng.close()
         import copy
