@@ -158,6 +158,17 @@ def _reference_modules(dims, odims, prompt):
 REF_TIME_BUDGET_S = 150.0        # the reference arm stops adding timed utterances beyond this (a step = one 8 s utterance)
 
 
+def headline_config(args, batch_per_gpu):
+    """`config` of the headline workload: the same dictionary on the b200 arm and on the reference arm."""
+    return {
+        "workload": f"{args.preset} greedy, batch={batch_per_gpu} per device, 8 s chunk: encoder + 4-token prefill + "
+                    f"{DECODE_LAUNCHES} decode launches (BASELINE.json configs[1])",
+        "batch_per_gpu": batch_per_gpu, "n_samples": N_SAMPLES, "decode_launches": DECODE_LAUNCHES,
+        "weights": "seeded random init (no checkpoints offline)",
+        "l2": "no flush: the 3.1 GB bf16 weight set streamed every decode launch is 24x the 126 MB L2",
+    }
+
+
 def run_reference(args, dims):
     """CPU arm: the reference's own modules (oracle/_ref) when staged, else the oracle port; torch fp32, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -207,8 +218,8 @@ def run_reference(args, dims):
         "ms_per_step": 1e3 * wall / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "rtf": wall / (audio_s * len(times)), "utterances_per_s": len(times) / wall,
-        "config": {"workload": f"{args.preset} greedy, batch=1, 8 s chunk: encoder + 4-token prefill + "
-                               f"{DECODE_LAUNCHES} decode launches, host CPU", "decode_launches": DECODE_LAUNCHES},
+        "config": headline_config(args, 1),          # the b200 arm's config, key for key (the device is named in `device`)
+        "device": f"host CPU, {cores} threads",
         "cpu_baseline": {"value": value, "unit": "x real time", "cores": cores, "kind": kind,
                          "sample": f"{len(times)} utterance(s) of the same workload (a step = one 8 s utterance; the run stops "
                                    f"adding utterances after {REF_TIME_BUDGET_S:.0f} s); {what}"},
@@ -665,13 +676,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic", "impl": "b200",
             "rtf": (ms_total / 1e3) / total_audio, "utterances_per_s": B * world * args.steps / (ms_total / 1e3),
-            "config": {
-                "workload": f"{args.preset} {args.precision} greedy, batch={B}/GPU, 8 s chunk, {world}xB200: encoder + "
-                            f"4-token prefill + {DECODE_LAUNCHES} decode launches",
-                "batch_per_gpu": B, "n_samples": N_SAMPLES, "decode_launches": DECODE_LAUNCHES,
-                "weights": "seeded random init (no checkpoints offline)",
-                "l2": "no flush: the 3.1 GB bf16 weight set streamed every decode launch is 24x the 126 MB L2",
-            },
+            "config": headline_config(args, B),
+            "device": f"{world}xB200",
             "e2e": {"value": e2e, "unit": "x real time", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(pcm_np.nbytes + B * len(prompt) * 4),
                     "d2h_bytes_per_step": int(B * (dims.max_target + 1) * 4)},
