@@ -122,6 +122,8 @@ def main(argv=None) -> int:
     pcm = [ingest.to_model_rate(x, r, sr) for x, r in clips]
     opts = _options(args.set)
     nb = max(1, min(args.batch, 8, len(pcm)))
+    if opts.INPUT_AUDIO_LENGTH > 0 and max(len(x) for x in pcm) > opts.INPUT_AUDIO_LENGTH:
+        nb = 8                               # long-form: the windows after the first run as batches (WhisperPipeline, BATCH_WINDOWS)
     eng = WhisperEngine(dims, tensors, precision=args.precision, max_batch=nb, max_samples=max(480000, max(len(x) for x in pcm)),
                         device=args.device)
     pipe = WhisperPipeline(eng, md, opts)

@@ -45,6 +45,7 @@ class InferenceOptions:
     USE_NORMALISE_AUDIO: bool = False
     INPUT_AUDIO_LENGTH: int = 0          # 0 = dynamic audio axis (Export_Whisper.py:743): one window = the whole clip
     SAMPLING_SEED: int = 0
+    BATCH_WINDOWS: bool = True           # not a reference constant: windows after the first go through the engine as batches (same ids)
 
 
 def prepare_audio_input(audio_int16: np.ndarray, target_dtype, *, audio_pcm_scale: int, target_rms: float = 4096.0,
@@ -168,12 +169,26 @@ class WhisperPipeline:
         no_speech = False
         prob = None
         t0 = time.time()
-        for w in range(windows):
+        max_b = int(getattr(self.engine, "max_batch", 1)) if o.BATCH_WINDOWS else 1
+        w = 0
+        while w < windows:
             window = audio[:, :, w * stride:w * stride + input_len]
             needs_probe = w == 0 and (o.DETECT_LANGUAGE or o.NO_SPEECH_DETECTION)
             prompt = [self.start_token, language_id, self.task_token, self.no_timestamps]
             generate_limit = max(0, self.max_seq_len - len(prompt))
             self._configure(generate_limit)
+            if not needs_probe and max_b > 1 and windows - w > 1:
+                # windows share no state (the reference re-runs encoder + prefill per window with the same prompt, :766-827), so the
+                # remaining ones go through the engine as batches: same ids, window order kept
+                nb = min(max_b, windows - w)
+                batch = np.stack([audio[0, 0, (w + j) * stride:(w + j) * stride + input_len] for j in range(nb)])
+                self.engine.encode(batch)
+                self.engine.prefill(prompt, want_logits=False)
+                for toks in self.engine.decode():
+                    steps += max(0, len(toks) - 1)
+                    all_tokens.extend(toks)
+                w += nb
+                continue
             self.engine.encode(window.reshape(1, -1))
             if needs_probe:
                 logits, _ = self.engine.prefill([self.start_token])
@@ -198,6 +213,7 @@ class WhisperPipeline:
             toks = self.engine.decode()[0]
             steps += max(0, len(toks) - 1)
             all_tokens.extend(toks)
+            w += 1
         elapsed = time.time() - t0
         if o.REMOVE_REPEATED_PARTS and all_tokens:
             all_tokens = list(remove_repeated_parts(all_tokens, 3, len(all_tokens)))

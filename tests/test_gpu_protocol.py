@@ -90,6 +90,29 @@ def test_default_protocol_pipeline(path):
     eng.close()
 
 
+@pytest.mark.parametrize("probe", [True, False])
+def test_long_form_windows_batched_equal_sequential(probe):
+    """Long-form audio: the windows after the first go through the engine as batches (`BATCH_WINDOWS`; the reference runs them one
+    by one, Inference_Whisper_ONNX.py:766-827, and they share no state).  Seven 0.5 s windows with stride 0.45 s on a batch-4 engine:
+    ids, window count and detected language identical to the sequential loop."""
+    from b200asr.synth import synth_pcm
+    g, raw, tensors = load_case(GOLD[2])
+    md = _metadata(g)
+    eng = make_engine(tensors, "f32", max_batch=4, max_samples=64000)
+    pcm = synth_pcm(77, 50000)
+    out = {}
+    for batched in (True, False):
+        opt = InferenceOptions(REPEAT_PENALTY=0.8, PENALTY_RANGE=3, NO_SPEECH_THRESHOLD=2.0, DETECT_LANGUAGE=probe, NO_SPEECH_DETECTION=probe,
+                               INPUT_AUDIO_LENGTH=8000, SLIDING_WINDOW=7200, BATCH_WINDOWS=batched)
+        pipe = WhisperPipeline(eng, md, opt)
+        pipe.max_seq_len = 448
+        r = pipe.transcribe_pcm(pcm)
+        out[batched] = (r.tokens, r.windows, r.language_token, r.decode_steps)
+    assert out[True] == out[False]
+    assert out[True][1] == 7 and len(out[True][0]) > 7
+    eng.close()
+
+
 def test_session_shim_runs_reference_shaped_loop():
     """The probe / prefill / decode call sequence of Inference_Whisper_ONNX.py:437-663 against the shim."""
     g, raw, tensors = load_case(GOLD[1])
