@@ -150,3 +150,53 @@ def test_pipeline_transcribe_batch_equals_clip_by_clip():
         assert abs(batch[b].no_speech_probability - one.no_speech_probability) <= 1e-5
     assert len({r.language_token for r in batch}) >= 1 and all(len(r.tokens) > 0 for r in batch)
     eng.close()
+
+
+def test_cli_batch_mode_end_to_end(tmp_path, capsys):
+    """`python -m b200asr.cli whisper --model-folder F --audio a.wav b.wav c.wav --batch 4`: three WAV files of different lengths
+    in one ragged batch; every file's report block carries the ids the oracle gives that clip alone (language detected per clip)."""
+    import json
+    import wave
+    import torch
+    from b200asr import cli, ingest
+    from b200asr.config import WHISPER_TINY_TEST as dims
+    from b200asr.synth import synth_whisper_checkpoint
+    g, raw_o, tensors = load_case(GOLD[0])
+    raw = synth_whisper_checkpoint(dims, int(g["seed"]))
+    cfg = {"num_mel_bins": dims.n_mels, "d_model": dims.d_model, "encoder_attention_heads": dims.n_heads,
+           "decoder_attention_heads": dims.n_heads, "encoder_ffn_dim": dims.ffn, "decoder_ffn_dim": dims.ffn,
+           "encoder_layers": dims.enc_layers, "decoder_layers": dims.dec_layers, "vocab_size": dims.vocab,
+           "max_source_positions": dims.max_source, "max_target_positions": dims.max_target}
+    p = g["prompt"].tolist()
+    gen = {"suppress_tokens": g["suppress"].tolist(), "begin_suppress_tokens": g["begin_suppress"].tolist(),
+           "lang_to_id": {f"<|l{int(t)}|>": int(t) for t in g["lang_ids"]} | {"<|en|>": p[1]},
+           "task_to_id": {"transcribe": p[2]}, "no_timestamps_token_id": p[3], "decoder_start_token_id": p[0], "eos_token_id": 2,
+           "no_speech_token_id": 13}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    (tmp_path / "generation_config.json").write_text(json.dumps(gen))
+    ingest.write_safetensors(tmp_path / "model.safetensors", {k: v.numpy() for k, v in raw.items()})
+    clips = _clips()[:3]
+    paths = []
+    for i, c in enumerate(clips):
+        path = tmp_path / f"clip{i}.wav"
+        with wave.open(str(path), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+            w.writeframes(c.astype("<i2").tobytes())
+        paths.append(str(path))
+    rc = cli.main(["whisper", "--model-folder", str(tmp_path), "--audio", *paths, "--precision", "f32", "--batch", "4",
+                   "--set", "REPEAT_PENALTY=1.0", "NO_SPEECH_THRESHOLD=2.0"])
+    out = capsys.readouterr().out
+    assert rc == 0 and out.count("ASR Result:") == 3
+    blocks = out.split("Test Input Audio: ")[1:]
+    fw = wo.fold_weights(raw_o, wo.TINY_TEST, g["suppress"].tolist(), g["begin_suppress"].tolist())
+    lang_names = {v: k[2:-2] for k, v in gen["lang_to_id"].items()}
+    for blk, clip in zip(blocks, clips):
+        ids = [int(t) for t in blk.split("ASR Result:\n")[1].split("\n")[0].split()]
+        with torch.no_grad():
+            probe = wo.greedy_transcribe(clip, fw, wo.TINY_TEST, [p[0]], stop_tokens=[], max_new=1, return_logits=True)
+        lang_ids = g["lang_ids"].astype(int).tolist() + [p[1]]
+        det = lang_ids[int(np.argmax(np.asarray(probe["step_logits"][0])[lang_ids]))]
+        assert f"Detected Language: {lang_names[det]}" in blk
+        with torch.no_grad():
+            ref = wo.greedy_transcribe(clip, fw, wo.TINY_TEST, [p[0], det, p[2], p[3]], stop_tokens=[2], max_new=40, return_logits=False)
+        assert ids[:40] == ref["tokens"][:40]
