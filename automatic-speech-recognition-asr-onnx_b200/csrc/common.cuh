@@ -248,6 +248,7 @@ struct StreamArgs {
   int l2_hint;                         // 1: weight / KV boxes are loaded with an L2 evict-first policy
   int multi;                           // 1: the m.first_n_new prompt positions of every clip run as rows of ONE iteration (single-iteration launch)
   int keep_state;                      // 1: leave DecState (kv_len, step) as it is -- another sub-batch launch of the same positions follows
+  int lean;                            // 1: a plain greedy decode launch may take the instantiation with the rarely used branches compiled out
   int debug;
 };
 constexpr int kStreamMaxBatch = 8;

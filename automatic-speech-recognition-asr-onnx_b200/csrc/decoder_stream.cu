@@ -183,7 +183,10 @@ __device__ __forceinline__ int first_task(int l, int kind, int task_inv) {
 // DBG: per-phase time stamps into a.timing (block 0), compiled only into the instrumented instantiation
 // F8: the weight ring carries E4M3 bytes (atom = 128 rows x 128 k), activations are staged as four E5M2 rows per utterance,
 //     the epilogue multiplies by the per-row weight scale (NRT <= 4)
-template <int NRT, bool DBG, bool F8>
+// LEAN: the plain greedy decode launch (one new token per clip per iteration, no prompt rows, no begin-suppress, no penalty, no
+//       logits dump, no per-clip key counts): the same arithmetic with those branches compiled out -- the phase loop's instruction
+//       footprint decides its speed, and this is the launch that runs 32 of the 33 heads of a clip
+template <int NRT, bool DBG, bool F8, bool LEAN>
 __global__ void __launch_bounds__(kStThreads, 1)
 decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __grid_constant__ CUtensorMap kc_map,
                       const __grid_constant__ CUtensorMap vc_map, const __grid_constant__ StreamArgs sa) {
@@ -223,13 +226,13 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   constexpr int KSH = F8 ? 7 : 6;                          // log2(k per atom): a 128-byte swizzle row holds 64 bf16 or 128 fp8 weights
   const int KAd = d >> KSH;                                // k-atoms of a d-wide row
   const int KUd = d >> 6;                                  // 64-wide activation units of a d-wide row (who stages a unit contributes its statistics)
-  const int n_first = a.first_n_new > 0 ? a.first_n_new : 1;
+  const int n_first = LEAN ? 1 : (a.first_n_new > 0 ? a.first_n_new : 1);
   // sa.multi: the n_first prompt positions of every utterance are processed together in ONE iteration, as NF "virtual
   // utterances" per clip (row vu = utterance * NF + position; causal self-attention among a clip's rows).  Such a launch has
   // a single iteration (the host follows it with a plain decode launch), so the row count is a launch constant.
-  const int NF = sa.multi ? n_first : 1;
+  const int NF = LEAN ? 1 : (sa.multi ? n_first : 1);
   const int R = B * NF;                                    // activation rows of this launch
-  const int total_iters = sa.multi ? 1 : a.n_iters + n_first - 1;   // otherwise: leading forced (prompt) tokens, then n_iters heads
+  const int total_iters = (!LEAN && sa.multi) ? 1 : a.n_iters + n_first - 1;   // otherwise: leading forced (prompt) tokens, then n_iters heads
   const int ntask = R * H;
   const long long xreg = sa.set_words - (long long)L * sa.layer_words;   // residual-stream words + head statistics
   const int kv0 = a.state->kv_len;
@@ -304,7 +307,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
       };
       for (int it = 0; it < total_iters && !stop; ++it) {
         const int kv = kv0 + it;
-        const bool head_on = sa.multi || it >= n_first - 1;
+        const bool head_on = LEAN || sa.multi || it >= n_first - 1;
         for (int l = 0; l < L && !stop; ++l) {
           for (int ph = 0; ph < 8 && !stop; ++ph) {
             if (ph == 1) {                      // resident self-KV rows [0, kv) of my (utterance, head) tasks: K_i, V_i interleaved
@@ -417,7 +420,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           if (s_break_it <= it) break;
         }
         const int kv = kv0 + it;
-        const bool head_on = sa.multi || it >= n_first - 1;
+        const bool head_on = LEAN || sa.multi || it >= n_first - 1;
         for (int l = 0; l < L; ++l) {
           for (int ph = 0; ph < 8; ++ph) {
             if (ph == 1 || ph == 4) {             // attention stages are consumed by the workers: skip over them
@@ -466,15 +469,15 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
 
     for (int it = 0; it < total_iters; ++it) {
       const int kv = kv0 + it;
-      const bool head_on = sa.multi || it >= n_first - 1;
-      const bool begin_on = head_on && (sa.multi || it == n_first - 1) && a.first_is_prefill && a.begin_bias != nullptr;
+      const bool head_on = LEAN || sa.multi || it >= n_first - 1;
+      const bool begin_on = !LEAN && head_on && (sa.multi || it == n_first - 1) && a.first_is_prefill && a.begin_bias != nullptr;
       if (wt == 0) {
         int done = 1;
         for (int b = 0; b < B; ++b) done &= (s_fin[b] != 0);
-        if (it < n_first && a.first_is_prefill) done = 0;          // the prefill always runs
+        if (!LEAN && it < n_first && a.first_is_prefill) done = 0;          // the prefill always runs
         s_go = done ? 2 : 1;
       }
-      if (wt < R && it < n_first) s_tok[wt] = a.first_tokens[sa.multi ? wt : wt * n_first + it];
+      if (wt < R && it < n_first) s_tok[wt] = a.first_tokens[(!LEAN && sa.multi) ? wt : wt * n_first + it];
       wbar();
       if (wt == 0) { if (s_go == 2) s_break_it = it; else s_step = it + 1; }
       if (s_go == 2) break;
@@ -517,7 +520,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           for (int t = first_task(l, kind, sa.task_inv); t < ntask; t += G) {
             const int vu = t / H, h = t - vu * H;            // row (virtual utterance) and head
             const int ub = vu / NF, pi = vu - ub * NF;       // clip and position within this launch's new rows
-            const int nvalid = kind ? (a.t_valid ? a.t_valid[ub] : T) : kv;
+            const int nvalid = kind ? ((!LEAN && a.t_valid) ? a.t_valid[ub] : T) : kv;
             // q of my row, and (self-attention) k / v of the clip's new rows 0..pi: the causal part that is not in the cache yet
             const int nitems = kind ? 64 : 64 + (pi + 1) * 128;
 #pragma unroll 1
@@ -691,7 +694,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           if (wt == 0) {
             // sliding-window penalty ids (APPLY_PENALTY, Export_Whisper.py:318-331): active once generated >= penalty_range
             int nmax = 0;
-            if (a.penalty_value != 1.0f && !begin_on) {
+            if (!LEAN && a.penalty_value != 1.0f && !begin_on) {
               for (int b = 0; b < B; ++b) {
                 const bool act = s_ngen[b] >= a.penalty_range;
                 const int ns = s_nsave[b];
@@ -941,7 +944,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
         const int t_end = r.z + (r.y - r.x) / KAd;
         const float* wscale = sa.head_s;
         wbar();                                             // s_pen / s_pen_n visible
-        const bool pen_on = s_pen_n > 0;
+        const bool pen_on = !LEAN && s_pen_n > 0;
         float mean[RR], rstd[RR], bvv[RR]; int bii[RR];
 #pragma unroll
         for (int rr = 0; rr < RR; ++rr) { mean[rr] = 0.f; rstd[rr] = 1.f; bvv[rr] = -INFINITY; bii[rr] = 0x7fffffff; }
@@ -1005,7 +1008,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
                     for (int qq = 0; qq < s_pen_n; ++qq) hit |= (s_pen[ub * 32 + qq] == n);
                     if (hit) val *= a.penalty_value;
                   }
-                  if (a.logits) a.logits[(long long)ub * a.vocab + n] = val;
+                  if (!LEAN && a.logits) a.logits[(long long)ub * a.vocab + n] = val;
                   val += bg;
                   if (val > bvv[rr] || (val == bvv[rr] && n < bii[rr])) { bvv[rr] = val; bii[rr] = n; }
                 }
@@ -1301,15 +1304,20 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
 
 cudaError_t launch_decoder_stream(const StreamArgs& sa_in, const CUtensorMap& cross_map, const CUtensorMap& kc_map,
                                   const CUtensorMap& vc_map, int nrt, int num_sms, size_t smem_bytes, cudaStream_t st) {
-  void* fns[11] = {(void*)decoder_stream_kernel<1, false, false>, (void*)decoder_stream_kernel<2, false, false>,
-                   (void*)decoder_stream_kernel<4, false, false>, (void*)decoder_stream_kernel<8, false, false>,
-                   (void*)decoder_stream_kernel<1, true, false>, (void*)decoder_stream_kernel<2, true, false>,
-                   (void*)decoder_stream_kernel<4, true, false>, (void*)decoder_stream_kernel<8, true, false>,
-                   (void*)decoder_stream_kernel<1, false, true>, (void*)decoder_stream_kernel<2, false, true>,
-                   (void*)decoder_stream_kernel<4, false, true>};
+  void* fns[15] = {(void*)decoder_stream_kernel<1, false, false, false>, (void*)decoder_stream_kernel<2, false, false, false>,
+                   (void*)decoder_stream_kernel<4, false, false, false>, (void*)decoder_stream_kernel<8, false, false, false>,
+                   (void*)decoder_stream_kernel<1, true, false, false>, (void*)decoder_stream_kernel<2, true, false, false>,
+                   (void*)decoder_stream_kernel<4, true, false, false>, (void*)decoder_stream_kernel<8, true, false, false>,
+                   (void*)decoder_stream_kernel<1, false, true, false>, (void*)decoder_stream_kernel<2, false, true, false>,
+                   (void*)decoder_stream_kernel<4, false, true, false>,
+                   (void*)decoder_stream_kernel<1, false, false, true>, (void*)decoder_stream_kernel<2, false, false, true>,
+                   (void*)decoder_stream_kernel<4, false, false, true>, (void*)decoder_stream_kernel<8, false, false, true>};
   if (sa_in.fp8 && (nrt > 4 || sa_in.m.timing)) return cudaErrorInvalidValue;
-  const int slot = sa_in.fp8 ? 8 + (nrt == 1 ? 0 : (nrt == 2 ? 1 : 2))
-                             : (nrt == 1 ? 0 : (nrt == 2 ? 1 : (nrt == 4 ? 2 : 3))) + (sa_in.m.timing ? 4 : 0);
+  const MegaArgs& ma = sa_in.m;
+  const bool lean = sa_in.lean && !sa_in.fp8 && !ma.timing && !sa_in.multi && ma.first_n_new <= 1 && !ma.first_is_prefill && !ma.t_valid &&
+                    ma.penalty_value == 1.0f && !ma.logits;
+  const int cls = nrt == 1 ? 0 : (nrt == 2 ? 1 : (nrt == 4 ? 2 : 3));
+  const int slot = sa_in.fp8 ? 8 + cls : (lean ? 11 + cls : cls + (ma.timing ? 4 : 0));
   void* fn = fns[slot];
   static AttrOnce attr;
   if (attr.need(slot)) {

@@ -102,6 +102,7 @@ struct b200asr_engine {
     StreamPlan plans[4]; bool plan_ok[4] = {false, false, false, false}; bool tables = false;   // one plan per row-count class (1, 2, 4, 8)
   } stt[2];
   bool use_fp8 = false;
+  bool stream_lean = true;
   unsigned long long* st_acc = nullptr; size_t st_acc_words = 0; unsigned long long* st_cand = nullptr; size_t st_cand_words = 0;
   CUtensorMap st_cross{}, st_kc{}, st_vc{}; int st_map_B = -1, st_map_T = -1;
   std::string graph_key;
@@ -717,6 +718,7 @@ static int launch_stream(b200asr_engine* e, int rows, int n_heads_iters, const i
   sa.cnt_ld = pl.cnt_ld; sa.xt = pl.xt; sa.n_stages = pl.n_stages; sa.n_slots = pl.n_slots;
   sa.task_inv = e->ring_task_inv; sa.l2_hint = e->stream_l2_hint ? 1 : 0; sa.debug = e->stream_debug; sa.multi = multi ? 1 : 0;
   sa.keep_state = keep_state ? 1 : 0;
+  sa.lean = e->stream_lean ? 1 : 0;
   if (nclips > 0 && nclips < e->B) {
     MegaArgs& m = sa.m;
     const b200asr_config& c = e->cfg;
@@ -906,6 +908,7 @@ int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value) {
   if (!strcmp(key, "stream_debug")) { e->stream_debug = (int)value; return B200ASR_OK; }
   if (!strcmp(key, "stream_multi")) { e->stream_multi = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "fp8")) { e->use_fp8 = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "stream_lean")) { e->stream_lean = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring")) { e->use_ring = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_tc")) { e->ring_tc = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "ring_debug")) { e->ring_debug = (int)value; return B200ASR_OK; }

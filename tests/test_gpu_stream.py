@@ -145,3 +145,26 @@ def test_stream_multi_row_prefill_equals_token_by_token(nb):
     print(f"batch {nb}: multi-row vs token-by-token prefill max |dlogit| =", d)
     assert d <= 5e-4
     assert out[1][1] == out[0][1]
+
+
+@pytest.mark.parametrize("nb", [1, 4, 8])
+def test_stream_lean_instantiation_gives_the_same_streams(nb):
+    """The plain greedy decode launch runs an instantiation with the rarely used branches compiled out (`stream_lean`, default on:
+    no prompt rows, begin-suppress, penalty, logits dump or per-clip key counts).  Same arithmetic: token streams identical to
+    the full instantiation's, for the device loop and for transcribe, and the full one still serves penalty / ragged launches."""
+    g, raw, tensors = load_case(GOLD[0])
+    clips = np.stack([synth_pcm(70 + i, 24160) for i in range(nb)])
+    out = {}
+    for lean in (1, 0):
+        eng = _mk(tensors, 1, max_batch=nb)
+        eng.set_option("stream_lean", lean)
+        eng.set_decode_options(stop_ids=[], generate_limit=12)
+        a = eng.transcribe(clips, g["prompt"], max_new=12)
+        eng.encode(clips)
+        eng.prefill(g["prompt"], want_logits=False)
+        b = eng.decode()
+        eng.set_decode_options(stop_ids=[], generate_limit=9, repeat_penalty=0.8, penalty_range=3)
+        c = eng.transcribe(clips, g["prompt"], max_new=9)
+        out[lean] = (a, b, c)
+        eng.close()
+    assert out[1] == out[0]
