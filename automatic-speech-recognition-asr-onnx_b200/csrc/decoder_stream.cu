@@ -94,6 +94,15 @@ __device__ __noinline__ void swait_slow(uint64_t* bar, uint32_t parity, int wher
 __device__ __forceinline__ void swait(uint64_t* bar, uint32_t parity, int where) {
   if (!mbar_try_wait(bar, parity)) swait_slow(bar, parity, where);
 }
+// in-place writers: wait (rare) until every reader CTA of the previous residual-stream version has reported
+__device__ __noinline__ void rd_wait_slow(const u64* p, unsigned ex) {
+  const long long t0 = clock64();
+  for (;;) {
+    const u64 w = ld_w(p);
+    if (acc_cnt(w) == ex) return;
+    if (clock64() - t0 > kStSpin) st_timeout(21, (int)acc_cnt(w), (int)ex);
+  }
+}
 __device__ __noinline__ float2 gelu2(float a, float b) { return make_float2(gelu_erf(a), gelu_erf(b)); }
 
 // (mean, rstd) from the two statistics words of a row (sum x in 2^-24, sum x^2 in 2^-12 fixed point)
@@ -203,7 +212,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   int4* s_sched = reinterpret_cast<int4*>(bbuf + (size_t)sa.n_slots * kStSlot);     // {atom begin, atom end, first tile, first k-atom}
   unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_sched) + (size_t)n_sched * 16;
   unsigned short* s_xexp = reinterpret_cast<unsigned short*>(s_cnt + up16((size_t)n_cnt));
-  float* s_cand = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_xexp) + up16((size_t)n_xexp * 2));   // [G][NRT][2]
+  float* s_cand = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_xexp) + up16((size_t)(n_xexp + 3 * L) * 2));   // [G][NRT][2]
   float* s_part = s_cand + (((size_t)G * NRT * 2 + 3) & ~(size_t)3);             // [8][68] per-warp (max, sum, o[64]) + [8*68] new-token score
   float* s_qs = s_part + kStWorkerWarps * kStPartLd + 8;                         // [64]
   float* s_knv = s_qs + 64;                                                      // [2][64]
@@ -251,7 +260,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
 #pragma unroll 1
   for (int i = tid; i < n_cnt; i += kStThreads) s_cnt[i] = sa.cnt[i];
 #pragma unroll 1
-  for (int i = tid; i < n_xexp; i += kStThreads) s_xexp[i] = sa.xexp[i];
+  for (int i = tid; i < n_xexp + 3 * L; i += kStThreads) s_xexp[i] = sa.xexp[i];     // + [L][3] CTAs that read the residual stream in qkv / cq / fc1
 #pragma unroll 1
   for (int i = tid; i < sa.n_slots * kStSlot / 16; i += kStThreads) reinterpret_cast<uint4*>(bbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid < B) {
@@ -369,7 +378,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
       int tctr = 0;
       const uint32_t ring_u = smem_u32(ring), bbuf_u = smem_u32(bbuf);
       const int ml = warp == 10;                          // my lane: atoms whose offset in the run has my parity
-      auto linear = [&](int4 r, int KA) {
+      auto linear = [&](int4 r, int KA, u64* rd_sig) {
         // everything that does not depend on this phase's activations happens before the wait for them: my weight stages of
         // the phase (streamed ahead by the producer) and the first accumulator buffer are confirmed here, so the section
         // between "B operand staged" and "accumulator ready" is MMA issue only (measured: 0.91 -> 0.86 ms per step)
@@ -382,6 +391,9 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
         if (r.x >= r.y) return;                            // no atoms of this phase here: no hand-shake either (workers skip it too)
         swait(&b_ready, bpar, 3); bpar ^= 1u;
         tc_fence_after();
+        // every worker of this CTA has consumed its input words: report the CTA as a finished reader of the residual stream
+        // (qkv / cq / fc1; the in-place writers of the next version wait for all of them, see the epilogue)
+        if (rd_sig && ml == 0) red_add(rd_sig, 1ull << 52);
         int ka = r.w;
         bool tile_start = true, fresh = true;
         for (int at = r.x; at < r.y; ++at) {
@@ -430,11 +442,13 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               ring_adv(p, n, NS);
             } else {
               const int p6 = phase_p6(ph);
-              linear(s_sched[l * 6 + p6], phase_ka(p6, d, ffn, KSH));
+              u64* lay_w = sa.acc + (size_t)(it & 1) * sa.set_words + xreg + (long long)l * sa.layer_words;
+              linear(s_sched[l * 6 + p6], phase_ka(p6, d, ffn, KSH),
+                     (p6 == 0 || p6 == 2 || p6 == 4) ? lay_w + (long long)NRT * (6 * d + ffn) + 6 * NRT + (p6 >> 1) : nullptr);
             }
           }
         }
-        if (head_on) linear(s_sched[6 * L], KAd);
+        if (head_on) linear(s_sched[6 * L], KAd, nullptr);
       }
     }
     __syncwarp();
@@ -855,6 +869,10 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           if (nat > 0) {                                     // phases without atoms here have no MMA side to hand over to
             fence_proxy_async_smem();
             mbar_arrive(&b_ready);
+            // (The residual stream is accumulated IN PLACE by out / cross-out / fc2, so those writers may only start once every
+            // reader of the version before has consumed it: a reader that fell a phase behind would otherwise poll for a
+            // contributor count the words have already passed -- observed as a hang once in ~500 clips under stress.  The MMA lane
+            // reports the CTA as done when b_ready completes; the writers check in their epilogue.)
           }
           // statistics after the MMA has been released: the readers need them one phase later.  One RED pair per warp,
           // counting the k-atoms it covers (nstat is warp-uniform)
@@ -869,6 +887,13 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           // ---- TMEM epilogue: row sums (hi + lo) -> fixed point -> RED into the output words.  `bias` (and x0 at layer 0) is
           //      added by the contributor that owns k-atom 0 of the tile. ----
           int tile = r.z, at = r.x;
+          // in-place writers (out, cross-out, fc2): all readers of the previous version of the residual stream must be done; the
+          // word is requested here, before the wait for the tensor core, so the check costs no latency in the common case
+          const bool inplace = p6 == 1 || p6 == 3 || p6 == 5;
+          const u64* rdp = stats + 6 * NRT + (p6 >> 1);
+          const unsigned rd_ex = inplace ? (unsigned)s_xexp[n_xexp + l * 3 + (p6 >> 1)] : 0u;
+          u64 rdw = (inplace && epi_warp && at < r.y) ? ld_w(rdp) : 0ull;
+          bool rd_ok = !inplace;
 #pragma unroll 1
           while (at < r.y) {
             const int tend = min(r.y, at + KA - (at == r.x ? r.w : 0));
@@ -912,6 +937,10 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&acc_empty[buf]);
+              if (!rd_ok) {
+                if (acc_cnt(rdw) != rd_ex) rd_wait_slow(rdp, rd_ex);
+                rd_ok = true;
+              }
               if (n < Nrows) {
 #pragma unroll
                 for (int rr = 0; rr < RR; ++rr) {
@@ -1224,7 +1253,7 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
   std::vector<int4> sched((size_t)G * n_sched);
   const int cnt_ld = std::max(tiles(3 * d), tiles(ffn)), xt = tiles(d);
   std::vector<unsigned char> cnt((size_t)L * 3 * cnt_ld, 0);
-  std::vector<unsigned short> xexp((size_t)L * 3 * xt, 0);
+  std::vector<unsigned short> xexp((size_t)L * 3 * xt + (size_t)L * 3, 0);      // + [L][3]: CTAs with atoms in qkv / cq / fc1 (readers of the residual stream)
   std::vector<long long> load(G, 0);
   std::vector<int> order(G);
   std::vector<int> xcum(xt, 0);
@@ -1259,6 +1288,9 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
       for (int t = 0; t < nt; ++t) if (c_of[t] > 255) return false;
       if (p6 == 0 || p6 == 2 || p6 == 4) {
         const int row = l * 3 + (p6 >> 1);
+        int readers = 0;
+        for (int c = 0; c < G; ++c) { const int4 rr = sched[(size_t)c * n_sched + l * 6 + p6]; readers += rr.y > rr.x; }
+        xexp[(size_t)L * 3 * xt + row] = (unsigned short)readers;
         for (int t = 0; t < nt; ++t) cnt[(size_t)row * cnt_ld + t] = (unsigned char)c_of[t];
       } else {
         const int row = l * 3 + (p6 == 1 ? 0 : (p6 == 3 ? 1 : 2));
@@ -1278,13 +1310,13 @@ bool stream_plan(int batch, int d, int ffn, int n_heads, int vocab, int n_layers
   max_slots = std::max(max_slots, KAd);
   if (plan) {
     plan->nrt = nrt; plan->cnt_ld = cnt_ld; plan->xt = xt; plan->n_slots = max_slots;
-    long long lw = (long long)nrt * (6 * d + ffn) + 6 * nrt;
+    long long lw = (long long)nrt * (6 * d + ffn) + 6 * nrt + 4;        // + 3 reader-done counters
     lw = (lw + 15) / 16 * 16;
     long long xr = (long long)nrt * d + 2 * nrt;
     xr = (xr + 15) / 16 * 16;
     plan->layer_words = lw; plan->set_words = xr + (long long)L * lw;
     plan->cand_words = (size_t)2 * G * nrt * 2;
-    const int n_cnt = L * 3 * cnt_ld, n_xexp = L * 3 * xt;
+    const int n_cnt = L * 3 * cnt_ld, n_xexp = L * 3 * xt + L * 3;
     auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t fixed = 1024 /*alignment*/ + (size_t)max_slots * kStSlot + (size_t)n_sched * 16 + up16((size_t)n_cnt) +
                          up16((size_t)n_xexp * 2) +
