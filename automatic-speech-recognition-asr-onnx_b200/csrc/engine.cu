@@ -102,7 +102,7 @@ struct b200asr_engine {
     StreamPlan plans[4]; bool plan_ok[4] = {false, false, false, false}; bool tables = false;   // one plan per row-count class (1, 2, 4, 8)
   } stt[2];
   bool use_fp8 = false;
-  bool stream_lean = false;        // off: under stress (hundreds of back-to-back transcribe calls) the lean instantiation hung once in ~250 launches; see DESIGN.md section 7
+  bool stream_lean = true;
   unsigned long long* st_acc = nullptr; size_t st_acc_words = 0; unsigned long long* st_cand = nullptr; size_t st_cand_words = 0;
   CUtensorMap st_cross{}, st_kc{}, st_vc{}; int st_map_B = -1, st_map_T = -1;
   std::string graph_key;
