@@ -220,7 +220,11 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   float* s_sc = s_best + kStWorkerWarps * NRT * 2 + ((4 - ((kStWorkerWarps * NRT * 2) & 3)) & 3);   // [8 warps][64] attention scores / probabilities
 
   __shared__ uint64_t full_bar[kStMaxStages], empty_bar[kStMaxStages];
-  __shared__ uint64_t b_ready, acc_full[2], acc_empty[2];
+  // slot_bar[s] (4+ rows): the B operand of k-atom slot s is staged (every staging lane of every active row arrives), so the MMA lanes
+  // start on the slots whose input words have landed while the stagers of the others are still polling -- with 4+ rows staging
+  // takes several poll rounds (0.982 -> 0.935 ms per step at batch 4); with 1-2 rows one hand-over per phase through b_ready is
+  // faster (0.817 vs 0.840 ms at batch 1)
+  __shared__ uint64_t slot_bar[32], b_ready, acc_full[2], acc_empty[2];
   __shared__ int box_cnt[kStMaxStages];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_tok[8], s_ngen[8], s_fin[8], s_nsave[8];
@@ -246,10 +250,12 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
   const long long xreg = sa.set_words - (long long)L * sa.layer_words;   // residual-stream words + head statistics
   const int kv0 = a.state->kv_len;
   constexpr int kEpiWarps = NRT > 4 ? 8 : 4;
+  constexpr bool kSlotHandOver = NRT >= 4;                 // B operand handed to the MMA lanes slot by slot instead of once per phase
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); box_cnt[s] = 0; }
     mbar_init(&b_ready, kStWorkers);
+    for (int s = 0; s < 32; ++s) mbar_init(&slot_bar[s], (uint32_t)(32 * R * (F8 ? 2 : 1)));
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 2); mbar_init(&acc_empty[s], kStWorkerWarps); }
     mbar_fence_init();
     prefetch_tensormap(&cross_map); prefetch_tensormap(&kc_map); prefetch_tensormap(&vc_map);
@@ -374,7 +380,7 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
     if (lane == 0) {
       constexpr uint32_t idesc = F8 ? idesc_f8_e4m3_e5m2(128, 16) : idesc_bf16(128, 16);
       RingPos p{0, 0};
-      uint32_t bpar = 0;
+      uint32_t bpar = 0, spar = 0;                        // parity of b_ready; bit s: parity of slot s's next hand-over
       int tctr = 0;
       const uint32_t ring_u = smem_u32(ring), bbuf_u = smem_u32(bbuf);
       const int ml = warp == 10;                          // my lane: atoms whose offset in the run has my parity
@@ -389,11 +395,15 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           if (r.x < r.y) swait(&acc_empty[tctr & 1], (uint32_t)(((tctr >> 1) & 1) ^ 1), 4);
         }
         if (r.x >= r.y) return;                            // no atoms of this phase here: no hand-shake either (workers skip it too)
-        swait(&b_ready, bpar, 3); bpar ^= 1u;
-        tc_fence_after();
-        // every worker of this CTA has consumed its input words: report the CTA as a finished reader of the residual stream
-        // (qkv / cq / fc1; the in-place writers of the next version wait for all of them, see the epilogue)
-        if (rd_sig && ml == 0) red_add(rd_sig, 1ull << 52);
+        const int nsl = min(r.y - r.x, KA);                // slots the workers stage in this phase
+        uint32_t waited = 0;
+        if (!kSlotHandOver) {
+          swait(&b_ready, bpar, 3); bpar ^= 1u;
+          tc_fence_after();
+          // every worker of this CTA has consumed its input words: report the CTA as a finished reader of the residual stream
+          // (qkv / cq / fc1; the in-place writers of the next version wait for all of them, see the epilogue)
+          if (rd_sig && ml == 0) red_add(rd_sig, 1ull << 52);
+        }
         int ka = r.w;
         bool tile_start = true, fresh = true;
         for (int at = r.x; at < r.y; ++at) {
@@ -403,6 +413,10 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
           if (((at - r.x) & 1) == ml) {
             if (at - r.x >= npre) { swait(&full_bar[p.stage], p.phase, 5); tc_fence_after(); }
             int slot = ka - r.w; if (slot < 0) slot += KA;
+            if (kSlotHandOver) {
+              if (!((waited >> slot) & 1u)) { swait(&slot_bar[slot], (spar >> slot) & 1u, 3); waited |= 1u << slot; }
+              tc_fence_after();
+            }
             const uint64_t adesc = smem_desc_sw128(ring_u + (uint32_t)p.stage * kStStage);
             const uint64_t bdesc = smem_desc_sw128(bbuf_u + (uint32_t)slot * kStSlot);
 #pragma unroll
@@ -422,6 +436,14 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
             ++tctr; fresh = true; tile_start = true;
             if (ka == KA) ka = 0;
           }
+        }
+        if (kSlotHandOver) {
+          if (rd_sig && ml == 0) {                         // reader report: once EVERY slot of the phase is staged (the other lane's too)
+            for (int sl = 0; sl < nsl; ++sl)
+              if (!((waited >> sl) & 1u)) swait(&slot_bar[sl], (spar >> sl) & 1u, 3);
+            red_add(rd_sig, 1ull << 52);
+          }
+          spar ^= nsl >= 32 ? 0xffffffffu : ((1u << nsl) - 1u);    // every staged slot completed one hand-over, waited on by me or not
         }
       };
       for (int it = 0; it < total_iters; ++it) {
@@ -864,9 +886,13 @@ decoder_stream_kernel(const __grid_constant__ CUtensorMap cross_map, const __gri
               *reinterpret_cast<__nv_bfloat162*>(slotp + (rh >> 3) * 1024 + (rh & 7) * 128 + ((chunk ^ (rh & 7)) << 4) + within) = hi;
               *reinterpret_cast<__nv_bfloat162*>(slotp + (rl >> 3) * 1024 + (rl & 7) * 128 + ((chunk ^ (rl & 7)) << 4) + within) = lo;
               }
+              if (kSlotHandOver) {
+                fence_proxy_async_smem();
+                mbar_arrive(&slot_bar[F8 ? (s >> 1) : s]);    // this lane's share of the slot is visible to the tensor core
+              }
             }
           }
-          if (nat > 0) {                                     // phases without atoms here have no MMA side to hand over to
+          if (!kSlotHandOver && nat > 0) {                   // phases without atoms here have no MMA side to hand over to
             fence_proxy_async_smem();
             mbar_arrive(&b_ready);
             // (The residual stream is accumulated IN PLACE by out / cross-out / fc2, so those writers may only start once every

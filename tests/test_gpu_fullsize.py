@@ -99,6 +99,23 @@ def test_large_v3_fp8_kernel_matches_fp32_engine_on_dequantised_weights():
     assert np.array_equal(got.argmax(-1)[safe], want.argmax(-1)[safe])
 
 
+def test_large_v3_back_to_back_clips_stress():
+    """400 back-to-back clips through the one-call path at full size: every call returns, and returns the same tokens.  Guards the
+    exchange protocol of the streaming decode kernel: before the in-place writers of the residual stream waited for the readers
+    of the previous version, a CTA that fell one phase behind hung the chain about once in 500 clips (DESIGN.md section 7, item 10;
+    `tools/stress_transcribe.py` runs the long version)."""
+    pcm = synth_pcm(0, 128000)
+    tensors = fold_whisper(synth_whisper_checkpoint(DIMS, 20260, pos_scale=POS_SCALE), DIMS, SUP, BEG)
+    eng = WhisperEngine(DIMS, tensors, precision="bf16", max_batch=8, max_samples=128000)
+    del tensors
+    eng.set_decode_options(stop_ids=[], generate_limit=33)
+    first = eng.transcribe(pcm, PROMPT, max_new=33)
+    assert len(set(first[0])) >= 10
+    for i in range(400):
+        assert eng.transcribe(pcm, PROMPT, max_new=33) == first, i
+    eng.close()
+
+
 # ---- Qwen3-ASR-0.6B dimensions (BASELINE configs[4]'s model): one 8 s clip, prefill + 2 decode steps ----
 @pytest.fixture(scope="module")
 def qwen_reference():
