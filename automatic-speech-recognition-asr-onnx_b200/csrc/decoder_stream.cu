@@ -30,6 +30,13 @@
 //
 // Accumulator words are double-buffered by step parity; while a step runs on one set every CTA zeroes its share of
 // the other (last read one step earlier, all CTAs pass the per-step arg-max exchange in between).
+//
+// The one place where a word is written more than once per step is the residual stream (out / cross-out / fc2 add into it
+// in place).  A reader that fell a phase behind would poll for a contributor count the words have already passed, so the
+// in-place writers wait for a per-(layer, version) "readers done" word that the MMA lane of every reading CTA bumps once the
+// CTA's B operand is complete (three 8-byte words per layer; found by tools/stress_transcribe.py).
+// With 4+ activation rows the B operand is handed to the MMA lanes slot by slot (one mbarrier per k-atom slot), with 1-2
+// rows once per phase.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda_fp16.h>
