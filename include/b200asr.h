@@ -131,7 +131,11 @@ int b200asr_get_stage(b200asr_engine* e, const char* name, float* out, int64_t c
  * batch <= 8), "stream_multi" = prompt rows of all clips as one multi-row prefill iteration, "stream_l2_hint" = L2 evict-first
  * policy on the streamed boxes; with "stream" 0: "ring" = round 1's CUDA-core streaming kernel (batch <= 4), else "mega" = the
  * grid-barrier kernel, else the per-op CUDA graph.  "mega_timing" 1 selects the instrumented build (per-phase stamps, read back
- * with get_stage("mega_timing")). */
+ * with get_stage("mega_timing")).  "fp8" (default 0): decoder matrices + tied head as E4M3 with per-row scales in the streaming
+ * kernel (quantised on device at the next launch; batch <= 4; any launch the FP8 kernel cannot take is refused with
+ * B200ASR_E_INVALID).  "stream_lean" (default 1): plain greedy decode launches use the instantiation with the prompt / penalty /
+ * logits / ragged branches compiled out.  "pdl" (default 1): encoder GEMMs and LayerNorm kernels launch as programmatic
+ * dependents; "enc_graph" (default 1): the encoder replays as one CUDA graph per (batch, length). */
 int b200asr_set_option(b200asr_engine* e, const char* key, int64_t value);
 void* b200asr_stream(b200asr_engine* e);                 /* cudaStream_t of the engine */
 int b200asr_synchronize(b200asr_engine* e);
