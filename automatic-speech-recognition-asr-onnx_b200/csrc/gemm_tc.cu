@@ -404,7 +404,12 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t st, std:
   // largest N tile that still gives (nearly) one tile per SM; small problems take the narrow tile
   // up to four row tiles (one short clip): every tile is latency-bound (pipeline fill + epilogue tail), and narrow tiles
   // spread that tail over more SMs -- measured 5.06 ms vs 5.26 ms for the large-v3 encoder at batch 1
-  if (g.batch == 1 && tm <= 4) return launch_bn<64>(g, num_sms, st, err);
+  if (g.batch == 1 && tm <= 4) {
+    // ... except when 128-wide tiles fill the machine in exactly one round (the 400-row QKV GEMM: 4 x 30 = 120 tiles instead
+    // of 240 tiles in two rounds: encoder 3.49 -> 3.40 ms; 256-wide tiles for the 5120-wide fc1 measured slower, 3.43)
+    if (tiles(128) <= num_sms && tiles(128) * 4 >= (int64_t)num_sms * 3) return launch_bn<128>(g, num_sms, st, err);
+    return launch_bn<64>(g, num_sms, st, err);
+  }
   const int64_t want = (int64_t)num_sms * 9 / 10;
   if (tiles(256) >= want) return launch_bn<256>(g, num_sms, st, err);
   if (tiles(128) >= want) return launch_bn<128>(g, num_sms, st, err);
