@@ -405,9 +405,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t st, std:
   // up to four row tiles (one short clip): every tile is latency-bound (pipeline fill + epilogue tail), and narrow tiles
   // spread that tail over more SMs -- measured 5.06 ms vs 5.26 ms for the large-v3 encoder at batch 1
   if (g.batch == 1 && tm <= 4) {
-    // ... except when 128-wide tiles fill the machine in exactly one round (the 400-row QKV GEMM: 4 x 30 = 120 tiles instead
-    // of 240 tiles in two rounds: encoder 3.49 -> 3.40 ms; 256-wide tiles for the 5120-wide fc1 measured slower, 3.43)
-    if (tiles(128) <= num_sms && tiles(128) * 4 >= (int64_t)num_sms * 3) return launch_bn<128>(g, num_sms, st, err);
+    // ... except when 128-wide tiles fill the machine in about one round (400 rows: QKV 4 x 30 = 120 tiles, fc1 160 tiles, instead
+    // of 240 / 320 in two / three rounds: encoder 3.49 -> 3.33 ms; 256-wide tiles for the 5120-wide fc1 measured slower)
+    if (tiles(128) <= num_sms + num_sms / 8 && tiles(128) * 4 >= (int64_t)num_sms * 3) return launch_bn<128>(g, num_sms, st, err);
     return launch_bn<64>(g, num_sms, st, err);
   }
   const int64_t want = (int64_t)num_sms * 9 / 10;
