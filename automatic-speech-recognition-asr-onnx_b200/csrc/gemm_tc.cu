@@ -410,7 +410,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t st, std:
     if (tiles(128) <= num_sms + num_sms / 8 && tiles(128) * 4 >= (int64_t)num_sms * 3) return launch_bn<128>(g, num_sms, st, err);
     return launch_bn<64>(g, num_sms, st, err);
   }
-  const int64_t want = (int64_t)num_sms * 9 / 10;
+  const int64_t want = (int64_t)num_sms * 8 / 10;      // (1600 rows x 1280 columns: 130 tiles of 128 in one round beat 260 tiles of 64 in two)
   if (tiles(256) >= want) return launch_bn<256>(g, num_sms, st, err);
   if (tiles(128) >= want) return launch_bn<128>(g, num_sms, st, err);
   return launch_bn<64>(g, num_sms, st, err);
