@@ -399,8 +399,9 @@ int enqueue_decoder(b200asr_engine* e, const int* tokens_dev, int n_new, bool fi
 
 int ensure_step_graph(b200asr_engine* e) {
   char key[384];
-  snprintf(key, sizeof key, "%d/%d/%d/%g/%d/%zu/%g/%d/%g/%g/%llu/%p", e->B, e->T_enc, e->limit, e->repeat_penalty, e->penalty_range,
-           e->stop_ids.size(), e->samp_temperature, e->samp_top_k, e->samp_top_p, e->samp_rep, e->samp_seed, (void*)e->samp_noise);
+  snprintf(key, sizeof key, "%d/%d/%d/%g/%d/%zu/%g/%d/%g/%g/%llu/%p/%d", e->B, e->T_enc, e->limit, e->repeat_penalty, e->penalty_range,
+           e->stop_ids.size(), e->samp_temperature, e->samp_top_k, e->samp_top_p, e->samp_rep, e->samp_seed, (void*)e->samp_noise,
+           e->ragged ? 1 : 0);          // (the per-clip key-count pointer of the cross-attention launches is baked into the nodes)
   if (e->step_graph && e->graph_key == key) return B200ASR_OK;
   if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
   cudaGraph_t graph = nullptr;

@@ -112,6 +112,26 @@ def test_ragged_decoder_paths_agree_bf16():
         assert d <= 1e-2
 
 
+def test_ragged_after_uniform_on_the_same_engine_and_shape():
+    """The per-op decoder replays one CUDA graph per step; its cross-attention nodes carry the per-clip key-count pointer, so a
+    ragged batch after a uniform batch of the same shape (and back) must not reuse the other's graph."""
+    g, raw, tensors = load_case(GOLD[0])
+    clips = _clips()[:2]
+    pcm, lens = WhisperEngine.pad_ragged(clips)
+    forced = g["forced_tokens"].tolist()[:3]
+    for opts in ({"stream": 0, "mega": 0}, {"stream": 0}, {}):
+        eng = make_engine(tensors, "bf16", max_batch=2)
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        u1 = _run(eng, pcm, g["prompt"], forced)                   # uniform: both rows at full length (padding is audio here)
+        r1 = _run(eng, pcm, g["prompt"], forced, lens=lens)
+        u2 = _run(eng, pcm, g["prompt"], forced)
+        r2 = _run(eng, pcm, g["prompt"], forced, lens=lens)
+        assert np.array_equal(u1, u2) and np.array_equal(r1, r2), opts
+        assert maxdiff(u1[1], r1[1]) > 1e-3, opts                  # the shorter clip really is treated differently
+        eng.close()
+
+
 def test_ragged_argument_checks():
     g, raw, tensors = load_case(GOLD[0])
     eng = make_engine(tensors, "bf16", max_batch=2)
