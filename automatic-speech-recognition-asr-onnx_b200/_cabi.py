@@ -105,6 +105,12 @@ SYMBOLS = {
     "b200asr_qwen_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "b200asr_qwen_transcribe_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                                    C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+    "b200asr_qwen_upload_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "b200asr_qwen_encode_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                             C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+    "b200asr_qwen_transcribe_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                                 C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                                 C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "b200asr_qwen_get_stage": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64)]),
     "b200asr_qwen_kernel_launches": (C.c_int64, [C.c_void_p]),
     "b200asr_qwen_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),

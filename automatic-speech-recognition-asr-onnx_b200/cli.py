@@ -79,6 +79,7 @@ def main(argv=None) -> int:
     qp.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     qp.add_argument("--device", type=int, default=0)
     qp.add_argument("--set", nargs="*", default=[], metavar="NAME=VALUE", help="REPEAT_PENALTY=1.0 PENALTY_RANGE=10")
+    qp.add_argument("--batch", type=int, default=1, help="transcribe the files in ragged batches of up to N clips (each clip keeps its single-clip result)")
     svp = sub.add_parser("sensevoice")
     svp.add_argument("--model-folder", "--onnx-folder", dest="folder", required=True)
     svp.add_argument("--tokenizer-path", default=None, help="SentencePiece model (default: chn_jpn_yue_eng_ko_spectok.bpe.model in the folder)")
@@ -170,14 +171,17 @@ def _main_qwen(args) -> int:
     del state
     clips = [ingest.read_wav(p) for p in args.audio]
     pcm = [ingest.to_model_rate(x, r, dims.sample_rate) for x, r in clips]
-    eng = qw.QwenEngine(dims, tensors, prompt, precision=args.precision, max_batch=1,
+    nb = max(1, min(args.batch, 8, len(pcm)))
+    eng = qw.QwenEngine(dims, tensors, prompt, precision=args.precision, max_batch=nb,
                         max_samples=max(480000, max(len(x) for x in pcm)), device=args.device)
     query = [int(i) for i in tokenizer.encode(args.prompt, add_special_tokens=False)] if args.prompt else []
-    for path, x in zip(args.audio, pcm):
+    kw = dict(query_ids=query, language_tail_ids=tails.get(args.language, ()), sample_rate=dims.sample_rate,
+              repeat_penalty=float(consts["REPEAT_PENALTY"]), penalty_range=int(consts["PENALTY_RANGE"]))
+    batched = qw.transcribe_clips(eng, pcm, max_batch=nb, **kw) if nb > 1 else None
+    for k, (path, x) in enumerate(zip(args.audio, pcm)):
         print(f"\nTest audio : {path}   ({len(x) / dims.sample_rate:.2f} s)")
         print("-" * 70)
-        res = qw.transcribe_clip(eng, x, query_ids=query, language_tail_ids=tails.get(args.language, ()), sample_rate=dims.sample_rate,
-                                 repeat_penalty=float(consts["REPEAT_PENALTY"]), penalty_range=int(consts["PENALTY_RANGE"]))
+        res = batched[k] if batched is not None else qw.transcribe_clip(eng, x, **kw)
         text = tokenizer.decode(res["tokens"], skip_special_tokens=True)
         print(f"\nASR Result:\n{text}\n\nRTF: {res['rtf']:.4f}")
     eng.close()

@@ -162,6 +162,7 @@ struct SelectArgs {
   float temperature; int top_k; float top_p; float rep_penalty; unsigned long long seed;
   const float* noise; int noise_ld; int noise_rows;   // optional uniform noise [launch][max_batch][top_k] (reproducible runs)
   int noise_batch;                                    // max_batch: the row stride of `noise` in utterances
+  const int* limit_v;                                 // optional [B]: per-utterance generation limit, min(limit, limit_v[b]) (ragged Qwen3-ASR batches)
 };
 cudaError_t launch_select_token(const SelectArgs& a, cudaStream_t st);
 cudaError_t launch_softmax_pick(const float* logits, const float* add_bias, int vocab, int batch, int index,

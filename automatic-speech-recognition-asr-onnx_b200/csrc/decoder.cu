@@ -492,12 +492,13 @@ select_token_kernel(SelectArgs a) {
     if (!a.finished[b]) {
       bool stop = false;
       for (int s = 0; s < a.n_stop; ++s) stop |= (a.stop_ids[s] == besti);
-      if (stop || a.limit <= 0) {
+      const int limit = a.limit_v ? min(a.limit, a.limit_v[b]) : a.limit;
+      if (stop || limit <= 0) {
         a.finished[b] = 1;
       } else {
         a.tokens[(int64_t)b * a.tokens_ld + gen] = besti;
         a.n_gen[b] = gen + 1;
-        if (gen + 1 >= a.limit) a.finished[b] = 1;
+        if (gen + 1 >= limit) a.finished[b] = 1;
       }
     }
   }

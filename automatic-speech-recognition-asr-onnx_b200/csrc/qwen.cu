@@ -49,14 +49,15 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 template <typename T> __device__ __forceinline__ void store_as(void* p, int64_t i, float v) { reinterpret_cast<T*>(p)[i] = from_f<T>(v); }
 
 // ---- features: max(x, amax - 8) -> (x + 4) / 4, zero rows up to the chunk multiple (:857-865) ----
-__global__ void qwen_feat_kernel(const float* __restrict__ mel_raw, const int* __restrict__ max_key, int frames, int frames_pad,
-                                 int n_mels, float* __restrict__ feat) {
+//      `frames` = rows of the batch grid (the longest clip); a clip's own rows end at n_per_clip[b] / hop (ragged batches)
+__global__ void qwen_feat_kernel(const float* __restrict__ mel_raw, const int* __restrict__ max_key, const int* __restrict__ n_per_clip,
+                                 int hop, int frames, int frames_pad, int n_mels, float* __restrict__ feat) {
   const int b = blockIdx.y;
   const float floor_v = key_to_float(max_key[b]) - 8.0f;
-  const int64_t n = (int64_t)frames_pad * n_mels, nv = (int64_t)frames * n_mels;
+  const int64_t n = (int64_t)frames_pad * n_mels, ld = (int64_t)frames * n_mels, nv = (int64_t)(n_per_clip[b] / hop) * n_mels;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = 0.f;
-    if (i < nv) v = (fmaxf(mel_raw[b * nv + i], floor_v) + 4.0f) * 0.25f;
+    if (i < nv) v = (fmaxf(mel_raw[b * ld + i], floor_v) + 4.0f) * 0.25f;
     feat[b * n + i] = v;
   }
 }
@@ -134,12 +135,14 @@ qwen_im2col_kernel(const T* __restrict__ in /*[chunks][Ti][Fi][C]*/, int Ti, int
 }
 
 // ---- stem rows [B][chunks*13][d] + pos[row % 13] -> window-padded hidden [B][n_win*tpw][d] (:880-897) ----
-__global__ void qwen_window_kernel(const float* __restrict__ stem, const float* __restrict__ pos, int n_chunks, int rows_win, int d,
-                                   float* __restrict__ h) {
+//      rows past the clip's own last chunk are zero (ragged batches: exactly what the clip sees when it runs alone)
+__global__ void qwen_window_kernel(const float* __restrict__ stem, const float* __restrict__ pos, const int* __restrict__ n_per_clip, int hop,
+                                   int n_chunks, int rows_win, int d, float* __restrict__ h) {
   const int r = blockIdx.x, b = blockIdx.y;
   const int valid_rows = n_chunks * kChunkTok;
+  const int own_rows = ((n_per_clip[b] / hop + kChunk - 1) / kChunk) * kChunkTok;
   float* dst = h + ((int64_t)b * rows_win + r) * d;
-  if (r < valid_rows) {
+  if (r < own_rows) {
     const float* src = stem + ((int64_t)b * valid_rows + r) * d;
     const float* p = pos + (int64_t)(r % kChunkTok) * d;
     for (int i = threadIdx.x; i < d; i += blockDim.x) dst[i] = src[i] + p[i];
@@ -171,10 +174,10 @@ qwen_mask_softmax_kernel(const float* __restrict__ s, OutT* __restrict__ p, int6
 
 // ---- prompt rows: token embedding or audio row (:925, CONCAT_EMBED :1428-1435) ----
 template <typename WT>
-__global__ void qwen_prompt_kernel(const int* __restrict__ src /*[n_prompt]: id >= 0, or -(audio row) - 1*/, const WT* __restrict__ embed,
+__global__ void qwen_prompt_kernel(const int* __restrict__ src /*[B][n_prompt]: id >= 0, or -(audio row) - 1*/, const WT* __restrict__ embed,
                                    const float* __restrict__ enc_out, int64_t enc_stride, int n_prompt, int d, float* __restrict__ x) {
   const int pos = blockIdx.x, b = blockIdx.y;
-  const int s = src[pos];
+  const int s = src[(int64_t)b * n_prompt + pos];
   float* dst = x + ((int64_t)b * n_prompt + pos) * d;
   if (s >= 0) {
     const WT* e = embed + (int64_t)s * d;
@@ -198,11 +201,11 @@ __global__ void qwen_embed_kernel(const int* __restrict__ tokens, const WT* __re
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 qwen_rmsnorm_kernel(const float* __restrict__ x, int64_t ldx, int row_mul, int row_off, const float* __restrict__ gamma, float eps,
-                    OutT* __restrict__ out, int64_t ldo, int rows, int d) {
+                    OutT* __restrict__ out, int64_t ldo, int rows, int d, const int* __restrict__ row_off_v = nullptr) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float* xr = x + ((int64_t)r * row_mul + row_off) * ldx;
+  const float* xr = x + ((int64_t)r * row_mul + row_off + (row_off_v ? row_off_v[r] : 0)) * ldx;      // (ragged prefill: a clip's own last prompt row)
   float q = 0.f;
   for (int i = lane; i < d; i += 32) q += xr[i] * xr[i];
   const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
@@ -427,7 +430,7 @@ template <typename KT, int DH>
 __global__ void __launch_bounds__(kAttDecThreads)
 qwen_attn_decode_kernel(const float* __restrict__ qkv /*[B][(H+2KH)*DH]*/, const float* __restrict__ g, const float* __restrict__ cosT,
                         const float* __restrict__ sinT, float eps, KT* __restrict__ kc, KT* __restrict__ vc, int64_t cache_layer_off,
-                        int H, int KH, int max_seq, const DecState* __restrict__ state, float* __restrict__ ctx) {
+                        int H, int KH, int max_seq, const DecState* __restrict__ state, const int* __restrict__ kv_off, float* __restrict__ ctx) {
   extern __shared__ float dsm[];                 // q[DH] | k_new[DH] | v_new[DH] | scores[max_seq] | part[16][DH]
   constexpr int NW = kAttDecThreads / 32;
   __shared__ float red[NW];
@@ -439,7 +442,9 @@ qwen_attn_decode_kernel(const float* __restrict__ qkv /*[B][(H+2KH)*DH]*/, const
   float* part = sc + max_seq;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
-  const int pos = state->kv_len, n_keys = pos + 1;
+  // kv_off[b] <= 0: this clip's prompt is that much shorter than the longest.  A clip that reached its own generation_limit keeps
+  // stepping until the batch's last clip has (its tokens are no longer accepted): its position stays inside its own cache rows
+  const int pos = min(state->kv_len + kv_off[b], max_seq - 1), n_keys = pos + 1;
   const int kh = h / (H / KH);
   const int NHD = H + 2 * KH;
   KT* K = kc + cache_layer_off + ((int64_t)b * KH + kh) * max_seq * DH;
@@ -556,7 +561,8 @@ template <int DH, int SK, bool VPF>
 __global__ void __launch_bounds__(256, VPF ? 1 : 2)
 qwen_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ g, const float* __restrict__ cosT,
                        const float* __restrict__ sinT, float eps, bf16* __restrict__ kc, bf16* __restrict__ vc, int64_t cache_layer_off,
-                       int H, int KH, int max_seq, const DecState* __restrict__ state, float* __restrict__ part /*[B*H][S][DH+2]*/,
+                       int H, int KH, int max_seq, const DecState* __restrict__ state, const int* __restrict__ kv_off,
+                       float* __restrict__ part /*[B*H][S][DH+2]*/,
                        int* __restrict__ counter /*[B*H]*/, float* __restrict__ ctx) {
   constexpr int M = DH / 32, half = DH / 2, EPL = DH / 32, VK = SK / 8;
   __shared__ float qs[DH], kn[DH], vn[DH], sc[SK], red[8], pw[8][DH];
@@ -564,7 +570,7 @@ qwen_attn_split_kernel(const float* __restrict__ qkv, const float* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
   const int S = gridDim.y, sp = blockIdx.y;
-  const int pos = state->kv_len, n_keys = pos + 1;
+  const int pos = min(state->kv_len + kv_off[b], max_seq - 1), n_keys = pos + 1;      // (clamp: see qwen_attn_decode_kernel)
   const int per = (n_keys + S - 1) / S;
   const int lo = sp * per, hi = min(n_keys, lo + per);
   const int kh = h / (H / KH);
@@ -1009,7 +1015,10 @@ struct b200asr_qwen {
   int* d_stop = nullptr;
   int max_frames = 0, max_chunks = 0, max_win = 0;
   // per call
+  //   n_samples / frames / n_chunks / n_win / n_audio / n_prompt describe the LONGEST clip of the batch (= every clip of a uniform
+  //   batch); clip_ns / clip_prompt hold each clip's own values, and the device reads them from d_ns / kv_off / d_limit
   int B = 0, n_samples = 0, frames = 0, n_chunks = 0, n_win = 0, n_audio = 0, n_prompt = 0, pcm_dtype = B200ASR_PCM_I16;
+  std::vector<int> clip_ns, clip_prompt;
   bool prefilled = false;
   int limit = 0;
   // encoder buffers
@@ -1018,6 +1027,9 @@ struct b200asr_qwen {
   float *stem = nullptr, *h = nullptr, *S = nullptr, *enc_out = nullptr;
   void *xhat = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *P = nullptr;
   int *win_valid = nullptr, *prompt_src = nullptr;
+  int *d_ns = nullptr;        // [max_batch] samples per clip (front end: reflect pad and arg-max at the clip's own end)
+  int *kv_off = nullptr;      // [max_batch] clip prompt length - longest prompt length (<= 0): cache position = DecState.kv_len + kv_off[b]
+  int *d_limit = nullptr;     // [max_batch] generation limit of each clip (max_seq_len - 10 - its prompt length)
   // decoder buffers
   float *x = nullptr, *qkvf = nullptr, *q = nullptr, *gu = nullptr, *xl = nullptr, *logits = nullptr, *cand_val = nullptr;
   int* cand_idx = nullptr;
@@ -1107,9 +1119,9 @@ int qwen_encoder(b200asr_qwen* e) {
   const int64_t chunks = (int64_t)B * e->n_chunks;
   QKL(launch_fill_i32(e->max_key, INT_MIN, B, e->st));
   QKL(launch_logmel(e->pcm, e->pcm_dtype == B200ASR_PCM_F32, B, e->n_samples, e->n_samples, e->basis_t, QWF(e, "mel_fbank"),
-                    e->fb_start, e->fb_len, c.n_fft, c.hop, c.n_mels, e->mel_raw, e->max_key, e->st));
-  qwen_feat_kernel<<<dim3(grid_for((int64_t)frames_pad * c.n_mels, 256, 64), B), 256, 0, e->st>>>(e->mel_raw, e->max_key, e->frames, frames_pad,
-                                                                                                 c.n_mels, e->feat);
+                    e->fb_start, e->fb_len, c.n_fft, c.hop, c.n_mels, e->mel_raw, e->max_key, e->st, e->d_ns));
+  qwen_feat_kernel<<<dim3(grid_for((int64_t)frames_pad * c.n_mels, 256, 64), B), 256, 0, e->st>>>(e->mel_raw, e->max_key, e->d_ns, c.hop, e->frames,
+                                                                                                 frames_pad, c.n_mels, e->feat);
   QKL(cudaGetLastError());
   // conv stem: time 100 -> 50 -> 25 -> 13, mel n_mels -> /2 -> /4 -> /8
   const int T1 = 50, T2 = 25, T3 = 13;
@@ -1138,7 +1150,7 @@ int qwen_encoder(b200asr_qwen* e) {
   QRET(qwen_gemm(e, qwen_linear(e, e->c3, (int64_t)F3 * C, "conv_out.w", "", e->stem, D, kF32, rows_stem, D, F3 * C)));
   const int tpw = c.chunks_per_window * kChunkTok;
   const int rows_win = e->n_win * tpw;
-  qwen_window_kernel<<<dim3(rows_win, B), 128, 0, e->st>>>(e->stem, QWF(e, "enc_pos"), e->n_chunks, rows_win, D, e->h);
+  qwen_window_kernel<<<dim3(rows_win, B), 128, 0, e->st>>>(e->stem, QWF(e, "enc_pos"), e->d_ns, c.hop, e->n_chunks, rows_win, D, e->h);
   QKL(cudaGetLastError());
   const int M = B * rows_win, NW = B * e->n_win;
   for (int i = 0; i < c.enc_layers; ++i) {
@@ -1207,15 +1219,15 @@ int qwen_attention_launch(b200asr_qwen* e, int layer, int rows, int n_new, bool 
     const int S = (c.max_seq_len + kSplitKeys - 1) / kSplitKeys, S2 = (c.max_seq_len + 2 * kSplitKeys - 1) / (2 * kSplitKeys);
     const bool pdl_att = e->use_pdl && (rows <= 2 || e->pdl_all);
     if (ad == kBF16 && e->use_attn_split && rows * H * S <= 2 * e->num_sms) {      // 1-2 clips: (head, 128-key range) CTAs with every cache row in registers (measured better than 256-key ranges at 2 clips: 1.10 vs 1.16 ms/step)
-      QKL(launch_pdl(qwen_attn_split_kernel<DH, kSplitKeys, true>, dim3(rows * H, S), dim3(256), 0, e->st, pdl_att, (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, e->att_part, e->att_counter, (float*)e->actx));
+      QKL(launch_pdl(qwen_attn_split_kernel<DH, kSplitKeys, true>, dim3(rows * H, S), dim3(256), 0, e->st, pdl_att, (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (const int*)e->kv_off, e->att_part, e->att_counter, (float*)e->actx));
       return B200ASR_OK;
     }
     if (ad == kBF16 && e->use_attn_split && rows * H * S2 <= 2 * e->num_sms) {     // 3-4 clips: 256-key ranges keep the grid inside one wave
-      QKL(launch_pdl(qwen_attn_split_kernel<DH, 2 * kSplitKeys, false>, dim3(rows * H, S2), dim3(256), 0, e->st, pdl_att, (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, e->att_part, e->att_counter, (float*)e->actx));
+      QKL(launch_pdl(qwen_attn_split_kernel<DH, 2 * kSplitKeys, false>, dim3(rows * H, S2), dim3(256), 0, e->st, pdl_att, (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (const int*)e->kv_off, e->att_part, e->att_counter, (float*)e->actx));
       return B200ASR_OK;
     }
-    if (ad == kBF16) QKL(launch_pdl(qwen_attn_decode_kernel<bf16, DH>, dim3(rows * H), dim3(kAttDecThreads), dsmem, e->st, e->use_pdl && (rows <= 2 || e->pdl_all), (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (float*)e->actx));
-    else QKL(launch_pdl(qwen_attn_decode_kernel<float, DH>, dim3(rows * H), dim3(kAttDecThreads), dsmem, e->st, e->use_pdl && (rows <= 2 || e->pdl_all), (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (float*)e->kc, (float*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (float*)e->actx));
+    if (ad == kBF16) QKL(launch_pdl(qwen_attn_decode_kernel<bf16, DH>, dim3(rows * H), dim3(kAttDecThreads), dsmem, e->st, e->use_pdl && (rows <= 2 || e->pdl_all), (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (bf16*)e->kc, (bf16*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (const int*)e->kv_off, (float*)e->actx));
+    else QKL(launch_pdl(qwen_attn_decode_kernel<float, DH>, dim3(rows * H), dim3(kAttDecThreads), dsmem, e->st, e->use_pdl && (rows <= 2 || e->pdl_all), (const float*)e->qkvf, g, cosT, sinT, c.rms_eps, (float*)e->kc, (float*)e->vc, layer_off, H, KH, c.max_seq_len, (const DecState*)e->dstate, (const int*)e->kv_off, (float*)e->actx));
     return B200ASR_OK;
   }
   const int total_qk = rows * (H + 2 * KH), total_at = rows * H;
@@ -1316,7 +1328,9 @@ int qwen_decoder(b200asr_qwen* e, int n_new) {
     }
   }
   // final RMS norm with its learned weight on the last row of every utterance, then the vocabulary projection (:1331-1333)
-  qwen_rmsnorm_kernel<float><<<(B + 7) / 8, 256, 0, e->st>>>(e->x, Hd, n_new, n_new - 1, QWF(e, "final_norm.g"), c.rms_eps, e->xl, Hd, B, Hd);
+  //   (prefill of a ragged batch: the shorter clips' last prompt rows sit kv_off[b] rows before the batch's last row)
+  qwen_rmsnorm_kernel<float><<<(B + 7) / 8, 256, 0, e->st>>>(e->x, Hd, n_new, n_new - 1, QWF(e, "final_norm.g"), c.rms_eps, e->xl, Hd, B, Hd,
+                                                             n_new > 1 ? e->kv_off : nullptr);
   QKL(cudaGetLastError());
   const std::string head = e->w.count("lm_head.w") ? "lm_head.w" : "embed.w";
   QRET(qwen_gemv(e, e->xl, Hd, false, false, head, nullptr, 0, e->logits, c.vocab, B, c.vocab, Hd));
@@ -1342,6 +1356,7 @@ int qwen_decoder(b200asr_qwen* e, int n_new) {
   s.temperature = e->samp_temperature; s.top_k = e->samp_top_k; s.top_p = e->samp_top_p; s.rep_penalty = e->samp_rep;
   s.seed = e->samp_seed; s.noise = e->samp_noise; s.noise_ld = e->samp_top_k; s.noise_rows = e->samp_noise_rows;
   s.noise_batch = e->cfg.max_batch;          // noise rows are laid out [launch][max_batch][top_k]
+  s.limit_v = e->d_limit;
   QKL(launch_select_token(s, e->st));
   e->launches++;
   return B200ASR_OK;
@@ -1381,19 +1396,39 @@ int qwen_fetch_logits_token(b200asr_qwen* e, float* logits_out, int32_t* token_o
   return B200ASR_OK;
 }
 
-int qwen_upload(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples) {
+// pinned host staging: [max_batch][max_seq_len] prompt layout | 16 (all-done flag) | [max_batch][max_win] window key counts | 4 x [max_batch]
+int* hp_flag(b200asr_qwen* e) { return e->h_pinned + (size_t)e->cfg.max_batch * e->cfg.max_seq_len; }
+int* hp_win(b200asr_qwen* e) { return hp_flag(e) + 16; }
+int* hp_misc(b200asr_qwen* e, int k) { return hp_win(e) + (size_t)e->cfg.max_batch * e->max_win + (size_t)k * e->cfg.max_batch; }
+int audio_rows(int frames) { return (frames / kChunk) * kChunkTok + aftercnn_len(frames % kChunk); }
+
+// `n_samples` = row stride of `pcm_host` = the longest clip; `lens` (nullable) = samples of each clip, the rest of its row is padding
+int qwen_upload(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples, const int32_t* lens = nullptr) {
   const b200asr_qwen_config& c = e->cfg;
   if (!e->finalized) return e->fail(B200ASR_E_INVALID, "weights not finalized");
   if (!pcm_host) return e->fail(B200ASR_E_INVALID, "null argument");
   if (batch <= 0 || batch > c.max_batch) return e->fail(B200ASR_E_INVALID, "batch out of range");
   if (n_samples < c.n_fft || n_samples > c.max_samples) return e->fail(B200ASR_E_INVALID, "n_samples out of range");
   if (pcm_dtype != B200ASR_PCM_I16 && pcm_dtype != B200ASR_PCM_F32) return e->fail(B200ASR_E_INVALID, "bad pcm dtype");
+  if (lens) {
+    int longest = 0;
+    for (int b = 0; b < batch; ++b) {
+      if (lens[b] < c.n_fft || lens[b] > n_samples) return e->fail(B200ASR_E_INVALID, "clip length out of range (n_fft <= lens[b] <= n_samples)");
+      longest = lens[b] > longest ? lens[b] : longest;
+    }
+    if (longest != n_samples) return e->fail(B200ASR_E_INVALID, "n_samples must equal the longest clip of a ragged batch");
+  }
   e->B = batch; e->n_samples = n_samples; e->pcm_dtype = pcm_dtype;
   e->frames = n_samples / c.hop;
   e->n_chunks = (e->frames + kChunk - 1) / kChunk;
   e->n_win = (e->n_chunks + c.chunks_per_window - 1) / c.chunks_per_window;
-  e->n_audio = (e->frames / kChunk) * kChunkTok + aftercnn_len(e->frames % kChunk);
+  e->n_audio = audio_rows(e->frames);
+  e->clip_ns.assign((size_t)batch, n_samples);
+  if (lens) e->clip_ns.assign(lens, lens + batch);
   e->prefilled = false;
+  int* hn = hp_misc(e, 0);
+  memcpy(hn, e->clip_ns.data(), (size_t)batch * 4);
+  QCK(cudaMemcpyAsync(e->d_ns, hn, (size_t)batch * 4, cudaMemcpyHostToDevice, e->st));
   QCK(cudaMemcpyAsync(e->pcm, pcm_host, (size_t)batch * n_samples * (pcm_dtype == B200ASR_PCM_F32 ? 4 : 2), cudaMemcpyHostToDevice, e->st));
   return B200ASR_OK;
 }
@@ -1403,14 +1438,21 @@ int qwen_encode_resident(b200asr_qwen* e, const int32_t* query_ids, int32_t n_qu
   const b200asr_qwen_config& c = e->cfg;
   if (e->B <= 0) return e->fail(B200ASR_E_INVALID, "no PCM uploaded");
   if (n_query < 0 || n_lang < 0 || (n_query && !query_ids) || (n_lang && !lang_ids)) return e->fail(B200ASR_E_INVALID, "bad prompt ids");
-  std::vector<int> src;
+  // every clip's prompt = head | query | suffix | its own audio rows | tail | language tail; shorter clips are padded at the END with
+  // token 0 up to the longest prompt: causal attention keeps those rows out of every real row, the head reads each clip's own last
+  // row, and the decode steps overwrite their cache rows before reading them (cache position = kv_len + kv_off[b])
+  std::vector<int> src;                                  // the longest clip's layout (range checks below), then every clip's
   auto push_ids = [&](const int* ids, size_t n) { for (size_t i = 0; i < n; ++i) src.push_back(ids[i]); };
-  push_ids(e->head_ids.data(), e->head_ids.size());
-  push_ids(query_ids, (size_t)n_query);
-  push_ids(e->suffix_ids.data(), e->suffix_ids.size());
-  for (int i = 0; i < e->n_audio; ++i) src.push_back(-i - 1);
-  push_ids(e->tail_ids.data(), e->tail_ids.size());
-  push_ids(lang_ids, (size_t)n_lang);
+  auto layout = [&](int n_audio) {
+    src.clear();
+    push_ids(e->head_ids.data(), e->head_ids.size());
+    push_ids(query_ids, (size_t)n_query);
+    push_ids(e->suffix_ids.data(), e->suffix_ids.size());
+    for (int i = 0; i < n_audio; ++i) src.push_back(-i - 1);
+    push_ids(e->tail_ids.data(), e->tail_ids.size());
+    push_ids(lang_ids, (size_t)n_lang);
+  };
+  layout(e->n_audio);
   for (int i = 0; i < n_query; ++i) if (query_ids[i] < 0) return e->fail(B200ASR_E_INVALID, "prompt token id out of range");
   for (int i = 0; i < n_lang; ++i) if (lang_ids[i] < 0) return e->fail(B200ASR_E_INVALID, "prompt token id out of range");
   for (int v : e->head_ids) if (v < 0) return e->fail(B200ASR_E_INVALID, "prompt token id out of range");
@@ -1419,24 +1461,38 @@ int qwen_encode_resident(b200asr_qwen* e, const int32_t* query_ids, int32_t n_qu
   for (int v : src) if (v >= c.vocab) return e->fail(B200ASR_E_INVALID, "prompt token id out of range");
   e->n_prompt = (int)src.size();
   if (e->n_prompt > c.max_seq_len) return e->fail(B200ASR_E_INVALID, "prompt longer than max_seq_len");
-  e->limit = c.max_seq_len - 10 - e->n_prompt;             // Inference_Qwen_ASR_ONNX.py:666
-  if (e->limit < 0) e->limit = 0;
   int* hp = e->h_pinned;
-  memcpy(hp, src.data(), src.size() * 4);
-  int* hv = hp + c.max_seq_len + 16;
-  for (int b = 0; b < e->B; ++b)
+  int* hv = hp_win(e);
+  int *h_off = hp_misc(e, 1), *h_lim = hp_misc(e, 2);
+  const int NP = e->n_prompt;
+  e->clip_prompt.assign((size_t)e->B, NP);
+  e->limit = 0;
+  for (int b = 0; b < e->B; ++b) {
+    const int frames_b = e->clip_ns[b] / c.hop;
+    layout(audio_rows(frames_b));
+    const int np = (int)src.size();
+    e->clip_prompt[b] = np;
+    memcpy(hp + (size_t)b * NP, src.data(), (size_t)np * 4);
+    for (int i = np; i < NP; ++i) hp[(size_t)b * NP + i] = 0;
+    h_off[b] = np - NP;
+    int lim = c.max_seq_len - 10 - np;                       // Inference_Qwen_ASR_ONNX.py:666
+    h_lim[b] = lim < 0 ? 0 : lim;
+    e->limit = h_lim[b] > e->limit ? h_lim[b] : e->limit;    // the loop runs to the largest limit; the selection kernel holds each clip to its own
     for (int w = 0; w < e->n_win; ++w) {
       int n = 0;
       for (int k = 0; k < c.chunks_per_window; ++k) {
         const int ch = w * c.chunks_per_window + k;
-        int len = e->frames - ch * kChunk;
+        int len = frames_b - ch * kChunk;
         len = len < 0 ? 0 : (len > kChunk ? kChunk : len);
         if (ch < e->n_chunks) n += aftercnn_len(len);
       }
       hv[b * e->n_win + w] = n;
     }
-  QCK(cudaMemcpyAsync(e->prompt_src, hp, src.size() * 4, cudaMemcpyHostToDevice, e->st));
+  }
+  QCK(cudaMemcpyAsync(e->prompt_src, hp, (size_t)e->B * NP * 4, cudaMemcpyHostToDevice, e->st));
   QCK(cudaMemcpyAsync(e->win_valid, hv, (size_t)e->B * e->n_win * 4, cudaMemcpyHostToDevice, e->st));
+  QCK(cudaMemcpyAsync(e->kv_off, h_off, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->st));
+  QCK(cudaMemcpyAsync(e->d_limit, h_lim, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->st));
   QRET(qwen_encoder(e));
   const int64_t enc_stride = (int64_t)e->n_win * c.chunks_per_window * kChunkTok * c.out_dim;
   if (e->act == kBF16) qwen_prompt_kernel<bf16><<<dim3(e->n_prompt, e->B), 128, 0, e->st>>>(e->prompt_src, (const bf16*)QW(e, "embed.w"), e->enc_out, enc_stride, e->n_prompt, c.hidden, e->x);
@@ -1455,7 +1511,7 @@ int qwen_decode_loop(b200asr_qwen* e, int max_new) {
   if (e->use_graph) QRET(qwen_ensure_graph(e));
   for (int s = 0; s < steps; ++s) {
     if ((s & 15) == 0) {
-      int* flag = e->h_pinned + e->cfg.max_seq_len;
+      int* flag = hp_flag(e);
       QCK(cudaMemcpyAsync(flag, &e->dstate->all_done, 4, cudaMemcpyDeviceToHost, e->st));
       QCK(cudaStreamSynchronize(e->st));
       if (*flag) break;
@@ -1530,7 +1586,7 @@ void b200asr_qwen_destroy(b200asr_qwen* e) {
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
   void* bufs[] = {e->basis_t, e->fb_start, e->fb_len, e->stage_buf, e->d_stop, e->pcm, e->mel_raw, e->max_key, e->feat, e->c1, e->col, e->c2, e->c3,
-                  e->stem, e->h, e->S, e->enc_out, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->win_valid, e->prompt_src, e->x, e->qkvf, e->q, e->gu,
+                  e->stem, e->h, e->S, e->enc_out, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->win_valid, e->prompt_src, e->d_ns, e->kv_off, e->d_limit, e->x, e->qkvf, e->q, e->gu,
                   e->xl, e->logits, e->cand_val, e->cand_idx, e->att_part, e->att_counter, e->samp_noise, e->xn, e->actx, e->mlp, e->kc, e->vc, e->dstate, e->cur_token, e->tokens, e->n_gen, e->finished, e->save_id, e->n_save};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
@@ -1714,7 +1770,10 @@ int b200asr_qwen_finalize_weights(b200asr_qwen* e) {
     QRET(qwen_alloc(e, &e->S, (size_t)B * e->max_win * c.enc_heads * tpw * tpw * 4));
     QRET(qwen_alloc(e, &e->P, (size_t)B * e->max_win * c.enc_heads * tpw * tpw * es));
     QRET(qwen_alloc(e, &e->win_valid, (size_t)B * e->max_win * 4));
-    QRET(qwen_alloc(e, &e->prompt_src, (size_t)c.max_seq_len * 4));
+    QRET(qwen_alloc(e, &e->prompt_src, (size_t)B * c.max_seq_len * 4));
+    QRET(qwen_alloc(e, &e->d_ns, (size_t)B * 4));
+    QRET(qwen_alloc(e, &e->kv_off, (size_t)B * 4));
+    QRET(qwen_alloc(e, &e->d_limit, (size_t)B * 4));
     QRET(qwen_alloc(e, &e->x, (size_t)rows * Hd * 4));
     QRET(qwen_alloc(e, &e->xn, (size_t)rows * Hd * 4));
     QRET(qwen_alloc(e, &e->qkvf, (size_t)rows * NQ * 4));
@@ -1739,7 +1798,7 @@ int b200asr_qwen_finalize_weights(b200asr_qwen* e) {
     QRET(qwen_alloc(e, &e->save_id, (size_t)B * c.max_seq_len * 4));
     QRET(qwen_alloc(e, &e->n_save, (size_t)B * 4));
     if (!e->d_stop) QCK(cudaMalloc(&e->d_stop, 64 * 4));
-    QCK(cudaMallocHost(&e->h_pinned, ((size_t)c.max_seq_len + 16 + B * e->max_win + 64) * 4));   // prompt layout | flag | window key counts
+    QCK(cudaMallocHost(&e->h_pinned, ((size_t)B * c.max_seq_len + 16 + B * e->max_win + 4 * B + 64) * 4));   // layout: hp_flag / hp_win / hp_misc
     const size_t smem = (size_t)4 * (dh + c.max_seq_len) * sizeof(float);
     if (smem > 48 * 1024) {
       QCK(cudaFuncSetAttribute(qwen_attn_kernel<bf16, float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1837,6 +1896,39 @@ int b200asr_qwen_transcribe_resident(b200asr_qwen* e, const int32_t* query_ids, 
                                      int32_t n_language_tail, int32_t max_new, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
   if (!e) return B200ASR_E_INVALID;
   QCK(cudaSetDevice(e->cfg.device));
+  return qwen_transcribe_resident(e, query_ids, n_query, language_tail_ids, n_language_tail, max_new, tokens_out, tokens_ld, lens_out);
+}
+
+// ---- ragged batches: clips of different lengths in one batch, each with the result it has when it runs alone ----
+int b200asr_qwen_upload_ragged(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples, const int32_t* lens) {
+  if (!e) return B200ASR_E_INVALID;
+  QCK(cudaSetDevice(e->cfg.device));
+  if (!lens) return e->fail(B200ASR_E_INVALID, "null argument");
+  QRET(qwen_upload(e, pcm_host, pcm_dtype, batch, n_samples, lens));
+  QCK(cudaStreamSynchronize(e->st));
+  return B200ASR_OK;
+}
+
+int b200asr_qwen_encode_ragged(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples, const int32_t* lens,
+                               const int32_t* query_ids, int32_t n_query, const int32_t* language_tail_ids, int32_t n_language_tail,
+                               int32_t* n_prompt_out) {
+  if (!e) return B200ASR_E_INVALID;
+  QCK(cudaSetDevice(e->cfg.device));
+  if (!lens) return e->fail(B200ASR_E_INVALID, "null argument");
+  QRET(qwen_upload(e, pcm_host, pcm_dtype, batch, n_samples, lens));
+  QRET(qwen_encode_resident(e, query_ids, n_query, language_tail_ids, n_language_tail));
+  QCK(cudaStreamSynchronize(e->st));
+  if (n_prompt_out) for (int b = 0; b < e->B; ++b) n_prompt_out[b] = e->clip_prompt[b];
+  return B200ASR_OK;
+}
+
+int b200asr_qwen_transcribe_ragged(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples, const int32_t* lens,
+                                   const int32_t* query_ids, int32_t n_query, const int32_t* language_tail_ids, int32_t n_language_tail,
+                                   int32_t max_new, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out) {
+  if (!e) return B200ASR_E_INVALID;
+  QCK(cudaSetDevice(e->cfg.device));
+  if (!lens) return e->fail(B200ASR_E_INVALID, "null argument");
+  QRET(qwen_upload(e, pcm_host, pcm_dtype, batch, n_samples, lens));
   return qwen_transcribe_resident(e, query_ids, n_query, language_tail_ids, n_language_tail, max_new, tokens_out, tokens_ld, lens_out);
 }
 

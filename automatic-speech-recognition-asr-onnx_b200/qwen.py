@@ -315,10 +315,35 @@ class QwenEngine:
             return pcm, _cabi.PCM_F32
         raise TypeError(f"PCM dtype must be int16 or float32, got {pcm.dtype}")
 
-    def encode(self, pcm: np.ndarray, query_ids: Sequence[int] = (), language_tail_ids: Sequence[int] = ()) -> int:
-        """pcm [B][N]: int16, or float32 already in [-1,1] (audio_pcm_scale 32768).  Returns the prompt length."""
+    @staticmethod
+    def pad_ragged(clips: Sequence[np.ndarray]):
+        """Clips of different lengths -> ([B][longest] zero-padded PCM, lens) for the `lens=` arguments below."""
+        clips = [np.asarray(c).reshape(-1) for c in clips]
+        lens = np.array([c.size for c in clips], np.int32)
+        pcm = np.zeros((len(clips), int(lens.max())), clips[0].dtype)
+        for b, c in enumerate(clips):
+            pcm[b, :c.size] = c
+        return pcm, lens
+
+    def _lens(self, pcm: np.ndarray, lens) -> np.ndarray:
+        lens = np.ascontiguousarray(np.asarray(lens, dtype=np.int32).reshape(-1))
+        if lens.size != pcm.shape[0]:
+            raise ValueError(f"lens has {lens.size} entries for a batch of {pcm.shape[0]}")
+        return lens
+
+    def encode(self, pcm: np.ndarray, query_ids: Sequence[int] = (), language_tail_ids: Sequence[int] = (), lens=None):
+        """pcm [B][N]: int16, or float32 already in [-1,1] (audio_pcm_scale 32768).  Returns the prompt length; with `lens`
+        (ragged batch: samples per clip, N = the longest) the list of per-clip prompt lengths."""
         pcm, code = self._pcm(pcm)
         q, l = _i32(query_ids), _i32(language_tail_ids)
+        if lens is not None:
+            lens = self._lens(pcm, lens)
+            npr = np.zeros(pcm.shape[0], np.int32)
+            self._ck(self.lib.b200asr_qwen_encode_ragged(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1],
+                                                         lens.ctypes.data_as(_cabi._I32P), _ptr(q), q.size, _ptr(l), l.size,
+                                                         npr.ctypes.data_as(_cabi._I32P)))
+            self.batch, self.n_prompt = pcm.shape[0], int(npr.max())
+            return npr.tolist()
         n = C.c_int32(0)
         self._ck(self.lib.b200asr_qwen_encode(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1], _ptr(q), q.size,
                                               _ptr(l), l.size, C.byref(n)))
@@ -347,22 +372,36 @@ class QwenEngine:
         return [toks[b, :lens[b]].tolist() for b in range(self.batch)]
 
     def transcribe(self, pcm: np.ndarray, query_ids: Sequence[int] = (), language_tail_ids: Sequence[int] = (), max_new: int = -1,
-                   out_tokens: Optional[np.ndarray] = None, out_lens: Optional[np.ndarray] = None) -> List[List[int]]:
+                   out_tokens: Optional[np.ndarray] = None, out_lens: Optional[np.ndarray] = None, lens=None) -> List[List[int]]:
+        """`lens` (samples per clip, pcm padded to the longest) = a ragged batch: every clip gets the tokens it has alone."""
         pcm, code = self._pcm(pcm)
         q, l = _i32(query_ids), _i32(language_tail_ids)
         B = pcm.shape[0]
         ld = self.dims.max_seq_len
         toks = out_tokens if out_tokens is not None else np.zeros((B, ld), np.int32)
+        clip_lens = None if lens is None else self._lens(pcm, lens)
         lens = out_lens if out_lens is not None else np.zeros(B, np.int32)
+        if clip_lens is not None:
+            self._ck(self.lib.b200asr_qwen_transcribe_ragged(self.h, pcm.ctypes.data_as(C.c_void_p), code, B, pcm.shape[1],
+                                                             clip_lens.ctypes.data_as(_cabi._I32P), _ptr(q), q.size, _ptr(l), l.size,
+                                                             max_new, toks.ctypes.data_as(_cabi._I32P), toks.shape[1],
+                                                             lens.ctypes.data_as(_cabi._I32P)))
+            self.batch = B
+            return [toks[b, :lens[b]].tolist() for b in range(B)]
         self._ck(self.lib.b200asr_qwen_transcribe(self.h, pcm.ctypes.data_as(C.c_void_p), code, B, pcm.shape[1], _ptr(q), q.size, _ptr(l),
                                                   l.size, max_new, toks.ctypes.data_as(_cabi._I32P), toks.shape[1],
                                                   lens.ctypes.data_as(_cabi._I32P)))
         self.batch = B
         return [toks[b, :lens[b]].tolist() for b in range(B)]
 
-    def upload(self, pcm: np.ndarray):
+    def upload(self, pcm: np.ndarray, lens=None):
         pcm, code = self._pcm(pcm)
-        self._ck(self.lib.b200asr_qwen_upload(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1]))
+        if lens is not None:
+            lens = self._lens(pcm, lens)
+            self._ck(self.lib.b200asr_qwen_upload_ragged(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1],
+                                                         lens.ctypes.data_as(_cabi._I32P)))
+        else:
+            self._ck(self.lib.b200asr_qwen_upload(self.h, pcm.ctypes.data_as(C.c_void_p), code, pcm.shape[0], pcm.shape[1]))
         self.batch = pcm.shape[0]
 
     def transcribe_resident(self, query_ids: Sequence[int] = (), language_tail_ids: Sequence[int] = (), max_new: int = -1) -> List[List[int]]:
@@ -417,3 +456,29 @@ def transcribe_clip(engine: QwenEngine, raw_audio_int16: np.ndarray, *, query_id
     wall = time.time() - t0
     audio_s = pcm.shape[1] / float(sample_rate)
     return {"tokens": tokens, "wall_s": wall, "rtf": wall / audio_s if audio_s > 0 else float("inf")}
+
+
+def transcribe_clips(engine: QwenEngine, clips: Sequence[np.ndarray], *, query_ids: Sequence[int] = (),
+                     language_tail_ids: Sequence[int] = (), sample_rate: int = 16000, repeat_penalty: float = REPEAT_PENALTY,
+                     penalty_range: int = PENALTY_RANGE, max_batch: Optional[int] = None):
+    """`transcribe_clip` for a list of clips of any lengths: ragged batches of up to `max_batch` (default: the engine's) clips,
+    neighbours in length together; every clip gets the tokens it gets alone (the script runs one clip per call,
+    Inference_Qwen_ASR_ONNX.py:586-745).  Returns one {"tokens", "wall_s", "rtf"} per clip, in input order; a batch's wall time
+    is shared by its clips in proportion to their audio."""
+    from .sharding import ragged_batches
+    clips = [np.asarray(c, dtype=np.int16).reshape(-1)[:engine.max_samples] for c in clips]
+    nb = max(1, min(int(max_batch or engine.max_batch), engine.max_batch))
+    engine.set_decode_options(repeat_penalty, penalty_range)
+    out: List[Optional[dict]] = [None] * len(clips)
+    for group in ragged_batches(range(len(clips)), [c.size for c in clips], nb):
+        pcm, lens = QwenEngine.pad_ragged([clips[i] for i in group])
+        t0 = time.time()
+        toks = engine.transcribe(pcm, query_ids, language_tail_ids, lens=lens)
+        wall = time.time() - t0
+        total = float(lens.sum())
+        for i, t, n in zip(group, toks, lens):
+            share = wall * float(n) / total
+            audio_s = float(n) / float(sample_rate)
+            out[i] = {"tokens": t, "wall_s": share, "rtf": share / audio_s if audio_s > 0 else float("inf")}
+    return out
+

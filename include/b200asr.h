@@ -282,6 +282,19 @@ int b200asr_qwen_transcribe(b200asr_qwen* e, const void* pcm_host, int32_t pcm_d
 int b200asr_qwen_upload(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples);
 int b200asr_qwen_transcribe_resident(b200asr_qwen* e, const int32_t* query_ids, int32_t n_query, const int32_t* language_tail_ids,
                                      int32_t n_language_tail, int32_t max_new, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
+/* Ragged batches: clips of different lengths in one batch, each with the tokens it gets when it runs alone.  pcm
+ * [batch][n_samples] with n_samples = the longest clip; lens[b] (n_fft <= lens[b] <= n_samples) = samples of clip b, the rest of
+ * its row is ignored.  Per clip: its own reflect padding and log-mel maximum, chunk / window key counts, audio rows, prompt length
+ * (n_prompt_out [batch]), RoPE positions, cache length and generation_limit = max_seq_len - 10 - its prompt length (the reference
+ * runs one clip per call, Inference_Qwen_ASR_ONNX.py:586-745).  After _upload_ragged / _encode_ragged the prefill / decode_step /
+ * decode / transcribe_resident calls above work on the ragged batch; get_stage rows past a clip's own length are padding. */
+int b200asr_qwen_upload_ragged(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples, const int32_t* lens);
+int b200asr_qwen_encode_ragged(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples, const int32_t* lens,
+                               const int32_t* query_ids, int32_t n_query, const int32_t* language_tail_ids, int32_t n_language_tail,
+                               int32_t* n_prompt_out);
+int b200asr_qwen_transcribe_ragged(b200asr_qwen* e, const void* pcm_host, int32_t pcm_dtype, int32_t batch, int32_t n_samples, const int32_t* lens,
+                                   const int32_t* query_ids, int32_t n_query, const int32_t* language_tail_ids, int32_t n_language_tail,
+                                   int32_t max_new, int32_t* tokens_out, int32_t tokens_ld, int32_t* lens_out);
 /* "features" [B][frames][n_mels], "audio_hidden" [B][n_audio][out_dim], "prompt_embed" [B][n_prompt][hidden] (before
  * prefill), "logits" [B][vocab] */
 int b200asr_qwen_get_stage(b200asr_qwen* e, const char* name, float* out, int64_t capacity, int64_t* numel_out);

@@ -159,3 +159,43 @@ def test_qwen3_asr_0_6b_logits_match_oracle(qwen_reference, precision, tol):
     assert np.array_equal(got.argmax(-1)[safe], want[:3].argmax(-1)[safe])
     if precision == "f32":
         assert sel == toks
+
+
+def test_qwen3_asr_0_6b_ragged_batch_equals_single_clips_bf16():
+    """Qwen3-ASR-0.6B, bf16: a 30 s, an 8 s and a 13.4 s clip in one ragged batch against each clip alone.  Prefill logits bit for
+    bit (GEMM rows, windows and causal rows are independent of their neighbours); decode steps within 0.05 with the default
+    kernels (the key-split decode attention picks its range width by batch size, like a uniform batch does) and bit for bit,
+    with identical greedy streams, when both run the single-CTA attention kernel."""
+    from b200asr import qwen as qw
+    dims = qw.QWEN3_ASR_0_6B
+    prompt = qw.QwenPrompt(qw.QWEN3_PROMPT.head_ids, qw.QWEN3_PROMPT.suffix_ids, qw.QWEN3_PROMPT.tail_ids, ())
+    tensors = qw.fold_qwen(qw.synth_qwen_checkpoint(dims, 20261), dims)
+    eng = qw.QwenEngine(dims, tensors, prompt, precision="bf16", max_batch=3, max_samples=480000)
+    del tensors
+    clips = [synth_pcm(3, 480000), synth_pcm(4, 128000), synth_pcm(5, 213977)]
+    pcm, lens = qw.QwenEngine.pad_ragged(clips)
+
+    def walk(p, steps, **kw):
+        n = eng.encode(p, **kw)
+        lg, _ = eng.prefill()
+        rows = [lg.copy()]
+        for _ in range(steps):
+            lg, _ = eng.decode_step()
+            rows.append(lg.copy())
+        return n, np.stack(rows, axis=1)
+
+    n_prompt, lb = walk(pcm, 3, lens=lens)
+    alone = [walk(c, 3) for c in clips]
+    assert n_prompt == [a[0] for a in alone] and len(set(n_prompt)) == 3
+    for b in range(3):
+        assert np.array_equal(lb[b, 0], alone[b][1][0, 0]), b
+        d = float(np.abs(lb[b] - alone[b][1][0]).max())
+        print(f"qwen3-asr-0.6b ragged clip {b} (prompt {n_prompt[b]}): decode-step max|dlogit| vs alone = {d:.2e}")
+        assert d <= 0.05
+    eng.set_option("attn_split", 0)
+    _, lb = walk(pcm, 3, lens=lens)
+    for b in range(3):
+        assert np.array_equal(lb[b], walk(clips[b], 3)[1][0]), b
+    got = eng.transcribe(pcm, max_new=24, lens=lens)
+    assert got == [eng.transcribe(c, max_new=24)[0] for c in clips]
+    eng.close()

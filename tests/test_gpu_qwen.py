@@ -319,3 +319,15 @@ def test_qwen_cli_end_to_end_from_hf_folder_tokenizer_and_wav(tmp_path, capsys):
                                 fast.encode("hello world", add_special_tokens=False), tails["English"])
     text = out.split("ASR Result:\n")[1].split("\n\nRTF")[0]
     assert text == fast.decode(want, skip_special_tokens=True)
+    # two files of different lengths in one ragged batch: the same per-file text as one file per call
+    with wave.open(str(tmp_path / "short.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm[:len(pcm) // 3].astype("<i2").tobytes())
+    files = [str(tmp_path / "short.wav"), str(tmp_path / "clip.wav")]
+    texts = {}
+    for nb in (1, 2):
+        rc = cli.main(["qwen", "--model-folder", str(tmp_path), "--audio", *files, "--precision", "f32", "--language", "English",
+                       "--prompt", "hello world", "--set", "REPEAT_PENALTY=1.0", "--batch", str(nb)])
+        out = capsys.readouterr().out
+        assert rc == 0
+        texts[nb] = [blk.split("\n\nRTF")[0] for blk in out.split("ASR Result:\n")[1:]]
+    assert len(texts[1]) == 2 and texts[1] == texts[2] and texts[2][1] == text

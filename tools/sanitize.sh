@@ -10,6 +10,7 @@ compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test
 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_qwen.py -m gpu -q -x -k "split_attention or tiled_prefill" 2>&1 | tail -6
 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_paraformer.py -m gpu -q -x -k "batched_decoder and f32" 2>&1 | tail -6
 # round 2: ragged batches (per-clip lengths read on the device), the FP8 instantiation of the streaming decode kernel, long-sequence attention
+timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_qwen_ragged.py -m gpu -q -x -k "generation_limit or (equals_single and bf16) or graph" 2>&1 | tail -6
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ragged.py tests/test_gpu_nar_ragged.py -m gpu -q -x -k "f32 or bf16" 2>&1 | tail -6
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_fp8.py -m gpu -q -x -k "case0 or batch" 2>&1 | tail -6
 # racecheck is not usable on decoder_stream_kernel: the only hazards it reports are the intentional volatile hand-off of the step
