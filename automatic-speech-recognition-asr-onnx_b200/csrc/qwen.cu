@@ -920,6 +920,8 @@ qwen_gemv_kernel(QGemvArgs a) {
   }
 }
 
+#include "qwen_persist.cuh"
+
 // ---- first stage of the vocabulary arg-max: one CTA per (slice, utterance) keeps its slice's best (value, lowest id) ----
 constexpr int kArgSlices = 128;
 __global__ void __launch_bounds__(256)
@@ -1044,6 +1046,12 @@ struct b200asr_qwen {
   bool pdl_all = false;
   float* att_part = nullptr; int* att_counter = nullptr;
   int* h_pinned = nullptr;
+  // persistent decode-layer kernel (qwen_persist.cuh): layer table, barrier counter and its host-side running total
+  QPersistLayer* p_layers = nullptr; unsigned* p_bar = nullptr; unsigned p_bar_count = 0;
+  bool use_persist = false;                        // off by default: measured slower than the PDL graph
+  int persist_grid = 0, persist_per_sm = 2, persist_dbg = 0;
+  unsigned long long* p_timing = nullptr;          // 512 stamps of the last persistent launch ("persist_timing" option)
+  //   persist_grid: 0 = not probed yet, -1 = unsupported here, else CTAs of the cooperative launch
 
   int fail(int code, const std::string& m) { err = m; return code; }
   int cuda_fail(cudaError_t e, const char* what) { err = std::string(what) + ": " + cudaGetErrorString(e); return B200ASR_E_CUDA; }
@@ -1289,13 +1297,71 @@ int qwen_gemv(b200asr_qwen* e, const float* x, int64_t ldx, bool rms, bool swigl
   return B200ASR_OK;
 }
 
+// ---- the decoder layers of one decode step as one cooperative launch (bf16, <= 4 clips, known reduction-length classes) ----
+struct QPersistPlan { const void* fn; size_t smem; };
+template <int DH, int KSH, int KSQ, int KSI>
+QPersistPlan qwen_persist_plan_t(size_t smem) { return {(const void*)qwen_persist_kernel<DH, KSH, KSQ, KSI>, smem}; }
+
+QPersistPlan qwen_persist_plan(const b200asr_qwen_config& c) {
+  const int Hd = c.hidden, QD = c.heads * c.head_dim, I = c.inter;
+  const int cap = 8 * 256 * kGemvCH;
+  if (Hd % 8 || QD % 8 || I % 8 || Hd > cap || QD > cap || I > cap) return {nullptr, 0};
+  if ((c.max_seq_len + kPersistSK - 1) / kPersistSK > (c.max_seq_len + kSplitKeys - 1) / kSplitKeys) return {nullptr, 0};      // att_part capacity
+  const int mk = Hd > QD ? (Hd > I ? Hd : I) : (QD > I ? QD : I);
+  const size_t smem = (size_t)kGemvRows * mk * sizeof(float);
+  const int ksh = qp_ks_for(Hd), ksq = qp_ks_for(QD), ksi = qp_ks_for(I);
+  if (c.head_dim == 128 && ksh == 1 && ksq == 2 && ksi == 4) return qwen_persist_plan_t<128, 1, 2, 4>(smem);      // Qwen3-ASR-0.6B
+  if (c.head_dim == 128 && ksh == 2 && ksq == 2 && ksi == 8) return qwen_persist_plan_t<128, 2, 2, 8>(smem);      // Qwen3-ASR-1.7B
+  if (c.head_dim == 64 && ksh == 1 && ksq == 1 && ksi == 1) return qwen_persist_plan_t<64, 1, 1, 1>(smem);        // test dims
+  return {nullptr, 0};
+}
+
+// once, at finalize: can 2 CTAs per SM of the kernel for these dims be co-resident?  persist_grid = CTAs, or -1
+void qwen_persist_probe(b200asr_qwen* e) {
+  e->persist_grid = -1;
+  if (e->act != kBF16) return;
+  const QPersistPlan pl = qwen_persist_plan(e->cfg);
+  if (!pl.fn) return;
+  int per_sm = 0, coop = 0;
+  // (always: the 48 KB default covers static + dynamic shared memory together)
+  if (cudaFuncSetAttribute(pl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) { cudaGetLastError(); return; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pl.fn, kPersistThreads, pl.smem) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->cfg.device);
+  if (per_sm >= 2 && coop) e->persist_grid = 2 * e->num_sms;
+}
+bool qwen_persist_active(const b200asr_qwen* e, int rows) {
+  return e->use_persist && e->persist_grid > 0 && e->p_layers && rows <= kGemvRows && e->samp_temperature <= 0.f ? true : false;
+}
+
+int qwen_persist_layers(b200asr_qwen* e, int rows) {
+  const b200asr_qwen_config& c = e->cfg;
+  const QPersistPlan pl = qwen_persist_plan(c);
+  QPersistArgs a{};
+  a.layers = e->p_layers; a.n_layers = c.dec_layers;
+  a.x = e->x; a.qkvf = e->qkvf; a.actx = (float*)e->actx; a.gu = e->gu;
+  a.rows = rows; a.hidden = c.hidden; a.heads = c.heads; a.kv_heads = c.kv_heads; a.inter = c.inter; a.max_seq = c.max_seq_len; a.eps = c.rms_eps;
+  a.cosT = QWF(e, "rope_cos"); a.sinT = QWF(e, "rope_sin");
+  a.kc = (bf16*)e->kc; a.vc = (bf16*)e->vc; a.cache_layer_stride = (long long)c.max_batch * c.kv_heads * c.max_seq_len * c.head_dim;
+  a.state = e->dstate; a.kv_off = e->kv_off; a.att_part = e->att_part; a.att_counter = e->att_counter;
+  a.S = (c.max_seq_len + kPersistSK - 1) / kPersistSK;
+  a.bar = e->p_bar; a.bar_base = e->p_bar_count; a.dbg = e->persist_dbg;
+  a.timing = e->p_timing; a.timing_cap = 512;
+  const int grid = e->persist_per_sm == 1 ? e->persist_grid / 2 : e->persist_grid;
+  void* params[] = {(void*)&a};
+  QKL(cudaLaunchCooperativeKernel(pl.fn, dim3(grid), dim3(kPersistThreads), params, pl.smem, e->st));
+  e->p_bar_count += 5u * (unsigned)c.dec_layers * (unsigned)grid;      // arrivals of this launch (unsigned wrap is fine: signed compare)
+  return B200ASR_OK;
+}
+
 // ---- decoder over `n_new` new positions per utterance (x rows = [B][n_new][hidden], fp32), then head + selection ----
 int qwen_decoder(b200asr_qwen* e, int n_new) {
   const b200asr_qwen_config& c = e->cfg;
   const int B = e->B, Hd = c.hidden, H = c.heads, KH = c.kv_heads, dh = c.head_dim, I = c.inter, ad = e->act;
   const int rows = B * n_new, NQ = (H + 2 * KH) * dh;
   const bool gemv = n_new == 1;
-  for (int i = 0; i < c.dec_layers; ++i) {
+  const bool persist = gemv && qwen_persist_active(e, rows);
+  if (persist) QRET(qwen_persist_layers(e, rows));
+  for (int i = 0; i < c.dec_layers && !persist; ++i) {
     const std::string p = "dec" + std::to_string(i) + ".";
     if (gemv) {
       QRET(qwen_gemv(e, e->x, Hd, true, false, p + "qkv.w", nullptr, 0, e->qkvf, NQ, rows, NQ, Hd));
@@ -1508,7 +1574,8 @@ int qwen_decode_loop(b200asr_qwen* e, int max_new) {
   // the prefill already selected (and possibly accepted) the first token; every replay adds at most one more
   int steps = e->limit - 1;
   if (max_new >= 0 && max_new - 1 < steps) steps = max_new - 1;
-  if (e->use_graph) QRET(qwen_ensure_graph(e));
+  const bool graph = e->use_graph && !qwen_persist_active(e, e->B);      // (a cooperative launch carries a per-launch barrier base: not replayed)
+  if (graph) QRET(qwen_ensure_graph(e));
   for (int s = 0; s < steps; ++s) {
     if ((s & 15) == 0) {
       int* flag = hp_flag(e);
@@ -1516,7 +1583,7 @@ int qwen_decode_loop(b200asr_qwen* e, int max_new) {
       QCK(cudaStreamSynchronize(e->st));
       if (*flag) break;
     }
-    if (e->use_graph) { QCK(cudaGraphLaunch(e->step_graph, e->st)); e->launches += e->graph_nodes; }
+    if (graph) { QCK(cudaGraphLaunch(e->step_graph, e->st)); e->launches += e->graph_nodes; }
     else QRET(qwen_step(e, e->cur_token));
   }
   return B200ASR_OK;
@@ -1587,7 +1654,7 @@ void b200asr_qwen_destroy(b200asr_qwen* e) {
   for (auto& kv : e->w) cudaFree(kv.second.ptr);
   void* bufs[] = {e->basis_t, e->fb_start, e->fb_len, e->stage_buf, e->d_stop, e->pcm, e->mel_raw, e->max_key, e->feat, e->c1, e->col, e->c2, e->c3,
                   e->stem, e->h, e->S, e->enc_out, e->xhat, e->qkv, e->ctx, e->ffn, e->P, e->win_valid, e->prompt_src, e->d_ns, e->kv_off, e->d_limit, e->x, e->qkvf, e->q, e->gu,
-                  e->xl, e->logits, e->cand_val, e->cand_idx, e->att_part, e->att_counter, e->samp_noise, e->xn, e->actx, e->mlp, e->kc, e->vc, e->dstate, e->cur_token, e->tokens, e->n_gen, e->finished, e->save_id, e->n_save};
+                  e->xl, e->logits, e->cand_val, e->cand_idx, e->att_part, e->att_counter, e->p_layers, e->p_bar, e->p_timing, e->samp_noise, e->xn, e->actx, e->mlp, e->kc, e->vc, e->dstate, e->cur_token, e->tokens, e->n_gen, e->finished, e->save_id, e->n_save};
   for (void* p : bufs) if (p) cudaFree(p);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   cudaStreamDestroy(e->st);
@@ -1809,6 +1876,20 @@ int b200asr_qwen_finalize_weights(b200asr_qwen* e) {
       QCK(cudaFuncSetAttribute(qwen_attn_kernel<float, float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
   }
+  if (e->act == kBF16) {               // (rebuilt at every finalize: set_tensor replaces device buffers)
+    std::vector<QPersistLayer> tab((size_t)c.dec_layers);
+    for (int i = 0; i < c.dec_layers; ++i) {
+      const std::string p = "dec" + std::to_string(i) + ".";
+      tab[i].qkv_w = (const bf16*)QW(e, p + "qkv.w"); tab[i].o_w = (const bf16*)QW(e, p + "o.w");
+      tab[i].gu_w = (const bf16*)QW(e, p + "gate_up.w"); tab[i].down_w = (const bf16*)QW(e, p + "down.w");
+      tab[i].qk_g = QWF(e, p + "qk_norm.g");
+    }
+    QCK(cudaStreamSynchronize(e->st));
+    if (!e->p_layers) QCK(cudaMalloc(&e->p_layers, tab.size() * sizeof(QPersistLayer)));
+    QCK(cudaMemcpy(e->p_layers, tab.data(), tab.size() * sizeof(QPersistLayer), cudaMemcpyHostToDevice));
+    if (!e->p_bar) { QRET(qwen_alloc(e, &e->p_bar, 16)); e->p_bar_count = 0; }
+    if (e->persist_grid == 0) qwen_persist_probe(e);
+  }
   QCK(cudaStreamSynchronize(e->st));
   e->finalized = true;
   return B200ASR_OK;
@@ -1847,7 +1928,7 @@ int b200asr_qwen_decode_step(b200asr_qwen* e, const int32_t* token_in, float* lo
   if (token_in) {
     QCK(cudaMemcpyAsync(e->cur_token, token_in, (size_t)e->B * 4, cudaMemcpyHostToDevice, e->st));
     QRET(qwen_step(e, e->cur_token));
-  } else if (e->use_graph) {
+  } else if (e->use_graph && !qwen_persist_active(e, e->B)) {
     QRET(qwen_ensure_graph(e));
     QCK(cudaGraphLaunch(e->step_graph, e->st));
     e->launches += e->graph_nodes;
@@ -1955,6 +2036,12 @@ int b200asr_qwen_get_stage(b200asr_qwen* e, const char* name_c, float* out, int6
     if (numel_out) *numel_out = n;
     return B200ASR_OK;
   }
+  if (name == "persist_timing") {      // 512 x u64 nanosecond stamps as 1024 floats' worth of raw bytes
+    if (!e->p_timing || capacity < 1024) return e->fail(B200ASR_E_INVALID, "persist_timing is off or the buffer is too small");
+    QCK(cudaMemcpy(out, e->p_timing, 512 * 8, cudaMemcpyDeviceToHost));
+    if (numel_out) *numel_out = 1024;
+    return B200ASR_OK;
+  }
   const void* src = nullptr; int64_t n = 0;
   if (name == "logits") { src = e->logits; n = B * c.vocab; }
   else if (name == "prompt_embed" && !e->prefilled) { src = e->x; n = B * e->n_prompt * c.hidden; }
@@ -1970,6 +2057,13 @@ int b200asr_qwen_set_option(b200asr_qwen* e, const char* key, int64_t value) {
   if (!e || !key) return B200ASR_E_INVALID;
   if (!strcmp(key, "graph")) { e->use_graph = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "attn_tc")) { e->use_attn_tc = value != 0; return B200ASR_OK; }
+  if (!strcmp(key, "persist")) { e->use_persist = value != 0; e->persist_per_sm = value == 2 ? 1 : 2; return B200ASR_OK; }   // 2: one CTA per SM
+  if (!strcmp(key, "persist_timing")) {
+    if (value && !e->p_timing) QCK(cudaMalloc(&e->p_timing, 512 * 8));
+    if (!value && e->p_timing) { cudaStreamSynchronize(e->st); cudaFree(e->p_timing); e->p_timing = nullptr; }
+    return B200ASR_OK;
+  }
+  if (!strcmp(key, "persist_dbg")) { e->persist_dbg = (int)value; return B200ASR_OK; }                                      // timing experiments
   if (!strcmp(key, "attn_tiled")) { e->use_attn_tiled = value != 0; return B200ASR_OK; }
   if (!strcmp(key, "pdl")) {
     e->use_pdl = value != 0; e->pdl_all = value == 2;

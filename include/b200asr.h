@@ -301,7 +301,10 @@ int b200asr_qwen_get_stage(b200asr_qwen* e, const char* name, float* out, int64_
 int64_t b200asr_qwen_kernel_launches(const b200asr_qwen* e);
 /* options: "graph" (0/1, default 1): replay a decode step as one CUDA graph; "attn_tc" (0/1): fused tcgen05 encoder attention;
  * "attn_split" (0/1, default 1, bf16 cache): key-split decode attention with register-resident cache rows;
- * "pdl" (0/1, default 1): launch decode-step kernels as programmatic dependents (batches of 1-2 clips) */
+ * "pdl" (0/1, default 1): launch decode-step kernels as programmatic dependents (batches of 1-2 clips);
+ * "persist" (0/1, default 0; bf16, <= 4 clips, arg-max heads): the 5 x n_layers decoder-layer launches of a decode step as one
+ * cooperative kernel with grid barriers (csrc/qwen_persist.cuh) -- same tokens, measured slower than the default on B200;
+ * "persist_timing" (0/1): block 0 stamps %globaltimer at every phase of that kernel, read back with get_stage("persist_timing") */
 int b200asr_qwen_set_option(b200asr_qwen* e, const char* key, int64_t value);
 void* b200asr_qwen_stream(b200asr_qwen* e);
 
